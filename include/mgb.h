@@ -1,0 +1,163 @@
+/*
+ * mgb.h -- C ABI of libmarsgb.so: the B200-native (sm_100a) groupby-aggregation hot path of Mars.
+ *
+ * This is the drop-in boundary.  The reference has no native code on this path:
+ * its operands' `execute(ctx, op)` classmethods call pandas.  Every entry point below names the reference
+ * call site (paths relative to the reference checkout) whose arithmetic it replaces.  The Python executors
+ * in mars_b200/executors.py bind these symbols with ctypes and are registered through the reference's own
+ * plug-in seam `Operand.register_executor` (mars/core/operand/core.py:458-464).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; device pointers unless a name ends in `_host`.
+ *   - every column is a dense array of 8-byte elements (int64 keys; float64 or int64 values).
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
+ *   - every function returns an mgb_status; nothing calls exit()/abort(); mgb_last_error() returns a
+ *     thread-local message for the last non-OK status (reference error contract: raise -> ExecutionError,
+ *     mars/services/subtask/worker/processor.py:210-214).
+ *   - the caller owns all input/output buffers (torch allocator); scratch memory is taken from the CUDA
+ *     stream-ordered pool (cudaMallocAsync) on the given stream.
+ */
+#ifndef MGB_H_
+#define MGB_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MGB_VERSION 100
+
+typedef enum {
+  MGB_OK = 0,
+  MGB_ERR_INVALID = 1,     /* bad argument */
+  MGB_ERR_CUDA = 2,        /* CUDA runtime error (message has cudaGetErrorString) */
+  MGB_ERR_UNSUPPORTED = 3, /* valid request outside the implemented envelope */
+  MGB_ERR_NCCL = 4,
+  MGB_ERR_OVERFLOW = 5,    /* an internal capacity bound was exceeded (bug or corrupted input) */
+  MGB_ERR_STATE = 6        /* call order violated (e.g. emit before finalize) */
+} mgb_status;
+
+typedef enum { MGB_F64 = 0, MGB_I64 = 1 } mgb_dtype;
+
+/* Atomic reductions of the groupby map/combine/agg stages.  The reference decomposes user functions into
+ * these steps in ReductionCompiler (mars/dataframe/reduction/core.py:976-1031):
+ *   sum -> map sum / agg sum;  count -> map count / agg SUM (of int64 counts);  min, max -> same;
+ *   mean = sum/count;  var = sum, sum(x**2), count.
+ * NaN handling follows pandas skipna=True: NaN values are skipped by SUM/SUMSQ/MIN/MAX and not counted by
+ * COUNT; an all-NaN group yields sum 0.0, count 0, min/max NaN.                                          */
+typedef enum { MGB_SUM = 0, MGB_SUMSQ = 1, MGB_COUNT = 2, MGB_MIN = 3, MGB_MAX = 4 } mgb_op;
+
+#define MGB_MAX_KEYS 2
+#define MGB_MAX_VALS 64
+#define MGB_MAX_ACCS 64
+
+typedef struct {
+  int32_t n_keys;                  /* 1..MGB_MAX_KEYS int64 key columns                               */
+  int32_t n_vals;                  /* 0..MGB_MAX_VALS value columns                                   */
+  int32_t n_accs;                  /* 1..MGB_MAX_ACCS accumulators                                    */
+  int32_t val_dtype[MGB_MAX_VALS]; /* mgb_dtype of each value column                                  */
+  int32_t acc_col[MGB_MAX_ACCS];   /* value column each accumulator reads                             */
+  int32_t acc_op[MGB_MAX_ACCS];    /* mgb_op; output dtype: COUNT -> I64, otherwise the column dtype  */
+} mgb_agg_spec;
+
+const char* mgb_last_error(void);
+int mgb_version(void);
+/* Device sanity probe: returns MGB_OK and fills sm_count / cc (major*10+minor) of the current device. */
+int mgb_device_info(int32_t* sm_count, int32_t* cc);
+
+/* ---- a5: partition assignment --------------------------------------------------------------------
+ * Replaces `pd.util.hash_pandas_object(idx, categorize=False) % size` in hash_dataframe_on
+ * (mars/dataframe/utils.py:77-101) as used by DataFrameGroupByOperand.execute_map
+ * (mars/dataframe/groupby/core.py:353-435).  Bit-exact: one int64 key -> pandas `_hash_ndarray`
+ * (splitmix64 finaliser on the uint64 view); several keys -> `hash_tuples`/`combine_hash_arrays`.      */
+int mgb_hash_keys(const int64_t* const* key_cols, int32_t n_keys, int64_t n_rows, uint64_t* out_hash,
+                  void* stream);
+int mgb_partition_ids(const int64_t* const* key_cols, int32_t n_keys, int64_t n_rows, int64_t n_partitions,
+                      int32_t* out_pid, void* stream);
+
+/* ---- a5/a6: split partial rows into per-reducer blocks --------------------------------------------
+ * Replaces `RangeIndex.groupby(hash % size)` + the K `iloc[f_i]` takes (groupby/core.py:389-435).
+ * Stable: inside every partition rows keep their input order (== ascending positions f_i).
+ * out_cols[c][out_offsets[p] .. out_offsets[p+1]) holds partition p of column c; out_offsets has
+ * n_partitions+1 int64 entries on the device.  1 <= n_partitions <= 65536.                              */
+int mgb_partition_scatter(const int32_t* pid, int64_t n_rows, int32_t n_partitions,
+                          const void* const* in_cols, void* const* out_cols, int32_t n_cols,
+                          int64_t* out_offsets, void* stream);
+
+/* ---- a4/a9/a10: hash aggregation -------------------------------------------------------------------
+ * Replaces `df.groupby(keys).agg(...)` of DataFrameGroupByAgg._execute_map / _execute_combine /
+ * _execute_agg (mars/dataframe/groupby/aggregation.py:1043-1267, pandas group_sum/min/max/count).
+ * One aggregator consumes any number of row batches (chunks) and yields one row per distinct key tuple.
+ *   create -> update* -> finalize -> emit -> destroy
+ * update() is asynchronous on `stream`; the batch's column buffers must stay alive until finalize()
+ * returns.  finalize() synchronises the stream once and reports the group count so the caller can
+ * allocate the output columns.  emit() writes key columns (int64) and accumulator columns (8-byte, dtype
+ * per spec) in table order; with sort_keys != 0 rows are ordered by the key tuple ascending
+ * (groupby(sort=True)).                                                                                 */
+typedef struct mgb_agg mgb_agg;
+int mgb_agg_create(mgb_agg** out, const mgb_agg_spec* spec, void* stream);
+int mgb_agg_update(mgb_agg* agg, const int64_t* const* key_cols, const void* const* val_cols,
+                   int64_t n_rows);
+int mgb_agg_finalize(mgb_agg* agg, int64_t* out_n_groups);
+int mgb_agg_emit(mgb_agg* agg, int64_t* const* out_key_cols, void* const* out_acc_cols, int32_t sort_keys);
+int mgb_agg_destroy(mgb_agg* agg);
+/* Diagnostics of the last finalize (which pre-aggregation path consumed the rows):
+ * stats[0]=rows pre-aggregated by the privatised tiny-cardinality kernel, [1]=rows pre-aggregated by the
+ * shared-memory hash table kernel, [2]=rows spilled to the global table, [3]=partial rows merged,
+ * [4]=global table capacity, [5]=kernels launched by this aggregator so far.                            */
+int mgb_agg_stats(mgb_agg* agg, int64_t* stats6);
+
+/* Host-buffer convenience used by the end-to-end path: key/value columns live in (pinned) host memory,
+ * are streamed to the device in row blocks overlapped with the kernels, and the result is written to
+ * host arrays with capacity max_groups.  Returns the number of groups through out_n_groups
+ * (MGB_ERR_OVERFLOW if it exceeds max_groups).                                                           */
+int mgb_groupby_agg_host(const mgb_agg_spec* spec, const int64_t* const* key_cols_host,
+                         const void* const* val_cols_host, int64_t n_rows, int64_t block_rows,
+                         int64_t* const* out_key_cols_host, void* const* out_acc_cols_host,
+                         int64_t max_groups, int32_t sort_keys, int64_t* out_n_groups, void* stream);
+
+/* ---- a10: post functions -----------------------------------------------------------------------------
+ * The generated post_funcs of the reference, evaluated in float64 in the reference's operation order
+ * (mars/dataframe/reduction/mean.py:26-33, var.py:38-48):
+ *   mean = S / C;   var(ddof!=0) = (Q - S*S/C) / (C - ddof);   var(ddof==0) = Q/C - (S/C)*(S/C)
+ * sum_dtype tells whether S (and Q) are float64 or int64 columns; C is int64.                           */
+int mgb_post_mean(const void* sum, int32_t sum_dtype, const int64_t* count, double* out, int64_t n,
+                  void* stream);
+int mgb_post_var(const void* sum, const void* sumsq, int32_t sum_dtype, const int64_t* count, int32_t ddof,
+                 double* out, int64_t n, void* stream);
+
+/* ---- a7/a8: row-wise concatenation of partial columns (pd.concat(axis=0), groupby/core.py:457,
+ * merge/concat.py:339-348): copies n_rows 8-byte elements of src into dst starting at dst_offset.      */
+int mgb_copy_rows(void* dst, int64_t dst_offset, const void* src, int64_t n_rows, void* stream);
+
+/* ---- sort=True support: argsort of int64 key tuples (lexicographic, stable) and row gather ---------- */
+int mgb_argsort_keys(const int64_t* const* key_cols, int32_t n_keys, int64_t n_rows, int32_t* out_perm,
+                     void* stream);
+int mgb_gather_rows(const void* const* in_cols, void* const* out_cols, int32_t n_cols, const int32_t* perm,
+                    int64_t n_rows, void* stream);
+
+/* ---- a6/e: multi-GPU exchange (grouped ncclSend/ncclRecv all-to-all over NVLink) ---------------------
+ * Replaces the storage-service shuffle transport (mars/services/subtask/worker/processor.py:396-432,
+ * mars/services/storage/transfer.py:63-206).  libnccl is dlopen()ed from `path` (NULL: default search). */
+typedef struct mgb_comm mgb_comm;
+int mgb_nccl_load(const char* libnccl_path);
+int mgb_comm_unique_id(uint8_t out_id[128]);
+int mgb_comm_init(mgb_comm** out, const uint8_t id[128], int32_t rank, int32_t n_ranks);
+/* For each of n_cols 8-byte columns: rank r sends send_cols[c][send_offsets[p] .. send_offsets[p+1]) to
+ * peer p and receives recv_offsets[p+1]-recv_offsets[p] elements from peer p at recv_cols[c]+recv_offsets[p].
+ * Offsets are host arrays of n_ranks+1 int64.  One ncclGroupStart/End for all columns and peers.        */
+int mgb_comm_alltoallv(mgb_comm* comm, const void* const* send_cols, const int64_t* send_offsets_host,
+                       void* const* recv_cols, const int64_t* recv_offsets_host, int32_t n_cols,
+                       void* stream);
+int mgb_comm_allgather_i64(mgb_comm* comm, const int64_t* send, int64_t* recv, int64_t count, void* stream);
+int mgb_comm_destroy(mgb_comm* comm);
+
+/* ---- microbenchmarks used by profiles/ (not part of the operand path) -------------------------------- */
+int mgb_bench_atomics(int32_t mode, int64_t n_rows, int32_t n_slots, int32_t iters, float* out_ms,
+                      void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MGB_H_ */

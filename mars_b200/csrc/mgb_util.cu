@@ -1,0 +1,280 @@
+// libmarsgb: error plumbing, prefix scan, pandas-exact key hashing, post functions, row copies.
+#include <stdarg.h>
+
+#include "mgb_common.cuh"
+
+// ----------------------------------------------------------------------------------------------------
+// errors
+// ----------------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+
+void mgb_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char* mgb_last_error(void) { return g_err; }
+extern "C" int mgb_version(void) { return MGB_VERSION; }
+
+int mgb_sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+extern "C" int mgb_device_info(int32_t* sm_count, int32_t* cc) {
+  int dev = 0, maj = 0, min = 0, sms = 0;
+  MGB_CUDA(cudaGetDevice(&dev));
+  MGB_CUDA(cudaDeviceGetAttribute(&maj, cudaDevAttrComputeCapabilityMajor, dev));
+  MGB_CUDA(cudaDeviceGetAttribute(&min, cudaDevAttrComputeCapabilityMinor, dev));
+  MGB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  if (sm_count) *sm_count = sms;
+  if (cc) *cc = maj * 10 + min;
+  return MGB_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------
+// exclusive scan (int64), three-phase: per-block scan of SCAN_TILE elements, scan of block totals by a
+// single block, add-back.  Used by the partition histogram, radix sort and table compaction.
+// ----------------------------------------------------------------------------------------------------
+#define SCAN_THREADS 512
+#define SCAN_ITEMS 8
+#define SCAN_TILE (SCAN_THREADS * SCAN_ITEMS)
+
+__device__ __forceinline__ int64_t block_exclusive_scan(int64_t v, int64_t* total, int64_t* smem_warp) {
+  // v: per-thread value; returns exclusive prefix in thread order, *total = block sum
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int64_t x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int64_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) smem_warp[warp] = x;
+  __syncthreads();
+  if (warp == 0) {
+    int64_t w = lane < (SCAN_THREADS / 32) ? smem_warp[lane] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int64_t y = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += y;
+    }
+    if (lane < (SCAN_THREADS / 32)) smem_warp[lane] = w;  // inclusive over warps
+  }
+  __syncthreads();
+  int64_t warp_base = warp == 0 ? 0 : smem_warp[warp - 1];
+  *total = smem_warp[SCAN_THREADS / 32 - 1];
+  __syncthreads();
+  return warp_base + x - v;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(int64_t* data, int64_t n, int64_t* tile_sums) {
+  __shared__ int64_t sw[32];
+  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+  int64_t v[SCAN_ITEMS];
+  int64_t s = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) {
+    v[i] = (base + i < n) ? data[base + i] : 0;
+    s += v[i];
+  }
+  int64_t total;
+  int64_t ex = block_exclusive_scan(s, &total, sw);
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) {
+    if (base + i < n) data[base + i] = ex;
+    ex += v[i];
+  }
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+// single block: exclusive scan of m tile sums (any m), total -> *total_out
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_sums(int64_t* sums, int64_t m, int64_t* total_out) {
+  __shared__ int64_t sw[32];
+  __shared__ int64_t carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int64_t start = 0; start < m; start += SCAN_THREADS) {
+    int64_t i = start + threadIdx.x;
+    int64_t v = i < m ? sums[i] : 0;
+    int64_t total;
+    int64_t ex = block_exclusive_scan(v, &total, sw);
+    int64_t carry = carry_s;
+    if (i < m) sums[i] = carry + ex;
+    __syncthreads();
+    if (threadIdx.x == 0) carry_s = carry + total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && total_out) *total_out = carry_s;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_add(int64_t* data, int64_t n, const int64_t* tile_sums) {
+  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+  const int64_t add = tile_sums[blockIdx.x];
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i)
+    if (base + i < n) data[base + i] += add;
+}
+
+int mgb_scan_exclusive_i64(int64_t* data, int64_t n, int64_t* total_out, cudaStream_t st) {
+  if (n <= 0) {
+    if (total_out) MGB_CUDA(cudaMemsetAsync(total_out, 0, sizeof(int64_t), st));
+    return MGB_OK;
+  }
+  const int64_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+  int64_t* sums = nullptr;
+  MGB_CUDA(cudaMallocAsync((void**)&sums, sizeof(int64_t) * tiles, st));
+  k_scan_tiles<<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(data, n, sums);
+  k_scan_sums<<<1, SCAN_THREADS, 0, st>>>(sums, tiles, total_out);
+  if (tiles > 1) k_scan_add<<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(data, n, sums);
+  cudaError_t e = cudaGetLastError();
+  cudaFreeAsync(sums, st);
+  if (e != cudaSuccess) {
+    mgb_set_error("scan launch failed: %s", cudaGetErrorString(e));
+    return MGB_ERR_CUDA;
+  }
+  return MGB_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------
+// a5: key hashing and partition ids
+// ----------------------------------------------------------------------------------------------------
+struct KeyCols {
+  const int64_t* k[MGB_MAX_KEYS];
+};
+
+template <int NK, bool WANT_PID>
+__global__ void __launch_bounds__(256) k_hash(KeyCols kc, int64_t n, uint64_t R, uint64_t* out_hash,
+                                              int32_t* out_pid) {
+  const bool pow2 = (R & (R - 1)) == 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t k[NK];
+#pragma unroll
+    for (int j = 0; j < NK; ++j) k[j] = (int64_t)mgb_ld_stream((const uint64_t*)kc.k[j] + i);
+    uint64_t h = mgb_hash_tuple<NK>(k);
+    if (WANT_PID)
+      out_pid[i] = (int32_t)(pow2 ? (h & (R - 1)) : (h % R));
+    else
+      out_hash[i] = h;
+  }
+}
+
+static int launch_hash(const int64_t* const* key_cols, int32_t n_keys, int64_t n, uint64_t R,
+                       uint64_t* out_hash, int32_t* out_pid, cudaStream_t st) {
+  MGB_REQUIRE(n_keys >= 1 && n_keys <= MGB_MAX_KEYS, MGB_ERR_UNSUPPORTED,
+              "n_keys=%d outside [1,%d]", n_keys, MGB_MAX_KEYS);
+  MGB_REQUIRE(n >= 0, MGB_ERR_INVALID, "negative row count");
+  if (n == 0) return MGB_OK;
+  KeyCols kc;
+  for (int j = 0; j < MGB_MAX_KEYS; ++j) kc.k[j] = j < n_keys ? key_cols[j] : nullptr;
+  int64_t blocks = (n + 255) / 256;
+  int64_t cap = (int64_t)mgb_sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  const bool pid = out_pid != nullptr;
+#define L(NK)                                                                                   \
+  if (pid)                                                                                      \
+    k_hash<NK, true><<<(unsigned)blocks, 256, 0, st>>>(kc, n, R, out_hash, out_pid);            \
+  else                                                                                          \
+    k_hash<NK, false><<<(unsigned)blocks, 256, 0, st>>>(kc, n, R, out_hash, out_pid);
+  if (n_keys == 1) {
+    L(1)
+  } else {
+    L(2)
+  }
+#undef L
+  MGB_CHECK_LAUNCH();
+  return MGB_OK;
+}
+
+extern "C" int mgb_hash_keys(const int64_t* const* key_cols, int32_t n_keys, int64_t n_rows,
+                             uint64_t* out_hash, void* stream) {
+  MGB_REQUIRE(key_cols && (out_hash || n_rows == 0), MGB_ERR_INVALID, "null pointer");
+  return launch_hash(key_cols, n_keys, n_rows, 1, out_hash, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int mgb_partition_ids(const int64_t* const* key_cols, int32_t n_keys, int64_t n_rows,
+                                 int64_t n_partitions, int32_t* out_pid, void* stream) {
+  MGB_REQUIRE(key_cols && (out_pid || n_rows == 0), MGB_ERR_INVALID, "null pointer");
+  MGB_REQUIRE(n_partitions >= 1 && n_partitions <= 0x7fffffffLL, MGB_ERR_INVALID,
+              "n_partitions=%lld out of range", (long long)n_partitions);
+  return launch_hash(key_cols, n_keys, n_rows, (uint64_t)n_partitions, nullptr, out_pid,
+                     (cudaStream_t)stream);
+}
+
+// ----------------------------------------------------------------------------------------------------
+// a10: post functions.  Operation order follows the reference's generated source exactly.
+// ----------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double as_f64(const void* p, int dt, int64_t i) {
+  return dt == MGB_F64 ? ((const double*)p)[i] : (double)((const int64_t*)p)[i];
+}
+
+__global__ void k_post_mean(const void* sum, int dt, const int64_t* cnt, double* out, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = as_f64(sum, dt, i) / (double)cnt[i];
+}
+
+__global__ void k_post_var(const void* sum, const void* sumsq, int dt, const int64_t* cnt, int ddof,
+                           double* out, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const double s = as_f64(sum, dt, i), q = as_f64(sumsq, dt, i), c = (double)cnt[i];
+    double r;
+    if (ddof == 0) {
+      // (x**2).mean() - (x.mean())**2
+      const double m2 = __ddiv_rn(q, c), m = __ddiv_rn(s, c);
+      r = __dsub_rn(m2, __dmul_rn(m, m));
+    } else {
+      // ((x**2).sum() - x.sum()**2 / cnt) / (cnt - ddof)      (no FMA contraction: *_rn intrinsics)
+      const double t = __ddiv_rn(__dmul_rn(s, s), c);
+      r = __ddiv_rn(__dsub_rn(q, t), __dsub_rn(c, (double)ddof));
+    }
+    out[i] = r;
+  }
+}
+
+static unsigned grid_for(int64_t n) {
+  int64_t b = (n + 255) / 256, cap = (int64_t)mgb_sm_count() * 16;
+  return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+extern "C" int mgb_post_mean(const void* sum, int32_t sum_dtype, const int64_t* count, double* out,
+                             int64_t n, void* stream) {
+  MGB_REQUIRE(n >= 0, MGB_ERR_INVALID, "negative n");
+  if (n == 0) return MGB_OK;
+  MGB_REQUIRE(sum && count && out, MGB_ERR_INVALID, "null pointer");
+  k_post_mean<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(sum, sum_dtype, count, out, n);
+  MGB_CHECK_LAUNCH();
+  return MGB_OK;
+}
+
+extern "C" int mgb_post_var(const void* sum, const void* sumsq, int32_t sum_dtype, const int64_t* count,
+                            int32_t ddof, double* out, int64_t n, void* stream) {
+  MGB_REQUIRE(n >= 0, MGB_ERR_INVALID, "negative n");
+  if (n == 0) return MGB_OK;
+  MGB_REQUIRE(sum && sumsq && count && out, MGB_ERR_INVALID, "null pointer");
+  k_post_var<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(sum, sumsq, sum_dtype, count, ddof, out, n);
+  MGB_CHECK_LAUNCH();
+  return MGB_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------
+// a7/a8: concatenation building block
+// ----------------------------------------------------------------------------------------------------
+extern "C" int mgb_copy_rows(void* dst, int64_t dst_offset, const void* src, int64_t n_rows, void* stream) {
+  MGB_REQUIRE(n_rows >= 0 && dst_offset >= 0, MGB_ERR_INVALID, "negative size");
+  if (n_rows == 0) return MGB_OK;
+  MGB_REQUIRE(dst && src, MGB_ERR_INVALID, "null pointer");
+  MGB_CUDA(cudaMemcpyAsync((char*)dst + dst_offset * 8, src, (size_t)n_rows * 8, cudaMemcpyDeviceToDevice,
+                           (cudaStream_t)stream));
+  return MGB_OK;
+}

@@ -1,0 +1,106 @@
+"""TEST INFRASTRUCTURE ONLY -- drives the *real* reference operands (build container only).
+
+``run_reference(raw, by, func, ...)`` builds ``md.DataFrame(raw, chunk_size).groupby(...).agg(...)`` with
+the unmodified reference imported from ``$MARS_REF_DIR`` (default ``/tmp/mars_ref``, produced by
+``oracle/build_ref.sh``), tiles it with the reference's own ``ChunkGraphBuilder`` and executes every chunk
+operand through the reference's global ``execute(ctx, op)`` (mars/core/operand/core.py:475-512) with a
+``dict`` context -- the same call the worker makes (mars/services/subtask/worker/processor.py:206-214).
+Every intermediate value is recorded so golden fixtures can pin partition assignment and partials.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+REF_DIR = os.environ.get("MARS_REF_DIR", "/tmp/mars_ref")
+
+
+def reference_available() -> bool:
+    return os.path.isdir(os.path.join(REF_DIR, "mars"))
+
+
+def _import_reference():
+    here = os.path.dirname(os.path.abspath(__file__))
+    if here not in sys.path:
+        sys.path.insert(0, here)
+    import ref_shim  # noqa: F401
+
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    import mars  # noqa: F401
+    import mars.dataframe as md
+
+    return md
+
+
+class _Ctx(dict):
+    _current = None
+
+    def set_current_chunk(self, chunk):
+        self._current = chunk
+
+    def get_current_chunk(self):
+        return self._current
+
+    @staticmethod
+    def new_custom_log_dir():
+        return None
+
+
+def run_reference(raw, by, func, chunk_size, method="tree", sort=True, as_index=True,
+                  combine_size=None, selection=None):
+    """Returns dict(result=pd.DataFrame, chunks=[...per-op records...])."""
+    md = _import_reference()
+    from mars.core import TileableGraph, TileableGraphBuilder, ChunkGraphBuilder
+    from mars.core.mode import enter_mode
+    from mars.core.operand import execute, OperandStage
+
+    mdf = md.DataFrame(raw, chunk_size=chunk_size)
+    g = mdf.groupby(by, sort=sort, as_index=as_index)
+    if selection is not None:
+        g = g[selection]
+    kw = {}
+    if combine_size is not None:
+        kw["combine_size"] = combine_size
+    t = g.agg(func, method=method, **kw)
+
+    tg = TileableGraph([t.data])
+    next(TileableGraphBuilder(tg).build())
+    cg = next(ChunkGraphBuilder(tg, fuse_enabled=False).build())
+    ctx = _Ctx()
+    records = []
+    result_chunks = {c.key: c for c in cg.result_chunks}
+    with enter_mode(build=False, kernel=True):
+        for c in cg.topological_iter():
+            ctx.set_current_chunk(c)
+            before = set(ctx.keys())
+            execute(ctx, c.op)
+            new_keys = [k for k in ctx.keys() if k not in before]
+            records.append(
+                dict(
+                    op=type(c.op).__name__,
+                    stage=None if c.op.stage is None else OperandStage(c.op.stage).name,
+                    index=tuple(c.index) if c.index is not None else None,
+                    key=c.key,
+                    new_keys=new_keys,
+                )
+            )
+    outs = sorted(result_chunks.values(), key=lambda c: c.index)
+    import pandas as pd
+
+    result = pd.concat([ctx[c.key] for c in outs], axis=0) if len(outs) > 1 else ctx[outs[0].key]
+    return dict(result=result, records=records, ctx=ctx, chunk_results=[ctx[c.key] for c in outs],
+                tileable=t)
+
+
+if __name__ == "__main__":
+    import numpy as np
+    import pandas as pd
+
+    rng = np.random.default_rng(0)
+    raw = pd.DataFrame({"key": rng.integers(0, 50, 1000), "v0": rng.random(1000), "v1": rng.random(1000)})
+    for method, sort in [("tree", True), ("shuffle", False), ("shuffle", True)]:
+        out = run_reference(raw, "key", ["sum", "mean", "count", "min", "max", "var"], 250, method, sort)
+        exp = raw.groupby("key", sort=True).agg(["sum", "mean", "count", "min", "max", "var"])
+        pd.testing.assert_frame_equal(out["result"].sort_index(), exp, rtol=1e-9)
+        print(method, sort, "OK", [(r["op"], r["stage"]) for r in out["records"]][:12])
