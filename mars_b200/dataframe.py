@@ -1,0 +1,467 @@
+"""User API and operands of the chunked DataFrame groupby-aggregation path (host side, pure Python).
+
+Mirror of the reference's surface for this path -- same operand names, stages, tiling rules and chunk metas:
+
+  md.DataFrame(raw, chunk_size=...)          mars/dataframe/initializer.py, datasource/dataframe.py
+  df.to_gpu()                                mars/dataframe/base/to_gpu.py:19-35
+  df.groupby(by, sort=, as_index=)           mars/dataframe/groupby/core.py:511-534
+  groupby[...].agg(func, method=, combine_size=)   mars/dataframe/groupby/aggregation.py:1287-1354
+  DataFrameGroupByAgg.tile (tree / shuffle / auto) mars/dataframe/groupby/aggregation.py:428-949
+  DataFrameGroupByOperand map/reduce, DataFrameShuffleProxy, DataFrameConcat
+
+Only *graph construction* lives here; nothing in this module computes on data.  The operands have no CPU
+``execute``: the GPU executors of ``mars_b200.executors`` are registered on them through
+``Operand.register_executor`` -- the same seam the real reference offers (see mars_b200.plugin).
+"""
+from __future__ import annotations
+
+import itertools
+from collections import OrderedDict
+from typing import Any, Dict, List, Optional
+
+import numpy as np
+import pandas as pd
+
+from .core import (ChunkData, IndexValue, MapReduceOperand, Operand, OperandStage, ShuffleProxy,
+                   TileableData, new_key)
+from .reduction import ReductionSteps, check_supported, compile_reduction
+
+
+class _Options:
+    """reference: mars/config.py:363-371"""
+    combine_size = 4
+    chunk_store_limit = 128 * 1024 ** 2
+    chunk_size = None
+
+
+options = _Options()
+
+
+# ----------------------------------------------------------------------------------------------------
+# operands
+# ----------------------------------------------------------------------------------------------------
+class DataFrameDataSource(Operand):
+    """Holds one row-slice of the user's pandas frame (host memory)."""
+
+
+class DataFrameToGPU(Operand):
+    """Host -> device copy of a chunk (reference: DataFrameToGPU.execute, to_gpu.py:28-35)."""
+
+
+class DataFrameToCPU(Operand):
+    """Device -> host copy of a chunk (reference: dataframe/base/to_cpu.py)."""
+
+
+class DataFrameShuffleProxy(ShuffleProxy):
+    """reference: mars/dataframe/operands.py:461-467"""
+
+
+class DataFrameConcat(Operand):
+    """Row-wise concatenation; on this path only the tuple-of-partials branch (merge/concat.py:339-348)."""
+
+
+class DataFrameGroupByOperand(MapReduceOperand):
+    """groupby operand; stage map/reduce implement the hash shuffle (groupby/core.py:353-485).
+
+    fields: by, level, as_index, sort, group_keys, shuffle_size"""
+
+    def __init__(self, by=None, level=None, as_index=True, sort=True, group_keys=None, shuffle_size=None, **kw):
+        super().__init__(by=by, level=level, as_index=as_index, sort=sort, group_keys=group_keys,
+                         shuffle_size=shuffle_size, **kw)
+
+    @property
+    def is_dataframe_obj(self):
+        return True
+
+    @property
+    def groupby_params(self):
+        return dict(by=self.by, level=self.level, as_index=self.as_index, sort=self.sort,
+                    group_keys=self.group_keys)
+
+
+class DataFrameGroupByAgg(Operand):
+    """groupby aggregation operand with stages map / combine / agg (aggregation.py:164-1284)."""
+
+    def __init__(self, raw_func=None, raw_func_kw=None, func=None, func_rename=None, raw_groupby_params=None,
+                 groupby_params=None, method="auto", use_inf_as_na=False, combine_size=None,
+                 chunk_store_limit=None, pre_funcs=None, agg_funcs=None, post_funcs=None, index_levels=None,
+                 size_recorder_name=None, **kw):
+        super().__init__(raw_func=raw_func, raw_func_kw=raw_func_kw or {}, func=func, func_rename=func_rename,
+                         raw_groupby_params=raw_groupby_params, groupby_params=groupby_params, method=method,
+                         use_inf_as_na=use_inf_as_na, combine_size=combine_size,
+                         chunk_store_limit=chunk_store_limit, pre_funcs=pre_funcs, agg_funcs=agg_funcs,
+                         post_funcs=post_funcs, index_levels=index_levels,
+                         size_recorder_name=size_recorder_name, tileable_op_key=None, **kw)
+
+    # ---- function normalisation (reference: normalize_reduction_funcs, reduction/aggregation.py:959-1006)
+    def _normalize(self):
+        raw = self.raw_func
+        if isinstance(raw, dict):
+            func = OrderedDict()
+            for col, fs in raw.items():
+                fs = [fs] if isinstance(fs, str) else list(fs)
+                func[col] = [check_supported(f) for f in fs]
+            self.func = func
+        elif isinstance(raw, (list, tuple)):
+            self.func = [check_supported(f) for f in raw]
+        else:
+            self.func = [check_supported(raw)]
+
+    # ---- compile (reference: _compile_funcs, aggregation.py:525-549)
+    @classmethod
+    def _compile_funcs(cls, op) -> ReductionSteps:
+        if isinstance(op.func, list):
+            it = [(None, f) for f in op.func]
+        else:
+            it = [(col, f) for col, fs in op.func.items() for f in fs]
+        return compile_reduction(it, ddof=op.raw_func_kw.get("ddof", 1))
+
+    # ---- tile helpers ------------------------------------------------------------------------------
+    @classmethod
+    def _gen_map_chunks(cls, op, in_chunks, out_df, steps: ReductionSteps) -> List[ChunkData]:
+        """one stage=map chunk per input chunk (aggregation.py:473-523)"""
+        out = []
+        for chunk in in_chunks:
+            map_op = op.copy().reset_key()
+            map_op.groupby_params = dict(op.groupby_params, as_index=True)
+            map_op.stage = OperandStage.map
+            map_op.pre_funcs = steps.pre_funcs
+            map_op.agg_funcs = steps.agg_funcs
+            out.append(map_op.new_chunk([chunk], shape=out_df.shape, index=(chunk.index[0], 0),
+                                        index_value=out_df.index_value, columns_value=out_df.columns_value,
+                                        dtypes=out_df.dtypes))
+        return out
+
+    @classmethod
+    def _agg_like_op(cls, op, stage, steps, with_post):
+        new = op.copy().reset_key()
+        new.stage = stage
+        params = dict(op.groupby_params)
+        params.pop("selection", None)
+        params.pop("by", None)
+        params["level"] = list(range(op.index_levels))   # group on index levels after the map stage
+        new.groupby_params = params
+        new.agg_funcs = steps.agg_funcs
+        new.pre_funcs = None
+        new.post_funcs = steps.post_funcs if with_post else None
+        return new
+
+    @classmethod
+    def _build_tree_chunks(cls, op, chunks, steps, combine_size, input_chunk_size=None, chunk_store_limit=None):
+        """combine_size-ary tree of concat + stage=combine (aggregation.py:715-780)"""
+        out_df = op.outputs[0]
+        check_size = chunk_store_limit is not None
+        concat_size = input_chunk_size
+        while (not check_size or concat_size < chunk_store_limit) and len(chunks) > combine_size:
+            new_chunks = []
+            for idx, i in enumerate(range(0, len(chunks), combine_size)):
+                chks = chunks[i:i + combine_size]
+                if len(chks) == 1:
+                    chk = chks[0]
+                else:
+                    for j, c in enumerate(chks):
+                        c.index = (j, 0)
+                    chk = DataFrameConcat(gpu=op.gpu).new_chunk(chks, dtypes=chks[0].dtypes,
+                                                               shape=(np.nan, out_df.shape[1]), index=(idx, 0))
+                cop = cls._agg_like_op(op, OperandStage.combine, steps, with_post=False)
+                new_chunks.append(cop.new_chunk([chk], index=(idx, 0), shape=(np.nan, out_df.shape[1]),
+                                                index_value=chks[0].index_value,
+                                                columns_value=out_df.columns_value, dtypes=out_df.dtypes))
+            chunks = new_chunks
+            if concat_size is not None:
+                concat_size *= combine_size
+        return (chunks, concat_size) if concat_size else chunks
+
+    @classmethod
+    def _build_out_tileable(cls, op, out_df, combined, steps):
+        """final concat + stage=agg (aggregation.py:782-823)"""
+        if len(combined) == 1:
+            chk = combined[0]
+        else:
+            for j, c in enumerate(combined):
+                c.index = (j, 0)
+            chk = DataFrameConcat(gpu=op.gpu).new_chunk(combined, dtypes=combined[0].dtypes,
+                                                        shape=(np.nan, out_df.shape[1]), index=(0, 0))
+        aop = cls._agg_like_op(op, OperandStage.agg, steps, with_post=True)
+        aop.tileable_op_key = op.key
+        chunk = aop.new_chunk([chk], index=(0, 0), **out_df.params)
+        return _finish_tileable(op, out_df, [chunk])
+
+    @classmethod
+    def _gen_shuffle_chunks(cls, op, chunks):
+        """hash shuffle: n map -> proxy -> n reduce, partition count == number of mapper chunks
+        (aggregation.py:428-471)"""
+        n = len(chunks)
+        maps = []
+        for chunk in chunks:
+            mop = DataFrameGroupByOperand(stage=OperandStage.map, shuffle_size=n, gpu=op.gpu)
+            maps.append(mop.new_chunk([chunk], shape=(np.nan, np.nan), index=chunk.index,
+                                      index_value=op.outputs[0].index_value))
+        proxy = DataFrameShuffleProxy(gpu=op.gpu).new_chunk(maps, shape=())
+        reduces = []
+        for idx in itertools.product(range(n), range(1)):
+            rop = DataFrameGroupByOperand(stage=OperandStage.reduce, n_reducers=n, gpu=op.gpu)
+            reduces.append(rop.new_chunk([proxy], shape=(np.nan, np.nan), index=idx,
+                                         index_value=op.outputs[0].index_value))
+        return reduces
+
+    @classmethod
+    def _perform_shuffle(cls, op, agg_chunks, in_df, out_df, steps):
+        """aggregation.py:643-702"""
+        if op.groupby_params["sort"] and len(in_df.chunks) > 1:
+            raise NotImplementedError(
+                "groupby(sort=True).agg(method='shuffle') range-partitions with PSRS sampling "
+                "(mars/dataframe/groupby/sort.py); this build implements the hash shuffle: pass sort=False "
+                "(SURVEY.md section 8f, rank 1)")
+        reduce_chunks = cls._gen_shuffle_chunks(op, agg_chunks)
+        outs = []
+        for chunk in reduce_chunks:
+            aop = cls._agg_like_op(op, OperandStage.agg, steps, with_post=True)
+            aop.tileable_op_key = op.key
+            outs.append(aop.new_chunk([chunk], index=chunk.index, **out_df.params))
+        return _finish_tileable(op, out_df, outs)
+
+    @classmethod
+    def _tile_with_tree(cls, op, in_df, out_df, steps):
+        chunks = cls._gen_map_chunks(op, in_df.chunks, out_df, steps)
+        chunks = cls._build_tree_chunks(op, chunks, steps, op.combine_size)
+        return cls._build_out_tileable(op, out_df, chunks, steps)
+
+    @classmethod
+    def _tile_with_shuffle(cls, op, in_df, out_df, steps):
+        chunks = cls._gen_map_chunks(op, in_df.chunks, out_df, steps)
+        return cls._perform_shuffle(op, chunks, in_df, out_df, steps)
+
+    @classmethod
+    def _build_tree_and_shuffle_chunks(cls, op, in_df, out_df, steps, sample_map_chunks, sample_agg_sizes):
+        """decision rule of method='auto' (aggregation.py:838-884)"""
+        combine_size = op.combine_size
+        left = cls._gen_map_chunks(op, in_df.chunks[combine_size:], out_df, steps)
+        input_size = sum(sample_agg_sizes) / len(sample_agg_sizes)
+        limit = op.chunk_store_limit / 4
+        combined, concat_size = cls._build_tree_chunks(op, sample_map_chunks + left, steps, combine_size,
+                                                       input_size, limit)
+        if concat_size <= limit:
+            return cls._build_out_tileable(op, out_df, combined, steps)
+        return cls._perform_shuffle(op, combined, in_df, out_df, steps)
+
+    @classmethod
+    def tile(cls, op):
+        """Generator: yields chunk lists that must be executed before tiling can continue (method='auto'
+        samples the first combine_size map chunks, aggregation.py:887-925); returns the tiled tileable."""
+        in_df = op.inputs[0]
+        out_df = op.outputs[0]
+        steps = cls._compile_funcs(op)
+        if op.method == "auto":
+            if len(in_df.chunks) <= op.combine_size:
+                return cls._tile_with_tree(op, in_df, out_df, steps)
+            recorder = SizeRecorder()
+            chunks = cls._gen_map_chunks(op, in_df.chunks[:op.combine_size], out_df, steps)
+            for c in chunks:
+                c.op.size_recorder_name = recorder.name
+            yield chunks
+            raw_sizes, agg_sizes = recorder.get()
+            SizeRecorder.destroy(recorder.name)
+            for c in chunks:
+                c.op.size_recorder_name = None
+            return cls._build_tree_and_shuffle_chunks(op, in_df, out_df, steps, chunks, agg_sizes)
+        if op.method == "shuffle":
+            return cls._tile_with_shuffle(op, in_df, out_df, steps)
+        if op.method == "tree":
+            return cls._tile_with_tree(op, in_df, out_df, steps)
+        raise NotImplementedError(op.method)
+
+
+class SizeRecorder:
+    """reference: aggregation.py:79-89 (a remote object there; process-local registry here)."""
+    _registry: Dict[str, "SizeRecorder"] = {}
+
+    def __init__(self):
+        self.name = new_key("sizerec")
+        self._raw, self._agg = [], []
+        SizeRecorder._registry[self.name] = self
+
+    def record(self, raw_size: int, agg_size: int):
+        self._raw.append(raw_size)
+        self._agg.append(agg_size)
+
+    def get(self):
+        return self._raw, self._agg
+
+    @classmethod
+    def lookup(cls, name):
+        return cls._registry[name]
+
+    @classmethod
+    def destroy(cls, name):
+        cls._registry.pop(name, None)
+
+
+def _finish_tileable(op, out_df, chunks):
+    out_df.chunks = chunks
+    out_df.nsplits = ((np.nan,) * len(chunks), (out_df.shape[1],))
+    return out_df
+
+
+# ----------------------------------------------------------------------------------------------------
+# user-facing objects
+# ----------------------------------------------------------------------------------------------------
+class DataFrame:
+    """Lazy chunked DataFrame (row chunks only, like the inputs of the groupby path)."""
+
+    def __init__(self, data, chunk_size: Optional[int] = None, gpu: bool = False, _tileable=None):
+        if _tileable is not None:
+            self.data = _tileable
+            return
+        if not isinstance(data, pd.DataFrame):
+            data = pd.DataFrame(data)
+        n = len(data)
+        chunk_size = int(chunk_size or options.chunk_size or max(n, 1))
+        op = DataFrameDataSource(gpu=False)
+        t = op.new_tileable([], shape=data.shape, dtypes=data.dtypes, index_value=IndexValue(data.index),
+                            columns_value=IndexValue(data.columns))
+        chunks = []
+        for i, start in enumerate(range(0, max(n, 1), chunk_size)):
+            piece = data.iloc[start:start + chunk_size]
+            cop = DataFrameDataSource(gpu=False, data=piece)
+            chunks.append(cop.new_chunk([], shape=piece.shape, index=(i, 0), dtypes=data.dtypes,
+                                        index_value=IndexValue(piece.index), columns_value=IndexValue(data.columns)))
+        t.chunks = chunks
+        t.nsplits = (tuple(c.shape[0] for c in chunks), (data.shape[1],))
+        self.data = t
+        if gpu:
+            self.data = self.to_gpu().data
+
+    # metadata passthrough
+    @property
+    def shape(self):
+        return self.data.shape
+
+    @property
+    def dtypes(self):
+        return self.data.dtypes
+
+    @property
+    def chunks(self):
+        return self.data.chunks
+
+    @property
+    def op(self):
+        return self.data.op
+
+    @property
+    def columns_value(self):
+        return self.data.columns_value
+
+    @property
+    def index_value(self):
+        return self.data.index_value
+
+    def to_gpu(self) -> "DataFrame":
+        src = self.data
+        op = DataFrameToGPU(gpu=True)
+        t = op.new_tileable([src], **src.params)
+        t.chunks = [DataFrameToGPU(gpu=True).new_chunk([c], shape=c.shape, index=c.index, dtypes=c.dtypes,
+                                                       index_value=c.index_value, columns_value=c.columns_value)
+                    for c in src.chunks]
+        t.nsplits = src.nsplits
+        return DataFrame(None, _tileable=t)
+
+    def groupby(self, by=None, level=None, as_index=True, sort=True, group_keys=True) -> "DataFrameGroupBy":
+        if level is not None:
+            raise NotImplementedError("groupby(level=...) on the input frame is outside the GPU path")
+        if by is None:
+            raise TypeError("You have to supply one of 'by' and 'level'")
+        if not isinstance(by, (list, tuple)):
+            by = [by]
+        by = list(by)
+        for b in by:
+            if b not in self.data.dtypes.index:
+                raise KeyError(b)
+        return DataFrameGroupBy(self, by, as_index=as_index, sort=sort, group_keys=group_keys)
+
+    # execution sugar (reference: .execute() / .fetch(), deploy/oscar/session.py)
+    def execute(self, session=None, **kw):
+        from .session import get_default_session
+        (session or get_default_session()).execute(self, **kw)
+        return self
+
+    def fetch(self, session=None):
+        from .session import get_default_session
+        return (session or get_default_session()).fetch(self)
+
+
+class DataFrameGroupBy:
+    def __init__(self, df: DataFrame, by: List[Any], as_index=True, sort=True, group_keys=True, selection=None):
+        self.df = df
+        self.by = by
+        self.as_index = as_index
+        self.sort = sort
+        self.group_keys = group_keys
+        self.selection = selection
+
+    def __getitem__(self, item):
+        """column selection (reference: groupby/getitem.py:38-41 only records `selection`)"""
+        sel = list(item) if isinstance(item, (list, tuple)) else [item]
+        for c in sel:
+            if c not in self.df.dtypes.index:
+                raise KeyError(c)
+        return DataFrameGroupBy(self.df, self.by, self.as_index, self.sort, self.group_keys, selection=sel)
+
+    @property
+    def groupby_params(self):
+        p = dict(by=list(self.by), level=None, as_index=self.as_index, sort=self.sort, group_keys=self.group_keys)
+        if self.selection is not None:
+            p["selection"] = list(self.selection)
+        return p
+
+    def _mock_result(self, func, **kw) -> pd.DataFrame:
+        """schema inference by running real pandas on a small mock frame (reference: build_mock_agg_result,
+        aggregation.py:142-161)"""
+        dtypes = self.df.dtypes
+        mock = pd.DataFrame({c: np.arange(1, 5).astype(dt) for c, dt in dtypes.items()})
+        g = mock.groupby(self.by, as_index=self.as_index, sort=self.sort)
+        if self.selection is not None:
+            g = g[self.selection]
+        return g.agg(func, **kw)
+
+    def agg(self, func=None, method="auto", combine_size=None, **kw) -> DataFrame:
+        if method is None:
+            method = "auto"
+        if method not in ("shuffle", "tree", "auto"):
+            raise ValueError(f"Method {method} is not available, please specify 'tree' or 'shuffle")
+        if not self.as_index:
+            raise NotImplementedError("as_index=False is applied on the host by the caller in this build")
+        gpu = bool(self.df.op.gpu)
+        op = DataFrameGroupByAgg(raw_func=func, raw_func_kw=kw, method=method,
+                                 raw_groupby_params=self.groupby_params, groupby_params=self.groupby_params,
+                                 combine_size=combine_size or options.combine_size,
+                                 chunk_store_limit=options.chunk_store_limit, use_inf_as_na=False, gpu=gpu)
+        op._normalize()
+        mock = self._mock_result(func, **kw)
+        if isinstance(mock, pd.Series):
+            raise NotImplementedError("series-valued aggregation results are outside the GPU path")
+        op.index_levels = mock.index.nlevels
+        t = op.new_tileable([self.df.data], shape=(np.nan, mock.shape[1]), dtypes=mock.dtypes,
+                            index_value=IndexValue(mock.index[:0]), columns_value=IndexValue(mock.columns))
+        return DataFrame(None, _tileable=t)
+
+    aggregate = agg
+
+    def sum(self, **kw):
+        return self.agg("sum", **kw)
+
+    def count(self, **kw):
+        return self.agg("count", **kw)
+
+    def min(self, **kw):
+        return self.agg("min", **kw)
+
+    def max(self, **kw):
+        return self.agg("max", **kw)
+
+    def mean(self, **kw):
+        return self.agg("mean", **kw)
+
+    def var(self, **kw):
+        return self.agg("var", **kw)

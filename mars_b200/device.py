@@ -1,0 +1,134 @@
+"""Device-resident frames: what flows through ``ctx`` between the GPU executors.
+
+The reference moves pandas (or cudf) DataFrames between operands; on a GPU band the partial results of the
+groupby path never leave HBM, so the values placed in ``ctx`` are ``DeviceFrame`` objects: a list of int64
+index (group key) columns plus named float64/int64 data columns, each a 1-D CUDA tensor.  A tuple of K
+DeviceFrames sharing their index tensors replaces the reference's tuple of K DataFrames
+(mars/dataframe/groupby/aggregation.py:1128).  Frames are freed by Python reference counting, exactly like
+the processor frees ctx entries (processor.py:276-282).
+"""
+from __future__ import annotations
+
+from typing import Any, List, Optional, Sequence
+
+import numpy as np
+import pandas as pd
+import torch
+
+
+class DeviceFrame:
+    __slots__ = ("index_names", "index", "columns", "data", "_n")
+
+    def __init__(self, index_names: Sequence[Any], index: Optional[Sequence[torch.Tensor]],
+                 columns: Sequence[Any], data: Sequence[torch.Tensor], n_rows: Optional[int] = None):
+        self.index_names = list(index_names)
+        self.index = None if index is None else list(index)   # None == RangeIndex (raw input chunk)
+        self.columns = list(columns)
+        self.data = list(data)
+        if n_rows is None:
+            if self.data:
+                n_rows = int(self.data[0].numel())
+            elif self.index:
+                n_rows = int(self.index[0].numel())
+            else:
+                n_rows = 0
+        self._n = n_rows
+
+    # ---- pandas-like surface used by metas / size accounting (subtask/utils.py:62-68)
+    def __len__(self):
+        return self._n
+
+    @property
+    def shape(self):
+        return (self._n, len(self.columns))
+
+    @property
+    def ndim(self):
+        return 2
+
+    @property
+    def dtypes(self):
+        return pd.Series([np.dtype(str(t.dtype).replace("torch.", "")) for t in self.data], index=self.columns)
+
+    @property
+    def nbytes(self) -> int:
+        total = sum(t.numel() * t.element_size() for t in self.data)
+        if self.index:
+            total += sum(t.numel() * t.element_size() for t in self.index)
+        return total
+
+    def __sizeof__(self):
+        return 64 + self.nbytes
+
+    @property
+    def device(self):
+        ts = self.data or self.index or []
+        return ts[0].device if ts else torch.device("cpu")
+
+    def column(self, name) -> torch.Tensor:
+        return self.data[self.columns.index(name)]
+
+    def slice_rows(self, start: int, stop: int) -> "DeviceFrame":
+        return DeviceFrame(self.index_names, None if self.index is None else [t[start:stop] for t in self.index],
+                           self.columns, [t[start:stop] for t in self.data], stop - start)
+
+    def same_index(self, other: "DeviceFrame") -> bool:
+        """True when both frames share their index tensors (reference: item.index.equals(index),
+        groupby/core.py:381-391 -- here a pointer comparison, no data pass)."""
+        if self.index is None or other.index is None:
+            return self.index is other.index and len(self) == len(other)
+        if len(self.index) != len(other.index) or len(self) != len(other):
+            return False
+        return all(a.data_ptr() == b.data_ptr() and a.numel() == b.numel() for a, b in zip(self.index, other.index))
+
+    # ---- host <-> device (reference: DataFrameToGPU / DataFrameToCPU, dataframe/base/to_gpu.py:28-35)
+    @classmethod
+    def from_pandas(cls, df: pd.DataFrame, device="cuda", index_as_keys: bool = False) -> "DeviceFrame":
+        """H2D copy of a pandas chunk.  Numeric columns only: float64, int64 (narrower ints / bool are widened
+        to int64, which is what pandas' own group_sum does); anything else raises NotImplementedError so
+        that the caller can fall back to the reference executor."""
+        cols, data = [], []
+        for name in df.columns:
+            s = df[name]
+            arr = s.to_numpy()
+            if arr.dtype == np.float64 or arr.dtype == np.int64:
+                pass
+            elif arr.dtype.kind in "iub" and arr.dtype.itemsize <= 8 and arr.dtype != np.uint64:
+                arr = arr.astype(np.int64)
+            else:
+                raise NotImplementedError(f"column {name!r} has dtype {arr.dtype}: the GPU groupby path handles "
+                                          f"float64 and int64 columns")
+            t = torch.from_numpy(np.ascontiguousarray(arr))
+            data.append(t.to(device, non_blocking=True))
+            cols.append(name)
+        index = None
+        names: List[Any] = []
+        if index_as_keys:
+            names = list(df.index.names)
+            if isinstance(df.index, pd.MultiIndex):
+                levels = [df.index.get_level_values(i).to_numpy() for i in range(df.index.nlevels)]
+            else:
+                levels = [df.index.to_numpy()]
+            index = []
+            for lv in levels:
+                if lv.dtype != np.int64:
+                    raise NotImplementedError(f"group key dtype {lv.dtype}: int64 keys only")
+                index.append(torch.from_numpy(np.ascontiguousarray(lv)).to(device, non_blocking=True))
+        return cls(names, index, cols, data, len(df))
+
+    def to_pandas(self) -> pd.DataFrame:
+        data = {i: t.cpu().numpy() for i, t in enumerate(self.data)}
+        df = pd.DataFrame(data)
+        df.columns = pd.Index(self.columns) if not (self.columns and isinstance(self.columns[0], tuple)) \
+            else pd.MultiIndex.from_tuples(self.columns)
+        if self.index is not None:
+            arrays = [t.cpu().numpy() for t in self.index]
+            if len(arrays) == 1:
+                df.index = pd.Index(arrays[0], name=self.index_names[0] if self.index_names else None)
+            else:
+                df.index = pd.MultiIndex.from_arrays(arrays, names=self.index_names)
+        return df
+
+    def __repr__(self):
+        return (f"DeviceFrame(rows={self._n}, index={self.index_names if self.index is not None else 'range'}, "
+                f"columns={self.columns}, device={self.device})")

@@ -1,0 +1,482 @@
+"""GPU executors for the groupby-aggregation operands: ``fn(ctx, op) -> None``.
+
+Each function replaces one ``execute`` classmethod of the reference and is registered through
+``Operand.register_executor`` (mars/core/operand/core.py:458-464).  They are written against the operand
+*protocol* only (``op.stage``, ``op.inputs/outputs``, ``op.groupby_params``, ``op.pre_funcs/agg_funcs/
+post_funcs``, ``op.shuffle_size``, ``op.iter_mapper_data(ctx)``, ``ctx.get_current_chunk()``), so the same
+code serves the host mirror in ``mars_b200.dataframe`` and the real reference classes (``mars_b200.plugin``).
+
+  execute_groupby_agg      DataFrameGroupByAgg.execute        aggregation.py:1269-1284 (map/combine/agg)
+  execute_groupby_operand  DataFrameGroupByOperand.execute    groupby/core.py:353-508 (shuffle map/reduce)
+  execute_concat           DataFrameConcat.execute (tuples)   merge/concat.py:339-348
+  execute_to_gpu           DataFrameToGPU.execute             base/to_gpu.py:28-35
+  execute_datasource       (host chunk provider of the mirror)
+
+Values in ``ctx``: raw chunks and partials are ``DeviceFrame`` objects (HBM resident); the final stage=agg
+output is a ``pandas.DataFrame`` because chunk metas are computed from it (subtask/utils.py:62-68).
+All arithmetic happens in libmarsgb.so (mars_b200.kernels); there is no CPU fallback.
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import pandas as pd
+import torch
+
+from . import kernels as K
+from ._lib import MarsGBError
+from .device import DeviceFrame
+from .reduction import _DECOMP
+
+_OPCODE = {"sum": K.SUM, "count": K.COUNT, "min": K.MIN, "max": K.MAX}
+_DECOMP_EXT = dict(_DECOMP, std=_DECOMP["var"])
+
+# the kernels module is looked up through this indirection so that host-logic tests can substitute a
+# recording double; the product never rebinds it.
+_kernels = K
+
+
+def _stage(op) -> Optional[str]:
+    st = getattr(op, "stage", None)
+    return None if st is None else getattr(st, "name", str(st))
+
+
+def _device() -> torch.device:
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _as_device_frame(value, index_as_keys=False) -> DeviceFrame:
+    if isinstance(value, DeviceFrame):
+        return value
+    if isinstance(value, pd.DataFrame):
+        return DeviceFrame.from_pandas(value, device=_device(), index_as_keys=index_as_keys)
+    raise NotImplementedError(f"cannot move {type(value).__name__} to the GPU groupby path")
+
+
+# ----------------------------------------------------------------------------------------------------
+# step planning
+# ----------------------------------------------------------------------------------------------------
+def classify_pre(func) -> str:
+    """'identity' or 'square'.  Mirror steps carry ``kind``; the reference's generated callables are probed
+    on a two-element series (their source is ``return invar0`` or ``invar0.pow(2)``, Appendix A.3)."""
+    kind = getattr(func, "kind", None)
+    if kind is not None:
+        return kind
+    probe = pd.Series([3.0, -2.0])
+    try:
+        out = func(probe, gpu=False)
+    except TypeError:
+        out = func(probe)
+    out = np.asarray(out, dtype="float64")
+    if np.array_equal(out, [3.0, -2.0]):
+        return "identity"
+    if np.array_equal(out, [9.0, 4.0]):
+        return "square"
+    raise NotImplementedError("pre-aggregation function is neither identity nor x**2")
+
+
+def classify_post(func, n_inputs: int) -> Optional[Tuple[str, int]]:
+    """(kind, ddof) for identity / mean / var post functions, None if unrecognised (then the callable itself
+    is evaluated on host copies of the merged partials)."""
+    kind = getattr(func, "kind", None)
+    if kind is not None:
+        return kind, getattr(func, "ddof", 1)
+
+    def call(*a):
+        try:
+            return np.asarray(func(*a, gpu=False), dtype="float64")
+        except TypeError:
+            return np.asarray(func(*a), dtype="float64")
+
+    try:
+        if n_inputs == 1:
+            x = pd.Series([3.0, 5.0])
+            return ("identity", 1) if np.array_equal(call(x), [3.0, 5.0]) else None
+        if n_inputs == 2:
+            s, c = pd.Series([6.0, 9.0]), pd.Series([3, 2])
+            return ("mean", 1) if np.array_equal(call(s, c), [2.0, 4.5]) else None
+        if n_inputs == 3:
+            q, s, c = pd.Series([14.0, 41.0]), pd.Series([6.0, 9.0]), pd.Series([3, 2])
+            got = call(q, s, c)
+            for ddof in (1, 0):
+                if ddof == 0:
+                    exp = (q / c - (s / c) ** 2).to_numpy()
+                else:
+                    exp = ((q - s ** 2 / c) / (c - ddof)).to_numpy()
+                if np.allclose(got, exp, rtol=1e-15, atol=0):
+                    return "var", ddof
+    except Exception:  # noqa: BLE001
+        return None
+    return None
+
+
+class _Step:
+    __slots__ = ("pre_kind", "map_func", "agg_func", "output_key", "cols")
+
+    def __init__(self, pre_kind, map_func, agg_func, output_key, cols):
+        self.pre_kind, self.map_func, self.agg_func = pre_kind, map_func, agg_func
+        self.output_key, self.cols = output_key, cols
+
+
+def _needed_columns(op, value_cols: Sequence[Any], pre_kind: str, map_func: str, pre_cols) -> List[Any]:
+    """Value columns on which the atomic step (pre_kind, map_func) is actually consumed by a user function.
+    The reference evaluates every step on every referred column (its map frames carry all of them); the
+    columns no post function reads are dead and are not computed here."""
+    func = getattr(op, "func", None)
+    base = [c for c in value_cols if pre_cols is None or c in pre_cols]
+    if func is None:
+        return base
+    if isinstance(func, (list, tuple)):
+        per_col = {c: list(func) for c in base}
+    else:
+        per_col = {c: list(fs) if isinstance(fs, (list, tuple)) else [fs] for c, fs in func.items()}
+    out = []
+    for c in base:
+        for f in per_col.get(c, []):
+            dec = _DECOMP_EXT.get(f) if isinstance(f, str) else None
+            if dec is None:
+                raise NotImplementedError(f"aggregation function {f!r} is outside the GPU groupby path")
+            if any(k == pre_kind and m == map_func for k, m, _ in dec):
+                out.append(c)
+                break
+    return out
+
+
+def _plan_steps(op, value_cols) -> List[_Step]:
+    pre_by_key = {}
+    for p in (getattr(op, "pre_funcs", None) or []):
+        pre_by_key[p.output_key] = (classify_pre(p.func), p.columns)
+    steps = []
+    for a in op.agg_funcs:
+        if a.custom_reduction is not None or a.map_func_name == "custom_reduction":
+            raise NotImplementedError("custom reductions run on the reference executor")
+        if a.map_func_name not in _OPCODE or a.agg_func_name not in _OPCODE:
+            raise NotImplementedError(f"atomic step {a.map_func_name}->{a.agg_func_name} is outside the GPU path")
+        if a.kwds and not a.kwds.get("skipna", True):
+            raise NotImplementedError("skipna=False is outside the GPU path")
+        pre_kind, pre_cols = pre_by_key.get(a.input_key, ("identity", None))
+        cols = _needed_columns(op, value_cols, pre_kind, a.map_func_name, pre_cols) if value_cols is not None else None
+        steps.append(_Step(pre_kind, a.map_func_name, a.agg_func_name, a.output_key, cols))
+    return steps
+
+
+# ----------------------------------------------------------------------------------------------------
+# DataFrameGroupByAgg
+# ----------------------------------------------------------------------------------------------------
+def _execute_agg_map(ctx, op):
+    """stage=map: per-chunk group-by + K atomic reductions (reference: _execute_map, aggregation.py:1043-1128)"""
+    frame = _as_device_frame(ctx[op.inputs[0].key])
+    params = op.groupby_params
+    by = params.get("by")
+    if not isinstance(by, (list, tuple)) or not by or any(not isinstance(b, (str, int, tuple)) for b in by):
+        raise NotImplementedError("groupby keys must be column labels on the GPU path")
+    by = list(by)
+    if frame.index is not None:
+        raise NotImplementedError("map stage expects a raw chunk (RangeIndex)")
+    selection = params.get("selection")
+    value_cols = [c for c in frame.columns if c not in by and (selection is None or c in selection)]
+    steps = _plan_steps(op, value_cols)
+    keys = [frame.column(b) for b in by]
+    for b, k in zip(by, keys):
+        if k.dtype != torch.int64:
+            raise NotImplementedError(f"group key {b!r} has dtype {k.dtype}: int64 keys only")
+    used: List[Any] = []
+    for s in steps:
+        for c in s.cols:
+            if c not in used:
+                used.append(c)
+    if not used:
+        raise NotImplementedError("no value column to aggregate")
+    vals = [frame.column(c) for c in used]
+    accs = []
+    for s in steps:
+        code = _OPCODE[s.map_func]
+        if s.pre_kind == "square":
+            if s.map_func != "sum":
+                raise NotImplementedError("x**2 is only aggregated with sum")
+            code = K.SUMSQ
+        for c in s.cols:
+            accs.append((used.index(c), code))
+    out_keys, out_accs, stats = _kernels.groupby_aggregate(keys, vals, accs, sort=False)
+    frames, pos = [], 0
+    for s in steps:
+        frames.append(DeviceFrame(by, out_keys, s.cols, out_accs[pos:pos + len(s.cols)], int(out_keys[0].numel())))
+        pos += len(s.cols)
+    rec = getattr(op, "size_recorder_name", None)
+    if rec is not None:
+        _record_sizes(ctx, rec, frame.nbytes, sum(f.nbytes for f in frames))
+    ctx[op.outputs[0].key] = tuple(frames)
+
+
+def _record_sizes(ctx, name, raw_size, agg_size):
+    getter = getattr(ctx, "get_remote_object", None)
+    if getter is not None:  # real Mars context (aggregation.py:1120-1126)
+        getter(name).record(raw_size, agg_size)
+        return
+    from .dataframe import SizeRecorder
+    SizeRecorder.lookup(name).record(raw_size, agg_size)
+
+
+def _merge_partials(frames: Sequence[DeviceFrame], steps: Sequence[_Step], sort: bool) -> List[DeviceFrame]:
+    """Re-aggregate partial frames slot-wise: slot k -> groupby(level).agg(agg_func_k)
+    (reference: _execute_combine, aggregation.py:1130-1164; count partials are SUMmed as int64)."""
+    if len(frames) != len(steps):
+        raise MarsGBError(1, f"{len(frames)} partial frames for {len(steps)} aggregation steps")
+    first = frames[0]
+    shared = all(first.same_index(f) for f in frames[1:])
+    groups: List[List[int]] = []
+    if shared:
+        cur, width = [], 0
+        for i, f in enumerate(frames):
+            if cur and width + len(f.columns) > 64:
+                groups.append(cur)
+                cur, width = [], 0
+            cur.append(i)
+            width += len(f.columns)
+        groups.append(cur)
+    else:
+        groups = [[i] for i in range(len(frames))]
+    force_sort = sort or len(groups) > 1
+    out: List[Optional[DeviceFrame]] = [None] * len(frames)
+    for grp in groups:
+        base = frames[grp[0]]
+        vals, accs = [], []
+        for i in grp:
+            code = _OPCODE[steps[i].agg_func]
+            for t in frames[i].data:
+                accs.append((len(vals), code))
+                vals.append(t)
+        k, a, _ = _kernels.groupby_aggregate(base.index, vals, accs, sort=force_sort)
+        pos = 0
+        for i in grp:
+            ncol = len(frames[i].columns)
+            out[i] = DeviceFrame(base.index_names, k, frames[i].columns, a[pos:pos + ncol], int(k[0].numel()))
+            pos += ncol
+    return out  # type: ignore[return-value]
+
+
+def _partials_of(value) -> List[DeviceFrame]:
+    if not isinstance(value, tuple):
+        value = (value,)
+    return [_as_device_frame(v, index_as_keys=True) for v in value if not isinstance(v, bool)]
+
+
+def _execute_agg_combine(ctx, op):
+    frames = _partials_of(ctx[op.inputs[0].key])
+    steps = _plan_steps(op, None)
+    ctx[op.outputs[0].key] = tuple(_merge_partials(frames, steps, sort=False))
+
+
+def _execute_agg_agg(ctx, op):
+    """stage=agg: final merge, post functions, result frame (reference: _execute_agg, aggregation.py:1166-1267)"""
+    out_chunk = op.outputs[0]
+    frames = _partials_of(ctx[op.inputs[0].key])
+    steps = _plan_steps(op, None)
+    sort = bool(op.groupby_params.get("sort", True))
+    merged = _merge_partials(frames, steps, sort=sort)
+    by_key = {s.output_key: f for s, f in zip(steps, merged)}
+    col_value = out_chunk.columns_value.to_pandas()
+    two_level = col_value.nlevels > 1
+    pieces: Dict[Any, np.ndarray] = {}
+    host_eval = []
+    for p in op.post_funcs:
+        inputs = [by_key[k] for k in p.input_keys]
+        cols = list(p.columns) if p.columns is not None else None
+        common = [c for c in inputs[0].columns if all(c in f.columns for f in inputs[1:])
+                  and (cols is None or c in cols)]
+        cls = classify_post(p.func, len(inputs))
+        for c in common:
+            label = (c, p.func_name) if two_level else c
+            if cls is None:
+                host_eval.append((label, p, c, inputs))
+                continue
+            kind, ddof = cls
+            ts = [f.column(c) for f in inputs]
+            if kind == "identity":
+                res = ts[0]
+            elif kind == "mean":
+                res = _kernels.post_mean(ts[0], ts[1])
+            else:
+                res = _kernels.post_var(ts[1], ts[0], ts[2], ddof)   # inputs: sum(x**2), sum(x), count
+            pieces[label] = res
+    # one D2H per result column (tiny except for very high cardinality)
+    host = {label: t.cpu().numpy() for label, t in pieces.items()}
+    for label, p, c, inputs in host_eval:
+        args = [pd.Series(f.column(c).cpu().numpy()) for f in inputs]
+        try:
+            host[label] = np.asarray(p.func(*args, gpu=False))
+        except TypeError:
+            host[label] = np.asarray(p.func(*args))
+    base = merged[0]
+    idx_arrays = [t.cpu().numpy() for t in base.index]
+    names = base.index_names
+    out_names = getattr(out_chunk.index_value, "names", None) if out_chunk.index_value is not None else None
+    if out_names and len(out_names) == len(idx_arrays) and any(n is not None for n in out_names):
+        names = list(out_names)
+    if len(idx_arrays) == 1:
+        index = pd.Index(idx_arrays[0], name=names[0] if names else None)
+    else:
+        index = pd.MultiIndex.from_arrays(idx_arrays, names=names)
+    labels = list(host.keys())
+    result = pd.DataFrame({i: host[l] for i, l in enumerate(labels)}, index=index)
+    result.columns = pd.MultiIndex.from_tuples(labels) if two_level else pd.Index(labels)
+    if not op.groupby_params.get("as_index", True):
+        result = result.reset_index()
+    result = result.reindex(col_value, axis=1)
+    dtypes = getattr(out_chunk, "dtypes", None)
+    if dtypes is not None and len(result) == 0:
+        result = result.astype(dtypes)
+    ctx[out_chunk.key] = result
+
+
+def execute_groupby_agg(ctx, op):
+    st = _stage(op)
+    if st == "map":
+        _execute_agg_map(ctx, op)
+    elif st == "combine":
+        _execute_agg_combine(ctx, op)
+    elif st == "agg":
+        _execute_agg_agg(ctx, op)
+    else:
+        raise ValueError("Aggregation operand not executable")
+
+
+# ----------------------------------------------------------------------------------------------------
+# DataFrameGroupByOperand: hash shuffle
+# ----------------------------------------------------------------------------------------------------
+def _execute_shuffle_map(ctx, op):
+    """stage=map: partition id = pandas hash of the group keys % shuffle_size; one block per reducer,
+    empty ones included (reference: execute_map, groupby/core.py:353-435; contract shuffle.py:124-130)."""
+    by = getattr(op, "by", None)
+    if isinstance(by, (list, tuple)) or callable(by):
+        raise NotImplementedError("shuffling on `by` columns (plain groupby) is outside the agg path")
+    chunk = op.outputs[0]
+    value = ctx[op.inputs[0].key]
+    is_tuple = isinstance(value, tuple)
+    frames = _partials_of(value)
+    R = int(op.shuffle_size)
+    mapper_index = ctx.get_current_chunk().index
+    # frames sharing their index are hashed and split together (reference hashes once per distinct index)
+    groups: List[List[int]] = []
+    for i, f in enumerate(frames):
+        for g in groups:
+            if frames[g[0]].same_index(f):
+                g.append(i)
+                break
+        else:
+            groups.append([i])
+    blocks: List[List[Optional[DeviceFrame]]] = [[None] * len(frames) for _ in range(R)]
+    for g in groups:
+        base = frames[g[0]]
+        pid = _kernels.partition_ids(base.index, R)
+        cols = list(base.index)
+        for i in g:
+            cols.extend(frames[i].data)
+        outs, offsets = _kernels.partition_scatter(pid, R, cols)
+        nk = len(base.index)
+        for r in range(R):
+            a, b = offsets[r], offsets[r + 1]
+            keys_r = [t[a:b] for t in outs[:nk]]
+            pos = nk
+            for i in g:
+                ncol = len(frames[i].columns)
+                blocks[r][i] = DeviceFrame(frames[i].index_names, keys_r, frames[i].columns,
+                                           [t[a:b] for t in outs[pos:pos + ncol]], b - a)
+                pos += ncol
+    for r in range(R):
+        reducer_index = (r, chunk.index[1]) if getattr(op, "is_dataframe_obj", True) else (r,)
+        if is_tuple:
+            ctx[chunk.key, reducer_index] = (mapper_index, tuple(blocks[r]) + (False,))
+        else:
+            ctx[chunk.key, reducer_index] = (mapper_index, blocks[r][0])
+
+
+def _concat_frames(frames: Sequence[DeviceFrame], shared_keys=None) -> DeviceFrame:
+    first = frames[0]
+    keys = shared_keys
+    if keys is None and first.index is not None:
+        keys = [_kernels.concat_columns([f.index[j] for f in frames]) for j in range(len(first.index))]
+    data = [_kernels.concat_columns([f.data[j] for f in frames]) for j in range(len(first.columns))]
+    return DeviceFrame(first.index_names, keys, first.columns, data, sum(len(f) for f in frames))
+
+
+def _concat_partial_tuples(items: Sequence[Sequence[DeviceFrame]]) -> Tuple[DeviceFrame, ...]:
+    """slot-wise row concatenation of partial tuples; slots that share their index keep sharing it."""
+    n_slots = len(items[0])
+    out: List[DeviceFrame] = []
+    for n in range(n_slots):
+        shared = None
+        for m in range(n):
+            if all(it[m].same_index(it[n]) for it in items):
+                shared = out[m].index
+                break
+        out.append(_concat_frames([it[n] for it in items], shared_keys=shared))
+    return tuple(out)
+
+
+def _execute_shuffle_reduce(ctx, op):
+    """stage=reduce: gather mapper blocks ordered by mapper index, concat slot-wise
+    (reference: execute_reduce, groupby/core.py:437-485)."""
+    chunk = op.outputs[0]
+    input_idx_to_df = dict(op.iter_mapper_data(ctx))
+    res = [input_idx_to_df[i] for i in sorted(input_idx_to_df.keys()) if input_idx_to_df[i] is not None]
+    if isinstance(res[0], tuple):
+        if res[0][-1]:
+            raise NotImplementedError("deliver_by shuffles are outside the agg path")
+        items = [[_as_device_frame(v, index_as_keys=True) for v in it[:-1]] for it in res]
+        r: Any = _concat_partial_tuples(items)
+        if chunk.index_value is not None and getattr(chunk.index_value, "name", None) is not None:
+            for f in r:
+                if len(f.index_names) == 1:
+                    f.index_names = [chunk.index_value.name]
+    else:
+        r = _concat_frames([_as_device_frame(v, index_as_keys=True) for v in res])
+    ctx[chunk.key] = r
+
+
+def execute_groupby_operand(ctx, op):
+    st = _stage(op)
+    if st == "map":
+        _execute_shuffle_map(ctx, op)
+    elif st == "reduce":
+        _execute_shuffle_reduce(ctx, op)
+    else:
+        raise NotImplementedError("plain groupby objects (apply/transform) are outside the GPU agg path")
+
+
+# ----------------------------------------------------------------------------------------------------
+# concat / data movement
+# ----------------------------------------------------------------------------------------------------
+def execute_concat(ctx, op):
+    """tuple branch of DataFrameConcat.execute (merge/concat.py:339-348): tree glue between levels."""
+    inputs = [ctx[c.key] for c in op.inputs]
+    if not inputs or not isinstance(inputs[0], tuple):
+        raise NotImplementedError("DataFrameConcat of plain frames stays on the reference executor")
+    items = [_partials_of(v) for v in inputs]
+    ctx[op.outputs[0].key] = _concat_partial_tuples(items)
+
+
+def execute_to_gpu(ctx, op):
+    ctx[op.outputs[0].key] = _as_device_frame(ctx[op.inputs[0].key])
+
+
+def execute_to_cpu(ctx, op):
+    v = ctx[op.inputs[0].key]
+    ctx[op.outputs[0].key] = v.to_pandas() if isinstance(v, DeviceFrame) else v
+
+
+def execute_datasource(ctx, op):
+    ctx[op.outputs[0].key] = op.data
+
+
+def register_gpu_executors():
+    """Install the GPU executors on the host-mirror operand classes."""
+    from . import dataframe as md
+
+    md.DataFrameGroupByAgg.register_executor(execute_groupby_agg)
+    md.DataFrameGroupByOperand.register_executor(execute_groupby_operand)
+    md.DataFrameConcat.register_executor(execute_concat)
+    md.DataFrameToGPU.register_executor(execute_to_gpu)
+    md.DataFrameToCPU.register_executor(execute_to_cpu)
+    md.DataFrameDataSource.register_executor(execute_datasource)

@@ -1,0 +1,243 @@
+"""Tensor-level wrappers over the C ABI (include/mgb.h).  PyTorch is used for allocation and streams only.
+
+Every function takes CUDA tensors (int64 keys; float64 / int64 values), passes raw device pointers and the
+current CUDA stream to libmarsgb.so and returns freshly allocated CUDA tensors.  Nothing here computes on
+the CPU: a non-CUDA tensor raises ``MarsGBError`` (no fallback path exists).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import F64, I64, SUM, SUMSQ, COUNT, MIN, MAX, MarsGBError, check  # noqa: F401
+
+# number of libmarsgb kernel launches issued through this module (bench.py reports it as gpu_launches)
+launch_counter = 0
+
+
+def _count(n):
+    global launch_counter
+    launch_counter += n
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _req(t: torch.Tensor, what: str, dtypes=(torch.int64, torch.float64)) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise MarsGBError(1, f"{what}: expected a torch.Tensor, got {type(t).__name__}")
+    if not t.is_cuda:
+        raise MarsGBError(2, f"{what}: tensor lives on {t.device}; the groupby path runs on CUDA only "
+                             f"(no CPU fallback)")
+    if t.dtype not in dtypes:
+        raise MarsGBError(3, f"{what}: dtype {t.dtype} not supported (need one of {dtypes})")
+    if t.dim() != 1:
+        raise MarsGBError(1, f"{what}: expected a 1-D column, got shape {tuple(t.shape)}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def dtype_code(t: torch.Tensor) -> int:
+    return F64 if t.dtype == torch.float64 else I64
+
+
+def _ptrs(ts: Sequence[torch.Tensor]):
+    return _lib.ptr_array([t.data_ptr() for t in ts])
+
+
+def device_info() -> Tuple[int, int]:
+    lib = _lib.load()
+    a, b = C.c_int32(), C.c_int32()
+    check(lib.mgb_device_info(C.byref(a), C.byref(b)))
+    return a.value, b.value
+
+
+# ---------------------------------------------------------------------------------------------- hashing
+def hash_keys(keys: Sequence[torch.Tensor]) -> torch.Tensor:
+    """uint64 pandas hash of each key tuple, returned as the int64 bit pattern (mgb_hash_keys)."""
+    lib = _lib.load()
+    keys = [_req(k, f"key {i}", (torch.int64,)) for i, k in enumerate(keys)]
+    n = keys[0].numel()
+    out = torch.empty(n, dtype=torch.int64, device=keys[0].device)
+    check(lib.mgb_hash_keys(_ptrs(keys), len(keys), n, out.data_ptr(), _stream()))
+    _count(1 if n else 0)
+    return out
+
+
+def partition_ids(keys: Sequence[torch.Tensor], n_partitions: int) -> torch.Tensor:
+    """int32 reducer index `hash % n_partitions` per row (mgb_partition_ids)."""
+    lib = _lib.load()
+    keys = [_req(k, f"key {i}", (torch.int64,)) for i, k in enumerate(keys)]
+    n = keys[0].numel()
+    out = torch.empty(n, dtype=torch.int32, device=keys[0].device)
+    check(lib.mgb_partition_ids(_ptrs(keys), len(keys), n, int(n_partitions), out.data_ptr(), _stream()))
+    _count(1 if n else 0)
+    return out
+
+
+def partition_scatter(pid: torch.Tensor, n_partitions: int, cols: Sequence[torch.Tensor]):
+    """Stable split of rows into per-partition blocks.  Returns (out_cols, offsets) with offsets a host
+    list of n_partitions+1 ints (one small device->host copy)."""
+    lib = _lib.load()
+    pid = _req(pid, "pid", (torch.int32,))
+    cols = [_req(c, f"column {i}") for i, c in enumerate(cols)]
+    n = pid.numel()
+    dev = pid.device
+    outs = [torch.empty_like(c) for c in cols]
+    offsets = torch.empty(n_partitions + 1, dtype=torch.int64, device=dev)
+    check(lib.mgb_partition_scatter(pid.data_ptr(), n, int(n_partitions), _ptrs(cols), _ptrs(outs), len(cols),
+                                    offsets.data_ptr(), _stream()))
+    _count(7 if n else 1)
+    return outs, offsets.cpu().tolist()
+
+
+# ------------------------------------------------------------------------------------------ aggregation
+class Aggregator:
+    """Streaming hash aggregation: update() any number of row batches, then result()."""
+
+    def __init__(self, n_keys: int, val_dtypes: Sequence[int], accs: Sequence[Tuple[int, int]]):
+        self._lib = _lib.load()
+        self.n_keys = n_keys
+        self.val_dtypes = list(val_dtypes)
+        self.accs = list(accs)
+        self._spec = _lib.make_spec(n_keys, self.val_dtypes, self.accs)
+        self._h = C.c_void_p()
+        self._keep = []  # batches must stay alive until finalize
+        self._device = None
+        self.stats = None
+        check(self._lib.mgb_agg_create(C.byref(self._h), C.byref(self._spec), _stream()))
+
+    def update(self, keys: Sequence[torch.Tensor], vals: Sequence[torch.Tensor]):
+        keys = [_req(k, f"key {i}", (torch.int64,)) for i, k in enumerate(keys)]
+        vals = [_req(v, f"value {i}") for i, v in enumerate(vals)]
+        if len(keys) != self.n_keys or len(vals) != len(self.val_dtypes):
+            raise MarsGBError(1, "column count does not match the aggregator spec")
+        for i, v in enumerate(vals):
+            if dtype_code(v) != self.val_dtypes[i]:
+                raise MarsGBError(1, f"value column {i} dtype {v.dtype} does not match the spec")
+            if v.numel() != keys[0].numel():
+                raise MarsGBError(1, "ragged batch: columns differ in length")
+        self._device = keys[0].device
+        n = keys[0].numel()
+        # one update() handles < 2^31 rows; larger batches are split here
+        step = (1 << 31) - 1024
+        for r0 in range(0, n, step):
+            ks = [k[r0:r0 + step] for k in keys]
+            vs = [v[r0:r0 + step] for v in vals]
+            self._keep.append((ks, vs))
+            check(self._lib.mgb_agg_update(self._h, _ptrs(ks), _ptrs(vs), ks[0].numel()))
+        return self
+
+    def result(self, sort: bool = False, device=None):
+        """-> (key tensors, accumulator tensors)."""
+        g = C.c_int64()
+        check(self._lib.mgb_agg_finalize(self._h, C.byref(g)))
+        self._keep.clear()
+        G = g.value
+        dev = self._device or device or torch.device("cuda", torch.cuda.current_device())
+        keys = [torch.empty(G, dtype=torch.int64, device=dev) for _ in range(self.n_keys)]
+        accs = []
+        for col, op in self.accs:
+            dt = torch.int64 if (op == COUNT or self.val_dtypes[col] == I64) else torch.float64
+            accs.append(torch.empty(G, dtype=dt, device=dev))
+        check(self._lib.mgb_agg_emit(self._h, _ptrs(keys), _ptrs(accs), 1 if sort else 0))
+        st = (C.c_int64 * 6)()
+        check(self._lib.mgb_agg_stats(self._h, st))
+        self.stats = dict(rows_tiny=st[0], rows_smem=st[1], rows_spilled=st[2], partial_rows=st[3],
+                          table_capacity=st[4], launches=st[5])
+        _count(st[5])
+        return keys, accs
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.mgb_agg_destroy(self._h)
+            self._h = C.c_void_p()
+        self._keep = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+
+def groupby_aggregate(keys, vals, accs, sort=False):
+    """One-shot: (key tensors, accumulator tensors, stats)."""
+    agg = Aggregator(len(keys), [dtype_code(v) for v in vals], accs)
+    try:
+        agg.update(keys, vals)
+        k, a = agg.result(sort=sort, device=keys[0].device)
+        return k, a, agg.stats
+    finally:
+        agg.close()
+
+
+# ------------------------------------------------------------------------------------------------- post
+def post_mean(s: torch.Tensor, c: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    s, c = _req(s, "sum"), _req(c, "count", (torch.int64,))
+    out = torch.empty(s.numel(), dtype=torch.float64, device=s.device)
+    check(lib.mgb_post_mean(s.data_ptr(), dtype_code(s), c.data_ptr(), out.data_ptr(), s.numel(), _stream()))
+    _count(1 if s.numel() else 0)
+    return out
+
+
+def post_var(s: torch.Tensor, q: torch.Tensor, c: torch.Tensor, ddof: int = 1) -> torch.Tensor:
+    lib = _lib.load()
+    s, q, c = _req(s, "sum"), _req(q, "sum of squares"), _req(c, "count", (torch.int64,))
+    if s.dtype != q.dtype:
+        raise MarsGBError(1, "sum and sum-of-squares must share a dtype")
+    out = torch.empty(s.numel(), dtype=torch.float64, device=s.device)
+    check(lib.mgb_post_var(s.data_ptr(), q.data_ptr(), dtype_code(s), c.data_ptr(), int(ddof), out.data_ptr(),
+                           s.numel(), _stream()))
+    _count(1 if s.numel() else 0)
+    return out
+
+
+# ----------------------------------------------------------------------------------------- concat / sort
+def concat_columns(pieces: Sequence[torch.Tensor]) -> torch.Tensor:
+    """Row-wise concatenation of one column's pieces with device-to-device copies (mgb_copy_rows)."""
+    lib = _lib.load()
+    pieces = [_req(p, "piece") for p in pieces]
+    if len(pieces) == 1:
+        return pieces[0]
+    total = sum(p.numel() for p in pieces)
+    out = torch.empty(total, dtype=pieces[0].dtype, device=pieces[0].device)
+    off = 0
+    for p in pieces:
+        if p.dtype != out.dtype:
+            raise MarsGBError(1, "concat: pieces differ in dtype")
+        check(lib.mgb_copy_rows(out.data_ptr(), off, p.data_ptr(), p.numel(), _stream()))
+        off += p.numel()
+    return out
+
+
+def argsort_keys(keys: Sequence[torch.Tensor]) -> torch.Tensor:
+    lib = _lib.load()
+    keys = [_req(k, f"key {i}", (torch.int64,)) for i, k in enumerate(keys)]
+    n = keys[0].numel()
+    perm = torch.empty(n, dtype=torch.int32, device=keys[0].device)
+    check(lib.mgb_argsort_keys(_ptrs(keys), len(keys), n, perm.data_ptr(), _stream()))
+    _count(4 * 8 * len(keys) if n else 0)
+    return perm
+
+
+def gather_rows(cols: Sequence[torch.Tensor], perm: torch.Tensor) -> List[torch.Tensor]:
+    lib = _lib.load()
+    cols = [_req(c, f"column {i}") for i, c in enumerate(cols)]
+    perm = _req(perm, "perm", (torch.int32,))
+    n = perm.numel()
+    outs = [torch.empty(n, dtype=c.dtype, device=c.device) for c in cols]
+    check(lib.mgb_gather_rows(_ptrs(cols), _ptrs(outs), len(cols), perm.data_ptr(), n, _stream()))
+    _count(1 if n and cols else 0)
+    return outs
+
+
+def bench_atomics(mode: int, n_rows: int, n_slots: int, iters: int = 5) -> float:
+    lib = _lib.load()
+    ms = C.c_float()
+    check(lib.mgb_bench_atomics(mode, n_rows, n_slots, iters, C.byref(ms), _stream()))
+    return ms.value

@@ -1,0 +1,281 @@
+"""Multi-GPU plumbing for the shuffle: one process per GPU, partials stay in HBM.
+
+``Exchange.shuffle`` replaces the storage-service transport between DataFrameGroupByOperand map and reduce
+(mapper blocks `ctx[(mapper_key, reducer_index)]`, mars/core/operand/shuffle.py:111-130): every rank packs the
+blocks of its mapper chunks by destination rank and one grouped ncclSend/ncclRecv all-to-all
+(``mgb_comm_alltoallv``) moves all columns; the receiver re-inserts the blocks under the same ctx keys, so
+the reduce executor is unchanged.  Block sizes travel through a small host-side all-gather (the 8x8 count
+matrix of section 8e).  ``torch.distributed`` is used for rendezvous and host metadata only.
+
+The byte mover is a *transport* object: ``NcclTransport`` (product) drives libmarsgb's NCCL exchange; tests
+substitute a gloo transport to exercise the host logic with world_size 2 on CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import glob
+import os
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from ._lib import MarsGBError, check
+from .device import DeviceFrame
+
+
+def _find_libnccl() -> Optional[str]:
+    """The NCCL torch was built against (nvidia/nccl wheel), else the system one."""
+    try:
+        import nvidia.nccl  # type: ignore
+
+        for root in list(nvidia.nccl.__path__):
+            hits = sorted(glob.glob(os.path.join(root, "lib", "libnccl.so*")))
+            if hits:
+                return hits[0]
+    except Exception:  # noqa: BLE001
+        pass
+    return None
+
+
+class NcclTransport:
+    """grouped ncclSend/ncclRecv all-to-all through libmarsgb (mgb_comm_alltoallv)."""
+
+    def __init__(self, rank: int, world: int, meta_group=None):
+        self.rank, self.world = rank, world
+        self._lib = _lib.load()
+        path = _find_libnccl()
+        check(self._lib.mgb_nccl_load(path.encode() if path else None))
+        uid = (C.c_uint8 * 128)()
+        if rank == 0:
+            check(self._lib.mgb_comm_unique_id(uid))
+        box = [bytes(uid)]
+        dist.broadcast_object_list(box, src=0, group=meta_group)
+        uid = (C.c_uint8 * 128).from_buffer_copy(box[0])
+        self._comm = C.c_void_p()
+        check(self._lib.mgb_comm_init(C.byref(self._comm), uid, rank, world))
+        self.bytes_sent = 0
+
+    def alltoallv(self, send_cols: Sequence[torch.Tensor], send_off: Sequence[int], recv_off: Sequence[int]):
+        dev = torch.device("cuda", torch.cuda.current_device())
+        recv_cols = []
+        for c in send_cols:
+            if not c.is_cuda:
+                raise MarsGBError(2, "NCCL exchange needs CUDA tensors")
+            recv_cols.append(torch.empty(recv_off[-1], dtype=c.dtype, device=dev))
+        so = (C.c_int64 * (self.world + 1))(*send_off)
+        ro = (C.c_int64 * (self.world + 1))(*recv_off)
+        sp = _lib.ptr_array([c.data_ptr() for c in send_cols])
+        rp = _lib.ptr_array([c.data_ptr() for c in recv_cols])
+        check(self._lib.mgb_comm_alltoallv(self._comm, sp, so, rp, ro, len(send_cols),
+                                           torch.cuda.current_stream().cuda_stream))
+        own = send_off[self.rank + 1] - send_off[self.rank]
+        self.bytes_sent += 8 * len(send_cols) * (send_off[-1] - own)
+        return recv_cols
+
+    def close(self):
+        if self._comm:
+            self._lib.mgb_comm_destroy(self._comm)
+            self._comm = C.c_void_p()
+
+
+def _concat(pieces: List[torch.Tensor], like: torch.Tensor) -> torch.Tensor:
+    pieces = [p for p in pieces if p.numel()]
+    if not pieces:
+        return like[:0]
+    if like.is_cuda:
+        from . import kernels
+
+        return kernels.concat_columns(pieces)
+    return torch.cat(pieces)  # CPU tensors only occur in host-logic tests (gloo transport)
+
+
+class Exchange:
+    def __init__(self, transport, rank: int, world: int, meta_group=None):
+        self.transport = transport
+        self.rank, self.world = rank, world
+        self.meta_group = meta_group
+        self.shuffle_rows_sent = 0
+
+    # ------------------------------------------------------------------------------------------ helpers
+    def _gather_meta(self, obj):
+        out = [None] * self.world
+        dist.all_gather_object(out, obj, group=self.meta_group)
+        return out
+
+    @staticmethod
+    def _payload_frames(payload) -> Tuple[List[DeviceFrame], bool]:
+        if isinstance(payload, tuple):
+            return [f for f in payload if isinstance(f, DeviceFrame)], True
+        return [payload], False
+
+    @staticmethod
+    def _schema(frames: List[DeviceFrame]):
+        return dict(index_names=frames[0].index_names, nk=len(frames[0].index),
+                    slots=[(f.columns, [str(t.dtype) for t in f.data]) for f in frames])
+
+    @staticmethod
+    def _flatten(frames: List[DeviceFrame]) -> List[torch.Tensor]:
+        for f in frames[1:]:
+            if not frames[0].same_index(f):
+                raise NotImplementedError("exchange expects the partial frames of one block to share their index")
+        cols = list(frames[0].index)
+        for f in frames:
+            cols.extend(f.data)
+        return cols
+
+    @staticmethod
+    def _rebuild(schema, cols: List[torch.Tensor], a: int, b: int, as_tuple: bool):
+        nk = schema["nk"]
+        keys = [t[a:b] for t in cols[:nk]]
+        frames, pos = [], nk
+        for columns, _ in schema["slots"]:
+            frames.append(DeviceFrame(schema["index_names"], keys, columns, [t[a:b] for t in cols[pos:pos + len(columns)]],
+                                      b - a))
+            pos += len(columns)
+        return tuple(frames) + (False,) if as_tuple else frames[0]
+
+    # ------------------------------------------------------------------------------------------ shuffle
+    def shuffle(self, ctx, proxy_chunk, owners: Dict[str, int]):
+        mappers = list(proxy_chunk.op.inputs)
+        R = int(mappers[0].op.shuffle_size)
+        local = [i for i, m in enumerate(mappers) if owners[m.key] == self.rank]
+        dest = lambda r: r % self.world  # noqa: E731  reducer placement, must match Session._owner
+        counts, schema, as_tuple = {}, None, True
+        for i in local:
+            m = mappers[i]
+            for r in range(R):
+                _, payload = ctx[(m.key, (r, m.index[1] if len(m.index) > 1 else 0))]
+                frames, as_tuple = self._payload_frames(payload)
+                counts[(i, r)] = len(frames[0])
+                if schema is None:
+                    schema = self._schema(frames)
+        metas = self._gather_meta(dict(counts=counts, schema=schema, as_tuple=as_tuple))
+        all_counts = {}
+        for m_ in metas:
+            all_counts.update(m_["counts"])
+            if schema is None and m_["schema"] is not None:
+                schema, as_tuple = m_["schema"], m_["as_tuple"]
+        if schema is None:
+            return
+        owner_of_mapper = [owners[m.key] for m in mappers]
+        ncols = schema["nk"] + sum(len(c) for c, _ in schema["slots"])
+        # pack: for destination p, reducers r (r % P == p) ascending, local mappers ascending
+        pieces: List[List[torch.Tensor]] = [[] for _ in range(ncols)]
+        send_off = [0]
+        template: Optional[List[torch.Tensor]] = None
+        for p in range(self.world):
+            n = 0
+            if p != self.rank:
+                for r in range(R):
+                    if dest(r) != p:
+                        continue
+                    for i in local:
+                        m = mappers[i]
+                        key = (m.key, (r, m.index[1] if len(m.index) > 1 else 0))
+                        frames, _ = self._payload_frames(ctx[key][1])
+                        cols = self._flatten(frames)
+                        template = template or cols
+                        for j, t in enumerate(cols):
+                            pieces[j].append(t)
+                        n += len(frames[0])
+                        del ctx[key]
+            send_off.append(send_off[-1] + n)
+        if template is None:
+            # nothing to send: still need typed empty columns
+            dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else "cpu"
+            template = [torch.empty(0, dtype=torch.int64, device=dev) for _ in range(schema["nk"])]
+            for columns, dts in schema["slots"]:
+                template += [torch.empty(0, dtype=getattr(torch, d.replace("torch.", "")), device=dev) for d in dts]
+        send_cols = [_concat(pieces[j], template[j]) for j in range(ncols)]
+        recv_off = [0]
+        for q in range(self.world):
+            n = 0
+            if q != self.rank:
+                for r in range(R):
+                    if dest(r) != self.rank:
+                        continue
+                    for i, m in enumerate(mappers):
+                        if owner_of_mapper[i] == q:
+                            n += all_counts[(i, r)]
+            recv_off.append(recv_off[-1] + n)
+        recv_cols = self.transport.alltoallv(send_cols, send_off, recv_off)
+        self.shuffle_rows_sent += send_off[-1]
+        # unpack
+        for q in range(self.world):
+            if q == self.rank:
+                continue
+            pos = recv_off[q]
+            for r in range(R):
+                if dest(r) != self.rank:
+                    continue
+                for i, m in enumerate(mappers):
+                    if owner_of_mapper[i] != q:
+                        continue
+                    n = all_counts[(i, r)]
+                    key = (m.key, (r, m.index[1] if len(m.index) > 1 else 0))
+                    ctx[key] = (m.index, self._rebuild(schema, recv_cols, pos, pos + n, as_tuple))
+                    pos += n
+
+    # ------------------------------------------------------------------------------- point-to-point fetch
+    def transfer(self, ctx, key, src: int, dst: int):
+        """Move ctx[key] (a tuple of partial frames) from rank src to rank dst (tree branch gather)."""
+        box = [None]
+        if self.rank == src:
+            frames, as_tuple = self._payload_frames(ctx[key])
+            box = [dict(schema=self._schema(frames), n=len(frames[0]), as_tuple=as_tuple)]
+        dist.broadcast_object_list(box, src=src, group=self.meta_group)
+        meta = box[0]
+        if self.rank not in (src, dst):
+            return
+        n = meta["n"]
+        send_off = [0] * (self.world + 1)
+        recv_off = [0] * (self.world + 1)
+        if self.rank == src:
+            cols = self._flatten(self._payload_frames(ctx[key])[0])
+            for p in range(dst + 1, self.world + 1):
+                send_off[p] = n
+        else:
+            dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else "cpu"
+            cols = [torch.empty(0, dtype=torch.int64, device=dev) for _ in range(meta["schema"]["nk"])]
+            for columns, dts in meta["schema"]["slots"]:
+                cols += [torch.empty(0, dtype=getattr(torch, d.replace("torch.", "")), device=dev) for d in dts]
+            for p in range(src + 1, self.world + 1):
+                recv_off[p] = n
+        recv = self.transport.alltoallv(cols, send_off, recv_off)
+        if self.rank == dst:
+            v = self._rebuild(meta["schema"], recv, 0, n, meta["as_tuple"])
+            if meta["as_tuple"]:
+                v = v[:-1]  # partial tuples outside the shuffle carry no deliver_by flag
+            ctx[key] = v
+
+    def fetch_result(self, obj, owner: int):
+        box = [obj if self.rank == owner else None]
+        dist.broadcast_object_list(box, src=owner, group=self.meta_group)
+        return box[0]
+
+    def sync_size_recorders(self, chunks):
+        from .dataframe import SizeRecorder
+
+        names = sorted({c.op.size_recorder_name for c in chunks if getattr(c.op, "size_recorder_name", None)})
+        for name in names:
+            rec = SizeRecorder.lookup(name)
+            metas = self._gather_meta((list(rec._raw), list(rec._agg)))
+            rec._raw = [x for m in metas for x in m[0]]
+            rec._agg = [x for m in metas for x in m[1]]
+
+
+def init_exchange(backend: Optional[str] = None) -> Exchange:
+    """Create the exchange for this process from the torchrun environment (RANK / WORLD_SIZE / LOCAL_RANK,
+    MASTER_ADDR / MASTER_PORT).  One process per GPU."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    if torch.cuda.is_available():
+        torch.cuda.set_device(local % torch.cuda.device_count())
+    if not dist.is_initialized():
+        dist.init_process_group(backend=backend or "gloo", rank=rank, world_size=world)
+    meta_group = None  # default group is gloo: host metadata only; bytes move through libmarsgb + NCCL
+    transport = NcclTransport(rank, world, meta_group)
+    return Exchange(transport, rank, world, meta_group)
