@@ -1,0 +1,395 @@
+#!/usr/bin/env python
+"""bench.py -- groupby-agg rows/s on the TPC-H-Q1-shaped config (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A *step* is one pass of the hot path over the whole batch: the Q1-shaped lineitem frame (SF10 cardinality,
+59,986,052 rows per GPU, chunk_size 2^22 -> 15 row chunks) goes through
+`df.groupby(['returnflag','linestatus']).agg({...q01...})` tiled exactly like the reference tiles it
+(DataFrameGroupByAgg map per chunk -> concat/combine tree -> agg) and every chunk operand is executed through
+the registered `fn(ctx, op)` executors, which call libmarsgb.so through the C ABI.
+
+  value   rows/s with the chunks already resident in HBM (DeviceFrame data source)
+  e2e     rows/s with HOST (pinned) chunks: per step H2D of every chunk (DataFrameToGPU) and D2H of the result
+          frame are inside the timed region
+  roofline  dominant kernel (map-side pre-aggregation): algorithmic bytes (64 B/row) / its CUDA-event time
+  cpu_baseline  the oracle port of the reference's pandas path on a bounded sample, all host cores
+
+N > 1 (torchrun): weak scaling -- every rank owns its own 15 chunks (chunk c of rank r is global chunk
+15 r + c); map + local tree are independent per rank; the per-rank partial tuples (4 groups) are gathered to
+rank 0 with the NCCL exchange and the final agg stage runs there.  No other data-path collective.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED = 20240229
+ROWS_PER_GPU = 59_986_052
+CHUNK_ROWS = 1 << 22
+BY = ["returnflag", "linestatus"]
+COLUMNS = ["returnflag", "linestatus", "quantity", "extendedprice", "discount", "disc_price", "charge", "orderkey"]
+Q1_FUNC = {"quantity": ["sum", "mean"], "extendedprice": ["sum", "mean"], "disc_price": ["sum"],
+           "charge": ["sum"], "discount": ["mean"], "orderkey": ["count"]}
+BYTES_PER_ROW = 8 * len(COLUMNS)          # every input column read once: 64 B/row
+L2_BYTES = 126 << 20
+
+
+def gen_chunk(global_chunk_index: int, rows: int) -> dict:
+    """Q1-shaped synthetic lineitem chunk, numpy default_rng(seed + chunk)."""
+    rng = np.random.default_rng(SEED + global_chunk_index)
+    grp = rng.choice(4, size=rows, p=[0.2466, 0.0006, 0.5063, 0.2465])      # AF, NF, NO, RF
+    returnflag = np.array([0, 1, 1, 2], dtype=np.int64)[grp]
+    linestatus = np.array([0, 0, 1, 0], dtype=np.int64)[grp]
+    quantity = rng.integers(1, 51, rows).astype(np.float64)
+    price = rng.uniform(900.0, 105000.0, rows)
+    discount = rng.integers(0, 11, rows) / 100.0
+    tax = rng.integers(0, 9, rows) / 100.0
+    disc_price = price * (1.0 - discount)
+    charge = disc_price * (1.0 + tax)
+    orderkey = rng.integers(1, 60_000_000, rows, dtype=np.int64)
+    return dict(returnflag=returnflag, linestatus=linestatus, quantity=quantity, extendedprice=price,
+                discount=discount, disc_price=disc_price, charge=charge, orderkey=orderkey)
+
+
+def chunk_sizes(total_rows: int, chunk_rows: int):
+    return [min(chunk_rows, total_rows - s) for s in range(0, total_rows, chunk_rows)]
+
+
+# ----------------------------------------------------------------------------------------------------
+# CPU arm: oracle port of the reference's pandas path (bounded sample, all host cores)
+# ----------------------------------------------------------------------------------------------------
+_CPU_CHUNKS = None
+
+
+def _cpu_map(i):
+    import pandas as pd
+    import mars_groupby_oracle as orc
+
+    return orc.agg_map(pd.DataFrame(_CPU_CHUNKS[i], copy=False), BY, Q1_FUNC)
+
+
+def cpu_path(n_chunks: int, rows: int, steps: int, warmup: int, cores: int):
+    """map stage fanned out over `cores` processes (one chunk per task, what Mars does with n_cpu bands),
+    concat / combine tree / agg in the parent.  Returns (rows/s, seconds per step list)."""
+    global _CPU_CHUNKS
+    import multiprocessing as mp
+    import pandas as pd
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import mars_groupby_oracle as orc
+
+    _CPU_CHUNKS = [gen_chunk(i, rows) for i in range(n_chunks)]
+    ctx = mp.get_context("fork")
+    times = []
+    with ctx.Pool(cores) as pool:
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            level = pool.map(_cpu_map, range(n_chunks), chunksize=1)
+            while len(level) > 4:
+                level = [orc.agg_combine(orc.concat_partials(level[i:i + 4]), Q1_FUNC) if len(level[i:i + 4]) > 1
+                         else orc.agg_combine(level[i], Q1_FUNC) for i in range(0, len(level), 4)]
+            cat = level[0] if len(level) == 1 else orc.concat_partials(level)
+            res = orc.agg_agg(cat, Q1_FUNC, sort=True)
+            dt = time.perf_counter() - t0
+            if it >= warmup:
+                times.append(dt)
+            assert len(res) >= 1
+    _CPU_CHUNKS = None
+    total_rows = n_chunks * rows
+    return total_rows * len(times) / sum(times), times
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_chunks = max(2, min(15, cores))
+    steps, warmup = args.steps, min(args.warmup, 1)
+    rps, times = cpu_path(n_chunks, args.chunk_rows, steps, warmup, cores)
+    sample = f"{n_chunks} chunks x {args.chunk_rows} rows of the Q1-shaped workload per step, map stage on {cores} processes"
+    line = {
+        "impl": "reference", "metric": "groupby-agg rows/s", "value": rps, "unit": "rows/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * sum(times) / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": rps, "unit": "rows/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": rps, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": "TPC-H Q1-shaped synthetic lineitem (BASELINE.json configs[1]): groupby(returnflag, "
+                        "linestatus) sum/mean/count, 2 int64 keys + 5 float64 + 1 int64 value columns",
+            "rows_per_gpu": args.rows, "chunk_rows": args.chunk_rows, "chunks_per_gpu": len(chunk_sizes(args.rows, args.chunk_rows)),
+            "groups": 4, "method": "tree (auto)", "bytes_per_row": BYTES_PER_ROW,
+            "l2": "inputs larger than L2 (%.2f GB per step per GPU)" % (args.rows * BYTES_PER_ROW / 1e9),
+            "parallelism": f"dp{world} (row chunks sharded, weak)"}
+
+
+# ----------------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.idx = device_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=open(self.path, "w"),
+                                         stderr=subprocess.DEVNULL)
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for ln in open(self.path):
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:  # noqa: BLE001
+            pass
+        if sm:
+            # under load = samples in the upper half of the observed range
+            out["sm_mhz"] = statistics.median(sm)
+            out["sm_max_mhz"] = max(mx)
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# ----------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------
+def main_ours(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    # CPU baseline first (rank 0, N=1 only): it forks worker processes, which must happen before CUDA starts
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        n_chunks = max(2, min(8, cores))
+        rps, times = cpu_path(n_chunks, args.chunk_rows, 2, 1, cores)
+        cpu_baseline = {"value": rps, "unit": "rows/s", "cores": cores, "kind": "port",
+                        "sample": f"{n_chunks} chunks x {args.chunk_rows} rows per step, 2 steps after 1 warm-up, "
+                                  f"oracle port (pandas) of the reference operands, map stage on {cores} processes; "
+                                  f"{sum(times):.1f} s"}
+
+    import pandas as pd
+    import torch
+    import torch.distributed as dist
+
+    import mars_b200 as md
+    from mars_b200 import _lib, kernels
+    from mars_b200.device import DeviceFrame
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    exchange = None
+    if world > 1:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    lib = _lib.load()
+
+    sizes = chunk_sizes(args.rows, args.chunk_rows)
+    n_chunks = len(sizes)
+    rows_rank = sum(sizes)
+
+    # host chunks in pinned memory (one flat pinned tensor per chunk, columns are views) -> pandas frames
+    host_frames, dev_frames = [], []
+    for c, rows in enumerate(sizes):
+        cols = gen_chunk(rank * n_chunks + c, rows)
+        flat = torch.empty((len(COLUMNS), rows), dtype=torch.int64).pin_memory()
+        data = {}
+        for j, name in enumerate(COLUMNS):
+            view = flat[j].numpy().view(cols[name].dtype)
+            view[:] = cols[name]
+            data[name] = view
+        host_frames.append(pd.DataFrame(data, copy=False))
+        dev_frames.append(DeviceFrame([], None, COLUMNS, [
+            flat[j].to(dev, non_blocking=True).view(torch.float64 if cols[n_].dtype == np.float64 else torch.int64)
+            for j, n_ in enumerate(COLUMNS)], rows))
+        del cols
+    torch.cuda.synchronize()
+    h2d_bytes = rows_rank * BYTES_PER_ROW
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def finish_cross_rank(partials):
+        """weak-scaling tail: per-rank partial tuples (<= 4 groups) -> rank 0 -> final agg there"""
+        raise NotImplementedError
+
+    def step(resident: bool):
+        frames = dev_frames if resident else host_frames
+        mdf = md.DataFrame.from_chunks(frames)
+        if not resident:
+            mdf = mdf.to_gpu()
+        sess = md.new_session(default=False)
+        r = mdf.groupby(BY).agg(Q1_FUNC, method="auto")
+        if world == 1:
+            r.execute(session=sess)
+            out = r.fetch(session=sess)
+        else:
+            out = sess.execute_local_then_gather(r, dist, rank, world)
+        return out
+
+    def timed(resident: bool, steps: int, warmup: int):
+        for _ in range(warmup):
+            step(resident)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            out = step(resident)
+        e1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = e0.elapsed_time(e1)
+        # the result frame is fetched to the host inside every step, so device time ~ wall time; use the
+        # larger of the two so that host-side work after the last kernel is not hidden
+        ms = max(ms, wall * 1e3)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, out
+
+    # ---- e2e (host chunks) first, then the device-resident headline with clocks + per-kernel timing
+    ms_e2e, out_e2e = timed(False, max(1, min(args.steps, 3)), 1)
+    e2e_steps = max(1, min(args.steps, 3))
+
+    sampler = ClockSampler(local)
+    lib.mgb_prof_enable(1)
+    for _ in range(args.warmup):
+        step(True)
+    barrier()
+    lib.mgb_prof_reset()
+    launches0 = kernels.launch_counter
+    sampler.start()
+    ms, out = timed(True, args.steps, 0)
+    clocks = sampler.stop()
+    launches = kernels.launch_counter - launches0
+    import ctypes as C
+    prof = {}
+    for kid, name in enumerate(["preagg_tiny", "preagg_smem", "merge", "update_global", "table_init", "emit", "hash",
+                                "partition", "sort", "post"]):
+        tot, cnt = C.c_double(), C.c_int64()
+        lib.mgb_prof_read(kid, C.byref(tot), C.byref(cnt))
+        if cnt.value:
+            prof[name] = {"ms_total": tot.value, "launches": cnt.value}
+    lib.mgb_prof_enable(0)
+
+    if rank == 0:
+        # sanity: the two paths agree and the counts add up
+        assert out.shape == out_e2e.shape
+        total_rows = rows_rank * world
+        cnt_col = ("orderkey", "count")
+        assert int(out[cnt_col].sum()) == total_rows, (int(out[cnt_col].sum()), total_rows)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:  # noqa: BLE001
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        dom = prof.get("preagg_tiny") or prof.get("preagg_smem") or {"ms_total": float("nan"), "launches": 1}
+        per_launch_ms = dom["ms_total"] / dom["launches"]
+        rows_per_launch = rows_rank * args.steps / dom["launches"]
+        achieved = rows_per_launch * BYTES_PER_ROW / (per_launch_ms * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            except Exception:  # noqa: BLE001
+                traffic = None
+        value = total_rows * args.steps / (ms * 1e-3)
+        e2e_value = total_rows * e2e_steps / (ms_e2e * 1e-3)
+        line = {
+            "metric": "groupby-agg rows/s", "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, world),
+            "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": h2d_bytes * world,
+                    "d2h_bytes_per_step": int(out.shape[0] * (out.shape[1] + len(BY)) * 8),
+                    "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": "k_preagg_tiny" if "preagg_tiny" in prof else "k_preagg_smem",
+                         "kernel_ms_per_launch": per_launch_ms, "bytes_per_launch": rows_per_launch * BYTES_PER_ROW,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
+                         "step_hbm_frac": (rows_rank * BYTES_PER_ROW / (ms / args.steps * 1e-3) / 1e9) / peak},
+            "kernel_time_ms": prof,
+            "clocks": clocks,
+            "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows", type=int, default=ROWS_PER_GPU, help="rows per GPU (default: SF10 lineitem cardinality)")
+    ap.add_argument("--chunk-rows", type=int, default=CHUNK_ROWS)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        main_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -153,6 +153,27 @@ int mgb_comm_alltoallv(mgb_comm* comm, const void* const* send_cols, const int64
 int mgb_comm_allgather_i64(mgb_comm* comm, const int64_t* send, int64_t* recv, int64_t count, void* stream);
 int mgb_comm_destroy(mgb_comm* comm);
 
+/* ---- per-kernel device timing (bench.py roofline: CUDA events on the launching stream around each
+ * kernel of the timed region).  Off by default; enabling adds two cudaEventRecord per launch.          */
+typedef enum {
+  MGB_K_PREAGG_TINY = 0,  /* map-side pre-aggregation, privatised tiny-cardinality kernel */
+  MGB_K_PREAGG_SMEM = 1,  /* map-side pre-aggregation, shared-memory hash table kernel */
+  MGB_K_MERGE = 2,        /* partial rows -> global table (reduce-side merge) */
+  MGB_K_UPDATE_GLOBAL = 3,/* spilled raw rows -> global table */
+  MGB_K_TABLE_INIT = 4,
+  MGB_K_EMIT = 5,         /* table compaction (count, scan, write) */
+  MGB_K_HASH = 6,         /* key hash / partition id */
+  MGB_K_PARTITION = 7,    /* histogram + scan + scatter */
+  MGB_K_SORT = 8,         /* radix argsort + gather for sort=True */
+  MGB_K_POST = 9,
+  MGB_K_COUNT_ = 10
+} mgb_kernel_id;
+int mgb_prof_enable(int32_t on);
+int mgb_prof_reset(void);
+/* total device milliseconds and number of bracketed launches of kernel_id since the last reset
+ * (synchronises on the recorded events). */
+int mgb_prof_read(int32_t kernel_id, double* out_total_ms, int64_t* out_launches);
+
 /* ---- microbenchmarks used by profiles/ (not part of the operand path) -------------------------------- */
 int mgb_bench_atomics(int32_t mode, int64_t n_rows, int32_t n_slots, int32_t iters, float* out_ms,
                       void* stream);

@@ -81,6 +81,9 @@ SIGNATURES = {
     "mgb_comm_alltoallv": (C.c_int, [_vp, _pp, C.POINTER(_i64), _pp, C.POINTER(_i64), _i32, _vp]),
     "mgb_comm_allgather_i64": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
     "mgb_comm_destroy": (C.c_int, [_vp]),
+    "mgb_prof_enable": (C.c_int, [_i32]),
+    "mgb_prof_reset": (C.c_int, []),
+    "mgb_prof_read": (C.c_int, [_i32, C.POINTER(C.c_double), C.POINTER(_i64)]),
     "mgb_bench_atomics": (C.c_int, [_i32, _i64, _i32, _i32, C.POINTER(C.c_float), _vp]),
 }
 

@@ -950,6 +950,7 @@ extern "C" int mgb_agg_update(mgb_agg* a, const int64_t* const* key_cols, const 
     p.sticky_fail = a->sticky_fail;
     p.stg = u.tstg;
     size_t sm = (size_t)(MGB_MAX_KEYS * TINY_MAX_GC + (size_t)TINY_WARPS * GC * L.na * 32) * 8 + 64;
+    MgbProfScope prof(MGB_K_PREAGG_TINY, st);
 #define CALL(NK, NV)                                                               \
   MGB_TRY(set_smem(k_preagg_tiny<NK, NV>, sm));                                    \
   k_preagg_tiny<NK, NV><<<tiny_grid, TINY_WARPS * 32, sm, st>>>(p);
@@ -971,6 +972,7 @@ extern "C" int mgb_agg_update(mgb_agg* a, const int64_t* const* key_cols, const 
     p.inter_cap = u.inter_cap;
     p.miss = u.miss + (size_t)g * n_rows;
     size_t sm = (size_t)cap * (L.nk + (p.a1 - p.a0)) * 8 + 64;
+    MgbProfScope prof(MGB_K_PREAGG_SMEM, st);
 #define CALL(NK, NV)                                                               \
   MGB_TRY(set_smem(k_preagg_smem<NK, NV>, sm));                                    \
   k_preagg_smem<NK, NV><<<smem_grid, SMEM_THREADS, sm, st>>>(p);
@@ -1035,6 +1037,7 @@ extern "C" int mgb_agg_finalize(mgb_agg* a, int64_t* out_n_groups) {
   {
     long long words = (C + 1) * L.W;
     long long b = (words + 255) / 256, capb = (long long)a->sms * 16;
+    MgbProfScope prof(MGB_K_TABLE_INIT, st);
     k_table_init<<<(unsigned)(b > capb ? capb : b), 256, 0, st>>>(a->table, L, C + 1);
     MGB_CHECK_LAUNCH();
     a->stats[5]++;
@@ -1058,6 +1061,7 @@ extern "C" int mgb_agg_finalize(mgb_agg* a, int64_t* out_n_groups) {
     }
     if (m.n_rows > 0) {
       unsigned g = grid_rows(a, m.n_rows, GLOBAL_THREADS, 1);
+      MgbProfScope prof(MGB_K_MERGE, st);
       if (L.nk == 1)
         k_merge_staged<1><<<g, GLOBAL_THREADS, 0, st>>>(m);
       else
@@ -1081,6 +1085,7 @@ extern "C" int mgb_agg_finalize(mgb_agg* a, int64_t* out_n_groups) {
       p.gather = u.miss + (size_t)g * u.batch.n;
       p.n_rows = nm;
       unsigned grid = grid_rows(a, nm, GLOBAL_THREADS, GLOBAL_ROWS);
+      MgbProfScope prof(MGB_K_UPDATE_GLOBAL, st);
 #define CALL(NK, NV) k_update_global<NK, NV><<<grid, GLOBAL_THREADS, 0, st>>>(p);
       DISPATCH_NK_NV(L.nk, p.b.ncol, CALL);
 #undef CALL
@@ -1140,6 +1145,7 @@ extern "C" int mgb_agg_emit(mgb_agg* a, int64_t* const* out_key_cols, void* cons
   }
   const long long slots = a->C + 1;
   const long long tiles = (slots + EMIT_THREADS - 1) / EMIT_THREADS;
+  MgbProfScope prof(MGB_K_EMIT, st);
   int64_t* tile_counts = nullptr;
   MGB_CUDA(cudaMallocAsync((void**)&tile_counts, sizeof(int64_t) * tiles, st));
   if (L.nk == 1)

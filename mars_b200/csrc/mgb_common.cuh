@@ -47,6 +47,24 @@ void mgb_set_error(const char* fmt, ...);
 int mgb_sm_count();
 
 // ----------------------------------------------------------------------------------------------------
+// per-kernel device timing (mgb_prof_*): when enabled, every launch site brackets its kernel with two CUDA
+// events on the launching stream; mgb_prof_read sums the elapsed times per kernel id.
+// ----------------------------------------------------------------------------------------------------
+bool mgb_prof_on();
+void mgb_prof_record(int kernel_id, cudaStream_t st, bool begin);
+struct MgbProfScope {
+  int id;
+  cudaStream_t st;
+  bool on;
+  MgbProfScope(int id_, cudaStream_t st_) : id(id_), st(st_), on(mgb_prof_on()) {
+    if (on) mgb_prof_record(id, st, true);
+  }
+  ~MgbProfScope() {
+    if (on) mgb_prof_record(id, st, false);
+  }
+};
+
+// ----------------------------------------------------------------------------------------------------
 // pandas-exact hashing (pandas/core/util/hashing.py: _hash_ndarray tail, combine_hash_arrays), as used by
 // the reference's hash_dataframe_on (mars/dataframe/utils.py:77-101).
 // ----------------------------------------------------------------------------------------------------

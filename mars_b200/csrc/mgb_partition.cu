@@ -288,6 +288,7 @@ extern "C" int mgb_argsort_keys(const int64_t* const* key_cols, int32_t n_keys, 
               (long long)n_rows);
   if (n_rows == 0) return MGB_OK;
   MGB_REQUIRE(key_cols && out_perm, MGB_ERR_INVALID, "null pointer");
+  MgbProfScope prof(MGB_K_SORT, (cudaStream_t)stream);
   return mgb_radix_sort_perm_keys(key_cols, n_keys, n_rows, out_perm, (cudaStream_t)stream);
 }
 
@@ -305,6 +306,7 @@ extern "C" int mgb_partition_scatter(const int32_t* pid, int64_t n_rows, int32_t
     MGB_CUDA(cudaMemsetAsync(out_offsets, 0, sizeof(int64_t) * ((size_t)n_partitions + 1), st));
     return MGB_OK;
   }
+  MgbProfScope prof(MGB_K_PARTITION, st);
   int32_t* perm = nullptr;
   MGB_CUDA(cudaMallocAsync((void**)&perm, sizeof(int32_t) * n_rows, st));
   int status = mgb_radix_sort_perm_pid(pid, n_rows, n_partitions, perm, out_offsets, st);

@@ -42,6 +42,85 @@ extern "C" int mgb_device_info(int32_t* sm_count, int32_t* cc) {
 }
 
 // ----------------------------------------------------------------------------------------------------
+// per-kernel device timing
+// ----------------------------------------------------------------------------------------------------
+#include <mutex>
+#include <vector>
+struct ProfRec {
+  int id;
+  cudaEvent_t e0, e1;
+};
+static bool g_prof_on = false;
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof_recs;
+static std::vector<cudaEvent_t> g_prof_pool;
+
+bool mgb_prof_on() { return g_prof_on; }
+
+static cudaEvent_t prof_event() {
+  if (!g_prof_pool.empty()) {
+    cudaEvent_t e = g_prof_pool.back();
+    g_prof_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+
+void mgb_prof_record(int kernel_id, cudaStream_t st, bool begin) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (begin) {
+    ProfRec r{kernel_id, prof_event(), nullptr};
+    if (r.e0) cudaEventRecord(r.e0, st);
+    g_prof_recs.push_back(r);
+  } else {
+    for (size_t i = g_prof_recs.size(); i-- > 0;) {
+      ProfRec& r = g_prof_recs[i];
+      if (r.id == kernel_id && r.e1 == nullptr) {
+        r.e1 = prof_event();
+        if (r.e1) cudaEventRecord(r.e1, st);
+        break;
+      }
+    }
+  }
+}
+
+extern "C" int mgb_prof_enable(int32_t on) {
+  g_prof_on = on != 0;
+  return MGB_OK;
+}
+
+extern "C" int mgb_prof_reset(void) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (auto& r : g_prof_recs) {
+    if (r.e0) g_prof_pool.push_back(r.e0);
+    if (r.e1) g_prof_pool.push_back(r.e1);
+  }
+  g_prof_recs.clear();
+  return MGB_OK;
+}
+
+extern "C" int mgb_prof_read(int32_t kernel_id, double* out_total_ms, int64_t* out_launches) {
+  MGB_REQUIRE(out_total_ms && out_launches, MGB_ERR_INVALID, "null pointer");
+  MGB_REQUIRE(kernel_id >= 0 && kernel_id < MGB_K_COUNT_, MGB_ERR_INVALID, "kernel id %d", kernel_id);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  double total = 0;
+  int64_t n = 0;
+  for (auto& r : g_prof_recs) {
+    if (r.id != kernel_id || !r.e0 || !r.e1) continue;
+    MGB_CUDA(cudaEventSynchronize(r.e1));
+    float ms = 0;
+    MGB_CUDA(cudaEventElapsedTime(&ms, r.e0, r.e1));
+    total += ms;
+    ++n;
+  }
+  *out_total_ms = total;
+  *out_launches = n;
+  return MGB_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------
 // exclusive scan (int64), three-phase: per-block scan of SCAN_TILE elements, scan of block totals by a
 // single block, add-back.  Used by the partition histogram, radix sort and table compaction.
 // ----------------------------------------------------------------------------------------------------
@@ -180,6 +259,7 @@ static int launch_hash(const int64_t* const* key_cols, int32_t n_keys, int64_t n
   int64_t cap = (int64_t)mgb_sm_count() * 16;
   if (blocks > cap) blocks = cap;
   const bool pid = out_pid != nullptr;
+  MgbProfScope prof(MGB_K_HASH, st);
 #define L(NK)                                                                                   \
   if (pid)                                                                                      \
     k_hash<NK, true><<<(unsigned)blocks, 256, 0, st>>>(kc, n, R, out_hash, out_pid);            \
@@ -252,6 +332,7 @@ extern "C" int mgb_post_mean(const void* sum, int32_t sum_dtype, const int64_t* 
   MGB_REQUIRE(n >= 0, MGB_ERR_INVALID, "negative n");
   if (n == 0) return MGB_OK;
   MGB_REQUIRE(sum && count && out, MGB_ERR_INVALID, "null pointer");
+  MgbProfScope prof(MGB_K_POST, (cudaStream_t)stream);
   k_post_mean<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(sum, sum_dtype, count, out, n);
   MGB_CHECK_LAUNCH();
   return MGB_OK;
@@ -262,6 +343,7 @@ extern "C" int mgb_post_var(const void* sum, const void* sumsq, int32_t sum_dtyp
   MGB_REQUIRE(n >= 0, MGB_ERR_INVALID, "negative n");
   if (n == 0) return MGB_OK;
   MGB_REQUIRE(sum && sumsq && count && out, MGB_ERR_INVALID, "null pointer");
+  MgbProfScope prof(MGB_K_POST, (cudaStream_t)stream);
   k_post_var<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(sum, sumsq, sum_dtype, count, ddof, out, n);
   MGB_CHECK_LAUNCH();
   return MGB_OK;

@@ -332,6 +332,34 @@ class DataFrame:
         if gpu:
             self.data = self.to_gpu().data
 
+    @classmethod
+    def from_chunks(cls, chunks, gpu: Optional[bool] = None) -> "DataFrame":
+        """Lazy frame over row chunks that already exist -- pandas frames in host memory (then ``.to_gpu()``
+        inserts the H2D step) or ``DeviceFrame`` objects already resident in HBM (what a GPU band's chunk
+        store hands to the processor, processor.py:147-175).  No data is copied or sliced."""
+        from .device import DeviceFrame
+
+        first = chunks[0]
+        resident = isinstance(first, DeviceFrame)
+        if gpu is None:
+            gpu = resident
+        dtypes = first.dtypes
+        columns = pd.Index(list(first.columns))
+        n = sum(len(c) for c in chunks)
+        op = DataFrameDataSource(gpu=gpu)
+        t = op.new_tileable([], shape=(n, len(columns)), dtypes=dtypes, index_value=IndexValue(pd.RangeIndex(n)),
+                            columns_value=IndexValue(columns))
+        out, start = [], 0
+        for i, piece in enumerate(chunks):
+            cop = DataFrameDataSource(gpu=gpu, data=piece)
+            out.append(cop.new_chunk([], shape=(len(piece), len(columns)), index=(i, 0), dtypes=dtypes,
+                                     index_value=IndexValue(pd.RangeIndex(start, start + len(piece))),
+                                     columns_value=IndexValue(columns)))
+            start += len(piece)
+        t.chunks = out
+        t.nsplits = (tuple(c.shape[0] for c in out), (len(columns),))
+        return cls(None, _tileable=t)
+
     # metadata passthrough
     @property
     def shape(self):
@@ -419,7 +447,13 @@ class DataFrameGroupBy:
         """schema inference by running real pandas on a small mock frame (reference: build_mock_agg_result,
         aggregation.py:142-161)"""
         dtypes = self.df.dtypes
-        mock = pd.DataFrame({c: np.arange(1, 5).astype(dt) for c, dt in dtypes.items()})
+        def mock_col(dt):
+            try:
+                return np.arange(1, 5).astype(dt)
+            except (TypeError, ValueError):
+                return pd.Series(list("abcd")).astype(dt)
+
+        mock = pd.DataFrame({c: mock_col(dt) for c, dt in dtypes.items()})
         g = mock.groupby(self.by, as_index=self.as_index, sort=self.sort)
         if self.selection is not None:
             g = g[self.selection]

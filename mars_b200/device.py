@@ -16,6 +16,20 @@ import pandas as pd
 import torch
 
 
+def _to_device(arr: np.ndarray, device) -> torch.Tensor:
+    """H2D copy of one 8-byte column (pandas hands out read-only views; torch wants writable memory)."""
+    arr = np.ascontiguousarray(arr)
+    if not arr.flags.writeable:
+        # pandas hands out read-only views of the column; the copy below only reads, so re-flag the view
+        # instead of copying the chunk on the host
+        try:
+            arr = arr.view()
+            arr.flags.writeable = True
+        except ValueError:
+            arr = arr.copy()
+    return torch.from_numpy(arr).to(device, non_blocking=True)
+
+
 class DeviceFrame:
     __slots__ = ("index_names", "index", "columns", "data", "_n")
 
@@ -98,8 +112,7 @@ class DeviceFrame:
             else:
                 raise NotImplementedError(f"column {name!r} has dtype {arr.dtype}: the GPU groupby path handles "
                                           f"float64 and int64 columns")
-            t = torch.from_numpy(np.ascontiguousarray(arr))
-            data.append(t.to(device, non_blocking=True))
+            data.append(_to_device(arr, device))
             cols.append(name)
         index = None
         names: List[Any] = []
@@ -113,7 +126,7 @@ class DeviceFrame:
             for lv in levels:
                 if lv.dtype != np.int64:
                     raise NotImplementedError(f"group key dtype {lv.dtype}: int64 keys only")
-                index.append(torch.from_numpy(np.ascontiguousarray(lv)).to(device, non_blocking=True))
+                index.append(_to_device(lv, device))
         return cls(names, index, cols, data, len(df))
 
     def to_pandas(self) -> pd.DataFrame:

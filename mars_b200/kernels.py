@@ -24,6 +24,8 @@ def _count(n):
 
 
 def _stream() -> int:
+    if not torch.cuda.is_available():
+        raise MarsGBError(2, "no CUDA device: the groupby path runs on the GPU only (no CPU fallback)")
     return torch.cuda.current_stream().cuda_stream
 
 

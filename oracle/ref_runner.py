@@ -76,8 +76,16 @@ def run_reference(raw, by, func, chunk_size, method="tree", sort=True, as_index=
             before = set(ctx.keys())
             execute(ctx, c.op)
             new_keys = [k for k in ctx.keys() if k not in before]
+            step_keys = None
+            if getattr(c.op, "agg_funcs", None) and getattr(c.op, "pre_funcs", None):
+                # slot order of the partial tuple is the (hash-seed dependent) order of op.agg_funcs: name
+                # every slot "<map func>_<identity|square>" so fixtures do not depend on it
+                ident = {p.output_key for p in c.op.pre_funcs if p.input_key == p.output_key}
+                step_keys = [f"{a.map_func_name}_{'identity' if a.input_key in ident else 'square'}"
+                             for a in c.op.agg_funcs]
             records.append(
                 dict(
+                    step_keys=step_keys,
                     op=type(c.op).__name__,
                     stage=None if c.op.stage is None else OperandStage(c.op.stage).name,
                     index=tuple(c.index) if c.index is not None else None,

@@ -1,0 +1,242 @@
+"""GPU parity tests of the individual C-ABI entry points (include/mgb.h) against the oracle."""
+from __future__ import annotations
+
+import numpy as np
+import pandas as pd
+import pytest
+import torch
+
+import mars_groupby_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def K(cuda_device):
+    from mars_b200 import kernels
+
+    sms, cc = kernels.device_info()
+    assert cc >= 100, f"sm_100a library on compute capability {cc}"
+    return kernels
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+# ------------------------------------------------------------------------------------------------ hash
+def test_hash_known_answers(K):
+    # SURVEY.md Appendix C (pandas docstring / installed pandas)
+    h = K.hash_keys([dev(np.array([1, 2, 3], dtype=np.int64))]).cpu().numpy().view(np.uint64)
+    assert h.tolist() == [6238072747940578789, 15839785061582574730, 2185194620014831856]
+    h = K.hash_keys([dev(np.array([0, -1, 2 ** 63 - 1, -2 ** 63], dtype=np.int64))]).cpu().numpy().view(np.uint64)
+    assert h.tolist() == [0, 13029008266876403067, 6514504133438201533, 2720858781877447050]
+    h = K.hash_keys([dev(np.array([1, 2, 3], dtype=np.int64)), dev(np.array([10, 20, 30], dtype=np.int64))])
+    assert h.cpu().numpy().view(np.uint64).tolist() == [912933651372556365, 2058288944137990103,
+                                                         1448569499672317777]
+    pid = K.partition_ids([dev(np.array([1, 2, 3], dtype=np.int64))], 8).cpu().numpy()
+    assert pid.tolist() == [5, 2, 0]
+
+
+@pytest.mark.parametrize("n_keys", [1, 2])
+@pytest.mark.parametrize("n", [0, 1, 1000, 1 << 20])
+def test_hash_matches_pandas_and_oracle(K, n_keys, n):
+    rng = np.random.default_rng(n + n_keys)
+    cols = [rng.integers(-2 ** 63, 2 ** 63 - 1, n, dtype=np.int64) for _ in range(n_keys)]
+    got = K.hash_keys([dev(c) for c in cols]).cpu().numpy().view(np.uint64)
+    np.testing.assert_array_equal(got, orc.hash_keys(cols))
+    if n:
+        idx = pd.Index(cols[0]) if n_keys == 1 else pd.MultiIndex.from_arrays(cols)
+        exp = pd.util.hash_pandas_object(idx, categorize=False).to_numpy()
+        np.testing.assert_array_equal(got, exp)
+    for R in (1, 3, 8, 64, 1000):
+        pid = K.partition_ids([dev(c) for c in cols], R).cpu().numpy()
+        np.testing.assert_array_equal(pid, orc.partition_ids(cols, R))
+
+
+# ------------------------------------------------------------------------------------------- partition
+@pytest.mark.parametrize("n,R", [(0, 4), (1, 1), (5000, 7), (100000, 64), (300000, 256), (200000, 1000),
+                                 (1 << 20, 2)])
+def test_partition_scatter_is_stable_split(K, n, R):
+    rng = np.random.default_rng(n * 31 + R)
+    keys = rng.integers(0, max(n // 3, 1) + 1, n, dtype=np.int64)
+    vals = rng.random(n)
+    ivals = rng.integers(-5, 5, n, dtype=np.int64)
+    pid = orc.partition_ids([keys], R).astype(np.int32)
+    outs, offsets = K.partition_scatter(dev(pid), R, [dev(keys), dev(vals), dev(ivals)])
+    order = np.argsort(pid, kind="stable")
+    exp_off = np.searchsorted(pid[order], np.arange(R + 1)).tolist()
+    assert offsets == exp_off
+    np.testing.assert_array_equal(outs[0].cpu().numpy(), keys[order])
+    np.testing.assert_array_equal(outs[1].cpu().numpy(), vals[order])
+    np.testing.assert_array_equal(outs[2].cpu().numpy(), ivals[order])
+
+
+# ----------------------------------------------------------------------------------------- aggregation
+ALL_OPS = ["sum", "sumsq", "count", "min", "max"]
+
+
+def pandas_agg(keys, vals, accs):
+    """expected accumulators via pandas at the reference's call sites (groupby(...).agg)"""
+    df = pd.DataFrame({f"k{j}": k for j, k in enumerate(keys)})
+    for i, v in enumerate(vals):
+        df[f"v{i}"] = v
+    g = df.groupby([f"k{j}" for j in range(len(keys))], sort=True)
+    out = []
+    for col, op in accs:
+        s = g[f"v{col}"]
+        if op == "sumsq":
+            d2 = df.copy()
+            d2[f"v{col}"] = d2[f"v{col}"] ** 2
+            r = d2.groupby([f"k{j}" for j in range(len(keys))], sort=True)[f"v{col}"].sum()
+        else:
+            r = getattr(s, op)()
+        out.append(r)
+    idx = out[0].index
+    key_arrays = [idx.get_level_values(j).to_numpy() for j in range(idx.nlevels)]
+    return key_arrays, [r.to_numpy() for r in out]
+
+
+def run_agg(K, keys, vals, accs, sort=True, batches=1):
+    code = dict(sum=K.SUM, sumsq=K.SUMSQ, count=K.COUNT, min=K.MIN, max=K.MAX)
+    agg = K.Aggregator(len(keys), [K.F64 if v.dtype == np.float64 else K.I64 for v in vals],
+                       [(c, code[o]) for c, o in accs])
+    n = len(keys[0])
+    bounds = np.linspace(0, n, batches + 1).astype(int)
+    for b in range(batches):
+        s, e = bounds[b], bounds[b + 1]
+        agg.update([dev(k[s:e]) for k in keys], [dev(v[s:e]) for v in vals])
+    k, a = agg.result(sort=sort)
+    stats = agg.stats
+    agg.close()
+    return [t.cpu().numpy() for t in k], [t.cpu().numpy() for t in a], stats
+
+
+def check_agg(K, keys, vals, accs, batches=1, expect_path=None):
+    gk, ga, stats = run_agg(K, keys, vals, accs, sort=True, batches=batches)
+    ek, ea = pandas_agg(keys, vals, accs)
+    for a, b in zip(gk, ek):
+        np.testing.assert_array_equal(a, b)
+    for (col, op), a, b in zip(accs, ga, ea):
+        if op in ("count", "min", "max") or b.dtype.kind in "iu":
+            np.testing.assert_array_equal(a, b.astype(a.dtype), err_msg=f"{op} of column {col}")
+        else:
+            np.testing.assert_allclose(a, b, rtol=1e-9, atol=0, equal_nan=True, err_msg=f"{op} of column {col}")
+    if expect_path is not None:
+        assert stats[expect_path] > 0, stats
+    # unsorted emit returns the same rows in table order
+    uk, ua, _ = run_agg(K, keys, vals, accs, sort=False, batches=batches)
+    order = np.lexsort(tuple(reversed(uk)))
+    for a, b in zip(uk, gk):
+        np.testing.assert_array_equal(a[order], b)
+    for a, b in zip(ua, ga):
+        if a.dtype.kind in "iu":
+            np.testing.assert_array_equal(a[order], b)
+        else:
+            np.testing.assert_allclose(a[order], b, rtol=1e-12, equal_nan=True)
+    return stats
+
+
+@pytest.mark.parametrize("n_keys", [1, 2])
+@pytest.mark.parametrize("n,card,path", [
+    (1, 1, None), (1000, 3, "rows_tiny"), (200000, 4, "rows_tiny"), (200000, 1000, "rows_smem"),
+    (500000, 50000, None), (300000, 300000, None)])
+def test_aggregate_matches_pandas(K, n_keys, n, card, path):
+    rng = np.random.default_rng(n + card + n_keys)
+    if n_keys == 1:
+        keys = [rng.integers(-(card // 2), card - card // 2, n, dtype=np.int64)]
+    else:
+        c1 = max(int(np.sqrt(card)), 1)
+        keys = [rng.integers(0, c1, n, dtype=np.int64), rng.integers(-3, max(card // c1, 1) - 3, n, dtype=np.int64)]
+    vals = [rng.normal(10, 3, n), rng.random(n), rng.integers(-100, 100, n, dtype=np.int64)]
+    accs = [(0, o) for o in ALL_OPS] + [(1, "sum"), (1, "count"), (2, "sum"), (2, "min"), (2, "max"), (2, "count")]
+    check_agg(K, keys, vals, accs, expect_path=path)
+
+
+def test_aggregate_many_batches_and_wide(K):
+    rng = np.random.default_rng(5)
+    n = 120000
+    keys = [rng.integers(0, 300, n, dtype=np.int64)]
+    vals = [rng.normal(10, 3, n) for _ in range(11)]      # > 8 value columns: two column groups
+    accs = [(c, o) for c in range(11) for o in ("sum", "min", "max")]
+    check_agg(K, keys, vals, accs, batches=5)
+
+
+def test_aggregate_nan_and_marker_keys(K):
+    rng = np.random.default_rng(6)
+    n = 50000
+    keys = [rng.choice(np.array([0, -1, 2 ** 63 - 1, -2 ** 63, 7, 1 << 40], dtype=np.int64), n)]
+    v0 = rng.random(n)
+    v0[rng.random(n) < 0.3] = np.nan
+    v1 = rng.normal(0, 1, n)
+    v1[keys[0] == 7] = np.nan
+    accs = [(0, o) for o in ALL_OPS] + [(1, o) for o in ALL_OPS]
+    check_agg(K, keys, [v0, v1], accs)
+    # two keys, both equal to the empty marker (INT64_MIN)
+    k1 = rng.choice(np.array([-2 ** 63, 0, 5], dtype=np.int64), n)
+    k2 = rng.choice(np.array([-2 ** 63, 1], dtype=np.int64), n)
+    check_agg(K, [k1, k2], [v0, v1], accs)
+    # many distinct keys including the marker -> global table path
+    k = rng.integers(-2 ** 63, 2 ** 63 - 1, n, dtype=np.int64)
+    k[::97] = -2 ** 63
+    check_agg(K, [k], [v0, v1], accs)
+
+
+def test_aggregate_skewed_keys(K):
+    rng = np.random.default_rng(7)
+    n = 400000
+    keys = [np.minimum(rng.zipf(1.2, n), 10 ** 8).astype(np.int64)]
+    vals = [rng.random(n)]
+    check_agg(K, keys, vals, [(0, "sum"), (0, "count")])
+
+
+def test_empty_aggregator(K):
+    agg = K.Aggregator(1, [K.F64], [(0, K.SUM)])
+    k, a = agg.result(sort=True)
+    assert k[0].numel() == 0 and a[0].numel() == 0
+    agg.close()
+
+
+# ------------------------------------------------------------------------------------------------ post
+def test_post_functions_follow_reference_operation_order(K):
+    rng = np.random.default_rng(8)
+    n = 10000
+    c = rng.integers(1, 50, n)
+    s = rng.normal(10, 3, n) * c
+    q = s * s / c + rng.random(n) * c
+    got = K.post_mean(dev(s), dev(c)).cpu().numpy()
+    np.testing.assert_array_equal(got, s / c)
+    for ddof in (1, 0):
+        got = K.post_var(dev(s), dev(q), dev(c), ddof).cpu().numpy()
+        exp = orc.post_var(pd.Series(q), pd.Series(s), pd.Series(c), ddof=ddof).to_numpy()
+        np.testing.assert_array_equal(got.view(np.int64), exp.view(np.int64))   # bit-exact: same op order, no FMA
+
+
+# ----------------------------------------------------------------------------------------- sort / concat
+@pytest.mark.parametrize("n_keys", [1, 2])
+def test_argsort_and_gather(K, n_keys):
+    rng = np.random.default_rng(9)
+    n = 70000
+    cols = [rng.integers(-2 ** 62, 2 ** 62, n, dtype=np.int64) if j == 0 else rng.integers(-4, 4, n, dtype=np.int64)
+            for j in range(n_keys)]
+    if n_keys == 2:
+        cols[0] = rng.integers(-50, 50, n, dtype=np.int64)
+    perm = K.argsort_keys([dev(c) for c in cols]).cpu().numpy()
+    exp = np.lexsort(tuple(reversed(cols)))
+    np.testing.assert_array_equal(perm, exp)      # LSD radix sort is stable, like lexsort
+    vals = rng.random(n)
+    out = K.gather_rows([dev(vals)], dev(perm.astype(np.int32)))[0].cpu().numpy()
+    np.testing.assert_array_equal(out, vals[exp])
+
+
+def test_concat_columns(K):
+    a, b, c = np.arange(5.0), np.arange(0.0), np.arange(7.0) * 2
+    out = K.concat_columns([dev(a), dev(b), dev(c)]).cpu().numpy()
+    np.testing.assert_array_equal(out, np.concatenate([a, b, c]))
+
+
+def test_cpu_tensor_is_rejected_loudly(K):
+    from mars_b200 import MarsGBError
+
+    with pytest.raises(MarsGBError):
+        K.hash_keys([torch.arange(4, dtype=torch.int64)])

@@ -1,0 +1,162 @@
+"""Host-side logic on CPU: tiling shapes, function decomposition, executor / session plumbing.
+
+The executors run against tests/fake_kernels.py (a CPU double of mars_b200.kernels) so that everything above
+the C ABI -- step planning, partial tuples, shuffle blocks incl. empty ones, tree concat, post step wiring,
+result frame labels / dtypes -- is checked against the reference's golden outputs without a GPU.  The CUDA
+kernels themselves are covered by the `-m gpu` tests."""
+from __future__ import annotations
+
+import numpy as np
+import pandas as pd
+import pytest
+import torch
+
+import fake_kernels
+import mars_groupby_oracle as orc
+from conftest import assert_frames_match, golden_names, load_golden
+
+
+@pytest.fixture()
+def md(monkeypatch):
+    import mars_b200 as m
+    from mars_b200 import executors
+
+    monkeypatch.setattr(executors, "_kernels", fake_kernels)
+    monkeypatch.setattr(executors, "_device", lambda: torch.device("cpu"))
+    return m
+
+
+def tile(md, t):
+    gen = type(t.op).tile(t.op)
+    try:
+        next(gen)
+    except StopIteration as stop:
+        return stop.value
+    raise AssertionError("unexpected yield")
+
+
+def op_names(chunks):
+    from mars_b200.core import build_chunk_graph
+
+    return [f"{type(c.op).__name__}:{getattr(c.op.stage, 'name', None)}" for c in build_chunk_graph(chunks)]
+
+
+# ---------------------------------------------------------------- tile shapes (reference test_groupby.py:97-192)
+def test_tree_tiling_shape(md):
+    raw = pd.DataFrame({"key": np.arange(100) % 7, "v": np.arange(100.0)})
+    r = md.DataFrame(raw, chunk_size=10).groupby("key").agg(["sum", "mean", "count"], method="tree")
+    t = tile(md, r.data)
+    names = op_names(t.chunks)
+    assert len(t.chunks) == 1 and t.chunks[0].op.stage.name == "agg"
+    assert names.count("DataFrameGroupByAgg:map") == 10
+    assert names.count("DataFrameGroupByAgg:combine") == 3      # 10 -> 3 -> 1 with combine_size 4
+    assert names.count("DataFrameConcat:None") == 4
+    agg_op = t.chunks[0].op
+    assert agg_op.groupby_params["level"] == [0] and "by" not in agg_op.groupby_params
+
+
+def test_hash_shuffle_tiling_shape(md):
+    raw = pd.DataFrame({"key": np.arange(100) % 7, "v": np.arange(100.0)})
+    r = md.DataFrame(raw, chunk_size=25).groupby("key", sort=False).agg(["sum"], method="shuffle")
+    t = tile(md, r.data)
+    names = op_names(t.chunks)
+    assert len(t.chunks) == 4
+    assert names.count("DataFrameGroupByOperand:map") == 4 and names.count("DataFrameGroupByOperand:reduce") == 4
+    assert names.count("DataFrameShuffleProxy:None") == 1
+    for c in t.chunks:
+        red = c.op.inputs[0].op
+        assert red.n_reducers == 4
+        assert all(m.op.shuffle_size == 4 for m in red.inputs[0].op.inputs)     # R == number of mapper chunks
+
+
+def test_sorted_shuffle_is_declared_out_of_scope(md):
+    raw = pd.DataFrame({"key": np.arange(100) % 7, "v": np.arange(100.0)})
+    r = md.DataFrame(raw, chunk_size=25).groupby("key", sort=True).agg(["sum"], method="shuffle")
+    with pytest.raises(NotImplementedError, match="PSRS"):
+        tile(md, r.data)
+
+
+def test_decomposition_matches_reference_compiler():
+    from mars_b200.reduction import compile_reduction
+
+    steps = compile_reduction([(None, f) for f in ["sum", "mean", "count", "min", "max", "var"]])
+    got = [(a.map_func_name, a.agg_func_name, p.func.kind) for a in steps.agg_funcs
+           for p in steps.pre_funcs if p.output_key == a.input_key]
+    # SURVEY.md Appendix A.3 (probed from ReductionCompiler): K = 5 atomic steps, count merges with SUM
+    assert sorted(got) == sorted([("sum", "sum", "identity"), ("count", "sum", "identity"), ("min", "min", "identity"),
+                                  ("max", "max", "identity"), ("sum", "sum", "square")])
+    var = [p for p in steps.post_funcs if p.func_name == "var"][0]
+    assert [k for k in var.input_keys] == ["agg_sum_square", "agg_sum_identity", "agg_count_identity"]
+    steps = compile_reduction([(None, f) for f in ["sum", "mean", "count"]])
+    assert len(steps.agg_funcs) == 2 and len(steps.pre_funcs) == 1
+
+
+# ------------------------------------------------------------------------------ full path through the double
+@pytest.mark.parametrize("name", golden_names())
+def test_executor_plumbing_reproduces_reference(md, name):
+    g = load_golden(name)
+    s = g.spec
+    sess = md.new_session(default=False)
+    r = md.DataFrame(g.raw, chunk_size=s["chunk_size"]).to_gpu().groupby(s["by"], sort=s["sort"]) \
+        .agg(s["func"], method=s["method"])
+    r.execute(session=sess)
+    got = r.fetch(session=sess)
+    assert_frames_match(got, g.result, sort_index=not s["sort"])
+    chunks = sorted(r.data.chunks, key=lambda c: c.index)
+    assert len(chunks) == len(g.chunk_results)
+    for c, exp in zip(chunks, g.chunk_results):
+        assert_frames_match(sess._results[c.key], exp, sort_index=not s["sort"])
+
+
+def test_auto_method_samples_then_decides(md):
+    rng = np.random.default_rng(0)
+    raw = pd.DataFrame({"key": rng.integers(0, 50, 4000), "v": rng.random(4000)})
+    sess = md.new_session(default=False)
+    r = md.DataFrame(raw, chunk_size=400).to_gpu().groupby("key").agg(["sum", "count"], method="auto")
+    r.execute(session=sess)
+    assert len(r.data.chunks) == 1                                   # small partials -> tree
+    assert_frames_match(r.fetch(session=sess), raw.groupby("key").agg(["sum", "count"]), sort_index=False)
+    # force the shuffle decision with a tiny store limit (reference test_groupby.py:172-192)
+    from mars_b200 import options
+    old = options.chunk_store_limit
+    options.chunk_store_limit = 64
+    try:
+        sess = md.new_session(default=False)
+        r = md.DataFrame(raw, chunk_size=400).to_gpu().groupby("key", sort=False).agg(["sum", "count"], method="auto")
+        r.execute(session=sess)
+        assert len(r.data.chunks) > 1
+        assert "DataFrameGroupByOperand:reduce" in sess.executed_ops
+        assert_frames_match(r.fetch(session=sess), raw.groupby("key").agg(["sum", "count"]), sort_index=True)
+    finally:
+        options.chunk_store_limit = old
+
+
+def test_shuffle_mapper_emits_every_reducer_block(md):
+    from mars_b200.core import ProcessorContext, build_chunk_graph, execute
+
+    raw = pd.DataFrame({"key": np.array([3, 3, 3, 3], dtype=np.int64), "v": np.arange(4.0)})
+    r = md.DataFrame(raw, chunk_size=1).to_gpu().groupby("key", sort=False).agg(["sum"], method="shuffle")
+    t = tile(md, r.data)
+    ctx = ProcessorContext()
+    for c in build_chunk_graph(t.chunks):
+        if type(c.op).__name__ == "DataFrameShuffleProxy":
+            break
+        ctx.set_current_chunk(c)
+        execute(ctx, c.op)
+    mappers = [c for c in build_chunk_graph(t.chunks) if type(c.op).__name__ == "DataFrameGroupByOperand"
+               and c.op.stage.name == "map"]
+    target = int(orc.partition_ids([np.array([3])], 4)[0])
+    for m in mappers:
+        for i in range(4):
+            idx, payload = ctx[(m.key, (i, 0))]           # all 4 blocks exist (shuffle.py:124-130)
+            assert idx == m.index and payload[-1] is False
+            assert len(payload[0]) == (1 if i == target else 0)
+
+
+def test_errors_wrap_into_execution_error(md):
+    from mars_b200 import ExecutionError
+
+    raw = pd.DataFrame({"key": ["a", "b"], "v": [1.0, 2.0]})
+    r = md.DataFrame(raw, chunk_size=1).to_gpu().groupby("key").agg(["sum"], method="tree")
+    with pytest.raises(ExecutionError):
+        r.execute(session=md.new_session(default=False))
