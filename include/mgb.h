@@ -108,6 +108,30 @@ int mgb_agg_destroy(mgb_agg* agg);
  * [4]=global table capacity, [5]=kernels launched by this aggregator so far.                            */
 int mgb_agg_stats(mgb_agg* agg, int64_t* stats6);
 
+/* Low-cardinality fast paths (one kernel launch + one 8-byte device->host read each).
+ *
+ * mgb_preagg_dense: stage=map pre-aggregation (aggregation.py:1043-1128) of ONE row batch whose distinct key
+ * tuples fit on chip (TPC-H Q1 shape).  Accumulators live in shared memory, privatised per warp and per
+ * lane; the last CTA merges the per-CTA partial rows.  Output columns need capacity mgb_dense_capacity()
+ * rows.  *out_n_groups = -1 means "not a dense shape" (too many groups / live columns): nothing was written
+ * and the caller uses mgb_agg_*.  int64 columns that are only counted are not read at all.
+ *
+ * mgb_merge_small: stage=combine / stage=agg re-aggregation (aggregation.py:1130-1267) of small partial
+ * tuples WITHOUT the concat copy of merge/concat.py:339-348: n_pieces partial blocks (piece i: piece_rows[i]
+ * rows, key columns piece_key_cols[i][0..n_keys), accumulator columns piece_acc_cols[i][0..n_accs)) are
+ * merged by a single CTA; acc_op is the merge op (MGB_SUM for sums and counts, MGB_MIN, MGB_MAX), val_dtype
+ * of acc_col gives the column dtype.  sort_keys != 0 orders the result by key tuple.  Output columns need
+ * capacity sum(piece_rows).  *out_n_groups = -1: more than MGB_SMALL_MAX_ROWS (2048) rows in total or more
+ * than 16 non-empty pieces -- use mgb_agg_*.                                                             */
+int mgb_dense_capacity(int64_t* out_rows);
+int mgb_preagg_dense(const mgb_agg_spec* spec, const int64_t* const* key_cols, const void* const* val_cols,
+                     int64_t n_rows, int64_t* const* out_key_cols, void* const* out_acc_cols,
+                     int64_t out_capacity, int64_t* out_n_groups, void* stream);
+int mgb_merge_small(const mgb_agg_spec* spec, int32_t n_pieces, const int64_t* piece_rows,
+                    const int64_t* const* const* piece_key_cols, const void* const* const* piece_acc_cols,
+                    int64_t* const* out_key_cols, void* const* out_acc_cols, int64_t out_capacity,
+                    int32_t sort_keys, int64_t* out_n_groups, void* stream);
+
 /* Host-buffer convenience used by the end-to-end path: key/value columns live in (pinned) host memory,
  * are streamed to the device in row blocks overlapped with the kernels, and the result is written to
  * host arrays with capacity max_groups.  Returns the number of groups through out_n_groups

@@ -10,7 +10,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmarsgb.so")
-SOURCES = ["mgb_util.cu", "mgb_partition.cu", "mgb_agg.cu", "mgb_nccl.cu", "mgb_host.cu"]
+SOURCES = ["mgb_util.cu", "mgb_partition.cu", "mgb_agg.cu", "mgb_dense.cu", "mgb_nccl.cu", "mgb_host.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

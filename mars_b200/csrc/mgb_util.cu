@@ -26,6 +26,14 @@ int mgb_sm_count() {
     int n = 0;
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
     cached[dev] = n;
+    // first use of this device: keep freed scratch in the stream-ordered pool instead of returning it to the
+    // driver at every synchronisation (the default threshold 0 makes each cudaMallocAsync a driver call)
+    cudaMemPool_t pool = nullptr;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess && pool) {
+      unsigned long long keep = ~0ULL;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
   }
   return cached[dev];
 }

@@ -145,3 +145,65 @@ class DeviceFrame:
     def __repr__(self):
         return (f"DeviceFrame(rows={self._n}, index={self.index_names if self.index is not None else 'range'}, "
                 f"columns={self.columns}, device={self.device})")
+
+
+class PiecewiseFrame:
+    """Row-wise concatenation of DeviceFrames that is NOT materialised: what the GPU executors return for
+    ``pd.concat(axis=0)`` of partial frames (DataFrameConcat tuple branch, merge/concat.py:339-348, and the
+    reducer's gather, groupby/core.py:457).  The consumer -- a combine / agg stage -- reads the pieces in
+    place, so the concat costs no kernel and no copy.  ``materialize()`` performs the real concatenation for
+    consumers that need one contiguous frame."""
+
+    __slots__ = ("pieces",)
+
+    def __init__(self, pieces: Sequence[DeviceFrame]):
+        flat: List[DeviceFrame] = []
+        for p in pieces:
+            flat.extend(p.pieces if isinstance(p, PiecewiseFrame) else [p])
+        self.pieces = flat
+
+    def __len__(self):
+        return sum(len(p) for p in self.pieces)
+
+    @property
+    def columns(self):
+        return self.pieces[0].columns
+
+    @property
+    def index_names(self):
+        return self.pieces[0].index_names
+
+    @property
+    def shape(self):
+        return (len(self), len(self.columns))
+
+    @property
+    def ndim(self):
+        return 2
+
+    @property
+    def dtypes(self):
+        return self.pieces[0].dtypes
+
+    @property
+    def nbytes(self):
+        return sum(p.nbytes for p in self.pieces)
+
+    def __sizeof__(self):
+        return 64 + self.nbytes
+
+    def materialize(self, concat_columns, shared_keys=None) -> DeviceFrame:
+        first = self.pieces[0]
+        if len(self.pieces) == 1:
+            return first
+        keys = shared_keys
+        if keys is None and first.index is not None:
+            keys = [concat_columns([f.index[j] for f in self.pieces]) for j in range(len(first.index))]
+        data = [concat_columns([f.data[j] for f in self.pieces]) for j in range(len(first.columns))]
+        return DeviceFrame(first.index_names, keys, first.columns, data, len(self))
+
+    def to_pandas(self) -> pd.DataFrame:
+        return pd.concat([p.to_pandas() for p in self.pieces], axis=0)
+
+    def __repr__(self):
+        return f"PiecewiseFrame(rows={len(self)}, pieces={len(self.pieces)}, columns={self.columns})"

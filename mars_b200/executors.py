@@ -26,7 +26,7 @@ import torch
 
 from . import kernels as K
 from ._lib import MarsGBError
-from .device import DeviceFrame
+from .device import DeviceFrame, PiecewiseFrame
 from .reduction import _DECOMP
 
 _OPCODE = {"sum": K.SUM, "count": K.COUNT, "min": K.MIN, "max": K.MAX}
@@ -35,6 +35,7 @@ _DECOMP_EXT = dict(_DECOMP, std=_DECOMP["var"])
 # the kernels module is looked up through this indirection so that host-logic tests can substitute a
 # recording double; the product never rebinds it.
 _kernels = K
+_dense_rejected = set()
 
 
 def _stage(op) -> Optional[str]:
@@ -198,7 +199,18 @@ def _execute_agg_map(ctx, op):
             code = K.SUMSQ
         for c in s.cols:
             accs.append((used.index(c), code))
-    out_keys, out_accs, stats = _kernels.groupby_aggregate(keys, vals, accs, sort=False)
+    # low-cardinality chunks take the one-launch dense path; a shape that did not fit is remembered so
+    # the following chunks of the same computation go straight to the general hash-table path
+    shape_key = (tuple(by), tuple(used), tuple(accs))
+    res = None
+    if shape_key not in _dense_rejected and hasattr(_kernels, "preagg_dense"):
+        res = _kernels.preagg_dense(keys, vals, accs)
+        if res is None:
+            _dense_rejected.add(shape_key)
+    if res is None:
+        out_keys, out_accs, _ = _kernels.groupby_aggregate(keys, vals, accs, sort=False)
+    else:
+        out_keys, out_accs = res
     frames, pos = [], 0
     for s in steps:
         frames.append(DeviceFrame(by, out_keys, s.cols, out_accs[pos:pos + len(s.cols)], int(out_keys[0].numel())))
@@ -218,63 +230,93 @@ def _record_sizes(ctx, name, raw_size, agg_size):
     SizeRecorder.lookup(name).record(raw_size, agg_size)
 
 
-def _merge_partials(frames: Sequence[DeviceFrame], steps: Sequence[_Step], sort: bool) -> List[DeviceFrame]:
+def _merge_partials(slots: Sequence[Sequence[DeviceFrame]], steps: Sequence[_Step], sort: bool) -> List[DeviceFrame]:
     """Re-aggregate partial frames slot-wise: slot k -> groupby(level).agg(agg_func_k)
-    (reference: _execute_combine, aggregation.py:1130-1164; count partials are SUMmed as int64)."""
-    if len(frames) != len(steps):
-        raise MarsGBError(1, f"{len(frames)} partial frames for {len(steps)} aggregation steps")
-    first = frames[0]
-    shared = all(first.same_index(f) for f in frames[1:])
+    (reference: _execute_combine, aggregation.py:1130-1164; count partials are SUMmed as int64).
+    ``slots[k]`` lists the pieces of slot k (a virtual concat: the pieces are read in place)."""
+    if len(slots) != len(steps):
+        raise MarsGBError(1, f"{len(slots)} partial frames for {len(steps)} aggregation steps")
+    n_pieces = len(slots[0])
+    first = slots[0]
+    shared = all(len(sl) == n_pieces and all(first[i].same_index(sl[i]) for i in range(n_pieces))
+                 for sl in slots[1:])
     groups: List[List[int]] = []
     if shared:
         cur, width = [], 0
-        for i, f in enumerate(frames):
-            if cur and width + len(f.columns) > 64:
+        for i, sl in enumerate(slots):
+            if cur and width + len(sl[0].columns) > 64:
                 groups.append(cur)
                 cur, width = [], 0
             cur.append(i)
-            width += len(f.columns)
+            width += len(sl[0].columns)
         groups.append(cur)
     else:
-        groups = [[i] for i in range(len(frames))]
+        groups = [[i] for i in range(len(slots))]
     force_sort = sort or len(groups) > 1
-    out: List[Optional[DeviceFrame]] = [None] * len(frames)
+    out: List[Optional[DeviceFrame]] = [None] * len(slots)
     for grp in groups:
-        base = frames[grp[0]]
-        vals, accs = [], []
-        for i in grp:
-            code = _OPCODE[steps[i].agg_func]
-            for t in frames[i].data:
-                accs.append((len(vals), code))
-                vals.append(t)
-        k, a, _ = _kernels.groupby_aggregate(base.index, vals, accs, sort=force_sort)
+        base = slots[grp[0]]
+        pieces = [i for i in range(len(base)) if len(base[i]) > 0] or [0]
+        ops = [_OPCODE[steps[i].agg_func] for i in grp for _ in slots[i][0].columns]
+        res = None
+        if hasattr(_kernels, "merge_small") and sum(len(base[i]) for i in pieces) <= 2048 and len(pieces) <= 16:
+            res = _kernels.merge_small([base[i].index for i in pieces],
+                                       [[t for s in grp for t in slots[s][i].data] for i in pieces], ops, sort=force_sort)
+        if res is None:
+            first_vals = [t for s in grp for t in slots[s][pieces[0]].data]
+            agg = _kernels.Aggregator(len(base[0].index), [_kernels.dtype_code(t) for t in first_vals],
+                                      list(enumerate(ops)))
+            try:
+                for i in pieces:
+                    agg.update(base[i].index, [t for s in grp for t in slots[s][i].data])
+                res = agg.result(sort=force_sort, device=base[0].device)
+            finally:
+                agg.close()
+        k, a = res
         pos = 0
         for i in grp:
-            ncol = len(frames[i].columns)
-            out[i] = DeviceFrame(base.index_names, k, frames[i].columns, a[pos:pos + ncol], int(k[0].numel()))
+            ncol = len(slots[i][0].columns)
+            out[i] = DeviceFrame(base[0].index_names, k, slots[i][0].columns, a[pos:pos + ncol], int(k[0].numel()))
             pos += ncol
     return out  # type: ignore[return-value]
 
 
-def _partials_of(value) -> List[DeviceFrame]:
+def _pieces_of(value) -> List[List[DeviceFrame]]:
+    """partial tuple -> per slot the list of pieces (DeviceFrame: one piece; PiecewiseFrame: its pieces)"""
     if not isinstance(value, tuple):
         value = (value,)
-    return [_as_device_frame(v, index_as_keys=True) for v in value if not isinstance(v, bool)]
+    slots = []
+    for v in value:
+        if isinstance(v, bool):
+            continue
+        if isinstance(v, PiecewiseFrame):
+            slots.append(list(v.pieces))
+        else:
+            slots.append([_as_device_frame(v, index_as_keys=True)])
+    return slots
+
+
+def _partials_of(value) -> List[DeviceFrame]:
+    """partial tuple -> one contiguous DeviceFrame per slot (materialises virtual concats)"""
+    out = []
+    for pieces in _pieces_of(value):
+        out.append(pieces[0] if len(pieces) == 1 else PiecewiseFrame(pieces).materialize(_kernels.concat_columns))
+    return out
 
 
 def _execute_agg_combine(ctx, op):
-    frames = _partials_of(ctx[op.inputs[0].key])
+    slots = _pieces_of(ctx[op.inputs[0].key])
     steps = _plan_steps(op, None)
-    ctx[op.outputs[0].key] = tuple(_merge_partials(frames, steps, sort=False))
+    ctx[op.outputs[0].key] = tuple(_merge_partials(slots, steps, sort=False))
 
 
 def _execute_agg_agg(ctx, op):
     """stage=agg: final merge, post functions, result frame (reference: _execute_agg, aggregation.py:1166-1267)"""
     out_chunk = op.outputs[0]
-    frames = _partials_of(ctx[op.inputs[0].key])
+    slots = _pieces_of(ctx[op.inputs[0].key])
     steps = _plan_steps(op, None)
     sort = bool(op.groupby_params.get("sort", True))
-    merged = _merge_partials(frames, steps, sort=sort)
+    merged = _merge_partials(slots, steps, sort=sort)
     by_key = {s.output_key: f for s, f in zip(steps, merged)}
     col_value = out_chunk.columns_value.to_pandas()
     two_level = col_value.nlevels > 1
@@ -300,16 +342,18 @@ def _execute_agg_agg(ctx, op):
             else:
                 res = _kernels.post_var(ts[1], ts[0], ts[2], ddof)   # inputs: sum(x**2), sum(x), count
             pieces[label] = res
-    # one D2H per result column (tiny except for very high cardinality)
-    host = {label: t.cpu().numpy() for label, t in pieces.items()}
+    # all result columns and the group keys cross to the host with ONE synchronisation
+    base = merged[0]
+    labels_dev = list(pieces.keys())
+    arrays = _to_host([pieces[l] for l in labels_dev] + list(base.index))
+    host = dict(zip(labels_dev, arrays[:len(labels_dev)]))
+    idx_arrays = arrays[len(labels_dev):]
     for label, p, c, inputs in host_eval:
         args = [pd.Series(f.column(c).cpu().numpy()) for f in inputs]
         try:
             host[label] = np.asarray(p.func(*args, gpu=False))
         except TypeError:
             host[label] = np.asarray(p.func(*args))
-    base = merged[0]
-    idx_arrays = [t.cpu().numpy() for t in base.index]
     names = base.index_names
     out_names = getattr(out_chunk.index_value, "names", None) if out_chunk.index_value is not None else None
     if out_names and len(out_names) == len(idx_arrays) and any(n is not None for n in out_names):
@@ -328,6 +372,13 @@ def _execute_agg_agg(ctx, op):
     if dtypes is not None and len(result) == 0:
         result = result.astype(dtypes)
     ctx[out_chunk.key] = result
+
+
+def _to_host(columns):
+    fn = getattr(_kernels, "to_host", None)
+    if fn is not None:
+        return fn(columns)
+    return [t.cpu().numpy() for t in columns]
 
 
 def execute_groupby_agg(ctx, op):
@@ -401,18 +452,11 @@ def _concat_frames(frames: Sequence[DeviceFrame], shared_keys=None) -> DeviceFra
     return DeviceFrame(first.index_names, keys, first.columns, data, sum(len(f) for f in frames))
 
 
-def _concat_partial_tuples(items: Sequence[Sequence[DeviceFrame]]) -> Tuple[DeviceFrame, ...]:
-    """slot-wise row concatenation of partial tuples; slots that share their index keep sharing it."""
+def _concat_partial_tuples(items: Sequence[Sequence[Any]]) -> Tuple[PiecewiseFrame, ...]:
+    """slot-wise row concatenation of partial tuples -- virtual: the pieces stay where they are and the
+    consuming combine / agg stage reads them in place (no copy kernel)."""
     n_slots = len(items[0])
-    out: List[DeviceFrame] = []
-    for n in range(n_slots):
-        shared = None
-        for m in range(n):
-            if all(it[m].same_index(it[n]) for it in items):
-                shared = out[m].index
-                break
-        out.append(_concat_frames([it[n] for it in items], shared_keys=shared))
-    return tuple(out)
+    return tuple(PiecewiseFrame([it[n] for it in items]) for n in range(n_slots))
 
 
 def _execute_shuffle_reduce(ctx, op):
@@ -428,8 +472,9 @@ def _execute_shuffle_reduce(ctx, op):
         r: Any = _concat_partial_tuples(items)
         if chunk.index_value is not None and getattr(chunk.index_value, "name", None) is not None:
             for f in r:
-                if len(f.index_names) == 1:
-                    f.index_names = [chunk.index_value.name]
+                for piece in f.pieces:
+                    if len(piece.index_names) == 1:
+                        piece.index_names = [chunk.index_value.name]
     else:
         r = _concat_frames([_as_device_frame(v, index_as_keys=True) for v in res])
     ctx[chunk.key] = r
@@ -453,7 +498,7 @@ def execute_concat(ctx, op):
     inputs = [ctx[c.key] for c in op.inputs]
     if not inputs or not isinstance(inputs[0], tuple):
         raise NotImplementedError("DataFrameConcat of plain frames stays on the reference executor")
-    items = [_partials_of(v) for v in inputs]
+    items = [[PiecewiseFrame(pieces) for pieces in _pieces_of(v)] for v in inputs]
     ctx[op.outputs[0].key] = _concat_partial_tuples(items)
 
 

@@ -177,6 +177,125 @@ def groupby_aggregate(keys, vals, accs, sort=False):
         agg.close()
 
 
+# ------------------------------------------------------------------------------ low-cardinality fast paths
+_spec_cache = {}
+_dense_cap = None
+
+
+def _spec(n_keys, val_dtypes, accs):
+    key = (n_keys, tuple(val_dtypes), tuple(accs))
+    sp = _spec_cache.get(key)
+    if sp is None:
+        sp = _spec_cache[key] = _lib.make_spec(n_keys, list(val_dtypes), list(accs))
+    return sp
+
+
+def _out_dtype(val_dtypes, col, op):
+    return torch.int64 if (op == COUNT or val_dtypes[col] == I64) else torch.float64
+
+
+def _alloc_block(n_keys, val_dtypes, accs, cap, device):
+    """One [n_keys + n_accs, cap] buffer; returns (block, key views, accumulator views)."""
+    block = torch.empty((n_keys + len(accs), max(cap, 1)), dtype=torch.int64, device=device)
+    keys = [block[j] for j in range(n_keys)]
+    outs = []
+    for a, (col, op) in enumerate(accs):
+        row = block[n_keys + a]
+        outs.append(row if _out_dtype(val_dtypes, col, op) == torch.int64 else row.view(torch.float64))
+    return block, keys, outs
+
+
+def preagg_dense(keys: Sequence[torch.Tensor], vals: Sequence[torch.Tensor], accs: Sequence[Tuple[int, int]]):
+    """Map-side pre-aggregation of one chunk on the low-cardinality path (mgb_preagg_dense): one launch.
+    Returns (key tensors, accumulator tensors) or None when the chunk is not a dense shape (too many groups
+    for the on-chip accumulators) -- the caller then uses ``groupby_aggregate``."""
+    global _dense_cap
+    lib = _lib.load()
+    if len(vals) > _lib.MGB_MAX_VALS or len(accs) > _lib.MGB_MAX_ACCS:
+        return None
+    keys = [_req(k, f"key {i}", (torch.int64,)) for i, k in enumerate(keys)]
+    vals = [_req(v, f"value {i}") for i, v in enumerate(vals)]
+    n = keys[0].numel()
+    dts = [dtype_code(v) for v in vals]
+    spec = _spec(len(keys), dts, accs)
+    if _dense_cap is None:
+        c = C.c_int64()
+        check(lib.mgb_dense_capacity(C.byref(c)))
+        _dense_cap = c.value
+    _, okeys, oaccs = _alloc_block(len(keys), dts, accs, _dense_cap, keys[0].device)
+    g = C.c_int64()
+    check(lib.mgb_preagg_dense(C.byref(spec), _ptrs(keys), _ptrs(vals), n, _ptrs(okeys), _ptrs(oaccs), _dense_cap,
+                               C.byref(g), _stream()))
+    if g.value < 0:
+        return None
+    _count(1 if n else 0)
+    G = g.value
+    return [k[:G] for k in okeys], [a[:G] for a in oaccs]
+
+
+def merge_small(pieces_keys: Sequence[Sequence[torch.Tensor]], pieces_accs: Sequence[Sequence[torch.Tensor]],
+                acc_ops: Sequence[int], sort: bool = False):
+    """Re-aggregation of small partial blocks without concatenating them (mgb_merge_small): one launch.
+    pieces_keys[i] / pieces_accs[i]: key / accumulator columns of partial block i; acc_ops[a]: merge op
+    (SUM for sums and counts, MIN, MAX).  Returns (keys, accs) or None if the input is not small."""
+    lib = _lib.load()
+    n_pieces = len(pieces_keys)
+    rows = [int(pk[0].numel()) for pk in pieces_keys]
+    total = sum(rows)
+    na = len(acc_ops)
+    if total > 2048 or n_pieces > 64 or na > _lib.MGB_MAX_ACCS or na > _lib.MGB_MAX_VALS:
+        return None
+    nk = len(pieces_keys[0])
+    first = pieces_accs[0]
+    dts = [dtype_code(t) for t in first]
+    accs = tuple((a, op) for a, op in enumerate(acc_ops))
+    spec = _spec(nk, dts, accs)
+    for pk, pa in zip(pieces_keys, pieces_accs):
+        for t in pk:
+            _req(t, "piece key", (torch.int64,))
+        for a, t in enumerate(pa):
+            _req(t, "piece accumulator")
+            if dtype_code(t) != dts[a]:
+                raise MarsGBError(1, "partial blocks differ in accumulator dtype")
+    device = pieces_keys[0][0].device
+    block = torch.empty((nk + na, max(total, 1)), dtype=torch.int64, device=device)
+    okeys = [block[j] for j in range(nk)]
+    oaccs = [block[nk + a] if dts[a] == I64 else block[nk + a].view(torch.float64) for a in range(na)]
+    rows_arr = (C.c_int64 * max(n_pieces, 1))(*rows)
+    key_tabs = [_ptrs(pk) for pk in pieces_keys]
+    acc_tabs = [_ptrs(pa) for pa in pieces_accs]
+    kt = (_lib._pp * max(n_pieces, 1))(*[C.cast(t, _lib._pp) for t in key_tabs])
+    at = (_lib._pp * max(n_pieces, 1))(*[C.cast(t, _lib._pp) for t in acc_tabs])
+    g = C.c_int64()
+    check(lib.mgb_merge_small(C.byref(spec), n_pieces, rows_arr, kt, at, _ptrs(okeys), _ptrs(oaccs), total,
+                              1 if sort else 0, C.byref(g), _stream()))
+    if g.value < 0:
+        return None
+    _count(1 if total else 0)
+    G = g.value
+    return [k[:G] for k in okeys], [a[:G] for a in oaccs]
+
+
+def to_host(columns: Sequence[torch.Tensor]):
+    """Device -> host read of several equally long 8-byte columns with one synchronisation: asynchronous
+    copies into one pinned block, then a single stream sync.  Returns numpy arrays (copies)."""
+    import numpy as np
+
+    if not columns:
+        return []
+    n = int(columns[0].numel())
+    host = torch.empty((len(columns), max(n, 1)), dtype=torch.int64, pin_memory=True)
+    for j, c in enumerate(columns):
+        c = _req(c, f"column {j}")
+        host[j, :n].view(c.dtype).copy_(c, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    out = []
+    for j, c in enumerate(columns):
+        arr = host[j, :n].numpy()
+        out.append(arr.view(np.float64).copy() if c.dtype == torch.float64 else arr.copy())
+    return out
+
+
 # ------------------------------------------------------------------------------------------------- post
 def post_mean(s: torch.Tensor, c: torch.Tensor) -> torch.Tensor:
     lib = _lib.load()

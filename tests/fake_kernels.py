@@ -64,6 +64,32 @@ def groupby_aggregate(keys, vals, accs, sort=False):
             dict(rows_tiny=0, rows_smem=0, rows_spilled=0, partial_rows=0, table_capacity=0, launches=0))
 
 
+class Aggregator:
+    """double of kernels.Aggregator: collects row batches, aggregates them on result()"""
+
+    def __init__(self, n_keys, val_dtypes, accs):
+        self.n_keys, self.accs = n_keys, list(accs)
+        self._k = [[] for _ in range(n_keys)]
+        self._v = [[] for _ in val_dtypes]
+        self.stats = None
+
+    def update(self, keys, vals):
+        for j, k in enumerate(keys):
+            self._k[j].append(k)
+        for j, v in enumerate(vals):
+            self._v[j].append(v)
+        return self
+
+    def result(self, sort=False, device=None):
+        keys = [torch.cat(k) if k else torch.empty(0, dtype=torch.int64) for k in self._k]
+        vals = [torch.cat(v) for v in self._v]
+        k, a, self.stats = groupby_aggregate(keys, vals, self.accs, sort=sort)
+        return k, a
+
+    def close(self):
+        pass
+
+
 def post_mean(s, c):
     calls.append("post_mean")
     return torch.from_numpy(_np(s) / _np(c))

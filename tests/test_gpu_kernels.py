@@ -240,3 +240,119 @@ def test_cpu_tensor_is_rejected_loudly(K):
 
     with pytest.raises(MarsGBError):
         K.hash_keys([torch.arange(4, dtype=torch.int64)])
+
+
+# --------------------------------------------------------------------------- low-cardinality fast paths
+def _codes(K, accs):
+    code = dict(sum=K.SUM, sumsq=K.SUMSQ, count=K.COUNT, min=K.MIN, max=K.MAX)
+    return [(c, code[o]) for c, o in accs]
+
+
+def check_dense(K, keys, vals, accs, expect_fit=True):
+    res = K.preagg_dense([dev(k) for k in keys], [dev(v) for v in vals], _codes(K, accs))
+    if not expect_fit:
+        assert res is None
+        return
+    assert res is not None, "dense path rejected a shape that fits"
+    gk = [t.cpu().numpy() for t in res[0]]
+    ga = [t.cpu().numpy() for t in res[1]]
+    ek, ea = pandas_agg(keys, vals, accs)
+    order = np.lexsort(tuple(reversed(gk)))
+    for a, b in zip(gk, ek):
+        np.testing.assert_array_equal(a[order], b)
+    for (col, op), a, b in zip(accs, ga, ea):
+        a = a[order]
+        assert a.dtype == (np.int64 if (op == "count" or b.dtype.kind in "iu") else np.float64)
+        if op in ("count", "min", "max") or b.dtype.kind in "iu":
+            np.testing.assert_array_equal(a, b.astype(a.dtype), err_msg=f"{op} of column {col}")
+        else:
+            np.testing.assert_allclose(a, b, rtol=1e-9, atol=0, equal_nan=True, err_msg=f"{op} of column {col}")
+
+
+@pytest.mark.parametrize("n", [1, 255, 1024, 100_003, 3_000_000])
+@pytest.mark.parametrize("n_keys", [1, 2])
+def test_dense_sum_count_shapes(K, n, n_keys):
+    rng = np.random.default_rng(n + n_keys)
+    keys = [rng.integers(0, 3, n, dtype=np.int64)] + ([rng.integers(-1, 1, n, dtype=np.int64)] if n_keys == 2 else [])
+    vals = [rng.random(n), rng.normal(5, 2, n), rng.integers(1, 10 ** 6, n, dtype=np.int64), rng.random(n),
+            rng.random(n), rng.random(n)]
+    vals[3][rng.random(n) < 0.1] = np.nan
+    accs = [(0, "sum"), (1, "sum"), (3, "sum"), (4, "sum"), (5, "sum"), (0, "count"), (1, "count"), (3, "count"),
+            (2, "count"), (2, "sum")]
+    check_dense(K, keys, vals, accs)
+
+
+@pytest.mark.parametrize("ncol", [1, 2, 3, 5, 8])
+def test_dense_all_ops(K, ncol):
+    rng = np.random.default_rng(ncol)
+    n = 200_000
+    keys = [rng.integers(-2, 2, n, dtype=np.int64)]
+    vals = [rng.normal(10, 3, n) if c % 3 else rng.integers(-1000, 1000, n, dtype=np.int64) for c in range(ncol)]
+    if ncol > 1:
+        vals[1][rng.random(n) < 0.2] = np.nan
+        vals[1][keys[0] == 1] = np.nan     # an all-NaN group: sum 0, count 0, min/max NaN
+    accs = [(c, o) for c in range(ncol) for o in ALL_OPS]
+    if len(accs) > 64:
+        accs = accs[:64]
+    check_dense(K, keys, vals, accs)
+
+
+def test_dense_rejects_high_cardinality_and_marker_keys(K):
+    rng = np.random.default_rng(1)
+    n = 50_000
+    check_dense(K, [rng.integers(0, 500, n, dtype=np.int64)], [rng.random(n)], [(0, "sum")], expect_fit=False)
+    # INT64_MIN / extreme keys are ordinary keys on the dense path
+    keys = [rng.choice(np.array([-2 ** 63, 2 ** 63 - 1, 0], dtype=np.int64), n)]
+    check_dense(K, keys, [rng.random(n)], [(0, "sum"), (0, "count"), (0, "min"), (0, "max")])
+    # exactly at the per-CTA group capacity boundary: a handful of groups, one of them very rare
+    keys = [rng.integers(0, 6, n, dtype=np.int64)]
+    keys[0][n // 2] = 77
+    check_dense(K, keys, [rng.random(n)], [(0, "sum"), (0, "count")])
+
+
+@pytest.mark.parametrize("n_keys", [1, 2])
+@pytest.mark.parametrize("sort", [False, True])
+def test_merge_small_matches_pandas(K, n_keys, sort):
+    rng = np.random.default_rng(3 + n_keys)
+    pieces_k, pieces_a, frames = [], [], []
+    for i, n in enumerate([7, 0, 300, 1, 900]):
+        ks = [rng.integers(-20, 20, n, dtype=np.int64) for _ in range(n_keys)]
+        s = rng.normal(3, 1, n)
+        c = rng.integers(0, 5, n, dtype=np.int64)
+        mn = rng.normal(0, 1, n)
+        mn[rng.random(n) < 0.3] = np.nan
+        mx = rng.integers(-9, 9, n, dtype=np.int64)
+        pieces_k.append([dev(k) for k in ks])
+        pieces_a.append([dev(s), dev(c), dev(mn), dev(mn.copy()), dev(mx)])
+        frames.append(pd.DataFrame(dict({f"k{j}": k for j, k in enumerate(ks)}, s=s, c=c, mn=mn, mx2=mn, mx=mx)))
+    res = K.merge_small(pieces_k, pieces_a, [K.SUM, K.SUM, K.MIN, K.MAX, K.MAX], sort=sort)
+    assert res is not None
+    gk = [t.cpu().numpy() for t in res[0]]
+    ga = [t.cpu().numpy() for t in res[1]]
+    exp = pd.concat(frames).groupby([f"k{j}" for j in range(n_keys)], sort=True).agg(
+        s=("s", "sum"), c=("c", "sum"), mn=("mn", "min"), mx2=("mx2", "max"), mx=("mx", "max"))
+    order = np.lexsort(tuple(reversed(gk)))
+    if sort:
+        np.testing.assert_array_equal(order, np.arange(len(order)))
+    for j in range(n_keys):
+        np.testing.assert_array_equal(gk[j][order], exp.index.get_level_values(j).to_numpy())
+    np.testing.assert_allclose(ga[0][order], exp["s"].to_numpy(), rtol=1e-12)
+    np.testing.assert_array_equal(ga[1][order], exp["c"].to_numpy())
+    np.testing.assert_array_equal(ga[2][order], exp["mn"].to_numpy())
+    np.testing.assert_array_equal(ga[3][order], exp["mx2"].to_numpy())
+    np.testing.assert_array_equal(ga[4][order], exp["mx"].to_numpy())
+
+
+def test_merge_small_declines_large_inputs(K):
+    k = dev(np.arange(3000, dtype=np.int64))
+    assert K.merge_small([[k]], [[dev(np.ones(3000))]], [K.SUM]) is None
+    res = K.merge_small([[k[:0]]], [[dev(np.ones(0))]], [K.SUM])
+    assert res is not None and res[0][0].numel() == 0
+
+
+def test_to_host_single_sync(K):
+    a, b = np.arange(10.0), np.arange(10, dtype=np.int64)
+    out = K.to_host([dev(a), dev(b)])
+    np.testing.assert_array_equal(out[0], a)
+    np.testing.assert_array_equal(out[1], b)
+    assert out[0].dtype == np.float64 and out[1].dtype == np.int64

@@ -68,7 +68,7 @@ def test_map_stage_partials_match_reference(md, name):
     map_i = 0
     for c in build_chunk_graph(t.chunks):
         if type(c.op).__name__ == "DataFrameGroupByAgg" and c.op.stage.name != "map":
-            break
+            continue
         if type(c.op).__name__ not in ("DataFrameDataSource", "DataFrameToGPU", "DataFrameGroupByAgg"):
             continue
         ctx.set_current_chunk(c)
