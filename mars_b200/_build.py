@@ -11,6 +11,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmarsgb.so")
 SOURCES = ["mgb_util.cu", "mgb_partition.cu", "mgb_agg.cu", "mgb_dense.cu", "mgb_nccl.cu", "mgb_host.cu"]
+# (source, object suffix, extra defines): the dense kernels are instantiated in four units to compile in parallel
+VARIANTS = [("mgb_dense_inst.cu", f"_{nk}_{th}", [f"-DDN_NK={nk}", f"-DDN_TH={th}"]) for nk in (1, 2) for th in (256, 512)]
+HEADERS = ["mgb_common.cuh", "mgb_dense.cuh"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
@@ -29,10 +32,8 @@ def needs_build() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES] + [
-        os.path.join(CSRC, "mgb_common.cuh"),
-        os.path.join(HERE, "..", "include", "mgb.h"),
-    ]
+    deps = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(CSRC, v[0]) for v in VARIANTS] + [
+        os.path.join(CSRC, h) for h in HEADERS] + [os.path.join(HERE, "..", "include", "mgb.h")]
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
@@ -43,9 +44,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
 
-    def compile_one(src):
-        obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+    def compile_one(job):
+        src, suffix, defines = job
+        obj = os.path.join(objdir, src.replace(".cu", suffix + ".o"))
+        cmd = [nvcc, *NVCC_FLAGS, *defines, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             print(" ".join(cmd), file=sys.stderr)
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -53,8 +55,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
         return obj
 
-    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
-        objs = list(ex.map(compile_one, SOURCES))
+    jobs = VARIANTS + [(s, "", []) for s in SOURCES]   # longest first
+    with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
+        objs = list(ex.map(compile_one, jobs))
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static", "-o", LIB, *objs, "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

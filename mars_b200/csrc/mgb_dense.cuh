@@ -1,0 +1,606 @@
+// libmarsgb: device code shared by the low-cardinality fast paths (see mgb_dense.cu for the overview).
+#pragma once
+#include "mgb_common.cuh"
+
+#define DN_MAX_GC 16
+#define DN_SMEM_BUDGET (208 * 1024)
+#define MGB_SMALL_MAX_ROWS 2048
+#define SM_TAB 4096            // hash slots of the small merge (>= 2 * MGB_SMALL_MAX_ROWS)
+#define SM_THREADS 512
+#define SM_MAX_PIECES 16
+
+#define OPB(op) (1u << (op))
+
+// --------------------------------------------------------------------------------------------------
+// shared "merge partial rows into unique output rows" machinery (one CTA)
+// --------------------------------------------------------------------------------------------------
+struct OutCols {
+  uint64_t* key[MGB_MAX_KEYS];
+  uint64_t* acc[MGB_MAX_ACCS];
+  uint8_t op[MGB_MAX_ACCS];   // merge op of accumulator a: MGB_SUM (adds; also counts), MGB_MIN, MGB_MAX
+  uint8_t dt[MGB_MAX_ACCS];   // MGB_F64 / MGB_I64 of the emitted column
+  int na;
+};
+
+template <int NK>
+__device__ __forceinline__ uint32_t small_hash(const uint64_t* k) {
+  uint64_t h = mgb_mix64(k[0]);
+  if (NK == 2) h = mgb_mix64(h ^ (k[1] * 0x9e3779b97f4a7c15ULL));
+  return (uint32_t)(h >> 40);
+}
+
+// Insert-or-find a key tuple in the CTA's table.  tab_idx[slot] = -1 empty, -2 being written, >= 0 dense row.
+// Keys are published before the index (threadfence_block) so readers that see idx >= 0 see the keys.
+template <int NK>
+__device__ __forceinline__ int small_find_or_insert(uint64_t* tab_keys, int* tab_idx, int* n_unique,
+                                                    const uint64_t* k) {
+  uint32_t s = small_hash<NK>(k) & (SM_TAB - 1);
+  for (int probe = 0; probe < SM_TAB; ++probe, s = (s + 1) & (SM_TAB - 1)) {
+    int cur = *(volatile int*)&tab_idx[s];
+    if (cur == -1) {
+      cur = atomicCAS(&tab_idx[s], -1, -2);
+      if (cur == -1) {
+        tab_keys[s] = k[0];
+        if (NK == 2) tab_keys[SM_TAB + s] = k[1];
+        const int idx = atomicAdd(n_unique, 1);
+        __threadfence_block();
+        *(volatile int*)&tab_idx[s] = idx;
+        return idx;
+      }
+    }
+    while (cur == -2) cur = *(volatile int*)&tab_idx[s];   // writer is a few instructions from publishing
+    bool eq = ((volatile uint64_t*)tab_keys)[s] == k[0];
+    if (NK == 2) eq = eq && ((volatile uint64_t*)tab_keys)[SM_TAB + s] == k[1];
+    if (eq) return cur;
+  }
+  return -1;
+}
+
+__device__ __forceinline__ void out_init(const OutCols& o, int rows) {
+  for (int i = threadIdx.x; i < rows * o.na; i += blockDim.x) {
+    const int a = i / rows, r = i - a * rows;
+    o.acc[a][r] = mgb_acc_init(o.op[a]);
+  }
+}
+
+// accumulate decoded partial value v into output row idx (global atomics: the rows are few)
+__device__ __forceinline__ void out_accumulate(const OutCols& o, int a, int idx, uint64_t v) {
+  const int op = o.op[a], dt = o.dt[a];
+  uint64_t* p = o.acc[a] + idx;
+  if (op == MGB_MIN || op == MGB_MAX) {
+    uint64_t e;
+    if (dt == MGB_F64) {
+      if (mgb_is_nan_bits(v)) return;   // NaN partial == "no value"
+      e = mgb_enc_f64(v);
+    } else {
+      e = mgb_enc_i64(v);
+    }
+    if (op == MGB_MIN)
+      atomicMin((unsigned long long*)p, (unsigned long long)e);
+    else
+      atomicMax((unsigned long long*)p, (unsigned long long)e);
+  } else if (dt == MGB_F64) {
+    atomicAdd((double*)p, __longlong_as_double((long long)v));
+  } else {
+    atomicAdd((unsigned long long*)p, (unsigned long long)v);
+  }
+}
+
+// L2 load (bypasses the non-coherent L1): data written by other CTAs before a __threadfence + ticket.
+// A plain intrinsic, not volatile asm: the compiler may batch several of them (memory-level parallelism).
+__device__ __forceinline__ uint64_t ld_cg(const uint64_t* p) { return __ldcg((const unsigned long long*)p); }
+
+// decode min/max columns in place (rows [0, n)); call after a __syncthreads + __threadfence
+__device__ __forceinline__ void out_decode(const OutCols& o, int n) {
+  for (int a = 0; a < o.na; ++a) {
+    if (o.op[a] != MGB_MIN && o.op[a] != MGB_MAX) continue;
+    for (int r = threadIdx.x; r < n; r += blockDim.x)
+      o.acc[a][r] = mgb_acc_decode(o.op[a], o.dt[a], ld_cg(o.acc[a] + r));
+  }
+}
+
+template <int NK>
+__device__ __forceinline__ bool key_less(const uint64_t* a, const uint64_t* b) {
+  const int64_t a0 = (int64_t)a[0], b0 = (int64_t)b[0];
+  if (NK == 1) return a0 < b0;
+  if (a0 != b0) return a0 < b0;
+  return (int64_t)a[1] < (int64_t)b[1];
+}
+
+// --------------------------------------------------------------------------------------------------
+// dense pre-aggregation
+// --------------------------------------------------------------------------------------------------
+#define DN_TAB 64             // key-table slots per CTA (open addressing; entries never move)
+
+struct DenseParams {
+  const uint64_t* keys[MGB_MAX_KEYS];
+  const uint64_t* cols[8];
+  long long n;
+  int GC;                   // groups per CTA (accumulator capacity); group ids are dense, in insertion order
+  int stride_g;             // 32-bit words per (warp, group) accumulator block
+  int off_nan, off_sum, off_sumsq, off_min, off_max;   // word offsets of column 0's slot inside a block
+  uint32_t f64_mask;        // bit c: loaded column c is float64 (else int64)
+  uint32_t op_mask[5];      // per mgb_op: bit c set when column c carries that accumulator
+  // global staging: row = cta * GC + g; words: keys[NK] | rows | per column: nan, then the kinds in use
+  uint64_t* stg;
+  int stg_w;                // words per staged row
+  int wpc;                  // words per column in a staged row
+  int kind_off[5];          // word of kind k (1 sum, 2 sumsq, 3 min, 4 max) inside a column's group; 0 is the NaN count
+  int* cta_ng;              // per CTA: number of groups staged
+  unsigned int* ticket;
+  int* fail;
+  int merge_smem_words;     // 8-byte words of shared memory the last CTA may use for staged rows
+  // output (spec order)
+  OutCols out;
+  uint8_t out_col[MGB_MAX_ACCS];   // loaded column of spec accumulator a, 0xFF: "rows of the group"
+  uint8_t out_src[MGB_MAX_ACCS];   // mgb_op the staged value comes from
+  long long* out_n;                // device: number of groups, -1 on failure
+};
+
+template <int NK>
+__device__ __forceinline__ uint32_t dense_hash(const uint64_t* k) {
+  uint32_t h = (uint32_t)k[0] * 0x9E3779B1u + (uint32_t)(k[0] >> 32) * 0x85EBCA77u;
+  if (NK == 2) h += (uint32_t)k[1] * 0xC2B2AE3Du + (uint32_t)(k[1] >> 32) * 0x27D4EB2Fu;
+  h ^= h >> 15;
+  return h * 0x2C1B3C6Du;
+}
+
+// lock-free probe of the CTA's key table starting at slot s; returns the group id or -1 when the probe
+// sequence reaches an empty slot.  tgid[s] < 0: empty; an entry is published (tgid written) after its keys.
+template <int NK>
+__device__ __forceinline__ int dense_probe(const uint64_t* tkeys, const int* tgid, int s, uint64_t k0, uint64_t k1) {
+  for (int probe = 0; probe < DN_TAB; ++probe) {
+    const int tg = ((const volatile int*)tgid)[s];
+    if (tg < 0) return -1;
+    bool eq = ((const volatile uint64_t*)tkeys)[s] == k0;
+    if (NK == 2) eq = eq && ((const volatile uint64_t*)tkeys)[DN_TAB + s] == k1;
+    if (eq) return tg;
+    s = (s + 1) & (DN_TAB - 1);
+  }
+  return -1;
+}
+
+// Warp-collective slow path of the group lookup (kept out of line: it runs a handful of times per CTA).
+// Lanes with live && g < 0 hold keys that missed in the table; one distinct key at a time is looked up
+// again (another warp may have inserted it meanwhile) and otherwise inserted by lane 0 under the CTA lock
+// (a single try-lock per round, so waiting warps spin on lock-free probes, not on the lock word).
+// Returns the lane's group id, or -2 when the CTA already holds GC groups.
+template <int NK>
+__device__ __noinline__ int dense_slow_lookup(uint64_t* tkeys, int* tgid, uint64_t* gkeys, int* s_ng, int* s_lock,
+                                              int GC, uint64_t k0, uint64_t k1, bool live, int g) {
+  const int lane = threadIdx.x & 31;
+  unsigned need = __ballot_sync(0xffffffffu, live && g < 0);
+  while (need) {
+    const int src = __ffs(need) - 1;
+    const uint64_t s0 = __shfl_sync(0xffffffffu, k0, src);
+    const uint64_t s1 = __shfl_sync(0xffffffffu, k1, src);
+    const uint64_t ks[2] = {s0, s1};
+    const int home = (int)(dense_hash<NK>(ks) >> 26);
+    int gi = -1;
+    if (lane == 0) {
+      gi = dense_probe<NK>(tkeys, tgid, home, s0, s1);
+      if (gi < 0 && atomicCAS(s_lock, 0, 1) == 0) {
+        __threadfence_block();
+        int q = home;
+        gi = -2;
+        for (int probe = 0; probe < DN_TAB; ++probe) {
+          const int tg = ((volatile int*)tgid)[q];
+          if (tg < 0) {   // free slot: the key is new
+            const int ng = *(volatile int*)s_ng;
+            if (ng < GC) {
+              ((volatile uint64_t*)tkeys)[q] = s0;
+              ((volatile uint64_t*)gkeys)[ng] = s0;
+              if (NK == 2) {
+                ((volatile uint64_t*)tkeys)[DN_TAB + q] = s1;
+                ((volatile uint64_t*)gkeys)[DN_MAX_GC + ng] = s1;
+              }
+              __threadfence_block();
+              ((volatile int*)tgid)[q] = ng;
+              *(volatile int*)s_ng = ng + 1;
+              gi = ng;
+            }
+            break;
+          }
+          bool eq = ((volatile uint64_t*)tkeys)[q] == s0;
+          if (NK == 2) eq = eq && ((volatile uint64_t*)tkeys)[DN_TAB + q] == s1;
+          if (eq) {
+            gi = tg;
+            break;
+          }
+          q = (q + 1) & (DN_TAB - 1);
+        }
+        __threadfence_block();
+        atomicExch(s_lock, 0);
+      }
+    }
+    gi = __shfl_sync(0xffffffffu, gi, 0);
+    if (gi == -2) return -2;
+    if (gi >= 0 && live && g < 0 && k0 == s0 && (NK == 1 || k1 == s1)) g = gi;
+    need = __ballot_sync(0xffffffffu, live && g < 0);   // gi == -1: lock was busy, go round again
+  }
+  return g;
+}
+
+// combine two decoded partial values of one accumulator: kind 1,2 add; 3 min; 4 max (f64 min/max ignore NaN,
+// which is the "no value" marker of a partial)
+__device__ __forceinline__ uint64_t dense_combine(int kind, bool f, uint64_t v, uint64_t y) {
+  if (f) {
+    const double a = __longlong_as_double((long long)v), b = __longlong_as_double((long long)y);
+    const double r = kind <= 2 ? a + b : kind == 3 ? fmin(a, b) : fmax(a, b);
+    return (uint64_t)__double_as_longlong(r);
+  }
+  const long long a = (long long)v, b = (long long)y;
+  return (uint64_t)(kind <= 2 ? a + b : kind == 3 ? min(a, b) : max(a, b));
+}
+
+// PLAIN: every loaded column is float64 and carries SUM, no SUMSQ / MIN / MAX (sum / mean / count shapes):
+// straight-line DADD updates.  Otherwise the generic body tests the per-column masks (warp-uniform branches).
+template <int NK, int NV, bool PLAIN, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) k_preagg_dense(const DenseParams p) {
+  constexpr int DN_WARPS = THREADS / 32;
+  constexpr int DN_R = 1024 / THREADS;   // rows per thread per tile: a tile is always 1024 rows
+  constexpr int DN_THREADS = THREADS;
+  constexpr bool ALLOPS = !PLAIN;
+  extern __shared__ __align__(16) uint32_t dsm[];
+  // layout: acc[warp][GC][stride_g] | tkeys[NK][TAB] (u64) | gkeys[NK][MAX_GC] (u64) | tgid[TAB] | ints
+  const int GC = p.GC;
+  uint32_t* acc = dsm;
+  uint64_t* tkeys = (uint64_t*)(dsm + (size_t)DN_WARPS * GC * p.stride_g);
+  uint64_t* gkeys = tkeys + MGB_MAX_KEYS * DN_TAB;
+  int* tgid = (int*)(gkeys + MGB_MAX_KEYS * DN_MAX_GC);
+  int* s_int = tgid + DN_TAB;
+  int* s_ng = s_int;
+  int* s_lock = s_int + 1;
+  int* s_fail = s_int + 2;
+  int* s_last = s_int + 3;
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t* wacc = acc + (size_t)warp * GC * p.stride_g;
+  const uint32_t f64m = p.f64_mask;
+  const uint32_t summ = p.op_mask[MGB_SUM], sqm = p.op_mask[MGB_SUMSQ], minm = p.op_mask[MGB_MIN],
+                 maxm = p.op_mask[MGB_MAX];
+  const int o_nan = p.off_nan, o_sum = p.off_sum >> 1, o_sq = p.off_sumsq >> 1, o_min = p.off_min >> 1,
+            o_max = p.off_max >> 1;
+  // ---- init accumulators: zeros, except min (+inf / INT64_MAX) and max (-inf / INT64_MIN)
+  for (int i = lane; i < GC * p.stride_g; i += 32) wacc[i] = 0;
+  if (ALLOPS) {
+    __syncwarp();
+    for (int g = 0; g < GC; ++g)
+      for (int c = 0; c < NV; ++c) {
+        uint64_t* b = (uint64_t*)(wacc + (size_t)g * p.stride_g);
+        const bool f = (f64m >> c) & 1;
+        if ((minm >> c) & 1u) b[o_min + c * 32 + lane] = f ? 0x7ff0000000000000ULL : 0x7fffffffffffffffULL;
+        if ((maxm >> c) & 1u) b[o_max + c * 32 + lane] = f ? 0xfff0000000000000ULL : 0x8000000000000000ULL;
+      }
+  }
+  for (int i = threadIdx.x; i < DN_TAB; i += DN_THREADS) tgid[i] = -1;
+  if (threadIdx.x == 0) {
+    *s_ng = 0;
+    *s_lock = 0;
+    *s_fail = 0;
+    *s_last = 0;
+  }
+  __syncthreads();
+
+  bool failed = false;
+
+  // one row: group lookup, then lane-private accumulator updates
+  auto process_row = [&](const uint64_t* k, const uint64_t* x, const bool live) {
+    const int s = (int)(dense_hash<NK>(k) >> 26);
+    // first probe without branches (the common case); further probes only for the lanes that need them
+    const int tg = ((const volatile int*)tgid)[s];
+    bool hit = tg >= 0 && ((const volatile uint64_t*)tkeys)[s] == k[0];
+    if (NK == 2) hit = hit && ((const volatile uint64_t*)tkeys)[DN_TAB + s] == k[1];
+    int g = hit ? tg : -1;
+    if (__any_sync(0xffffffffu, live && !hit)) {
+      if (live && !hit && tg >= 0)
+        g = dense_probe<NK>(tkeys, tgid, (s + 1) & (DN_TAB - 1), k[0], NK == 2 ? k[1] : 0);
+      if (__any_sync(0xffffffffu, live && g < 0)) {   // some lane met a key this CTA has not seen yet
+        g = dense_slow_lookup<NK>(tkeys, tgid, gkeys, s_ng, s_lock, GC, k[0], NK == 2 ? k[1] : 0, live, g);
+        if (__any_sync(0xffffffffu, g == -2)) {   // more distinct keys than group slots: not a dense chunk
+          failed = true;
+          return;
+        }
+      }
+    }
+    if (!live) return;
+    uint32_t* blk = wacc + g * p.stride_g;   // block base; lane-private columns inside
+    blk[lane] += 1;                          // rows of the group
+    double* d = (double*)blk + lane;
+    long long* q = (long long*)blk + lane;
+    if (PLAIN) {
+      bool anynan = false;
+#pragma unroll
+      for (int c = 0; c < NV; ++c) {
+        const double xv = __longlong_as_double((long long)x[c]);
+        anynan = anynan || (xv != xv);
+      }
+      if (!anynan) {   // distinct slots: independent LDS / DADD / STS chains
+        double a[NV];
+#pragma unroll
+        for (int c = 0; c < NV; ++c) a[c] = d[o_sum + c * 32];
+#pragma unroll
+        for (int c = 0; c < NV; ++c) a[c] += __longlong_as_double((long long)x[c]);
+#pragma unroll
+        for (int c = 0; c < NV; ++c) d[o_sum + c * 32] = a[c];
+      } else {         // rare: count(x) = rows - nan, sums skip NaN
+#pragma unroll
+        for (int c = 0; c < NV; ++c) {
+          const double xv = __longlong_as_double((long long)x[c]);
+          if (xv != xv)
+            atomicAdd(&blk[o_nan + c], 1u);
+          else
+            d[o_sum + c * 32] += xv;
+        }
+      }
+      return;
+    }
+    // generic: NaN bookkeeping first (rare): count(x) = rows - nan, every accumulator skips NaN
+    uint32_t nanm = 0;
+#pragma unroll
+    for (int c = 0; c < NV; ++c)
+      if (((f64m >> c) & 1u) && mgb_is_nan_bits(x[c])) nanm |= 1u << c;
+    if (nanm) {
+#pragma unroll
+      for (int c = 0; c < NV; ++c)
+        if ((nanm >> c) & 1u) atomicAdd(&blk[o_nan + c], 1u);
+    }
+#pragma unroll
+    for (int c = 0; c < NV; ++c) {
+      if ((nanm >> c) & 1u) continue;
+      if ((f64m >> c) & 1u) {
+        const double xv = __longlong_as_double((long long)x[c]);
+        if ((summ >> c) & 1u) d[o_sum + c * 32] += xv;
+        if ((sqm >> c) & 1u) d[o_sq + c * 32] += xv * xv;
+        if ((minm >> c) & 1u) d[o_min + c * 32] = fmin(d[o_min + c * 32], xv);
+        if ((maxm >> c) & 1u) d[o_max + c * 32] = fmax(d[o_max + c * 32], xv);
+      } else {
+        const long long xv = (long long)x[c];
+        if ((summ >> c) & 1u) q[o_sum + c * 32] += xv;
+        if ((sqm >> c) & 1u) q[o_sq + c * 32] += xv * xv;
+        if ((minm >> c) & 1u) q[o_min + c * 32] = min(q[o_min + c * 32], xv);
+        if ((maxm >> c) & 1u) q[o_max + c * 32] = max(q[o_max + c * 32], xv);
+      }
+    }
+  };
+
+  const long long n = p.n;
+  constexpr long long TILE = (long long)DN_THREADS * DN_R;
+  const long long nfull = n / TILE;   // full tiles take the unpredicated, double-buffered loop
+
+  uint64_t kb[2][DN_R][NK];
+  uint64_t xb[2][DN_R][NV];
+  const uint64_t* pk[NK];
+  const uint64_t* pc[NV];
+#pragma unroll
+  for (int j = 0; j < NK; ++j) pk[j] = p.keys[j] + threadIdx.x;
+#pragma unroll
+  for (int c = 0; c < NV; ++c) pc[c] = p.cols[c] + threadIdx.x;
+
+  auto load_tile = [&](int buf, long long t) {
+    const long long off = t * TILE;
+#pragma unroll
+    for (int j = 0; j < NK; ++j) {
+      const uint64_t* b = pk[j] + off;
+#pragma unroll
+      for (int r = 0; r < DN_R; ++r) kb[buf][r][j] = __ldcs((const unsigned long long*)b + r * DN_THREADS);
+    }
+#pragma unroll
+    for (int c = 0; c < NV; ++c) {
+      const uint64_t* b = pc[c] + off;
+#pragma unroll
+      for (int r = 0; r < DN_R; ++r) xb[buf][r][c] = __ldcs((const unsigned long long*)b + r * DN_THREADS);
+    }
+  };
+  auto process_tile = [&](int buf) {
+#pragma unroll
+    for (int r = 0; r < DN_R; ++r) {
+      if (failed) return;
+      process_row(kb[buf][r], xb[buf][r], true);
+    }
+  };
+
+  long long t = blockIdx.x;
+  if (t < nfull) load_tile(0, t);
+  int iter = 0;
+  while (t < nfull && !failed) {
+    const long long t1 = t + gridDim.x;
+    if (t1 < nfull) load_tile(1, t1);
+    process_tile(0);
+    if (failed || t1 >= nfull) break;
+    const long long t2 = t1 + gridDim.x;
+    if (t2 < nfull) load_tile(0, t2);
+    process_tile(1);
+    t = t2;
+    if ((++iter & 7) == 0 && *(volatile int*)p.fail) failed = true;   // somebody else gave up: stop early
+  }
+  // ragged tail (< TILE rows): one CTA, a warp-sized slice at a time; lanes past the end stay in the
+  // warp-collective lookup but neither look up nor accumulate
+  if (!failed && (int)(nfull % gridDim.x) == (int)blockIdx.x) {
+    for (long long i0 = nfull * TILE + warp * 32; i0 < n && !failed; i0 += DN_THREADS) {
+      const long long i = i0 + lane;
+      const bool live = i < n;
+      uint64_t k[NK], x[NV];
+#pragma unroll
+      for (int j = 0; j < NK; ++j) k[j] = live ? p.keys[j][i] : 0;
+#pragma unroll
+      for (int c = 0; c < NV; ++c) x[c] = live ? p.cols[c][i] : 0;
+      process_row(k, x, live);
+    }
+  }
+  if (failed) {
+    *s_fail = 1;
+    *p.fail = 1;
+  }
+  __syncthreads();
+  const bool cta_failed = *s_fail != 0;
+
+  // ---- CTA reduction -> staging rows (one per group of this CTA), decoded values
+  const int ng = cta_failed ? 0 : *(volatile int*)s_ng;
+  const int W = p.stg_w, WPC = p.wpc;
+  constexpr int SLOTS = 1 + NV * 5;
+  for (int qq = warp; qq < ng * SLOTS; qq += DN_WARPS) {
+    const int g = qq / SLOTS, s = qq - g * SLOTS;
+    uint64_t* row = p.stg + ((size_t)blockIdx.x * GC + g) * W;
+    if (s == 0) {   // rows
+      uint32_t v = 0;
+      for (int w = 0; w < DN_WARPS; ++w) v += acc[((size_t)w * GC + g) * p.stride_g + lane];
+      v = __reduce_add_sync(0xffffffffu, v);
+      if (lane == 0) row[NK] = v;
+      continue;
+    }
+    const int c = (s - 1) / 5, kind = (s - 1) % 5;   // kind: 0 nan, 1 sum, 2 sumsq, 3 min, 4 max
+    if (kind == 0) {
+      uint32_t v = lane < DN_WARPS ? acc[((size_t)lane * GC + g) * p.stride_g + o_nan + c] : 0u;
+      v = __reduce_add_sync(0xffffffffu, v);
+      if (lane == 0) row[NK + 1 + c * WPC] = v;
+      continue;
+    }
+    if (!ALLOPS && kind > 1) continue;
+    const uint32_t m = kind == 1 ? summ : kind == 2 ? sqm : kind == 3 ? minm : maxm;
+    if (!((m >> c) & 1u)) continue;
+    const int off = kind == 1 ? o_sum : kind == 2 ? o_sq : kind == 3 ? o_min : o_max;
+    const bool f = (f64m >> c) & 1u;
+    // two independent chains over the warps' private copies, then the lanes
+    uint64_t v0 = ((const uint64_t*)(acc + ((size_t)0 * GC + g) * p.stride_g))[off + c * 32 + lane];
+    uint64_t v1 = ((const uint64_t*)(acc + ((size_t)1 * GC + g) * p.stride_g))[off + c * 32 + lane];
+    for (int w = 2; w < DN_WARPS; w += 2) {
+      v0 = dense_combine(kind, f, v0, ((const uint64_t*)(acc + ((size_t)w * GC + g) * p.stride_g))[off + c * 32 + lane]);
+      v1 = dense_combine(kind, f, v1, ((const uint64_t*)(acc + ((size_t)(w + 1) * GC + g) * p.stride_g))[off + c * 32 + lane]);
+    }
+    uint64_t v = dense_combine(kind, f, v0, v1);
+    for (int o = 16; o > 0; o >>= 1) v = dense_combine(kind, f, v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (lane == 0) row[NK + 1 + c * WPC + p.kind_off[kind]] = v;
+  }
+  for (int qq = threadIdx.x; qq < ng * NK; qq += DN_THREADS) {
+    const int g = qq / NK, j = qq - g * NK;
+    p.stg[((size_t)blockIdx.x * GC + g) * W + j] = gkeys[j * DN_MAX_GC + g];
+  }
+  if (threadIdx.x == 0) p.cta_ng[blockIdx.x] = ng;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int tk = atomicAdd(p.ticket, 1u);
+    *s_last = (tk == gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!*s_last) return;
+
+  // ---- last CTA: merge all staged rows into unique output rows.  Shared memory is re-used:
+  //      tab_keys[NK][SM_TAB] | tab_idx[SM_TAB] | ints[8] | items[grid*GC] | item_idx[grid*GC] | sbuf[...]
+  __threadfence();
+  if (*(volatile int*)p.fail) {
+    if (threadIdx.x == 0) *p.out_n = -1;
+    return;
+  }
+  uint64_t* tab_keys = (uint64_t*)dsm;
+  int* tab_idx = (int*)(tab_keys + MGB_MAX_KEYS * SM_TAB);
+  int* n_unique = tab_idx + SM_TAB;
+  int* n_items = n_unique + 1;
+  int* items = n_unique + 8;
+  const int n_slots = (gridDim.x * GC + 1) & ~1;   // even: keeps sbuf 8-byte aligned
+  int* item_idx = items + n_slots;
+  uint64_t* sbuf = (uint64_t*)(item_idx + n_slots);
+  for (int i = threadIdx.x; i < SM_TAB; i += DN_THREADS) tab_idx[i] = -1;
+  if (threadIdx.x == 0) {
+    *n_unique = 0;
+    *n_items = 0;
+  }
+  __syncthreads();
+  for (int cta = threadIdx.x; cta < (int)gridDim.x; cta += DN_THREADS) {
+    const int cnt = ((volatile int*)p.cta_ng)[cta];
+    int pos = cnt ? atomicAdd(n_items, cnt) : 0;
+    for (int g = 0; g < cnt; ++g) items[pos++] = cta * GC + g;
+  }
+  __syncthreads();
+  const int total = *n_items;
+  // pass 1: dense output row of every staged row (shared-memory hash table on the key tuple)
+  for (int it = threadIdx.x; it < total; it += DN_THREADS) {
+    const uint64_t* row = p.stg + (size_t)items[it] * W;
+    uint64_t k[NK];
+#pragma unroll
+    for (int j = 0; j < NK; ++j) k[j] = ld_cg(row + j);
+    const int idx = small_find_or_insert<NK>(tab_keys, tab_idx, n_unique, k);
+    item_idx[it] = idx;
+#pragma unroll
+    for (int j = 0; j < NK; ++j) p.out.key[j][idx] = k[j];   // same value from every writer
+  }
+  __syncthreads();
+  const int nu = *n_unique;
+  const int na = p.out.na;
+  // pass 2: staged rows -> shared memory in batches (coalesced), one warp per (output row, accumulator)
+  // reduces its contributions in a fixed order: no atomics, run-to-run deterministic sums
+  const int RB = p.merge_smem_words / W;
+  for (int b0 = 0; b0 < total; b0 += RB) {
+    const int nb = total - b0 < RB ? total - b0 : RB;
+#pragma unroll 4
+    for (int w = threadIdx.x; w < nb * W; w += DN_THREADS) {
+      const int j = w / W;
+      sbuf[w] = ld_cg(p.stg + (size_t)items[b0 + j] * W + (w - j * W));
+    }
+    __syncthreads();
+    for (int pair = warp; pair < nu * na; pair += DN_WARPS) {
+      const int u = pair / na, a = pair - u * na;
+      const int c = p.out_col[a], src = p.out_src[a];
+      const bool f = src != MGB_COUNT && c != 0xFF && ((f64m >> c) & 1u);
+      const int kind = src == MGB_SUM ? 1 : src == MGB_SUMSQ ? 2 : src == MGB_MIN ? 3 : src == MGB_MAX ? 4 : 1;
+      // identity: 0 for sums / counts, NaN (ignored by fmin / fmax) for float min / max, extremes for int
+      uint64_t v = 0;
+      if (kind == 3) v = f ? 0x7ff8000000000000ULL : 0x7fffffffffffffffULL;
+      if (kind == 4) v = f ? 0x7ff8000000000000ULL : 0x8000000000000000ULL;
+      for (int j = lane; j < nb; j += 32) {
+        if (item_idx[b0 + j] != u) continue;
+        const uint64_t* row = sbuf + (size_t)j * W;
+        const uint64_t rows = row[NK];
+        const uint64_t nanc = (c != 0xFF && ((f64m >> c) & 1u)) ? row[NK + 1 + c * WPC] : 0;
+        if (src == MGB_COUNT) {
+          v += rows - nanc;
+        } else if (kind <= 2 || rows != nanc) {   // min / max of an all-NaN partial: no value
+          v = dense_combine(kind, f, v, row[NK + 1 + c * WPC + p.kind_off[kind]]);
+        }
+      }
+      for (int o = 16; o > 0; o >>= 1) v = dense_combine(kind, f, v, __shfl_xor_sync(0xffffffffu, v, o));
+      if (lane == 0) {
+        uint64_t* dst = p.out.acc[a] + u;
+        *dst = b0 == 0 ? v : dense_combine(kind, f, *dst, v);
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *p.out_n = nu;
+}
+
+// one translation unit per (NK, THREADS) pair instantiates the kernels (mgb_dense_inst.cu)
+template <int NK, int TH>
+int mgb_dense_launch(const DenseParams& p, int ncol, bool plain, int grid, size_t smem, cudaStream_t st) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+#define LAUNCH(NV, PL)                                                                                       \
+  do {                                                                                                      \
+    static bool attr_set[8] = {false};   /* per device: the opt-in is sticky, set it once */                \
+    if (!attr_set[dev & 7]) {                                                                               \
+      MGB_CUDA(cudaFuncSetAttribute(k_preagg_dense<NK, NV, PL, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                    227 * 1024));                                                           \
+      attr_set[dev & 7] = true;                                                                             \
+    }                                                                                                       \
+    k_preagg_dense<NK, NV, PL, TH><<<grid, TH, smem, st>>>(p);                                              \
+  } while (0)
+#define PICK_NV(PL)                     \
+  do {                                  \
+    switch (ncol) {                     \
+      case 1: LAUNCH(1, PL); break;     \
+      case 2: LAUNCH(2, PL); break;     \
+      case 3: LAUNCH(3, PL); break;     \
+      case 4: LAUNCH(4, PL); break;     \
+      case 5: LAUNCH(5, PL); break;     \
+      case 6: LAUNCH(6, PL); break;     \
+      case 7: LAUNCH(7, PL); break;     \
+      default: LAUNCH(8, PL); break;    \
+    }                                   \
+  } while (0)
+  if (plain) PICK_NV(true); else PICK_NV(false);
+#undef PICK_NV
+#undef LAUNCH
+  MGB_CHECK_LAUNCH();
+  return MGB_OK;
+}
