@@ -176,10 +176,16 @@ extern "C" int mgb_preagg_dense(const mgb_agg_spec* spec, const int64_t* const* 
   // the CTA owns its SM: take (almost) all shared memory; the last CTA re-uses it for the cross-CTA merge
   const size_t acc_smem = (size_t)n_warps * GC * p.stride_g * 4 + fixed;
   size_t smem = acc_smem < 112 * 1024 ? 112 * 1024 : acc_smem;   // >= 112 KB for the cross-CTA merge tables
-  const size_t merge_fixed = (size_t)MGB_MAX_KEYS * SM_TAB * 8 + SM_TAB * 4 + 32 + 2 * ((size_t)grid * GC + 2) * 4;
-  MGB_REQUIRE((size_t)n_warps * GC * p.stride_g * 4 + fixed <= smem && merge_fixed + 64 * (size_t)p.stg_w * 8 <= smem,
-              MGB_ERR_OVERFLOW, "dense path shared-memory plan does not fit");
-  p.merge_smem_words = (int)((smem - merge_fixed) / 8);
+  // last-CTA merge: key table + 5 int arrays of at most grid * GC (+2) entries
+  const size_t merge_smem = (size_t)MGB_MAX_KEYS * SM_TAB * 8 + SM_TAB * 4 + 32 + 5 * ((size_t)grid * GC + 4) * 4;
+  MGB_REQUIRE(acc_smem <= smem && merge_smem <= smem, MGB_ERR_OVERFLOW, "dense path shared-memory plan does not fit");
+  static const char* env_dbg = getenv("MGB_DENSE_DEBUG");   // experiments only: per-CTA phase timestamps
+  long long* dbg = nullptr;
+  if (env_dbg) {
+    MGB_CUDA(cudaMalloc((void**)&dbg, sizeof(long long) * (4 * grid + 8)));
+    MGB_CUDA(cudaMemset(dbg, 0, sizeof(long long) * (4 * grid + 8)));
+    p.dbg = dbg;
+  }
   {
     MgbProfScope prof(MGB_K_PREAGG_TINY, st);
     int status;
@@ -194,6 +200,25 @@ extern "C" int mgb_preagg_dense(const mgb_agg_spec* spec, const int64_t* const* 
   MGB_CUDA(cudaMemcpyAsync(s->out_n_host, s->out_n, sizeof(long long), cudaMemcpyDeviceToHost, st));
   MGB_CUDA(cudaStreamSynchronize(st));
   *out_n_groups = s->out_n_host[0];
+  if (dbg) {
+    long long* h = (long long*)malloc(sizeof(long long) * (4 * grid + 8));
+    cudaMemcpy(h, dbg, sizeof(long long) * (4 * grid + 8), cudaMemcpyDeviceToHost);
+    long long t0 = h[0], mx[4] = {0, 0, 0, 0}, mn[4] = {1LL << 62, 1LL << 62, 1LL << 62, 1LL << 62};
+    for (int i = 0; i < grid; ++i) if (h[i * 4] < t0) t0 = h[i * 4];
+    for (int i = 0; i < grid; ++i)
+      for (int j = 0; j < 4; ++j) {
+        if (!h[i * 4 + j]) continue;
+        long long d = h[i * 4 + j] - t0;
+        if (d > mx[j]) mx[j] = d;
+        if (d < mn[j]) mn[j] = d;
+      }
+    fprintf(stderr, "dense phases (ns since first CTA start): start %lld..%lld | main loop done %lld..%lld | staged+ticket %lld..%lld | last CTA end %lld\n",
+            mn[0], mx[0], mn[1], mx[1], mn[2], mx[2], mx[3]);
+    fprintf(stderr, "  last CTA: enter %lld | table init %lld | items %lld | pass1 %lld | staged copy %lld\n", h[4 * grid] - t0,
+            h[4 * grid + 1] - t0, h[4 * grid + 2] - t0, h[4 * grid + 3] - t0, h[4 * grid + 4] - t0);
+    free(h);
+    cudaFree(dbg);
+  }
   return MGB_OK;
 }
 

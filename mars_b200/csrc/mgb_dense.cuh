@@ -129,13 +129,19 @@ struct DenseParams {
   int* cta_ng;              // per CTA: number of groups staged
   unsigned int* ticket;
   int* fail;
-  int merge_smem_words;     // 8-byte words of shared memory the last CTA may use for staged rows
   // output (spec order)
   OutCols out;
   uint8_t out_col[MGB_MAX_ACCS];   // loaded column of spec accumulator a, 0xFF: "rows of the group"
   uint8_t out_src[MGB_MAX_ACCS];   // mgb_op the staged value comes from
   long long* out_n;                // device: number of groups, -1 on failure
+  long long* dbg;                  // optional [grid][4] phase timestamps (ns), profiling experiments only
 };
+
+__device__ __forceinline__ long long dense_now() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 template <int NK>
 __device__ __forceinline__ uint32_t dense_hash(const uint64_t* k) {
@@ -255,6 +261,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_preagg_dense(const DenseParams p
   int* s_last = s_int + 3;
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 4 + 0] = dense_now();
   uint32_t* wacc = acc + (size_t)warp * GC * p.stride_g;
   const uint32_t f64m = p.f64_mask;
   const uint32_t summ = p.op_mask[MGB_SUM], sqm = p.op_mask[MGB_SUMSQ], minm = p.op_mask[MGB_MIN],
@@ -433,6 +440,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_preagg_dense(const DenseParams p
     *p.fail = 1;
   }
   __syncthreads();
+  if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 4 + 1] = dense_now();
   const bool cta_failed = *s_fail != 0;
 
   // ---- CTA reduction -> staging rows (one per group of this CTA), decoded values
@@ -484,6 +492,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_preagg_dense(const DenseParams p
     *s_last = (tk == gridDim.x - 1) ? 1 : 0;
   }
   __syncthreads();
+  if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 4 + 2] = dense_now();
   if (!*s_last) return;
 
   // ---- last CTA: merge all staged rows into unique output rows.  Shared memory is re-used:
@@ -501,12 +510,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_preagg_dense(const DenseParams p
   const int n_slots = (gridDim.x * GC + 1) & ~1;   // even: keeps sbuf 8-byte aligned
   int* item_idx = items + n_slots;
   uint64_t* sbuf = (uint64_t*)(item_idx + n_slots);
+  if (p.dbg && threadIdx.x == 0) p.dbg[gridDim.x * 4 + 0] = dense_now();
   for (int i = threadIdx.x; i < SM_TAB; i += DN_THREADS) tab_idx[i] = -1;
   if (threadIdx.x == 0) {
     *n_unique = 0;
     *n_items = 0;
   }
   __syncthreads();
+  if (p.dbg && threadIdx.x == 0) p.dbg[gridDim.x * 4 + 1] = dense_now();
   for (int cta = threadIdx.x; cta < (int)gridDim.x; cta += DN_THREADS) {
     const int cnt = ((volatile int*)p.cta_ng)[cta];
     int pos = cnt ? atomicAdd(n_items, cnt) : 0;
@@ -514,6 +525,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_preagg_dense(const DenseParams p
   }
   __syncthreads();
   const int total = *n_items;
+  if (p.dbg && threadIdx.x == 0) p.dbg[gridDim.x * 4 + 2] = dense_now();
   // pass 1: dense output row of every staged row (shared-memory hash table on the key tuple)
   for (int it = threadIdx.x; it < total; it += DN_THREADS) {
     const uint64_t* row = p.stg + (size_t)items[it] * W;
@@ -528,46 +540,72 @@ __global__ void __launch_bounds__(THREADS, 1) k_preagg_dense(const DenseParams p
   __syncthreads();
   const int nu = *n_unique;
   const int na = p.out.na;
-  // pass 2: staged rows -> shared memory in batches (coalesced), one warp per (output row, accumulator)
-  // reduces its contributions in a fixed order: no atomics, run-to-run deterministic sums
-  const int RB = p.merge_smem_words / W;
-  for (int b0 = 0; b0 < total; b0 += RB) {
-    const int nb = total - b0 < RB ? total - b0 : RB;
+  if (p.dbg && threadIdx.x == 0) p.dbg[gridDim.x * 4 + 3] = dense_now();
+  // pass 2: counting sort of the staged rows by output row (shared memory), then 8 lanes per
+  // (output row, accumulator) pair reduce that row's contributions straight from L2 and combine by shuffles
+  int* ucnt = (int*)sbuf;              // [nu + 1] counts -> exclusive starts
+  int* ufill = ucnt + (nu + 1);        // [nu]
+  int* sorted = ufill + nu;            // [total] item numbers grouped by output row
+  for (int i = threadIdx.x; i <= nu; i += DN_THREADS) ucnt[i] = 0;
+  for (int i = threadIdx.x; i < nu; i += DN_THREADS) ufill[i] = 0;
+  __syncthreads();
+  for (int it = threadIdx.x; it < total; it += DN_THREADS) atomicAdd(&ucnt[item_idx[it]], 1);
+  __syncthreads();
+  if (warp == 0) {   // exclusive scan of ucnt[0..nu] by one warp, 32 entries per step
+    int carry = 0;
+    for (int base = 0; base <= nu; base += 32) {
+      const int i = base + lane;
+      const int v = i <= nu ? ucnt[i] : 0;
+      int x = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+      }
+      if (i <= nu) ucnt[i] = carry + x - v;
+      carry += __shfl_sync(0xffffffffu, x, 31);
+    }
+  }
+  __syncthreads();
+  for (int it = threadIdx.x; it < total; it += DN_THREADS) {
+    const int u = item_idx[it];
+    sorted[ucnt[u] + atomicAdd(&ufill[u], 1)] = it;
+  }
+  __syncthreads();
+  if (p.dbg && threadIdx.x == 0) p.dbg[gridDim.x * 4 + 4] = dense_now();
+  const int sl = lane & 7, pl = lane >> 3;
+  for (int pair0 = 0; pair0 < nu * na; pair0 += DN_WARPS * 4) {
+    const int pair = pair0 + warp * 4 + pl;
+    const bool on = pair < nu * na;
+    const int u = on ? pair / na : 0, a = on ? pair - u * na : 0;
+    const int c = p.out_col[a], src = p.out_src[a];
+    const bool fcol = c != 0xFF && ((f64m >> c) & 1u);
+    const bool f = src != MGB_COUNT && fcol;
+    const int kind = src == MGB_SUM ? 1 : src == MGB_SUMSQ ? 2 : src == MGB_MIN ? 3 : src == MGB_MAX ? 4 : 1;
+    const int voff = NK + 1 + (c == 0xFF ? 0 : c * WPC + p.kind_off[kind]);
+    const int noff = NK + 1 + (c == 0xFF ? 0 : c * WPC);
+    // identity: 0 for sums / counts, NaN (ignored by fmin / fmax) for float min / max, extremes for int
+    uint64_t v = 0;
+    if (kind == 3) v = f ? 0x7ff8000000000000ULL : 0x7fffffffffffffffULL;
+    if (kind == 4) v = f ? 0x7ff8000000000000ULL : 0x8000000000000000ULL;
+    const int q1 = on ? ucnt[u + 1] : 0;
 #pragma unroll 4
-    for (int w = threadIdx.x; w < nb * W; w += DN_THREADS) {
-      const int j = w / W;
-      sbuf[w] = ld_cg(p.stg + (size_t)items[b0 + j] * W + (w - j * W));
+    for (int q = (on ? ucnt[u] : 0) + sl; q < q1; q += 8) {
+      const uint64_t* row = p.stg + (size_t)items[sorted[q]] * W;
+      const uint64_t rows = ld_cg(row + NK);
+      const uint64_t nanc = fcol ? ld_cg(row + noff) : 0;
+      const uint64_t x = src == MGB_COUNT ? 0 : ld_cg(row + voff);
+      if (src == MGB_COUNT)
+        v += rows - nanc;
+      else if (kind <= 2 || rows != nanc)   // min / max of an all-NaN partial: no value
+        v = dense_combine(kind, f, v, x);
     }
-    __syncthreads();
-    for (int pair = warp; pair < nu * na; pair += DN_WARPS) {
-      const int u = pair / na, a = pair - u * na;
-      const int c = p.out_col[a], src = p.out_src[a];
-      const bool f = src != MGB_COUNT && c != 0xFF && ((f64m >> c) & 1u);
-      const int kind = src == MGB_SUM ? 1 : src == MGB_SUMSQ ? 2 : src == MGB_MIN ? 3 : src == MGB_MAX ? 4 : 1;
-      // identity: 0 for sums / counts, NaN (ignored by fmin / fmax) for float min / max, extremes for int
-      uint64_t v = 0;
-      if (kind == 3) v = f ? 0x7ff8000000000000ULL : 0x7fffffffffffffffULL;
-      if (kind == 4) v = f ? 0x7ff8000000000000ULL : 0x8000000000000000ULL;
-      for (int j = lane; j < nb; j += 32) {
-        if (item_idx[b0 + j] != u) continue;
-        const uint64_t* row = sbuf + (size_t)j * W;
-        const uint64_t rows = row[NK];
-        const uint64_t nanc = (c != 0xFF && ((f64m >> c) & 1u)) ? row[NK + 1 + c * WPC] : 0;
-        if (src == MGB_COUNT) {
-          v += rows - nanc;
-        } else if (kind <= 2 || rows != nanc) {   // min / max of an all-NaN partial: no value
-          v = dense_combine(kind, f, v, row[NK + 1 + c * WPC + p.kind_off[kind]]);
-        }
-      }
-      for (int o = 16; o > 0; o >>= 1) v = dense_combine(kind, f, v, __shfl_xor_sync(0xffffffffu, v, o));
-      if (lane == 0) {
-        uint64_t* dst = p.out.acc[a] + u;
-        *dst = b0 == 0 ? v : dense_combine(kind, f, *dst, v);
-      }
-    }
-    __syncthreads();
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) v = dense_combine(kind, f, v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (on && sl == 0) p.out.acc[a][u] = v;
   }
   if (threadIdx.x == 0) *p.out_n = nu;
+  if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 4 + 3] = dense_now();
 }
 
 // one translation unit per (NK, THREADS) pair instantiates the kernels (mgb_dense_inst.cu)
