@@ -159,7 +159,7 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=open(self.path, "w"),
+                                          "-lms", "20", "-i", str(self.idx)], stdout=open(self.path, "w"),
                                          stderr=subprocess.DEVNULL)
         except Exception:  # noqa: BLE001
             self.proc = None
@@ -261,10 +261,6 @@ def main_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def finish_cross_rank(partials):
-        """weak-scaling tail: per-rank partial tuples (<= 4 groups) -> rank 0 -> final agg there"""
-        raise NotImplementedError
-
     def step(resident: bool):
         frames = dev_frames if resident else host_frames
         mdf = md.DataFrame.from_chunks(frames)
@@ -276,7 +272,7 @@ def main_ours(args):
             r.execute(session=sess)
             out = r.fetch(session=sess)
         else:
-            out = sess.execute_local_then_gather(r, dist, rank, world)
+            out = sess.execute_sharded_tree(r)
         return out
 
     def timed(resident: bool, steps: int, warmup: int):

@@ -419,6 +419,9 @@ class DataFrame:
         return (session or get_default_session()).fetch(self)
 
 
+_mock_cache: Dict[Any, Any] = {}
+
+
 class DataFrameGroupBy:
     def __init__(self, df: DataFrame, by: List[Any], as_index=True, sort=True, group_keys=True, selection=None):
         self.df = df
@@ -447,6 +450,16 @@ class DataFrameGroupBy:
         """schema inference by running real pandas on a small mock frame (reference: build_mock_agg_result,
         aggregation.py:142-161)"""
         dtypes = self.df.dtypes
+        try:   # the mock only depends on the schema and the call: cache it (graph building stays cheap)
+            cache_key = (tuple((str(c), str(dt)) for c, dt in dtypes.items()), tuple(map(str, self.by)), self.as_index,
+                         self.sort, None if self.selection is None else tuple(map(str, self.selection)), repr(func),
+                         repr(sorted(kw.items())))
+            hit = _mock_cache.get(cache_key)
+            if hit is not None:
+                return hit
+        except Exception:  # noqa: BLE001
+            cache_key = None
+
         def mock_col(dt):
             try:
                 return np.arange(1, 5).astype(dt)
@@ -457,7 +470,10 @@ class DataFrameGroupBy:
         g = mock.groupby(self.by, as_index=self.as_index, sort=self.sort)
         if self.selection is not None:
             g = g[self.selection]
-        return g.agg(func, **kw)
+        out = g.agg(func, **kw)
+        if cache_key is not None:
+            _mock_cache[cache_key] = out
+        return out
 
     def agg(self, func=None, method="auto", combine_size=None, **kw) -> DataFrame:
         if method is None:

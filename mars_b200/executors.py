@@ -165,23 +165,34 @@ def _plan_steps(op, value_cols) -> List[_Step]:
 # ----------------------------------------------------------------------------------------------------
 # DataFrameGroupByAgg
 # ----------------------------------------------------------------------------------------------------
-def _execute_agg_map(ctx, op):
-    """stage=map: per-chunk group-by + K atomic reductions (reference: _execute_map, aggregation.py:1043-1128)"""
-    frame = _as_device_frame(ctx[op.inputs[0].key])
+class _MapPlan:
+    """Everything of a stage=map call that only depends on the operand's functions and the chunk schema."""
+    __slots__ = ("by", "key_pos", "used", "val_pos", "accs", "slots", "shape_key")
+
+
+_map_plans: Dict[Any, _MapPlan] = {}
+
+
+def _map_plan(op, frame: DeviceFrame) -> _MapPlan:
     params = op.groupby_params
     by = params.get("by")
+    selection = params.get("selection")
+    try:
+        sig = (tuple(frame.columns), tuple(by) if isinstance(by, (list, tuple)) else by,
+               None if selection is None else tuple(selection), repr(getattr(op, "func", None)),
+               tuple((a.input_key, a.map_func_name, a.agg_func_name, a.output_key) for a in op.agg_funcs),
+               tuple((p.input_key, p.output_key, None if p.columns is None else tuple(p.columns))
+                     for p in (op.pre_funcs or [])))
+        plan = _map_plans.get(sig)
+        if plan is not None:
+            return plan
+    except TypeError:
+        sig = None
     if not isinstance(by, (list, tuple)) or not by or any(not isinstance(b, (str, int, tuple)) for b in by):
         raise NotImplementedError("groupby keys must be column labels on the GPU path")
     by = list(by)
-    if frame.index is not None:
-        raise NotImplementedError("map stage expects a raw chunk (RangeIndex)")
-    selection = params.get("selection")
     value_cols = [c for c in frame.columns if c not in by and (selection is None or c in selection)]
     steps = _plan_steps(op, value_cols)
-    keys = [frame.column(b) for b in by]
-    for b, k in zip(by, keys):
-        if k.dtype != torch.int64:
-            raise NotImplementedError(f"group key {b!r} has dtype {k.dtype}: int64 keys only")
     used: List[Any] = []
     for s in steps:
         for c in s.cols:
@@ -189,32 +200,54 @@ def _execute_agg_map(ctx, op):
                 used.append(c)
     if not used:
         raise NotImplementedError("no value column to aggregate")
-    vals = [frame.column(c) for c in used]
-    accs = []
+    accs, slots = [], []
     for s in steps:
         code = _OPCODE[s.map_func]
         if s.pre_kind == "square":
             if s.map_func != "sum":
                 raise NotImplementedError("x**2 is only aggregated with sum")
             code = K.SUMSQ
+        slots.append((list(s.cols), len(accs), len(accs) + len(s.cols)))
         for c in s.cols:
             accs.append((used.index(c), code))
+    plan = _MapPlan()
+    plan.by = by
+    plan.key_pos = [frame.columns.index(b) for b in by]
+    plan.used = used
+    plan.val_pos = [frame.columns.index(c) for c in used]
+    plan.accs = tuple(accs)
+    plan.slots = slots
+    plan.shape_key = (tuple(by), tuple(used), plan.accs)
+    if sig is not None:
+        _map_plans[sig] = plan
+    return plan
+
+
+def _execute_agg_map(ctx, op):
+    """stage=map: per-chunk group-by + K atomic reductions (reference: _execute_map, aggregation.py:1043-1128)"""
+    frame = _as_device_frame(ctx[op.inputs[0].key])
+    if frame.index is not None:
+        raise NotImplementedError("map stage expects a raw chunk (RangeIndex)")
+    plan = _map_plan(op, frame)
+    data = frame.data
+    keys = [data[i] for i in plan.key_pos]
+    for b, k in zip(plan.by, keys):
+        if k.dtype != torch.int64:
+            raise NotImplementedError(f"group key {b!r} has dtype {k.dtype}: int64 keys only")
+    vals = [data[i] for i in plan.val_pos]
     # low-cardinality chunks take the one-launch dense path; a shape that did not fit is remembered so
     # the following chunks of the same computation go straight to the general hash-table path
-    shape_key = (tuple(by), tuple(used), tuple(accs))
     res = None
-    if shape_key not in _dense_rejected and hasattr(_kernels, "preagg_dense"):
-        res = _kernels.preagg_dense(keys, vals, accs)
+    if plan.shape_key not in _dense_rejected and hasattr(_kernels, "preagg_dense"):
+        res = _kernels.preagg_dense(keys, vals, plan.accs)
         if res is None:
-            _dense_rejected.add(shape_key)
+            _dense_rejected.add(plan.shape_key)
     if res is None:
-        out_keys, out_accs, _ = _kernels.groupby_aggregate(keys, vals, accs, sort=False)
+        out_keys, out_accs, _ = _kernels.groupby_aggregate(keys, vals, list(plan.accs), sort=False)
     else:
         out_keys, out_accs = res
-    frames, pos = [], 0
-    for s in steps:
-        frames.append(DeviceFrame(by, out_keys, s.cols, out_accs[pos:pos + len(s.cols)], int(out_keys[0].numel())))
-        pos += len(s.cols)
+    n_out = int(out_keys[0].numel())
+    frames = [DeviceFrame(plan.by, out_keys, cols, out_accs[a0:a1], n_out) for cols, a0, a1 in plan.slots]
     rec = getattr(op, "size_recorder_name", None)
     if rec is not None:
         _record_sizes(ctx, rec, frame.nbytes, sum(f.nbytes for f in frames))
@@ -363,11 +396,21 @@ def _execute_agg_agg(ctx, op):
     else:
         index = pd.MultiIndex.from_arrays(idx_arrays, names=names)
     labels = list(host.keys())
-    result = pd.DataFrame({i: host[l] for i, l in enumerate(labels)}, index=index)
-    result.columns = pd.MultiIndex.from_tuples(labels) if two_level else pd.Index(labels)
-    if not op.groupby_params.get("as_index", True):
-        result = result.reset_index()
-    result = result.reindex(col_value, axis=1)
+    as_index = op.groupby_params.get("as_index", True)
+    result = None
+    if as_index and len(set(labels)) == len(labels) and set(labels) == set(col_value):
+        # declared column order == a permutation of what was computed: assemble directly (no reindex)
+        try:
+            result = pd.DataFrame._from_arrays([host[l] for l in col_value], columns=col_value, index=index,
+                                               verify_integrity=False)
+        except Exception:  # noqa: BLE001  (private pandas constructor: fall back to the public route)
+            result = None
+    if result is None:
+        result = pd.DataFrame({i: host[l] for i, l in enumerate(labels)}, index=index)
+        result.columns = pd.MultiIndex.from_tuples(labels) if two_level else pd.Index(labels)
+        if not as_index:
+            result = result.reset_index()
+        result = result.reindex(col_value, axis=1)
     dtypes = getattr(out_chunk, "dtypes", None)
     if dtypes is not None and len(result) == 0:
         result = result.astype(dtypes)

@@ -23,9 +23,15 @@ def _count(n):
     launch_counter += n
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream() -> int:
+    """cudaStream_t of torch's current stream on the current device (the stream every kernel is launched on)."""
     if not torch.cuda.is_available():
         raise MarsGBError(2, "no CUDA device: the groupby path runs on the GPU only (no CPU fallback)")
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -205,6 +211,73 @@ def _alloc_block(n_keys, val_dtypes, accs, cap, device):
     return block, keys, outs
 
 
+class _FastCall:
+    """Pre-built ctypes argument arrays of one call shape: per call only raw pointers are filled in."""
+
+    __slots__ = ("spec", "nk", "nv", "na", "kp", "vp", "okp", "oap", "is_float", "n_int", "n_float", "int_row",
+                 "float_row", "g")
+
+    def __init__(self, nk, dts, accs):
+        self.spec = _lib.make_spec(nk, list(dts), list(accs))
+        self.nk, self.nv, self.na = nk, len(dts), len(accs)
+        self.kp = (C.c_void_p * nk)()
+        self.vp = (C.c_void_p * max(self.nv, 1))()
+        self.okp = (C.c_void_p * nk)()
+        self.oap = (C.c_void_p * max(self.na, 1))()
+        self.is_float = [_out_dtype(dts, col, op) == torch.float64 for col, op in accs]
+        self.int_row, self.float_row = [], []
+        ni, nf = nk, 0
+        for f in self.is_float:
+            if f:
+                self.float_row.append(nf)
+                self.int_row.append(-1)
+                nf += 1
+            else:
+                self.int_row.append(ni)
+                self.float_row.append(-1)
+                ni += 1
+        self.n_int, self.n_float = ni, nf
+        self.g = C.c_int64()
+
+    def alloc(self, cap, device):
+        """int64 block [n_keys + int accs, cap] and float64 block [float accs, cap]; output pointers set."""
+        cap = max(int(cap), 1)
+        bi = torch.empty((self.n_int, cap), dtype=torch.int64, device=device)
+        bf = torch.empty((max(self.n_float, 1), cap), dtype=torch.float64, device=device)
+        pi, pf, stride = bi.data_ptr(), bf.data_ptr(), cap * 8
+        for j in range(self.nk):
+            self.okp[j] = pi + j * stride
+        for a in range(self.na):
+            self.oap[a] = pf + self.float_row[a] * stride if self.is_float[a] else pi + self.int_row[a] * stride
+        return bi, bf
+
+    def views(self, bi, bf, G):
+        """(key tensors, accumulator tensors) of the first G rows -- two slices + two unbinds in total."""
+        ri = bi[:, :G].unbind(0)
+        rf = bf[:, :G].unbind(0)
+        keys = list(ri[:self.nk])
+        accs = [rf[self.float_row[a]] if self.is_float[a] else ri[self.int_row[a]] for a in range(self.na)]
+        return keys, accs
+
+
+_fast_cache = {}
+
+
+def _fast(nk, dts, accs) -> _FastCall:
+    key = (nk, tuple(dts), tuple(accs))
+    fc = _fast_cache.get(key)
+    if fc is None:
+        fc = _fast_cache[key] = _FastCall(nk, dts, accs)
+    return fc
+
+
+def _check_col(t, what):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dim() == 1 and t.is_contiguous()
+            and t.dtype in (torch.int64, torch.float64)):
+        _req(t, what)   # raises the precise error
+        raise MarsGBError(1, f"{what}: expected a contiguous 1-D CUDA column")
+
+
 def preagg_dense(keys: Sequence[torch.Tensor], vals: Sequence[torch.Tensor], accs: Sequence[Tuple[int, int]]):
     """Map-side pre-aggregation of one chunk on the low-cardinality path (mgb_preagg_dense): one launch.
     Returns (key tensors, accumulator tensors) or None when the chunk is not a dense shape (too many groups
@@ -213,24 +286,29 @@ def preagg_dense(keys: Sequence[torch.Tensor], vals: Sequence[torch.Tensor], acc
     lib = _lib.load()
     if len(vals) > _lib.MGB_MAX_VALS or len(accs) > _lib.MGB_MAX_ACCS:
         return None
-    keys = [_req(k, f"key {i}", (torch.int64,)) for i, k in enumerate(keys)]
-    vals = [_req(v, f"value {i}") for i, v in enumerate(vals)]
+    for i, k in enumerate(keys):
+        _check_col(k, "key column")
+        if k.dtype != torch.int64:
+            raise MarsGBError(3, f"key {i}: dtype {k.dtype} not supported (int64 keys)")
+    for v in vals:
+        _check_col(v, "value column")
     n = keys[0].numel()
-    dts = [dtype_code(v) for v in vals]
-    spec = _spec(len(keys), dts, accs)
+    fc = _fast(len(keys), [F64 if v.dtype == torch.float64 else I64 for v in vals], accs)
     if _dense_cap is None:
         c = C.c_int64()
         check(lib.mgb_dense_capacity(C.byref(c)))
         _dense_cap = c.value
-    _, okeys, oaccs = _alloc_block(len(keys), dts, accs, _dense_cap, keys[0].device)
-    g = C.c_int64()
-    check(lib.mgb_preagg_dense(C.byref(spec), _ptrs(keys), _ptrs(vals), n, _ptrs(okeys), _ptrs(oaccs), _dense_cap,
-                               C.byref(g), _stream()))
-    if g.value < 0:
+    for j, k in enumerate(keys):
+        fc.kp[j] = k.data_ptr()
+    for j, v in enumerate(vals):
+        fc.vp[j] = v.data_ptr()
+    bi, bf = fc.alloc(_dense_cap, keys[0].device)
+    check(lib.mgb_preagg_dense(C.byref(fc.spec), fc.kp, fc.vp, n, fc.okp, fc.oap, _dense_cap, C.byref(fc.g), _stream()))
+    G = fc.g.value
+    if G < 0:
         return None
     _count(1 if n else 0)
-    G = g.value
-    return [k[:G] for k in okeys], [a[:G] for a in oaccs]
+    return fc.views(bi, bf, G)
 
 
 def merge_small(pieces_keys: Sequence[Sequence[torch.Tensor]], pieces_accs: Sequence[Sequence[torch.Tensor]],
@@ -247,33 +325,34 @@ def merge_small(pieces_keys: Sequence[Sequence[torch.Tensor]], pieces_accs: Sequ
         return None
     nk = len(pieces_keys[0])
     first = pieces_accs[0]
-    dts = [dtype_code(t) for t in first]
-    accs = tuple((a, op) for a, op in enumerate(acc_ops))
-    spec = _spec(nk, dts, accs)
-    for pk, pa in zip(pieces_keys, pieces_accs):
-        for t in pk:
-            _req(t, "piece key", (torch.int64,))
+    dts = [F64 if t.dtype == torch.float64 else I64 for t in first]
+    fc = _fast(nk, dts, tuple((a, op) for a, op in enumerate(acc_ops)))
+    kt = (_lib._pp * max(n_pieces, 1))()
+    at = (_lib._pp * max(n_pieces, 1))()
+    keep = []
+    for i, (pk, pa) in enumerate(zip(pieces_keys, pieces_accs)):
+        karr = (C.c_void_p * nk)()
+        aarr = (C.c_void_p * max(na, 1))()
+        for j, t in enumerate(pk):
+            _check_col(t, "piece key")
+            karr[j] = t.data_ptr()
         for a, t in enumerate(pa):
-            _req(t, "piece accumulator")
-            if dtype_code(t) != dts[a]:
+            _check_col(t, "piece accumulator")
+            if (t.dtype == torch.float64) != (dts[a] == F64):
                 raise MarsGBError(1, "partial blocks differ in accumulator dtype")
-    device = pieces_keys[0][0].device
-    block = torch.empty((nk + na, max(total, 1)), dtype=torch.int64, device=device)
-    okeys = [block[j] for j in range(nk)]
-    oaccs = [block[nk + a] if dts[a] == I64 else block[nk + a].view(torch.float64) for a in range(na)]
+            aarr[a] = t.data_ptr()
+        keep.append((karr, aarr))
+        kt[i] = C.cast(karr, _lib._pp)
+        at[i] = C.cast(aarr, _lib._pp)
+    bi, bf = fc.alloc(total, pieces_keys[0][0].device)
     rows_arr = (C.c_int64 * max(n_pieces, 1))(*rows)
-    key_tabs = [_ptrs(pk) for pk in pieces_keys]
-    acc_tabs = [_ptrs(pa) for pa in pieces_accs]
-    kt = (_lib._pp * max(n_pieces, 1))(*[C.cast(t, _lib._pp) for t in key_tabs])
-    at = (_lib._pp * max(n_pieces, 1))(*[C.cast(t, _lib._pp) for t in acc_tabs])
-    g = C.c_int64()
-    check(lib.mgb_merge_small(C.byref(spec), n_pieces, rows_arr, kt, at, _ptrs(okeys), _ptrs(oaccs), total,
-                              1 if sort else 0, C.byref(g), _stream()))
-    if g.value < 0:
+    check(lib.mgb_merge_small(C.byref(fc.spec), n_pieces, rows_arr, kt, at, fc.okp, fc.oap, total, 1 if sort else 0,
+                              C.byref(fc.g), _stream()))
+    G = fc.g.value
+    if G < 0:
         return None
     _count(1 if total else 0)
-    G = g.value
-    return [k[:G] for k in okeys], [a[:G] for a in oaccs]
+    return fc.views(bi, bf, G)
 
 
 def to_host(columns: Sequence[torch.Tensor]):

@@ -112,6 +112,90 @@ class Session:
         self._owners = owners
         return df
 
+    # ------------------------------------------------------------------------- sharded tree branch
+    def execute_sharded_tree(self, df: DataFrame, group=None, max_groups: int = 2368):
+        """Weak-scaling execution of a low-cardinality (tree-branch) groupby-agg over row chunks that are
+        sharded across ranks -- one process per GPU:
+
+          1. every rank tiles and runs its LOCAL map -> concat/combine tree (independent, no communication);
+          2. the local partial tuple is re-aggregated once (stage=combine semantics) and packed into a
+             fixed-capacity block;
+          3. ONE collective: all_gather of the packed blocks + row counts (NCCL over NVLink; the partials are
+             a few rows, so this is latency-, not bandwidth-bound);
+          4. rank 0 runs the stage=agg operand over the gathered pieces (virtual concat) and owns the result.
+
+        ``df`` is this rank's lazy groupby-agg over its own chunks.  Returns the result frame on rank 0 and
+        None elsewhere.  Falls back to NotImplementedError when a rank holds more than ``max_groups`` groups
+        (then the shuffle branch with the all-to-all exchange is the right plan)."""
+        import torch
+        import torch.distributed as dist
+
+        from .device import DeviceFrame, PiecewiseFrame
+        from .executors import _merge_partials, _pieces_of, _plan_steps
+
+        t = df.data
+        ctx = ProcessorContext()
+        owners: Dict[str, int] = {}
+        world = dist.get_world_size(group)
+        rank = dist.get_rank(group)
+        saved_rank, saved_world = self.rank, self.world
+        self.rank, self.world = 0, 1                      # the local graph runs entirely on this rank
+        try:
+            if t.chunks is None:
+                gen = type(t.op).tile(t.op)
+                try:
+                    to_run = next(gen)
+                    while True:
+                        self._run_chunks(list(to_run), ctx, owners)
+                        to_run = gen.send(None)
+                except StopIteration as stop:
+                    if stop.value is not None and stop.value is not t:
+                        t = stop.value
+            if len(t.chunks) != 1 or getattr(t.chunks[0].op.stage, "name", None) != "agg":
+                raise NotImplementedError("execute_sharded_tree expects the tree branch (one stage=agg chunk)")
+            agg_chunk = t.chunks[0]
+            feed = agg_chunk.op.inputs[0]
+            self._run_chunks([feed], ctx, owners)
+        finally:
+            self.rank, self.world = saved_rank, saved_world
+        steps = _plan_steps(agg_chunk.op, None)
+        merged = _merge_partials(_pieces_of(ctx[feed.key]), steps, sort=False)
+        n = len(merged[0])
+        if n > max_groups:
+            raise NotImplementedError(f"{n} groups on one rank: use the shuffle branch")
+        dev = merged[0].device
+        nk = len(merged[0].index)
+        cols = list(merged[0].index) + [c for f in merged for c in f.data]
+        block = torch.zeros((len(cols), max_groups), dtype=torch.int64, device=dev)
+        for j, c in enumerate(cols):
+            block[j, :n].copy_(c.view(torch.int64))
+        count = torch.tensor([n], dtype=torch.int64, device=dev)
+        blocks = [torch.empty_like(block) for _ in range(world)]
+        counts = [torch.empty_like(count) for _ in range(world)]
+        dist.all_gather(blocks, block, group=group)
+        dist.all_gather(counts, count, group=group)
+        if rank != 0:
+            return None
+        ns = [int(c.item()) for c in counts]
+        slots = []
+        pos = nk
+        for f in merged:
+            pieces = []
+            for r in range(world):
+                keys = [blocks[r][j, :ns[r]] for j in range(nk)]
+                data = [blocks[r][pos + j, :ns[r]].view(t_.dtype) for j, t_ in enumerate(f.data)]
+                pieces.append(DeviceFrame(f.index_names, keys, f.columns, data, ns[r]))
+            slots.append(PiecewiseFrame(pieces))
+            pos += len(f.data)
+        ctx[feed.key] = tuple(slots)
+        ctx.set_current_chunk(agg_chunk)
+        try:
+            core.execute(ctx, agg_chunk.op)
+        except Exception as e:
+            raise core.ExecutionError(e) from e
+        self.executed_ops.append("DataFrameGroupByAgg:agg")
+        return ctx[agg_chunk.key]
+
     def fetch(self, df: DataFrame) -> pd.DataFrame:
         """Concatenate the result chunks in chunk order (multi-GPU: gathered to every rank as pandas)."""
         t = df.data

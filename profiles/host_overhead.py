@@ -26,11 +26,12 @@ t1 = time.perf_counter()
 print(f"preagg_dense wrapper: {1e6 * (t1 - t0) / N:.1f} us per call")
 # raw C call with preallocated outputs
 dts = [K.dtype_code(v) for v in vals]
-spec = K._spec(2, dts, accs)
+fc = K._fast(2, dts, accs)
+spec = fc.spec
 cap = C.c_int64()
 lib.mgb_dense_capacity(C.byref(cap))
-_, ok, oa = K._alloc_block(2, dts, accs, cap.value, "cuda")
-kp, vp, okp, oap = K._ptrs(keys), K._ptrs(vals), K._ptrs(ok), K._ptrs(oa)
+blocks = fc.alloc(cap.value, "cuda")
+kp, vp, okp, oap = K._ptrs(keys), K._ptrs(vals), fc.okp, fc.oap
 gq = C.c_int64()
 st = torch.cuda.current_stream().cuda_stream
 t0 = time.perf_counter()
@@ -49,9 +50,9 @@ print(f"kernel by CUDA events: {1e3 * tot.value / cnt.value:.1f} us per launch (
       f"{rows * 64 / (tot.value / cnt.value * 1e-3) / 1e9:.0f} GB/s algorithmic (64 B/row)")
 t0 = time.perf_counter()
 for _ in range(N):
-    torch.empty((11, cap.value), dtype=torch.int64, device="cuda")
+    fc.alloc(cap.value, "cuda")
 t1 = time.perf_counter()
-print(f"torch.empty block: {1e6 * (t1 - t0) / N:.1f} us")
+print(f"output block allocation: {1e6 * (t1 - t0) / N:.1f} us")
 t0 = time.perf_counter()
 for _ in range(N):
     torch.cuda.current_stream().synchronize()
