@@ -145,57 +145,77 @@ def workload_config(args, world):
 # clocks
 # ----------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled DURING the timed region (NVML in a background thread, 5 ms period;
+    falls back to one `nvidia-smi` query when NVML is unavailable)."""
 
     def __init__(self, device_index: int):
         self.idx = device_index
-        self.proc = None
-        self.path = None
+        self.samples, self.max_mhz, self.reasons = [], None, set()
+        self._stop = threading.Event()
+        self._thread = None
+        self._nvml = None
+
+    def _loop(self):
+        nv, h = self._nvml, self._handle
+        bits = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "sw_power_cap": 0x4}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:  # noqa: BLE001
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for name, bit in bits.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                break
+            self._stop.wait(0.005)
 
     def start(self):
         try:
-            fd, self.path = tempfile.mkstemp(suffix=".csv")
-            os.close(fd)
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "20", "-i", str(self.idx)], stdout=open(self.path, "w"),
-                                         stderr=subprocess.DEVNULL)
+            import pynvml as nv
+
+            nv.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[self.idx]) if visible and visible.split(",")[self.idx].isdigit() else self.idx
+            self._handle = nv.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(self._handle, nv.NVML_CLOCK_SM)
+            self._nvml = nv
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
         except Exception:  # noqa: BLE001
-            self.proc = None
+            self._nvml = None
+
+    def poke(self):
+        """one sample taken by the caller itself (between two steps of the timed region): the background
+        thread can be starved by the GIL while the main thread runs Python"""
+        if self._nvml is not None:
+            try:
+                self.samples.append(self._nvml.nvmlDeviceGetClockInfo(self._handle, self._nvml.NVML_CLOCK_SM))
+            except Exception:  # noqa: BLE001
+                pass
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        if self.proc is None:
-            return out
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:  # noqa: BLE001
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        try:
-            for ln in open(self.path):
-                f = [x.strip() for x in ln.split(",")]
-                if len(f) < 9:
-                    continue
-                try:
-                    sm.append(float(f[1]))
-                    mx.append(float(f[2]))
-                except ValueError:
-                    continue
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            os.unlink(self.path)
+        if self._nvml is not None:
+            self._stop.set()
+            self._thread.join(timeout=2)
+            if self.samples:
+                out.update(sm_mhz=statistics.median(self.samples), sm_max_mhz=self.max_mhz, samples=len(self.samples),
+                           reasons=sorted(self.reasons), source="nvml: background thread (5 ms) + one sample after every step, inside the timed region")
+                return out
+        try:   # fallback: one nvidia-smi query right after the timed region
+            q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+                "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+            txt = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.idx)],
+                                 capture_output=True, text=True, timeout=10).stdout.strip().splitlines()[0]
+            f = [x.strip() for x in txt.split(",")]
+            out.update(sm_mhz=float(f[0]), sm_max_mhz=float(f[1]), samples=1, source="nvidia-smi after the timed region",
+                       reasons=[n for n, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                                   "sw_power_cap"), f[2:6]) if v.lower().startswith("active")])
         except Exception:  # noqa: BLE001
             pass
-        if sm:
-            # under load = samples in the upper half of the observed range
-            out["sm_mhz"] = statistics.median(sm)
-            out["sm_max_mhz"] = max(mx)
-            out["samples"] = len(sm)
-        out["reasons"] = sorted(reasons)
         return out
 
 
@@ -212,9 +232,9 @@ def main_ours(args):
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         n_chunks = max(2, min(8, cores))
-        rps, times = cpu_path(n_chunks, args.chunk_rows, 2, 1, cores)
+        rps, times = cpu_path(n_chunks, args.chunk_rows, 4, 1, cores)
         cpu_baseline = {"value": rps, "unit": "rows/s", "cores": cores, "kind": "port",
-                        "sample": f"{n_chunks} chunks x {args.chunk_rows} rows per step, 2 steps after 1 warm-up, "
+                        "sample": f"{n_chunks} chunks x {args.chunk_rows} rows per step, 4 steps after 1 warm-up, "
                                   f"oracle port (pandas) of the reference operands, map stage on {cores} processes; "
                                   f"{sum(times):.1f} s"}
 
@@ -275,7 +295,7 @@ def main_ours(args):
             out = sess.execute_sharded_tree(r)
         return out
 
-    def timed(resident: bool, steps: int, warmup: int):
+    def timed(resident: bool, steps: int, warmup: int, sampler=None):
         for _ in range(warmup):
             step(resident)
         barrier()
@@ -284,6 +304,8 @@ def main_ours(args):
         e0.record()
         for _ in range(steps):
             out = step(resident)
+            if sampler is not None:
+                sampler.poke()
         e1.record()
         barrier()
         wall = time.perf_counter() - t0
@@ -309,7 +331,7 @@ def main_ours(args):
     lib.mgb_prof_reset()
     launches0 = kernels.launch_counter
     sampler.start()
-    ms, out = timed(True, args.steps, 0)
+    ms, out = timed(True, args.steps, 0, sampler)
     clocks = sampler.stop()
     launches = kernels.launch_counter - launches0
     import ctypes as C
@@ -338,11 +360,11 @@ def main_ours(args):
         per_launch_ms = dom["ms_total"] / dom["launches"]
         rows_per_launch = rows_rank * args.steps / dom["launches"]
         achieved = rows_per_launch * BYTES_PER_ROW / (per_launch_ms * 1e-3) / 1e9
-        traffic = None
+        traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu capture
         tpath = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
         if os.path.exists(tpath):
             try:
-                traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+                traffic = json.load(open(tpath))["dram_bytes_per_row"] * rows_per_launch
             except Exception:  # noqa: BLE001
                 traffic = None
         value = total_rows * args.steps / (ms * 1e-3)
@@ -357,7 +379,7 @@ def main_ours(args):
                     "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "k_preagg_tiny" if "preagg_tiny" in prof else "k_preagg_smem",
+                         "traffic": traffic, "kernel": "k_preagg_dense" if "preagg_tiny" in prof else "k_preagg_smem",
                          "kernel_ms_per_launch": per_launch_ms, "bytes_per_launch": rows_per_launch * BYTES_PER_ROW,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
                          "step_hbm_frac": (rows_rank * BYTES_PER_ROW / (ms / args.steps * 1e-3) / 1e9) / peak},

@@ -1,0 +1,88 @@
+"""Registration of the GPU executors on the REAL reference classes (when ``mars`` is importable).
+
+This module is what a Mars deployment loads into every GPU-band sub-process so that the operands of the
+groupby-aggregation path run on libmarsgb.so instead of pandas/cudf.  Loading mechanisms offered by the
+reference (all unchanged host code):
+
+  * service YAML ``third_party_modules: [mars_b200.plugin]`` or env ``MARS_LOAD_MODULES=mars_b200.plugin``
+    (mars/deploy/utils.py:193-219, mars/oscar/backends/pool.py:712-715) -- the module is imported in every
+    pool process; importing it calls ``register_on_mars()``;
+  * setuptools entry point group ``mars_extensions`` -> ``init`` (mars/core/entrypoints.py:24-42);
+  * per-run ``extra_config={"operand_executors": {...}}`` under the checked test processor
+    (mars/services/subtask/worker/tests/subtask_processor.py:58-62).
+
+The executors are the same functions that serve the host mirror (``mars_b200.executors``): they only use
+the operand protocol (``op.stage``, ``op.inputs/outputs``, ``op.groupby_params``, ``op.pre_funcs/agg_funcs/
+post_funcs``, ``op.shuffle_size``, ``op.iter_mapper_data(ctx)``, ``ctx.get_current_chunk()``).
+
+Fallback contract (SURVEY.md section 8b "Errors"): an executor that meets something outside the GPU envelope
+(object keys, custom reductions, sort=True PSRS shuffle chunks, CPU bands) raises NotImplementedError
+*before touching data*; ``_with_reference_fallback`` then calls the class's own ``execute`` -- the
+reference's pandas path -- explicitly, because the dispatcher itself does not fall back to it
+(mars/core/operand/core.py:501-509).  Ops placed on CPU bands (``op.gpu`` false) always take the reference
+path: this plugin only claims GPU bands.
+"""
+from __future__ import annotations
+
+import functools
+
+from . import executors
+
+
+def _with_reference_fallback(cls, fn, gpu_only=True):
+    reference_execute = cls.execute
+
+    @functools.wraps(fn)
+    def wrapped(ctx, op):
+        if gpu_only and not getattr(op, "gpu", False):
+            return reference_execute(ctx, op)
+        try:
+            return fn(ctx, op)
+        except NotImplementedError:
+            return reference_execute(ctx, op)
+
+    return wrapped
+
+
+def register_on_mars(gpu_only: bool = True):
+    """Install the executors on mars.dataframe's operand classes.  Returns the list of patched classes."""
+    from mars.dataframe.base.to_cpu import DataFrameToCPU
+    from mars.dataframe.base.to_gpu import DataFrameToGPU
+    from mars.dataframe.groupby.aggregation import DataFrameGroupByAgg
+    from mars.dataframe.groupby.core import DataFrameGroupByOperand
+    from mars.dataframe.merge.concat import DataFrameConcat
+
+    table = [
+        (DataFrameGroupByAgg, executors.execute_groupby_agg),
+        (DataFrameGroupByOperand, executors.execute_groupby_operand),
+        (DataFrameConcat, executors.execute_concat),
+        (DataFrameToGPU, executors.execute_to_gpu),
+        (DataFrameToCPU, executors.execute_to_cpu),
+    ]
+    for cls, fn in table:
+        cls.register_executor(_with_reference_fallback(cls, fn, gpu_only=gpu_only))
+    return [cls for cls, _ in table]
+
+
+def unregister_on_mars():
+    from mars.dataframe.base.to_cpu import DataFrameToCPU
+    from mars.dataframe.base.to_gpu import DataFrameToGPU
+    from mars.dataframe.groupby.aggregation import DataFrameGroupByAgg
+    from mars.dataframe.groupby.core import DataFrameGroupByOperand
+    from mars.dataframe.merge.concat import DataFrameConcat
+
+    for cls in (DataFrameGroupByAgg, DataFrameGroupByOperand, DataFrameConcat, DataFrameToGPU, DataFrameToCPU):
+        cls.unregister_executor()
+
+
+def init():
+    """entry point for the ``mars_extensions`` group"""
+    register_on_mars()
+
+
+try:  # imported through third_party_modules / MARS_LOAD_MODULES inside a Mars pool process
+    import mars  # noqa: F401
+except ImportError:  # the host mirror is used instead (mars_b200.dataframe)
+    pass
+else:
+    register_on_mars()

@@ -1,0 +1,78 @@
+"""Drop-in check against the REAL reference operands (build container only: needs the shimmed reference
+build of oracle/build_ref.sh; skipped on the GPU box, where /root/reference does not exist).
+
+The reference's own chunk graph (its tiling, its ReductionCompiler output, its chunk metas) is executed with
+the executors of this package registered through ``Operand.register_executor`` -- the seam of SURVEY.md
+section 8b -- and the result is compared with the reference's own pandas path.  Runs on CPU with the test
+double of the kernels module, so what is verified here is the operand-protocol side of the executors: that
+they understand the real ``op.pre_funcs / agg_funcs / post_funcs`` callables, the real shuffle keys and chunk
+metas.  The CUDA side is verified by the -m gpu tests against the same golden outputs."""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import pandas as pd
+import pytest
+import torch
+
+import fake_kernels
+from conftest import assert_frames_match
+
+REF_DIR = os.environ.get("MARS_REF_DIR", "/tmp/mars_ref")
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF_DIR, "mars")),
+                                reason="shimmed reference build not present (build container only)")
+
+
+@pytest.fixture()
+def ref(monkeypatch):
+    import ref_runner
+
+    ref_runner._import_reference()
+    from mars_b200 import executors, plugin
+
+    monkeypatch.setattr(executors, "_kernels", fake_kernels)
+    monkeypatch.setattr(executors, "_device", lambda: torch.device("cpu"))
+    plugin.register_on_mars(gpu_only=False)
+    yield ref_runner
+    plugin.unregister_on_mars()
+
+
+CASES = [
+    ("key", ["sum", "mean", "count", "min", "max", "var"], "tree", True),
+    ("key", ["sum", "mean", "count", "min", "max", "var"], "shuffle", False),
+    (["k1", "k2"], ["min", "max", "var"], "shuffle", False),
+    (["k1", "k2"], {"v0": ["sum", "mean"], "v1": ["count"]}, "tree", True),
+    ("key", "sum", "tree", True),
+]
+
+
+@pytest.mark.parametrize("by,func,method,sort", CASES)
+def test_real_reference_graph_runs_on_our_executors(ref, by, func, method, sort):
+    rng = np.random.default_rng(7)
+    n = 2000
+    raw = pd.DataFrame({"key": rng.integers(-20, 20, n), "k1": rng.integers(0, 6, n), "k2": rng.integers(0, 4, n),
+                        "v0": rng.normal(10, 3, n), "v1": rng.random(n)})
+    cols = (["key"] if by == "key" else by) + ["v0", "v1"]
+    raw = raw[cols]
+    fake_kernels.calls.clear()
+    out = ref.run_reference(raw, by, func, 250, method=method, sort=sort)
+    assert "groupby_aggregate" in fake_kernels.calls, "the registered executors did not run"
+    exp = raw.groupby(by, sort=True).agg(func)
+    got = out["result"]
+    if isinstance(exp, pd.Series):
+        exp = exp.to_frame()
+    assert_frames_match(got.sort_index(), exp, sort_index=False)
+    ops = {(r["op"], r["stage"]) for r in out["records"]}
+    assert ("DataFrameGroupByAgg", "map") in ops and ("DataFrameGroupByAgg", "agg") in ops
+    if method == "shuffle":
+        assert ("DataFrameGroupByOperand", "map") in ops and ("DataFrameGroupByOperand", "reduce") in ops
+
+
+def test_unsupported_inputs_fall_back_to_the_reference_path(ref):
+    # object (string) keys are outside the GPU envelope: the plugin must hand the op to the reference executor
+    raw = pd.DataFrame({"key": list("abcab") * 40, "v": np.arange(200.0)})
+    out = ref.run_reference(raw, "key", ["sum", "count"], 50, method="tree", sort=True)
+    exp = raw.groupby("key").agg(["sum", "count"])
+    pd.testing.assert_frame_equal(out["result"], exp)
