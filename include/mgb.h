@@ -131,6 +131,22 @@ int mgb_merge_small(const mgb_agg_spec* spec, int32_t n_pieces, const int64_t* p
                     const int64_t* const* const* piece_key_cols, const void* const* const* piece_acc_cols,
                     int64_t* const* out_key_cols, void* const* out_acc_cols, int64_t out_capacity,
                     int32_t sort_keys, int64_t* out_n_groups, void* stream);
+/* Asynchronous variants: no host synchronisation, so a chain map -> combine -> ... -> agg of one subtask
+ * (the processor runs a subtask's operands back to back, processor.py:216-282) is enqueued without the host
+ * waiting for any intermediate size.  The group count goes to *out_n_dev, a caller-owned DEVICE int64
+ * (>= 0, or -1 for "not a dense / small input": then nothing useful was written and the caller redoes the
+ * step on the general path once it has read the count).  mgb_merge_small_async accepts pieces whose size is
+ * not known on the host yet: piece_rows[i] < 0 means "read it from the device int64 *piece_rows_dev[i]"
+ * (the out_n_dev of an earlier asynchronous call); a -1 found there propagates to *out_n_dev.  Output columns
+ * need capacity mgb_dense_capacity() rows resp. min(out_capacity, 2048).                                  */
+int mgb_preagg_dense_async(const mgb_agg_spec* spec, const int64_t* const* key_cols, const void* const* val_cols,
+                           int64_t n_rows, int64_t* const* out_key_cols, void* const* out_acc_cols,
+                           int64_t out_capacity, int64_t* out_n_dev, void* stream);
+int mgb_merge_small_async(const mgb_agg_spec* spec, int32_t n_pieces, const int64_t* piece_rows,
+                          const int64_t* const* piece_rows_dev, const int64_t* const* const* piece_key_cols,
+                          const void* const* const* piece_acc_cols, int64_t* const* out_key_cols,
+                          void* const* out_acc_cols, int64_t out_capacity, int32_t sort_keys, int64_t* out_n_dev,
+                          void* stream);
 
 /* Host-buffer convenience used by the end-to-end path: key/value columns live in (pinned) host memory,
  * are streamed to the device in row blocks overlapped with the kernels, and the result is written to

@@ -70,6 +70,9 @@ SIGNATURES = {
     "mgb_preagg_dense": (C.c_int, [C.POINTER(AggSpec), _pp, _pp, _i64, _pp, _pp, _i64, C.POINTER(_i64), _vp]),
     "mgb_merge_small": (C.c_int, [C.POINTER(AggSpec), _i32, C.POINTER(_i64), C.POINTER(_pp), C.POINTER(_pp), _pp, _pp,
                                   _i64, _i32, C.POINTER(_i64), _vp]),
+    "mgb_preagg_dense_async": (C.c_int, [C.POINTER(AggSpec), _pp, _pp, _i64, _pp, _pp, _i64, _vp, _vp]),
+    "mgb_merge_small_async": (C.c_int, [C.POINTER(AggSpec), _i32, C.POINTER(_i64), _pp, C.POINTER(_pp), C.POINTER(_pp),
+                                        _pp, _pp, _i64, _i32, _vp, _vp]),
     "mgb_groupby_agg_host": (
         C.c_int,
         [C.POINTER(AggSpec), _pp, _pp, _i64, _i64, _pp, _pp, _i64, _i32, C.POINTER(_i64), _vp],

@@ -62,23 +62,25 @@ extern "C" int mgb_dense_capacity(int64_t* out_rows) {
   return MGB_OK;
 }
 
-extern "C" int mgb_preagg_dense(const mgb_agg_spec* spec, const int64_t* const* key_cols,
-                                const void* const* val_cols, int64_t n_rows, int64_t* const* out_key_cols,
-                                void* const* out_acc_cols, int64_t out_capacity, int64_t* out_n_groups,
-                                void* stream) {
-  MGB_REQUIRE(spec && key_cols && val_cols && out_key_cols && out_acc_cols && out_n_groups, MGB_ERR_INVALID,
+// sets *out_n_dev (device) to `value` in stream order: -1 = "not a dense shape", 0 = empty input
+static int dense_set_count(int64_t* out_n_dev, int value, cudaStream_t st) {
+  MGB_CUDA(cudaMemsetAsync(out_n_dev, value < 0 ? 0xFF : 0, sizeof(int64_t), st));
+  return MGB_OK;
+}
+
+extern "C" int mgb_preagg_dense_async(const mgb_agg_spec* spec, const int64_t* const* key_cols,
+                                      const void* const* val_cols, int64_t n_rows, int64_t* const* out_key_cols,
+                                      void* const* out_acc_cols, int64_t out_capacity, int64_t* out_n_dev,
+                                      void* stream) {
+  MGB_REQUIRE(spec && key_cols && val_cols && out_key_cols && out_acc_cols && out_n_dev, MGB_ERR_INVALID,
               "null pointer");
   cudaStream_t st = (cudaStream_t)stream;
-  *out_n_groups = -1;
   const int nk = spec->n_keys, na = spec->n_accs;
   MGB_REQUIRE(nk >= 1 && nk <= MGB_MAX_KEYS, MGB_ERR_UNSUPPORTED, "n_keys=%d", nk);
   MGB_REQUIRE(na >= 1 && na <= MGB_MAX_ACCS && spec->n_vals >= 1 && spec->n_vals <= MGB_MAX_VALS,
               MGB_ERR_UNSUPPORTED, "spec outside the supported envelope");
   MGB_REQUIRE(n_rows >= 0, MGB_ERR_INVALID, "negative n_rows");
-  if (n_rows == 0) {
-    *out_n_groups = 0;
-    return MGB_OK;
-  }
+  if (n_rows == 0) return dense_set_count(out_n_dev, 0, st);
   DenseParams p;
   memset(&p, 0, sizeof(p));
   // columns that must be read: everything except int64 columns that are only counted
@@ -92,7 +94,7 @@ extern "C" int mgb_preagg_dense(const mgb_agg_spec* spec, const int64_t* const* 
     loaded_of[c] = -1;
     if (m == 0) continue;
     if (spec->val_dtype[c] == MGB_I64 && m == OPB(MGB_COUNT)) continue;
-    if (ncol == 8) return MGB_OK;   // more than 8 live columns: not a dense-path shape (caller falls back)
+    if (ncol == 8) return dense_set_count(out_n_dev, -1, st);   // more than 8 live columns: not a dense shape
     MGB_REQUIRE(val_cols[c], MGB_ERR_INVALID, "null value column %d", c);
     loaded_of[c] = ncol;
     p.cols[ncol] = (const uint64_t*)val_cols[c];
@@ -108,7 +110,7 @@ extern "C" int mgb_preagg_dense(const mgb_agg_spec* spec, const int64_t* const* 
     p.out.key[j] = (uint64_t*)out_key_cols[j];
   }
   p.n = n_rows;
-  if (ncol == 0) return MGB_OK;   // nothing but counts of int64 columns: leave it to the general path
+  if (ncol == 0) return dense_set_count(out_n_dev, -1, st);   // only counts of int64 columns: general path
   // accumulator block of one (warp, group), 32-bit words: rows[32] | sum[ncol][64] | (sumsq|min|max)[ncol][64]
   // | nan[32] (lane-private 8-byte slots except the per-column NaN counters, which are touched rarely)
   const uint32_t all_cols = (1u << ncol) - 1u;
@@ -141,7 +143,7 @@ extern "C" int mgb_preagg_dense(const mgb_agg_spec* spec, const int64_t* const* 
   }
   if (GC > DN_MAX_GC) GC = DN_MAX_GC;
   if (env_gc && atoi(env_gc) >= 2 && atoi(env_gc) < GC) GC = atoi(env_gc);
-  if (GC < 2) return MGB_OK;   // accumulators of a single group do not fit: general path
+  if (GC < 2) return dense_set_count(out_n_dev, -1, st);   // accumulators of one group do not fit: general path
   p.GC = GC;
   const int n_warps = threads / 32;
   const long long tile_rows = 1024;
@@ -159,7 +161,7 @@ extern "C" int mgb_preagg_dense(const mgb_agg_spec* spec, const int64_t* const* 
   p.cta_ng = s->ints;
   p.ticket = (unsigned int*)(s->ints + 1024);
   p.fail = s->ints + 1025;
-  p.out_n = s->out_n;
+  p.out_n = (long long*)out_n_dev;
   MGB_CUDA(cudaMemsetAsync(s->ints + 1024, 0, 2 * sizeof(int), st));
   p.out.na = na;
   for (int a = 0; a < na; ++a) {
@@ -197,10 +199,8 @@ extern "C" int mgb_preagg_dense(const mgb_agg_spec* spec, const int64_t* const* 
                               : mgb_dense_launch_2_256(p, ncol, plain, grid, smem, st);
     MGB_TRY(status);
   }
-  MGB_CUDA(cudaMemcpyAsync(s->out_n_host, s->out_n, sizeof(long long), cudaMemcpyDeviceToHost, st));
-  MGB_CUDA(cudaStreamSynchronize(st));
-  *out_n_groups = s->out_n_host[0];
   if (dbg) {
+    MGB_CUDA(cudaStreamSynchronize(st));
     long long* h = (long long*)malloc(sizeof(long long) * (4 * grid + 8));
     cudaMemcpy(h, dbg, sizeof(long long) * (4 * grid + 8), cudaMemcpyDeviceToHost);
     long long t0 = h[0], mx[4] = {0, 0, 0, 0}, mn[4] = {1LL << 62, 1LL << 62, 1LL << 62, 1LL << 62};
@@ -222,126 +222,203 @@ extern "C" int mgb_preagg_dense(const mgb_agg_spec* spec, const int64_t* const* 
   return MGB_OK;
 }
 
+extern "C" int mgb_preagg_dense(const mgb_agg_spec* spec, const int64_t* const* key_cols,
+                                const void* const* val_cols, int64_t n_rows, int64_t* const* out_key_cols,
+                                void* const* out_acc_cols, int64_t out_capacity, int64_t* out_n_groups,
+                                void* stream) {
+  MGB_REQUIRE(out_n_groups, MGB_ERR_INVALID, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  *out_n_groups = -1;
+  int dev = 0;
+  MGB_CUDA(cudaGetDevice(&dev));
+  DenseScratch* s = nullptr;
+  MGB_TRY(dense_scratch(dev, 0, 1, &s));
+  MGB_TRY(mgb_preagg_dense_async(spec, key_cols, val_cols, n_rows, out_key_cols, out_acc_cols, out_capacity,
+                                 (int64_t*)s->out_n, stream));
+  MGB_CUDA(cudaMemcpyAsync(s->out_n_host, s->out_n, sizeof(long long), cudaMemcpyDeviceToHost, st));
+  MGB_CUDA(cudaStreamSynchronize(st));
+  *out_n_groups = s->out_n_host[0];
+  return MGB_OK;
+}
+
 // --------------------------------------------------------------------------------------------------
-// small merge
+// small merge: one CTA, no atomics on the values, no host synchronisation required
 // --------------------------------------------------------------------------------------------------
 struct SmallPiece {
   const uint64_t* key[MGB_MAX_KEYS];
-  int n;
+  const long long* n_dev;   // device row count of the piece (output count of an earlier call), or nullptr
+  int n;                    // host-known row count (used when n_dev == nullptr)
 };
 
 struct SmallParams {
   int n_pieces;
-  int total;
+  int out_cap;
   SmallPiece piece[SM_MAX_PIECES];
-  const uint64_t* const* acc_ptrs;   // device table [piece][acc] (written by the host through pinned staging)
-  OutCols out;                       // final destination columns
-  uint64_t* tmp;                     // scratch rows for the sorted variant: [(nk + na)][total]
+  const uint64_t* const* acc_ptrs;   // device table [piece][acc]
+  OutCols out;                       // destination columns; op: MGB_SUM / MGB_MIN / MGB_MAX, dt: column dtype
   int sort;
-  long long* out_n;
+  long long* out_n;                  // device: number of groups, -1: not a small input / an input had failed
 };
 
 template <int NK>
 __global__ void __launch_bounds__(SM_THREADS, 1) k_merge_small(const SmallParams p) {
   extern __shared__ __align__(16) uint32_t ssm[];
-  uint64_t* tab_keys = (uint64_t*)ssm;                        // [NK][SM_TAB]
-  int* tab_idx = (int*)(tab_keys + MGB_MAX_KEYS * SM_TAB);    // [SM_TAB]
-  int& n_unique = tab_idx[SM_TAB];
-  for (int i = threadIdx.x; i < SM_TAB; i += SM_THREADS) tab_idx[i] = -1;
-  if (threadIdx.x == 0) n_unique = 0;
-  // when sorting, accumulate into scratch columns first, then scatter by rank
-  OutCols acc = p.out;
-  if (p.sort) {
-    for (int j = 0; j < NK; ++j) acc.key[j] = p.tmp + (size_t)j * p.total;
-    for (int a = 0; a < p.out.na; ++a) acc.acc[a] = p.tmp + (size_t)(NK + a) * p.total;
-  }
-  out_init(acc, p.total);
-  __threadfence();
-  __syncthreads();
-  for (int i = threadIdx.x; i < p.total; i += SM_THREADS) {
-    int pc = 0, r = i;
-    while (r >= p.piece[pc].n) {
-      r -= p.piece[pc].n;
-      ++pc;
+  constexpr int MAXR = MGB_SMALL_MAX_ROWS;
+  // layout (bytes): tab_keys 2*4096*8 | ukeys 2*2048*8 | tab_idx 4096*4 | item_idx, item_r, ucnt(+1), ufill, sorted,
+  //                 rank: 2048*4 each | item_pc 2048 | ints
+  uint64_t* tab_keys = (uint64_t*)ssm;
+  uint64_t* ukeys = tab_keys + MGB_MAX_KEYS * SM_TAB;
+  int* tab_idx = (int*)(ukeys + MGB_MAX_KEYS * MAXR);
+  int* item_idx = tab_idx + SM_TAB;
+  int* item_r = item_idx + MAXR;
+  int* ucnt = item_r + MAXR;            // MAXR + 1 (+ pad)
+  int* ufill = ucnt + MAXR + 2;
+  int* sorted = ufill + MAXR;
+  int* rank = sorted + MAXR;
+  unsigned char* item_pc = (unsigned char*)(rank + MAXR);
+  int* s_int = (int*)(item_pc + MAXR);
+  int* n_unique = s_int;                // [0]
+  int* s_total = s_int + 1;
+  int* pstart = s_int + 2;              // [SM_MAX_PIECES + 1]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int na = p.out.na;
+
+  if (threadIdx.x == 0) {
+    int total = 0;
+    bool bad = false;
+    for (int i = 0; i < p.n_pieces; ++i) {
+      long long n = p.piece[i].n_dev ? *(volatile const long long*)p.piece[i].n_dev : (long long)p.piece[i].n;
+      if (n < 0) bad = true;
+      pstart[i] = total;
+      total += n > 0 ? (int)(n > MAXR + 1 ? MAXR + 1 : n) : 0;
+      if (total > MAXR) bad = true;
     }
+    pstart[p.n_pieces] = total;
+    if (bad || total > p.out_cap) total = -1;
+    *s_total = total;
+    *n_unique = 0;
+  }
+  __syncthreads();
+  const int total = *s_total;
+  if (total < 0) {
+    if (threadIdx.x == 0) *p.out_n = -1;
+    return;
+  }
+  // hash table sized to the input: 2 * total rounded up to a power of two (>= 64)
+  int tsize = 64;
+  while (tsize < 2 * total) tsize <<= 1;
+  const uint32_t tmask = (uint32_t)tsize - 1u;
+  for (int i = threadIdx.x; i < tsize; i += SM_THREADS) tab_idx[i] = -1;
+  __syncthreads();
+  // pass 1: output row of every input row
+  for (int it = threadIdx.x; it < total; it += SM_THREADS) {
+    int pc = 0;
+    while (it >= pstart[pc + 1]) ++pc;
+    const int r = it - pstart[pc];
     uint64_t k[NK];
 #pragma unroll
-    for (int j = 0; j < NK; ++j) k[j] = p.piece[pc].key[j][r];
-    const int idx = small_find_or_insert<NK>(tab_keys, tab_idx, &n_unique, k);
-    if (idx < 0) continue;
+    for (int j = 0; j < NK; ++j) k[j] = ld_cg(p.piece[pc].key[j] + r);
+    const int idx = small_find_or_insert<NK>(tab_keys, tab_idx, n_unique, k, tmask);
+    item_idx[it] = idx;
+    item_r[it] = r;
+    item_pc[it] = (unsigned char)pc;
 #pragma unroll
-    for (int j = 0; j < NK; ++j) acc.key[j][idx] = k[j];
-    for (int a = 0; a < p.out.na; ++a) {
-      const uint64_t* col = p.acc_ptrs[pc * p.out.na + a];
-      out_accumulate(acc, a, idx, col[r]);
+    for (int j = 0; j < NK; ++j) ukeys[j * MAXR + idx] = k[j];   // same value from every writer
+  }
+  __syncthreads();
+  const int nu = *n_unique;
+  // output position of every unique key: rank by key tuple when sorting (keys are unique), else table order
+  for (int u = threadIdx.x; u < nu; u += SM_THREADS) {
+    int pos = u;
+    if (p.sort) {
+      uint64_t k[NK];
+#pragma unroll
+      for (int j = 0; j < NK; ++j) k[j] = ukeys[j * MAXR + u];
+      pos = 0;
+      for (int q = 0; q < nu; ++q) {
+        uint64_t o[NK];
+#pragma unroll
+        for (int j = 0; j < NK; ++j) o[j] = ukeys[j * MAXR + q];
+        pos += key_less<NK>(o, k) ? 1 : 0;
+      }
+    }
+    rank[u] = pos;
+#pragma unroll
+    for (int j = 0; j < NK; ++j) p.out.key[j][pos] = ukeys[j * MAXR + u];
+  }
+  // counting sort of the input rows by output row
+  for (int i = threadIdx.x; i <= nu; i += SM_THREADS) ucnt[i] = 0;
+  for (int i = threadIdx.x; i < nu; i += SM_THREADS) ufill[i] = 0;
+  __syncthreads();
+  for (int it = threadIdx.x; it < total; it += SM_THREADS) atomicAdd(&ucnt[item_idx[it]], 1);
+  __syncthreads();
+  if (warp == 0) {
+    int carry = 0;
+    for (int base = 0; base <= nu; base += 32) {
+      const int i = base + lane;
+      const int v = i <= nu ? ucnt[i] : 0;
+      int x = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+      }
+      if (i <= nu) ucnt[i] = carry + x - v;
+      carry += __shfl_sync(0xffffffffu, x, 31);
     }
   }
-  __threadfence();
   __syncthreads();
-  const int nu = n_unique;
-  out_decode(acc, nu);
+  for (int it = threadIdx.x; it < total; it += SM_THREADS) {
+    const int u = item_idx[it];
+    sorted[ucnt[u] + atomicAdd(&ufill[u], 1)] = it;
+  }
+  __syncthreads();
+  // 8 lanes per (output row, accumulator): contributions straight from L2, combined by shuffles
+  const int sl = lane & 7, pl = lane >> 3;
+  constexpr int WARPS = SM_THREADS / 32;
+  for (int pair0 = 0; pair0 < nu * na; pair0 += WARPS * 4) {
+    const int pair = pair0 + warp * 4 + pl;
+    const bool on = pair < nu * na;
+    const int u = on ? pair / na : 0, a = on ? pair - u * na : 0;
+    const int op = p.out.op[a];
+    const bool f = p.out.dt[a] == MGB_F64;
+    const int kind = op == MGB_MIN ? 3 : op == MGB_MAX ? 4 : 1;
+    // identity: 0 for sums / counts; NaN (ignored by fmin / fmax) for float min / max; extremes for int
+    uint64_t v = 0;
+    if (kind == 3) v = f ? 0x7ff8000000000000ULL : 0x7fffffffffffffffULL;
+    if (kind == 4) v = f ? 0x7ff8000000000000ULL : 0x8000000000000000ULL;
+    const int q1 = on ? ucnt[u + 1] : 0;
+#pragma unroll 4
+    for (int q = (on ? ucnt[u] : 0) + sl; q < q1; q += 8) {
+      const int it = sorted[q];
+      const uint64_t* col = p.acc_ptrs[item_pc[it] * na + a];
+      v = dense_combine(kind, f, v, ld_cg(col + item_r[it]));
+    }
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) v = dense_combine(kind, f, v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (on && sl == 0) p.out.acc[a][rank[u]] = v;
+  }
   if (threadIdx.x == 0) *p.out_n = nu;
-  if (!p.sort) return;
-  __threadfence();
-  __syncthreads();
-  // rank sort (nu <= 2048): rank = number of smaller key tuples; keys are unique
-  for (int i = threadIdx.x; i < nu; i += SM_THREADS) {
-    uint64_t k[NK];
-#pragma unroll
-    for (int j = 0; j < NK; ++j) k[j] = ld_cg(acc.key[j] + i);
-    int rank = 0;
-    for (int q = 0; q < nu; ++q) {
-      uint64_t o[NK];
-#pragma unroll
-      for (int j = 0; j < NK; ++j) o[j] = ld_cg(acc.key[j] + q);
-      rank += key_less<NK>(o, k) ? 1 : 0;
-    }
-#pragma unroll
-    for (int j = 0; j < NK; ++j) p.out.key[j][rank] = k[j];
-    for (int a = 0; a < p.out.na; ++a) p.out.acc[a][rank] = ld_cg(acc.acc[a] + i);
-  }
 }
 
 struct SmallScratch {
-  uint64_t* tmp = nullptr;
-  size_t tmp_words = 0;
   const uint64_t** ptrs_dev = nullptr;
   const uint64_t** ptrs_host = nullptr;   // pinned ring: SLOTS tables of SM_MAX_PIECES * MGB_MAX_ACCS pointers
+  cudaEvent_t ev[64] = {nullptr};         // completion of the launch that last used a slot
+  bool used[64] = {false};
   int slot = 0;
-  long long* out_n = nullptr;
+  long long* out_n = nullptr;             // scratch count for the synchronous entry point
   long long* out_n_host = nullptr;
 };
-#define SMALL_SLOTS 8
+#define SMALL_SLOTS 64
 static thread_local SmallScratch g_ss[8];
 
-extern "C" int mgb_merge_small(const mgb_agg_spec* spec, int32_t n_pieces, const int64_t* piece_rows,
-                               const int64_t* const* const* piece_key_cols,
-                               const void* const* const* piece_acc_cols, int64_t* const* out_key_cols,
-                               void* const* out_acc_cols, int64_t out_capacity, int32_t sort_keys,
-                               int64_t* out_n_groups, void* stream) {
-  MGB_REQUIRE(spec && piece_rows && piece_key_cols && piece_acc_cols && out_key_cols && out_acc_cols &&
-                  out_n_groups, MGB_ERR_INVALID, "null pointer");
-  cudaStream_t st = (cudaStream_t)stream;
-  *out_n_groups = -1;
-  const int nk = spec->n_keys, na = spec->n_accs;
-  MGB_REQUIRE(nk >= 1 && nk <= MGB_MAX_KEYS && na >= 1 && na <= MGB_MAX_ACCS, MGB_ERR_UNSUPPORTED,
-              "spec outside the supported envelope");
-  long long total = 0;
-  int used = 0;
-  for (int i = 0; i < n_pieces; ++i) {
-    MGB_REQUIRE(piece_rows[i] >= 0, MGB_ERR_INVALID, "negative piece size");
-    total += piece_rows[i];
-    if (piece_rows[i] > 0) ++used;
-  }
-  if (total == 0) {
-    *out_n_groups = 0;
-    return MGB_OK;
-  }
-  if (total > MGB_SMALL_MAX_ROWS || used > SM_MAX_PIECES) return MGB_OK;   // not small: general path
-  MGB_REQUIRE(out_capacity >= total, MGB_ERR_INVALID, "output capacity %lld < %lld rows",
-              (long long)out_capacity, total);
-  int dev = 0;
-  MGB_CUDA(cudaGetDevice(&dev));
+static size_t small_smem_bytes() {
+  return (size_t)MGB_MAX_KEYS * SM_TAB * 8 + (size_t)MGB_MAX_KEYS * MGB_SMALL_MAX_ROWS * 8 + SM_TAB * 4 +
+         6 * ((size_t)MGB_SMALL_MAX_ROWS + 2) * 4 + MGB_SMALL_MAX_ROWS + (SM_MAX_PIECES + 8) * 4 + 64;
+}
+
+static int small_scratch(int dev, SmallScratch** out) {
   MGB_REQUIRE(dev >= 0 && dev < 8, MGB_ERR_UNSUPPORTED, "device ordinal %d", dev);
   SmallScratch& s = g_ss[dev];
   const size_t table_words = (size_t)SM_MAX_PIECES * MGB_MAX_ACCS;
@@ -350,17 +427,59 @@ extern "C" int mgb_merge_small(const mgb_agg_spec* spec, int32_t n_pieces, const
     MGB_CUDA(cudaMallocHost((void**)&s.ptrs_host, table_words * 8 * SMALL_SLOTS));
     MGB_CUDA(cudaMalloc((void**)&s.out_n, 16));
     MGB_CUDA(cudaMallocHost((void**)&s.out_n_host, 16));
+    for (int i = 0; i < SMALL_SLOTS; ++i) MGB_CUDA(cudaEventCreateWithFlags(&s.ev[i], cudaEventDisableTiming));
+    const size_t smem = small_smem_bytes();
+    MGB_CUDA(cudaFuncSetAttribute(k_merge_small<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MGB_CUDA(cudaFuncSetAttribute(k_merge_small<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
-  const size_t tmp_words = (size_t)(nk + na) * MGB_SMALL_MAX_ROWS;
-  if (sort_keys && s.tmp_words < tmp_words) {
-    if (s.tmp) cudaFree(s.tmp);
-    MGB_CUDA(cudaMalloc((void**)&s.tmp, tmp_words * 8));
-    s.tmp_words = tmp_words;
+  *out = &s;
+  return MGB_OK;
+}
+
+extern "C" int mgb_merge_small_async(const mgb_agg_spec* spec, int32_t n_pieces, const int64_t* piece_rows,
+                                     const int64_t* const* piece_rows_dev,
+                                     const int64_t* const* const* piece_key_cols,
+                                     const void* const* const* piece_acc_cols, int64_t* const* out_key_cols,
+                                     void* const* out_acc_cols, int64_t out_capacity, int32_t sort_keys,
+                                     int64_t* out_n_dev, void* stream) {
+  MGB_REQUIRE(spec && piece_rows && piece_key_cols && piece_acc_cols && out_key_cols && out_acc_cols && out_n_dev,
+              MGB_ERR_INVALID, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nk = spec->n_keys, na = spec->n_accs;
+  MGB_REQUIRE(nk >= 1 && nk <= MGB_MAX_KEYS && na >= 1 && na <= MGB_MAX_ACCS, MGB_ERR_UNSUPPORTED,
+              "spec outside the supported envelope");
+  MGB_REQUIRE(out_capacity >= 0, MGB_ERR_INVALID, "negative capacity");
+  // pieces that are known to be empty are dropped; deferred ones (piece_rows < 0) must carry a device count
+  long long known = 0;
+  int used = 0;
+  for (int i = 0; i < n_pieces; ++i) {
+    if (piece_rows[i] < 0) {
+      MGB_REQUIRE(piece_rows_dev && piece_rows_dev[i], MGB_ERR_INVALID, "piece %d: deferred size without a device count", i);
+      ++used;
+    } else if (piece_rows[i] > 0) {
+      known += piece_rows[i];
+      ++used;
+    }
   }
+  if (known > MGB_SMALL_MAX_ROWS || known > out_capacity || used > SM_MAX_PIECES) {   // not small: tell the caller
+    MGB_CUDA(cudaMemsetAsync(out_n_dev, 0xFF, sizeof(int64_t), st));
+    return MGB_OK;
+  }
+  if (used == 0) {
+    MGB_CUDA(cudaMemsetAsync(out_n_dev, 0, sizeof(int64_t), st));
+    return MGB_OK;
+  }
+  int dev = 0;
+  MGB_CUDA(cudaGetDevice(&dev));
+  SmallScratch* sp = nullptr;
+  MGB_TRY(small_scratch(dev, &sp));
+  SmallScratch& s = *sp;
+  const size_t table_words = (size_t)SM_MAX_PIECES * MGB_MAX_ACCS;
   SmallParams p;
   memset(&p, 0, sizeof(p));
   const int slot = s.slot;
-  s.slot = (s.slot + 1) % SMALL_SLOTS;   // every call synchronises below, so a slot is free when reused
+  s.slot = (s.slot + 1) % SMALL_SLOTS;
+  if (s.used[slot]) MGB_CUDA(cudaEventSynchronize(s.ev[slot]));   // the launch that read this slot is done
   const uint64_t** host_tab = s.ptrs_host + (size_t)slot * table_words;
   int q = 0;
   for (int i = 0; i < n_pieces; ++i) {
@@ -369,7 +488,8 @@ extern "C" int mgb_merge_small(const mgb_agg_spec* spec, int32_t n_pieces, const
       MGB_REQUIRE(piece_key_cols[i] && piece_key_cols[i][j], MGB_ERR_INVALID, "null key column");
       p.piece[q].key[j] = (const uint64_t*)piece_key_cols[i][j];
     }
-    p.piece[q].n = (int)piece_rows[i];
+    p.piece[q].n = piece_rows[i] > 0 ? (int)piece_rows[i] : 0;
+    p.piece[q].n_dev = piece_rows[i] < 0 ? (const long long*)piece_rows_dev[i] : nullptr;
     for (int a = 0; a < na; ++a) {
       MGB_REQUIRE(piece_acc_cols[i] && piece_acc_cols[i][a], MGB_ERR_INVALID, "null accumulator column");
       host_tab[q * na + a] = (const uint64_t*)piece_acc_cols[i][a];
@@ -377,7 +497,7 @@ extern "C" int mgb_merge_small(const mgb_agg_spec* spec, int32_t n_pieces, const
     ++q;
   }
   p.n_pieces = q;
-  p.total = (int)total;
+  p.out_cap = (int)(out_capacity > MGB_SMALL_MAX_ROWS ? MGB_SMALL_MAX_ROWS : out_capacity);
   const uint64_t** dev_tab = s.ptrs_dev + (size_t)slot * table_words;
   MGB_CUDA(cudaMemcpyAsync(dev_tab, host_tab, (size_t)q * na * 8, cudaMemcpyHostToDevice, st));
   p.acc_ptrs = (const uint64_t* const*)dev_tab;
@@ -396,23 +516,45 @@ extern "C" int mgb_merge_small(const mgb_agg_spec* spec, int32_t n_pieces, const
     p.out.op[a] = (uint8_t)(op == MGB_MIN ? MGB_MIN : op == MGB_MAX ? MGB_MAX : MGB_SUM);
     p.out.dt[a] = (uint8_t)spec->val_dtype[c];
   }
-  p.tmp = s.tmp;
   p.sort = sort_keys ? 1 : 0;
-  p.out_n = s.out_n;
+  p.out_n = (long long*)out_n_dev;
   {
     MgbProfScope prof(MGB_K_MERGE, st);
-    const size_t smem = (size_t)MGB_MAX_KEYS * SM_TAB * 8 + SM_TAB * 4 + 64;
-    if (nk == 1) {
-      MGB_CUDA(cudaFuncSetAttribute(k_merge_small<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem = small_smem_bytes();
+    if (nk == 1)
       k_merge_small<1><<<1, SM_THREADS, smem, st>>>(p);
-    } else {
-      MGB_CUDA(cudaFuncSetAttribute(k_merge_small<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else
       k_merge_small<2><<<1, SM_THREADS, smem, st>>>(p);
-    }
     MGB_CHECK_LAUNCH();
   }
-  MGB_CUDA(cudaMemcpyAsync(s.out_n_host, s.out_n, sizeof(long long), cudaMemcpyDeviceToHost, st));
+  MGB_CUDA(cudaEventRecord(s.ev[slot], st));
+  s.used[slot] = true;
+  return MGB_OK;
+}
+
+extern "C" int mgb_merge_small(const mgb_agg_spec* spec, int32_t n_pieces, const int64_t* piece_rows,
+                               const int64_t* const* const* piece_key_cols,
+                               const void* const* const* piece_acc_cols, int64_t* const* out_key_cols,
+                               void* const* out_acc_cols, int64_t out_capacity, int32_t sort_keys,
+                               int64_t* out_n_groups, void* stream) {
+  MGB_REQUIRE(out_n_groups && piece_rows, MGB_ERR_INVALID, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  *out_n_groups = -1;
+  long long total = 0;
+  for (int i = 0; i < n_pieces; ++i) {
+    MGB_REQUIRE(piece_rows[i] >= 0, MGB_ERR_INVALID, "negative piece size");
+    total += piece_rows[i];
+  }
+  MGB_REQUIRE(out_capacity >= total || total > MGB_SMALL_MAX_ROWS, MGB_ERR_INVALID,
+              "output capacity %lld < %lld rows", (long long)out_capacity, total);
+  int dev = 0;
+  MGB_CUDA(cudaGetDevice(&dev));
+  SmallScratch* sp = nullptr;
+  MGB_TRY(small_scratch(dev, &sp));
+  MGB_TRY(mgb_merge_small_async(spec, n_pieces, piece_rows, nullptr, piece_key_cols, piece_acc_cols, out_key_cols,
+                                out_acc_cols, out_capacity, sort_keys, (int64_t*)sp->out_n, stream));
+  MGB_CUDA(cudaMemcpyAsync(sp->out_n_host, sp->out_n, sizeof(long long), cudaMemcpyDeviceToHost, st));
   MGB_CUDA(cudaStreamSynchronize(st));
-  *out_n_groups = s.out_n_host[0];
+  *out_n_groups = sp->out_n_host[0];
   return MGB_OK;
 }

@@ -33,9 +33,9 @@ __device__ __forceinline__ uint32_t small_hash(const uint64_t* k) {
 // Keys are published before the index (threadfence_block) so readers that see idx >= 0 see the keys.
 template <int NK>
 __device__ __forceinline__ int small_find_or_insert(uint64_t* tab_keys, int* tab_idx, int* n_unique,
-                                                    const uint64_t* k) {
-  uint32_t s = small_hash<NK>(k) & (SM_TAB - 1);
-  for (int probe = 0; probe < SM_TAB; ++probe, s = (s + 1) & (SM_TAB - 1)) {
+                                                    const uint64_t* k, uint32_t mask = SM_TAB - 1) {
+  uint32_t s = small_hash<NK>(k) & mask;
+  for (uint32_t probe = 0; probe <= mask; ++probe, s = (s + 1) & mask) {
     int cur = *(volatile int*)&tab_idx[s];
     if (cur == -1) {
       cur = atomicCAS(&tab_idx[s], -1, -2);

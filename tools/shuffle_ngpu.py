@@ -1,0 +1,70 @@
+#!/usr/bin/env python
+"""Hash-shuffle branch across N GPUs (one process per GPU, torchrun): parity against pandas + exchange bandwidth.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        tools/shuffle_ngpu.py [--rows 4000000] [--keys 1000000] [--chunks-per-gpu 4] [--check]
+
+Every rank generates the same seeded frame (so the pandas check can run on rank 0), owns the map chunks
+c % N == rank, and the shuffle moves partial blocks with the grouped ncclSend/ncclRecv all-to-all of
+libmarsgb (mgb_comm_alltoallv).  Prints one JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import pandas as pd
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import mars_b200 as md  # noqa: E402
+from mars_b200 import parallel  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--rows", type=int, default=4_000_000)
+    ap.add_argument("--keys", type=int, default=1_000_000)
+    ap.add_argument("--chunks-per-gpu", type=int, default=4)
+    ap.add_argument("--check", action="store_true")
+    args = ap.parse_args()
+    ex = parallel.init_exchange("gloo")          # gloo: host metadata; bytes move through libmarsgb + NCCL
+    rank, world = ex.rank, ex.world
+    rng = np.random.default_rng(11)
+    raw = pd.DataFrame({"key": rng.integers(0, args.keys, args.rows), "v": rng.random(args.rows)})
+    n_chunks = args.chunks_per_gpu * world
+    chunk = -(-args.rows // n_chunks)
+    times = []
+    for it in range(3):
+        sess = md.new_session(exchange=ex, default=False)
+        r = md.DataFrame(raw, chunk_size=chunk).to_gpu().groupby("key", sort=False).agg(["sum", "count"], method="shuffle")
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        r.execute(session=sess)
+        torch.cuda.synchronize()
+        dist.barrier()
+        times.append(time.perf_counter() - t0)
+    got = sess.fetch(r)
+    ok = None
+    if args.check and rank == 0:
+        exp = raw.groupby("key").agg(["sum", "count"])
+        g = got.sort_index()
+        ok = bool(g.index.equals(exp.index) and np.array_equal(g[("v", "count")], exp[("v", "count")])
+                  and np.allclose(g[("v", "sum")], exp[("v", "sum")], rtol=1e-9, atol=0))
+    sent = torch.tensor([float(ex.transport.bytes_sent)], dtype=torch.float64)
+    dist.all_reduce(sent)
+    if rank == 0:
+        print(json.dumps({"n_gpus": world, "rows": args.rows, "groups": int(len(got)), "chunks": n_chunks,
+                          "parity_vs_pandas": ok, "seconds_per_run": times, "rows_per_s": args.rows / min(times),
+                          "bytes_sent_all_ranks_3_runs": sent.item(),
+                          "ops": sorted(set(sess.executed_ops))}), flush=True)
+    ex.transport.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
