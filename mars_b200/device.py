@@ -9,6 +9,7 @@ the processor frees ctx entries (processor.py:276-282).
 """
 from __future__ import annotations
 
+import weakref
 from typing import Any, List, Optional, Sequence
 
 import numpy as np
@@ -30,31 +31,141 @@ def _to_device(arr: np.ndarray, device) -> torch.Tensor:
     return torch.from_numpy(arr).to(device, non_blocking=True)
 
 
+class Pending:
+    """Row count of a partial tuple that only the device knows so far.
+
+    The low-cardinality kernels can be enqueued without the host waiting for their result size: the output
+    columns are allocated at capacity, the group count lands in a device int64, and the frames built on the
+    columns carry this object instead of a length.  The first consumer that needs host-side sizes calls
+    ``resolve()``: one 8-byte read.  A count of -1 means the speculation failed (the chunk was not a dense
+    shape / a merge input was too large): ``replay`` then recomputes the columns on the general path from the
+    inputs it kept alive, and every frame of the tuple is re-pointed at the new columns."""
+
+    __slots__ = ("block", "row", "cap", "_frames", "replay", "value")
+
+    def __init__(self, block: torch.Tensor, row: int, cap: int, replay):
+        self.block, self.row, self.cap = block, row, cap
+        # weak: frames own their Pending (and through its replay closure the inputs), never the other way
+        # round -- no reference cycle, so dropping the frames frees the inputs immediately
+        self._frames: List[Any] = []
+        self.replay = replay
+        self.value: Optional[int] = None
+
+    @property
+    def frames(self):
+        return [f for f in (r() for r in self._frames) if f is not None]
+
+    def attach(self, frame):
+        self._frames.append(weakref.ref(frame))
+
+    def count_ptr(self) -> int:
+        return self.block.data_ptr() + self.row * self.block.shape[1] * 8
+
+    def settle(self, n: int):
+        """the count became known (>= 0) by other means (e.g. it travelled with the result block)"""
+        if self.value is None:
+            self.value = n
+            for f in self.frames:
+                f._finalize(n)
+            self.replay = None
+
+    def resolve(self) -> int:
+        if self.value is None:
+            n = int(self.block[self.row, 0].item())          # 8-byte D2H + sync
+            if n >= 0:
+                self.settle(n)
+            else:
+                keys, accs = self.replay()                    # general path, eager
+                n = int(keys[0].numel())
+                self.value = n
+                for f in self.frames:
+                    f._repoint(keys, accs, n)
+                self.replay = None
+        return self.value
+
+
 class DeviceFrame:
-    __slots__ = ("index_names", "index", "columns", "data", "_n")
+    __slots__ = ("index_names", "_index", "columns", "_data", "_n", "_pending", "_slot", "__weakref__")
 
     def __init__(self, index_names: Sequence[Any], index: Optional[Sequence[torch.Tensor]],
-                 columns: Sequence[Any], data: Sequence[torch.Tensor], n_rows: Optional[int] = None):
+                 columns: Sequence[Any], data: Sequence[torch.Tensor], n_rows: Optional[int] = None,
+                 pending: Optional[Pending] = None, slot=None):
         self.index_names = list(index_names)
-        self.index = None if index is None else list(index)   # None == RangeIndex (raw input chunk)
+        self._index = None if index is None else list(index)   # None == RangeIndex (raw input chunk)
         self.columns = list(columns)
-        self.data = list(data)
+        self._data = list(data)
+        self._pending = pending
+        self._slot = slot
+        if pending is not None:
+            pending.attach(self)
+            self._n = None
+            return
         if n_rows is None:
-            if self.data:
-                n_rows = int(self.data[0].numel())
-            elif self.index:
-                n_rows = int(self.index[0].numel())
+            if self._data:
+                n_rows = int(self._data[0].numel())
+            elif self._index:
+                n_rows = int(self._index[0].numel())
             else:
                 n_rows = 0
         self._n = n_rows
 
+    # ---- deferred size -------------------------------------------------------------------------------
+    @property
+    def is_pending(self) -> bool:
+        return self._pending is not None and self._pending.value is None
+
+    def _resolve(self):
+        if self._pending is not None and self._pending.value is None:
+            self._pending.resolve()
+
+    def _finalize(self, n: int):
+        """the speculative columns are valid: cut the capacity-length views down to n rows"""
+        if self._index is not None:
+            self._index = [t[:n] for t in self._index]
+        self._data = [t[:n] for t in self._data]
+        self._n = n
+
+    def _repoint(self, keys, accs, n: int):
+        a0, a1 = self._slot
+        self._index = list(keys)
+        self._data = list(accs[a0:a1])
+        self._n = n
+
+    @property
+    def index(self):
+        self._resolve()
+        return self._index
+
+    @index.setter
+    def index(self, value):
+        self._index = value
+
+    @property
+    def data(self):
+        self._resolve()
+        return self._data
+
+    @data.setter
+    def data(self, value):
+        self._data = value
+
+    @property
+    def raw_index(self):
+        """index columns as they are (capacity-length while the size is pending)"""
+        return self._index
+
+    @property
+    def raw_data(self):
+        return self._data
+
     # ---- pandas-like surface used by metas / size accounting (subtask/utils.py:62-68)
     def __len__(self):
+        self._resolve()
         return self._n
 
     @property
     def shape(self):
-        return (self._n, len(self.columns))
+        return (len(self), len(self.columns))
 
     @property
     def ndim(self):
@@ -62,13 +173,13 @@ class DeviceFrame:
 
     @property
     def dtypes(self):
-        return pd.Series([np.dtype(str(t.dtype).replace("torch.", "")) for t in self.data], index=self.columns)
+        return pd.Series([np.dtype(str(t.dtype).replace("torch.", "")) for t in self._data], index=self.columns)
 
     @property
     def nbytes(self) -> int:
-        total = sum(t.numel() * t.element_size() for t in self.data)
-        if self.index:
-            total += sum(t.numel() * t.element_size() for t in self.index)
+        total = sum(t.numel() * t.element_size() for t in self._data)
+        if self._index:
+            total += sum(t.numel() * t.element_size() for t in self._index)
         return total
 
     def __sizeof__(self):
@@ -76,7 +187,7 @@ class DeviceFrame:
 
     @property
     def device(self):
-        ts = self.data or self.index or []
+        ts = self._data or self._index or []
         return ts[0].device if ts else torch.device("cpu")
 
     def column(self, name) -> torch.Tensor:
@@ -89,11 +200,14 @@ class DeviceFrame:
     def same_index(self, other: "DeviceFrame") -> bool:
         """True when both frames share their index tensors (reference: item.index.equals(index),
         groupby/core.py:381-391 -- here a pointer comparison, no data pass)."""
-        if self.index is None or other.index is None:
-            return self.index is other.index and len(self) == len(other)
-        if len(self.index) != len(other.index) or len(self) != len(other):
+        a, b = self._index, other._index
+        if a is None or b is None:
+            return a is b and len(self) == len(other)
+        if len(a) != len(b):
             return False
-        return all(a.data_ptr() == b.data_ptr() and a.numel() == b.numel() for a, b in zip(self.index, other.index))
+        if self._pending is not other._pending and (self.is_pending or other.is_pending):
+            return False
+        return all(x.data_ptr() == y.data_ptr() and x.numel() == y.numel() for x, y in zip(a, b))
 
     # ---- host <-> device (reference: DataFrameToGPU / DataFrameToCPU, dataframe/base/to_gpu.py:28-35)
     @classmethod
@@ -143,7 +257,8 @@ class DeviceFrame:
         return df
 
     def __repr__(self):
-        return (f"DeviceFrame(rows={self._n}, index={self.index_names if self.index is not None else 'range'}, "
+        rows = "pending" if self.is_pending else self._n
+        return (f"DeviceFrame(rows={rows}, index={self.index_names if self._index is not None else 'range'}, "
                 f"columns={self.columns}, device={self.device})")
 
 

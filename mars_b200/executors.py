@@ -18,6 +18,7 @@ All arithmetic happens in libmarsgb.so (mars_b200.kernels); there is no CPU fall
 """
 from __future__ import annotations
 
+import os
 from typing import Any, Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -26,7 +27,7 @@ import torch
 
 from . import kernels as K
 from ._lib import MarsGBError
-from .device import DeviceFrame, PiecewiseFrame
+from .device import DeviceFrame, Pending, PiecewiseFrame
 from .reduction import _DECOMP
 
 _OPCODE = {"sum": K.SUM, "count": K.COUNT, "min": K.MIN, "max": K.MAX}
@@ -36,6 +37,8 @@ _DECOMP_EXT = dict(_DECOMP, std=_DECOMP["var"])
 # recording double; the product never rebinds it.
 _kernels = K
 _dense_rejected = set()
+# MGB_EAGER=1 disables the speculative asynchronous chain (every operand then waits for its result size)
+_ASYNC = os.environ.get("MGB_EAGER", "0") in ("", "0")
 
 
 def _stage(op) -> Optional[str]:
@@ -235,22 +238,43 @@ def _execute_agg_map(ctx, op):
         if k.dtype != torch.int64:
             raise NotImplementedError(f"group key {b!r} has dtype {k.dtype}: int64 keys only")
     vals = [data[i] for i in plan.val_pos]
-    # low-cardinality chunks take the one-launch dense path; a shape that did not fit is remembered so
-    # the following chunks of the same computation go straight to the general hash-table path
-    res = None
-    if plan.shape_key not in _dense_rejected and hasattr(_kernels, "preagg_dense"):
-        res = _kernels.preagg_dense(keys, vals, plan.accs)
-        if res is None:
-            _dense_rejected.add(plan.shape_key)
-    if res is None:
-        out_keys, out_accs, _ = _kernels.groupby_aggregate(keys, vals, list(plan.accs), sort=False)
-    else:
-        out_keys, out_accs = res
-    n_out = int(out_keys[0].numel())
-    frames = [DeviceFrame(plan.by, out_keys, cols, out_accs[a0:a1], n_out) for cols, a0, a1 in plan.slots]
+    # low-cardinality chunks take the one-launch dense path, enqueued WITHOUT waiting for its result size
+    # (the frames carry a Pending count).  A shape that turned out not to fit is remembered, so the following
+    # chunks of the same computation go straight to the general hash-table path.
     rec = getattr(op, "size_recorder_name", None)
-    if rec is not None:
-        _record_sizes(ctx, rec, frame.nbytes, sum(f.nbytes for f in frames))
+    frames = None
+    if plan.shape_key not in _dense_rejected:
+        if _ASYNC and hasattr(_kernels, "preagg_dense_async"):
+            res = _kernels.preagg_dense_async(keys, vals, plan.accs)
+            if res is None:
+                _dense_rejected.add(plan.shape_key)
+            else:
+                bi, bf, fc = res
+                accs = list(plan.accs)
+
+                def replay(keys=keys, vals=vals, accs=accs, shape_key=plan.shape_key):
+                    _dense_rejected.add(shape_key)
+                    k, a, _ = _kernels.groupby_aggregate(keys, vals, accs, sort=False)
+                    return k, a
+
+                pend = Pending(bi, fc.n_int, bi.shape[1], replay)
+                ck, ca = fc.views(bi, bf)
+                frames = [DeviceFrame(plan.by, ck, cols, ca[a0:a1], pending=pend, slot=(a0, a1))
+                          for cols, a0, a1 in plan.slots]
+        elif hasattr(_kernels, "preagg_dense"):
+            res = _kernels.preagg_dense(keys, vals, plan.accs)
+            if res is None:
+                _dense_rejected.add(plan.shape_key)
+            else:
+                out_keys, out_accs = res
+                n_out = int(out_keys[0].numel())
+                frames = [DeviceFrame(plan.by, out_keys, cols, out_accs[a0:a1], n_out) for cols, a0, a1 in plan.slots]
+    if frames is None:
+        out_keys, out_accs, _ = _kernels.groupby_aggregate(keys, vals, list(plan.accs), sort=False)
+        n_out = int(out_keys[0].numel())
+        frames = [DeviceFrame(plan.by, out_keys, cols, out_accs[a0:a1], n_out) for cols, a0, a1 in plan.slots]
+    if rec is not None:   # method='auto' samples real sizes: this resolves the count (one 8-byte read)
+        _record_sizes(ctx, rec, frame.nbytes, sum(len(f) * 8 * (len(f.columns) + len(plan.by)) for f in frames))
     ctx[op.outputs[0].key] = tuple(frames)
 
 
@@ -289,29 +313,59 @@ def _merge_partials(slots: Sequence[Sequence[DeviceFrame]], steps: Sequence[_Ste
     out: List[Optional[DeviceFrame]] = [None] * len(slots)
     for grp in groups:
         base = slots[grp[0]]
-        pieces = [i for i in range(len(base)) if len(base[i]) > 0] or [0]
         ops = [_OPCODE[steps[i].agg_func] for i in grp for _ in slots[i][0].columns]
-        res = None
-        if hasattr(_kernels, "merge_small") and sum(len(base[i]) for i in pieces) <= 2048 and len(pieces) <= 16:
-            res = _kernels.merge_small([base[i].index for i in pieces],
-                                       [[t for s in grp for t in slots[s][i].data] for i in pieces], ops, sort=force_sort)
-        if res is None:
-            first_vals = [t for s in grp for t in slots[s][pieces[0]].data]
-            agg = _kernels.Aggregator(len(base[0].index), [_kernels.dtype_code(t) for t in first_vals],
-                                      list(enumerate(ops)))
-            try:
-                for i in pieces:
-                    agg.update(base[i].index, [t for s in grp for t in slots[s][i].data])
-                res = agg.result(sort=force_sort, device=base[0].device)
-            finally:
-                agg.close()
-        k, a = res
+        pend_out = None
+        if _ASYNC and hasattr(_kernels, "merge_small_async"):
+            # sizes that are still on the device stay there: the merge reads them in the kernel
+            pieces = []
+            for i in range(len(base)):
+                f0 = base[i]
+                cols = [t for s in grp for t in slots[s][i].raw_data]
+                if f0.is_pending:
+                    pieces.append((f0.raw_index, cols, None, f0._pending.count_ptr()))
+                elif len(f0) > 0:
+                    pieces.append((f0.raw_index, cols, len(f0), 0))
+            if not pieces:
+                pieces.append((base[0].raw_index, [t for s in grp for t in slots[s][0].raw_data], 0, 0))
+            res = _kernels.merge_small_async(pieces, ops, sort=force_sort)
+            if res is not None:
+                bi, bf, fc = res
+                pend_out = Pending(bi, fc.n_int, bi.shape[1],
+                                   lambda grp=grp, ops=ops: _merge_general(slots, grp, ops, force_sort))
+                k, a = fc.views(bi, bf)
+        if pend_out is None:
+            res = None
+            live = [i for i in range(len(base)) if len(base[i]) > 0] or [0]
+            if hasattr(_kernels, "merge_small") and sum(len(base[i]) for i in live) <= 2048 and len(live) <= 16:
+                res = _kernels.merge_small([base[i].index for i in live],
+                                           [[t for s in grp for t in slots[s][i].data] for i in live], ops,
+                                           sort=force_sort)
+            k, a = res if res is not None else _merge_general(slots, grp, ops, force_sort)
         pos = 0
         for i in grp:
             ncol = len(slots[i][0].columns)
-            out[i] = DeviceFrame(base[0].index_names, k, slots[i][0].columns, a[pos:pos + ncol], int(k[0].numel()))
+            if pend_out is not None:
+                out[i] = DeviceFrame(base[0].index_names, k, slots[i][0].columns, a[pos:pos + ncol], pending=pend_out,
+                                     slot=(pos, pos + ncol))
+            else:
+                out[i] = DeviceFrame(base[0].index_names, k, slots[i][0].columns, a[pos:pos + ncol], int(k[0].numel()))
             pos += ncol
     return out  # type: ignore[return-value]
+
+
+def _merge_general(slots, grp, ops, sort):
+    """general hash aggregation over the pieces of the slots in ``grp`` (one update per piece, no concat);
+    resolves pending sizes (and replays failed speculations) of the inputs"""
+    base = slots[grp[0]]
+    live = [i for i in range(len(base)) if len(base[i]) > 0] or [0]
+    first_vals = [t for s in grp for t in slots[s][live[0]].data]
+    agg = _kernels.Aggregator(len(base[0].index), [_kernels.dtype_code(t) for t in first_vals], list(enumerate(ops)))
+    try:
+        for i in live:
+            agg.update(base[i].index, [t for s in grp for t in slots[s][i].data])
+        return agg.result(sort=sort, device=base[0].device)
+    finally:
+        agg.close()
 
 
 def _pieces_of(value) -> List[List[DeviceFrame]]:
@@ -350,35 +404,56 @@ def _execute_agg_agg(ctx, op):
     steps = _plan_steps(op, None)
     sort = bool(op.groupby_params.get("sort", True))
     merged = _merge_partials(slots, steps, sort=sort)
-    by_key = {s.output_key: f for s, f in zip(steps, merged)}
     col_value = out_chunk.columns_value.to_pandas()
     two_level = col_value.nlevels > 1
-    pieces: Dict[Any, np.ndarray] = {}
-    host_eval = []
-    for p in op.post_funcs:
-        inputs = [by_key[k] for k in p.input_keys]
-        cols = list(p.columns) if p.columns is not None else None
-        common = [c for c in inputs[0].columns if all(c in f.columns for f in inputs[1:])
-                  and (cols is None or c in cols)]
-        cls = classify_post(p.func, len(inputs))
-        for c in common:
-            label = (c, p.func_name) if two_level else c
-            if cls is None:
-                host_eval.append((label, p, c, inputs))
-                continue
-            kind, ddof = cls
-            ts = [f.column(c) for f in inputs]
-            if kind == "identity":
-                res = ts[0]
-            elif kind == "mean":
-                res = _kernels.post_mean(ts[0], ts[1])
-            else:
-                res = _kernels.post_var(ts[1], ts[0], ts[2], ddof)   # inputs: sum(x**2), sum(x), count
-            pieces[label] = res
-    # all result columns and the group keys cross to the host with ONE synchronisation
+    by_key = {s.output_key: f for s, f in zip(steps, merged)}
+
+    def post_columns(raw: bool):
+        """device columns of the result (post functions applied); raw: work on capacity-length columns of a
+        still-pending merge -- rows beyond the (device-side) count hold garbage that is cut off on the host"""
+        pieces: Dict[Any, Any] = {}
+        host_eval = []
+        for p in op.post_funcs:
+            inputs = [by_key[k] for k in p.input_keys]
+            cols = list(p.columns) if p.columns is not None else None
+            common = [c for c in inputs[0].columns if all(c in f.columns for f in inputs[1:])
+                      and (cols is None or c in cols)]
+            cls = classify_post(p.func, len(inputs))
+            for c in common:
+                label = (c, p.func_name) if two_level else c
+                if cls is None:
+                    host_eval.append((label, p, c, inputs))
+                    continue
+                kind, ddof = cls
+                ts = [(f.raw_data if raw else f.data)[f.columns.index(c)] for f in inputs]
+                if kind == "identity":
+                    res = ts[0]
+                elif kind == "mean":
+                    res = _kernels.post_mean(ts[0], ts[1])
+                else:
+                    res = _kernels.post_var(ts[1], ts[0], ts[2], ddof)   # inputs: sum(x**2), sum(x), count
+                pieces[label] = res
+        return pieces, host_eval
+
+    # all result columns, the group keys and -- when the merge is still pending -- its row count cross to the
+    # host with ONE synchronisation
     base = merged[0]
-    labels_dev = list(pieces.keys())
-    arrays = _to_host([pieces[l] for l in labels_dev] + list(base.index))
+    arrays = None
+    pend = base._pending if base.is_pending else None
+    if pend is not None and all(f._pending is pend for f in merged) and hasattr(_kernels, "to_host_counted"):
+        pieces, host_eval = post_columns(raw=True)
+        if not host_eval:
+            labels_dev = list(pieces.keys())
+            n, arrays = _kernels.to_host_counted([pieces[l] for l in labels_dev] + list(base.raw_index), pend.block,
+                                                 pend.row)
+            if n >= 0:
+                pend.settle(n)
+            else:
+                arrays = None   # speculation failed somewhere up the chain: resolve (replays) and redo eagerly
+    if arrays is None:
+        pieces, host_eval = post_columns(raw=False)
+        labels_dev = list(pieces.keys())
+        arrays = _to_host([pieces[l] for l in labels_dev] + list(base.index))
     host = dict(zip(labels_dev, arrays[:len(labels_dev)]))
     idx_arrays = arrays[len(labels_dev):]
     for label, p, c, inputs in host_eval:

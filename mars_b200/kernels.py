@@ -240,9 +240,10 @@ class _FastCall:
         self.g = C.c_int64()
 
     def alloc(self, cap, device):
-        """int64 block [n_keys + int accs, cap] and float64 block [float accs, cap]; output pointers set."""
+        """int64 block [n_keys + int accs + 1, cap] and float64 block [float accs, cap]; output pointers set.
+        The last int64 row is scratch for the device-side group count of the asynchronous entry points."""
         cap = max(int(cap), 1)
-        bi = torch.empty((self.n_int, cap), dtype=torch.int64, device=device)
+        bi = torch.empty((self.n_int + 1, cap), dtype=torch.int64, device=device)
         bf = torch.empty((max(self.n_float, 1), cap), dtype=torch.float64, device=device)
         pi, pf, stride = bi.data_ptr(), bf.data_ptr(), cap * 8
         for j in range(self.nk):
@@ -251,10 +252,14 @@ class _FastCall:
             self.oap[a] = pf + self.float_row[a] * stride if self.is_float[a] else pi + self.int_row[a] * stride
         return bi, bf
 
-    def views(self, bi, bf, G):
-        """(key tensors, accumulator tensors) of the first G rows -- two slices + two unbinds in total."""
-        ri = bi[:, :G].unbind(0)
-        rf = bf[:, :G].unbind(0)
+    def count_ptr(self, bi) -> int:
+        return bi.data_ptr() + self.n_int * bi.shape[1] * 8
+
+    def views(self, bi, bf, G=None):
+        """(key tensors, accumulator tensors) of the first G rows (all rows when G is None) -- two slices +
+        two unbinds in total."""
+        ri = (bi if G is None else bi[:, :G]).unbind(0)
+        rf = (bf if G is None else bf[:, :G]).unbind(0)
         keys = list(ri[:self.nk])
         accs = [rf[self.float_row[a]] if self.is_float[a] else ri[self.int_row[a]] for a in range(self.na)]
         return keys, accs
@@ -353,6 +358,107 @@ def merge_small(pieces_keys: Sequence[Sequence[torch.Tensor]], pieces_accs: Sequ
         return None
     _count(1 if total else 0)
     return fc.views(bi, bf, G)
+
+
+def preagg_dense_async(keys: Sequence[torch.Tensor], vals: Sequence[torch.Tensor], accs: Sequence[Tuple[int, int]]):
+    """Like ``preagg_dense`` but without host synchronisation (mgb_preagg_dense_async): returns
+    (int block, float block, fast-call) -- columns at capacity ``dense_capacity()``, the group count (or -1) in
+    the device int64 at ``fc.count_ptr(bi)``.  None when the shape can never be dense (too many columns)."""
+    global _dense_cap
+    lib = _lib.load()
+    if len(vals) > _lib.MGB_MAX_VALS or len(accs) > _lib.MGB_MAX_ACCS:
+        return None
+    for i, k in enumerate(keys):
+        _check_col(k, "key column")
+        if k.dtype != torch.int64:
+            raise MarsGBError(3, f"key {i}: dtype {k.dtype} not supported (int64 keys)")
+    for v in vals:
+        _check_col(v, "value column")
+    n = keys[0].numel()
+    fc = _fast(len(keys), [F64 if v.dtype == torch.float64 else I64 for v in vals], accs)
+    if _dense_cap is None:
+        c = C.c_int64()
+        check(lib.mgb_dense_capacity(C.byref(c)))
+        _dense_cap = c.value
+    for j, k in enumerate(keys):
+        fc.kp[j] = k.data_ptr()
+    for j, v in enumerate(vals):
+        fc.vp[j] = v.data_ptr()
+    bi, bf = fc.alloc(_dense_cap, keys[0].device)
+    check(lib.mgb_preagg_dense_async(C.byref(fc.spec), fc.kp, fc.vp, n, fc.okp, fc.oap, _dense_cap, fc.count_ptr(bi),
+                                     _stream()))
+    _count(1 if n else 0)
+    return bi, bf, fc
+
+
+SMALL_MAX_ROWS = 2048
+SMALL_MAX_PIECES = 16
+
+
+def merge_small_async(pieces, acc_ops: Sequence[int], sort: bool = False):
+    """Re-aggregation of small partial blocks without host synchronisation (mgb_merge_small_async).
+    ``pieces``: list of (key tensors, accumulator tensors, n_rows or None, device count pointer or 0); a piece
+    with n_rows None has its size in the device int64 at the given pointer.  Returns (int block, float block,
+    fast-call) at capacity SMALL_MAX_ROWS with the group count (or -1) at ``fc.count_ptr(bi)``; None when the
+    host can already tell that the input is not small."""
+    lib = _lib.load()
+    n_pieces = len(pieces)
+    na = len(acc_ops)
+    known = sum(p[2] for p in pieces if p[2] is not None)
+    live = sum(1 for p in pieces if p[2] is None or p[2] > 0)
+    if known > SMALL_MAX_ROWS or live > SMALL_MAX_PIECES or na > _lib.MGB_MAX_ACCS or na > _lib.MGB_MAX_VALS:
+        return None
+    nk = len(pieces[0][0])
+    dts = [F64 if t.dtype == torch.float64 else I64 for t in pieces[0][1]]
+    fc = _fast(nk, dts, tuple((a, op) for a, op in enumerate(acc_ops)))
+    kt = (_lib._pp * max(n_pieces, 1))()
+    at = (_lib._pp * max(n_pieces, 1))()
+    rows_arr = (C.c_int64 * max(n_pieces, 1))()
+    rows_dev = (C.c_void_p * max(n_pieces, 1))()
+    keep = []
+    for i, (pk, pa, n, cptr) in enumerate(pieces):
+        karr = (C.c_void_p * nk)()
+        aarr = (C.c_void_p * max(na, 1))()
+        for j, t in enumerate(pk):
+            _check_col(t, "piece key")
+            karr[j] = t.data_ptr()
+        for a, t in enumerate(pa):
+            _check_col(t, "piece accumulator")
+            if (t.dtype == torch.float64) != (dts[a] == F64):
+                raise MarsGBError(1, "partial blocks differ in accumulator dtype")
+            aarr[a] = t.data_ptr()
+        keep.append((karr, aarr))
+        kt[i] = C.cast(karr, _lib._pp)
+        at[i] = C.cast(aarr, _lib._pp)
+        rows_arr[i] = -1 if n is None else int(n)
+        rows_dev[i] = cptr if n is None else None
+    bi, bf = fc.alloc(SMALL_MAX_ROWS, pieces[0][0][0].device)
+    check(lib.mgb_merge_small_async(C.byref(fc.spec), n_pieces, rows_arr, rows_dev, kt, at, fc.okp, fc.oap,
+                                    SMALL_MAX_ROWS, 1 if sort else 0, fc.count_ptr(bi), _stream()))
+    _count(1)
+    return bi, bf, fc
+
+
+def to_host_counted(columns: Sequence[torch.Tensor], count_block: torch.Tensor, count_row: int):
+    """Device -> host read of capacity-length columns TOGETHER with their device-side row count: all copies
+    and the count go into one pinned block, one synchronisation.  Returns (n, numpy arrays cut to n rows) --
+    n < 0 means the speculative result is invalid (arrays are then None)."""
+    import numpy as np
+
+    cap = int(columns[0].numel()) if columns else 1
+    host = torch.empty((len(columns) + 1, max(cap, 1)), dtype=torch.int64, pin_memory=True)
+    for j, c in enumerate(columns):
+        host[j, :cap].view(c.dtype).copy_(c, non_blocking=True)
+    host[len(columns), :1].copy_(count_block[count_row, :1], non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    n = int(host[len(columns), 0])
+    if n < 0:
+        return n, None
+    out = []
+    for j, c in enumerate(columns):
+        arr = host[j, :n].numpy()
+        out.append(arr.view(np.float64).copy() if c.dtype == torch.float64 else arr.copy())
+    return n, out
 
 
 def to_host(columns: Sequence[torch.Tensor]):

@@ -200,3 +200,35 @@ def test_full_size_properties(md, n, card, nkeys):
     h = orc.hash_keys([t.cpu().numpy() for t in outs])
     for r in range(R):
         assert bool((h[offsets[r]:offsets[r + 1]] % np.uint64(R) == r).all())
+
+
+def test_speculative_dense_path_replays_when_a_chunk_is_not_dense(md):
+    """The map / combine / agg chain is enqueued without waiting for intermediate sizes.  Here the first
+    chunks are dense (3 groups) and the later ones are not (thousands of groups): their device-side count
+    comes back -1, the -1 propagates through the pending merges, and the agg stage replays the affected
+    operands on the general path from the inputs it kept alive."""
+    from mars_b200 import executors
+
+    rng = np.random.default_rng(21)
+    n = 80_000
+    key = np.concatenate([rng.integers(0, 3, n // 2), rng.integers(0, 5000, n // 2)])
+    raw = pd.DataFrame({"spec_key": key, "spec_v0": rng.normal(10, 3, n), "spec_v1": rng.random(n)})
+    func = ["sum", "mean", "count", "min", "max", "var"]
+    before = set(executors._dense_rejected)
+    got, sess, r = run(md, raw, "spec_key", func, 10_000, "tree", True)
+    exp = orc.run_groupby_agg(raw, "spec_key", func, 10_000, method="tree", sort=True)
+    assert_frames_match(got, exp, sort_index=False)
+    assert any(k[0] == ("spec_key",) for k in set(executors._dense_rejected) - before), "no replay happened"
+    # and again, now that the shape is known not to be dense (general path from the start)
+    got2, _, _ = run(md, raw, "spec_key", func, 10_000, "tree", True)
+    assert_frames_match(got2, exp, sort_index=False)
+
+
+def test_pending_partials_feed_the_shuffle_branch(md):
+    # dense map output (size still on the device) -> shuffle map must resolve it before partitioning
+    rng = np.random.default_rng(22)
+    n = 40_000
+    raw = pd.DataFrame({"pk": rng.integers(0, 7, n), "pv": rng.random(n)})
+    got, sess, r = run(md, raw, "pk", ["sum", "count"], 5_000, "shuffle", False)
+    exp = raw.groupby("pk").agg(["sum", "count"])
+    assert_frames_match(got, exp, sort_index=True)
