@@ -36,18 +36,28 @@ class ExecutionError(Exception):
 
 
 _key_counter = itertools.count()
+_key_salt = uuid.uuid4().hex[:8]   # per process: keys of different processes never collide
 
 
 def new_key(prefix: str = "") -> str:
-    return f"{prefix}{next(_key_counter):08x}{uuid.uuid4().hex[:8]}"
+    return f"{prefix}{next(_key_counter):08x}{_key_salt}"
 
 
 class IndexValue:
-    """Minimal stand-in for mars IndexValue: keeps the pandas Index (metadata only)."""
+    """Minimal stand-in for mars IndexValue: keeps the pandas Index (metadata only).  ``index`` may be a
+    zero-argument callable that builds the Index on first use (chunk metas are rarely looked at)."""
 
     def __init__(self, index, name=None):
-        self._index = index
-        self.name = name if name is not None else getattr(index, "name", None)
+        self._lazy = index if callable(index) else None
+        self._index_obj = None if callable(index) else index
+        self.name = name if name is not None else (None if callable(index) else getattr(index, "name", None))
+
+    @property
+    def _index(self):
+        if self._index_obj is None and self._lazy is not None:
+            self._index_obj = self._lazy()
+            self._lazy = None
+        return self._index_obj
 
     def to_pandas(self):
         return self._index

@@ -347,15 +347,17 @@ class DataFrame:
         columns = pd.Index(list(first.columns))
         n = sum(len(c) for c in chunks)
         op = DataFrameDataSource(gpu=gpu)
-        t = op.new_tileable([], shape=(n, len(columns)), dtypes=dtypes, index_value=IndexValue(pd.RangeIndex(n)),
-                            columns_value=IndexValue(columns))
+        cv = IndexValue(columns)
+        t = op.new_tileable([], shape=(n, len(columns)), dtypes=dtypes,
+                            index_value=IndexValue(lambda n=n: pd.RangeIndex(n)), columns_value=cv)
         out, start = [], 0
         for i, piece in enumerate(chunks):
             cop = DataFrameDataSource(gpu=gpu, data=piece)
-            out.append(cop.new_chunk([], shape=(len(piece), len(columns)), index=(i, 0), dtypes=dtypes,
-                                     index_value=IndexValue(pd.RangeIndex(start, start + len(piece))),
-                                     columns_value=IndexValue(columns)))
-            start += len(piece)
+            m = len(piece)
+            out.append(cop.new_chunk([], shape=(m, len(columns)), index=(i, 0), dtypes=dtypes,
+                                     index_value=IndexValue(lambda a=start, b=start + m: pd.RangeIndex(a, b)),
+                                     columns_value=cv))
+            start += m
         t.chunks = out
         t.nsplits = (tuple(c.shape[0] for c in out), (len(columns),))
         return cls(None, _tileable=t)

@@ -176,7 +176,23 @@ class _MapPlan:
 _map_plans: Dict[Any, _MapPlan] = {}
 
 
+_map_plans_fast: Dict[Any, Any] = {}
+
+
 def _map_plan(op, frame: DeviceFrame) -> _MapPlan:
+    # fast path: the mirror's map operands of one tileable share their agg_funcs list object
+    fast_key = (id(op.agg_funcs), id(op.groupby_params.get("by")), len(frame.columns))
+    hit = _map_plans_fast.get(fast_key)
+    if hit is not None and hit[0] is op.agg_funcs and hit[1] == frame.columns:
+        return hit[2]
+    plan = _map_plan_slow(op, frame)
+    if len(_map_plans_fast) > 256:
+        _map_plans_fast.clear()
+    _map_plans_fast[fast_key] = (op.agg_funcs, list(frame.columns), plan)
+    return plan
+
+
+def _map_plan_slow(op, frame: DeviceFrame) -> _MapPlan:
     params = op.groupby_params
     by = params.get("by")
     selection = params.get("selection")
@@ -245,7 +261,7 @@ def _execute_agg_map(ctx, op):
     frames = None
     if plan.shape_key not in _dense_rejected:
         if _ASYNC and hasattr(_kernels, "preagg_dense_async"):
-            res = _kernels.preagg_dense_async(keys, vals, plan.accs)
+            res = _kernels.preagg_dense_async(keys, vals, plan.accs, checked=True)
             if res is None:
                 _dense_rejected.add(plan.shape_key)
             else:
@@ -327,7 +343,7 @@ def _merge_partials(slots: Sequence[Sequence[DeviceFrame]], steps: Sequence[_Ste
                     pieces.append((f0.raw_index, cols, len(f0), 0))
             if not pieces:
                 pieces.append((base[0].raw_index, [t for s in grp for t in slots[s][0].raw_data], 0, 0))
-            res = _kernels.merge_small_async(pieces, ops, sort=force_sort)
+            res = _kernels.merge_small_async(pieces, ops, sort=force_sort, checked=True)
             if res is not None:
                 bi, bf, fc = res
                 pend_out = Pending(bi, fc.n_int, bi.shape[1],

@@ -360,7 +360,8 @@ def merge_small(pieces_keys: Sequence[Sequence[torch.Tensor]], pieces_accs: Sequ
     return fc.views(bi, bf, G)
 
 
-def preagg_dense_async(keys: Sequence[torch.Tensor], vals: Sequence[torch.Tensor], accs: Sequence[Tuple[int, int]]):
+def preagg_dense_async(keys: Sequence[torch.Tensor], vals: Sequence[torch.Tensor], accs: Sequence[Tuple[int, int]],
+                       checked: bool = False):
     """Like ``preagg_dense`` but without host synchronisation (mgb_preagg_dense_async): returns
     (int block, float block, fast-call) -- columns at capacity ``dense_capacity()``, the group count (or -1) in
     the device int64 at ``fc.count_ptr(bi)``.  None when the shape can never be dense (too many columns)."""
@@ -368,12 +369,13 @@ def preagg_dense_async(keys: Sequence[torch.Tensor], vals: Sequence[torch.Tensor
     lib = _lib.load()
     if len(vals) > _lib.MGB_MAX_VALS or len(accs) > _lib.MGB_MAX_ACCS:
         return None
-    for i, k in enumerate(keys):
-        _check_col(k, "key column")
-        if k.dtype != torch.int64:
-            raise MarsGBError(3, f"key {i}: dtype {k.dtype} not supported (int64 keys)")
-    for v in vals:
-        _check_col(v, "value column")
+    if not checked:   # columns of frames built by this package were validated when the frame was made
+        for i, k in enumerate(keys):
+            _check_col(k, "key column")
+            if k.dtype != torch.int64:
+                raise MarsGBError(3, f"key {i}: dtype {k.dtype} not supported (int64 keys)")
+        for v in vals:
+            _check_col(v, "value column")
     n = keys[0].numel()
     fc = _fast(len(keys), [F64 if v.dtype == torch.float64 else I64 for v in vals], accs)
     if _dense_cap is None:
@@ -395,7 +397,7 @@ SMALL_MAX_ROWS = 2048
 SMALL_MAX_PIECES = 16
 
 
-def merge_small_async(pieces, acc_ops: Sequence[int], sort: bool = False):
+def merge_small_async(pieces, acc_ops: Sequence[int], sort: bool = False, checked: bool = False):
     """Re-aggregation of small partial blocks without host synchronisation (mgb_merge_small_async).
     ``pieces``: list of (key tensors, accumulator tensors, n_rows or None, device count pointer or 0); a piece
     with n_rows None has its size in the device int64 at the given pointer.  Returns (int block, float block,
@@ -420,10 +422,12 @@ def merge_small_async(pieces, acc_ops: Sequence[int], sort: bool = False):
         karr = (C.c_void_p * nk)()
         aarr = (C.c_void_p * max(na, 1))()
         for j, t in enumerate(pk):
-            _check_col(t, "piece key")
+            if not checked:
+                _check_col(t, "piece key")
             karr[j] = t.data_ptr()
         for a, t in enumerate(pa):
-            _check_col(t, "piece accumulator")
+            if not checked:
+                _check_col(t, "piece accumulator")
             if (t.dtype == torch.float64) != (dts[a] == F64):
                 raise MarsGBError(1, "partial blocks differ in accumulator dtype")
             aarr[a] = t.data_ptr()
