@@ -97,6 +97,10 @@ int mgb_partition_scatter(const int32_t* pid, int64_t n_rows, int32_t n_partitio
  * (groupby(sort=True)).                                                                                 */
 typedef struct mgb_agg mgb_agg;
 int mgb_agg_create(mgb_agg** out, const mgb_agg_spec* spec, void* stream);
+/* Optional, before the first update: the caller expects (nearly) all key tuples of the coming batches to be
+ * distinct (it has seen an earlier chunk of the same computation spill most of its rows): the shared-memory
+ * pre-aggregation pass is skipped and every row goes straight to the global table at finalize.           */
+int mgb_agg_set_hint(mgb_agg* agg, int32_t expect_distinct_keys);
 int mgb_agg_update(mgb_agg* agg, const int64_t* const* key_cols, const void* const* val_cols,
                    int64_t n_rows);
 int mgb_agg_finalize(mgb_agg* agg, int64_t* out_n_groups);

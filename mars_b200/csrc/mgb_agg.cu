@@ -187,174 +187,196 @@ __global__ void __launch_bounds__(256) k_table_init(uint64_t* table, Layout L, l
 }
 
 // ----------------------------------------------------------------------------------------------------
-// phase 1a: privatised tiny-cardinality pre-aggregation
+// phase 1a: lean shared-memory hash pre-aggregation for the sum / mean / count shapes (PLAIN: every value
+// column float64 with SUM, no SUMSQ / MIN / MAX).  One pass, register double-buffered tiles of 1024 rows,
+// 512 threads per CTA, one CTA per SM.  Per-CTA table: keys[NK][cap] | rows[cap] (u32) | sum[NV][cap] (f64),
+// linear probing, 64-bit CAS claims.  count(x) == rows of the group because rows that carry a NaN (or a key
+// equal to the EMPTY marker) are not aggregated here but appended to the spill list, which the generic
+// global-table kernel handles.  When the table is 3/4 full it is frozen: hits keep aggregating on chip,
+// misses are spilled.  At the end every occupied slot becomes one partial row of the staging list.
 // ----------------------------------------------------------------------------------------------------
-struct TinyParams {
-  Batch b;
-  Layout L;
-  int GC;            // group capacity per CTA
-  int a0, a1;        // sorted accumulator range of this column group
+#define HASH_THREADS 512
+#define HASH_R 2
+
+struct HashParams {
+  const uint64_t* keys[MGB_MAX_KEYS];
+  const uint64_t* cols[8];
+  long long n;
+  int cap;                       // table slots (power of two)
+  int na;                        // spec accumulators
+  uint8_t acc_col[MGB_MAX_ACCS]; // spec accumulator a: value column it reads
+  uint8_t acc_op[MGB_MAX_ACCS];  // MGB_SUM or MGB_COUNT
   Ctl* ctl;
-  int* sticky_fail;  // aggregator-wide: a previous batch already proved the data is not tiny
-  Staging stg;
+  Staging stg;                   // column j < nk: key j, else spec accumulator j - nk
+  int32_t* miss;                 // spill list (row indices)
 };
 
-template <int NK>
-__device__ __forceinline__ int tiny_lookup(const volatile uint64_t* tk, int GC, int ng, const uint64_t* k) {
-  for (int j = 0; j < ng; ++j) {
-    bool eq = tk[j] == k[0];
-    if (NK == 2) eq = eq && (tk[GC + j] == k[1]);
-    if (eq) return j;
-  }
-  return -1;
-}
-
 template <int NK, int NV>
-__global__ void __launch_bounds__(TINY_WARPS * 32, 1) k_preagg_tiny(const TinyParams p) {
-  extern __shared__ __align__(16) uint64_t smem[];
-  // layout: tkeys[NK][GC] | acc[warp][g][a][lane] | ints
-  const int GC = p.GC;
-  const int nag = p.a1 - p.a0;
-  uint64_t* tk = smem;
-  uint64_t* accs = smem + MGB_MAX_KEYS * TINY_MAX_GC;
-  int* s_int = (int*)(accs + (size_t)TINY_WARPS * GC * nag * 32);
-  volatile int* s_ng = s_int;
-  int* s_lock = s_int + 1;
-  int* s_pos = s_int + 2;
+__global__ void __launch_bounds__(HASH_THREADS, 1) k_preagg_hash(const HashParams p) {
+  extern __shared__ __align__(16) uint64_t hsm[];
+  const int cap = p.cap;
+  const uint32_t mask = (uint32_t)cap - 1u;
+  uint64_t* sk = hsm;                                   // [NK][cap]
+  double* ssum = (double*)(sk + (size_t)NK * cap);      // [NV][cap]
+  uint32_t* srows = (uint32_t*)(ssum + (size_t)NV * cap);   // [cap]
+  int* s_int = (int*)(srows + cap);
+  int* s_count = s_int;   // occupied slots
+  int* s_cursor = s_int + 1;
+  long long* s_pos = (long long*)(s_int + 2);
+  const uint64_t E = (uint64_t)MGB_EMPTY_KEY;
 
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (*p.sticky_fail) {
-    if (threadIdx.x == 0) p.ctl->tiny_fail = 1;
-    return;
-  }
-  uint64_t* wacc = accs + (size_t)warp * GC * nag * 32;
-  for (int i = lane; i < GC * nag * 32; i += 32) {
-    const int a = (i >> 5) % nag;
-    wacc[i] = mgb_acc_init(p.L.acc[p.a0 + a].op);
+  for (int i = threadIdx.x; i < cap; i += HASH_THREADS) {
+    sk[i] = E;
+    if (NK == 2) sk[cap + i] = E;
+    srows[i] = 0;
+#pragma unroll
+    for (int c = 0; c < NV; ++c) ssum[(size_t)c * cap + i] = 0.0;
   }
   if (threadIdx.x == 0) {
-    *s_ng = 0;
-    *s_lock = 0;
+    *s_count = 0;
+    *s_cursor = 0;
   }
   __syncthreads();
 
-  const long long n = p.b.n;
-  const long long tile_rows = (long long)blockDim.x * TINY_ROWS;
-  const long long ntiles = (n + tile_rows - 1) / tile_rows;
-  bool failed = false;
-  for (long long t = blockIdx.x; t < ntiles && !failed; t += gridDim.x) {
-    if (__any_sync(0xffffffffu, *(volatile int*)&p.ctl->tiny_fail)) {
-      failed = true;
-      break;
-    }
-    const long long base = t * tile_rows + threadIdx.x;
-    uint64_t k[TINY_ROWS][NK];
-    uint64_t x[TINY_ROWS][NV];
-    bool valid[TINY_ROWS];
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = mgb_lanemask_lt();
+  const int max_fill = cap - cap / 4;
+  const long long n = p.n;
+  constexpr long long TILE = (long long)HASH_THREADS * HASH_R;
+  const long long nfull = n / TILE;
+
+  auto process_row = [&](const uint64_t* k, const uint64_t* x, long long row, bool live) {
+    int slot = -1;
+    if (live) {
+      bool ok = k[0] != E && (NK == 1 || k[1] != E);
 #pragma unroll
-    for (int r = 0; r < TINY_ROWS; ++r) {
-      const long long i = base + (long long)r * blockDim.x;
-      valid[r] = i < n;
-#pragma unroll
-      for (int j = 0; j < NK; ++j) k[r][j] = valid[r] ? mgb_ld_stream(p.b.keys[j] + i) : 0;
-#pragma unroll
-      for (int c = 0; c < NV; ++c) x[r][c] = (valid[r] && c < p.b.ncol) ? mgb_ld_stream(p.b.cols[c] + i) : 0;
-    }
-#pragma unroll
-    for (int r = 0; r < TINY_ROWS; ++r) {
-      int g = -1;
-      if (valid[r]) g = tiny_lookup<NK>(tk, TINY_MAX_GC, *s_ng, k[r]);
-      unsigned need = __ballot_sync(0xffffffffu, valid[r] && g < 0);
-      while (need) {
-        const int src = __ffs(need) - 1;
-        uint64_t ks[NK];
-#pragma unroll
-        for (int j = 0; j < NK; ++j) ks[j] = __shfl_sync(0xffffffffu, k[r][j], src);
-        int gi = 0;
-        if (lane == 0) {
-          while (atomicCAS(s_lock, 0, 1) != 0) {
-          }
-          __threadfence_block();
-          const int ng = *s_ng;
-          gi = tiny_lookup<NK>(tk, TINY_MAX_GC, ng, ks);
-          if (gi < 0) {
-            if (ng < GC) {
-#pragma unroll
-              for (int j = 0; j < NK; ++j) ((volatile uint64_t*)tk)[j * TINY_MAX_GC + ng] = ks[j];
-              __threadfence_block();
-              *s_ng = ng + 1;
-              gi = ng;
-            } else {
-              gi = -2;
+      for (int c = 0; c < NV; ++c) {
+        const double xv = __longlong_as_double((long long)x[c]);
+        ok = ok && (xv == xv);
+      }
+      if (ok) {
+        uint32_t idx = (uint32_t)(mgb_slot_hash(mgb_hash_tuple<NK>((const int64_t*)k)) >> 40) & mask;
+        // a frozen (3/4 full) table is probed 4 slots deep only: a key that sits further away is treated as
+        // a miss, which is still correct (the row is aggregated by the global path and merged with the
+        // staged partial of that key) and bounds the cost of a chunk whose keys are mostly distinct
+        const int max_probe = *(volatile int*)s_count >= max_fill ? 4 : cap;
+        for (int probe = 0; probe < max_probe; ++probe, idx = (idx + 1) & mask) {
+          uint64_t cur = *(volatile uint64_t*)&sk[idx];
+          if (cur == E) {
+            if (*(volatile int*)s_count >= max_fill) break;   // frozen: no more inserts
+            cur = atomicCAS((unsigned long long*)&sk[idx], (unsigned long long)E, (unsigned long long)k[0]);
+            if (cur == E) {
+              if (NK == 2) *(volatile uint64_t*)&sk[cap + idx] = k[1];
+              atomicAdd(s_count, 1);
+              slot = (int)idx;
+              break;
             }
           }
-          __threadfence_block();
-          atomicExch(s_lock, 0);
-        }
-        gi = __shfl_sync(0xffffffffu, gi, 0);
-        if (gi < 0) {
-          failed = true;
-          break;
-        }
-        bool mine = valid[r] && g < 0;
-#pragma unroll
-        for (int j = 0; j < NK; ++j) mine = mine && (k[r][j] == ks[j]);
-        if (mine) g = gi;
-        need = __ballot_sync(0xffffffffu, valid[r] && g < 0);
-      }
-      if (failed) break;
-      if (valid[r]) {
-        uint64_t* ga = wacc + (size_t)g * nag * 32 + lane;
-#pragma unroll
-        for (int c = 0; c < NV; ++c) {
-          if (c < p.b.ncol) {
-            const int jb = p.L.col_begin[p.b.c0 + c], je = p.L.col_begin[p.b.c0 + c + 1];
-            for (int j = jb; j < je; ++j) {
-              const AccDesc d = p.L.acc[j];
-              uint64_t contrib;
-              if (mgb_contrib(d.op, d.dt, x[r][c], &contrib)) {
-                uint64_t* a = ga + (size_t)(j - p.a0) * 32;
-                *a = mgb_combine(d.kind, *a, contrib);
-              }
+          if (cur == k[0]) {
+            if (NK == 1) {
+              slot = (int)idx;
+              break;
+            }
+            // second key of a freshly claimed slot may not be published yet: reads as EMPTY -> mismatch ->
+            // the row claims another slot; duplicate entries of one key are benign (merged later)
+            if (*(volatile uint64_t*)&sk[cap + idx] == k[1]) {
+              slot = (int)idx;
+              break;
             }
           }
         }
       }
+      if (slot >= 0) {
+        atomicAdd(&srows[slot], 1u);
+#pragma unroll
+        for (int c = 0; c < NV; ++c) atomicAdd(&ssum[(size_t)c * cap + slot], __longlong_as_double((long long)x[c]));
+      }
+    }
+    const bool miss = live && slot < 0;
+    const unsigned mm = __ballot_sync(0xffffffffu, miss);
+    if (mm) {   // warp-aggregated append to the spill list
+      unsigned long long pos = 0;
+      if (lane == 0) pos = atomicAdd(&p.ctl->miss_count[0], (unsigned long long)__popc(mm));
+      pos = __shfl_sync(0xffffffffu, pos, 0);
+      if (miss) p.miss[pos + __popc(mm & lt)] = (int32_t)row;
+    }
+  };
+
+  uint64_t kb[2][HASH_R][NK];
+  uint64_t xb[2][HASH_R][NV];
+  const uint64_t* pk[NK];
+  const uint64_t* pc[NV];
+#pragma unroll
+  for (int j = 0; j < NK; ++j) pk[j] = p.keys[j] + threadIdx.x;
+#pragma unroll
+  for (int c = 0; c < NV; ++c) pc[c] = p.cols[c] + threadIdx.x;
+  auto load_tile = [&](int buf, long long t) {
+    const long long off = t * TILE;
+#pragma unroll
+    for (int j = 0; j < NK; ++j)
+#pragma unroll
+      for (int r = 0; r < HASH_R; ++r) kb[buf][r][j] = __ldcs((const unsigned long long*)(pk[j] + off) + r * HASH_THREADS);
+#pragma unroll
+    for (int c = 0; c < NV; ++c)
+#pragma unroll
+      for (int r = 0; r < HASH_R; ++r) xb[buf][r][c] = __ldcs((const unsigned long long*)(pc[c] + off) + r * HASH_THREADS);
+  };
+  auto process_tile = [&](int buf, long long t) {
+    const long long base = t * TILE + threadIdx.x;
+#pragma unroll
+    for (int r = 0; r < HASH_R; ++r) process_row(kb[buf][r], xb[buf][r], base + (long long)r * HASH_THREADS, true);
+  };
+  long long t = blockIdx.x;
+  if (t < nfull) load_tile(0, t);
+  while (t < nfull) {
+    const long long t1 = t + gridDim.x;
+    if (t1 < nfull) load_tile(1, t1);
+    process_tile(0, t);
+    if (t1 >= nfull) break;
+    const long long t2 = t1 + gridDim.x;
+    if (t2 < nfull) load_tile(0, t2);
+    process_tile(1, t1);
+    t = t2;
+  }
+  if ((int)(nfull % gridDim.x) == (int)blockIdx.x) {   // ragged tail, whole warps so the ballots stay converged
+    for (long long i0 = nfull * TILE + (threadIdx.x & ~31); i0 < n; i0 += HASH_THREADS) {
+      const long long i = i0 + lane;
+      const bool live = i < n;
+      uint64_t k[NK], x[NV];
+#pragma unroll
+      for (int j = 0; j < NK; ++j) k[j] = live ? p.keys[j][i] : 0;
+#pragma unroll
+      for (int c = 0; c < NV; ++c) x[c] = live ? p.cols[c][i] : 0;
+      process_row(k, x, i, live);
     }
   }
-  if (failed) p.ctl->tiny_fail = 1;
+  // flush: one staged partial row per occupied slot
   __syncthreads();
-  if (*(volatile int*)&p.ctl->tiny_fail) {
-    if (threadIdx.x == 0) *p.sticky_fail = 1;
-    return;
+  const int cnt = *s_count;
+  if (cnt == 0) return;
+  if (threadIdx.x == 0) {
+    const unsigned long long pos = atomicAdd(&p.ctl->stg_count, (unsigned long long)cnt);
+    if (pos + cnt > (unsigned long long)p.stg.cap) {
+      p.ctl->err = 1;
+      *s_pos = -1;
+    } else {
+      *s_pos = (long long)pos;
+    }
   }
-  // reduce lanes and warps, stage one partial row per group of this CTA
-  const int ng = *s_ng;
-  if (ng == 0) return;
-  if (threadIdx.x == 0) *s_pos = (int)atomicAdd(&p.ctl->tiny_count, (unsigned long long)ng);
   __syncthreads();
   const long long pos0 = *s_pos;
-  for (int q = warp; q < ng * p.L.na; q += TINY_WARPS) {
-    const int g = q / p.L.na, spec_a = q % p.L.na;
-    // sorted position of spec accumulator spec_a (identity value if it is not in this column group)
-    int j = p.L.spec_sorted[spec_a];
-    if (j < p.a0 || j >= p.a1) j = -1;
-    const int op = p.L.spec_op[spec_a], dt = p.L.spec_dt[spec_a];
-    uint64_t v = mgb_acc_init(op);
-    if (j >= 0) {
-      const int kind = p.L.acc[j].kind;
-      for (int w = 0; w < TINY_WARPS; ++w)
-        v = mgb_combine(kind, v, accs[((size_t)w * GC + g) * nag * 32 + (size_t)(j - p.a0) * 32 + lane]);
-      for (int o = 16; o > 0; o >>= 1) {
-        uint64_t y = __shfl_xor_sync(0xffffffffu, v, o);
-        v = mgb_combine(kind, v, y);
-      }
+  if (pos0 < 0) return;
+  for (int i = threadIdx.x; i < cap; i += HASH_THREADS) {
+    const uint64_t k0 = sk[i];
+    if (k0 == E) continue;
+    const long long row = pos0 + atomicAdd(s_cursor, 1);
+    st_stage(p.stg, 0, row, k0);
+    if (NK == 2) st_stage(p.stg, 1, row, sk[cap + i]);
+    for (int a = 0; a < p.na; ++a) {
+      const uint64_t v = p.acc_op[a] == MGB_COUNT ? (uint64_t)srows[i]
+                                                   : (uint64_t)__double_as_longlong(ssum[(size_t)p.acc_col[a] * cap + i]);
+      st_stage(p.stg, NK + a, row, v);
     }
-    if (lane == 0) st_stage(p.stg, p.L.nk + spec_a, pos0 + g, mgb_acc_decode(op, dt, v));
-  }
-  for (int q = threadIdx.x; q < ng * NK; q += blockDim.x) {
-    const int g = q / NK, j = q % NK;
-    st_stage(p.stg, j, pos0 + g, tk[j * TINY_MAX_GC + g]);
   }
 }
 
@@ -639,6 +661,66 @@ __global__ void __launch_bounds__(GLOBAL_THREADS) k_update_global(const GlobalPa
   block_count_groups(inserted, p.g);
 }
 
+// Lean variant for the sum / mean / count shapes (every value column float64, accumulators SUM / COUNT):
+// straight-line per column, RED.ADD.F64 for the sums, one RED.ADD.U64 per counted column; NaN values are
+// skipped per column exactly like pandas' skipna sums / counts.
+struct GlobalPlainParams {
+  const uint64_t* keys[MGB_MAX_KEYS];
+  const uint64_t* cols[8];
+  int8_t sum_word[8];      // table word (after the keys) of column c's SUM accumulator, -1: none
+  int8_t cnt_word[8][4];   // up to 4 COUNT accumulators may share a column (dict forms); -1 terminated
+  int W;
+  uint64_t* table;
+  unsigned long long Cmask;
+  int shift;
+  GlobalCtl* g;
+  const int32_t* gather;
+  long long n_rows;
+};
+
+template <int NK, int NV>
+__global__ void __launch_bounds__(GLOBAL_THREADS) k_update_global_plain(const GlobalPlainParams p) {
+  int inserted = 0;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long q0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; q0 < p.n_rows; q0 += stride * 4) {
+    uint64_t k[4][NK];
+    uint64_t x[4][NV];
+    bool valid[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const long long q = q0 + (long long)r * stride;
+      valid[r] = q < p.n_rows;
+      long long i = 0;
+      if (valid[r]) i = p.gather ? (long long)p.gather[q] : q;
+#pragma unroll
+      for (int j = 0; j < NK; ++j) k[r][j] = valid[r] ? mgb_ld_stream(p.keys[j] + i) : 0;
+#pragma unroll
+      for (int c = 0; c < NV; ++c) x[r][c] = valid[r] ? mgb_ld_stream(p.cols[c] + i) : 0;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      if (!valid[r]) continue;
+      const uint64_t h = mgb_hash_tuple<NK>((const int64_t*)k[r]);
+      const long long slot = global_find_or_insert<NK>(p.table, p.W, p.Cmask, p.shift, k[r], h, p.g, &inserted);
+      if (slot < 0) {
+        p.g->err = 1;
+        continue;
+      }
+      uint64_t* acc = p.table + (unsigned long long)slot * p.W + NK;
+#pragma unroll
+      for (int c = 0; c < NV; ++c) {
+        const double xv = __longlong_as_double((long long)x[r][c]);
+        if (xv != xv) continue;
+        if (p.sum_word[c] >= 0) atomicAdd((double*)(acc + p.sum_word[c]), xv);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (p.cnt_word[c][q] >= 0) atomicAdd((unsigned long long*)(acc + p.cnt_word[c][q]), 1ULL);
+      }
+    }
+  }
+  block_count_groups(inserted, p.g);
+}
+
 // staged partial rows (decoded values, one column per spec accumulator) -> global table
 struct MergeParams {
   Staging stg;
@@ -755,6 +837,7 @@ struct UpdateRec {
   long long inter_cap;
   int32_t* miss;                  // [n_groups][n]
   bool tiny_tried;
+  bool direct;                    // no pre-aggregation pass: every row goes to the global table at finalize
 };
 
 struct mgb_agg {
@@ -770,6 +853,8 @@ struct mgb_agg {
   long long C;
   int shift;
   bool finalized;
+  bool direct_hint;       // caller expects (nearly) distinct keys: skip the shared-memory pre-aggregation
+  bool plain;             // sum / mean / count shape: lean kernels apply
   long long n_groups;
   std::vector<UpdateRec> updates;
   long long stats[6];
@@ -831,6 +916,20 @@ extern "C" int mgb_agg_create(mgb_agg** out, const mgb_agg_spec* spec, void* str
   }
   a->table = nullptr;
   a->C = 0;
+  a->direct_hint = false;
+  a->plain = a->n_col_groups == 1 && spec->n_vals <= 8;
+  for (int c = 0; c < spec->n_vals && a->plain; ++c) a->plain = spec->val_dtype[c] == MGB_F64;
+  for (int i = 0; i < spec->n_accs && a->plain; ++i) {
+    a->plain = spec->acc_op[i] == MGB_SUM || spec->acc_op[i] == MGB_COUNT;
+  }
+  if (a->plain) {   // at most one SUM and four COUNT accumulators per column fit the lean kernels' tables
+    for (int c = 0; c < spec->n_vals && a->plain; ++c) {
+      int ns = 0, nc = 0;
+      for (int i = 0; i < spec->n_accs; ++i)
+        if (spec->acc_col[i] == c) (spec->acc_op[i] == MGB_SUM ? ns : nc)++;
+      a->plain = ns <= 1 && nc <= 4;
+    }
+  }
   a->finalized = false;
   a->n_groups = 0;
   memset(a->stats, 0, sizeof(a->stats));
@@ -913,51 +1012,73 @@ extern "C" int mgb_agg_update(mgb_agg* a, const int64_t* const* key_cols, const 
   long long ntiles = (n_rows + tile_rows - 1) / tile_rows;
   int smem_grid = (int)(ntiles < a->sms ? ntiles : a->sms);
 
-  // tiny kernel applicability: a single column group and room for >= 4 groups per warp
-  int GC = 0;
-  if (a->n_col_groups == 1) {
-    size_t per_group = (size_t)L.na * 32 * 8 * TINY_WARPS;
-    GC = (int)((SMEM_BUDGET - 1024) / per_group);
-    if (GC > TINY_MAX_GC) GC = TINY_MAX_GC;
-    if (GC < 4) GC = 0;
+  if (a->direct_hint) {   // nothing to launch now: the whole batch is inserted at finalize
+    u.direct = true;
+    a->updates.push_back(u);
+    return MGB_OK;
   }
-  const long long ttile = (long long)TINY_WARPS * 32 * TINY_ROWS;
-  long long tt = (n_rows + ttile - 1) / ttile;
-  int tiny_grid = (int)(tt < a->sms ? tt : a->sms);
+  // PLAIN shape (every value column float64, only SUM / COUNT, one column group): lean hash kernel
+  const bool plain = a->plain;
+  int hcap = 4096;
+  while (hcap > 64 && (size_t)hcap * ((L.nk + L.nv) * 8 + 4) + 64 > SMEM_BUDGET) hcap >>= 1;
+  const long long htiles = (n_rows + 1023) / 1024;
+  const int hash_grid = (int)(htiles < a->sms ? htiles : a->sms);
+  if (plain) {
+    cap = hcap;
+    smem_grid = hash_grid;
+  }
 
-  // allocations: ctl | smem staging | tiny staging | spill lists
+  // allocations: ctl | staging | spill lists
   MGB_CUDA(cudaMallocAsync((void**)&u.ctl, sizeof(Ctl), st));
   MGB_CUDA(cudaMemsetAsync(u.ctl, 0, sizeof(Ctl), st));
   const int ncolstg = L.nk + L.na;
-  u.inter_cap = n_rows / FLUSH_GAIN;
+  u.inter_cap = plain ? 0 : n_rows / FLUSH_GAIN;
   if (u.inter_cap > MAX_INTER_ROWS) u.inter_cap = MAX_INTER_ROWS;
   u.stg.cap = u.inter_cap + (long long)smem_grid * cap * a->n_col_groups;
   MGB_CUDA(cudaMallocAsync((void**)&u.stg.base, (size_t)u.stg.cap * ncolstg * 8, st));
-  u.tstg.cap = (long long)tiny_grid * TINY_MAX_GC;
+  u.tstg.cap = 0;
   u.tstg.base = nullptr;
-  if (GC) MGB_CUDA(cudaMallocAsync((void**)&u.tstg.base, (size_t)u.tstg.cap * ncolstg * 8, st));
   MGB_CUDA(cudaMallocAsync((void**)&u.miss, sizeof(int32_t) * (size_t)n_rows * a->n_col_groups, st));
-  u.tiny_tried = GC > 0;
+  u.tiny_tried = false;
 
-  if (GC) {
-    TinyParams p;
-    fill_group(a, u, 0, &p.b);
-    p.L = L;
-    p.GC = GC;
-    p.a0 = 0;
-    p.a1 = L.na;
+  if (plain) {
+    HashParams p;
+    memset(&p, 0, sizeof(p));
+    for (int j = 0; j < L.nk; ++j) p.keys[j] = u.batch.keys[j];
+    for (int c = 0; c < L.nv; ++c) p.cols[c] = u.vals[c];
+    p.n = n_rows;
+    p.cap = hcap;
+    p.na = L.na;
+    for (int i = 0; i < L.na; ++i) {
+      p.acc_col[i] = (uint8_t)a->spec.acc_col[i];
+      p.acc_op[i] = (uint8_t)a->spec.acc_op[i];
+    }
     p.ctl = u.ctl;
-    p.sticky_fail = a->sticky_fail;
-    p.stg = u.tstg;
-    size_t sm = (size_t)(MGB_MAX_KEYS * TINY_MAX_GC + (size_t)TINY_WARPS * GC * L.na * 32) * 8 + 64;
-    MgbProfScope prof(MGB_K_PREAGG_TINY, st);
-#define CALL(NK, NV)                                                               \
-  MGB_TRY(set_smem(k_preagg_tiny<NK, NV>, sm));                                    \
-  k_preagg_tiny<NK, NV><<<tiny_grid, TINY_WARPS * 32, sm, st>>>(p);
-    DISPATCH_NK_NV(L.nk, p.b.ncol, CALL);
-#undef CALL
+    p.stg = u.stg;
+    p.miss = u.miss;
+    const size_t sm = (size_t)hcap * ((L.nk + L.nv) * 8 + 4) + 64;
+    MgbProfScope prof(MGB_K_PREAGG_SMEM, st);
+#define CALLH(NK, NV)                                          \
+  MGB_TRY(set_smem(k_preagg_hash<NK, NV>, sm));                \
+  k_preagg_hash<NK, NV><<<hash_grid, HASH_THREADS, sm, st>>>(p);
+#define PICKH(NK)                                  \
+  switch (L.nv) {                                  \
+    case 1: { CALLH(NK, 1) } break;                \
+    case 2: { CALLH(NK, 2) } break;                \
+    case 3: { CALLH(NK, 3) } break;                \
+    case 4: { CALLH(NK, 4) } break;                \
+    case 5: { CALLH(NK, 5) } break;                \
+    case 6: { CALLH(NK, 6) } break;                \
+    case 7: { CALLH(NK, 7) } break;                \
+    default: { CALLH(NK, 8) } break;               \
+  }
+    if (L.nk == 1) { PICKH(1) } else { PICKH(2) }
+#undef PICKH
+#undef CALLH
     MGB_CHECK_LAUNCH();
     a->stats[5]++;
+    a->updates.push_back(u);
+    return MGB_OK;
   }
   for (int g = 0; g < a->n_col_groups; ++g) {
     SmemParams p;
@@ -967,7 +1088,7 @@ extern "C" int mgb_agg_update(mgb_agg* a, const int64_t* const* key_cols, const 
     p.a0 = a->group_a0[g];
     p.a1 = a->group_a0[g + 1];
     p.ctl = u.ctl;
-    p.require_tiny_fail = GC ? 1 : 0;
+    p.require_tiny_fail = 0;
     p.stg = u.stg;
     p.inter_cap = u.inter_cap;
     p.miss = u.miss + (size_t)g * n_rows;
@@ -1001,12 +1122,22 @@ extern "C" int mgb_agg_finalize(mgb_agg* a, int64_t* out_n_groups) {
   const size_t U = a->updates.size();
   // 1. read back the phase-1 counters (the only mid-flight synchronisation)
   std::vector<Ctl> ctl(U);
-  for (size_t i = 0; i < U; ++i)
+  bool any_pre = false;
+  for (size_t i = 0; i < U; ++i) {
+    memset(&ctl[i], 0, sizeof(Ctl));
+    if (a->updates[i].direct) continue;
+    any_pre = true;
     MGB_CUDA(cudaMemcpyAsync(&ctl[i], a->updates[i].ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
-  MGB_CUDA(cudaStreamSynchronize(st));
+  }
+  if (any_pre) MGB_CUDA(cudaStreamSynchronize(st));
   long long total = 0;
   for (size_t i = 0; i < U; ++i) {
     const UpdateRec& u = a->updates[i];
+    if (u.direct) {
+      total += u.batch.n;
+      a->stats[2] += u.batch.n;
+      continue;
+    }
     MGB_REQUIRE(ctl[i].err == 0, MGB_ERR_OVERFLOW, "staging overflow in update %zu", i);
     const bool tiny_ok = u.tiny_tried && !ctl[i].tiny_fail;
     if (tiny_ok) {
@@ -1043,8 +1174,87 @@ extern "C" int mgb_agg_finalize(mgb_agg* a, int64_t* out_n_groups) {
     a->stats[5]++;
   }
   // 3. merges
+  GlobalPlainParams gp;
+  memset(&gp, 0, sizeof(gp));
+  if (a->plain) {
+    for (int c = 0; c < 8; ++c) {
+      gp.sum_word[c] = -1;
+      for (int q = 0; q < 4; ++q) gp.cnt_word[c][q] = -1;
+    }
+    for (int i = 0; i < L.na; ++i) {   // table word order == spec accumulator order
+      const int c = a->spec.acc_col[i];
+      if (a->spec.acc_op[i] == MGB_SUM) {
+        gp.sum_word[c] = (int8_t)i;
+      } else {
+        for (int q = 0; q < 4; ++q)
+          if (gp.cnt_word[c][q] < 0) {
+            gp.cnt_word[c][q] = (int8_t)i;
+            break;
+          }
+      }
+    }
+    gp.W = L.W;
+    gp.table = a->table;
+    gp.Cmask = (unsigned long long)(C - 1);
+    gp.shift = a->shift;
+    gp.g = a->gctl;
+  }
+  auto launch_plain = [&](const UpdateRec& u, const int32_t* gather, long long nrows) -> int {
+    GlobalPlainParams q = gp;
+    for (int j = 0; j < L.nk; ++j) q.keys[j] = u.batch.keys[j];
+    for (int c = 0; c < L.nv; ++c) q.cols[c] = u.vals[c];
+    q.gather = gather;
+    q.n_rows = nrows;
+    const unsigned grid = grid_rows(a, nrows, GLOBAL_THREADS, 4);
+    MgbProfScope prof(MGB_K_UPDATE_GLOBAL, st);
+#define CALLG(NK, NV) k_update_global_plain<NK, NV><<<grid, GLOBAL_THREADS, 0, st>>>(q);
+#define PICKG(NK)                                  \
+  switch (L.nv) {                                  \
+    case 1: { CALLG(NK, 1) } break;                \
+    case 2: { CALLG(NK, 2) } break;                \
+    case 3: { CALLG(NK, 3) } break;                \
+    case 4: { CALLG(NK, 4) } break;                \
+    case 5: { CALLG(NK, 5) } break;                \
+    case 6: { CALLG(NK, 6) } break;                \
+    case 7: { CALLG(NK, 7) } break;                \
+    default: { CALLG(NK, 8) } break;               \
+  }
+    if (L.nk == 1) { PICKG(1) } else { PICKG(2) }
+#undef PICKG
+#undef CALLG
+    MGB_CHECK_LAUNCH();
+    a->stats[5]++;
+    return MGB_OK;
+  };
   for (size_t i = 0; i < U; ++i) {
     const UpdateRec& u = a->updates[i];
+    if (u.direct && a->plain) {
+      MGB_TRY(launch_plain(u, nullptr, u.batch.n));
+      continue;
+    }
+    if (u.direct) {   // generic shapes: the descriptor-driven kernel over the whole batch, per column group
+      for (int g = 0; g < a->n_col_groups; ++g) {
+        GlobalParams p;
+        fill_group(a, u, g, &p.b);
+        p.L = L;
+        p.a0 = a->group_a0[g];
+        p.a1 = a->group_a0[g + 1];
+        p.table = a->table;
+        p.Cmask = (unsigned long long)(C - 1);
+        p.shift = a->shift;
+        p.g = a->gctl;
+        p.gather = nullptr;
+        p.n_rows = u.batch.n;
+        unsigned grid = grid_rows(a, u.batch.n, GLOBAL_THREADS, GLOBAL_ROWS);
+        MgbProfScope prof(MGB_K_UPDATE_GLOBAL, st);
+#define CALL(NK, NV) k_update_global<NK, NV><<<grid, GLOBAL_THREADS, 0, st>>>(p);
+        DISPATCH_NK_NV(L.nk, p.b.ncol, CALL);
+#undef CALL
+        MGB_CHECK_LAUNCH();
+        a->stats[5]++;
+      }
+      continue;
+    }
     const bool tiny_ok = u.tiny_tried && !ctl[i].tiny_fail;
     MergeParams m;
     m.L = L;
@@ -1070,6 +1280,11 @@ extern "C" int mgb_agg_finalize(mgb_agg* a, int64_t* out_n_groups) {
       a->stats[5]++;
     }
     if (tiny_ok) continue;
+    if (a->plain) {
+      const long long nm = (long long)ctl[i].miss_count[0];
+      if (nm > 0) MGB_TRY(launch_plain(u, u.miss, nm));
+      continue;
+    }
     for (int g = 0; g < a->n_col_groups; ++g) {
       const long long nm = (long long)ctl[i].miss_count[g];
       if (nm == 0) continue;
@@ -1101,10 +1316,10 @@ extern "C" int mgb_agg_finalize(mgb_agg* a, int64_t* out_n_groups) {
   // phase-1 scratch is no longer needed
   for (size_t i = 0; i < U; ++i) {
     UpdateRec& u = a->updates[i];
-    cudaFreeAsync(u.ctl, st);
-    cudaFreeAsync(u.stg.base, st);
+    if (u.ctl) cudaFreeAsync(u.ctl, st);
+    if (u.stg.base) cudaFreeAsync(u.stg.base, st);
     if (u.tstg.base) cudaFreeAsync(u.tstg.base, st);
-    cudaFreeAsync(u.miss, st);
+    if (u.miss) cudaFreeAsync(u.miss, st);
     u.ctl = nullptr;
     u.stg.base = u.tstg.base = nullptr;
     u.miss = nullptr;
@@ -1112,6 +1327,13 @@ extern "C" int mgb_agg_finalize(mgb_agg* a, int64_t* out_n_groups) {
   a->n_groups = (long long)gh.n_groups;
   a->finalized = true;
   *out_n_groups = a->n_groups;
+  return MGB_OK;
+}
+
+extern "C" int mgb_agg_set_hint(mgb_agg* a, int32_t expect_distinct_keys) {
+  MGB_REQUIRE(a, MGB_ERR_INVALID, "null aggregator");
+  MGB_REQUIRE(a->updates.empty(), MGB_ERR_STATE, "hint must be set before the first update");
+  a->direct_hint = expect_distinct_keys != 0;
   return MGB_OK;
 }
 

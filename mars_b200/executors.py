@@ -37,6 +37,7 @@ _DECOMP_EXT = dict(_DECOMP, std=_DECOMP["var"])
 # recording double; the product never rebinds it.
 _kernels = K
 _dense_rejected = set()
+_distinct_shapes = set()   # shapes whose chunks spilled most rows: skip the shared-memory pre-aggregation
 # MGB_EAGER=1 disables the speculative asynchronous chain (every operand then waits for its result size)
 _ASYNC = os.environ.get("MGB_EAGER", "0") in ("", "0")
 
@@ -286,7 +287,15 @@ def _execute_agg_map(ctx, op):
                 n_out = int(out_keys[0].numel())
                 frames = [DeviceFrame(plan.by, out_keys, cols, out_accs[a0:a1], n_out) for cols, a0, a1 in plan.slots]
     if frames is None:
-        out_keys, out_accs, _ = _kernels.groupby_aggregate(keys, vals, list(plan.accs), sort=False)
+        if plan.shape_key in _distinct_shapes:
+            out_keys, out_accs, stats = _kernels.groupby_aggregate(keys, vals, list(plan.accs), sort=False,
+                                                                   expect_distinct=True)
+            if stats and int(out_keys[0].numel()) * 4 < int(keys[0].numel()):
+                _distinct_shapes.discard(plan.shape_key)     # the data changed: pre-aggregation pays again
+        else:
+            out_keys, out_accs, stats = _kernels.groupby_aggregate(keys, vals, list(plan.accs), sort=False)
+            if stats and stats.get("rows_spilled", 0) * 2 > int(keys[0].numel()):
+                _distinct_shapes.add(plan.shape_key)
         n_out = int(out_keys[0].numel())
         frames = [DeviceFrame(plan.by, out_keys, cols, out_accs[a0:a1], n_out) for cols, a0, a1 in plan.slots]
     if rec is not None:   # method='auto' samples real sizes: this resolves the count (one 8-byte read)

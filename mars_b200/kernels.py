@@ -106,7 +106,8 @@ def partition_scatter(pid: torch.Tensor, n_partitions: int, cols: Sequence[torch
 class Aggregator:
     """Streaming hash aggregation: update() any number of row batches, then result()."""
 
-    def __init__(self, n_keys: int, val_dtypes: Sequence[int], accs: Sequence[Tuple[int, int]]):
+    def __init__(self, n_keys: int, val_dtypes: Sequence[int], accs: Sequence[Tuple[int, int]],
+                 expect_distinct: bool = False):
         self._lib = _lib.load()
         self.n_keys = n_keys
         self.val_dtypes = list(val_dtypes)
@@ -117,6 +118,8 @@ class Aggregator:
         self._device = None
         self.stats = None
         check(self._lib.mgb_agg_create(C.byref(self._h), C.byref(self._spec), _stream()))
+        if expect_distinct:   # skip the shared-memory pre-aggregation pass (mgb_agg_set_hint)
+            check(self._lib.mgb_agg_set_hint(self._h, 1))
 
     def update(self, keys: Sequence[torch.Tensor], vals: Sequence[torch.Tensor]):
         keys = [_req(k, f"key {i}", (torch.int64,)) for i, k in enumerate(keys)]
@@ -172,9 +175,9 @@ class Aggregator:
             pass
 
 
-def groupby_aggregate(keys, vals, accs, sort=False):
+def groupby_aggregate(keys, vals, accs, sort=False, expect_distinct=False):
     """One-shot: (key tensors, accumulator tensors, stats)."""
-    agg = Aggregator(len(keys), [dtype_code(v) for v in vals], accs)
+    agg = Aggregator(len(keys), [dtype_code(v) for v in vals], accs, expect_distinct=expect_distinct)
     try:
         agg.update(keys, vals)
         k, a = agg.result(sort=sort, device=keys[0].device)

@@ -46,7 +46,13 @@ elif shape == "cfg4":
 else:
     raise SystemExit(shape)
 bytes_in = rows * 8 * (len(keys) + len(vals))
+import ctypes as C  # noqa: E402
+from mars_b200 import _lib  # noqa: E402
+lib = _lib.load()
+NAMES = ["preagg_dense", "preagg_smem/hash", "merge", "update_global", "table_init", "emit", "hash", "partition", "sort", "post"]
 for it in range(iters):
+    lib.mgb_prof_enable(1 if it == iters - 1 else 0)
+    lib.mgb_prof_reset()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -54,7 +60,8 @@ for it in range(iters):
     res = K.preagg_dense(keys, vals, accs) if os.environ.get("MGB_NO_DENSE") is None else None
     stats = "dense"
     if res is None:
-        k, a, stats = K.groupby_aggregate(keys, vals, accs, sort=False)
+        k, a, stats = K.groupby_aggregate(keys, vals, accs, sort=False,
+                                          expect_distinct=os.environ.get("MGB_DISTINCT") is not None)
     else:
         k, a = res
     e1.record()
@@ -62,3 +69,10 @@ for it in range(iters):
     ms = e0.elapsed_time(e1)
     print(f"{shape} rows={rows} groups={k[0].numel()} {ms:.3f} ms  {bytes_in / ms / 1e6:.1f} GB/s  "
           f"wall {1e3 * (time.perf_counter() - t0):.3f} ms  {stats}", flush=True)
+prof = {}
+for kid, name in enumerate(NAMES):
+    tot, cnt = C.c_double(), C.c_int64()
+    lib.mgb_prof_read(kid, C.byref(tot), C.byref(cnt))
+    if cnt.value:
+        prof[name] = f"{1e3 * tot.value:.1f} us / {cnt.value}"
+print("kernel time (CUDA events, last iteration):", prof)

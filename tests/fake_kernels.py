@@ -44,7 +44,7 @@ def partition_scatter(pid, n_partitions, cols):
     return [c[idx] for c in cols], offsets
 
 
-def groupby_aggregate(keys, vals, accs, sort=False):
+def groupby_aggregate(keys, vals, accs, sort=False, expect_distinct=False):
     calls.append("groupby_aggregate")
     df = pd.DataFrame({f"k{j}": _np(k) for j, k in enumerate(keys)})
     names = [f"k{j}" for j in range(len(keys))]
@@ -67,7 +67,7 @@ def groupby_aggregate(keys, vals, accs, sort=False):
 class Aggregator:
     """double of kernels.Aggregator: collects row batches, aggregates them on result()"""
 
-    def __init__(self, n_keys, val_dtypes, accs):
+    def __init__(self, n_keys, val_dtypes, accs, expect_distinct=False):
         self.n_keys, self.accs = n_keys, list(accs)
         self._k = [[] for _ in range(n_keys)]
         self._v = [[] for _ in val_dtypes]

@@ -139,7 +139,7 @@ def check_agg(K, keys, vals, accs, batches=1, expect_path=None):
 
 @pytest.mark.parametrize("n_keys", [1, 2])
 @pytest.mark.parametrize("n,card,path", [
-    (1, 1, None), (1000, 3, "rows_tiny"), (200000, 4, "rows_tiny"), (200000, 1000, "rows_smem"),
+    (1, 1, None), (1000, 3, "rows_smem"), (200000, 4, "rows_smem"), (200000, 1000, "rows_smem"),
     (500000, 50000, None), (300000, 300000, None)])
 def test_aggregate_matches_pandas(K, n_keys, n, card, path):
     rng = np.random.default_rng(n + card + n_keys)
@@ -180,6 +180,23 @@ def test_aggregate_nan_and_marker_keys(K):
     k = rng.integers(-2 ** 63, 2 ** 63 - 1, n, dtype=np.int64)
     k[::97] = -2 ** 63
     check_agg(K, [k], [v0, v1], accs)
+
+
+@pytest.mark.parametrize("n_keys", [1, 2])
+@pytest.mark.parametrize("n,card", [(1000, 5), (300_000, 1000), (300_000, 2500), (400_000, 20_000), (250_000, 250_000)])
+def test_aggregate_plain_shapes_take_the_lean_hash_kernel(K, n_keys, n, card):
+    """sum / mean / count shapes (float64 columns, SUM + COUNT): k_preagg_hash, incl. NaNs (spilled rows),
+    a frozen table (more groups than slots) and marker keys"""
+    rng = np.random.default_rng(n + card + n_keys)
+    keys = [rng.integers(-(card // 2), card - card // 2, n, dtype=np.int64)]
+    if n_keys == 2:
+        keys.append(rng.integers(0, 3, n, dtype=np.int64))
+    keys[0][::101] = -2 ** 63
+    vals = [rng.normal(10, 3, n), rng.random(n), rng.random(n)]
+    vals[1][rng.random(n) < 0.05] = np.nan
+    accs = [(0, "sum"), (1, "sum"), (2, "sum"), (0, "count"), (1, "count")]
+    stats = check_agg(K, keys, vals, accs, batches=2)
+    assert stats["rows_smem"] > 0
 
 
 def test_aggregate_skewed_keys(K):
@@ -357,3 +374,26 @@ def test_to_host_single_sync(K):
     np.testing.assert_array_equal(out[0], a)
     np.testing.assert_array_equal(out[1], b)
     assert out[0].dtype == np.float64 and out[1].dtype == np.int64
+
+
+@pytest.mark.parametrize("plain", [True, False])
+def test_aggregate_with_distinct_keys_hint_skips_preaggregation(K, plain):
+    rng = np.random.default_rng(31)
+    n = 300_000
+    keys = [rng.integers(-2 ** 62, 2 ** 62, n, dtype=np.int64)]
+    keys[0][::7] = keys[0][0]          # some duplicates all the same
+    vals = [rng.normal(0, 1, n), rng.random(n)]
+    vals[1][rng.random(n) < 0.1] = np.nan
+    accs = [(0, "sum"), (1, "sum"), (0, "count"), (1, "count")] + ([] if plain else [(1, "min"), (0, "max"), (0, "sumsq")])
+    code = dict(sum=K.SUM, sumsq=K.SUMSQ, count=K.COUNT, min=K.MIN, max=K.MAX)
+    k, a, stats = K.groupby_aggregate([dev(x) for x in keys], [dev(v) for v in vals], [(c, code[o]) for c, o in accs],
+                                      sort=True, expect_distinct=True)
+    assert stats["rows_smem"] == 0 and stats["rows_spilled"] == n
+    ek, ea = pandas_agg(keys, vals, accs)
+    np.testing.assert_array_equal(k[0].cpu().numpy(), ek[0])
+    for (col, op), got, exp in zip(accs, a, ea):
+        got = got.cpu().numpy()
+        if op in ("count", "min", "max"):
+            np.testing.assert_array_equal(got, exp.astype(got.dtype))
+        else:
+            np.testing.assert_allclose(got, exp, rtol=1e-9, atol=0, equal_nan=True)
