@@ -76,6 +76,13 @@ int mgb_hash_keys(const int64_t* const* key_cols, int32_t n_keys, int64_t n_rows
 int mgb_partition_ids(const int64_t* const* key_cols, int32_t n_keys, int64_t n_rows, int64_t n_partitions,
                       int32_t* out_pid, void* stream);
 
+/* sort=True shuffle (PSRS): range partition by pivots.  Replaces the label slices
+ * `in_df.loc[pivots[i-1]:pivots[i]].drop(index=pivots[i-1])` of DataFrameGroupbySortShuffle._execute_map
+ * (mars/dataframe/groupby/sort.py:113-135): out_pid = number of pivot tuples strictly smaller than the key
+ * tuple (pivots ascending; signed int64, lexicographic).  pivot_cols are device arrays of n_pivots entries. */
+int mgb_range_partition_ids(const int64_t* const* key_cols, int32_t n_keys, int64_t n_rows,
+                            const int64_t* const* pivot_cols, int32_t n_pivots, int32_t* out_pid, void* stream);
+
 /* ---- a5/a6: split partial rows into per-reducer blocks --------------------------------------------
  * Replaces `RangeIndex.groupby(hash % size)` + the K `iloc[f_i]` takes (groupby/core.py:389-435).
  * Stable: inside every partition rows keep their input order (== ascending positions f_i).

@@ -8,11 +8,11 @@ Layout (only what the path needs):
                          DataFrameConcat / DataFrameToGPU (drop-in via Operand.register_executor)
   core.py, dataframe.py, reduction.py, session.py   host-side mirror of the reference interface
   parallel.py            multi-GPU shuffle exchange (grouped ncclSend/ncclRecv)
-  store.py               GPU-resident chunk store
   plugin.py              registration on the real `mars` package when it is importable
 """
 from .core import OperandStage, ExecutionError, execute  # noqa: F401
 from .dataframe import (DataFrame, DataFrameConcat, DataFrameGroupByAgg, DataFrameGroupByOperand,  # noqa: F401
+                        DataFrameGroupbyConcatPivot, DataFrameGroupbySortShuffle, DataFramePSRSGroupbySample,
                         DataFrameShuffleProxy, DataFrameToGPU, options)
 from .executors import register_gpu_executors  # noqa: F401
 from .session import Session, new_session, get_default_session  # noqa: F401

@@ -299,6 +299,65 @@ extern "C" int mgb_partition_ids(const int64_t* const* key_cols, int32_t n_keys,
 }
 
 // ----------------------------------------------------------------------------------------------------
+// sort=True shuffle: range partition of partial rows by pivots (DataFrameGroupbySortShuffle._execute_map,
+// mars/dataframe/groupby/sort.py:113-135).  Partition i holds the key tuples in (pivot[i-1], pivot[i]], i.e.
+// partition id = number of pivots strictly smaller than the key tuple (pivots ascending, signed int64,
+// lexicographic for several keys) -- a binary search per row over the pivot table.
+// ----------------------------------------------------------------------------------------------------
+template <int NK>
+__device__ __forceinline__ bool tuple_less(const int64_t* a, const int64_t* b) {
+  if (a[0] != b[0]) return a[0] < b[0];
+  if (NK == 1) return false;
+  return a[1] < b[1];
+}
+
+template <int NK>
+__global__ void __launch_bounds__(256) k_range_pid(KeyCols kc, KeyCols pv, int n_pivots, int64_t n, int32_t* out_pid) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t k[NK];
+#pragma unroll
+    for (int j = 0; j < NK; ++j) k[j] = (int64_t)mgb_ld_stream((const uint64_t*)kc.k[j] + i);
+    int lo = 0, hi = n_pivots;   // first pivot that is not < key
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      int64_t p[NK];
+#pragma unroll
+      for (int j = 0; j < NK; ++j) p[j] = pv.k[j][mid];
+      if (tuple_less<NK>(p, k))
+        lo = mid + 1;
+      else
+        hi = mid;
+    }
+    out_pid[i] = lo;
+  }
+}
+
+extern "C" int mgb_range_partition_ids(const int64_t* const* key_cols, int32_t n_keys, int64_t n_rows,
+                                       const int64_t* const* pivot_cols, int32_t n_pivots, int32_t* out_pid,
+                                       void* stream) {
+  MGB_REQUIRE(n_keys >= 1 && n_keys <= MGB_MAX_KEYS, MGB_ERR_UNSUPPORTED, "n_keys=%d outside [1,%d]", n_keys,
+              MGB_MAX_KEYS);
+  MGB_REQUIRE(n_rows >= 0 && n_pivots >= 0, MGB_ERR_INVALID, "negative size");
+  if (n_rows == 0) return MGB_OK;
+  MGB_REQUIRE(key_cols && out_pid && (n_pivots == 0 || pivot_cols), MGB_ERR_INVALID, "null pointer");
+  KeyCols kc, pv;
+  for (int j = 0; j < MGB_MAX_KEYS; ++j) {
+    kc.k[j] = j < n_keys ? key_cols[j] : nullptr;
+    pv.k[j] = (j < n_keys && n_pivots > 0) ? pivot_cols[j] : nullptr;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t blocks = (n_rows + 255) / 256, cap = (int64_t)mgb_sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  MgbProfScope prof(MGB_K_HASH, st);
+  if (n_keys == 1)
+    k_range_pid<1><<<(unsigned)blocks, 256, 0, st>>>(kc, pv, n_pivots, n_rows, out_pid);
+  else
+    k_range_pid<2><<<(unsigned)blocks, 256, 0, st>>>(kc, pv, n_pivots, n_rows, out_pid);
+  MGB_CHECK_LAUNCH();
+  return MGB_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------
 // a10: post functions.  Operation order follows the reference's generated source exactly.
 // ----------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double as_f64(const void* p, int dt, int64_t i) {

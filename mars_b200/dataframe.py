@@ -60,6 +60,23 @@ class DataFrameConcat(Operand):
     """Row-wise concatenation; on this path only the tuple-of-partials branch (merge/concat.py:339-348)."""
 
 
+class DataFramePSRSGroupbySample(Operand):
+    """regular samples of a key-sorted partial (reference: groupby/sort.py:70-97); field n_partition"""
+
+
+class DataFrameGroupbyConcatPivot(Operand):
+    """gathers the samples and picks p - 1 pivots (reference: groupby/sort.py:36-67)"""
+
+
+class DataFrameGroupbySortShuffle(MapReduceOperand):
+    """range shuffle of groupby(sort=True): map = split by pivots, reduce = gather (groupby/sort.py:100-167).
+
+    fields: by, n_partition, shuffle_size"""
+
+    def __init__(self, by=None, n_partition=None, shuffle_size=None, **kw):
+        super().__init__(by=by, n_partition=n_partition, shuffle_size=shuffle_size, **kw)
+
+
 class DataFrameGroupByOperand(MapReduceOperand):
     """groupby operand; stage map/reduce implement the hash shuffle (groupby/core.py:353-485).
 
@@ -206,14 +223,36 @@ class DataFrameGroupByAgg(Operand):
         return reduces
 
     @classmethod
+    def _gen_shuffle_chunks_with_pivot(cls, op, chunks):
+        """sort=True: PSRS range shuffle -- sample every partial, pick pivots, split by pivots, gather
+        (aggregation.py:316-426, 563-641)"""
+        n = len(chunks)
+        by = op.groupby_params["by"]
+        samples = []
+        for i, chunk in enumerate(chunks):
+            sop = DataFramePSRSGroupbySample(n_partition=n, by=by, gpu=op.gpu)
+            samples.append(sop.new_chunk([chunk], shape=(n, np.nan), index=(i, 0), index_value=chunk.index_value))
+        pivot = DataFrameGroupbyConcatPivot(n_partition=n, by=by, gpu=op.gpu).new_chunk(samples, shape=(n,))
+        maps = []
+        for chunk in chunks:
+            mop = DataFrameGroupbySortShuffle(stage=OperandStage.map, shuffle_size=n, n_partition=n, gpu=op.gpu)
+            maps.append(mop.new_chunk([chunk, pivot], shape=(np.nan, np.nan), index=chunk.index,
+                                      index_value=chunk.index_value))
+        proxy = DataFrameShuffleProxy(gpu=op.gpu).new_chunk(maps, shape=())
+        reduces = []
+        for i, m in enumerate(maps):
+            rop = DataFrameGroupbySortShuffle(stage=OperandStage.reduce, reducer_index=(i, 0), n_reducers=n, by=by,
+                                              gpu=op.gpu)
+            reduces.append(rop.new_chunk([proxy], shape=(np.nan, np.nan), index=m.index, index_value=m.index_value))
+        return reduces
+
+    @classmethod
     def _perform_shuffle(cls, op, agg_chunks, in_df, out_df, steps):
         """aggregation.py:643-702"""
         if op.groupby_params["sort"] and len(in_df.chunks) > 1:
-            raise NotImplementedError(
-                "groupby(sort=True).agg(method='shuffle') range-partitions with PSRS sampling "
-                "(mars/dataframe/groupby/sort.py); this build implements the hash shuffle: pass sort=False "
-                "(SURVEY.md section 8f, rank 1)")
-        reduce_chunks = cls._gen_shuffle_chunks(op, agg_chunks)
+            reduce_chunks = cls._gen_shuffle_chunks_with_pivot(op, agg_chunks)
+        else:
+            reduce_chunks = cls._gen_shuffle_chunks(op, agg_chunks)
         outs = []
         for chunk in reduce_chunks:
             aop = cls._agg_like_op(op, OperandStage.agg, steps, with_post=True)

@@ -399,7 +399,7 @@ def _pieces_of(value) -> List[List[DeviceFrame]]:
         value = (value,)
     slots = []
     for v in value:
-        if isinstance(v, bool):
+        if isinstance(v, bool) or v is None or isinstance(v, list):   # deliver_by flag / trailing `by`
             continue
         if isinstance(v, PiecewiseFrame):
             slots.append(list(v.pieces))
@@ -634,6 +634,113 @@ def execute_groupby_operand(ctx, op):
 
 
 # ----------------------------------------------------------------------------------------------------
+# sort=True shuffle: PSRS sample / pivots / range split (reference: mars/dataframe/groupby/sort.py)
+# ----------------------------------------------------------------------------------------------------
+def execute_psrs_sample(ctx, op):
+    """DataFramePSRSGroupbySample.execute (sort.py:70-97): n regular samples of the key-sorted first partial
+    frame.  Only the sampled KEYS matter downstream (the pivot operand looks at `.index` alone), so the device
+    work is: argsort the partial's key tuples, gather the n sampled positions, n x n_keys values to the host."""
+    value = ctx[op.inputs[0].key]
+    a = _partials_of(value)[0]
+    n = int(op.n_partition)
+    rows = len(a)
+    names = a.index_names
+    if rows == 0:
+        keys_host = [np.empty(0, dtype=np.int64) for _ in a.index]
+    else:
+        perm = _kernels.argsort_keys(a.index)
+        if rows < n:   # the reference repeats the frame num times and re-sorts: every key num times, in order
+            num = n // rows + 1
+            total = rows * num
+            w = total * 1.0 / (n + 1)
+            slc = np.linspace(max(w - 1, 0), total - 1, num=n, endpoint=False).astype(int) // num
+        else:
+            w = rows * 1.0 / (n + 1)
+            slc = np.linspace(max(w - 1, 0), rows - 1, num=n, endpoint=False).astype(int)
+        pos = torch.from_numpy(slc.astype(np.int32)).to(perm.device)
+        take = _kernels.gather_rows([perm.to(torch.int64)], pos)[0].to(torch.int32)
+        keys_host = _to_host(_kernels.gather_rows(list(a.index), take))
+    if len(keys_host) == 1:
+        index = pd.Index(keys_host[0], name=names[0] if names else None)
+    else:
+        index = pd.MultiIndex.from_arrays(keys_host, names=names)
+    ctx[op.outputs[-1].key] = pd.DataFrame(index=index)
+
+
+def execute_concat_pivot(ctx, op):
+    """DataFrameGroupbyConcatPivot.execute (sort.py:44-67).  Host logic on p*p sample keys (metadata-sized):
+    same statements as the reference, on the key indexes of the samples."""
+    n_inputs = len(op.inputs)
+    inputs = [ctx[c.key] for c in op.inputs if len(ctx[c.key]) > 0]
+    a = pd.concat(inputs, axis=0).sort_index()
+    index = a.index.drop_duplicates()
+    p = len(inputs)
+    if len(index) < p:
+        num = p // len(index) + 1
+        index = index.append([index] * (num - 1))
+    index = index.sort_values()
+    slc = np.linspace(p - 1, len(index) - 1, num=n_inputs - 1, endpoint=False).astype(int)
+    ctx[op.outputs[-1].key] = index.values[slc]
+
+
+def _pivot_columns(pivots, n_keys: int, device) -> List[torch.Tensor]:
+    if n_keys == 1:
+        cols = [np.asarray(pivots, dtype=np.int64)]
+    else:
+        cols = [np.asarray([t[j] for t in pivots], dtype=np.int64) for j in range(n_keys)]
+    return [torch.from_numpy(np.ascontiguousarray(c)).to(device) for c in cols]
+
+
+def _execute_sort_shuffle_map(ctx, op):
+    """DataFrameGroupbySortShuffle._execute_map (sort.py:113-135): partition i = keys in (pivot[i-1], pivot[i]].
+    The reference slices key-sorted frames by label; here every partial row finds its partition by a binary
+    search over the pivots (mgb_range_partition_ids) and the rows are split stably -- the blocks hold the same
+    row sets (their order inside a block differs, the stage=agg operand sorts its output anyway)."""
+    value, pivots = ctx[op.inputs[0].key], ctx[op.inputs[1].key]
+    frames = _partials_of(value)
+    out = op.outputs[0]
+    R = int(op.n_partition)
+    base = frames[0]
+    for f in frames[1:]:
+        if not base.same_index(f):
+            raise NotImplementedError("sort shuffle expects the partial frames of a tuple to share their index")
+    cols = list(base.index)
+    for f in frames:
+        cols.extend(f.data)
+    nk = len(base.index)
+    if len(base) == 0:
+        outs, offsets = cols, [0] * (R + 1)
+    else:
+        pid = _kernels.range_partition_ids(base.index, _pivot_columns(pivots, nk, base.device))
+        outs, offsets = _kernels.partition_scatter(pid, R, cols)
+    for r in range(R):
+        a, b = offsets[r], offsets[r + 1]
+        keys_r = [t[a:b] for t in outs[:nk]]
+        pos = nk
+        block = []
+        for f in frames:
+            ncol = len(f.columns)
+            block.append(DeviceFrame(f.index_names, keys_r, f.columns, [t[a:b] for t in outs[pos:pos + ncol]], b - a))
+            pos += ncol
+        ctx[out.key, (r, 0)] = tuple(block)
+
+
+def _execute_sort_shuffle_reduce(ctx, op):
+    """DataFrameGroupbySortShuffle._execute_reduce (sort.py:137-151): slot-wise (virtual) concat + `by`"""
+    raw_inputs = [v for v in op.iter_mapper_data(ctx) if v is not None]
+    items = [[_as_device_frame(v, index_as_keys=True) for v in it if not isinstance(v, (bool, list))]
+             for it in raw_inputs]
+    ctx[op.outputs[0].key] = _concat_partial_tuples(items) + (getattr(op, "by", None),)
+
+
+def execute_sort_shuffle(ctx, op):
+    if _stage(op) == "map":
+        _execute_sort_shuffle_map(ctx, op)
+    else:
+        _execute_sort_shuffle_reduce(ctx, op)
+
+
+# ----------------------------------------------------------------------------------------------------
 # concat / data movement
 # ----------------------------------------------------------------------------------------------------
 def execute_concat(ctx, op):
@@ -668,3 +775,6 @@ def register_gpu_executors():
     md.DataFrameToGPU.register_executor(execute_to_gpu)
     md.DataFrameToCPU.register_executor(execute_to_cpu)
     md.DataFrameDataSource.register_executor(execute_datasource)
+    md.DataFramePSRSGroupbySample.register_executor(execute_psrs_sample)
+    md.DataFrameGroupbyConcatPivot.register_executor(execute_concat_pivot)
+    md.DataFrameGroupbySortShuffle.register_executor(execute_sort_shuffle)

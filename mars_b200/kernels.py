@@ -86,6 +86,20 @@ def partition_ids(keys: Sequence[torch.Tensor], n_partitions: int) -> torch.Tens
     return out
 
 
+def range_partition_ids(keys: Sequence[torch.Tensor], pivots: Sequence[torch.Tensor]) -> torch.Tensor:
+    """int32 range partition of every key tuple: number of pivot tuples strictly smaller than it
+    (mgb_range_partition_ids; PSRS shuffle of groupby(sort=True))."""
+    lib = _lib.load()
+    keys = [_req(k, f"key {i}", (torch.int64,)) for i, k in enumerate(keys)]
+    pivots = [_req(p, f"pivot {i}", (torch.int64,)) for i, p in enumerate(pivots)]
+    n = keys[0].numel()
+    out = torch.empty(n, dtype=torch.int32, device=keys[0].device)
+    check(lib.mgb_range_partition_ids(_ptrs(keys), len(keys), n, _ptrs(pivots), pivots[0].numel() if pivots else 0,
+                                      out.data_ptr(), _stream()))
+    _count(1 if n else 0)
+    return out
+
+
 def partition_scatter(pid: torch.Tensor, n_partitions: int, cols: Sequence[torch.Tensor]):
     """Stable split of rows into per-partition blocks.  Returns (out_cols, offsets) with offsets a host
     list of n_partitions+1 ints (one small device->host copy)."""

@@ -50,9 +50,14 @@ def register_on_mars(gpu_only: bool = True):
     from mars.dataframe.base.to_gpu import DataFrameToGPU
     from mars.dataframe.groupby.aggregation import DataFrameGroupByAgg
     from mars.dataframe.groupby.core import DataFrameGroupByOperand
+    from mars.dataframe.groupby.sort import (DataFrameGroupbyConcatPivot, DataFrameGroupbySortShuffle,
+                                             DataFramePSRSGroupbySample)
     from mars.dataframe.merge.concat import DataFrameConcat
 
     table = [
+        (DataFramePSRSGroupbySample, executors.execute_psrs_sample),
+        (DataFrameGroupbyConcatPivot, executors.execute_concat_pivot),
+        (DataFrameGroupbySortShuffle, executors.execute_sort_shuffle),
         (DataFrameGroupByAgg, executors.execute_groupby_agg),
         (DataFrameGroupByOperand, executors.execute_groupby_operand),
         (DataFrameConcat, executors.execute_concat),
@@ -69,9 +74,12 @@ def unregister_on_mars():
     from mars.dataframe.base.to_gpu import DataFrameToGPU
     from mars.dataframe.groupby.aggregation import DataFrameGroupByAgg
     from mars.dataframe.groupby.core import DataFrameGroupByOperand
+    from mars.dataframe.groupby.sort import (DataFrameGroupbyConcatPivot, DataFrameGroupbySortShuffle,
+                                             DataFramePSRSGroupbySample)
     from mars.dataframe.merge.concat import DataFrameConcat
 
-    for cls in (DataFrameGroupByAgg, DataFrameGroupByOperand, DataFrameConcat, DataFrameToGPU, DataFrameToCPU):
+    for cls in (DataFrameGroupByAgg, DataFrameGroupByOperand, DataFrameConcat, DataFrameToGPU, DataFrameToCPU,
+                DataFramePSRSGroupbySample, DataFrameGroupbyConcatPivot, DataFrameGroupbySortShuffle):
         cls.unregister_executor()
 
 

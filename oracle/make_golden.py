@@ -78,6 +78,11 @@ CASES = [
     ("cfg1_small_tree", "cfg1_small", ["key"], ["sum", "mean", "count"], 2000, "tree", True),
     ("cfg1_small_shuffle", "cfg1_small", ["key"], ["sum", "mean", "count"], 2000, "shuffle", False),
     ("high_card_shuffle", "high_card", ["key"], ["sum", "count"], 1000, "shuffle", False),
+    # sort=True + shuffle: PSRS range partition (DataFrameGroupbySortShuffle)
+    ("single_key_all6_sortshuffle", "single_key_all6", ["key"], ALL6, 250, "shuffle", True),
+    ("two_keys_minmaxvar_sortshuffle", "two_keys_minmaxvar", ["k1", "k2"], ["min", "max", "var"], 200, "shuffle", True),
+    ("high_card_sortshuffle", "high_card", ["key"], ["sum", "count"], 1000, "shuffle", True),
+    ("nan_extreme_sortshuffle", "nan_and_extreme_keys", ["key"], ALL6, 100, "shuffle", True),
 ]
 
 

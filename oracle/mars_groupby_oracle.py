@@ -20,7 +20,9 @@ What is restated (paths relative to the reference checkout, mars-project/mars):
   concat_partials               DataFrameConcat.execute tuple branch  (merge/concat.py:339-348)
   agg_combine                   DataFrameGroupByAgg._execute_combine  (groupby/aggregation.py:1130-1164)
   agg_agg                       DataFrameGroupByAgg._execute_agg      (groupby/aggregation.py:1166-1267)
-  run_groupby_agg               tile rules tree / shuffle (aggregation.py:428-471, 715-835) + the above
+  psrs_sample / concat_pivot /  DataFramePSRSGroupbySample, DataFrameGroupbyConcatPivot, DataFrameGroupbySortShuffle
+  sort_shuffle_map / _reduce    (groupby/sort.py:36-167): the range shuffle taken when sort=True
+  run_groupby_agg               tile rules tree / shuffle (aggregation.py:428-471, 563-702, 715-835) + the above
 
 Parity pinning: tests/test_oracle.py checks this module against (i) the known-answer hash vectors of
 pandas and (ii) tests/golden/*.npz -- outputs of the *unmodified reference* executed
@@ -168,7 +170,7 @@ def _columns_of_step(step: Step, func, value_cols: Sequence[Any]) -> List[Any]:
 # ----------------------------------------------------------------------------------------------------
 # stages
 # ----------------------------------------------------------------------------------------------------
-def agg_map(chunk: pd.DataFrame, by: List[Any], func, selection=None) -> Tuple[pd.DataFrame, ...]:
+def agg_map(chunk: pd.DataFrame, by: List[Any], func, selection=None, sort: bool = False) -> Tuple[pd.DataFrame, ...]:
     """_execute_map: tuple of K partial frames indexed by the group key(s).  As in the reference the map
     stage always runs with sort as given and as_index=True; `sort` does not matter for parity because the
     merge re-groups.  Columns no user function consumes are not materialised (the reference computes them
@@ -184,7 +186,7 @@ def agg_map(chunk: pd.DataFrame, by: List[Any], func, selection=None) -> Tuple[p
         if s.pre == "square":
             data = data.copy()
             data[cols] = data[cols].pow(2)
-        g = data.groupby(by, sort=False)[cols]
+        g = data.groupby(by, sort=sort)[cols]
         res = g.agg([s.map_func])
         res.columns = res.columns.droplevel(-1)
         out.append(res)
@@ -288,20 +290,90 @@ def _ordered_unique(xs):
 
 
 # ----------------------------------------------------------------------------------------------------
+# sort=True shuffle: parallel sorting by regular sampling (PSRS) over the partial frames
+# ----------------------------------------------------------------------------------------------------
+def psrs_sample(first_partial: pd.DataFrame, n_partition: int) -> pd.DataFrame:
+    """DataFramePSRSGroupbySample.execute (sort.py:70-97): n regular samples of the key-sorted first frame"""
+    a = first_partial
+    n = n_partition
+    if a.shape[0] < n:
+        num = n // a.shape[0] + 1
+        a = pd.concat([a] * num).sort_index()
+    w = a.shape[0] * 1.0 / (n + 1)
+    slc = np.linspace(max(w - 1, 0), a.shape[0] - 1, num=n, endpoint=False).astype(int)
+    return a.iloc[slc]
+
+
+def concat_pivot(samples: Sequence[pd.DataFrame]) -> np.ndarray:
+    """DataFrameGroupbyConcatPivot.execute (sort.py:44-67): p - 1 pivots out of the gathered samples"""
+    n_inputs = len(samples)
+    inputs = [x for x in samples if len(x) > 0]
+    a = pd.concat(inputs, axis=0).sort_index()
+    index = a.index.drop_duplicates()
+    p = len(inputs)
+    if len(index) < p:
+        num = p // len(index) + 1
+        index = index.append([index] * (num - 1))
+    index = index.sort_values()
+    values = index.values
+    slc = np.linspace(p - 1, len(index) - 1, num=n_inputs - 1, endpoint=False).astype(int)
+    return values[slc]
+
+
+def sort_shuffle_map(partials: Tuple[pd.DataFrame, ...], pivots: np.ndarray, n_partition: int) -> Dict[int, Tuple]:
+    """DataFrameGroupbySortShuffle._execute_map (sort.py:113-135): partition i holds the keys in
+    (pivot[i-1], pivot[i]] -- label slices of the key-sorted frames, lower pivot dropped"""
+    def part(i, df):
+        if i == 0:
+            return df.loc[: pivots[i]]
+        if i == n_partition - 1:
+            return df.loc[pivots[i - 1]:].drop(index=pivots[i - 1], errors="ignore")
+        return df.loc[pivots[i - 1]: pivots[i]].drop(index=pivots[i - 1], errors="ignore")
+
+    return {i: tuple(part(i, x) for x in partials) for i in range(n_partition)}
+
+
+def sort_shuffle_reduce(blocks: Sequence[Tuple]) -> Tuple[pd.DataFrame, ...]:
+    """DataFrameGroupbySortShuffle._execute_reduce (sort.py:137-151), without the trailing `by`"""
+    return tuple(pd.concat([b[k] for b in blocks], axis=0) for k in range(len(blocks[0])))
+
+
+def range_partition_ids(key_cols: Sequence[np.ndarray], pivots: np.ndarray) -> np.ndarray:
+    """partition of every key tuple under the rule above: number of pivots strictly smaller than the key"""
+    if len(key_cols) == 1:
+        return np.searchsorted(np.asarray(pivots, dtype=np.int64), np.asarray(key_cols[0]), side="left")
+    piv = [tuple(int(v) for v in t) for t in pivots]
+    keys = list(zip(*[np.asarray(c).tolist() for c in key_cols]))
+    import bisect
+
+    return np.array([bisect.bisect_left(piv, k) for k in keys], dtype=np.int64)
+
+
+# ----------------------------------------------------------------------------------------------------
 # whole path
 # ----------------------------------------------------------------------------------------------------
 def run_groupby_agg(raw: pd.DataFrame, by, func, chunk_size: int, method: str = "tree", sort: bool = True,
                     combine_size: int = 4, selection=None, record: Optional[dict] = None) -> pd.DataFrame:
     """md.DataFrame(raw, chunk_size).groupby(by, sort=sort)[selection].agg(func, method=method) executed stage
-    by stage.  method='shuffle' requires sort=False (hash partition; sort=True range-partitions)."""
+    by stage.  method='shuffle': hash partition for sort=False, PSRS range partition for sort=True."""
     by = [by] if not isinstance(by, (list, tuple)) else list(by)
     chunks = [raw.iloc[i:i + chunk_size] for i in range(0, max(len(raw), 1), chunk_size)]
-    maps = [agg_map(c, by, func, selection) for c in chunks]
+    maps = [agg_map(c, by, func, selection, sort=sort) for c in chunks]
     if record is not None:
         record["map"] = maps
+    if method == "shuffle" and sort and len(chunks) > 1:
+        R = len(maps)
+        samples = [psrs_sample(m[0], R) for m in maps]
+        pivots = concat_pivot(samples)
+        blocks = [sort_shuffle_map(m, pivots, R) for m in maps]
+        if record is not None:
+            record["pivots"] = pivots
+            record["blocks"] = blocks
+        outs = [agg_agg(sort_shuffle_reduce([blocks[i][r] for i in range(R)]), func, sort=True) for r in range(R)]
+        if record is not None:
+            record["chunk_results"] = outs
+        return pd.concat(outs, axis=0)
     if method == "shuffle":
-        if sort and len(chunks) > 1:
-            raise NotImplementedError("sort=True + shuffle uses PSRS range partitioning")
         R = len(maps)
         blocks = [shuffle_map(m, R, (i, 0)) for i, m in enumerate(maps)]
         if record is not None:

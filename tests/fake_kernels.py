@@ -35,6 +35,13 @@ def partition_ids(keys, n_partitions):
     return torch.from_numpy(orc.partition_ids([_np(k) for k in keys], n_partitions).astype(np.int32))
 
 
+def range_partition_ids(keys, pivots):
+    calls.append("range_partition_ids")
+    piv = list(zip(*[_np(p).tolist() for p in pivots])) if len(pivots) > 1 else _np(pivots[0])
+    pid = orc.range_partition_ids([_np(k) for k in keys], piv)
+    return torch.from_numpy(np.asarray(pid).astype(np.int32))
+
+
 def partition_scatter(pid, n_partitions, cols):
     calls.append("partition_scatter")
     p = _np(pid)

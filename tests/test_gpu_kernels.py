@@ -397,3 +397,22 @@ def test_aggregate_with_distinct_keys_hint_skips_preaggregation(K, plain):
             np.testing.assert_array_equal(got, exp.astype(got.dtype))
         else:
             np.testing.assert_allclose(got, exp, rtol=1e-9, atol=0, equal_nan=True)
+
+
+@pytest.mark.parametrize("n_keys", [1, 2])
+def test_range_partition_ids_match_oracle(K, n_keys):
+    rng = np.random.default_rng(41 + n_keys)
+    n = 100_000
+    cols = [rng.integers(-1000, 1000, n, dtype=np.int64) for _ in range(n_keys)]
+    cols[0][:4] = [-2 ** 63, 2 ** 63 - 1, 0, -1]
+    if n_keys == 1:
+        pivots = np.array([-2 ** 63, -500, -500, 0, 17, 999, 2 ** 63 - 1], dtype=np.int64)
+        pcols = [pivots]
+    else:
+        tuples = sorted({(int(a), int(b)) for a, b in zip(rng.integers(-1000, 1000, 9), rng.integers(-1000, 1000, 9))})
+        tuples.insert(3, tuples[3])                     # a duplicated pivot: an empty partition
+        pivots = np.empty(len(tuples), dtype=object)
+        pivots[:] = tuples
+        pcols = [np.array([t[j] for t in tuples], dtype=np.int64) for j in range(2)]
+    got = K.range_partition_ids([dev(c) for c in cols], [dev(p) for p in pcols]).cpu().numpy()
+    np.testing.assert_array_equal(got, orc.range_partition_ids(cols, pivots))

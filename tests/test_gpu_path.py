@@ -97,6 +97,9 @@ CASES = [
     (60_000, ("key", 40_000), 1, ["sum", "count"], 7_500, "auto", False),
     (40_000, ("two", 900), 8, ["min", "max", "var"], 5_000, "shuffle", False),
     (40_000, ("zipf", 0), 1, ["mean", "count"], 5_000, "shuffle", False),
+    (60_000, ("key", 40_000), 1, ["sum", "count"], 7_500, "shuffle", True),      # PSRS range shuffle
+    (40_000, ("two", 900), 3, ["min", "max", "var"], 5_000, "shuffle", True),
+    (20_000, ("key", 3), 2, ["sum", "mean"], 2_500, "shuffle", True),            # fewer keys than partitions
     (10_000, ("key", 50), 2, "sum", 10_000, "tree", True),       # single chunk, single function
     (999, ("key", 7), 3, ["var"], 100, "tree", True),             # ragged last chunk
 ]
@@ -128,12 +131,19 @@ def test_matches_oracle_on_seeded_inputs(md, case):
     omethod = method
     if method == "auto":
         omethod = "shuffle" if len(r.data.chunks) > 1 else "tree"
-    exp = orc.run_groupby_agg(raw, by, func, chunk, method="tree" if (omethod == "shuffle" and sort) else omethod,
-                              sort=sort)
+    exp = orc.run_groupby_agg(raw, by, func, chunk, method=omethod, sort=sort)
     assert_frames_match(got, exp, sort_index=not sort)
     ops = set(sess.executed_ops)
-    if omethod == "shuffle":
+    if omethod == "shuffle" and not sort:
         assert "DataFrameGroupByOperand:map" in ops and "DataFrameGroupByOperand:reduce" in ops
+    if omethod == "shuffle" and sort:
+        assert "DataFrameGroupbySortShuffle:map" in ops and "DataFrameGroupbySortShuffle:reduce" in ops
+        # chunk i of the result holds exactly the keys of range partition i
+        rec = {}
+        orc.run_groupby_agg(raw, by, func, chunk, method="shuffle", sort=True, record=rec)
+        chunks = sorted(r.data.chunks, key=lambda c: c.index)
+        for c, e in zip(chunks, rec["chunk_results"]):
+            assert_frames_match(sess._results[c.key], e, sort_index=False)
     assert "DataFrameGroupByAgg:map" in ops and "DataFrameGroupByAgg:agg" in ops
 
 

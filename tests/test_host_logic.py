@@ -69,11 +69,23 @@ def test_hash_shuffle_tiling_shape(md):
         assert all(m.op.shuffle_size == 4 for m in red.inputs[0].op.inputs)     # R == number of mapper chunks
 
 
-def test_sorted_shuffle_is_declared_out_of_scope(md):
+def test_sort_shuffle_tiling_shape(md):
+    """sort=True + shuffle = PSRS range shuffle: sample per map chunk -> one pivot chunk -> sort-shuffle map
+    (reads the pivots) -> proxy -> sort-shuffle reduce -> agg (reference test_groupby.py:97-122)"""
     raw = pd.DataFrame({"key": np.arange(100) % 7, "v": np.arange(100.0)})
     r = md.DataFrame(raw, chunk_size=25).groupby("key", sort=True).agg(["sum"], method="shuffle")
-    with pytest.raises(NotImplementedError, match="PSRS"):
-        tile(md, r.data)
+    t = tile(md, r.data)
+    names = op_names(t.chunks)
+    assert len(t.chunks) == 4
+    assert names.count("DataFramePSRSGroupbySample:None") == 4
+    assert names.count("DataFrameGroupbyConcatPivot:None") == 1
+    assert names.count("DataFrameGroupbySortShuffle:map") == 4 and names.count("DataFrameGroupbySortShuffle:reduce") == 4
+    assert "DataFrameGroupByOperand:map" not in names
+    for c in t.chunks:
+        red = c.op.inputs[0].op
+        assert red.n_reducers == 4 and red.by == ["key"]
+        for m in red.inputs[0].op.inputs:
+            assert m.op.n_partition == 4 and type(m.op.inputs[1].op).__name__ == "DataFrameGroupbyConcatPivot"
 
 
 def test_decomposition_matches_reference_compiler():

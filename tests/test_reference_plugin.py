@@ -43,6 +43,8 @@ CASES = [
     ("key", ["sum", "mean", "count", "min", "max", "var"], "tree", True),
     ("key", ["sum", "mean", "count", "min", "max", "var"], "shuffle", False),
     (["k1", "k2"], ["min", "max", "var"], "shuffle", False),
+    ("key", ["sum", "mean", "count", "min", "max", "var"], "shuffle", True),       # PSRS range shuffle
+    (["k1", "k2"], ["sum", "count"], "shuffle", True),
     (["k1", "k2"], {"v0": ["sum", "mean"], "v1": ["count"]}, "tree", True),
     ("key", "sum", "tree", True),
 ]
@@ -66,8 +68,12 @@ def test_real_reference_graph_runs_on_our_executors(ref, by, func, method, sort)
     assert_frames_match(got.sort_index(), exp, sort_index=False)
     ops = {(r["op"], r["stage"]) for r in out["records"]}
     assert ("DataFrameGroupByAgg", "map") in ops and ("DataFrameGroupByAgg", "agg") in ops
-    if method == "shuffle":
+    if method == "shuffle" and not sort:
         assert ("DataFrameGroupByOperand", "map") in ops and ("DataFrameGroupByOperand", "reduce") in ops
+    if method == "shuffle" and sort:
+        assert ("DataFrameGroupbySortShuffle", "map") in ops and ("DataFrameGroupbySortShuffle", "reduce") in ops
+        assert "range_partition_ids" in fake_kernels.calls
+        assert got.index.is_monotonic_increasing          # globally sorted without a final sort_index
 
 
 def test_unsupported_inputs_fall_back_to_the_reference_path(ref):
