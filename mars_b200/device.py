@@ -17,8 +17,32 @@ import pandas as pd
 import torch
 
 
+h2d_bytes = 0   # bytes copied host -> device by this module (bench.py reports them per step)
+
+
+class HostColumn:
+    """A column of a chunk that is still in host memory: uploaded by DeviceFrame.col(i) on first use.  A column
+    no kernel reads (e.g. an int64 column that is only counted) never crosses PCIe."""
+    __slots__ = ("array",)
+
+    def __init__(self, array: np.ndarray):
+        self.array = array
+
+    @property
+    def dtype(self):
+        return torch.float64 if self.array.dtype == np.float64 else torch.int64
+
+    def numel(self):
+        return int(self.array.shape[0])
+
+    def element_size(self):
+        return 8
+
+
 def _to_device(arr: np.ndarray, device) -> torch.Tensor:
     """H2D copy of one 8-byte column (pandas hands out read-only views; torch wants writable memory)."""
+    global h2d_bytes
+    h2d_bytes += arr.size * arr.itemsize
     arr = np.ascontiguousarray(arr)
     if not arr.flags.writeable:
         # pandas hands out read-only views of the column; the copy below only reads, so re-flag the view
@@ -85,7 +109,7 @@ class Pending:
 
 
 class DeviceFrame:
-    __slots__ = ("index_names", "_index", "columns", "_data", "_n", "_pending", "_slot", "__weakref__")
+    __slots__ = ("index_names", "_index", "columns", "_data", "_n", "_pending", "_slot", "_home", "__weakref__")
 
     def __init__(self, index_names: Sequence[Any], index: Optional[Sequence[torch.Tensor]],
                  columns: Sequence[Any], data: Sequence[torch.Tensor], n_rows: Optional[int] = None,
@@ -96,6 +120,7 @@ class DeviceFrame:
         self._data = list(data)
         self._pending = pending
         self._slot = slot
+        self._home = None            # device of lazily uploaded columns (set by from_pandas(lazy=True))
         if pending is not None:
             pending.attach(self)
             self._n = None
@@ -143,7 +168,24 @@ class DeviceFrame:
     @property
     def data(self):
         self._resolve()
+        if self._home is not None:
+            for i, t in enumerate(self._data):
+                if isinstance(t, HostColumn):
+                    self._data[i] = _to_device(t.array, self._home)
+            self._home = None
         return self._data
+
+    def col(self, i: int) -> torch.Tensor:
+        """data column i on the device (uploads it now if it is still in host memory)"""
+        t = self._data[i]
+        if isinstance(t, HostColumn):
+            t = self._data[i] = _to_device(t.array, self._home)
+        elif self._pending is not None:
+            return self.data[i]
+        return t
+
+    def col_dtype(self, i: int):
+        return self._data[i].dtype
 
     @data.setter
     def data(self, value):
@@ -187,6 +229,8 @@ class DeviceFrame:
 
     @property
     def device(self):
+        if self._home is not None:
+            return self._home
         ts = self._data or self._index or []
         return ts[0].device if ts else torch.device("cpu")
 
@@ -211,10 +255,11 @@ class DeviceFrame:
 
     # ---- host <-> device (reference: DataFrameToGPU / DataFrameToCPU, dataframe/base/to_gpu.py:28-35)
     @classmethod
-    def from_pandas(cls, df: pd.DataFrame, device="cuda", index_as_keys: bool = False) -> "DeviceFrame":
+    def from_pandas(cls, df: pd.DataFrame, device="cuda", index_as_keys: bool = False, lazy: bool = False) -> "DeviceFrame":
         """H2D copy of a pandas chunk.  Numeric columns only: float64, int64 (narrower ints / bool are widened
         to int64, which is what pandas' own group_sum does); anything else raises NotImplementedError so
-        that the caller can fall back to the reference executor."""
+        that the caller can fall back to the reference executor.  lazy: data columns stay on the host until a
+        consumer asks for them (``col(i)`` / ``data``)."""
         cols, data = [], []
         for name in df.columns:
             s = df[name]
@@ -226,7 +271,7 @@ class DeviceFrame:
             else:
                 raise NotImplementedError(f"column {name!r} has dtype {arr.dtype}: the GPU groupby path handles "
                                           f"float64 and int64 columns")
-            data.append(_to_device(arr, device))
+            data.append(HostColumn(arr) if lazy else _to_device(arr, device))
             cols.append(name)
         index = None
         names: List[Any] = []
@@ -241,7 +286,10 @@ class DeviceFrame:
                 if lv.dtype != np.int64:
                     raise NotImplementedError(f"group key dtype {lv.dtype}: int64 keys only")
                 index.append(_to_device(lv, device))
-        return cls(names, index, cols, data, len(df))
+        out = cls(names, index, cols, data, len(df))
+        if lazy:
+            out._home = torch.device(device) if not isinstance(device, torch.device) else device
+        return out
 
     def to_pandas(self) -> pd.DataFrame:
         data = {i: t.cpu().numpy() for i, t in enumerate(self.data)}

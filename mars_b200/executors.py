@@ -40,6 +40,7 @@ _dense_rejected = set()
 _distinct_shapes = set()   # shapes whose chunks spilled most rows: skip the shared-memory pre-aggregation
 # MGB_EAGER=1 disables the speculative asynchronous chain (every operand then waits for its result size)
 _ASYNC = os.environ.get("MGB_EAGER", "0") in ("", "0")
+_LAZY_H2D = os.environ.get("MGB_EAGER_H2D", "0") in ("", "0")
 
 
 def _stage(op) -> Optional[str]:
@@ -51,11 +52,11 @@ def _device() -> torch.device:
     return torch.device("cuda", torch.cuda.current_device())
 
 
-def _as_device_frame(value, index_as_keys=False) -> DeviceFrame:
+def _as_device_frame(value, index_as_keys=False, lazy=False) -> DeviceFrame:
     if isinstance(value, DeviceFrame):
         return value
     if isinstance(value, pd.DataFrame):
-        return DeviceFrame.from_pandas(value, device=_device(), index_as_keys=index_as_keys)
+        return DeviceFrame.from_pandas(value, device=_device(), index_as_keys=index_as_keys, lazy=lazy)
     raise NotImplementedError(f"cannot move {type(value).__name__} to the GPU groupby path")
 
 
@@ -173,6 +174,14 @@ class _MapPlan:
     """Everything of a stage=map call that only depends on the operand's functions and the chunk schema."""
     __slots__ = ("by", "key_pos", "used", "val_pos", "accs", "slots", "shape_key")
 
+    def count_only_int(self, frame) -> Tuple[int, ...]:
+        """positions (in `used`) of int64 value columns whose only accumulators are COUNTs"""
+        out = []
+        for j, i in enumerate(self.val_pos):
+            if frame.col_dtype(i) == torch.int64 and all(op == K.COUNT for c, op in self.accs if c == j):
+                out.append(j)
+        return tuple(out)
+
 
 _map_plans: Dict[Any, _MapPlan] = {}
 
@@ -249,29 +258,37 @@ def _execute_agg_map(ctx, op):
     if frame.index is not None:
         raise NotImplementedError("map stage expects a raw chunk (RangeIndex)")
     plan = _map_plan(op, frame)
-    data = frame.data
-    keys = [data[i] for i in plan.key_pos]
-    for b, k in zip(plan.by, keys):
-        if k.dtype != torch.int64:
-            raise NotImplementedError(f"group key {b!r} has dtype {k.dtype}: int64 keys only")
-    vals = [data[i] for i in plan.val_pos]
+    for b, i in zip(plan.by, plan.key_pos):
+        if frame.col_dtype(i) != torch.int64:
+            raise NotImplementedError(f"group key {b!r} has dtype {frame.col_dtype(i)}: int64 keys only")
+    keys = [frame.col(i) for i in plan.key_pos]
+    dense_ok = plan.shape_key not in _dense_rejected
+    # the dense kernel does not read int64 columns that are only counted (count == rows of the group): those
+    # stay where they are (possibly in host memory) unless the general path turns out to be needed
+    skip = plan.count_only_int(frame) if dense_ok and _ASYNC and hasattr(_kernels, "preagg_dense_async") else ()
+    vals = [None if j in skip else frame.col(i) for j, i in enumerate(plan.val_pos)]
     # low-cardinality chunks take the one-launch dense path, enqueued WITHOUT waiting for its result size
     # (the frames carry a Pending count).  A shape that turned out not to fit is remembered, so the following
     # chunks of the same computation go straight to the general hash-table path.
     rec = getattr(op, "size_recorder_name", None)
     frames = None
-    if plan.shape_key not in _dense_rejected:
+
+    def all_vals():
+        return [frame.col(i) for i in plan.val_pos]
+
+    if dense_ok:
         if _ASYNC and hasattr(_kernels, "preagg_dense_async"):
-            res = _kernels.preagg_dense_async(keys, vals, plan.accs, checked=True)
+            dts = [K.F64 if frame.col_dtype(i) == torch.float64 else K.I64 for i in plan.val_pos]
+            res = _kernels.preagg_dense_async(keys, vals, plan.accs, checked=True, val_dtypes=dts)
             if res is None:
                 _dense_rejected.add(plan.shape_key)
             else:
                 bi, bf, fc = res
                 accs = list(plan.accs)
 
-                def replay(keys=keys, vals=vals, accs=accs, shape_key=plan.shape_key):
+                def replay(keys=keys, accs=accs, shape_key=plan.shape_key):
                     _dense_rejected.add(shape_key)
-                    k, a, _ = _kernels.groupby_aggregate(keys, vals, accs, sort=False)
+                    k, a, _ = _kernels.groupby_aggregate(keys, all_vals(), accs, sort=False)
                     return k, a
 
                 pend = Pending(bi, fc.n_int, bi.shape[1], replay)
@@ -279,6 +296,7 @@ def _execute_agg_map(ctx, op):
                 frames = [DeviceFrame(plan.by, ck, cols, ca[a0:a1], pending=pend, slot=(a0, a1))
                           for cols, a0, a1 in plan.slots]
         elif hasattr(_kernels, "preagg_dense"):
+            vals = all_vals()
             res = _kernels.preagg_dense(keys, vals, plan.accs)
             if res is None:
                 _dense_rejected.add(plan.shape_key)
@@ -287,6 +305,7 @@ def _execute_agg_map(ctx, op):
                 n_out = int(out_keys[0].numel())
                 frames = [DeviceFrame(plan.by, out_keys, cols, out_accs[a0:a1], n_out) for cols, a0, a1 in plan.slots]
     if frames is None:
+        vals = all_vals()
         if plan.shape_key in _distinct_shapes:
             out_keys, out_accs, stats = _kernels.groupby_aggregate(keys, vals, list(plan.accs), sort=False,
                                                                    expect_distinct=True)
@@ -753,7 +772,9 @@ def execute_concat(ctx, op):
 
 
 def execute_to_gpu(ctx, op):
-    ctx[op.outputs[0].key] = _as_device_frame(ctx[op.inputs[0].key])
+    """DataFrameToGPU.execute (base/to_gpu.py:28-35).  The columns are uploaded when their first consumer asks
+    for them, so a column no kernel reads (an int64 column that is only counted) never crosses PCIe."""
+    ctx[op.outputs[0].key] = _as_device_frame(ctx[op.inputs[0].key], lazy=_LAZY_H2D)
 
 
 def execute_to_cpu(ctx, op):

@@ -7,7 +7,7 @@ the CPU: a non-CUDA tensor raises ``MarsGBError`` (no fallback path exists).
 from __future__ import annotations
 
 import ctypes as C
-from typing import List, Sequence, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 import torch
 
@@ -377,8 +377,8 @@ def merge_small(pieces_keys: Sequence[Sequence[torch.Tensor]], pieces_accs: Sequ
     return fc.views(bi, bf, G)
 
 
-def preagg_dense_async(keys: Sequence[torch.Tensor], vals: Sequence[torch.Tensor], accs: Sequence[Tuple[int, int]],
-                       checked: bool = False):
+def preagg_dense_async(keys: Sequence[torch.Tensor], vals: Sequence[Optional[torch.Tensor]],
+                       accs: Sequence[Tuple[int, int]], checked: bool = False, val_dtypes=None):
     """Like ``preagg_dense`` but without host synchronisation (mgb_preagg_dense_async): returns
     (int block, float block, fast-call) -- columns at capacity ``dense_capacity()``, the group count (or -1) in
     the device int64 at ``fc.count_ptr(bi)``.  None when the shape can never be dense (too many columns)."""
@@ -392,9 +392,13 @@ def preagg_dense_async(keys: Sequence[torch.Tensor], vals: Sequence[torch.Tensor
             if k.dtype != torch.int64:
                 raise MarsGBError(3, f"key {i}: dtype {k.dtype} not supported (int64 keys)")
         for v in vals:
-            _check_col(v, "value column")
+            if v is not None:
+                _check_col(v, "value column")
     n = keys[0].numel()
-    fc = _fast(len(keys), [F64 if v.dtype == torch.float64 else I64 for v in vals], accs)
+    # a value column may be None: an int64 column that is only counted is never read by the kernel (its dtype
+    # then comes from val_dtypes); passing a null pointer for any other column is rejected by the library
+    dts = list(val_dtypes) if val_dtypes is not None else [F64 if v.dtype == torch.float64 else I64 for v in vals]
+    fc = _fast(len(keys), dts, accs)
     if _dense_cap is None:
         c = C.c_int64()
         check(lib.mgb_dense_capacity(C.byref(c)))
@@ -402,7 +406,7 @@ def preagg_dense_async(keys: Sequence[torch.Tensor], vals: Sequence[torch.Tensor
     for j, k in enumerate(keys):
         fc.kp[j] = k.data_ptr()
     for j, v in enumerate(vals):
-        fc.vp[j] = v.data_ptr()
+        fc.vp[j] = v.data_ptr() if v is not None else None
     bi, bf = fc.alloc(_dense_cap, keys[0].device)
     check(lib.mgb_preagg_dense_async(C.byref(fc.spec), fc.kp, fc.vp, n, fc.okp, fc.oap, _dense_cap, fc.count_ptr(bi),
                                      _stream()))

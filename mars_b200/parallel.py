@@ -56,6 +56,18 @@ class NcclTransport:
         self._comm = C.c_void_p()
         check(self._lib.mgb_comm_init(C.byref(self._comm), uid, rank, world))
         self.bytes_sent = 0
+        self.timed = False          # set True to bracket every exchange with CUDA events (bandwidth reports)
+        self._events = []           # (start, end, bytes sent to peers)
+
+    def exchange_stats(self):
+        """(total device milliseconds, bytes sent to peers) over the timed exchanges so far"""
+        ms = 0.0
+        nbytes = 0
+        for e0, e1, b in self._events:
+            e1.synchronize()
+            ms += e0.elapsed_time(e1)
+            nbytes += b
+        return ms, nbytes
 
     def alltoallv(self, send_cols: Sequence[torch.Tensor], send_off: Sequence[int], recv_off: Sequence[int]):
         dev = torch.device("cuda", torch.cuda.current_device())
@@ -68,10 +80,21 @@ class NcclTransport:
         ro = (C.c_int64 * (self.world + 1))(*recv_off)
         sp = _lib.ptr_array([c.data_ptr() for c in send_cols])
         rp = _lib.ptr_array([c.data_ptr() for c in recv_cols])
+        own = send_off[self.rank + 1] - send_off[self.rank]
+        nbytes = 8 * len(send_cols) * (send_off[-1] - own)
+        if self.timed:
+            # bandwidth measurement: line the ranks up first, otherwise the bracket includes waiting for a
+            # peer that is still packing its blocks
+            torch.cuda.synchronize()
+            dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         check(self._lib.mgb_comm_alltoallv(self._comm, sp, so, rp, ro, len(send_cols),
                                            torch.cuda.current_stream().cuda_stream))
-        own = send_off[self.rank + 1] - send_off[self.rank]
-        self.bytes_sent += 8 * len(send_cols) * (send_off[-1] - own)
+        if self.timed:
+            e1.record()
+            self._events.append((e0, e1, nbytes))
+        self.bytes_sent += nbytes
         return recv_cols
 
     def close(self):
