@@ -122,6 +122,7 @@ extern "C" int mgb_preagg_dense_async(const mgb_agg_spec* spec, const int64_t* c
   for (int kind = 1; kind <= 4; ++kind) {
     *kind_acc_off[kind] = off;
     p.kind_off[kind] = w;
+    if (p.op_mask[kind_op[kind]]) p.word_kind[w] = kind;
     if (p.op_mask[kind_op[kind]]) {
       off += 64 * ncol;
       ++w;
@@ -130,7 +131,7 @@ extern "C" int mgb_preagg_dense_async(const mgb_agg_spec* spec, const int64_t* c
   p.off_nan = off;
   p.stride_g = p.off_nan + 32;   // a multiple of 32 words: the bank of a lane-private slot depends on the lane only
   p.wpc = w;
-  const size_t fixed = (size_t)(MGB_MAX_KEYS * DN_TAB + MGB_MAX_KEYS * DN_MAX_GC) * 8 + DN_TAB * 4 + 64;
+  const size_t fixed = (size_t)(MGB_MAX_KEYS * DN_TAB + MGB_MAX_KEYS * DN_MAX_GC) * 8 + DN_TAB * 4 + 128;
   // 16 warps per CTA when that still leaves 8 group slots (and registers for the double-buffered rows),
   // otherwise 8 warps with twice the rows per thread
   int threads = 512;
@@ -179,7 +180,8 @@ extern "C" int mgb_preagg_dense_async(const mgb_agg_spec* spec, const int64_t* c
   const size_t acc_smem = (size_t)n_warps * GC * p.stride_g * 4 + fixed;
   size_t smem = acc_smem < 112 * 1024 ? 112 * 1024 : acc_smem;   // >= 112 KB for the cross-CTA merge tables
   // last-CTA merge: key table + 5 int arrays of at most grid * GC (+2) entries
-  const size_t merge_smem = (size_t)MGB_MAX_KEYS * SM_TAB * 8 + SM_TAB * 4 + 32 + 5 * ((size_t)grid * GC + 4) * 4;
+  const size_t merge_smem = (size_t)MGB_MAX_KEYS * SM_TAB * 8 + SM_TAB * 4 + 32 + 5 * ((size_t)grid * GC + 4) * 4 +
+                            (size_t)DN_MAX_GC * (p.stg_w + MGB_MAX_KEYS) * 8;
   MGB_REQUIRE(acc_smem <= smem && merge_smem <= smem, MGB_ERR_OVERFLOW, "dense path shared-memory plan does not fit");
   static const char* env_dbg = getenv("MGB_DENSE_DEBUG");   // experiments only: per-CTA phase timestamps
   long long* dbg = nullptr;
@@ -214,7 +216,7 @@ extern "C" int mgb_preagg_dense_async(const mgb_agg_spec* spec, const int64_t* c
       }
     fprintf(stderr, "dense phases (ns since first CTA start): start %lld..%lld | main loop done %lld..%lld | staged+ticket %lld..%lld | last CTA end %lld\n",
             mn[0], mx[0], mn[1], mx[1], mn[2], mx[2], mx[3]);
-    fprintf(stderr, "  last CTA: enter %lld | table init %lld | items %lld | pass1 %lld | staged copy %lld\n", h[4 * grid] - t0,
+    fprintf(stderr, "  last CTA: enter %lld | phase a %lld | phase b %lld | phase c %lld | phase d %lld\n", h[4 * grid] - t0,
             h[4 * grid + 1] - t0, h[4 * grid + 2] - t0, h[4 * grid + 3] - t0, h[4 * grid + 4] - t0);
     free(h);
     cudaFree(dbg);

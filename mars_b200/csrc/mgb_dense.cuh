@@ -126,6 +126,7 @@ struct DenseParams {
   int stg_w;                // words per staged row
   int wpc;                  // words per column in a staged row
   int kind_off[5];          // word of kind k (1 sum, 2 sumsq, 3 min, 4 max) inside a column's group; 0 is the NaN count
+  int word_kind[5];         // inverse: kind stored at word k of a column's group (word 0: NaN count)
   int* cta_ng;              // per CTA: number of groups staged
   unsigned int* ticket;
   int* fail;
@@ -443,25 +444,44 @@ __global__ void __launch_bounds__(THREADS, 1) k_preagg_dense(const DenseParams p
   if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 4 + 1] = dense_now();
   const bool cta_failed = *s_fail != 0;
 
-  // ---- CTA reduction -> staging rows (one per group of this CTA), decoded values
+  // ---- CTA reduction -> staging rows (one per group of this CTA), decoded values.  Rows are staged in key
+  //      order, so CTAs that saw the same key set (the common case) stage the same key at the same position.
   const int ng = cta_failed ? 0 : *(volatile int*)s_ng;
   const int W = p.stg_w, WPC = p.wpc;
+  // staging is transposed: the values of one (row, word) over all CTAs are contiguous, so that the last CTA
+  // reads them as full sectors
+#define STG(cta, r, w) (p.stg + ((size_t)((r) * W + (w)) * gridDim.x + (cta)))
+  int* s_rank = s_int + 8;   // [MAX_GC]
+  if (threadIdx.x < ng) {
+    uint64_t k[NK];
+#pragma unroll
+    for (int j = 0; j < NK; ++j) k[j] = gkeys[j * DN_MAX_GC + threadIdx.x];
+    int r = 0;
+    for (int q = 0; q < ng; ++q) {
+      uint64_t o[NK];
+#pragma unroll
+      for (int j = 0; j < NK; ++j) o[j] = gkeys[j * DN_MAX_GC + q];
+      r += key_less<NK>(o, k) ? 1 : 0;
+    }
+    s_rank[threadIdx.x] = r;
+  }
+  __syncthreads();
   constexpr int SLOTS = 1 + NV * 5;
   for (int qq = warp; qq < ng * SLOTS; qq += DN_WARPS) {
     const int g = qq / SLOTS, s = qq - g * SLOTS;
-    uint64_t* row = p.stg + ((size_t)blockIdx.x * GC + g) * W;
+    const int sr = s_rank[g];
     if (s == 0) {   // rows
       uint32_t v = 0;
       for (int w = 0; w < DN_WARPS; ++w) v += acc[((size_t)w * GC + g) * p.stride_g + lane];
       v = __reduce_add_sync(0xffffffffu, v);
-      if (lane == 0) row[NK] = v;
+      if (lane == 0) *STG(blockIdx.x, sr, NK) = v;
       continue;
     }
     const int c = (s - 1) / 5, kind = (s - 1) % 5;   // kind: 0 nan, 1 sum, 2 sumsq, 3 min, 4 max
     if (kind == 0) {
       uint32_t v = lane < DN_WARPS ? acc[((size_t)lane * GC + g) * p.stride_g + o_nan + c] : 0u;
       v = __reduce_add_sync(0xffffffffu, v);
-      if (lane == 0) row[NK + 1 + c * WPC] = v;
+      if (lane == 0) *STG(blockIdx.x, sr, NK + 1 + c * WPC) = v;
       continue;
     }
     if (!ALLOPS && kind > 1) continue;
@@ -478,11 +498,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_preagg_dense(const DenseParams p
     }
     uint64_t v = dense_combine(kind, f, v0, v1);
     for (int o = 16; o > 0; o >>= 1) v = dense_combine(kind, f, v, __shfl_xor_sync(0xffffffffu, v, o));
-    if (lane == 0) row[NK + 1 + c * WPC + p.kind_off[kind]] = v;
+    if (lane == 0) *STG(blockIdx.x, sr, NK + 1 + c * WPC + p.kind_off[kind]) = v;
   }
   for (int qq = threadIdx.x; qq < ng * NK; qq += DN_THREADS) {
     const int g = qq / NK, j = qq - g * NK;
-    p.stg[((size_t)blockIdx.x * GC + g) * W + j] = gkeys[j * DN_MAX_GC + g];
+    *STG(blockIdx.x, s_rank[g], j) = gkeys[j * DN_MAX_GC + g];
   }
   if (threadIdx.x == 0) p.cta_ng[blockIdx.x] = ng;
   __threadfence();
@@ -511,6 +531,98 @@ __global__ void __launch_bounds__(THREADS, 1) k_preagg_dense(const DenseParams p
   int* item_idx = items + n_slots;
   uint64_t* sbuf = (uint64_t*)(item_idx + n_slots);
   if (p.dbg && threadIdx.x == 0) p.dbg[gridDim.x * 4 + 0] = dense_now();
+  // ---- fast path: every CTA staged the same keys (in key order).  Then staged row r of every CTA belongs
+  //      to output row r: 8 lanes per (row, word) sum that word over the CTAs, no hashing, no sorting.  All
+  //      loads of a phase are independent and issued back to back (bounded, fully unrolled loops): the
+  //      phase costs one L2 round trip.
+  if (gridDim.x <= 8 * 20) {
+    const int G = (int)gridDim.x;
+    const int ng0 = ((volatile int*)p.cta_ng)[0];
+    uint64_t* red = sbuf;                 // [ng0][W]
+    uint64_t* k0 = sbuf + DN_MAX_GC * W;  // [ng0][NK]: keys of CTA 0
+    bool same = true;
+    for (int cta = threadIdx.x; cta < G; cta += DN_THREADS) same = same && ((volatile int*)p.cta_ng)[cta] == ng0;
+    for (int i = threadIdx.x; i < ng0 * NK; i += DN_THREADS) k0[i] = ld_cg(STG(0, i / NK, i % NK));
+    __syncthreads();
+    if (p.dbg && threadIdx.x == 0) p.dbg[gridDim.x * 4 + 1] = dense_now();
+    {
+      const int items = (G - 1) * ng0 * NK;
+      uint64_t got[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = threadIdx.x + u * DN_THREADS;
+        got[u] = 0;
+        if (i < items) {   // consecutive threads read consecutive CTAs of one (row, key word): full sectors
+          const int rj = i / (G - 1), cta = 1 + (i - rj * (G - 1));
+          got[u] = ld_cg(STG(cta, rj / NK, rj % NK));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = threadIdx.x + u * DN_THREADS;
+        if (i < items) same = same && got[u] == k0[i / (G - 1)];
+      }
+      if (items > 8 * DN_THREADS) same = false;   // more keys than this path is unrolled for: generic path
+    }
+    if (__syncthreads_and(same ? 1 : 0)) {
+      if (p.dbg && threadIdx.x == 0) p.dbg[gridDim.x * 4 + 2] = dense_now();
+      const int nw = W - NK;
+      const int sl8 = lane & 7;
+      for (int pair0 = 0; pair0 < ng0 * nw; pair0 += DN_WARPS * 4) {
+        const int pair = pair0 + warp * 4 + (lane >> 3);
+        const bool on = pair < ng0 * nw;
+        const int r = on ? pair / nw : 0, w = NK + (on ? pair - r * nw : 0);
+        int kind = 1;      // rows / NaN counts: integer adds
+        bool f = false;
+        if (w > NK) {
+          const int c = (w - NK - 1) / WPC, k = (w - NK - 1) - c * WPC;
+          if (k > 0) {
+            kind = p.word_kind[k];
+            f = (f64m >> c) & 1u;
+          }
+        }
+        uint64_t v = 0;
+        if (kind == 3) v = f ? 0x7ff8000000000000ULL : 0x7fffffffffffffffULL;
+        if (kind == 4) v = f ? 0x7ff8000000000000ULL : 0x8000000000000000ULL;
+        uint64_t x[20];
+#pragma unroll
+        for (int u = 0; u < 20; ++u) {
+          const int cta = sl8 + u * 8;
+          x[u] = (on && cta < G) ? ld_cg(STG(cta, r, w)) : v;
+        }
+#pragma unroll
+        for (int u = 0; u < 20; ++u)
+          if (sl8 + u * 8 < G) v = dense_combine(kind, f, v, x[u]);
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) v = dense_combine(kind, f, v, __shfl_xor_sync(0xffffffffu, v, o));
+        if (on && sl8 == 0) red[r * W + w] = v;
+      }
+      __syncthreads();
+      if (p.dbg && threadIdx.x == 0) p.dbg[gridDim.x * 4 + 3] = dense_now();
+      const int na = p.out.na;
+      for (int i = threadIdx.x; i < ng0 * na; i += DN_THREADS) {
+        const int r = i / na, a = i - r * na;
+        const int c = p.out_col[a], src = p.out_src[a];
+        const uint64_t rows = red[r * W + NK];
+        const bool fcol = c != 0xFF && ((f64m >> c) & 1u);
+        const uint64_t nanc = fcol ? red[r * W + NK + 1 + c * WPC] : 0;
+        uint64_t v;
+        if (src == MGB_COUNT) {
+          v = rows - nanc;
+        } else {
+          const int kind = src == MGB_SUM ? 1 : src == MGB_SUMSQ ? 2 : src == MGB_MIN ? 3 : 4;
+          v = red[r * W + NK + 1 + c * WPC + p.kind_off[kind]];
+          if (kind >= 3 && fcol && rows == nanc) v = 0x7ff8000000000000ULL;   // no value at all: NaN
+        }
+        p.out.acc[a][r] = v;
+      }
+      for (int i = threadIdx.x; i < ng0 * NK; i += DN_THREADS) p.out.key[i % NK][i / NK] = k0[i];
+      if (threadIdx.x == 0) *p.out_n = ng0;
+      if (p.dbg && threadIdx.x == 0) p.dbg[gridDim.x * 4 + 4] = dense_now();
+      if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 4 + 3] = dense_now();
+      return;
+    }
+  }
   for (int i = threadIdx.x; i < SM_TAB; i += DN_THREADS) tab_idx[i] = -1;
   if (threadIdx.x == 0) {
     *n_unique = 0;
@@ -528,10 +640,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_preagg_dense(const DenseParams p
   if (p.dbg && threadIdx.x == 0) p.dbg[gridDim.x * 4 + 2] = dense_now();
   // pass 1: dense output row of every staged row (shared-memory hash table on the key tuple)
   for (int it = threadIdx.x; it < total; it += DN_THREADS) {
-    const uint64_t* row = p.stg + (size_t)items[it] * W;
+    const int icta = items[it] / GC, ir = items[it] - icta * GC;
     uint64_t k[NK];
 #pragma unroll
-    for (int j = 0; j < NK; ++j) k[j] = ld_cg(row + j);
+    for (int j = 0; j < NK; ++j) k[j] = ld_cg(STG(icta, ir, j));
     const int idx = small_find_or_insert<NK>(tab_keys, tab_idx, n_unique, k);
     item_idx[it] = idx;
 #pragma unroll
@@ -591,10 +703,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_preagg_dense(const DenseParams p
     const int q1 = on ? ucnt[u + 1] : 0;
 #pragma unroll 4
     for (int q = (on ? ucnt[u] : 0) + sl; q < q1; q += 8) {
-      const uint64_t* row = p.stg + (size_t)items[sorted[q]] * W;
-      const uint64_t rows = ld_cg(row + NK);
-      const uint64_t nanc = fcol ? ld_cg(row + noff) : 0;
-      const uint64_t x = src == MGB_COUNT ? 0 : ld_cg(row + voff);
+      const int item = items[sorted[q]];
+      const int icta = item / GC, ir = item - icta * GC;
+      const uint64_t rows = ld_cg(STG(icta, ir, NK));
+      const uint64_t nanc = fcol ? ld_cg(STG(icta, ir, noff)) : 0;
+      const uint64_t x = src == MGB_COUNT ? 0 : ld_cg(STG(icta, ir, voff));
       if (src == MGB_COUNT)
         v += rows - nanc;
       else if (kind <= 2 || rows != nanc)   // min / max of an all-NaN partial: no value
