@@ -325,6 +325,7 @@ class SizeRecorder:
         self._agg.append(agg_size)
 
     def get(self):
+        self._agg = [a() if callable(a) else a for a in self._agg]
         return self._raw, self._agg
 
     @classmethod

@@ -317,15 +317,19 @@ def _execute_agg_map(ctx, op):
                 _distinct_shapes.add(plan.shape_key)
         n_out = int(out_keys[0].numel())
         frames = [DeviceFrame(plan.by, out_keys, cols, out_accs[a0:a1], n_out) for cols, a0, a1 in plan.slots]
-    if rec is not None:   # method='auto' samples real sizes: this resolves the count (one 8-byte read)
-        _record_sizes(ctx, rec, frame.nbytes, sum(len(f) * 8 * (len(f.columns) + len(plan.by)) for f in frames))
+    if rec is not None:   # method='auto' samples real sizes: resolves the count when the recorder is read
+        _record_sizes(ctx, rec, frame.nbytes,
+                      lambda: sum(len(f) * 8 * (len(f.columns) + len(plan.by)) for f in frames))
     ctx[op.outputs[0].key] = tuple(frames)
 
 
 def _record_sizes(ctx, name, raw_size, agg_size):
+    """agg_size may be a zero-argument callable: the mirror's recorder evaluates it when the tiler reads the
+    sizes (all sampled chunks are enqueued by then: one wait instead of one per chunk); a real Mars recorder
+    is a remote object and gets the number right away (aggregation.py:1120-1126)"""
     getter = getattr(ctx, "get_remote_object", None)
-    if getter is not None:  # real Mars context (aggregation.py:1120-1126)
-        getter(name).record(raw_size, agg_size)
+    if getter is not None:
+        getter(name).record(raw_size, agg_size() if callable(agg_size) else agg_size)
         return
     from .dataframe import SizeRecorder
     SizeRecorder.lookup(name).record(raw_size, agg_size)
@@ -513,7 +517,7 @@ def _execute_agg_agg(ctx, op):
     if len(idx_arrays) == 1:
         index = pd.Index(idx_arrays[0], name=names[0] if names else None)
     else:
-        index = pd.MultiIndex.from_arrays(idx_arrays, names=names)
+        index = _multi_index(idx_arrays, names)
     labels = list(host.keys())
     as_index = op.groupby_params.get("as_index", True)
     result = None
@@ -534,6 +538,19 @@ def _execute_agg_agg(ctx, op):
     if dtypes is not None and len(result) == 0:
         result = result.astype(dtypes)
     ctx[out_chunk.key] = result
+
+
+def _multi_index(arrays, names):
+    """pd.MultiIndex.from_arrays without its per-level Categorical round trip (the keys are int64 arrays)"""
+    try:
+        levels, codes = [], []
+        for a in arrays:
+            lv, inv = np.unique(a, return_inverse=True)
+            levels.append(pd.Index(lv))
+            codes.append(inv)
+        return pd.MultiIndex(levels=levels, codes=codes, names=names, verify_integrity=False)
+    except Exception:  # noqa: BLE001
+        return pd.MultiIndex.from_arrays(arrays, names=names)
 
 
 def _to_host(columns):

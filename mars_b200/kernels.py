@@ -471,17 +471,38 @@ def to_host_counted(columns: Sequence[torch.Tensor], count_block: torch.Tensor, 
     import numpy as np
 
     cap = int(columns[0].numel()) if columns else 1
-    host = torch.empty((len(columns) + 1, max(cap, 1)), dtype=torch.int64, pin_memory=True)
-    for j, c in enumerate(columns):
-        host[j, :cap].view(c.dtype).copy_(c, non_blocking=True)
-    host[len(columns), :1].copy_(count_block[count_row, :1], non_blocking=True)
+    # columns that are rows of one 2-D block (the output blocks of the merge) travel as ONE copy of the block
+    groups = {}      # id(base) -> (base, host row offset)
+    where = []       # per column: (host row, is_float)
+    rows = 0
+    for c in columns:
+        base = c._base
+        if base is not None and base.dim() == 2 and base.is_contiguous() and base.shape[1] == cap and c.stride(0) == 1:
+            ent = groups.get(id(base))
+            if ent is None:
+                ent = groups[id(base)] = (base, rows)
+                rows += base.shape[0]
+            where.append(ent[1] + (c.data_ptr() - base.data_ptr()) // (cap * 8))
+        else:
+            where.append(rows)
+            groups[id(c)] = (c, rows)
+            rows += 1
+    crow = rows
+    host = torch.empty((rows + 1, max(cap, 1)), dtype=torch.int64, pin_memory=True)
+    for t, r0 in groups.values():
+        if t.dim() == 2:
+            host[r0:r0 + t.shape[0], :cap].view(t.dtype).copy_(t, non_blocking=True)
+        else:
+            host[r0, :cap].view(t.dtype).copy_(t, non_blocking=True)
+    host[crow, :1].copy_(count_block[count_row, :1], non_blocking=True)
     torch.cuda.current_stream().synchronize()
-    n = int(host[len(columns), 0])
+    n = int(host[crow, 0])
     if n < 0:
         return n, None
+    hn = host.numpy()
     out = []
-    for j, c in enumerate(columns):
-        arr = host[j, :n].numpy()
+    for r, c in zip(where, columns):
+        arr = hn[r, :n]
         out.append(arr.view(np.float64).copy() if c.dtype == torch.float64 else arr.copy())
     return n, out
 

@@ -284,6 +284,7 @@ class Exchange:
         names = sorted({c.op.size_recorder_name for c in chunks if getattr(c.op, "size_recorder_name", None)})
         for name in names:
             rec = SizeRecorder.lookup(name)
+            rec.get()   # evaluates deferred sizes
             metas = self._gather_meta((list(rec._raw), list(rec._agg)))
             rec._raw = [x for m in metas for x in m[0]]
             rec._agg = [x for m in metas for x in m[1]]

@@ -24,11 +24,22 @@ cnt = collections.Counter()
 orig = core.execute
 
 
+import cProfile  # noqa: E402
+import pstats  # noqa: E402
+PROF = cProfile.Profile()
+PROFILE_STAGE = os.environ.get("PROFILE_STAGE")     # e.g. "agg", "combine", "map"
+
+
 def timed_execute(results, op):
     t0 = time.perf_counter()
+    prof = PROFILE_STAGE is not None and getattr(op.stage, "name", None) == PROFILE_STAGE
+    if prof:
+        PROF.enable()
     try:
         return orig(results, op)
     finally:
+        if prof:
+            PROF.disable()
         k = f"{type(op).__name__}:{getattr(op.stage, 'name', None)}"
         acc[k] += time.perf_counter() - t0
         cnt[k] += 1
@@ -69,3 +80,6 @@ in_ops = sum(acc.values())
 for k, v in sorted(acc.items(), key=lambda kv: -kv[1]):
     print(f"    {k:36s} {cnt[k] // N:3d} calls  {1e6 * v / cnt[k]:7.1f} us each  {1e3 * v / N:7.3f} ms per step")
 print(f"    session loop outside executors: {1e3 * (phases['execute (tile + run chunks)'] - in_ops) / N:.3f} ms per step")
+
+if PROFILE_STAGE:
+    pstats.Stats(PROF).sort_stats("tottime").print_stats(28)
