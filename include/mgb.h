@@ -113,10 +113,10 @@ int mgb_agg_update(mgb_agg* agg, const int64_t* const* key_cols, const void* con
 int mgb_agg_finalize(mgb_agg* agg, int64_t* out_n_groups);
 int mgb_agg_emit(mgb_agg* agg, int64_t* const* out_key_cols, void* const* out_acc_cols, int32_t sort_keys);
 int mgb_agg_destroy(mgb_agg* agg);
-/* Diagnostics of the last finalize (which pre-aggregation path consumed the rows):
- * stats[0]=rows pre-aggregated by the privatised tiny-cardinality kernel, [1]=rows pre-aggregated by the
- * shared-memory hash table kernel, [2]=rows spilled to the global table, [3]=partial rows merged,
- * [4]=global table capacity, [5]=kernels launched by this aggregator so far.                            */
+/* Diagnostics of the last finalize (which path consumed the rows): stats[0]=reserved (0), [1]=rows
+ * pre-aggregated by the shared-memory hash table kernels, [2]=rows that went to the global table as raw rows
+ * (spilled, or all of them under the distinct-keys hint), [3]=partial rows merged, [4]=global table capacity,
+ * [5]=kernels launched by this aggregator so far.                                                        */
 int mgb_agg_stats(mgb_agg* agg, int64_t* stats6);
 
 /* Low-cardinality fast paths (one kernel launch + one 8-byte device->host read each).
@@ -182,6 +182,11 @@ int mgb_post_var(const void* sum, const void* sumsq, int32_t sum_dtype, const in
  * merge/concat.py:339-348): copies n_rows 8-byte elements of src into dst starting at dst_offset.      */
 int mgb_copy_rows(void* dst, int64_t dst_offset, const void* src, int64_t n_rows, void* stream);
 
+/* a6: assembles the send buffer of the all-to-all: n_segments copies of n_rows[i] 8-byte elements from
+ * src[i] to dst[i] in one launch (per 96 segments) instead of one cudaMemcpyAsync per block and column.  */
+int mgb_copy_segments(const void* const* src, void* const* dst, const int64_t* n_rows, int32_t n_segments,
+                      void* stream);
+
 /* ---- sort=True support: argsort of int64 key tuples (lexicographic, stable) and row gather ---------- */
 int mgb_argsort_keys(const int64_t* const* key_cols, int32_t n_keys, int64_t n_rows, int32_t* out_perm,
                      void* stream);
@@ -224,6 +229,16 @@ int mgb_prof_reset(void);
 /* total device milliseconds and number of bracketed launches of kernel_id since the last reset
  * (synchronises on the recorded events). */
 int mgb_prof_read(int32_t kernel_id, double* out_total_ms, int64_t* out_launches);
+
+/* Peer-to-peer pull transport on one NVSwitch box (alternative to mgb_comm_alltoallv): mgb_ipc_arena returns a
+ * library-owned device arena of at least `bytes` (grown by reallocation; the caller packs its send buffer
+ * into it) and the arena's 64-byte CUDA IPC handle, which the caller publishes to the peers along with its
+ * block counts; mgb_ipc_open maps a peer's arena (cached per peer, re-opened when the handle changes);
+ * mgb_ipc_pull copies a slice out of it with cudaMemcpyAsync (copy engines over NVLink).  The caller
+ * synchronises its pack before publishing and runs a barrier after its pulls, before the arena is reused. */
+int mgb_ipc_arena(int64_t bytes, void** out_ptr, uint8_t out_handle[64]);
+int mgb_ipc_open(int32_t peer, const uint8_t handle[64], void** out_ptr);
+int mgb_ipc_pull(void* dst, const void* peer_src, int64_t bytes, void* stream);
 
 /* ---- microbenchmarks used by profiles/ (not part of the operand path) -------------------------------- */
 int mgb_bench_atomics(int32_t mode, int64_t n_rows, int32_t n_slots, int32_t iters, float* out_ms,

@@ -82,6 +82,7 @@ SIGNATURES = {
     "mgb_post_mean": (C.c_int, [_vp, _i32, _vp, _vp, _i64, _vp]),
     "mgb_post_var": (C.c_int, [_vp, _vp, _i32, _vp, _i32, _vp, _i64, _vp]),
     "mgb_copy_rows": (C.c_int, [_vp, _i64, _vp, _i64, _vp]),
+    "mgb_copy_segments": (C.c_int, [_pp, _pp, C.POINTER(_i64), _i32, _vp]),
     "mgb_argsort_keys": (C.c_int, [_pp, _i32, _i64, _vp, _vp]),
     "mgb_gather_rows": (C.c_int, [_pp, _pp, _i32, _vp, _i64, _vp]),
     "mgb_nccl_load": (C.c_int, [C.c_char_p]),
@@ -90,6 +91,9 @@ SIGNATURES = {
     "mgb_comm_alltoallv": (C.c_int, [_vp, _pp, C.POINTER(_i64), _pp, C.POINTER(_i64), _i32, _vp]),
     "mgb_comm_allgather_i64": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
     "mgb_comm_destroy": (C.c_int, [_vp]),
+    "mgb_ipc_arena": (C.c_int, [_i64, C.POINTER(_vp), _vp]),
+    "mgb_ipc_open": (C.c_int, [_i32, _vp, C.POINTER(_vp)]),
+    "mgb_ipc_pull": (C.c_int, [_vp, _vp, _i64, _vp]),
     "mgb_prof_enable": (C.c_int, [_i32]),
     "mgb_prof_reset": (C.c_int, []),
     "mgb_prof_read": (C.c_int, [_i32, C.POINTER(C.c_double), C.POINTER(_i64)]),

@@ -4,19 +4,16 @@
 // (mars/dataframe/groupby/aggregation.py:1043-1267).  Data flow of one aggregator:
 //
 //   update(batch)  -> phase 1, asynchronous, one pass over the batch's key + value columns
-//       k_preagg_tiny  : <= GC distinct keys per CTA.  Key list in shared memory, accumulators privatised
-//                        per warp *and per lane* ([group][acc][lane] words) so every update is a plain,
-//                        bank-conflict-free LDS/op/STS -- no atomics.  Aborts (flag) when a CTA meets more
-//                        than GC keys; then
-//       k_preagg_smem  : per-CTA shared-memory open-addressing table (linear probing, 64-bit CAS claims),
-//                        shared-memory atomics for the accumulators.  A full table is flushed to a global
-//                        staging list of partial rows while flushing pays off (>= FLUSH_GAIN rows absorbed
-//                        per staged row), otherwise frozen: hits keep aggregating on chip, misses are
-//                        appended to a row-index spill list.
+//       k_preagg_hash  : sum / mean / count shapes.  Per-CTA shared-memory hash table (linear probing, 64-bit
+//                        CAS claims), register double-buffered tiles; rows with a NaN / marker key and the
+//                        misses of a frozen (3/4 full) table go to a row-index spill list.
+//       k_preagg_smem  : every other shape (min / max / var, int columns, > 8 columns), descriptor driven;
+//                        a full table is flushed to the staging list while that pays off, else frozen.
+//       (skipped entirely when the caller set the distinct-keys hint)
 //   finalize()     -> phase 2, sizes the global table from the exact number of staged + spilled rows
-//       k_merge_staged : staged partial rows  -> global open-addressing table (64/128-bit CAS claims,
-//                        RED.ADD.F64 / atomicMin / atomicMax on the accumulators)
-//       k_update_global: spilled raw rows     -> same table (gather through the spill list)
+//       k_merge_staged        : staged partial rows -> global open-addressing table (64/128-bit CAS claims,
+//                               RED.ADD.F64 / atomicMin / atomicMax on the accumulators)
+//       k_update_global[_plain]: spilled raw rows   -> same table (gather through the spill list)
 //   emit()         -> k_emit_count / scan / k_emit_write compaction (+ radix argsort for sort=True)
 #include <new>
 #include <vector>
@@ -24,9 +21,6 @@
 #include "mgb_common.cuh"
 
 #define GROUP_COLS 8         // value columns handled per kernel instantiation
-#define TINY_WARPS 8
-#define TINY_ROWS 4          // rows per thread per tile (tiny kernel)
-#define TINY_MAX_GC 16
 #define SMEM_THREADS 512
 #define SMEM_ROWS 2          // rows per thread per tile (smem kernel)
 #define SMEM_CHECK_EVERY 4   // tiles between fill checks
@@ -56,10 +50,8 @@ struct Layout {
 };
 
 struct Ctl {                 // per update, device memory, zero-initialised
-  unsigned long long stg_count;   // staged partial rows (smem kernel)
-  unsigned long long tiny_count;  // staged partial rows (tiny kernel)
+  unsigned long long stg_count;   // staged partial rows
   unsigned long long miss_count[MGB_MAX_VALS / GROUP_COLS];  // spilled rows per column group
-  int tiny_fail;
   int err;
 };
 
@@ -389,7 +381,6 @@ struct SmemParams {
   int cap;            // table slots (power of two)
   int a0, a1;         // sorted accumulator range of this column group
   Ctl* ctl;
-  int require_tiny_fail;  // 1: run only if the tiny kernel gave up on this batch
   Staging stg;
   long long inter_cap;    // staging rows available to intermediate flushes
   int32_t* miss;          // spill list of this column group
@@ -438,7 +429,6 @@ __device__ __forceinline__ int smem_find_or_insert(uint64_t* sk, int cap, const 
 template <int NK, int NV>
 __global__ void __launch_bounds__(SMEM_THREADS, 1) k_preagg_smem(const SmemParams p) {
   extern __shared__ __align__(16) uint64_t smem[];
-  if (p.require_tiny_fail && !p.ctl->tiny_fail) return;
   const int cap = p.cap;
   const int nag = p.a1 - p.a0;
   uint64_t* sk = smem;                       // [NK][cap]
@@ -832,11 +822,9 @@ struct UpdateRec {
   Batch batch;                    // keys / n (cols filled per group at launch time)
   const uint64_t* vals[MGB_MAX_VALS];
   Ctl* ctl;                       // device
-  Staging stg;                    // smem-kernel staging
-  Staging tstg;                   // tiny-kernel staging
+  Staging stg;                    // staged partial rows of phase 1
   long long inter_cap;
-  int32_t* miss;                  // [n_groups][n]
-  bool tiny_tried;
+  int32_t* miss;                  // [n_col_groups][n]
   bool direct;                    // no pre-aggregation pass: every row goes to the global table at finalize
 };
 
@@ -1036,10 +1024,7 @@ extern "C" int mgb_agg_update(mgb_agg* a, const int64_t* const* key_cols, const 
   if (u.inter_cap > MAX_INTER_ROWS) u.inter_cap = MAX_INTER_ROWS;
   u.stg.cap = u.inter_cap + (long long)smem_grid * cap * a->n_col_groups;
   MGB_CUDA(cudaMallocAsync((void**)&u.stg.base, (size_t)u.stg.cap * ncolstg * 8, st));
-  u.tstg.cap = 0;
-  u.tstg.base = nullptr;
   MGB_CUDA(cudaMallocAsync((void**)&u.miss, sizeof(int32_t) * (size_t)n_rows * a->n_col_groups, st));
-  u.tiny_tried = false;
 
   if (plain) {
     HashParams p;
@@ -1088,7 +1073,6 @@ extern "C" int mgb_agg_update(mgb_agg* a, const int64_t* const* key_cols, const 
     p.a0 = a->group_a0[g];
     p.a1 = a->group_a0[g + 1];
     p.ctl = u.ctl;
-    p.require_tiny_fail = 0;
     p.stg = u.stg;
     p.inter_cap = u.inter_cap;
     p.miss = u.miss + (size_t)g * n_rows;
@@ -1139,22 +1123,15 @@ extern "C" int mgb_agg_finalize(mgb_agg* a, int64_t* out_n_groups) {
       continue;
     }
     MGB_REQUIRE(ctl[i].err == 0, MGB_ERR_OVERFLOW, "staging overflow in update %zu", i);
-    const bool tiny_ok = u.tiny_tried && !ctl[i].tiny_fail;
-    if (tiny_ok) {
-      total += (long long)ctl[i].tiny_count;
-      a->stats[0] += u.batch.n;
-    } else {
-      total += (long long)ctl[i].stg_count;
-      long long missed = 0;
-      for (int g = 0; g < a->n_col_groups; ++g) {
-        total += (long long)ctl[i].miss_count[g];
-        if ((long long)ctl[i].miss_count[g] > missed) missed = (long long)ctl[i].miss_count[g];
-      }
-      a->stats[1] += u.batch.n - missed;
-      a->stats[2] += missed;
-      a->stats[3] += (long long)ctl[i].stg_count;
+    total += (long long)ctl[i].stg_count;
+    long long missed = 0;
+    for (int g = 0; g < a->n_col_groups; ++g) {
+      total += (long long)ctl[i].miss_count[g];
+      if ((long long)ctl[i].miss_count[g] > missed) missed = (long long)ctl[i].miss_count[g];
     }
-    if (tiny_ok) a->stats[3] += (long long)ctl[i].tiny_count;
+    a->stats[1] += u.batch.n - missed;
+    a->stats[2] += missed;
+    a->stats[3] += (long long)ctl[i].stg_count;
   }
   // 2. global table sized from the exact row bound
   long long C = 1024;
@@ -1255,20 +1232,14 @@ extern "C" int mgb_agg_finalize(mgb_agg* a, int64_t* out_n_groups) {
       }
       continue;
     }
-    const bool tiny_ok = u.tiny_tried && !ctl[i].tiny_fail;
     MergeParams m;
     m.L = L;
     m.table = a->table;
     m.Cmask = (unsigned long long)(C - 1);
     m.shift = a->shift;
     m.g = a->gctl;
-    if (tiny_ok) {
-      m.stg = u.tstg;
-      m.n_rows = (long long)ctl[i].tiny_count;
-    } else {
-      m.stg = u.stg;
-      m.n_rows = (long long)ctl[i].stg_count;
-    }
+    m.stg = u.stg;
+    m.n_rows = (long long)ctl[i].stg_count;
     if (m.n_rows > 0) {
       unsigned g = grid_rows(a, m.n_rows, GLOBAL_THREADS, 1);
       MgbProfScope prof(MGB_K_MERGE, st);
@@ -1279,7 +1250,6 @@ extern "C" int mgb_agg_finalize(mgb_agg* a, int64_t* out_n_groups) {
       MGB_CHECK_LAUNCH();
       a->stats[5]++;
     }
-    if (tiny_ok) continue;
     if (a->plain) {
       const long long nm = (long long)ctl[i].miss_count[0];
       if (nm > 0) MGB_TRY(launch_plain(u, u.miss, nm));
@@ -1318,10 +1288,9 @@ extern "C" int mgb_agg_finalize(mgb_agg* a, int64_t* out_n_groups) {
     UpdateRec& u = a->updates[i];
     if (u.ctl) cudaFreeAsync(u.ctl, st);
     if (u.stg.base) cudaFreeAsync(u.stg.base, st);
-    if (u.tstg.base) cudaFreeAsync(u.tstg.base, st);
     if (u.miss) cudaFreeAsync(u.miss, st);
     u.ctl = nullptr;
-    u.stg.base = u.tstg.base = nullptr;
+    u.stg.base = nullptr;
     u.miss = nullptr;
   }
   a->n_groups = (long long)gh.n_groups;
@@ -1431,7 +1400,6 @@ extern "C" int mgb_agg_destroy(mgb_agg* a) {
   for (auto& u : a->updates) {
     if (u.ctl) cudaFreeAsync(u.ctl, st);
     if (u.stg.base) cudaFreeAsync(u.stg.base, st);
-    if (u.tstg.base) cudaFreeAsync(u.tstg.base, st);
     if (u.miss) cudaFreeAsync(u.miss, st);
   }
   if (a->table) cudaFreeAsync(a->table, st);

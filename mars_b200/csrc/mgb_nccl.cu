@@ -171,3 +171,75 @@ extern "C" int mgb_comm_destroy(mgb_comm* c) {
   delete c;
   return MGB_OK;
 }
+
+
+// ----------------------------------------------------------------------------------------------------
+// Peer-to-peer pull transport (alternative to the NCCL all-to-all on one NVSwitch box): every rank packs its
+// send buffer into a library-owned arena, publishes the arena's CUDA IPC handle together with the block
+// counts, and each receiver pulls its slices out of the peers' arenas with cudaMemcpyAsync -- the copy
+// engines move the bytes over NVLink, no SM and no NCCL kernel involved.
+// ----------------------------------------------------------------------------------------------------
+struct IpcArena {
+  void* base = nullptr;
+  size_t bytes = 0;
+  cudaIpcMemHandle_t handle;
+};
+struct IpcPeer {
+  bool open = false;
+  cudaIpcMemHandle_t handle;
+  void* ptr = nullptr;
+};
+static IpcArena g_arena[8];
+static IpcPeer g_peers[8][64];   // [local device][peer rank]
+
+extern "C" int mgb_ipc_arena(int64_t bytes, void** out_ptr, uint8_t out_handle[64]) {
+  MGB_REQUIRE(out_ptr && out_handle && bytes >= 0, MGB_ERR_INVALID, "bad argument");
+  int dev = 0;
+  MGB_CUDA(cudaGetDevice(&dev));
+  MGB_REQUIRE(dev >= 0 && dev < 8, MGB_ERR_UNSUPPORTED, "device ordinal %d", dev);
+  IpcArena& a = g_arena[dev];
+  if (a.bytes < (size_t)bytes || !a.base) {
+    // the caller guarantees (barrier after every exchange) that no peer is still reading the old arena
+    if (a.base) MGB_CUDA(cudaFree(a.base));
+    size_t want = (size_t)bytes + ((size_t)bytes >> 2);
+    if (want < (64u << 20)) want = 64u << 20;
+    a.base = nullptr;
+    a.bytes = 0;
+    MGB_CUDA(cudaMalloc(&a.base, want));
+    a.bytes = want;
+    MGB_CUDA(cudaIpcGetMemHandle(&a.handle, a.base));
+  }
+  *out_ptr = a.base;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  memcpy(out_handle, &a.handle, 64);
+  return MGB_OK;
+}
+
+extern "C" int mgb_ipc_open(int32_t peer, const uint8_t handle[64], void** out_ptr) {
+  MGB_REQUIRE(handle && out_ptr && peer >= 0 && peer < 64, MGB_ERR_INVALID, "bad argument");
+  int dev = 0;
+  MGB_CUDA(cudaGetDevice(&dev));
+  MGB_REQUIRE(dev >= 0 && dev < 8, MGB_ERR_UNSUPPORTED, "device ordinal %d", dev);
+  IpcPeer& p = g_peers[dev][peer];
+  if (p.open && memcmp(&p.handle, handle, 64) == 0) {
+    *out_ptr = p.ptr;
+    return MGB_OK;
+  }
+  if (p.open) {   // the peer re-allocated its arena: drop the stale mapping
+    cudaIpcCloseMemHandle(p.ptr);
+    p.open = false;
+  }
+  memcpy(&p.handle, handle, 64);
+  MGB_CUDA(cudaIpcOpenMemHandle(&p.ptr, p.handle, cudaIpcMemLazyEnablePeerAccess));
+  p.open = true;
+  *out_ptr = p.ptr;
+  return MGB_OK;
+}
+
+extern "C" int mgb_ipc_pull(void* dst, const void* peer_src, int64_t bytes, void* stream) {
+  MGB_REQUIRE(bytes >= 0, MGB_ERR_INVALID, "negative size");
+  if (bytes == 0) return MGB_OK;
+  MGB_REQUIRE(dst && peer_src, MGB_ERR_INVALID, "null pointer");
+  MGB_CUDA(cudaMemcpyAsync(dst, peer_src, (size_t)bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+  return MGB_OK;
+}

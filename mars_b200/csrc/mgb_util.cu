@@ -417,6 +417,60 @@ extern "C" int mgb_post_var(const void* sum, const void* sumsq, int32_t sum_dtyp
 }
 
 // ----------------------------------------------------------------------------------------------------
+// a6: packing of shuffle blocks -- many (source slice -> destination slice) copies of 8-byte elements in one
+// launch (the send buffer of the all-to-all is assembled from per-mapper, per-column slices).
+// ----------------------------------------------------------------------------------------------------
+#define SEG_MAX 96
+struct SegTable {
+  const uint64_t* src[SEG_MAX];
+  uint64_t* dst[SEG_MAX];
+  long long n[SEG_MAX];
+  int count;
+};
+
+__global__ void __launch_bounds__(256) k_copy_segments(const SegTable t) {
+  // blockIdx.y: segment; blockIdx.x strides over the segment
+  const int sgi = blockIdx.y;
+  const uint64_t* src = t.src[sgi];
+  uint64_t* dst = t.dst[sgi];
+  const long long n = t.n[sgi];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = mgb_ld_stream(src + i);
+}
+
+extern "C" int mgb_copy_segments(const void* const* src, void* const* dst, const int64_t* n_rows, int32_t n_segments,
+                                 void* stream) {
+  MGB_REQUIRE(n_segments >= 0, MGB_ERR_INVALID, "negative segment count");
+  if (n_segments == 0) return MGB_OK;
+  MGB_REQUIRE(src && dst && n_rows, MGB_ERR_INVALID, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int sms = mgb_sm_count();
+  for (int s0 = 0; s0 < n_segments; s0 += SEG_MAX) {
+    SegTable t;
+    t.count = 0;
+    long long longest = 0;
+    for (int i = s0; i < n_segments && t.count < SEG_MAX; ++i) {
+      MGB_REQUIRE(n_rows[i] >= 0, MGB_ERR_INVALID, "negative segment length");
+      if (n_rows[i] == 0) continue;
+      MGB_REQUIRE(src[i] && dst[i], MGB_ERR_INVALID, "null segment pointer");
+      t.src[t.count] = (const uint64_t*)src[i];
+      t.dst[t.count] = (uint64_t*)dst[i];
+      t.n[t.count] = n_rows[i];
+      if (n_rows[i] > longest) longest = n_rows[i];
+      ++t.count;
+    }
+    if (t.count == 0) continue;
+    long long bx = (longest + 256 * 8 - 1) / (256 * 8);
+    const long long cap = (long long)sms * 8 / t.count + 1;
+    if (bx > cap) bx = cap;
+    if (bx < 1) bx = 1;
+    k_copy_segments<<<dim3((unsigned)bx, (unsigned)t.count), 256, 0, st>>>(t);
+    MGB_CHECK_LAUNCH();
+  }
+  return MGB_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------
 // a7/a8: concatenation building block
 // ----------------------------------------------------------------------------------------------------
 extern "C" int mgb_copy_rows(void* dst, int64_t dst_offset, const void* src, int64_t n_rows, void* stream) {

@@ -567,6 +567,21 @@ def concat_columns(pieces: Sequence[torch.Tensor]) -> torch.Tensor:
     return out
 
 
+def copy_segments(segments) -> None:
+    """segments: list of (src tensor, dst) of 8-byte elements, dst a tensor of equal length or a raw device
+    address: all copied by one launch per 96 segments (mgb_copy_segments)."""
+    lib = _lib.load()
+    segs = [(a, b) for a, b in segments if a.numel()]
+    if not segs:
+        return
+    n = len(segs)
+    src = (C.c_void_p * n)(*[a.data_ptr() for a, _ in segs])
+    dst = (C.c_void_p * n)(*[b if isinstance(b, int) else b.data_ptr() for _, b in segs])
+    lens = (C.c_int64 * n)(*[a.numel() for a, _ in segs])
+    check(lib.mgb_copy_segments(src, dst, lens, n, _stream()))
+    _count((n + 95) // 96)
+
+
 def argsort_keys(keys: Sequence[torch.Tensor]) -> torch.Tensor:
     lib = _lib.load()
     keys = [_req(k, f"key {i}", (torch.int64,)) for i, k in enumerate(keys)]

@@ -103,6 +103,61 @@ class NcclTransport:
             self._comm = C.c_void_p()
 
 
+class IpcPullTransport:
+    """All-to-all on one NVSwitch box without NCCL: the send buffer is packed into a library-owned arena whose
+    CUDA IPC handle travels with the block counts (same metadata all-gather); every rank then PULLS its slices
+    out of the peers' arenas with cudaMemcpyAsync -- copy engines over NVLink, no SM involved (mgb_ipc_*).
+    Needs all GPUs of the box visible to every process (torchrun); the NCCL transport has no such need."""
+
+    pull = True
+
+    def __init__(self, rank: int, world: int, meta_group=None):
+        self.rank, self.world, self.meta_group = rank, world, meta_group
+        self._lib = _lib.load()
+        self.bytes_sent = 0
+        self.timed = False
+        self._events = []
+
+    exchange_stats = NcclTransport.exchange_stats
+
+    def reserve(self, n_elements: int):
+        """-> (device address of the send arena, IPC handle bytes)"""
+        ptr = C.c_void_p()
+        handle = (C.c_uint8 * 64)()
+        check(self._lib.mgb_ipc_arena(int(n_elements) * 8, C.byref(ptr), handle))
+        return int(ptr.value or 0), bytes(handle)
+
+    def pull(self, recvbuf: torch.Tensor, recv_off, peers):
+        """peers[q] = (handle bytes, element offset of my slice in q's arena) or None"""
+        stream = torch.cuda.current_stream().cuda_stream
+        nbytes = 0
+        if self.timed:
+            torch.cuda.synchronize()
+            dist.barrier(group=self.meta_group)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        for q, info in enumerate(peers):
+            n = recv_off[q + 1] - recv_off[q]
+            if q == self.rank or info is None or n == 0:
+                continue
+            handle, off = info
+            src = C.c_void_p()
+            hb = (C.c_uint8 * 64).from_buffer_copy(handle)
+            check(self._lib.mgb_ipc_open(q, hb, C.byref(src)))
+            check(self._lib.mgb_ipc_pull(recvbuf.data_ptr() + recv_off[q] * 8, (src.value or 0) + off * 8, n * 8, stream))
+            nbytes += n * 8
+        if self.timed:
+            e1.record()
+            self._events.append((e0, e1, nbytes))
+        self.bytes_sent += nbytes        # symmetric exchange: bytes pulled == bytes served on average
+        # nobody may repack its arena before every peer has finished pulling from it
+        torch.cuda.current_stream().synchronize()
+        dist.barrier(group=self.meta_group)
+
+    def close(self):
+        pass
+
+
 def _concat(pieces: List[torch.Tensor], like: torch.Tensor) -> torch.Tensor:
     pieces = [p for p in pieces if p.numel()]
     if not pieces:
@@ -112,6 +167,14 @@ def _concat(pieces: List[torch.Tensor], like: torch.Tensor) -> torch.Tensor:
 
         return kernels.concat_columns(pieces)
     return torch.cat(pieces)  # CPU tensors only occur in host-logic tests (gloo transport)
+
+
+def reducer_rank(r: int, n_reducers: int, world: int) -> int:
+    """Rank that runs reducer r: contiguous ranges of reducers per rank (the reference lets its scheduler place
+    reducers, mars/services/task/analyzer/analyzer.py:382-413 -- any fixed map is valid).  Ranges make the
+    blocks a mapper sends to one peer a single row range of its partitioned columns."""
+    per = -(-n_reducers // world)
+    return min(r // per, world - 1)
 
 
 class Exchange:
@@ -161,84 +224,123 @@ class Exchange:
 
     # ------------------------------------------------------------------------------------------ shuffle
     def shuffle(self, ctx, proxy_chunk, owners: Dict[str, int]):
+        """Moves every mapper block to the rank of its reducer.  Reducers are placed in contiguous ranges
+        (``reducer_rank``), so the blocks one mapper sends to one peer are ONE row range of its scattered
+        columns; the send buffer holds, per peer, all columns of all local mappers ([column][mapper][rows]) and
+        travels as a single message per peer.  The receiver's blocks are views into the receive buffer."""
         mappers = list(proxy_chunk.op.inputs)
         R = int(mappers[0].op.shuffle_size)
+        P = self.world
         local = [i for i, m in enumerate(mappers) if owners[m.key] == self.rank]
-        dest = lambda r: r % self.world  # noqa: E731  reducer placement, must match Session._owner
+
+        def key_of(m, r):
+            return (m.key, (r, m.index[1] if len(m.index) > 1 else 0))
+
         counts, schema, as_tuple = {}, None, True
         for i in local:
             m = mappers[i]
             for r in range(R):
-                _, payload = ctx[(m.key, (r, m.index[1] if len(m.index) > 1 else 0))]
+                _, payload = ctx[key_of(m, r)]
                 frames, as_tuple = self._payload_frames(payload)
                 counts[(i, r)] = len(frames[0])
                 if schema is None:
                     schema = self._schema(frames)
-        metas = self._gather_meta(dict(counts=counts, schema=schema, as_tuple=as_tuple))
+        reducers_of = [[r for r in range(R) if reducer_rank(r, R, P) == p] for p in range(P)]
+        on_gpu = torch.cuda.is_available()
+        dev = torch.device("cuda", torch.cuda.current_device()) if on_gpu else torch.device("cpu")
+        pull = bool(getattr(self.transport, "pull", False))
+        # ---- pack (needs local information only): peer p, column c, local mappers ascending, reducers of p
+        send_rows = [0 if p == self.rank else sum(counts[(i, r)] for i in local for r in reducers_of[p]) for p in range(P)]
+        ncols_local = 0 if schema is None else schema["nk"] + sum(len(c) for c, _ in schema["slots"])
+        send_off = [0]
+        for p in range(P):
+            send_off.append(send_off[-1] + ncols_local * send_rows[p])
+        handle = None
+        if pull:
+            send_ptr, handle = self.transport.reserve(max(send_off[-1], 1))
+            sendbuf = None
+        else:
+            sendbuf = torch.empty(max(send_off[-1], 1), dtype=torch.int64, device=dev)
+        segments = []
+        for p in range(P):
+            if p == self.rank:
+                continue
+            row0 = 0
+            for i in local:
+                m = mappers[i]
+                for r in reducers_of[p]:
+                    key = key_of(m, r)
+                    frames, _ = self._payload_frames(ctx[key][1])
+                    n = len(frames[0])
+                    if n:
+                        for c, t in enumerate(self._flatten(frames)):
+                            start = send_off[p] + c * send_rows[p] + row0
+                            if pull:
+                                segments.append((t, send_ptr + start * 8))
+                            else:
+                                segments.append((t, sendbuf[start:start + n].view(t.dtype)))
+                    row0 += n
+                    del ctx[key]
+        if segments:
+            if on_gpu:
+                from . import kernels
+
+                kernels.copy_segments(segments)
+            else:   # CPU tensors only occur in host-logic tests (gloo transport)
+                for src, dst in segments:
+                    dst.copy_(src)
+        if pull:
+            torch.cuda.current_stream().synchronize()   # the arena is complete before its handle is published
+        # ---- one metadata all-gather: block counts (+ the arena handle and slice offsets for pull transports)
+        metas = self._gather_meta(dict(counts=counts, schema=schema, as_tuple=as_tuple, handle=handle,
+                                       send_off=send_off if pull else None))
         all_counts = {}
         for m_ in metas:
             all_counts.update(m_["counts"])
             if schema is None and m_["schema"] is not None:
                 schema, as_tuple = m_["schema"], m_["as_tuple"]
         if schema is None:
+            if pull:
+                dist.barrier(group=self.meta_group)
             return
         owner_of_mapper = [owners[m.key] for m in mappers]
         ncols = schema["nk"] + sum(len(c) for c, _ in schema["slots"])
-        # pack: for destination p, reducers r (r % P == p) ascending, local mappers ascending
-        pieces: List[List[torch.Tensor]] = [[] for _ in range(ncols)]
-        send_off = [0]
-        template: Optional[List[torch.Tensor]] = None
-        for p in range(self.world):
-            n = 0
-            if p != self.rank:
-                for r in range(R):
-                    if dest(r) != p:
-                        continue
-                    for i in local:
-                        m = mappers[i]
-                        key = (m.key, (r, m.index[1] if len(m.index) > 1 else 0))
-                        frames, _ = self._payload_frames(ctx[key][1])
-                        cols = self._flatten(frames)
-                        template = template or cols
-                        for j, t in enumerate(cols):
-                            pieces[j].append(t)
-                        n += len(frames[0])
-                        del ctx[key]
-            send_off.append(send_off[-1] + n)
-        if template is None:
-            # nothing to send: still need typed empty columns
-            dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else "cpu"
-            template = [torch.empty(0, dtype=torch.int64, device=dev) for _ in range(schema["nk"])]
-            for columns, dts in schema["slots"]:
-                template += [torch.empty(0, dtype=getattr(torch, d.replace("torch.", "")), device=dev) for d in dts]
-        send_cols = [_concat(pieces[j], template[j]) for j in range(ncols)]
+        recv_rows = [0 if q == self.rank else
+                     sum(all_counts[(i, r)] for i, o in enumerate(owner_of_mapper) if o == q for r in reducers_of[self.rank])
+                     for q in range(P)]
         recv_off = [0]
-        for q in range(self.world):
-            n = 0
-            if q != self.rank:
-                for r in range(R):
-                    if dest(r) != self.rank:
-                        continue
+        for q in range(P):
+            recv_off.append(recv_off[-1] + ncols * recv_rows[q])
+        if pull:
+            recvbuf = torch.empty(max(recv_off[-1], 1), dtype=torch.int64, device=dev)
+            peers = [None if q == self.rank or metas[q]["handle"] is None else
+                     (metas[q]["handle"], metas[q]["send_off"][self.rank]) for q in range(P)]
+            self.transport.pull(recvbuf, recv_off, peers)
+        else:
+            recvbuf = self.transport.alltoallv([sendbuf], send_off, recv_off)[0]
+        self.shuffle_rows_sent += sum(send_rows)
+        # unpack: views into the receive buffer
+        dtypes = [torch.int64] * schema["nk"]
+        for _, dts in schema["slots"]:
+            dtypes += [getattr(torch, d.replace("torch.", "")) for d in dts]
+        for q in range(P):
+            if q == self.rank or recv_rows[q] == 0:
+                if q != self.rank:
                     for i, m in enumerate(mappers):
                         if owner_of_mapper[i] == q:
-                            n += all_counts[(i, r)]
-            recv_off.append(recv_off[-1] + n)
-        recv_cols = self.transport.alltoallv(send_cols, send_off, recv_off)
-        self.shuffle_rows_sent += send_off[-1]
-        # unpack
-        for q in range(self.world):
-            if q == self.rank:
+                            for r in reducers_of[self.rank]:
+                                ctx[key_of(m, r)] = (m.index, self._rebuild(
+                                    schema, [recvbuf[:0].view(dt) for dt in dtypes], 0, 0, as_tuple))
                 continue
-            pos = recv_off[q]
-            for r in range(R):
-                if dest(r) != self.rank:
+            cols = [recvbuf[recv_off[q] + c * recv_rows[q]: recv_off[q] + (c + 1) * recv_rows[q]].view(dtypes[c])
+                    for c in range(ncols)]
+            pos = 0
+            for i, m in enumerate(mappers):
+                if owner_of_mapper[i] != q:
                     continue
-                for i, m in enumerate(mappers):
-                    if owner_of_mapper[i] != q:
-                        continue
+                for r in reducers_of[self.rank]:
                     n = all_counts[(i, r)]
-                    key = (m.key, (r, m.index[1] if len(m.index) > 1 else 0))
-                    ctx[key] = (m.index, self._rebuild(schema, recv_cols, pos, pos + n, as_tuple))
+                    ctx[key_of(m, r)] = (m.index, self._rebuild(schema, cols, pos, pos + n, as_tuple))
                     pos += n
 
     # ------------------------------------------------------------------------------- point-to-point fetch
@@ -300,6 +402,7 @@ def init_exchange(backend: Optional[str] = None) -> Exchange:
         torch.cuda.set_device(local % torch.cuda.device_count())
     if not dist.is_initialized():
         dist.init_process_group(backend=backend or "gloo", rank=rank, world_size=world)
-    meta_group = None  # default group is gloo: host metadata only; bytes move through libmarsgb + NCCL
-    transport = NcclTransport(rank, world, meta_group)
+    meta_group = None  # default group is gloo: host metadata only; bytes move through libmarsgb
+    kind = os.environ.get("MGB_EXCHANGE", "nccl")
+    transport = IpcPullTransport(rank, world, meta_group) if kind == "ipc" else NcclTransport(rank, world, meta_group)
     return Exchange(transport, rank, world, meta_group)

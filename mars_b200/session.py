@@ -46,7 +46,9 @@ class Session:
         if isinstance(op, DataFrameShuffleProxy):
             return -1  # collective
         if isinstance(op.inputs[0].op, DataFrameShuffleProxy):
-            return int(chunk.index[0]) % self.world
+            from .parallel import reducer_rank
+
+            return reducer_rank(int(chunk.index[0]), len(op.inputs[0].op.inputs), self.world)
         return owners[op.inputs[0].key]
 
     # ---------------------------------------------------------------------------------- execution
