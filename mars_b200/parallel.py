@@ -136,9 +136,11 @@ class IpcPullTransport:
             dist.barrier(group=self.meta_group)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        for q, info in enumerate(peers):
+        for step in range(1, self.world):
+            q = (self.rank + step) % self.world     # staggered: at every step each arena serves one puller
+            info = peers[q]
             n = recv_off[q + 1] - recv_off[q]
-            if q == self.rank or info is None or n == 0:
+            if info is None or n == 0:
                 continue
             handle, off = info
             src = C.c_void_p()
@@ -403,6 +405,30 @@ def init_exchange(backend: Optional[str] = None) -> Exchange:
     if not dist.is_initialized():
         dist.init_process_group(backend=backend or "gloo", rank=rank, world_size=world)
     meta_group = None  # default group is gloo: host metadata only; bytes move through libmarsgb
-    kind = os.environ.get("MGB_EXCHANGE", "nccl")
-    transport = IpcPullTransport(rank, world, meta_group) if kind == "ipc" else NcclTransport(rank, world, meta_group)
+    # transport: MGB_EXCHANGE = nccl | ipc | auto (default).  auto = the peer-to-peer pull transport when every
+    # rank can map every peer's arena (one box, all GPUs visible, P2P capable), else grouped ncclSend/ncclRecv
+    kind = os.environ.get("MGB_EXCHANGE", "auto")
+    transport = None
+    if kind in ("ipc", "auto") and world > 1 and torch.cuda.is_available():
+        ok = False
+        try:
+            t = IpcPullTransport(rank, world, meta_group)
+            _, handle = t.reserve(1)
+            handles = [None] * world
+            dist.all_gather_object(handles, handle, group=meta_group)
+            lib = _lib.load()
+            for q, h in enumerate(handles):
+                if q != rank:
+                    src = C.c_void_p()
+                    check(lib.mgb_ipc_open(q, (C.c_uint8 * 64).from_buffer_copy(h), C.byref(src)))
+            ok = True
+        except Exception:  # noqa: BLE001
+            if kind == "ipc":
+                raise
+        flags = [None] * world
+        dist.all_gather_object(flags, ok, group=meta_group)
+        if all(flags):
+            transport = t
+    if transport is None:
+        transport = NcclTransport(rank, world, meta_group)
     return Exchange(transport, rank, world, meta_group)

@@ -76,7 +76,7 @@ def main():
     if rank == 0:
         worst_ms = max(float(s_[0]) for s_ in stats)
         per_gpu_bytes = max(float(s_[1]) for s_ in stats)
-        print(json.dumps({"n_gpus": world, "rows": args.rows, "groups": int(local_groups.item()), "chunks": n_chunks,
+        print(json.dumps({"n_gpus": world, "transport": type(ex.transport).__name__, "rows": args.rows, "groups": int(local_groups.item()), "chunks": n_chunks,
                           "parity_vs_pandas": ok, "seconds_per_run": times, "rows_per_s": args.rows / min(times[1:]),
                           "exchange": {"runs": 3, "device_ms_max_over_ranks": worst_ms,
                                        "bytes_sent_per_gpu": per_gpu_bytes,
