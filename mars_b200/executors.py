@@ -407,11 +407,22 @@ def _merge_general(slots, grp, ops, sort):
     base = slots[grp[0]]
     live = [i for i in range(len(base)) if len(base[i]) > 0] or [0]
     first_vals = [t for s in grp for t in slots[s][live[0]].data]
-    agg = _kernels.Aggregator(len(base[0].index), [_kernels.dtype_code(t) for t in first_vals], list(enumerate(ops)))
+    dts = [_kernels.dtype_code(t) for t in first_vals]
+    shape_key = ("merge", len(base[0].index), tuple(dts), tuple(ops))
+    distinct = shape_key in _distinct_shapes
+    agg = _kernels.Aggregator(len(base[0].index), dts, list(enumerate(ops)), expect_distinct=distinct)
     try:
+        rows = 0
         for i in live:
             agg.update(base[i].index, [t for s in grp for t in slots[s][i].data])
-        return agg.result(sort=sort, device=base[0].device)
+            rows += len(base[i])
+        res = agg.result(sort=sort, device=base[0].device)
+        st = getattr(agg, "stats", None) or {}
+        if distinct and int(res[0][0].numel()) * 4 < rows:
+            _distinct_shapes.discard(shape_key)          # the partials collapse again: pre-aggregation pays
+        elif not distinct and st.get("rows_spilled", 0) * 2 > rows:
+            _distinct_shapes.add(shape_key)
+        return res
     finally:
         agg.close()
 
@@ -522,12 +533,10 @@ def _execute_agg_agg(ctx, op):
     as_index = op.groupby_params.get("as_index", True)
     result = None
     if as_index and len(set(labels)) == len(labels) and set(labels) == set(col_value):
-        # declared column order == a permutation of what was computed: assemble directly (no reindex)
-        try:
-            result = pd.DataFrame._from_arrays([host[l] for l in col_value], columns=col_value, index=index,
-                                               verify_integrity=False)
-        except Exception:  # noqa: BLE001  (private pandas constructor: fall back to the public route)
-            result = None
+        # declared column order == a permutation of what was computed: assemble in that order, one block per
+        # column and no consolidation copy (copy=False) -- the frame wraps the arrays that came off the device
+        result = pd.DataFrame({i: host[l] for i, l in enumerate(col_value)}, index=index, copy=False)
+        result.columns = col_value
     if result is None:
         result = pd.DataFrame({i: host[l] for i, l in enumerate(labels)}, index=index)
         result.columns = pd.MultiIndex.from_tuples(labels) if two_level else pd.Index(labels)

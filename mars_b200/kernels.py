@@ -520,11 +520,9 @@ def to_host(columns: Sequence[torch.Tensor]):
         c = _req(c, f"column {j}")
         host[j, :n].view(c.dtype).copy_(c, non_blocking=True)
     torch.cuda.current_stream().synchronize()
-    out = []
-    for j, c in enumerate(columns):
-        arr = host[j, :n].numpy()
-        out.append(arr.view(np.float64).copy() if c.dtype == torch.float64 else arr.copy())
-    return out
+    # the arrays are views of the pinned block (which they keep alive): no second pass over the result
+    hn = host.numpy()
+    return [hn[j, :n].view(np.float64) if c.dtype == torch.float64 else hn[j, :n] for j, c in enumerate(columns)]
 
 
 # ------------------------------------------------------------------------------------------------- post
