@@ -340,7 +340,7 @@ def main_ours(args):
     launches = kernels.launch_counter - launches0
     import ctypes as C
     prof = {}
-    for kid, name in enumerate(["preagg_tiny", "preagg_smem", "merge", "update_global", "table_init", "emit", "hash",
+    for kid, name in enumerate(["preagg_dense", "preagg_smem", "merge", "update_global", "table_init", "emit", "hash",
                                 "partition", "sort", "post"]):
         tot, cnt = C.c_double(), C.c_int64()
         lib.mgb_prof_read(kid, C.byref(tot), C.byref(cnt))
@@ -360,7 +360,7 @@ def main_ours(args):
         except Exception:  # noqa: BLE001
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        dom = prof.get("preagg_tiny") or prof.get("preagg_smem") or {"ms_total": float("nan"), "launches": 1}
+        dom = prof.get("preagg_dense") or prof.get("preagg_smem") or {"ms_total": float("nan"), "launches": 1}
         per_launch_ms = dom["ms_total"] / dom["launches"]
         rows_per_launch = rows_rank * args.steps / dom["launches"]
         achieved = rows_per_launch * BYTES_PER_ROW / (per_launch_ms * 1e-3) / 1e9
@@ -385,7 +385,7 @@ def main_ours(args):
                     "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "k_preagg_dense" if "preagg_tiny" in prof else "k_preagg_smem",
+                         "traffic": traffic, "kernel": "k_preagg_dense" if "preagg_dense" in prof else "k_preagg_hash/k_preagg_smem",
                          "kernel_ms_per_launch": per_launch_ms, "bytes_per_launch": rows_per_launch * BYTES_PER_ROW,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
                          "step_hbm_frac": (rows_rank * BYTES_PER_ROW / (ms / args.steps * 1e-3) / 1e9) / peak},
