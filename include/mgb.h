@@ -222,7 +222,8 @@ typedef enum {
   MGB_K_PARTITION = 7,    /* histogram + scan + scatter */
   MGB_K_SORT = 8,         /* radix argsort + gather for sort=True */
   MGB_K_POST = 9,
-  MGB_K_COUNT_ = 10
+  MGB_K_BUCKET = 10,      /* bucketed aggregation: bucket ids, per-bucket aggregation, compaction */
+  MGB_K_COUNT_ = 11
 } mgb_kernel_id;
 int mgb_prof_enable(int32_t on);
 int mgb_prof_reset(void);

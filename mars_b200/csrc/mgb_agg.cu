@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "mgb_common.cuh"
+#include "mgb_layout.cuh"
 
 #define GROUP_COLS 8         // value columns handled per kernel instantiation
 #define SMEM_THREADS 512
@@ -29,25 +30,7 @@
 #define GLOBAL_ROWS 2
 #define SMEM_BUDGET (200 * 1024)
 #define MAX_INTER_ROWS (4LL << 20)
-
-struct AccDesc {
-  uint8_t col;   // value column (spec index)
-  uint8_t op;    // mgb_op
-  uint8_t dt;    // dtype of the value column
-  uint8_t kind;  // mgb_acc_kind
-};
-
-// Device-visible layout, passed by value.
-struct Layout {
-  int nk, nv, na;
-  int W;                                 // 8-byte words per global table slot (keys first)
-  AccDesc acc[MGB_MAX_ACCS];             // accumulators sorted by column
-  uint8_t acc_index[MGB_MAX_ACCS];       // spec index of sorted accumulator j
-  uint8_t col_begin[MGB_MAX_VALS + 1];   // sorted accumulators of column c: [col_begin[c], col_begin[c+1])
-  uint8_t spec_op[MGB_MAX_ACCS];         // op / dtype / sorted position of spec accumulator a
-  uint8_t spec_dt[MGB_MAX_ACCS];
-  uint8_t spec_sorted[MGB_MAX_ACCS];
-};
+#define BUCKET_MIN_ROWS 4096 // smaller direct inputs take the hash-table path
 
 struct Ctl {                 // per update, device memory, zero-initialised
   unsigned long long stg_count;   // staged partial rows
@@ -846,6 +829,8 @@ struct mgb_agg {
   long long n_groups;
   std::vector<UpdateRec> updates;
   long long stats[6];
+  bool bucket_mode;       // finalize took the bucketed path (mgb_bucket.cu): the result lives in `bkt`
+  BktResult bkt;
 };
 
 static int build_layout(const mgb_agg_spec* s, Layout* L) {
@@ -920,6 +905,8 @@ extern "C" int mgb_agg_create(mgb_agg** out, const mgb_agg_spec* spec, void* str
   }
   a->finalized = false;
   a->n_groups = 0;
+  a->bucket_mode = false;
+  memset(&a->bkt, 0, sizeof(a->bkt));
   memset(a->stats, 0, sizeof(a->stats));
   char* blk = nullptr;
   cudaError_t e = cudaMallocAsync((void**)&blk, 256, a->st);
@@ -1104,6 +1091,39 @@ extern "C" int mgb_agg_finalize(mgb_agg* a, int64_t* out_n_groups) {
   cudaStream_t st = a->st;
   const Layout& L = a->L;
   const size_t U = a->updates.size();
+  // 0. inputs that were not pre-aggregated (distinct-keys hint): bucketed aggregation -- no table sized by the
+  //    row count, no atomics on the values (mgb_bucket.cu).  Overflow of a bucket falls through to the table.
+  if (U > 0 && U < 65536 && mgb_bucket_supports(L)) {
+    bool all_direct = true;
+    long long T = 0;
+    for (size_t i = 0; i < U; ++i) {
+      all_direct = all_direct && a->updates[i].direct;
+      T += a->updates[i].batch.n;
+    }
+    if (all_direct && T >= BUCKET_MIN_ROWS && T < 0x7fffffffLL) {
+      std::vector<BktSource> srcs(U);
+      long long begin = 0;
+      for (size_t i = 0; i < U; ++i) {
+        const UpdateRec& u = a->updates[i];
+        memset(&srcs[i], 0, sizeof(BktSource));
+        for (int j = 0; j < L.nk; ++j) srcs[i].keys[j] = u.batch.keys[j];
+        for (int c = 0; c < L.nv; ++c) srcs[i].vals[c] = u.vals[c];
+        srcs[i].begin = begin;
+        begin += u.batch.n;
+      }
+      int overflow = 0;
+      MGB_TRY(mgb_bucket_aggregate(L, srcs.data(), (int)U, T, st, &a->bkt, &overflow));
+      if (!overflow) {
+        a->bucket_mode = true;
+        a->n_groups = a->bkt.G;
+        a->stats[2] += T;
+        a->stats[5] += 8;
+        a->finalized = true;
+        *out_n_groups = a->n_groups;
+        return MGB_OK;
+      }
+    }
+  }
   // 1. read back the phase-1 counters (the only mid-flight synchronisation)
   std::vector<Ctl> ctl(U);
   bool any_pre = false;
@@ -1338,14 +1358,20 @@ extern "C" int mgb_agg_emit(mgb_agg* a, int64_t* const* out_key_cols, void* cons
   const long long tiles = (slots + EMIT_THREADS - 1) / EMIT_THREADS;
   MgbProfScope prof(MGB_K_EMIT, st);
   int64_t* tile_counts = nullptr;
-  MGB_CUDA(cudaMallocAsync((void**)&tile_counts, sizeof(int64_t) * tiles, st));
-  if (L.nk == 1)
-    k_emit_count<1><<<(unsigned)tiles, EMIT_THREADS, 0, st>>>(a->table, L.W, a->C, a->gctl, tile_counts);
-  else
-    k_emit_count<2><<<(unsigned)tiles, EMIT_THREADS, 0, st>>>(a->table, L.W, a->C, a->gctl, tile_counts);
-  MGB_CHECK_LAUNCH();
-  int status = mgb_scan_exclusive_i64(tile_counts, tiles, nullptr, st);
-  if (status == MGB_OK) {
+  int status = MGB_OK;
+  if (a->bucket_mode) {
+    status = mgb_bucket_emit(L, a->bkt, out.key, out.acc, st);
+    mgb_bucket_free(&a->bkt, st);
+  } else {
+    MGB_CUDA(cudaMallocAsync((void**)&tile_counts, sizeof(int64_t) * tiles, st));
+    if (L.nk == 1)
+      k_emit_count<1><<<(unsigned)tiles, EMIT_THREADS, 0, st>>>(a->table, L.W, a->C, a->gctl, tile_counts);
+    else
+      k_emit_count<2><<<(unsigned)tiles, EMIT_THREADS, 0, st>>>(a->table, L.W, a->C, a->gctl, tile_counts);
+    MGB_CHECK_LAUNCH();
+    status = mgb_scan_exclusive_i64(tile_counts, tiles, nullptr, st);
+  }
+  if (status == MGB_OK && !a->bucket_mode) {
     if (L.nk == 1)
       k_emit_write<1><<<(unsigned)tiles, EMIT_THREADS, 0, st>>>(a->table, L, a->C, a->gctl, tile_counts, out);
     else
@@ -1357,7 +1383,7 @@ extern "C" int mgb_agg_emit(mgb_agg* a, int64_t* const* out_key_cols, void* cons
     }
   }
   a->stats[5] += 5;
-  cudaFreeAsync(tile_counts, st);
+  if (tile_counts) cudaFreeAsync(tile_counts, st);
   if (status == MGB_OK && sort_keys) {
     int32_t* perm = nullptr;
     cudaError_t e = cudaMallocAsync((void**)&perm, sizeof(int32_t) * G, st);
@@ -1404,6 +1430,7 @@ extern "C" int mgb_agg_destroy(mgb_agg* a) {
   }
   if (a->table) cudaFreeAsync(a->table, st);
   if (a->gctl) cudaFreeAsync(a->gctl, st);
+  mgb_bucket_free(&a->bkt, st);
   delete a;
   return MGB_OK;
 }

@@ -1,0 +1,478 @@
+// libmarsgb: bucketed aggregation for inputs that do not pre-aggregate (high-cardinality map chunks, reducer
+// side merges of many partial blocks) -- the second implementation behind mgb_agg_* (a4 / a9 / a10;
+// reference: DataFrameGroupByAgg._execute_map/_execute_combine/_execute_agg,
+// mars/dataframe/groupby/aggregation.py:1043-1267).
+//
+// The hash-table path (mgb_agg.cu) pays one atomic per (row, accumulator) into a table sized by the row
+// count; at 40 accumulators per row (min/max/var over 8 columns) or ~1e7 distinct keys per chunk that is
+// latency- and init-bound.  Here the rows of ALL sources (update() batches, read in place) are split by the
+// top bits of the key hash into B buckets of <= 512 rows on average:
+//
+//   k_bucket_ids    row -> bucket id                                          (reads the key columns once)
+//   radix passes    stable permutation of the row ids by bucket + bucket offsets   (mgb_partition.cu)
+//   k_bucket_agg    one CTA per bucket: key table in shared memory (dense group ids), counting sort of the
+//                   bucket's rows by group id, then one thread (one warp for groups of >= 32 rows) per
+//                   (group, value column) folds that group's values in REGISTERS and stores every
+//                   accumulator once.  No atomics on values; buckets of any length are processed in tiles.
+//   scan + k_bucket_emit   compaction of the per-bucket results into the caller's columns
+//
+// A bucket that holds more groups than its table reports overflow; the caller then runs the hash-table path.
+#include <stdlib.h>
+
+#include <vector>
+
+#include "mgb_layout.cuh"
+
+#define BK_THREADS 256
+#define BK_TAB 1024           // key table slots per bucket (power of two)
+#define BK_MAXG 896           // groups per bucket before overflow is declared (load <= 7/8)
+#define BK_RT 1024            // rows per tile
+#define BK_TARGET 512         // average rows per bucket (upper bound)
+#define BK_BIG 32             // groups with >= BK_BIG rows in a tile are folded by a whole warp
+#define BK_MAXA 8             // accumulators per value column handled in registers
+
+struct BktParams {
+  const BktSource* srcs;      // device array
+  const long long* begin;     // device [nsrc + 1]
+  BktSource src0;             // copy of source 0 (single-source fast path)
+  int nsrc;
+  long long T;
+  int logB;
+  const int32_t* perm;
+  const int64_t* off;
+  uint64_t* scratch;
+  int64_t* gcount;
+  int* err;
+  int stage;                  // debug: stop after this step of the first tile (0 = run everything)
+  Layout L;
+};
+
+__device__ __forceinline__ int bk_locate(const long long* __restrict__ begin, int nsrc, long long i) {
+  int lo = 0, hi = nsrc - 1;   // largest s with begin[s] <= i
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (__ldg(&begin[mid]) <= i)
+      lo = mid;
+    else
+      hi = mid - 1;
+  }
+  return lo;
+}
+
+template <int NK>
+__global__ void __launch_bounds__(256) k_bucket_ids(const BktSource* __restrict__ srcs,
+                                                    const long long* __restrict__ begin, BktSource src0, int nsrc,
+                                                    long long T, int logB, int32_t* __restrict__ pid) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < T;
+       i += (long long)gridDim.x * blockDim.x) {
+    int64_t k[NK];
+    if (nsrc == 1) {
+#pragma unroll
+      for (int j = 0; j < NK; ++j) k[j] = (int64_t)mgb_ld_stream(src0.keys[j] + i);
+    } else {
+      const int s = bk_locate(begin, nsrc, i);
+      const long long loc = i - __ldg(&begin[s]);
+#pragma unroll
+      for (int j = 0; j < NK; ++j) k[j] = (int64_t)mgb_ld_stream(srcs[s].keys[j] + loc);
+    }
+    const uint64_t sh = mgb_slot_hash(mgb_hash_tuple<NK>(k));
+    pid[i] = logB ? (int32_t)(sh >> (64 - logB)) : 0;
+  }
+}
+
+// find-or-insert in the CTA's key table; tab_idx[slot]: -1 empty, -2 being written, -3 poisoned (overflow),
+// >= 0 dense group id.  Called by ALL threads of a warp together (`valid` = this lane has a row): a lane that
+// meets a slot in the "being written" state does not spin on it -- the writer may be a lane of the same warp
+// that is parked at a reconvergence point -- it retries in the next round, after the whole warp has
+// reconverged at the vote.  The inserting thread also stores the key tuple of the new group into the
+// bucket's scratch rows.  Returns the group id, or -1 on overflow.
+template <int NK>
+__device__ __forceinline__ int bk_find_or_insert(uint64_t* tab_keys, int* tab_idx, int* n_unique, bool valid,
+                                                 const uint64_t* k, uint32_t slot, uint64_t* scratch, long long T,
+                                                 long long lo) {
+  bool done = !valid;
+  int g = -1;
+  uint32_t probe = 0;
+  while (__any_sync(0xffffffffu, !done)) {
+    if (!done) {
+      int cur = *(volatile int*)&tab_idx[slot];
+      if (cur == -1) {
+        cur = atomicCAS(&tab_idx[slot], -1, -2);
+        if (cur == -1) {
+          const int id = atomicAdd(n_unique, 1);
+          if (id >= BK_MAXG) {
+            *(volatile int*)&tab_idx[slot] = -3;   // the CTA aborts after the tile
+          } else {
+            tab_keys[slot] = k[0];
+            if (NK == 2) tab_keys[BK_TAB + slot] = k[1];
+            __threadfence_block();
+            *(volatile int*)&tab_idx[slot] = id;
+#pragma unroll
+            for (int j = 0; j < NK; ++j) scratch[(long long)j * T + lo + id] = k[j];
+            g = id;
+          }
+          done = true;
+        }
+      }
+      if (!done && cur != -2) {   // cur == -2: busy, look again next round
+        if (cur == -3) {
+          done = true;
+        } else {
+          bool eq = ((volatile uint64_t*)tab_keys)[slot] == k[0];
+          if (NK == 2) eq = eq && ((volatile uint64_t*)tab_keys)[BK_TAB + slot] == k[1];
+          if (eq) {
+            g = cur;
+            done = true;
+          } else {
+            slot = (slot + 1) & (BK_TAB - 1);
+            if (++probe == BK_TAB) done = true;
+          }
+        }
+      }
+    }
+  }
+  return g;
+}
+
+__device__ __forceinline__ uint64_t bk_shfl_down(uint64_t v, int o) {
+  uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+  lo = __shfl_down_sync(0xffffffffu, lo, o);
+  hi = __shfl_down_sync(0xffffffffu, hi, o);
+  return ((uint64_t)hi << 32) | lo;
+}
+
+template <int NK>
+__global__ void __launch_bounds__(BK_THREADS) k_bucket_agg(const BktParams p) {
+  __shared__ uint64_t tab_keys[NK * BK_TAB];
+  __shared__ int tab_idx[BK_TAB];
+  __shared__ int cnt[BK_TAB + 1];      // rows per group of the current tile -> exclusive starts
+  __shared__ int cursor[BK_TAB];
+  __shared__ uint32_t r_loc[BK_RT];
+  __shared__ uint16_t r_gid[BK_RT];
+  __shared__ uint16_t r_src[BK_RT];
+  __shared__ uint16_t sorted[BK_RT];
+  __shared__ int warp_tot[BK_THREADS / 32];
+  __shared__ int n_unique, failed;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long b = blockIdx.x;
+  const long long lo = p.off[b], hi = p.off[b + 1];
+  if (lo == hi) {
+    if (tid == 0) p.gcount[b] = 0;
+    return;
+  }
+  const long long T = p.T;
+  const Layout& L = p.L;
+  const int nk = L.nk, nv = L.nv;
+  for (int i = tid; i < BK_TAB; i += BK_THREADS) tab_idx[i] = -1;
+  if (tid == 0) {
+    n_unique = 0;
+    failed = 0;
+  }
+  __syncthreads();
+
+  for (long long tlo = lo; tlo < hi; tlo += BK_RT) {
+    const int m = (int)((hi - tlo) < BK_RT ? (hi - tlo) : BK_RT);
+    const int ng_before = n_unique;
+    for (int i = tid; i <= BK_TAB; i += BK_THREADS) cnt[i] = 0;
+    __syncthreads();
+    // 1. rows of the tile: key gather, group id, histogram by group
+    for (int r0 = 0; r0 < m; r0 += BK_THREADS) {   // uniform trip count: the table insert votes per warp
+      const int r = r0 + tid;
+      const bool valid = r < m;
+      const long long i = valid ? (long long)p.perm[tlo + r] : 0;
+      int s = 0;
+      long long loc = i;
+      uint64_t k[NK];
+#pragma unroll
+      for (int j = 0; j < NK; ++j) k[j] = 0;
+      if (valid) {
+        if (p.nsrc == 1) {
+#pragma unroll
+          for (int j = 0; j < NK; ++j) k[j] = __ldg(p.src0.keys[j] + i);
+        } else {
+          s = bk_locate(p.begin, p.nsrc, i);
+          loc = i - __ldg(&p.begin[s]);
+#pragma unroll
+          for (int j = 0; j < NK; ++j) k[j] = __ldg(p.srcs[s].keys[j] + loc);
+        }
+      }
+      const uint64_t sh = mgb_slot_hash(mgb_hash_tuple<NK>((const int64_t*)k));
+      const uint32_t slot = (uint32_t)(sh >> (54 - p.logB)) & (BK_TAB - 1);
+      const int g = bk_find_or_insert<NK>(tab_keys, tab_idx, &n_unique, valid, k, slot, p.scratch, T, lo);
+      if (valid) {
+        if (g < 0) {
+          failed = 1;
+        } else {
+          r_gid[r] = (uint16_t)g;
+          r_src[r] = (uint16_t)s;
+          r_loc[r] = (uint32_t)loc;
+          atomicAdd(&cnt[g], 1);
+        }
+      }
+    }
+    __syncthreads();
+    if (failed) {
+      if (tid == 0) atomicExch(p.err, 1);
+      return;
+    }
+    if (p.stage == 1) return;
+    const int ng = n_unique;
+    // 2. exclusive scan of cnt[0..ng) (4 entries per thread)
+    {
+      const int base = tid * 4;
+      int v0 = base + 0 < ng ? cnt[base + 0] : 0;
+      int v1 = base + 1 < ng ? cnt[base + 1] : 0;
+      int v2 = base + 2 < ng ? cnt[base + 2] : 0;
+      int v3 = base + 3 < ng ? cnt[base + 3] : 0;
+      const int tot = v0 + v1 + v2 + v3;
+      int x = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+      }
+      if (lane == 31) warp_tot[warp] = x;
+      __syncthreads();
+      int wp = 0;
+      for (int w = 0; w < warp; ++w) wp += warp_tot[w];
+      const int e = wp + x - tot;
+      if (base + 0 < ng) { cnt[base + 0] = e; cursor[base + 0] = e; }
+      if (base + 1 < ng) { cnt[base + 1] = e + v0; cursor[base + 1] = e + v0; }
+      if (base + 2 < ng) { cnt[base + 2] = e + v0 + v1; cursor[base + 2] = e + v0 + v1; }
+      if (base + 3 < ng) { cnt[base + 3] = e + v0 + v1 + v2; cursor[base + 3] = e + v0 + v1 + v2; }
+      if (tid == 0) cnt[ng] = m;
+    }
+    __syncthreads();
+    if (p.stage == 2) return;
+    // 3. counting sort of the tile's rows by group
+    for (int r = tid; r < m; r += BK_THREADS) sorted[atomicAdd(&cursor[r_gid[r]], 1)] = (uint16_t)r;
+    __syncthreads();
+    if (p.stage == 3) return;
+    // 4. fold: one (group, value column) per thread / per warp
+    const int n_items = ng * nv;
+    for (int pass = 0; pass < (p.stage == 4 ? 1 : 2); ++pass) {
+      const int first = pass == 0 ? tid : warp;
+      const int step = pass == 0 ? BK_THREADS : BK_THREADS / 32;
+      for (int idx = first; idx < n_items; idx += step) {
+        const int c = idx / ng, g = idx - c * ng;
+        const int st = cnt[g], n = cnt[g + 1] - st;
+        if (n == 0 || (pass == 0) != (n < BK_BIG)) continue;
+        const int a0 = L.col_begin[c], na_c = L.col_begin[c + 1] - a0;
+        if (na_c == 0) continue;
+        const int dt = L.acc[a0].dt;
+        uint64_t acc[BK_MAXA];
+#pragma unroll
+        for (int q = 0; q < BK_MAXA; ++q) acc[q] = q < na_c ? mgb_acc_init(L.acc[a0 + q].op) : 0;
+        const uint64_t* col0 = p.src0.vals[c];
+        const int j0 = pass == 0 ? 0 : lane, jstep = pass == 0 ? 1 : 32;
+#pragma unroll 2
+        for (int j = j0; j < n; j += jstep) {
+          const int r = sorted[st + j];
+          const uint64_t* col = p.nsrc == 1 ? col0 : p.srcs[r_src[r]].vals[c];
+          const uint64_t x = __ldg(col + r_loc[r]);
+#pragma unroll
+          for (int q = 0; q < BK_MAXA; ++q) {
+            if (q < na_c) {
+              uint64_t t;
+              if (mgb_contrib(L.acc[a0 + q].op, dt, x, &t)) acc[q] = mgb_combine(L.acc[a0 + q].kind, acc[q], t);
+            }
+          }
+        }
+        if (pass == 1) {
+#pragma unroll
+          for (int q = 0; q < BK_MAXA; ++q) {
+            if (q < na_c) {
+              const int kind = L.acc[a0 + q].kind;
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) acc[q] = mgb_combine(kind, acc[q], bk_shfl_down(acc[q], o));
+            }
+          }
+          if (lane != 0) continue;
+        }
+#pragma unroll
+        for (int q = 0; q < BK_MAXA; ++q) {
+          if (q < na_c) {
+            uint64_t* dst = p.scratch + (long long)(nk + L.acc_index[a0 + q]) * T + lo + g;
+            *dst = g >= ng_before ? acc[q] : mgb_combine(L.acc[a0 + q].kind, *dst, acc[q]);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (tid == 0) p.gcount[b] = n_unique;
+}
+
+struct BktEmitCols {
+  uint64_t* key[MGB_MAX_KEYS];
+  uint64_t* acc[MGB_MAX_ACCS];
+};
+
+// one warp per bucket: scratch rows [off[b], off[b] + n_b) -> output rows [goff[b], goff[b] + n_b), decoded
+__global__ void __launch_bounds__(256) k_bucket_emit(Layout L, const uint64_t* __restrict__ scratch, long long T,
+                                                     const int64_t* __restrict__ off,
+                                                     const int64_t* __restrict__ goff, int B, BktEmitCols out) {
+  const int lane = threadIdx.x & 31;
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long b = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); b < B; b += nwarps) {
+    const long long g0 = goff[b];
+    const int n = (int)(goff[b + 1] - g0);
+    if (n == 0) continue;
+    const long long lo = off[b];
+    for (int j = 0; j < L.nk; ++j)
+      for (int g = lane; g < n; g += 32) out.key[j][g0 + g] = scratch[(long long)j * T + lo + g];
+    for (int a = 0; a < L.na; ++a) {
+      const int op = L.spec_op[a], dt = L.spec_dt[a];
+      for (int g = lane; g < n; g += 32)
+        out.acc[a][g0 + g] = mgb_acc_decode(op, dt, scratch[(long long)(L.nk + a) * T + lo + g]);
+    }
+  }
+}
+
+bool mgb_bucket_supports(const Layout& L) {
+  for (int c = 0; c < L.nv; ++c)
+    if (L.col_begin[c + 1] - L.col_begin[c] > BK_MAXA) return false;
+  return true;
+}
+
+void mgb_bucket_free(BktResult* r, cudaStream_t st) {
+  if (r->scratch) cudaFreeAsync(r->scratch, st);
+  if (r->off) cudaFreeAsync(r->off, st);
+  if (r->goff) cudaFreeAsync(r->goff, st);
+  r->scratch = nullptr;
+  r->off = nullptr;
+  r->goff = nullptr;
+}
+
+static void bk_debug(const char* what, cudaStream_t st) {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("MGB_BUCKET_DEBUG");
+    on = (e && *e && *e != '0') ? 1 : 0;
+  }
+  if (!on) return;
+  fprintf(stderr, "[mgb bucket] %s ...", what);
+  fflush(stderr);
+  cudaError_t e = cudaStreamSynchronize(st);
+  fprintf(stderr, " %s\n", cudaGetErrorString(e));
+  fflush(stderr);
+}
+
+int mgb_bucket_aggregate(const Layout& L, const BktSource* srcs_host, int nsrc, long long T, cudaStream_t st,
+                         BktResult* out, int* overflow) {
+  *overflow = 0;
+  memset(out, 0, sizeof(*out));
+  MGB_REQUIRE(nsrc >= 1 && nsrc < 65536 && T >= 1 && T < 0x7fffffffLL, MGB_ERR_UNSUPPORTED,
+              "bucketed aggregation: %d sources, %lld rows", nsrc, T);
+  int logB = 0;
+  while (logB < 22 && (T >> logB) > BK_TARGET) ++logB;
+  const int B = 1 << logB;
+  const int ncol = L.nk + L.na;
+  char* small = nullptr;     // srcs | begin | err
+  const size_t src_bytes = sizeof(BktSource) * (size_t)nsrc;
+  const size_t begin_bytes = sizeof(long long) * ((size_t)nsrc + 1);
+  const size_t src_pad = (src_bytes + 255) & ~(size_t)255, begin_pad = (begin_bytes + 255) & ~(size_t)255;
+  int32_t *pid = nullptr, *perm = nullptr;
+  MGB_CUDA(cudaMallocAsync((void**)&small, src_pad + begin_pad + 256, st));
+  MGB_CUDA(cudaMallocAsync((void**)&pid, sizeof(int32_t) * (size_t)T, st));
+  MGB_CUDA(cudaMallocAsync((void**)&perm, sizeof(int32_t) * (size_t)T, st));
+  MGB_CUDA(cudaMallocAsync((void**)&out->off, sizeof(int64_t) * ((size_t)B + 1), st));
+  MGB_CUDA(cudaMallocAsync((void**)&out->goff, sizeof(int64_t) * ((size_t)B + 1), st));
+  MGB_CUDA(cudaMallocAsync((void**)&out->scratch, sizeof(uint64_t) * (size_t)ncol * (size_t)T, st));
+  out->T = T;
+  out->B = B;
+  BktSource* d_srcs = (BktSource*)small;
+  long long* d_begin = (long long*)(small + src_pad);
+  int* d_err = (int*)(small + src_pad + begin_pad);
+  {
+    std::vector<long long> begin((size_t)nsrc + 1);
+    for (int s = 0; s < nsrc; ++s) begin[s] = srcs_host[s].begin;
+    begin[nsrc] = T;
+    // pageable sources: the runtime stages these small copies before cudaMemcpyAsync returns
+    MGB_CUDA(cudaMemcpyAsync(d_srcs, srcs_host, src_bytes, cudaMemcpyHostToDevice, st));
+    MGB_CUDA(cudaMemcpyAsync(d_begin, begin.data(), begin_bytes, cudaMemcpyHostToDevice, st));
+  }
+  MGB_CUDA(cudaMemsetAsync(d_err, 0, 256, st));
+  MGB_CUDA(cudaMemsetAsync(out->goff + B, 0, sizeof(int64_t), st));
+  int status = MGB_OK;
+  {
+    MgbProfScope prof(MGB_K_BUCKET, st);
+    long long blocks = (T + 1023) / 1024, capb = (long long)mgb_sm_count() * 8;
+    const unsigned grid = (unsigned)(blocks > capb ? capb : blocks);
+    if (L.nk == 1)
+      k_bucket_ids<1><<<grid, 256, 0, st>>>(d_srcs, d_begin, srcs_host[0], nsrc, T, logB, pid);
+    else
+      k_bucket_ids<2><<<grid, 256, 0, st>>>(d_srcs, d_begin, srcs_host[0], nsrc, T, logB, pid);
+    MGB_CHECK_LAUNCH();
+    bk_debug("k_bucket_ids", st);
+    status = mgb_radix_sort_perm_pid_ex(pid, T, B, perm, out->off, false, st);
+    bk_debug("radix sort by bucket", st);
+    if (status == MGB_OK) {
+      BktParams p;
+      p.srcs = d_srcs;
+      p.begin = d_begin;
+      p.src0 = srcs_host[0];
+      p.nsrc = nsrc;
+      p.T = T;
+      p.logB = logB;
+      p.perm = perm;
+      p.off = out->off;
+      p.scratch = out->scratch;
+      p.gcount = out->goff;
+      p.err = d_err;
+      {
+        const char* e = getenv("MGB_BUCKET_STAGE");
+        p.stage = e ? atoi(e) : 0;
+      }
+      p.L = L;
+      if (L.nk == 1)
+        k_bucket_agg<1><<<(unsigned)B, BK_THREADS, 0, st>>>(p);
+      else
+        k_bucket_agg<2><<<(unsigned)B, BK_THREADS, 0, st>>>(p);
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) {
+        mgb_set_error("bucket aggregation launch: %s", cudaGetErrorString(e));
+        status = MGB_ERR_CUDA;
+      }
+    }
+    bk_debug("k_bucket_agg", st);
+    if (status == MGB_OK) status = mgb_scan_exclusive_i64(out->goff, (int64_t)B + 1, nullptr, st);
+    bk_debug("scan of group counts", st);
+  }
+  int err_h = 0;
+  int64_t G = 0;
+  if (status == MGB_OK) {
+    cudaError_t e = cudaMemcpyAsync(&err_h, d_err, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&G, out->goff + B, sizeof(int64_t), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+      mgb_set_error("bucket aggregation: %s", cudaGetErrorString(e));
+      status = MGB_ERR_CUDA;
+    }
+  }
+  cudaFreeAsync(pid, st);
+  cudaFreeAsync(perm, st);
+  cudaFreeAsync(small, st);
+  if (status != MGB_OK || err_h) {
+    mgb_bucket_free(out, st);
+    *overflow = err_h ? 1 : 0;
+    return status;
+  }
+  out->G = (long long)G;
+  return MGB_OK;
+}
+
+int mgb_bucket_emit(const Layout& L, const BktResult& r, uint64_t* const* out_key, uint64_t* const* out_acc,
+                    cudaStream_t st) {
+  BktEmitCols out;
+  memset(&out, 0, sizeof(out));
+  for (int j = 0; j < L.nk; ++j) out.key[j] = out_key[j];
+  for (int a = 0; a < L.na; ++a) out.acc[a] = out_acc[a];
+  long long blocks = ((long long)r.B + 7) / 8, capb = (long long)mgb_sm_count() * 16;
+  MgbProfScope prof(MGB_K_EMIT, st);
+  k_bucket_emit<<<(unsigned)(blocks > capb ? capb : blocks), 256, 0, st>>>(L, r.scratch, r.T, r.off, r.goff, r.B,
+                                                                          out);
+  MGB_CHECK_LAUNCH();
+  return MGB_OK;
+}

@@ -216,5 +216,9 @@ int mgb_scan_exclusive_i64(int64_t* data, int64_t n, int64_t* total_out, cudaStr
 // stable LSD radix passes over a permutation.  digit source: int32 pid array or int64 key column.
 int mgb_radix_sort_perm_pid(const int32_t* pid, int64_t n, int32_t n_partitions, int32_t* perm_out,
                             int64_t* offsets_out, cudaStream_t st);
+// same, any R < 2^31 (one pass per 8 bits); check_range = false skips the out-of-range test and its host
+// synchronisation (for partition ids computed by the library itself)
+int mgb_radix_sort_perm_pid_ex(const int32_t* pid, int64_t n, int32_t n_partitions, int32_t* perm_out,
+                               int64_t* offsets_out, bool check_range, cudaStream_t st);
 int mgb_radix_sort_perm_keys(const int64_t* const* key_cols_host_array, int32_t n_keys, int64_t n,
                              int32_t* perm_out, cudaStream_t st);

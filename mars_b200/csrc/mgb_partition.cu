@@ -162,8 +162,8 @@ __global__ void __launch_bounds__(256) k_pid_hist(const int32_t* pid, int64_t n,
   }
 }
 
-int mgb_radix_sort_perm_pid(const int32_t* pid, int64_t n, int32_t R, int32_t* perm_out, int64_t* offsets_out,
-                            cudaStream_t st) {
+int mgb_radix_sort_perm_pid_ex(const int32_t* pid, int64_t n, int32_t R, int32_t* perm_out, int64_t* offsets_out,
+                               bool check_range, cudaStream_t st) {
   // offsets
   MGB_CUDA(cudaMemsetAsync(offsets_out, 0, sizeof(int64_t) * ((size_t)R + 1), st));
   if (n == 0) return MGB_OK;
@@ -178,27 +178,26 @@ int mgb_radix_sort_perm_pid(const int32_t* pid, int64_t n, int32_t R, int32_t* p
     MGB_CHECK_LAUNCH();
   }
   MGB_TRY(mgb_scan_exclusive_i64(offsets_out, (int64_t)R + 1, nullptr, st));
-  // permutation: LSD passes on the pid digits
+  // permutation: stable LSD passes on the 8-bit digits of pid (1 pass for R <= 256, 2 for <= 65536, ...)
   const int64_t ntiles = (n + RP_TILE - 1) / RP_TILE;
   int64_t* hist = nullptr;
   MGB_CUDA(cudaMallocAsync((void**)&hist, sizeof(int64_t) * 256 * ntiles, st));
+  int npass = 1;
+  while (npass < 4 && ((int64_t)1 << (8 * npass)) < (int64_t)R) ++npass;
   int status = MGB_OK;
-  if (R <= 256) {
-    DigitSrc s{pid, nullptr, nullptr, 0};
-    status = radix_pass(s, n, perm_out, hist, nullptr, st);
-  } else {
-    int32_t* tmp = nullptr;
-    MGB_CUDA(cudaMallocAsync((void**)&tmp, sizeof(int32_t) * n, st));
-    DigitSrc s0{pid, nullptr, nullptr, 0};
-    status = radix_pass(s0, n, tmp, hist, nullptr, st);
-    if (status == MGB_OK) {
-      DigitSrc s1{pid, nullptr, tmp, 8};
-      status = radix_pass(s1, n, perm_out, hist, nullptr, st);
-    }
-    cudaFreeAsync(tmp, st);
+  int32_t* tmp = nullptr;
+  if (npass > 1) MGB_CUDA(cudaMallocAsync((void**)&tmp, sizeof(int32_t) * n, st));
+  int32_t* bufs[2] = {tmp, perm_out};
+  const int32_t* cur = nullptr;
+  for (int p = 0; p < npass && status == MGB_OK; ++p) {
+    int32_t* dst = bufs[((npass - 1 - p) & 1) ? 0 : 1];   // the last pass lands in perm_out
+    DigitSrc s{pid, nullptr, cur, 8 * p};
+    status = radix_pass(s, n, dst, hist, nullptr, st);
+    cur = dst;
   }
+  if (tmp) cudaFreeAsync(tmp, st);
   cudaFreeAsync(hist, st);
-  if (status != MGB_OK) {
+  if (status != MGB_OK || !check_range) {
     cudaFreeAsync(bad, st);
     return status;
   }
@@ -209,6 +208,11 @@ int mgb_radix_sort_perm_pid(const int32_t* pid, int64_t n, int32_t R, int32_t* p
   cudaFreeAsync(bad, st);
   MGB_REQUIRE(bad_h == 0, MGB_ERR_INVALID, "partition id outside [0, %d)", R);
   return MGB_OK;
+}
+
+int mgb_radix_sort_perm_pid(const int32_t* pid, int64_t n, int32_t R, int32_t* perm_out, int64_t* offsets_out,
+                            cudaStream_t st) {
+  return mgb_radix_sort_perm_pid_ex(pid, n, R, perm_out, offsets_out, true, st);
 }
 
 int mgb_radix_sort_perm_keys(const int64_t* const* key_cols, int32_t n_keys, int64_t n, int32_t* perm_out,

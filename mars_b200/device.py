@@ -65,10 +65,13 @@ class Pending:
     shape / a merge input was too large): ``replay`` then recomputes the columns on the general path from the
     inputs it kept alive, and every frame of the tuple is re-pointed at the new columns."""
 
-    __slots__ = ("block", "row", "cap", "_frames", "replay", "value")
+    __slots__ = ("block", "row", "cap", "_frames", "replay", "value", "fblock", "layout")
 
-    def __init__(self, block: torch.Tensor, row: int, cap: int, replay):
+    def __init__(self, block: torch.Tensor, row: int, cap: int, replay, fblock=None, layout=None):
         self.block, self.row, self.cap = block, row, cap
+        # float64 block and column layout of the same result (kernels._FastCall): lets a consumer ship the
+        # whole speculative result (both blocks, count row included) without looking at it
+        self.fblock, self.layout = fblock, layout
         # weak: frames own their Pending (and through its replay closure the inputs), never the other way
         # round -- no reference cycle, so dropping the frames frees the inputs immediately
         self._frames: List[Any] = []

@@ -187,6 +187,7 @@ _map_plans: Dict[Any, _MapPlan] = {}
 
 
 _map_plans_fast: Dict[Any, Any] = {}
+_PREAGG_GROUPS = 2048     # chunks with at most this many groups are worth the shared-memory pre-aggregation
 
 
 def _map_plan(op, frame: DeviceFrame) -> _MapPlan:
@@ -306,11 +307,14 @@ def _execute_agg_map(ctx, op):
                 frames = [DeviceFrame(plan.by, out_keys, cols, out_accs[a0:a1], n_out) for cols, a0, a1 in plan.slots]
     if frames is None:
         vals = all_vals()
+        # Shared-memory pre-aggregation pays while a CTA's table holds (nearly) all groups of the chunk; a
+        # shape whose rows mostly spilled is remembered and its next chunks go straight to the bucketed
+        # aggregation (distinct-keys hint), until a chunk comes back with few groups again.
         if plan.shape_key in _distinct_shapes:
             out_keys, out_accs, stats = _kernels.groupby_aggregate(keys, vals, list(plan.accs), sort=False,
                                                                    expect_distinct=True)
-            if stats and int(out_keys[0].numel()) * 4 < int(keys[0].numel()):
-                _distinct_shapes.discard(plan.shape_key)     # the data changed: pre-aggregation pays again
+            if stats and int(out_keys[0].numel()) <= _PREAGG_GROUPS:
+                _distinct_shapes.discard(plan.shape_key)
         else:
             out_keys, out_accs, stats = _kernels.groupby_aggregate(keys, vals, list(plan.accs), sort=False)
             if stats and stats.get("rows_spilled", 0) * 2 > int(keys[0].numel()):
@@ -379,7 +383,8 @@ def _merge_partials(slots: Sequence[Sequence[DeviceFrame]], steps: Sequence[_Ste
             if res is not None:
                 bi, bf, fc = res
                 pend_out = Pending(bi, fc.n_int, bi.shape[1],
-                                   lambda grp=grp, ops=ops: _merge_general(slots, grp, ops, force_sort))
+                                   lambda grp=grp, ops=ops: _merge_general(slots, grp, ops, force_sort),
+                                   fblock=bf, layout=fc)
                 k, a = fc.views(bi, bf)
         if pend_out is None:
             res = None
@@ -408,21 +413,13 @@ def _merge_general(slots, grp, ops, sort):
     live = [i for i in range(len(base)) if len(base[i]) > 0] or [0]
     first_vals = [t for s in grp for t in slots[s][live[0]].data]
     dts = [_kernels.dtype_code(t) for t in first_vals]
-    shape_key = ("merge", len(base[0].index), tuple(dts), tuple(ops))
-    distinct = shape_key in _distinct_shapes
-    agg = _kernels.Aggregator(len(base[0].index), dts, list(enumerate(ops)), expect_distinct=distinct)
+    # every piece is a partial frame with unique keys: pre-aggregating a piece on its own cannot reduce it, so
+    # the pieces go to the library with the distinct-keys hint (bucketed aggregation over all pieces in place)
+    agg = _kernels.Aggregator(len(base[0].index), dts, list(enumerate(ops)), expect_distinct=True)
     try:
-        rows = 0
         for i in live:
             agg.update(base[i].index, [t for s in grp for t in slots[s][i].data])
-            rows += len(base[i])
-        res = agg.result(sort=sort, device=base[0].device)
-        st = getattr(agg, "stats", None) or {}
-        if distinct and int(res[0][0].numel()) * 4 < rows:
-            _distinct_shapes.discard(shape_key)          # the partials collapse again: pre-aggregation pays
-        elif not distinct and st.get("rows_spilled", 0) * 2 > rows:
-            _distinct_shapes.add(shape_key)
-        return res
+        return agg.result(sort=sort, device=base[0].device)
     finally:
         agg.close()
 

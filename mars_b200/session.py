@@ -132,7 +132,7 @@ class Session:
         import torch
         import torch.distributed as dist
 
-        from .device import DeviceFrame, PiecewiseFrame
+        from .device import DeviceFrame, Pending, PiecewiseFrame
         from .executors import _merge_partials, _pieces_of, _plan_steps
 
         t = df.data
@@ -162,33 +162,39 @@ class Session:
             self.rank, self.world = saved_rank, saved_world
         steps = _plan_steps(agg_chunk.op, None)
         merged = _merge_partials(_pieces_of(ctx[feed.key]), steps, sort=False)
-        n = len(merged[0])
-        if n > max_groups:
-            raise NotImplementedError(f"{n} groups on one rank: use the shuffle branch")
-        dev = merged[0].device
-        nk = len(merged[0].index)
-        cols = list(merged[0].index) + [c for f in merged for c in f.data]
-        block = torch.zeros((len(cols), max_groups), dtype=torch.int64, device=dev)
-        for j, c in enumerate(cols):
-            block[j, :n].copy_(c.view(torch.int64))
-        count = torch.tensor([n], dtype=torch.int64, device=dev)
-        blocks = [torch.empty_like(block) for _ in range(world)]
-        counts = [torch.empty_like(count) for _ in range(world)]
-        dist.all_gather(blocks, block, group=group)
-        dist.all_gather(counts, count, group=group)
+        # Every rank ships its local result as the block pair of the speculative small-merge layout (int64
+        # block with the row count in its last row + float64 block, fixed capacity): two all-gathers of
+        # identical shape on every rank, no host synchronisation when the result is still speculative;
+        # rank 0's stage=agg merge reads every rank's row count on the device.
+        pend = merged[0]._pending
+        if (pend is not None and pend.value is None and pend.fblock is not None
+                and all(f._pending is pend for f in merged)):
+            bi, bf, fc = pend.block, pend.fblock, pend.layout
+        else:
+            bi, bf, fc = self._pack_block(merged, steps, max_groups)
+        gi = torch.empty((world * bi.shape[0], bi.shape[1]), dtype=bi.dtype, device=bi.device)
+        gf = torch.empty((world * bf.shape[0], bf.shape[1]), dtype=bf.dtype, device=bf.device)
+        dist.all_gather_into_tensor(gi, bi, group=group)     # concatenation along dim 0
+        dist.all_gather_into_tensor(gf, bf, group=group)
+        gi = gi.view(world, bi.shape[0], bi.shape[1])
+        gf = gf.view(world, bf.shape[0], bf.shape[1])
         if rank != 0:
             return None
-        ns = [int(c.item()) for c in counts]
-        slots = []
-        pos = nk
-        for f in merged:
-            pieces = []
-            for r in range(world):
-                keys = [blocks[r][j, :ns[r]] for j in range(nk)]
-                data = [blocks[r][pos + j, :ns[r]].view(t_.dtype) for j, t_ in enumerate(f.data)]
-                pieces.append(DeviceFrame(f.index_names, keys, f.columns, data, ns[r]))
-            slots.append(PiecewiseFrame(pieces))
-            pos += len(f.data)
+
+        def no_replay():
+            raise NotImplementedError("a rank's local partials do not fit the small-merge path: "
+                                      "use the shuffle branch")
+
+        pieces: List[List[DeviceFrame]] = [[] for _ in merged]
+        for r in range(world):
+            pr = Pending(gi[r], fc.n_int, gi.shape[2], no_replay)
+            k, a = fc.views(gi[r], gf[r])
+            a0 = 0
+            for i, f in enumerate(merged):
+                a1 = a0 + len(f.columns)
+                pieces[i].append(DeviceFrame(f.index_names, k, f.columns, a[a0:a1], pending=pr, slot=(a0, a1)))
+                a0 = a1
+        slots = [PiecewiseFrame(p) for p in pieces]
         ctx[feed.key] = tuple(slots)
         ctx.set_current_chunk(agg_chunk)
         try:
@@ -197,6 +203,27 @@ class Session:
             raise core.ExecutionError(e) from e
         self.executed_ops.append("DataFrameGroupByAgg:agg")
         return ctx[agg_chunk.key]
+
+    @staticmethod
+    def _pack_block(merged, steps, max_groups):
+        """partials whose size is known on the host -> block pair in the layout of the speculative
+        small-merge result (kernels._FastCall), so that every rank enters the same collectives"""
+        from . import kernels as K
+        from .executors import _OPCODE
+
+        n = len(merged[0])
+        cap = K.SMALL_MAX_ROWS
+        if n > min(cap, max_groups):
+            raise NotImplementedError(f"{n} groups on one rank: use the shuffle branch")
+        cols = [t for f in merged for t in f.data]
+        ops = [_OPCODE[st.agg_func] for st, f in zip(steps, merged) for _ in f.columns]
+        fc = K._fast(len(merged[0].index), [K.dtype_code(t) for t in cols], tuple(enumerate(ops)))
+        bi, bf = fc.alloc(cap, merged[0].device)
+        keys, accs = fc.views(bi, bf)
+        for dst, src in zip(keys + accs, list(merged[0].index) + cols):
+            dst[:n].copy_(src)
+        bi[fc.n_int, :1].fill_(n)
+        return bi, bf, fc
 
     def fetch(self, df: DataFrame) -> pd.DataFrame:
         """Concatenate the result chunks in chunk order (multi-GPU: gathered to every rank as pandas)."""

@@ -41,3 +41,4 @@ for _ in range(10):
     step()
 pr.disable()
 pstats.Stats(pr).sort_stats("cumulative").print_stats(45)
+pstats.Stats(pr).sort_stats("tottime").print_stats(45)

@@ -97,10 +97,10 @@ def pandas_agg(keys, vals, accs):
     return key_arrays, [r.to_numpy() for r in out]
 
 
-def run_agg(K, keys, vals, accs, sort=True, batches=1):
+def run_agg(K, keys, vals, accs, sort=True, batches=1, distinct=False):
     code = dict(sum=K.SUM, sumsq=K.SUMSQ, count=K.COUNT, min=K.MIN, max=K.MAX)
     agg = K.Aggregator(len(keys), [K.F64 if v.dtype == np.float64 else K.I64 for v in vals],
-                       [(c, code[o]) for c, o in accs])
+                       [(c, code[o]) for c, o in accs], expect_distinct=distinct)
     n = len(keys[0])
     bounds = np.linspace(0, n, batches + 1).astype(int)
     for b in range(batches):
@@ -112,8 +112,8 @@ def run_agg(K, keys, vals, accs, sort=True, batches=1):
     return [t.cpu().numpy() for t in k], [t.cpu().numpy() for t in a], stats
 
 
-def check_agg(K, keys, vals, accs, batches=1, expect_path=None):
-    gk, ga, stats = run_agg(K, keys, vals, accs, sort=True, batches=batches)
+def check_agg(K, keys, vals, accs, batches=1, expect_path=None, distinct=False):
+    gk, ga, stats = run_agg(K, keys, vals, accs, sort=True, batches=batches, distinct=distinct)
     ek, ea = pandas_agg(keys, vals, accs)
     for a, b in zip(gk, ek):
         np.testing.assert_array_equal(a, b)
@@ -125,7 +125,7 @@ def check_agg(K, keys, vals, accs, batches=1, expect_path=None):
     if expect_path is not None:
         assert stats[expect_path] > 0, stats
     # unsorted emit returns the same rows in table order
-    uk, ua, _ = run_agg(K, keys, vals, accs, sort=False, batches=batches)
+    uk, ua, _ = run_agg(K, keys, vals, accs, sort=False, batches=batches, distinct=distinct)
     order = np.lexsort(tuple(reversed(uk)))
     for a, b in zip(uk, gk):
         np.testing.assert_array_equal(a[order], b)
@@ -388,7 +388,7 @@ def test_aggregate_with_distinct_keys_hint_skips_preaggregation(K, plain):
     code = dict(sum=K.SUM, sumsq=K.SUMSQ, count=K.COUNT, min=K.MIN, max=K.MAX)
     k, a, stats = K.groupby_aggregate([dev(x) for x in keys], [dev(v) for v in vals], [(c, code[o]) for c, o in accs],
                                       sort=True, expect_distinct=True)
-    assert stats["rows_smem"] == 0 and stats["rows_spilled"] == n
+    assert stats["rows_smem"] == 0 and stats["rows_spilled"] == n and stats["table_capacity"] == 0
     ek, ea = pandas_agg(keys, vals, accs)
     np.testing.assert_array_equal(k[0].cpu().numpy(), ek[0])
     for (col, op), got, exp in zip(accs, a, ea):
@@ -397,6 +397,75 @@ def test_aggregate_with_distinct_keys_hint_skips_preaggregation(K, plain):
             np.testing.assert_array_equal(got, exp.astype(got.dtype))
         else:
             np.testing.assert_allclose(got, exp, rtol=1e-9, atol=0, equal_nan=True)
+
+
+# ------------------------------------------------------------------------ bucketed aggregation (mgb_bucket.cu)
+def _bucketed(stats):
+    """the distinct-keys hint was honoured by the bucketed path: no global table was built"""
+    return stats["table_capacity"] == 0 and stats["rows_spilled"] > 0
+
+
+@pytest.mark.parametrize("n_keys", [1, 2])
+@pytest.mark.parametrize("n,card,batches", [(5000, 4000, 1), (300_000, 300_000, 1), (300_000, 40_000, 7),
+                                            (1_200_000, 150_000, 3), (200_000, 13, 2)])
+def test_bucketed_aggregation_matches_pandas(K, n_keys, n, card, batches):
+    """inputs that are not pre-aggregated (distinct-keys hint): all ops, both dtypes, NaNs, several sources;
+    card=13 makes every bucket one long multi-tile run of a few big groups (warp-per-group fold)"""
+    rng = np.random.default_rng(n + card + n_keys)
+    if n_keys == 1:
+        keys = [rng.integers(-(card // 2), card - card // 2, n, dtype=np.int64)]
+    else:
+        c1 = max(int(np.sqrt(card)), 1)
+        keys = [rng.integers(0, c1, n, dtype=np.int64), rng.integers(-3, max(card // c1, 1) - 3, n, dtype=np.int64)]
+    keys[0][::1001] = -2 ** 63
+    vals = [rng.normal(10, 3, n), rng.random(n), rng.integers(-100, 100, n, dtype=np.int64)]
+    vals[1][rng.random(n) < 0.2] = np.nan
+    accs = [(0, o) for o in ALL_OPS] + [(1, o) for o in ALL_OPS] + [(2, "sum"), (2, "min"), (2, "max"), (2, "count")]
+    stats = check_agg(K, keys, vals, accs, batches=batches, distinct=True)
+    assert _bucketed(stats), stats
+
+
+def test_bucketed_aggregation_wide_min_max_var_shape(K):
+    """cfg4-shaped: two keys, 8 float64 columns x (min, max, sum, sumsq, count) = 40 accumulators"""
+    rng = np.random.default_rng(44)
+    n = 400_000
+    keys = [rng.integers(0, 300, n, dtype=np.int64), rng.integers(0, 200, n, dtype=np.int64)]
+    vals = [rng.normal(10, 3, n) for _ in range(8)]
+    accs = [(c, o) for o in ("min", "max", "sum", "sumsq", "count") for c in range(8)]
+    stats = check_agg(K, keys, vals, accs, batches=2, distinct=True)
+    assert _bucketed(stats), stats
+
+
+def test_bucketed_aggregation_skew_and_merge_ops(K):
+    """one key holds a third of the rows (a bucket of many tiles, folded by warps, merged across tiles);
+    reducer-side merge shape: int64 count partials summed, float64 min / max partials with NaN = no value"""
+    rng = np.random.default_rng(45)
+    n = 600_000
+    k = rng.integers(0, 200_000, n, dtype=np.int64)
+    k[rng.random(n) < 0.33] = 77
+    s = rng.normal(0, 1, n)
+    c = rng.integers(0, 50, n, dtype=np.int64)
+    mn = rng.random(n)
+    mn[rng.random(n) < 0.3] = np.nan
+    mn[k == 5] = np.nan
+    accs = [(0, "sum"), (1, "sum"), (2, "min"), (2, "max")]
+    stats = check_agg(K, [k], [s, c, mn], accs, batches=16, distinct=True)
+    assert _bucketed(stats), stats
+
+
+def test_bucketed_aggregation_overflow_falls_back_to_the_table(K):
+    """more groups in one bucket than its on-chip table holds: the library reports nothing wrong, it takes
+    the hash-table path (keys chosen so that the top bits of their slot hash collide)"""
+    cand = np.arange(1, 3_000_000, dtype=np.int64)
+    h = orc.hash_keys([cand]) * np.uint64(0x9e3779b97f4a7c15)
+    chosen = cand[(h >> np.uint64(64 - 9)) == 0][:2000]
+    assert len(chosen) == 2000
+    rng = np.random.default_rng(46)
+    keys = [np.repeat(chosen, 100)]            # 200k rows -> 512 buckets, every row in bucket 0
+    rng.shuffle(keys[0])
+    vals = [rng.random(len(keys[0]))]
+    stats = check_agg(K, keys, vals, [(0, "sum"), (0, "count"), (0, "max")], distinct=True)
+    assert stats["table_capacity"] > 0
 
 
 @pytest.mark.parametrize("n_keys", [1, 2])
