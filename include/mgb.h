@@ -104,19 +104,24 @@ int mgb_partition_scatter(const int32_t* pid, int64_t n_rows, int32_t n_partitio
  * (groupby(sort=True)).                                                                                 */
 typedef struct mgb_agg mgb_agg;
 int mgb_agg_create(mgb_agg** out, const mgb_agg_spec* spec, void* stream);
-/* Optional, before the first update: the caller expects (nearly) all key tuples of the coming batches to be
- * distinct (it has seen an earlier chunk of the same computation spill most of its rows): the shared-memory
- * pre-aggregation pass is skipped and every row goes straight to the global table at finalize.           */
+/* Optional, before the first update: the caller expects that pre-aggregating a batch on its own does not
+ * pay (an earlier chunk of the same computation spilled most of its rows; or the batches are partial frames
+ * with unique keys, as on the reducer side): the shared-memory pre-aggregation pass is skipped and finalize
+ * aggregates all batches in place with the bucketed aggregation (rows split by key hash into buckets of a
+ * few hundred rows, one CTA folds a bucket in registers, no atomics on the values); inputs it declines (see
+ * mgb_agg_stats) go row by row to the global hash table.                                                 */
 int mgb_agg_set_hint(mgb_agg* agg, int32_t expect_distinct_keys);
 int mgb_agg_update(mgb_agg* agg, const int64_t* const* key_cols, const void* const* val_cols,
                    int64_t n_rows);
 int mgb_agg_finalize(mgb_agg* agg, int64_t* out_n_groups);
 int mgb_agg_emit(mgb_agg* agg, int64_t* const* out_key_cols, void* const* out_acc_cols, int32_t sort_keys);
 int mgb_agg_destroy(mgb_agg* agg);
-/* Diagnostics of the last finalize (which path consumed the rows): stats[0]=reserved (0), [1]=rows
- * pre-aggregated by the shared-memory hash table kernels, [2]=rows that went to the global table as raw rows
- * (spilled, or all of them under the distinct-keys hint), [3]=partial rows merged, [4]=global table capacity,
- * [5]=kernels launched by this aggregator so far.                                                        */
+/* Diagnostics of the last finalize (which path consumed the rows): stats[0]=why the bucketed aggregation
+ * declined an input given under the distinct-keys hint (0 = it did not, 1 = a bucket overflowed its on-chip
+ * table, 2 = skewed keys: one bucket far longer than the average), [1]=rows pre-aggregated by the
+ * shared-memory hash table kernels, [2]=rows aggregated as raw rows (spilled, or all of them under the
+ * distinct-keys hint), [3]=partial rows merged, [4]=global table capacity (0: the bucketed aggregation
+ * produced the result, no table was built), [5]=kernels launched by this aggregator so far.               */
 int mgb_agg_stats(mgb_agg* agg, int64_t* stats6);
 
 /* Low-cardinality fast paths (one kernel launch + one 8-byte device->host read each).

@@ -1122,6 +1122,7 @@ extern "C" int mgb_agg_finalize(mgb_agg* a, int64_t* out_n_groups) {
         *out_n_groups = a->n_groups;
         return MGB_OK;
       }
+      a->stats[0] = overflow;   // why the bucketed path declined (1 = table overflow, 2 = skewed keys)
     }
   }
   // 1. read back the phase-1 counters (the only mid-flight synchronisation)

@@ -30,6 +30,7 @@
 #define BK_TARGET 512         // average rows per bucket (upper bound)
 #define BK_BIG 32             // groups with >= BK_BIG rows in a tile are folded by a whole warp
 #define BK_MAXA 8             // accumulators per value column handled in registers
+#define BK_SKEW_ROWS (64 * BK_TARGET)   // a longer bucket (one hot key) would serialise on one CTA: decline
 
 struct BktParams {
   const BktSource* srcs;      // device array
@@ -304,6 +305,17 @@ __global__ void __launch_bounds__(BK_THREADS) k_bucket_agg(const BktParams p) {
   if (tid == 0) p.gcount[b] = n_unique;
 }
 
+// longest bucket (skew check)
+__global__ void __launch_bounds__(256) k_bucket_max(const int64_t* __restrict__ off, int B, int* __restrict__ out) {
+  int m = 0;
+  for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (long long)gridDim.x * blockDim.x) {
+    const long long n = off[b + 1] - off[b];
+    m = max(m, (int)(n > 0x7fffffffLL ? 0x7fffffffLL : n));
+  }
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
 struct BktEmitCols {
   uint64_t* key[MGB_MAX_KEYS];
   uint64_t* acc[MGB_MAX_ACCS];
@@ -408,6 +420,24 @@ int mgb_bucket_aggregate(const Layout& L, const BktSource* srcs_host, int nsrc, 
     bk_debug("k_bucket_ids", st);
     status = mgb_radix_sort_perm_pid_ex(pid, T, B, perm, out->off, false, st);
     bk_debug("radix sort by bucket", st);
+    if (status == MGB_OK) {   // a hot key makes one bucket as long as its row count: leave that input to the table
+      const int gb = (B + 255) / 256;
+      k_bucket_max<<<gb > 1024 ? 1024 : gb, 256, 0, st>>>(out->off, B, d_err + 1);
+      int longest = 0;
+      cudaError_t e = cudaMemcpyAsync(&longest, d_err + 1, sizeof(int), cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) {
+        mgb_set_error("bucket aggregation: %s", cudaGetErrorString(e));
+        status = MGB_ERR_CUDA;
+      } else if (longest > BK_SKEW_ROWS) {
+        cudaFreeAsync(pid, st);
+        cudaFreeAsync(perm, st);
+        cudaFreeAsync(small, st);
+        mgb_bucket_free(out, st);
+        *overflow = 2;
+        return MGB_OK;
+      }
+    }
     if (status == MGB_OK) {
       BktParams p;
       p.srcs = d_srcs;

@@ -42,8 +42,8 @@ struct BktResult {
   long long G;                   // number of groups
 };
 
-// status MGB_OK with *overflow = 1 means: a bucket held more groups than its on-chip table (nothing was
-// produced; the caller takes the hash-table path)
+// status MGB_OK with *overflow != 0 means nothing was produced and the caller takes the hash-table path:
+// 1 = a bucket held more groups than its on-chip table, 2 = a bucket is far longer than the average (skewed keys)
 int mgb_bucket_aggregate(const Layout& L, const BktSource* srcs_host, int nsrc, long long T, cudaStream_t st,
                          BktResult* out, int* overflow);
 int mgb_bucket_emit(const Layout& L, const BktResult& r, uint64_t* const* out_key, uint64_t* const* out_acc,

@@ -187,6 +187,8 @@ _map_plans: Dict[Any, _MapPlan] = {}
 
 
 _map_plans_fast: Dict[Any, Any] = {}
+_DEVICE_RESULTS = os.environ.get("MGB_DEVICE_RESULTS", "1") not in ("0", "")
+_DEVICE_RESULT_ROWS = int(os.environ.get("MGB_DEVICE_RESULT_ROWS", "65536"))   # smaller results go straight to pandas
 _PREAGG_GROUPS = 2048     # chunks with at most this many groups are worth the shared-memory pre-aggregation
 
 
@@ -313,8 +315,8 @@ def _execute_agg_map(ctx, op):
         if plan.shape_key in _distinct_shapes:
             out_keys, out_accs, stats = _kernels.groupby_aggregate(keys, vals, list(plan.accs), sort=False,
                                                                    expect_distinct=True)
-            if stats and int(out_keys[0].numel()) <= _PREAGG_GROUPS:
-                _distinct_shapes.discard(plan.shape_key)
+            if stats and (int(out_keys[0].numel()) <= _PREAGG_GROUPS or stats.get("bucket_fallback") == 2):
+                _distinct_shapes.discard(plan.shape_key)   # few groups, or hot keys that pre-aggregation absorbs
         else:
             out_keys, out_accs, stats = _kernels.groupby_aggregate(keys, vals, list(plan.accs), sort=False)
             if stats and stats.get("rows_spilled", 0) * 2 > int(keys[0].numel()):
@@ -509,6 +511,12 @@ def _execute_agg_agg(ctx, op):
     if arrays is None:
         pieces, host_eval = post_columns(raw=False)
         labels_dev = list(pieces.keys())
+        if (not host_eval and _DEVICE_RESULTS and len(base) >= _DEVICE_RESULT_ROWS
+                and hasattr(_kernels, "to_host_concat")):
+            # large results stay in HBM; the D2H happens once, for all result chunks, at fetch time
+            ctx[out_chunk.key] = DeviceResult(labels_dev, [pieces[l] for l in labels_dev], base.index,
+                                              _result_meta(op, out_chunk, base.index_names, col_value))
+            return
         arrays = _to_host([pieces[l] for l in labels_dev] + list(base.index))
     host = dict(zip(labels_dev, arrays[:len(labels_dev)]))
     idx_arrays = arrays[len(labels_dev):]
@@ -518,32 +526,94 @@ def _execute_agg_agg(ctx, op):
             host[label] = np.asarray(p.func(*args, gpu=False))
         except TypeError:
             host[label] = np.asarray(p.func(*args))
-    names = base.index_names
+    ctx[out_chunk.key] = _assemble_result(host, idx_arrays, _result_meta(op, out_chunk, base.index_names, col_value))
+
+
+def _result_meta(op, out_chunk, index_names, col_value):
+    names = index_names
     out_names = getattr(out_chunk.index_value, "names", None) if out_chunk.index_value is not None else None
-    if out_names and len(out_names) == len(idx_arrays) and any(n is not None for n in out_names):
+    if out_names and len(out_names) == len(index_names) and any(n is not None for n in out_names):
         names = list(out_names)
+    return dict(names=list(names), col_value=col_value, two_level=col_value.nlevels > 1,
+                as_index=op.groupby_params.get("as_index", True), dtypes=getattr(out_chunk, "dtypes", None))
+
+
+def _assemble_result(host: Dict[Any, Any], idx_arrays, meta) -> pd.DataFrame:
+    """result frame from host arrays: labels / order / dtypes of the chunk meta (aggregation.py:1233-1267)"""
+    names, col_value = meta["names"], meta["col_value"]
     if len(idx_arrays) == 1:
-        index = pd.Index(idx_arrays[0], name=names[0] if names else None)
+        index = pd.Index(idx_arrays[0], name=names[0] if names else None, copy=False)
     else:
         index = _multi_index(idx_arrays, names)
     labels = list(host.keys())
-    as_index = op.groupby_params.get("as_index", True)
     result = None
-    if as_index and len(set(labels)) == len(labels) and set(labels) == set(col_value):
+    if meta["as_index"] and len(set(labels)) == len(labels) and set(labels) == set(col_value):
         # declared column order == a permutation of what was computed: assemble in that order, one block per
         # column and no consolidation copy (copy=False) -- the frame wraps the arrays that came off the device
         result = pd.DataFrame({i: host[l] for i, l in enumerate(col_value)}, index=index, copy=False)
         result.columns = col_value
     if result is None:
         result = pd.DataFrame({i: host[l] for i, l in enumerate(labels)}, index=index)
-        result.columns = pd.MultiIndex.from_tuples(labels) if two_level else pd.Index(labels)
-        if not as_index:
+        result.columns = pd.MultiIndex.from_tuples(labels) if meta["two_level"] else pd.Index(labels)
+        if not meta["as_index"]:
             result = result.reset_index()
         result = result.reindex(col_value, axis=1)
-    dtypes = getattr(out_chunk, "dtypes", None)
+    dtypes = meta["dtypes"]
     if dtypes is not None and len(result) == 0:
         result = result.astype(dtypes)
-    ctx[out_chunk.key] = result
+    return result
+
+
+class DeviceResult:
+    """Result chunk of a stage=agg operand that stays in HBM (what the reference's GPU mode produces: its
+    final chunks are cudf frames and the user calls ``.fetch().to_pandas()``, test_groupby_execution.py:788-793).
+    Frame-like for the processor's meta code (``shape`` / ``dtypes`` / ``index`` names, subtask/utils.py:62-68);
+    ``to_pandas()`` reads it back.  ``Session.fetch`` reads ALL result chunks into one pinned block and builds
+    the final frame without a host-side concat."""
+
+    __slots__ = ("labels", "columns", "index", "meta")
+
+    def __init__(self, labels, columns, index, meta):
+        self.labels, self.columns, self.index, self.meta = list(labels), list(columns), list(index), meta
+
+    def __len__(self):
+        return int(self.index[0].numel())
+
+    @property
+    def shape(self):
+        return (len(self), len(self.meta["col_value"]))
+
+    @property
+    def ndim(self):
+        return 2
+
+    @property
+    def dtypes(self):
+        return self.meta["dtypes"]
+
+    @property
+    def nbytes(self):
+        return sum(t.numel() * 8 for t in self.columns + self.index)
+
+    def __sizeof__(self):
+        return 64 + self.nbytes
+
+    def to_pandas(self) -> pd.DataFrame:
+        return DeviceResult.fetch_all([self])
+
+    @staticmethod
+    def fetch_all(parts: Sequence["DeviceResult"]) -> pd.DataFrame:
+        """row-wise concatenation of result chunks, assembled on the host in one pinned block"""
+        first = parts[0]
+        for p in parts[1:]:
+            if p.labels != first.labels or len(p.index) != len(first.index):
+                raise MarsGBError(1, "result chunks differ in their columns")
+        ncol = len(first.columns)
+        arrays = _kernels.to_host_concat([list(p.columns) + list(p.index) for p in parts])
+        return _assemble_result(dict(zip(first.labels, arrays[:ncol])), arrays[ncol:], first.meta)
+
+    def __repr__(self):
+        return f"DeviceResult(rows={len(self)}, columns={len(self.labels)})"
 
 
 def _multi_index(arrays, names):

@@ -171,7 +171,7 @@ class Aggregator:
         check(self._lib.mgb_agg_emit(self._h, _ptrs(keys), _ptrs(accs), 1 if sort else 0))
         st = (C.c_int64 * 6)()
         check(self._lib.mgb_agg_stats(self._h, st))
-        self.stats = dict(rows_tiny=st[0], rows_smem=st[1], rows_spilled=st[2], partial_rows=st[3],
+        self.stats = dict(bucket_fallback=st[0], rows_smem=st[1], rows_spilled=st[2], partial_rows=st[3],
                           table_capacity=st[4], launches=st[5])
         _count(st[5])
         return keys, accs
@@ -523,6 +523,31 @@ def to_host(columns: Sequence[torch.Tensor]):
     # the arrays are views of the pinned block (which they keep alive): no second pass over the result
     hn = host.numpy()
     return [hn[j, :n].view(np.float64) if c.dtype == torch.float64 else hn[j, :n] for j, c in enumerate(columns)]
+
+
+def to_host_concat(parts: Sequence[Sequence[torch.Tensor]]):
+    """Device -> host read of several row blocks that share their columns, concatenated row-wise on the way:
+    parts[i][j] is column j of block i.  One pinned block [columns, total rows], one asynchronous copy per
+    (block, column) straight to its final place, one synchronisation.  Returns one numpy array per column
+    (views of the pinned block)."""
+    import numpy as np
+
+    ncol = len(parts[0])
+    sizes = [int(p[0].numel()) if ncol else 0 for p in parts]
+    total = sum(sizes)
+    host = torch.empty((max(ncol, 1), max(total, 1)), dtype=torch.int64, pin_memory=True)
+    off = 0
+    for p, n in zip(parts, sizes):
+        for j, c in enumerate(p):
+            c = _req(c, f"column {j}")
+            if c.dtype != parts[0][j].dtype or int(c.numel()) != n:
+                raise MarsGBError(1, "result blocks differ in column dtype or length")
+            host[j, off:off + n].view(c.dtype).copy_(c, non_blocking=True)
+        off += n
+    torch.cuda.current_stream().synchronize()
+    hn = host.numpy()
+    return [hn[j, :total].view(np.float64) if c.dtype == torch.float64 else hn[j, :total]
+            for j, c in enumerate(parts[0])]
 
 
 # ------------------------------------------------------------------------------------------------- post

@@ -235,7 +235,14 @@ class Session:
             if self.world == 1:
                 parts.append(self._results[c.key])
             else:
-                parts.append(self.exchange.fetch_result(self._results.get(c.key), self._owners[c.key]))
+                obj = self._results.get(c.key)
+                if obj is not None and not isinstance(obj, pd.DataFrame):
+                    obj = obj.to_pandas()         # device-resident result chunk: read back on its owner
+                parts.append(self.exchange.fetch_result(obj, self._owners[c.key]))
+        from .executors import DeviceResult
+
+        if parts and all(isinstance(p, DeviceResult) for p in parts):
+            return DeviceResult.fetch_all(parts)      # one pinned block, no host-side concat
         parts = [p if isinstance(p, pd.DataFrame) else p.to_pandas() for p in parts]
         return parts[0] if len(parts) == 1 else pd.concat(parts, axis=0)
 

@@ -79,3 +79,12 @@ for e in api:
 print("host CUDA API time:")
 for name, (d, c) in sorted(by_api.items(), key=lambda kv: -kv[1][0])[:15]:
     print(f"  {d / 1e3:9.2f} ms {c:6d} x  {name}")
+if os.environ.get("PYPROF"):
+    import cProfile
+    import pstats
+
+    pr = cProfile.Profile()
+    pr.enable()
+    once()
+    pr.disable()
+    pstats.Stats(pr).sort_stats("tottime").print_stats(30)

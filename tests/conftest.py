@@ -77,6 +77,8 @@ def load_golden(name) -> Golden:
 def assert_frames_match(got: pd.DataFrame, exp: pd.DataFrame, sort_index: bool, rtol=1e-9):
     """Parity bar of BASELINE.json: group keys / counts / min / max bit-exact, float64 sum / mean / var within
     1e-9 relative; same column labels, order and dtypes."""
+    if not isinstance(got, pd.DataFrame):
+        got = got.to_pandas()                 # device-resident result chunk (executors.DeviceResult)
     if sort_index:
         got, exp = got.sort_index(), exp.sort_index()
     assert list(got.columns) == list(exp.columns), (list(got.columns), list(exp.columns))

@@ -68,7 +68,7 @@ def groupby_aggregate(keys, vals, accs, sort=False, expect_distinct=False):
     karr = [idx.get_level_values(j).to_numpy() for j in range(len(keys))]
     return ([torch.from_numpy(np.ascontiguousarray(k)) for k in karr],
             [torch.from_numpy(np.ascontiguousarray(r.to_numpy())) for r in outs],
-            dict(rows_tiny=0, rows_smem=0, rows_spilled=0, partial_rows=0, table_capacity=0, launches=0))
+            dict(bucket_fallback=0, rows_smem=0, rows_spilled=0, partial_rows=0, table_capacity=0, launches=0))
 
 
 class Aggregator:

@@ -381,7 +381,7 @@ def test_aggregate_with_distinct_keys_hint_skips_preaggregation(K, plain):
     rng = np.random.default_rng(31)
     n = 300_000
     keys = [rng.integers(-2 ** 62, 2 ** 62, n, dtype=np.int64)]
-    keys[0][::7] = keys[0][0]          # some duplicates all the same
+    keys[0][::13] = keys[0][0]         # some duplicates all the same (one bucket of many tiles)
     vals = [rng.normal(0, 1, n), rng.random(n)]
     vals[1][rng.random(n) < 0.1] = np.nan
     accs = [(0, "sum"), (1, "sum"), (0, "count"), (1, "count")] + ([] if plain else [(1, "min"), (0, "max"), (0, "sumsq")])
@@ -437,13 +437,13 @@ def test_bucketed_aggregation_wide_min_max_var_shape(K):
 
 
 def test_bucketed_aggregation_skew_and_merge_ops(K):
-    """one key holds a third of the rows (a bucket of many tiles, folded by warps, merged across tiles);
+    """one key holds 4 % of the rows (a bucket of many tiles, folded by warps, merged across tiles);
     reducer-side merge shape: int64 count partials summed, float64 min / max partials with NaN = no value"""
     rng = np.random.default_rng(45)
     n = 600_000
     k = rng.integers(0, 200_000, n, dtype=np.int64)
-    k[rng.random(n) < 0.33] = 77
-    s = rng.normal(0, 1, n)
+    k[rng.random(n) < 0.04] = 77
+    s = rng.normal(10, 3, n)         # positive mean: the hot key's sum must not cancel (1e-9 relative bar)
     c = rng.integers(0, 50, n, dtype=np.int64)
     mn = rng.random(n)
     mn[rng.random(n) < 0.3] = np.nan
@@ -451,6 +451,17 @@ def test_bucketed_aggregation_skew_and_merge_ops(K):
     accs = [(0, "sum"), (1, "sum"), (2, "min"), (2, "max")]
     stats = check_agg(K, [k], [s, c, mn], accs, batches=16, distinct=True)
     assert _bucketed(stats), stats
+
+
+def test_bucketed_aggregation_declines_heavily_skewed_keys(K):
+    """a key with a third of the rows would serialise its bucket on one CTA: the input goes to the hash table
+    and the statistics say why (the executors then stop giving the hint for this shape)"""
+    rng = np.random.default_rng(47)
+    n = 600_000
+    k = rng.integers(0, 200_000, n, dtype=np.int64)
+    k[rng.random(n) < 0.33] = 77
+    stats = check_agg(K, [k], [rng.normal(10, 3, n)], [(0, "sum"), (0, "count"), (0, "min")], distinct=True)
+    assert stats["bucket_fallback"] == 2 and stats["table_capacity"] > 0
 
 
 def test_bucketed_aggregation_overflow_falls_back_to_the_table(K):
@@ -461,11 +472,13 @@ def test_bucketed_aggregation_overflow_falls_back_to_the_table(K):
     chosen = cand[(h >> np.uint64(64 - 9)) == 0][:2000]
     assert len(chosen) == 2000
     rng = np.random.default_rng(46)
-    keys = [np.repeat(chosen, 100)]            # 200k rows -> 512 buckets, every row in bucket 0
+    # 200k rows -> 512 buckets; bucket 0 gets 2000 groups x 15 rows (more groups than its table, fewer rows
+    # than the skew limit), the other rows spread evenly
+    keys = [np.concatenate([np.repeat(chosen, 15), rng.integers(10_000_000, 20_000_000, 170_000, dtype=np.int64)])]
     rng.shuffle(keys[0])
     vals = [rng.random(len(keys[0]))]
     stats = check_agg(K, keys, vals, [(0, "sum"), (0, "count"), (0, "max")], distinct=True)
-    assert stats["table_capacity"] > 0
+    assert stats["table_capacity"] > 0 and stats["bucket_fallback"] == 1
 
 
 @pytest.mark.parametrize("n_keys", [1, 2])

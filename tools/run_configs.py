@@ -8,8 +8,10 @@ wait for host random numbers; every run ends with size-independent checks (the o
 these sizes; exact parity at oracle-sized inputs is what tests/ does):
   sum of counts == rows, keys unique, sum of sums == column total (1e-9), min <= max, groups == distinct keys
   computed independently with torch.unique on the raw keys.
-Prints one JSON line per config: rows/s with the chunks resident in HBM (whole operand chain incl. the fetch of
-the result frame), the plan taken, the number of groups.
+Prints one JSON line per config: rows/s with the chunks resident in HBM -- `rows_per_s` over the whole operand
+chain INCLUDING the fetch of the result frame to the host, `execute_rows_per_s` over the operand chain alone
+(device-resident in -> result chunks out; large result chunks stay in HBM until the fetch) --, the plan taken,
+the number of groups.
 """
 import argparse
 import json
@@ -79,7 +81,7 @@ def run(cfg, scale, repeats):
         frames.append(DeviceFrame([], None, list(cols.keys()), list(cols.values()), min(chunk, n - s)))
     torch.cuda.synchronize()
     by_list = [by] if isinstance(by, str) else by
-    times = []
+    times, exec_times = [], []
     out = None
     for it in range(repeats + 1):
         sess = md.new_session(default=False)
@@ -87,10 +89,13 @@ def run(cfg, scale, repeats):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         r.execute(session=sess)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
         out = r.fetch(session=sess)
         torch.cuda.synchronize()
         if it:
             times.append(time.perf_counter() - t0)
+            exec_times.append(t1 - t0)
     # size-independent checks
     vcol = [c for c in frames[0].columns if c not in by_list][0]
     checks = {}
@@ -122,7 +127,8 @@ def run(cfg, scale, repeats):
         checks["sorted"] = bool(out.index.is_monotonic_increasing)
     print(json.dumps({"config": cfg, "scale": scale, "rows": n, "chunks": len(frames), "groups": int(len(out)),
                       "result_chunks": len(r.data.chunks), "plan": sorted(set(sess.executed_ops)),
-                      "seconds": times, "rows_per_s": n / min(times), "checks": checks,
+                      "seconds": times, "rows_per_s": n / min(times),
+                      "execute_seconds": exec_times, "execute_rows_per_s": n / min(exec_times), "checks": checks,
                       "all_checks_pass": all(checks.values())}), flush=True)
     del frames, out
     torch.cuda.empty_cache()
