@@ -30,6 +30,10 @@
 #define BK_TARGET 512         // average rows per bucket (upper bound)
 #define BK_BIG 32             // groups with >= BK_BIG rows in a tile are folded by a whole warp
 #define BK_MAXA 8             // accumulators per value column handled in registers
+// Inputs larger than this are first moved into coarse bucket order.  Measured on B200 (profiles/README.md): the
+// move makes k_bucket_agg 17-26 % faster (its gathers become L2-resident) but costs more than that saves
+// (0.55 ms per 15.6 M two-column rows, 2.4 ms per 7.8 M ten-column rows), so it is off unless asked for.
+#define BK_MOVE_BYTES_DEFAULT 0x7fffffffffffffffLL
 #define BK_SKEW_ROWS (64 * BK_TARGET)   // a longer bucket (one hot key) would serialise on one CTA: decline
 
 struct BktParams {
@@ -44,7 +48,6 @@ struct BktParams {
   uint64_t* scratch;
   int64_t* gcount;
   int* err;
-  int stage;                  // debug: stop after this step of the first tile (0 = run everything)
   Layout L;
 };
 
@@ -153,7 +156,8 @@ __global__ void __launch_bounds__(BK_THREADS) k_bucket_agg(const BktParams p) {
   __shared__ uint16_t r_src[BK_RT];
   __shared__ uint16_t sorted[BK_RT];
   __shared__ int warp_tot[BK_THREADS / 32];
-  __shared__ int n_unique, failed;
+  __shared__ int big[BK_RT / BK_BIG];   // groups with >= BK_BIG rows in the current tile
+  __shared__ int n_unique, failed, n_big;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long b = blockIdx.x;
@@ -176,6 +180,7 @@ __global__ void __launch_bounds__(BK_THREADS) k_bucket_agg(const BktParams p) {
     const int m = (int)((hi - tlo) < BK_RT ? (hi - tlo) : BK_RT);
     const int ng_before = n_unique;
     for (int i = tid; i <= BK_TAB; i += BK_THREADS) cnt[i] = 0;
+    if (tid == 0) n_big = 0;
     __syncthreads();
     // 1. rows of the tile: key gather, group id, histogram by group
     for (int r0 = 0; r0 < m; r0 += BK_THREADS) {   // uniform trip count: the table insert votes per warp
@@ -217,7 +222,6 @@ __global__ void __launch_bounds__(BK_THREADS) k_bucket_agg(const BktParams p) {
       if (tid == 0) atomicExch(p.err, 1);
       return;
     }
-    if (p.stage == 1) return;
     const int ng = n_unique;
     // 2. exclusive scan of cnt[0..ng) (4 entries per thread)
     {
@@ -227,6 +231,10 @@ __global__ void __launch_bounds__(BK_THREADS) k_bucket_agg(const BktParams p) {
       int v2 = base + 2 < ng ? cnt[base + 2] : 0;
       int v3 = base + 3 < ng ? cnt[base + 3] : 0;
       const int tot = v0 + v1 + v2 + v3;
+      if (v0 >= BK_BIG) big[atomicAdd(&n_big, 1)] = base + 0;
+      if (v1 >= BK_BIG) big[atomicAdd(&n_big, 1)] = base + 1;
+      if (v2 >= BK_BIG) big[atomicAdd(&n_big, 1)] = base + 2;
+      if (v3 >= BK_BIG) big[atomicAdd(&n_big, 1)] = base + 3;
       int x = tot;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
@@ -245,20 +253,26 @@ __global__ void __launch_bounds__(BK_THREADS) k_bucket_agg(const BktParams p) {
       if (tid == 0) cnt[ng] = m;
     }
     __syncthreads();
-    if (p.stage == 2) return;
     // 3. counting sort of the tile's rows by group
     for (int r = tid; r < m; r += BK_THREADS) sorted[atomicAdd(&cursor[r_gid[r]], 1)] = (uint16_t)r;
     __syncthreads();
-    if (p.stage == 3) return;
     // 4. fold: one (group, value column) per thread / per warp
-    const int n_items = ng * nv;
-    for (int pass = 0; pass < (p.stage == 4 ? 1 : 2); ++pass) {
+    // pass 0: one thread per (group, column) with < BK_BIG rows; pass 1: one warp per (big group, column)
+    const int nb = n_big;
+    const uint32_t inv_ng = 0xffffffffu / (uint32_t)ng + 1u;   // idx / ng == umulhi(idx, inv_ng) for idx < 2^22
+    for (int pass = 0; pass < 2; ++pass) {
+      if (pass == 1 && nb == 0) break;
+      const int n_items = (pass == 0 ? ng : nb) * nv;
+      const int per = pass == 0 ? ng : nb;
+      const uint32_t inv = pass == 0 ? inv_ng : 0xffffffffu / (uint32_t)nb + 1u;
       const int first = pass == 0 ? tid : warp;
       const int step = pass == 0 ? BK_THREADS : BK_THREADS / 32;
       for (int idx = first; idx < n_items; idx += step) {
-        const int c = idx / ng, g = idx - c * ng;
+        const int c = per == 1 ? idx : (int)__umulhi((uint32_t)idx, inv);
+        const int gi = idx - c * per;
+        const int g = pass == 0 ? gi : big[gi];
         const int st = cnt[g], n = cnt[g + 1] - st;
-        if (n == 0 || (pass == 0) != (n < BK_BIG)) continue;
+        if (n == 0 || (pass == 0 && n >= BK_BIG)) continue;
         const int a0 = L.col_begin[c], na_c = L.col_begin[c + 1] - a0;
         if (na_c == 0) continue;
         const int dt = L.acc[a0].dt;
@@ -357,6 +371,14 @@ void mgb_bucket_free(BktResult* r, cudaStream_t st) {
   r->goff = nullptr;
 }
 
+static long long g_move_bytes = BK_MOVE_BYTES_DEFAULT;
+
+extern "C" int mgb_set_tuning(int32_t key, int64_t value) {
+  MGB_REQUIRE(key == MGB_TUNE_BUCKET_MOVE_BYTES, MGB_ERR_INVALID, "unknown tuning key %d", key);
+  g_move_bytes = value < 0 ? BK_MOVE_BYTES_DEFAULT : (long long)value;
+  return MGB_OK;
+}
+
 static void bk_debug(const char* what, cudaStream_t st) {
   static int on = -1;
   if (on < 0) {
@@ -385,7 +407,8 @@ int mgb_bucket_aggregate(const Layout& L, const BktSource* srcs_host, int nsrc, 
   const size_t src_bytes = sizeof(BktSource) * (size_t)nsrc;
   const size_t begin_bytes = sizeof(long long) * ((size_t)nsrc + 1);
   const size_t src_pad = (src_bytes + 255) & ~(size_t)255, begin_pad = (begin_bytes + 255) & ~(size_t)255;
-  int32_t *pid = nullptr, *perm = nullptr;
+  int32_t *pid = nullptr, *perm = nullptr, *pid2 = nullptr;
+  uint64_t* moved = nullptr;
   MGB_CUDA(cudaMallocAsync((void**)&small, src_pad + begin_pad + 256, st));
   MGB_CUDA(cudaMallocAsync((void**)&pid, sizeof(int32_t) * (size_t)T, st));
   MGB_CUDA(cudaMallocAsync((void**)&perm, sizeof(int32_t) * (size_t)T, st));
@@ -418,7 +441,20 @@ int mgb_bucket_aggregate(const Layout& L, const BktSource* srcs_host, int nsrc, 
       k_bucket_ids<2><<<grid, 256, 0, st>>>(d_srcs, d_begin, srcs_host[0], nsrc, T, logB, pid);
     MGB_CHECK_LAUNCH();
     bk_debug("k_bucket_ids", st);
-    status = mgb_radix_sort_perm_pid_ex(pid, T, B, perm, out->off, false, st);
+    // Inputs larger than L2: first move the rows (all columns) into the order of the top 8 bits of the bucket
+    // id -- sequential reads, 256 write streams that L2 combines.  The per-bucket gathers below then stay
+    // inside one coarse range (a few MB, shared by the CTAs that run at the same time) instead of touching a
+    // random 64-byte DRAM burst per 8-byte value.
+    const int32_t* pid_sorted_src = pid;
+    if ((long long)(L.nk + L.nv) * 8 * T > g_move_bytes && logB > 0) {
+      MGB_CUDA(cudaMallocAsync((void**)&moved, sizeof(uint64_t) * (size_t)(L.nk + L.nv) * (size_t)T, st));
+      MGB_CUDA(cudaMallocAsync((void**)&pid2, sizeof(int32_t) * (size_t)T, st));
+      status = mgb_radix_move_sources(pid, T, logB > 8 ? logB - 8 : 0, d_srcs, d_begin, srcs_host[0], nsrc, L.nk, L.nv,
+                                      moved, pid2, st);
+      bk_debug("move rows to coarse bucket order", st);
+      pid_sorted_src = pid2;
+    }
+    if (status == MGB_OK) status = mgb_radix_sort_perm_pid_ex(pid_sorted_src, T, B, perm, out->off, false, st);
     bk_debug("radix sort by bucket", st);
     if (status == MGB_OK) {   // a hot key makes one bucket as long as its row count: leave that input to the table
       const int gb = (B + 255) / 256;
@@ -433,6 +469,8 @@ int mgb_bucket_aggregate(const Layout& L, const BktSource* srcs_host, int nsrc, 
         cudaFreeAsync(pid, st);
         cudaFreeAsync(perm, st);
         cudaFreeAsync(small, st);
+        if (moved) cudaFreeAsync(moved, st);
+        if (pid2) cudaFreeAsync(pid2, st);
         mgb_bucket_free(out, st);
         *overflow = 2;
         return MGB_OK;
@@ -444,6 +482,12 @@ int mgb_bucket_aggregate(const Layout& L, const BktSource* srcs_host, int nsrc, 
       p.begin = d_begin;
       p.src0 = srcs_host[0];
       p.nsrc = nsrc;
+      if (moved) {   // the moved copy is ONE source
+        memset(&p.src0, 0, sizeof(p.src0));
+        for (int j = 0; j < L.nk; ++j) p.src0.keys[j] = moved + (size_t)j * (size_t)T;
+        for (int c = 0; c < L.nv; ++c) p.src0.vals[c] = moved + (size_t)(L.nk + c) * (size_t)T;
+        p.nsrc = 1;
+      }
       p.T = T;
       p.logB = logB;
       p.perm = perm;
@@ -451,10 +495,6 @@ int mgb_bucket_aggregate(const Layout& L, const BktSource* srcs_host, int nsrc, 
       p.scratch = out->scratch;
       p.gcount = out->goff;
       p.err = d_err;
-      {
-        const char* e = getenv("MGB_BUCKET_STAGE");
-        p.stage = e ? atoi(e) : 0;
-      }
       p.L = L;
       if (L.nk == 1)
         k_bucket_agg<1><<<(unsigned)B, BK_THREADS, 0, st>>>(p);
@@ -484,6 +524,8 @@ int mgb_bucket_aggregate(const Layout& L, const BktSource* srcs_host, int nsrc, 
   cudaFreeAsync(pid, st);
   cudaFreeAsync(perm, st);
   cudaFreeAsync(small, st);
+  if (moved) cudaFreeAsync(moved, st);
+  if (pid2) cudaFreeAsync(pid2, st);
   if (status != MGB_OK || err_h) {
     mgb_bucket_free(out, st);
     *overflow = err_h ? 1 : 0;

@@ -22,6 +22,8 @@ else:
     vals = [torch.randn(n, generator=g, device="cuda", dtype=torch.float64) * 3 + 10 for _ in range(8)]
     accs = [(c, o) for o in (K.MIN, K.MAX, K.SUM, K.SUMSQ, K.COUNT) for c in range(8)]
 lib = _lib.load()
+if __import__("os").environ.get("MOVE_BYTES"):
+    K.set_tuning(K.TUNE_BUCKET_MOVE_BYTES, int(__import__("os").environ["MOVE_BYTES"]))
 for it in range(4):
     if it == 3:
         lib.mgb_prof_enable(1)
@@ -38,3 +40,22 @@ for kid, name in enumerate(["dense", "preagg", "merge", "update_global", "table_
     lib.mgb_prof_read(kid, C.byref(tot), C.byref(c))
     if c.value:
         print(f"    {name:14s} {tot.value:8.3f} ms / {c.value}")
+if __import__("os").environ.get("TIMELINE"):
+    import collections
+    import json
+
+    from torch.profiler import ProfilerActivity, profile
+
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        K.groupby_aggregate(keys, vals, accs, sort=False, expect_distinct=True)
+        torch.cuda.synchronize()
+    prof.export_chrome_trace("/tmp/prof_bucket_trace.json")
+    ev = json.load(open("/tmp/prof_bucket_trace.json"))["traceEvents"]
+    by = collections.defaultdict(lambda: [0.0, 0])
+    for e in ev:
+        if e.get("ph") == "X" and e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset"):
+            nm = e["name"].split("(")[0].split("<")[0]
+            by[nm][0] += e["dur"]
+            by[nm][1] += 1
+    for nm, (d, c) in sorted(by.items(), key=lambda kv: -kv[1][0]):
+        print(f"    {d:9.1f} us {c:4d} x {nm}")
