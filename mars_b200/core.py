@@ -186,8 +186,15 @@ def execute(results: Dict, op: Operand):
     class's own ``execute``."""
     op.pre_execute()
     try:
-        for cls in type(op).__mro__:
-            executor = Operand._op_type_to_executor.get(cls)
+        registry = Operand._op_type_to_executor
+        executor = registry.get(type(op))
+        if executor is not None:          # the common case: an executor registered for the exact class
+            try:
+                return executor(results, op)
+            except NotImplementedError:
+                pass
+        for cls in type(op).__mro__[1:]:
+            executor = registry.get(cls)
             if executor is None:
                 continue
             try:

@@ -313,19 +313,27 @@ __global__ void __launch_bounds__(SM_THREADS, 1) k_merge_small(const SmallParams
   for (int i = threadIdx.x; i < tsize; i += SM_THREADS) tab_idx[i] = -1;
   __syncthreads();
   // pass 1: output row of every input row
-  for (int it = threadIdx.x; it < total; it += SM_THREADS) {
-    int pc = 0;
-    while (it >= pstart[pc + 1]) ++pc;
-    const int r = it - pstart[pc];
+  for (int it0 = 0; it0 < total; it0 += SM_THREADS) {   // uniform trip count: the insert votes per warp
+    const int it = it0 + (int)threadIdx.x;
+    const bool valid = it < total;
+    int pc = 0, r = 0;
     uint64_t k[NK];
 #pragma unroll
-    for (int j = 0; j < NK; ++j) k[j] = ld_cg(p.piece[pc].key[j] + r);
-    const int idx = small_find_or_insert<NK>(tab_keys, tab_idx, n_unique, k, tmask);
-    item_idx[it] = idx;
-    item_r[it] = r;
-    item_pc[it] = (unsigned char)pc;
+    for (int j = 0; j < NK; ++j) k[j] = 0;
+    if (valid) {
+      while (it >= pstart[pc + 1]) ++pc;
+      r = it - pstart[pc];
 #pragma unroll
-    for (int j = 0; j < NK; ++j) ukeys[j * MAXR + idx] = k[j];   // same value from every writer
+      for (int j = 0; j < NK; ++j) k[j] = ld_cg(p.piece[pc].key[j] + r);
+    }
+    const int idx = small_find_or_insert<NK>(tab_keys, tab_idx, n_unique, valid, k, tmask);
+    if (valid) {
+      item_idx[it] = idx;
+      item_r[it] = r;
+      item_pc[it] = (unsigned char)pc;
+#pragma unroll
+      for (int j = 0; j < NK; ++j) ukeys[j * MAXR + idx] = k[j];   // same value from every writer
+    }
   }
   __syncthreads();
   const int nu = *n_unique;

@@ -31,29 +31,44 @@ __device__ __forceinline__ uint32_t small_hash(const uint64_t* k) {
 
 // Insert-or-find a key tuple in the CTA's table.  tab_idx[slot] = -1 empty, -2 being written, >= 0 dense row.
 // Keys are published before the index (threadfence_block) so readers that see idx >= 0 see the keys.
+// Called by ALL lanes of a warp together (`valid` = this lane has a key): a lane that meets a slot in the
+// "being written" state does not spin on it -- the writer may be a lane of its own warp, parked at a
+// reconvergence point -- it looks again in the next round, after the warp has reconverged at the vote.
 template <int NK>
-__device__ __forceinline__ int small_find_or_insert(uint64_t* tab_keys, int* tab_idx, int* n_unique,
+__device__ __forceinline__ int small_find_or_insert(uint64_t* tab_keys, int* tab_idx, int* n_unique, bool valid,
                                                     const uint64_t* k, uint32_t mask = SM_TAB - 1) {
   uint32_t s = small_hash<NK>(k) & mask;
-  for (uint32_t probe = 0; probe <= mask; ++probe, s = (s + 1) & mask) {
-    int cur = *(volatile int*)&tab_idx[s];
-    if (cur == -1) {
-      cur = atomicCAS(&tab_idx[s], -1, -2);
+  bool done = !valid;
+  int idx = -1;
+  uint32_t probe = 0;
+  while (__any_sync(0xffffffffu, !done)) {
+    if (!done) {
+      int cur = *(volatile int*)&tab_idx[s];
       if (cur == -1) {
-        tab_keys[s] = k[0];
-        if (NK == 2) tab_keys[SM_TAB + s] = k[1];
-        const int idx = atomicAdd(n_unique, 1);
-        __threadfence_block();
-        *(volatile int*)&tab_idx[s] = idx;
-        return idx;
+        cur = atomicCAS(&tab_idx[s], -1, -2);
+        if (cur == -1) {
+          tab_keys[s] = k[0];
+          if (NK == 2) tab_keys[SM_TAB + s] = k[1];
+          idx = atomicAdd(n_unique, 1);
+          __threadfence_block();
+          *(volatile int*)&tab_idx[s] = idx;
+          done = true;
+        }
+      }
+      if (!done && cur != -2) {   // cur == -2: the writer publishes within its round, look again
+        bool eq = ((volatile uint64_t*)tab_keys)[s] == k[0];
+        if (NK == 2) eq = eq && ((volatile uint64_t*)tab_keys)[SM_TAB + s] == k[1];
+        if (eq) {
+          idx = cur;
+          done = true;
+        } else {
+          s = (s + 1) & mask;
+          if (++probe > mask) done = true;   // table full (callers size it at >= 2x the rows)
+        }
       }
     }
-    while (cur == -2) cur = *(volatile int*)&tab_idx[s];   // writer is a few instructions from publishing
-    bool eq = ((volatile uint64_t*)tab_keys)[s] == k[0];
-    if (NK == 2) eq = eq && ((volatile uint64_t*)tab_keys)[SM_TAB + s] == k[1];
-    if (eq) return cur;
   }
-  return -1;
+  return idx;
 }
 
 __device__ __forceinline__ void out_init(const OutCols& o, int rows) {
@@ -639,15 +654,23 @@ __global__ void __launch_bounds__(THREADS, 1) k_preagg_dense(const DenseParams p
   const int total = *n_items;
   if (p.dbg && threadIdx.x == 0) p.dbg[gridDim.x * 4 + 2] = dense_now();
   // pass 1: dense output row of every staged row (shared-memory hash table on the key tuple)
-  for (int it = threadIdx.x; it < total; it += DN_THREADS) {
-    const int icta = items[it] / GC, ir = items[it] - icta * GC;
+  for (int it0 = 0; it0 < total; it0 += DN_THREADS) {   // uniform trip count: the insert votes per warp
+    const int it = it0 + (int)threadIdx.x;
+    const bool valid = it < total;
     uint64_t k[NK];
 #pragma unroll
-    for (int j = 0; j < NK; ++j) k[j] = ld_cg(STG(icta, ir, j));
-    const int idx = small_find_or_insert<NK>(tab_keys, tab_idx, n_unique, k);
-    item_idx[it] = idx;
+    for (int j = 0; j < NK; ++j) k[j] = 0;
+    if (valid) {
+      const int icta = items[it] / GC, ir = items[it] - icta * GC;
 #pragma unroll
-    for (int j = 0; j < NK; ++j) p.out.key[j][idx] = k[j];   // same value from every writer
+      for (int j = 0; j < NK; ++j) k[j] = ld_cg(STG(icta, ir, j));
+    }
+    const int idx = small_find_or_insert<NK>(tab_keys, tab_idx, n_unique, valid, k);
+    if (valid) {
+      item_idx[it] = idx;
+#pragma unroll
+      for (int j = 0; j < NK; ++j) p.out.key[j][idx] = k[j];   // same value from every writer
+    }
   }
   __syncthreads();
   const int nu = *n_unique;

@@ -384,7 +384,15 @@ class DataFrame:
         if gpu is None:
             gpu = resident
         dtypes = first.dtypes
-        columns = pd.Index(list(first.columns))
+        try:
+            ckey = tuple(first.columns)
+            columns = _columns_cache.get(ckey)
+        except TypeError:
+            ckey, columns = None, None
+        if columns is None:
+            columns = pd.Index(list(first.columns))
+            if ckey is not None:
+                _columns_cache[ckey] = columns
         n = sum(len(c) for c in chunks)
         op = DataFrameDataSource(gpu=gpu)
         cv = IndexValue(columns)
@@ -462,6 +470,9 @@ class DataFrame:
 
 
 _mock_cache: Dict[Any, Any] = {}
+_mock_fast: Dict[Any, Any] = {}       # keyed on the identity of the (cached) dtypes Series
+_columns_cache: Dict[Any, Any] = {}
+_mock_meta: Dict[int, Any] = {}       # per cached mock frame: what agg() reads from it
 
 
 class DataFrameGroupBy:
@@ -492,6 +503,24 @@ class DataFrameGroupBy:
         """schema inference by running real pandas on a small mock frame (reference: build_mock_agg_result,
         aggregation.py:142-161)"""
         dtypes = self.df.dtypes
+        fast_key = None
+        try:   # same schema object, same call as before: no string building at all
+            fast_key = (id(dtypes), tuple(self.by), self.as_index, self.sort,
+                        None if self.selection is None else tuple(self.selection),
+                        id(func) if isinstance(func, (dict, list)) else func, tuple(sorted(kw.items())))
+            hit = _mock_fast.get(fast_key)
+            if hit is not None and hit[0] is dtypes and (hit[1] is func or hit[1] == func):
+                return hit[2]
+        except TypeError:
+            fast_key = None
+        out = self._mock_result_slow(func, dtypes, **kw)
+        if fast_key is not None:
+            if len(_mock_fast) > 256:
+                _mock_fast.clear()
+            _mock_fast[fast_key] = (dtypes, func, out)
+        return out
+
+    def _mock_result_slow(self, func, dtypes, **kw) -> pd.DataFrame:
         try:   # the mock only depends on the schema and the call: cache it (graph building stays cheap)
             cache_key = (tuple((str(c), str(dt)) for c, dt in dtypes.items()), tuple(map(str, self.by)), self.as_index,
                          self.sort, None if self.selection is None else tuple(map(str, self.selection)), repr(func),
@@ -533,9 +562,15 @@ class DataFrameGroupBy:
         mock = self._mock_result(func, **kw)
         if isinstance(mock, pd.Series):
             raise NotImplementedError("series-valued aggregation results are outside the GPU path")
-        op.index_levels = mock.index.nlevels
-        t = op.new_tileable([self.df.data], shape=(np.nan, mock.shape[1]), dtypes=mock.dtypes,
-                            index_value=IndexValue(mock.index[:0]), columns_value=IndexValue(mock.columns))
+        meta = _mock_meta.get(id(mock))
+        if meta is None or meta[0] is not mock:
+            if len(_mock_meta) > 256:
+                _mock_meta.clear()
+            meta = _mock_meta[id(mock)] = (mock, mock.index.nlevels, mock.shape[1], mock.dtypes, mock.index[:0],
+                                           mock.columns)
+        op.index_levels = meta[1]
+        t = op.new_tileable([self.df.data], shape=(np.nan, meta[2]), dtypes=meta[3],
+                            index_value=IndexValue(meta[4]), columns_value=IndexValue(meta[5]))
         return DataFrame(None, _tileable=t)
 
     aggregate = agg

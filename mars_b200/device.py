@@ -111,6 +111,9 @@ class Pending:
         return self.value
 
 
+_dtypes_cache: dict = {}
+
+
 class DeviceFrame:
     __slots__ = ("index_names", "_index", "columns", "_data", "_n", "_pending", "_slot", "_home", "__weakref__")
 
@@ -218,7 +221,19 @@ class DeviceFrame:
 
     @property
     def dtypes(self):
-        return pd.Series([np.dtype(str(t.dtype).replace("torch.", "")) for t in self._data], index=self.columns)
+        # one Series object per schema: graph building looks at it for every chunk and caches on its identity
+        try:
+            key = (tuple(self.columns), tuple(t.dtype for t in self._data))
+            hit = _dtypes_cache.get(key)
+        except TypeError:
+            key, hit = None, None
+        if hit is None:
+            hit = pd.Series([np.dtype(str(t.dtype).replace("torch.", "")) for t in self._data], index=self.columns)
+            if key is not None:
+                if len(_dtypes_cache) > 256:
+                    _dtypes_cache.clear()
+                _dtypes_cache[key] = hit
+        return hit
 
     @property
     def nbytes(self) -> int:

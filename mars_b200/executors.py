@@ -172,15 +172,20 @@ def _plan_steps(op, value_cols) -> List[_Step]:
 # ----------------------------------------------------------------------------------------------------
 class _MapPlan:
     """Everything of a stage=map call that only depends on the operand's functions and the chunk schema."""
-    __slots__ = ("by", "key_pos", "used", "val_pos", "accs", "slots", "shape_key")
+    __slots__ = ("by", "key_pos", "used", "val_pos", "accs", "slots", "shape_key", "_by_dtypes")
 
-    def count_only_int(self, frame) -> Tuple[int, ...]:
-        """positions (in `used`) of int64 value columns whose only accumulators are COUNTs"""
-        out = []
-        for j, i in enumerate(self.val_pos):
-            if frame.col_dtype(i) == torch.int64 and all(op == K.COUNT for c, op in self.accs if c == j):
-                out.append(j)
-        return tuple(out)
+    def for_dtypes(self, frame):
+        """per column-dtype signature of the chunk: (keys are int64?, positions (in `used`) of int64 value
+        columns whose only accumulators are COUNTs, dtype codes of the value columns)"""
+        sig = tuple(t.dtype for t in frame.raw_data)
+        hit = self._by_dtypes.get(sig)
+        if hit is None:
+            keys_ok = all(sig[i] == torch.int64 for i in self.key_pos)
+            skip = tuple(j for j, i in enumerate(self.val_pos)
+                         if sig[i] == torch.int64 and all(op == K.COUNT for c, op in self.accs if c == j))
+            dts = [K.F64 if sig[i] == torch.float64 else K.I64 for i in self.val_pos]
+            hit = self._by_dtypes[sig] = (keys_ok, skip, dts)
+        return hit
 
 
 _map_plans: Dict[Any, _MapPlan] = {}
@@ -250,6 +255,7 @@ def _map_plan_slow(op, frame: DeviceFrame) -> _MapPlan:
     plan.accs = tuple(accs)
     plan.slots = slots
     plan.shape_key = (tuple(by), tuple(used), plan.accs)
+    plan._by_dtypes = {}
     if sig is not None:
         _map_plans[sig] = plan
     return plan
@@ -261,14 +267,16 @@ def _execute_agg_map(ctx, op):
     if frame.index is not None:
         raise NotImplementedError("map stage expects a raw chunk (RangeIndex)")
     plan = _map_plan(op, frame)
-    for b, i in zip(plan.by, plan.key_pos):
-        if frame.col_dtype(i) != torch.int64:
-            raise NotImplementedError(f"group key {b!r} has dtype {frame.col_dtype(i)}: int64 keys only")
+    keys_ok, count_only, dts = plan.for_dtypes(frame)
+    if not keys_ok:
+        for b, i in zip(plan.by, plan.key_pos):
+            if frame.col_dtype(i) != torch.int64:
+                raise NotImplementedError(f"group key {b!r} has dtype {frame.col_dtype(i)}: int64 keys only")
     keys = [frame.col(i) for i in plan.key_pos]
     dense_ok = plan.shape_key not in _dense_rejected
     # the dense kernel does not read int64 columns that are only counted (count == rows of the group): those
     # stay where they are (possibly in host memory) unless the general path turns out to be needed
-    skip = plan.count_only_int(frame) if dense_ok and _ASYNC and hasattr(_kernels, "preagg_dense_async") else ()
+    skip = count_only if dense_ok and _ASYNC and hasattr(_kernels, "preagg_dense_async") else ()
     vals = [None if j in skip else frame.col(i) for j, i in enumerate(plan.val_pos)]
     # low-cardinality chunks take the one-launch dense path, enqueued WITHOUT waiting for its result size
     # (the frames carry a Pending count).  A shape that turned out not to fit is remembered, so the following
@@ -281,7 +289,6 @@ def _execute_agg_map(ctx, op):
 
     if dense_ok:
         if _ASYNC and hasattr(_kernels, "preagg_dense_async"):
-            dts = [K.F64 if frame.col_dtype(i) == torch.float64 else K.I64 for i in plan.val_pos]
             res = _kernels.preagg_dense_async(keys, vals, plan.accs, checked=True, val_dtypes=dts)
             if res is None:
                 _dense_rejected.add(plan.shape_key)

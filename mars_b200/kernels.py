@@ -293,11 +293,22 @@ class _FastCall:
 _fast_cache = {}
 
 
+_fast_by_id = {}
+
+
 def _fast(nk, dts, accs) -> _FastCall:
+    # callers pass the same (cached) dtype-code list and accumulator tuple for every chunk of a computation
+    ik = (nk, id(dts), id(accs))
+    hit = _fast_by_id.get(ik)
+    if hit is not None and hit[0] is dts and hit[1] is accs:
+        return hit[2]
     key = (nk, tuple(dts), tuple(accs))
     fc = _fast_cache.get(key)
     if fc is None:
         fc = _fast_cache[key] = _FastCall(nk, dts, accs)
+    if len(_fast_by_id) > 1024:
+        _fast_by_id.clear()
+    _fast_by_id[ik] = (dts, accs, fc)
     return fc
 
 
@@ -405,7 +416,7 @@ def preagg_dense_async(keys: Sequence[torch.Tensor], vals: Sequence[Optional[tor
     n = keys[0].numel()
     # a value column may be None: an int64 column that is only counted is never read by the kernel (its dtype
     # then comes from val_dtypes); passing a null pointer for any other column is rejected by the library
-    dts = list(val_dtypes) if val_dtypes is not None else [F64 if v.dtype == torch.float64 else I64 for v in vals]
+    dts = val_dtypes if val_dtypes is not None else [F64 if v.dtype == torch.float64 else I64 for v in vals]
     fc = _fast(len(keys), dts, accs)
     if _dense_cap is None:
         c = C.c_int64()

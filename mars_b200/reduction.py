@@ -121,9 +121,28 @@ def steps_of(func_name: str) -> List[Tuple[str, str, str]]:
     return list(_DECOMP[check_supported(func_name)])
 
 
+_compiled: Dict[Any, "ReductionSteps"] = {}
+
+
 def compile_reduction(funcs: Sequence[Tuple[Optional[str], str]], ddof: int = 1) -> ReductionSteps:
     """funcs: [(column or None, func name), ...] in user order -- (None, f) applies f to every value column
-    (list form); (col, f) comes from the dict form.  Shared atomic steps are emitted once."""
+    (list form); (col, f) comes from the dict form.  Shared atomic steps are emitted once.  The result only
+    depends on the arguments and is never modified by its users: compiled once per distinct call."""
+    try:
+        key = (tuple(funcs), ddof)
+        hit = _compiled.get(key)
+    except TypeError:
+        key, hit = None, None
+    if hit is None:
+        hit = _compile_reduction(funcs, ddof)
+        if key is not None:
+            if len(_compiled) > 256:
+                _compiled.clear()
+            _compiled[key] = hit
+    return hit
+
+
+def _compile_reduction(funcs: Sequence[Tuple[Optional[str], str]], ddof: int = 1) -> ReductionSteps:
     pre: Dict[str, ReductionPreStep] = {}
     agg: Dict[Tuple[str, str], ReductionAggStep] = {}
     post: Dict[str, Dict[str, Any]] = {}

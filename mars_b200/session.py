@@ -24,6 +24,9 @@ from .core import ChunkData, ProcessorContext, build_chunk_graph
 from .dataframe import DataFrame, DataFrameShuffleProxy
 
 
+_op_names: Dict[object, str] = {}
+
+
 class Session:
     def __init__(self, exchange=None):
         """exchange: a ``mars_b200.parallel.Exchange`` for multi-GPU runs (None: single GPU)."""
@@ -52,7 +55,45 @@ class Session:
         return owners[op.inputs[0].key]
 
     # ---------------------------------------------------------------------------------- execution
+    def _run_chunks_local(self, result_chunks: List[ChunkData], ctx: ProcessorContext, owners: Dict[str, int]):
+        """single-process form of ``_run_chunks``: same order, same reference-counted release of inputs, none
+        of the placement / transfer bookkeeping"""
+        order = [c for c in build_chunk_graph(result_chunks) if c.key not in owners]
+        refs: Dict[str, int] = {}
+        for c in order:
+            for inp in c.op.inputs:
+                k = inp.key
+                refs[k] = refs.get(k, 0) + 1
+        keep = {c.key for c in result_chunks}
+        log = self.executed_ops
+        execute = core.execute
+        for c in order:
+            owners[c.key] = 0
+            op = c.op
+            if not isinstance(op, DataFrameShuffleProxy):
+                ctx._current_chunk = c
+                try:
+                    execute(ctx, op)
+                except Exception as e:  # same wrapping as processor.py:210-214
+                    raise core.ExecutionError(e) from e
+                tag = (type(op), op.stage)
+                name = _op_names.get(tag)
+                if name is None:
+                    name = _op_names[tag] = f"{type(op).__name__}:{getattr(op.stage, 'name', None)}"
+                log.append(name)
+            for inp in op.inputs:
+                k = inp.key
+                n = refs[k] - 1
+                refs[k] = n
+                if n == 0 and k not in keep:
+                    ctx.pop(k, None)
+            if op.stage is core.OperandStage.reduce and isinstance(op, core.MapReduceOperand):
+                for key in op.iter_mapper_keys():    # mapper blocks of this reducer are consumed
+                    ctx.pop(key, None)
+
     def _run_chunks(self, result_chunks: List[ChunkData], ctx: ProcessorContext, owners: Dict[str, int]):
+        if self.world == 1:
+            return self._run_chunks_local(result_chunks, ctx, owners)
         order = [c for c in build_chunk_graph(result_chunks) if c.key not in owners]
         refs = collections.Counter()
         for c in order:
