@@ -16,7 +16,7 @@ the operand protocol (``op.stage``, ``op.inputs/outputs``, ``op.groupby_params``
 post_funcs``, ``op.shuffle_size``, ``op.iter_mapper_data(ctx)``, ``ctx.get_current_chunk()``).
 
 Fallback contract (SURVEY.md section 8b "Errors"): an executor that meets something outside the GPU envelope
-(object keys, custom reductions, sort=True PSRS shuffle chunks, CPU bands) raises NotImplementedError
+(object keys, custom reductions, CPU bands) raises NotImplementedError
 *before touching data*; ``_with_reference_fallback`` then calls the class's own ``execute`` -- the
 reference's pandas path -- explicitly, because the dispatcher itself does not fall back to it
 (mars/core/operand/core.py:501-509).  Ops placed on CPU bands (``op.gpu`` false) always take the reference
@@ -53,6 +53,10 @@ def register_on_mars(gpu_only: bool = True):
     from mars.dataframe.groupby.sort import (DataFrameGroupbyConcatPivot, DataFrameGroupbySortShuffle,
                                              DataFramePSRSGroupbySample)
     from mars.dataframe.merge.concat import DataFrameConcat
+
+    # result chunks go through Mars's storage service, which expects pandas (or cudf) frames: hand out pandas
+    # until a GPU StorageBackend holds DeviceResult chunks
+    executors._DEVICE_RESULTS = False
 
     table = [
         (DataFramePSRSGroupbySample, executors.execute_psrs_sample),
