@@ -114,8 +114,19 @@ class Pending:
 _dtypes_cache: dict = {}
 
 
+class ColumnSet:
+    """Equally long device columns that many row-range frames share (the output of one partition scatter), with
+    their base pointers read once."""
+    __slots__ = ("cols", "ptrs")
+
+    def __init__(self, cols: Sequence[torch.Tensor]):
+        self.cols = list(cols)
+        self.ptrs = [t.data_ptr() for t in self.cols]
+
+
 class DeviceFrame:
-    __slots__ = ("index_names", "_index", "columns", "_data", "_n", "_pending", "_slot", "_home", "__weakref__")
+    __slots__ = ("index_names", "_index", "columns", "_data", "_n", "_pending", "_slot", "_home", "_src",
+                 "__weakref__")
 
     def __init__(self, index_names: Sequence[Any], index: Optional[Sequence[torch.Tensor]],
                  columns: Sequence[Any], data: Sequence[torch.Tensor], n_rows: Optional[int] = None,
@@ -127,6 +138,7 @@ class DeviceFrame:
         self._pending = pending
         self._slot = slot
         self._home = None            # device of lazily uploaded columns (set by from_pandas(lazy=True))
+        self._src = None             # row range of scattered columns that has not been sliced yet (from_range)
         if pending is not None:
             pending.attach(self)
             self._n = None
@@ -139,6 +151,41 @@ class DeviceFrame:
             else:
                 n_rows = 0
         self._n = n_rows
+
+    # ---- row range of shared columns (shuffle blocks) ---------------------------------------------------
+    @classmethod
+    def from_range(cls, index_names, columns, src: "ColumnSet", k0: int, k1: int, d0: int, d1: int, a: int,
+                   b: int) -> "DeviceFrame":
+        """Rows [a, b) of ``src.cols[k0:k1]`` (group keys) and ``src.cols[d0:d1]`` (data): a shuffle block.  A
+        mapper emits R x K of these per chunk; nothing is sliced until a consumer asks for tensors, and the
+        aggregation kernels never do -- they take ``ptrs()``."""
+        f = cls.__new__(cls)
+        f.index_names = index_names
+        f._index = None
+        f.columns = columns
+        f._data = None
+        f._n = b - a
+        f._pending = None
+        f._slot = None
+        f._home = None
+        f._src = (src, k0, k1, d0, d1, a, b)
+        return f
+
+    def _mat(self):
+        src, k0, k1, d0, d1, a, b = self._src
+        cols = src.cols
+        self._index = [t[a:b] for t in cols[k0:k1]]
+        self._data = [t[a:b] for t in cols[d0:d1]]
+        self._src = None
+
+    def ptrs(self):
+        """(key column pointers, data column pointers) as integers"""
+        if self._src is not None:
+            src, k0, k1, d0, d1, a, b = self._src
+            off, p = a * 8, src.ptrs
+            return [x + off for x in p[k0:k1]], [x + off for x in p[d0:d1]]
+        idx = self.index
+        return ([t.data_ptr() for t in idx] if idx else []), [t.data_ptr() for t in self.data]
 
     # ---- deferred size -------------------------------------------------------------------------------
     @property
@@ -164,6 +211,8 @@ class DeviceFrame:
 
     @property
     def index(self):
+        if self._src is not None:
+            self._mat()
         self._resolve()
         return self._index
 
@@ -173,6 +222,8 @@ class DeviceFrame:
 
     @property
     def data(self):
+        if self._src is not None:
+            self._mat()
         self._resolve()
         if self._home is not None:
             for i, t in enumerate(self._data):
@@ -183,6 +234,8 @@ class DeviceFrame:
 
     def col(self, i: int) -> torch.Tensor:
         """data column i on the device (uploads it now if it is still in host memory)"""
+        if self._src is not None:
+            self._mat()
         t = self._data[i]
         if isinstance(t, HostColumn):
             t = self._data[i] = _to_device(t.array, self._home)
@@ -191,6 +244,8 @@ class DeviceFrame:
         return t
 
     def col_dtype(self, i: int):
+        if self._src is not None:
+            return self._src[0].cols[self._src[3] + i].dtype
         return self._data[i].dtype
 
     @data.setter
@@ -200,10 +255,14 @@ class DeviceFrame:
     @property
     def raw_index(self):
         """index columns as they are (capacity-length while the size is pending)"""
+        if self._src is not None:
+            self._mat()
         return self._index
 
     @property
     def raw_data(self):
+        if self._src is not None:
+            self._mat()
         return self._data
 
     # ---- pandas-like surface used by metas / size accounting (subtask/utils.py:62-68)
@@ -221,6 +280,8 @@ class DeviceFrame:
 
     @property
     def dtypes(self):
+        if self._src is not None:
+            self._mat()
         # one Series object per schema: graph building looks at it for every chunk and caches on its identity
         try:
             key = (tuple(self.columns), tuple(t.dtype for t in self._data))
@@ -237,6 +298,9 @@ class DeviceFrame:
 
     @property
     def nbytes(self) -> int:
+        if self._src is not None:
+            _, k0, k1, d0, d1, a, b = self._src
+            return (b - a) * 8 * (k1 - k0 + d1 - d0)
         total = sum(t.numel() * t.element_size() for t in self._data)
         if self._index:
             total += sum(t.numel() * t.element_size() for t in self._index)
@@ -247,6 +311,8 @@ class DeviceFrame:
 
     @property
     def device(self):
+        if self._src is not None:
+            return self._src[0].cols[0].device
         if self._home is not None:
             return self._home
         ts = self._data or self._index or []
@@ -262,6 +328,13 @@ class DeviceFrame:
     def same_index(self, other: "DeviceFrame") -> bool:
         """True when both frames share their index tensors (reference: item.index.equals(index),
         groupby/core.py:381-391 -- here a pointer comparison, no data pass)."""
+        sa, sb = self._src, other._src
+        if sa is not None and sb is not None:   # two unsliced row ranges: same columns, same rows
+            return sa[0] is sb[0] and sa[1] == sb[1] and sa[2] == sb[2] and sa[5] == sb[5] and sa[6] == sb[6]
+        if sa is not None:
+            self._mat()
+        if sb is not None:
+            other._mat()
         a, b = self._index, other._index
         if a is None or b is None:
             return a is b and len(self) == len(other)
@@ -324,7 +397,8 @@ class DeviceFrame:
 
     def __repr__(self):
         rows = "pending" if self.is_pending else self._n
-        return (f"DeviceFrame(rows={rows}, index={self.index_names if self._index is not None else 'range'}, "
+        has_index = self._index is not None or (self._src is not None and self._src[2] > self._src[1])
+        return (f"DeviceFrame(rows={rows}, index={self.index_names if has_index else 'range'}, "
                 f"columns={self.columns}, device={self.device})")
 
 

@@ -27,7 +27,7 @@ import torch
 
 from . import kernels as K
 from ._lib import MarsGBError
-from .device import DeviceFrame, Pending, PiecewiseFrame
+from .device import ColumnSet, DeviceFrame, Pending, PiecewiseFrame
 from .reduction import _DECOMP
 
 _OPCODE = {"sum": K.SUM, "count": K.COUNT, "min": K.MIN, "max": K.MAX}
@@ -376,7 +376,12 @@ def _merge_partials(slots: Sequence[Sequence[DeviceFrame]], steps: Sequence[_Ste
         base = slots[grp[0]]
         ops = [_OPCODE[steps[i].agg_func] for i in grp for _ in slots[i][0].columns]
         pend_out = None
-        if _ASYNC and hasattr(_kernels, "merge_small_async"):
+        # sizes first (known on the host without touching any column): large inputs skip the small-merge attempt
+        known = sum(len(f) for f in base if not f.is_pending)
+        n_live = sum(1 for f in base if f.is_pending or len(f) > 0)
+        small = (known <= getattr(_kernels, "SMALL_MAX_ROWS", 2048)
+                 and n_live <= getattr(_kernels, "SMALL_MAX_PIECES", 16))
+        if small and _ASYNC and hasattr(_kernels, "merge_small_async"):
             # sizes that are still on the device stay there: the merge reads them in the kernel
             pieces = []
             for i in range(len(base)):
@@ -426,8 +431,17 @@ def _merge_general(slots, grp, ops, sort):
     # the pieces go to the library with the distinct-keys hint (bucketed aggregation over all pieces in place)
     agg = _kernels.Aggregator(len(base[0].index), dts, list(enumerate(ops)), expect_distinct=True)
     try:
-        for i in live:
-            agg.update(base[i].index, [t for s in grp for t in slots[s][i].data])
+        if hasattr(agg, "update_ptrs"):     # pointer level: shuffle blocks are unsliced row ranges
+            dev = base[0].device
+            for i in live:
+                fr = [slots[s][i] for s in grp]
+                kp, vp = fr[0].ptrs()
+                for f in fr[1:]:
+                    vp = vp + f.ptrs()[1]
+                agg.update_ptrs(kp, vp, len(fr[0]), fr, dev)
+        else:
+            for i in live:
+                agg.update(base[i].index, [t for s in grp for t in slots[s][i].data])
         return agg.result(sort=sort, device=base[0].device)
     finally:
         agg.close()
@@ -688,15 +702,18 @@ def _execute_shuffle_map(ctx, op):
             cols.extend(frames[i].data)
         outs, offsets = _kernels.partition_scatter(pid, R, cols)
         nk = len(base.index)
+        # R x K blocks per chunk: row ranges of the scattered columns, sliced only if somebody asks for tensors
+        src = ColumnSet(outs)
+        spans, pos = [], nk
+        for i in g:
+            ncol = len(frames[i].columns)
+            spans.append((i, frames[i].index_names, frames[i].columns, pos, pos + ncol))
+            pos += ncol
         for r in range(R):
             a, b = offsets[r], offsets[r + 1]
-            keys_r = [t[a:b] for t in outs[:nk]]
-            pos = nk
-            for i in g:
-                ncol = len(frames[i].columns)
-                blocks[r][i] = DeviceFrame(frames[i].index_names, keys_r, frames[i].columns,
-                                           [t[a:b] for t in outs[pos:pos + ncol]], b - a)
-                pos += ncol
+            row = blocks[r]
+            for i, names, columns, d0, d1 in spans:
+                row[i] = DeviceFrame.from_range(names, columns, src, 0, nk, d0, d1, a, b)
     for r in range(R):
         reducer_index = (r, chunk.index[1]) if getattr(op, "is_dataframe_obj", True) else (r,)
         if is_tuple:

@@ -156,6 +156,21 @@ class Aggregator:
             check(self._lib.mgb_agg_update(self._h, _ptrs(ks), _ptrs(vs), ks[0].numel()))
         return self
 
+    def update_ptrs(self, key_ptrs: Sequence[int], val_ptrs: Sequence[int], n: int, keep, device=None):
+        """``update`` for callers that hold validated columns and already know their device pointers (row
+        ranges of scattered columns: no tensor views are created).  ``keep`` is whatever keeps the memory
+        alive until finalize."""
+        if len(key_ptrs) != self.n_keys or len(val_ptrs) != len(self.val_dtypes):
+            raise MarsGBError(1, "column count does not match the aggregator spec")
+        if n >= (1 << 31) - 1024:
+            raise MarsGBError(4, "a pointer-level batch must hold fewer than 2^31 rows")
+        if device is not None:
+            self._device = device
+        if n > 0:
+            self._keep.append(keep)
+            check(self._lib.mgb_agg_update(self._h, _lib.ptr_array(key_ptrs), _lib.ptr_array(val_ptrs), n))
+        return self
+
     def result(self, sort: bool = False, device=None):
         """-> (key tensors, accumulator tensors)."""
         g = C.c_int64()

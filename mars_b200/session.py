@@ -133,6 +133,20 @@ class Session:
                     ctx.pop(key, None)
 
     def execute(self, df: DataFrame, **kw):
+        # The chunk graph of a large shuffle keeps ~1e5 small containers alive (frames, column lists, tensor
+        # views); none of them forms a reference cycle (device.Pending holds weak references), but every few
+        # hundred allocations the cyclic collector walks all of them.  It is paused while the graph runs.
+        import gc
+
+        was_enabled = gc.isenabled()
+        gc.disable()
+        try:
+            return self._execute(df, **kw)
+        finally:
+            if was_enabled:
+                gc.enable()
+
+    def _execute(self, df: DataFrame, **kw):
         t = df.data
         ctx = ProcessorContext()
         owners: Dict[str, int] = {}
