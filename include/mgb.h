@@ -124,12 +124,6 @@ int mgb_agg_destroy(mgb_agg* agg);
  * produced the result, no table was built), [5]=kernels launched by this aggregator so far.               */
 int mgb_agg_stats(mgb_agg* agg, int64_t* stats6);
 
-/* Tuning knobs (process-wide; tests and profiling).  MGB_TUNE_BUCKET_MOVE_BYTES: inputs of the bucketed
- * aggregation larger than this many bytes are first moved into coarse bucket order so that the per-bucket
- * gathers stay L2-resident (default: never -- measured slower on B200; 0 = always, negative = restore the
- * default).                                                                                             */
-#define MGB_TUNE_BUCKET_MOVE_BYTES 0
-int mgb_set_tuning(int32_t key, int64_t value);
 
 /* Low-cardinality fast paths (one kernel launch + one 8-byte device->host read each).
  *

@@ -68,7 +68,6 @@ SIGNATURES = {
     "mgb_agg_emit": (C.c_int, [_vp, _pp, _pp, _i32]),
     "mgb_agg_destroy": (C.c_int, [_vp]),
     "mgb_agg_stats": (C.c_int, [_vp, C.POINTER(_i64)]),
-    "mgb_set_tuning": (C.c_int, [_i32, _i64]),
     "mgb_dense_capacity": (C.c_int, [C.POINTER(_i64)]),
     "mgb_preagg_dense": (C.c_int, [C.POINTER(AggSpec), _pp, _pp, _i64, _pp, _pp, _i64, C.POINTER(_i64), _vp]),
     "mgb_merge_small": (C.c_int, [C.POINTER(AggSpec), _i32, C.POINTER(_i64), C.POINTER(_pp), C.POINTER(_pp), _pp, _pp,

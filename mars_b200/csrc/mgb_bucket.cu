@@ -8,7 +8,10 @@
 // latency- and init-bound.  Here the rows of ALL sources (update() batches, read in place) are split by the
 // top bits of the key hash into B buckets of <= 512 rows on average:
 //
-//   k_bucket_ids    row -> bucket id                                          (reads the key columns once)
+//   k_bucket_pack   one sequential pass over the column-major batches: row -> bucket id, and the row itself
+//                   (keys + values) into a ROW-MAJOR staging array through a shared-memory transpose.  The
+//                   gathers of the next kernel then fetch one row = one or two 64-byte DRAM bursts instead
+//                   of one burst per 8-byte column value (measured: 1118 -> ~190 B/row on 80-byte rows).
 //   radix passes    stable permutation of the row ids by bucket + bucket offsets   (mgb_partition.cu)
 //   k_bucket_agg    one CTA per bucket: key table in shared memory (dense group ids), counting sort of the
 //                   bucket's rows by group id, then one thread (one warp for groups of >= 32 rows) per
@@ -30,17 +33,11 @@
 #define BK_TARGET 512         // average rows per bucket (upper bound)
 #define BK_BIG 32             // groups with >= BK_BIG rows in a tile are folded by a whole warp
 #define BK_MAXA 8             // accumulators per value column handled in registers
-// Inputs larger than this are first moved into coarse bucket order.  Measured on B200 (profiles/README.md): the
-// move makes k_bucket_agg 17-26 % faster (its gathers become L2-resident) but costs more than that saves
-// (0.55 ms per 15.6 M two-column rows, 2.4 ms per 7.8 M ten-column rows), so it is off unless asked for.
-#define BK_MOVE_BYTES_DEFAULT 0x7fffffffffffffffLL
 #define BK_SKEW_ROWS (64 * BK_TARGET)   // a longer bucket (one hot key) would serialise on one CTA: decline
 
 struct BktParams {
-  const BktSource* srcs;      // device array
-  const long long* begin;     // device [nsrc + 1]
-  BktSource src0;             // copy of source 0 (single-source fast path)
-  int nsrc;
+  const uint64_t* rows;       // row-major staging: row i at rows + i * W, keys first, then the value columns
+  int W;
   long long T;
   int logB;
   const int32_t* perm;
@@ -63,24 +60,61 @@ __device__ __forceinline__ int bk_locate(const long long* __restrict__ begin, in
   return lo;
 }
 
+#define BKP_ROWS 256   // rows per tile of the pack kernel (== its block size)
+
+struct BktPackParams {
+  const BktSource* srcs;      // device array
+  const long long* begin;     // device [nsrc + 1]
+  BktSource src0;             // copy of source 0 (single-source fast path)
+  int nsrc, nk, nv;
+  long long T;
+  int logB;
+  int32_t* pid;
+  uint64_t* rows;
+};
+
+// Tile of 256 rows: every thread reads its row column by column (coalesced across the warp), the tile is
+// transposed through shared memory (row stride padded to an odd number of words: no bank conflicts) and
+// written out as 256 * W contiguous words.
 template <int NK>
-__global__ void __launch_bounds__(256) k_bucket_ids(const BktSource* __restrict__ srcs,
-                                                    const long long* __restrict__ begin, BktSource src0, int nsrc,
-                                                    long long T, int logB, int32_t* __restrict__ pid) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < T;
-       i += (long long)gridDim.x * blockDim.x) {
-    int64_t k[NK];
-    if (nsrc == 1) {
+__global__ void __launch_bounds__(BKP_ROWS) k_bucket_pack(const BktPackParams p) {
+  extern __shared__ uint64_t tile[];
+  const int W = p.nk + p.nv, Wp = W | 1;
+  const long long ntiles = (p.T + BKP_ROWS - 1) / BKP_ROWS;
+  for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const long long i = t * BKP_ROWS + threadIdx.x;
+    if (i < p.T) {
+      const BktSource* src = &p.src0;
+      long long loc = i;
+      if (p.nsrc > 1) {
+        const int s = bk_locate(p.begin, p.nsrc, i);
+        src = &p.srcs[s];
+        loc = i - __ldg(&p.begin[s]);
+      }
+      uint64_t* row = tile + threadIdx.x * Wp;
+      int64_t k[NK];
 #pragma unroll
-      for (int j = 0; j < NK; ++j) k[j] = (int64_t)mgb_ld_stream(src0.keys[j] + i);
-    } else {
-      const int s = bk_locate(begin, nsrc, i);
-      const long long loc = i - __ldg(&begin[s]);
-#pragma unroll
-      for (int j = 0; j < NK; ++j) k[j] = (int64_t)mgb_ld_stream(srcs[s].keys[j] + loc);
+      for (int j = 0; j < NK; ++j) {
+        const uint64_t v = mgb_ld_stream(src->keys[j] + loc);
+        k[j] = (int64_t)v;
+        row[j] = v;
+      }
+      const uint64_t sh = mgb_slot_hash(mgb_hash_tuple<NK>(k));
+      p.pid[i] = p.logB ? (int32_t)(sh >> (64 - p.logB)) : 0;
+#pragma unroll 4
+      for (int c = 0; c < p.nv; ++c) row[NK + c] = mgb_ld_stream(src->vals[c] + loc);
     }
-    const uint64_t sh = mgb_slot_hash(mgb_hash_tuple<NK>(k));
-    pid[i] = logB ? (int32_t)(sh >> (64 - logB)) : 0;
+    __syncthreads();
+    const long long base = t * BKP_ROWS;
+    const int nrow = (int)((p.T - base) < BKP_ROWS ? (p.T - base) : BKP_ROWS);
+    const int nword = nrow * W;
+    const uint32_t inv = 0xffffffffu / (uint32_t)W + 1u;
+    uint64_t* out = p.rows + base * W;
+    for (int idx = threadIdx.x; idx < nword; idx += BKP_ROWS) {
+      const int r = W == 1 ? idx : (int)__umulhi((uint32_t)idx, inv);
+      out[idx] = tile[r * Wp + (idx - r * W)];
+    }
+    __syncthreads();
   }
 }
 
@@ -153,7 +187,6 @@ __global__ void __launch_bounds__(BK_THREADS) k_bucket_agg(const BktParams p) {
   __shared__ int cursor[BK_TAB];
   __shared__ uint32_t r_loc[BK_RT];
   __shared__ uint16_t r_gid[BK_RT];
-  __shared__ uint16_t r_src[BK_RT];
   __shared__ uint16_t sorted[BK_RT];
   __shared__ int warp_tot[BK_THREADS / 32];
   __shared__ int big[BK_RT / BK_BIG];   // groups with >= BK_BIG rows in the current tile
@@ -187,22 +220,9 @@ __global__ void __launch_bounds__(BK_THREADS) k_bucket_agg(const BktParams p) {
       const int r = r0 + tid;
       const bool valid = r < m;
       const long long i = valid ? (long long)p.perm[tlo + r] : 0;
-      int s = 0;
-      long long loc = i;
       uint64_t k[NK];
 #pragma unroll
-      for (int j = 0; j < NK; ++j) k[j] = 0;
-      if (valid) {
-        if (p.nsrc == 1) {
-#pragma unroll
-          for (int j = 0; j < NK; ++j) k[j] = __ldg(p.src0.keys[j] + i);
-        } else {
-          s = bk_locate(p.begin, p.nsrc, i);
-          loc = i - __ldg(&p.begin[s]);
-#pragma unroll
-          for (int j = 0; j < NK; ++j) k[j] = __ldg(p.srcs[s].keys[j] + loc);
-        }
-      }
+      for (int j = 0; j < NK; ++j) k[j] = valid ? __ldg(p.rows + i * p.W + j) : 0;
       const uint64_t sh = mgb_slot_hash(mgb_hash_tuple<NK>((const int64_t*)k));
       const uint32_t slot = (uint32_t)(sh >> (54 - p.logB)) & (BK_TAB - 1);
       const int g = bk_find_or_insert<NK>(tab_keys, tab_idx, &n_unique, valid, k, slot, p.scratch, T, lo);
@@ -211,8 +231,7 @@ __global__ void __launch_bounds__(BK_THREADS) k_bucket_agg(const BktParams p) {
           failed = 1;
         } else {
           r_gid[r] = (uint16_t)g;
-          r_src[r] = (uint16_t)s;
-          r_loc[r] = (uint32_t)loc;
+          r_loc[r] = (uint32_t)i;
           atomicAdd(&cnt[g], 1);
         }
       }
@@ -279,13 +298,12 @@ __global__ void __launch_bounds__(BK_THREADS) k_bucket_agg(const BktParams p) {
         uint64_t acc[BK_MAXA];
 #pragma unroll
         for (int q = 0; q < BK_MAXA; ++q) acc[q] = q < na_c ? mgb_acc_init(L.acc[a0 + q].op) : 0;
-        const uint64_t* col0 = p.src0.vals[c];
+        const uint64_t* col0 = p.rows + nk + c;      // value c of row i at col0[i * W]
+        const long long W = p.W;
         const int j0 = pass == 0 ? 0 : lane, jstep = pass == 0 ? 1 : 32;
 #pragma unroll 2
         for (int j = j0; j < n; j += jstep) {
-          const int r = sorted[st + j];
-          const uint64_t* col = p.nsrc == 1 ? col0 : p.srcs[r_src[r]].vals[c];
-          const uint64_t x = __ldg(col + r_loc[r]);
+          const uint64_t x = __ldg(col0 + (long long)r_loc[sorted[st + j]] * W);
 #pragma unroll
           for (int q = 0; q < BK_MAXA; ++q) {
             if (q < na_c) {
@@ -371,14 +389,6 @@ void mgb_bucket_free(BktResult* r, cudaStream_t st) {
   r->goff = nullptr;
 }
 
-static long long g_move_bytes = BK_MOVE_BYTES_DEFAULT;
-
-extern "C" int mgb_set_tuning(int32_t key, int64_t value) {
-  MGB_REQUIRE(key == MGB_TUNE_BUCKET_MOVE_BYTES, MGB_ERR_INVALID, "unknown tuning key %d", key);
-  g_move_bytes = value < 0 ? BK_MOVE_BYTES_DEFAULT : (long long)value;
-  return MGB_OK;
-}
-
 static void bk_debug(const char* what, cudaStream_t st) {
   static int on = -1;
   if (on < 0) {
@@ -402,16 +412,17 @@ int mgb_bucket_aggregate(const Layout& L, const BktSource* srcs_host, int nsrc, 
   int logB = 0;
   while (logB < 22 && (T >> logB) > BK_TARGET) ++logB;
   const int B = 1 << logB;
-  const int ncol = L.nk + L.na;
-  char* small = nullptr;     // srcs | begin | err
+  const int ncol = L.nk + L.na, W = L.nk + L.nv;
+  char* small = nullptr;     // srcs | begin | err, longest bucket
   const size_t src_bytes = sizeof(BktSource) * (size_t)nsrc;
   const size_t begin_bytes = sizeof(long long) * ((size_t)nsrc + 1);
   const size_t src_pad = (src_bytes + 255) & ~(size_t)255, begin_pad = (begin_bytes + 255) & ~(size_t)255;
-  int32_t *pid = nullptr, *perm = nullptr, *pid2 = nullptr;
-  uint64_t* moved = nullptr;
+  int32_t *pid = nullptr, *perm = nullptr;
+  uint64_t* rows = nullptr;
   MGB_CUDA(cudaMallocAsync((void**)&small, src_pad + begin_pad + 256, st));
   MGB_CUDA(cudaMallocAsync((void**)&pid, sizeof(int32_t) * (size_t)T, st));
   MGB_CUDA(cudaMallocAsync((void**)&perm, sizeof(int32_t) * (size_t)T, st));
+  MGB_CUDA(cudaMallocAsync((void**)&rows, sizeof(uint64_t) * (size_t)W * (size_t)T, st));
   MGB_CUDA(cudaMallocAsync((void**)&out->off, sizeof(int64_t) * ((size_t)B + 1), st));
   MGB_CUDA(cudaMallocAsync((void**)&out->goff, sizeof(int64_t) * ((size_t)B + 1), st));
   MGB_CUDA(cudaMallocAsync((void**)&out->scratch, sizeof(uint64_t) * (size_t)ncol * (size_t)T, st));
@@ -430,31 +441,41 @@ int mgb_bucket_aggregate(const Layout& L, const BktSource* srcs_host, int nsrc, 
   }
   MGB_CUDA(cudaMemsetAsync(d_err, 0, 256, st));
   MGB_CUDA(cudaMemsetAsync(out->goff + B, 0, sizeof(int64_t), st));
+  auto release = [&]() {
+    cudaFreeAsync(pid, st);
+    cudaFreeAsync(perm, st);
+    cudaFreeAsync(rows, st);
+    cudaFreeAsync(small, st);
+  };
   int status = MGB_OK;
   {
     MgbProfScope prof(MGB_K_BUCKET, st);
-    long long blocks = (T + 1023) / 1024, capb = (long long)mgb_sm_count() * 8;
-    const unsigned grid = (unsigned)(blocks > capb ? capb : blocks);
-    if (L.nk == 1)
-      k_bucket_ids<1><<<grid, 256, 0, st>>>(d_srcs, d_begin, srcs_host[0], nsrc, T, logB, pid);
-    else
-      k_bucket_ids<2><<<grid, 256, 0, st>>>(d_srcs, d_begin, srcs_host[0], nsrc, T, logB, pid);
-    MGB_CHECK_LAUNCH();
-    bk_debug("k_bucket_ids", st);
-    // Inputs larger than L2: first move the rows (all columns) into the order of the top 8 bits of the bucket
-    // id -- sequential reads, 256 write streams that L2 combines.  The per-bucket gathers below then stay
-    // inside one coarse range (a few MB, shared by the CTAs that run at the same time) instead of touching a
-    // random 64-byte DRAM burst per 8-byte value.
-    const int32_t* pid_sorted_src = pid;
-    if ((long long)(L.nk + L.nv) * 8 * T > g_move_bytes && logB > 0) {
-      MGB_CUDA(cudaMallocAsync((void**)&moved, sizeof(uint64_t) * (size_t)(L.nk + L.nv) * (size_t)T, st));
-      MGB_CUDA(cudaMallocAsync((void**)&pid2, sizeof(int32_t) * (size_t)T, st));
-      status = mgb_radix_move_sources(pid, T, logB > 8 ? logB - 8 : 0, d_srcs, d_begin, srcs_host[0], nsrc, L.nk, L.nv,
-                                      moved, pid2, st);
-      bk_debug("move rows to coarse bucket order", st);
-      pid_sorted_src = pid2;
+    // 1. bucket ids + row-major copy of the rows
+    BktPackParams pp;
+    pp.srcs = d_srcs;
+    pp.begin = d_begin;
+    pp.src0 = srcs_host[0];
+    pp.nsrc = nsrc;
+    pp.nk = L.nk;
+    pp.nv = L.nv;
+    pp.T = T;
+    pp.logB = logB;
+    pp.pid = pid;
+    pp.rows = rows;
+    const size_t sm = (size_t)BKP_ROWS * (size_t)(W | 1) * 8;
+    const long long ntiles = (T + BKP_ROWS - 1) / BKP_ROWS, capb = (long long)mgb_sm_count() * 16;
+    const unsigned grid = (unsigned)(ntiles > capb ? capb : ntiles);
+    if (L.nk == 1) {
+      if (sm > 48 * 1024) MGB_CUDA(cudaFuncSetAttribute(k_bucket_pack<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      k_bucket_pack<1><<<grid, BKP_ROWS, sm, st>>>(pp);
+    } else {
+      if (sm > 48 * 1024) MGB_CUDA(cudaFuncSetAttribute(k_bucket_pack<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      k_bucket_pack<2><<<grid, BKP_ROWS, sm, st>>>(pp);
     }
-    if (status == MGB_OK) status = mgb_radix_sort_perm_pid_ex(pid_sorted_src, T, B, perm, out->off, false, st);
+    MGB_CHECK_LAUNCH();
+    bk_debug("k_bucket_pack", st);
+    // 2. row ids in bucket order
+    status = mgb_radix_sort_perm_pid_ex(pid, T, B, perm, out->off, false, st);
     bk_debug("radix sort by bucket", st);
     if (status == MGB_OK) {   // a hot key makes one bucket as long as its row count: leave that input to the table
       const int gb = (B + 255) / 256;
@@ -466,28 +487,17 @@ int mgb_bucket_aggregate(const Layout& L, const BktSource* srcs_host, int nsrc, 
         mgb_set_error("bucket aggregation: %s", cudaGetErrorString(e));
         status = MGB_ERR_CUDA;
       } else if (longest > BK_SKEW_ROWS) {
-        cudaFreeAsync(pid, st);
-        cudaFreeAsync(perm, st);
-        cudaFreeAsync(small, st);
-        if (moved) cudaFreeAsync(moved, st);
-        if (pid2) cudaFreeAsync(pid2, st);
+        release();
         mgb_bucket_free(out, st);
         *overflow = 2;
         return MGB_OK;
       }
     }
+    // 3. one CTA per bucket
     if (status == MGB_OK) {
       BktParams p;
-      p.srcs = d_srcs;
-      p.begin = d_begin;
-      p.src0 = srcs_host[0];
-      p.nsrc = nsrc;
-      if (moved) {   // the moved copy is ONE source
-        memset(&p.src0, 0, sizeof(p.src0));
-        for (int j = 0; j < L.nk; ++j) p.src0.keys[j] = moved + (size_t)j * (size_t)T;
-        for (int c = 0; c < L.nv; ++c) p.src0.vals[c] = moved + (size_t)(L.nk + c) * (size_t)T;
-        p.nsrc = 1;
-      }
+      p.rows = rows;
+      p.W = W;
       p.T = T;
       p.logB = logB;
       p.perm = perm;
@@ -521,11 +531,7 @@ int mgb_bucket_aggregate(const Layout& L, const BktSource* srcs_host, int nsrc, 
       status = MGB_ERR_CUDA;
     }
   }
-  cudaFreeAsync(pid, st);
-  cudaFreeAsync(perm, st);
-  cudaFreeAsync(small, st);
-  if (moved) cudaFreeAsync(moved, st);
-  if (pid2) cudaFreeAsync(pid2, st);
+  release();
   if (status != MGB_OK || err_h) {
     mgb_bucket_free(out, st);
     *overflow = err_h ? 1 : 0;

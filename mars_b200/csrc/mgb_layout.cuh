@@ -51,8 +51,3 @@ int mgb_bucket_emit(const Layout& L, const BktResult& r, uint64_t* const* out_ke
 void mgb_bucket_free(BktResult* r, cudaStream_t st);
 bool mgb_bucket_supports(const Layout& L);
 
-// stable split of the rows of all sources by the 8-bit digit (pid >> shift) & 255, moving every column:
-// out column j (keys first, then values) at out + j * T, pid_out = pid in the new order (mgb_partition.cu)
-int mgb_radix_move_sources(const int32_t* pid, long long T, int shift, const BktSource* d_srcs,
-                           const long long* d_begin, const BktSource& src0, int nsrc, int nk, int nv, uint64_t* out,
-                           int32_t* pid_out, cudaStream_t st);

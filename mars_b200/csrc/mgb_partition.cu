@@ -7,7 +7,6 @@
 //   (mars/dataframe/groupby/core.py:389-435).  Stability == the ascending positions `f_i` of the reference.
 // * mgb_argsort_keys: LSD radix sort of int64 key tuples (groupby(sort=True) output order).
 #include "mgb_common.cuh"
-#include "mgb_layout.cuh"
 
 #define RP_THREADS 256
 #define RP_ROUNDS 8
@@ -120,113 +119,6 @@ static int radix_pass(const DigitSrc& s, int64_t n, int32_t* perm_out, int64_t* 
   k_radix_scatter<<<(unsigned)ntiles, RP_THREADS, 0, st>>>(s, n, ntiles, hist, trivial_flag, perm_out);
   MGB_CHECK_LAUNCH();
   return MGB_OK;
-}
-
-// --------------------------------------------------------------------------------------------------
-// stable 8-bit split that moves the rows themselves (every column of every source), used by the bucketed
-// aggregation to bring inputs larger than L2 into coarse bucket order (mgb_bucket.cu)
-// --------------------------------------------------------------------------------------------------
-struct MoveParams {
-  const BktSource* srcs;
-  const long long* begin;
-  BktSource src0;
-  int nsrc, nk, nv;
-  long long T;
-  uint64_t* out;
-  int32_t* pid_out;
-};
-
-__global__ void __launch_bounds__(RP_THREADS) k_radix_move(DigitSrc s, int64_t n, int64_t ntiles,
-                                                           const int64_t* __restrict__ hist, const MoveParams mp) {
-  __shared__ int64_t base[256];
-  __shared__ int64_t wpos[RP_WARPS][256];
-  __shared__ uint16_t wc[RP_WARPS][256];
-  const int64_t tile = blockIdx.x;
-  const int64_t tbase = tile * RP_TILE;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const unsigned lt = mgb_lanemask_lt();
-  base[threadIdx.x] = hist[(int64_t)threadIdx.x * ntiles + tile];
-  for (int r = 0; r < RP_ROUNDS; ++r) {
-#pragma unroll
-    for (int w = 0; w < RP_WARPS; ++w) wc[w][threadIdx.x] = 0;
-    __syncthreads();
-    const int64_t i = tbase + (int64_t)r * RP_THREADS + threadIdx.x;
-    const bool valid = i < n;
-    uint32_t d = 256u + (uint32_t)lane;  // invalid lanes never match anybody
-    int32_t pv = 0;
-    if (valid) {
-      pv = s.pid[i];
-      d = ((uint32_t)pv >> s.shift) & 255u;
-    }
-    const unsigned peers = __match_any_sync(0xffffffffu, d);
-    const int lr = __popc(peers & lt);
-    if (valid && lr == 0) wc[warp][d] = (uint16_t)__popc(peers);
-    __syncthreads();
-    {
-      int64_t run = base[threadIdx.x];
-#pragma unroll
-      for (int w = 0; w < RP_WARPS; ++w) {
-        wpos[w][threadIdx.x] = run;
-        run += wc[w][threadIdx.x];
-      }
-      base[threadIdx.x] = run;
-    }
-    __syncthreads();
-    if (valid) {
-      const int64_t dst = wpos[warp][d] + lr;
-      mp.pid_out[dst] = pv;
-      const BktSource* src = &mp.src0;
-      int64_t loc = i;
-      if (mp.nsrc > 1) {
-        int lo = 0, hi = mp.nsrc - 1;
-        while (lo < hi) {
-          const int mid = (lo + hi + 1) >> 1;
-          if (__ldg(&mp.begin[mid]) <= i)
-            lo = mid;
-          else
-            hi = mid - 1;
-        }
-        src = &mp.srcs[lo];
-        loc = i - __ldg(&mp.begin[lo]);
-      }
-      for (int j = 0; j < mp.nk; ++j) mp.out[(int64_t)j * mp.T + dst] = mgb_ld_stream(src->keys[j] + loc);
-      for (int c = 0; c < mp.nv; ++c)
-        mp.out[(int64_t)(mp.nk + c) * mp.T + dst] = mgb_ld_stream(src->vals[c] + loc);
-    }
-  }
-}
-
-int mgb_radix_move_sources(const int32_t* pid, long long T, int shift, const BktSource* d_srcs,
-                           const long long* d_begin, const BktSource& src0, int nsrc, int nk, int nv, uint64_t* out,
-                           int32_t* pid_out, cudaStream_t st) {
-  if (T == 0) return MGB_OK;
-  const int64_t ntiles = (T + RP_TILE - 1) / RP_TILE;
-  int64_t* hist = nullptr;
-  MGB_CUDA(cudaMallocAsync((void**)&hist, sizeof(int64_t) * 256 * ntiles, st));
-  DigitSrc s{pid, nullptr, nullptr, shift};
-  k_radix_hist<<<(unsigned)ntiles, RP_THREADS, 0, st>>>(s, T, ntiles, hist);
-  MGB_CHECK_LAUNCH();
-  int status = mgb_scan_exclusive_i64(hist, 256 * ntiles, nullptr, st);
-  if (status == MGB_OK) {
-    MoveParams mp;
-    mp.srcs = d_srcs;
-    mp.begin = d_begin;
-    mp.src0 = src0;
-    mp.nsrc = nsrc;
-    mp.nk = nk;
-    mp.nv = nv;
-    mp.T = T;
-    mp.out = out;
-    mp.pid_out = pid_out;
-    k_radix_move<<<(unsigned)ntiles, RP_THREADS, 0, st>>>(s, T, ntiles, hist, mp);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) {
-      mgb_set_error("row move launch: %s", cudaGetErrorString(e));
-      status = MGB_ERR_CUDA;
-    }
-  }
-  cudaFreeAsync(hist, st);
-  return status;
 }
 
 __global__ void k_iota(int32_t* p, int64_t n) {

@@ -204,14 +204,6 @@ class Aggregator:
             pass
 
 
-TUNE_BUCKET_MOVE_BYTES = 0
-
-
-def set_tuning(key: int, value: int):
-    """process-wide tuning knob of the library (mgb_set_tuning); tests and profiling"""
-    check(_lib.load().mgb_set_tuning(int(key), int(value)))
-
-
 def groupby_aggregate(keys, vals, accs, sort=False, expect_distinct=False):
     """One-shot: (key tensors, accumulator tensors, stats)."""
     agg = Aggregator(len(keys), [dtype_code(v) for v in vals], accs, expect_distinct=expect_distinct)

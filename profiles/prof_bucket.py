@@ -22,8 +22,6 @@ else:
     vals = [torch.randn(n, generator=g, device="cuda", dtype=torch.float64) * 3 + 10 for _ in range(8)]
     accs = [(c, o) for o in (K.MIN, K.MAX, K.SUM, K.SUMSQ, K.COUNT) for c in range(8)]
 lib = _lib.load()
-if __import__("os").environ.get("MOVE_BYTES"):
-    K.set_tuning(K.TUNE_BUCKET_MOVE_BYTES, int(__import__("os").environ["MOVE_BYTES"]))
 for it in range(4):
     if it == 3:
         lib.mgb_prof_enable(1)

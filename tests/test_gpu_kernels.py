@@ -405,19 +405,10 @@ def _bucketed(stats):
     return stats["table_capacity"] == 0 and stats["rows_spilled"] > 0
 
 
-@pytest.fixture(params=["gather in place", "rows moved to coarse bucket order first"])
-def bucket_move(request, K):
-    """both data paths of the bucketed aggregation: inputs below the L2-sized threshold are gathered in place,
-    larger ones are first moved into coarse bucket order (forced here by a zero threshold)"""
-    K.set_tuning(K.TUNE_BUCKET_MOVE_BYTES, 0 if request.param.startswith("rows moved") else 1 << 60)
-    yield request.param
-    K.set_tuning(K.TUNE_BUCKET_MOVE_BYTES, -1)
-
-
 @pytest.mark.parametrize("n_keys", [1, 2])
 @pytest.mark.parametrize("n,card,batches", [(5000, 4000, 1), (300_000, 300_000, 1), (300_000, 40_000, 7),
                                             (1_200_000, 150_000, 3), (200_000, 13, 2)])
-def test_bucketed_aggregation_matches_pandas(K, bucket_move, n_keys, n, card, batches):
+def test_bucketed_aggregation_matches_pandas(K, n_keys, n, card, batches):
     """inputs that are not pre-aggregated (distinct-keys hint): all ops, both dtypes, NaNs, several sources;
     card=13 makes every bucket one long multi-tile run of a few big groups (warp-per-group fold)"""
     rng = np.random.default_rng(n + card + n_keys)
@@ -434,7 +425,7 @@ def test_bucketed_aggregation_matches_pandas(K, bucket_move, n_keys, n, card, ba
     assert _bucketed(stats), stats
 
 
-def test_bucketed_aggregation_wide_min_max_var_shape(K, bucket_move):
+def test_bucketed_aggregation_wide_min_max_var_shape(K):
     """cfg4-shaped: two keys, 8 float64 columns x (min, max, sum, sumsq, count) = 40 accumulators"""
     rng = np.random.default_rng(44)
     n = 400_000
@@ -445,7 +436,7 @@ def test_bucketed_aggregation_wide_min_max_var_shape(K, bucket_move):
     assert _bucketed(stats), stats
 
 
-def test_bucketed_aggregation_skew_and_merge_ops(K, bucket_move):
+def test_bucketed_aggregation_skew_and_merge_ops(K):
     """one key holds 4 % of the rows (a bucket of many tiles, folded by warps, merged across tiles);
     reducer-side merge shape: int64 count partials summed, float64 min / max partials with NaN = no value"""
     rng = np.random.default_rng(45)
