@@ -36,7 +36,7 @@
 #define BK_SKEW_ROWS (64 * BK_TARGET)   // a longer bucket (one hot key) would serialise on one CTA: decline
 
 struct BktParams {
-  const uint64_t* rows;       // row-major staging: row i at rows + i * W, keys first, then the value columns
+  const uint64_t* __restrict__ rows;   // row-major staging: row i at rows + i * W, keys first, then the value columns
   int W;
   long long T;
   int logB;
@@ -172,13 +172,6 @@ __device__ __forceinline__ int bk_find_or_insert(uint64_t* tab_keys, int* tab_id
   return g;
 }
 
-__device__ __forceinline__ uint64_t bk_shfl_down(uint64_t v, int o) {
-  uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
-  lo = __shfl_down_sync(0xffffffffu, lo, o);
-  hi = __shfl_down_sync(0xffffffffu, hi, o);
-  return ((uint64_t)hi << 32) | lo;
-}
-
 template <int NK>
 __global__ void __launch_bounds__(BK_THREADS) k_bucket_agg(const BktParams p) {
   __shared__ uint64_t tab_keys[NK * BK_TAB];
@@ -295,39 +288,75 @@ __global__ void __launch_bounds__(BK_THREADS) k_bucket_agg(const BktParams p) {
         const int a0 = L.col_begin[c], na_c = L.col_begin[c + 1] - a0;
         if (na_c == 0) continue;
         const int dt = L.acc[a0].dt;
-        uint64_t acc[BK_MAXA];
-#pragma unroll
-        for (int q = 0; q < BK_MAXA; ++q) acc[q] = q < na_c ? mgb_acc_init(L.acc[a0 + q].op) : 0;
+        // the five canonical accumulators of the column, in registers: sum, sum of squares, count, and the
+        // sortable encodings of min / max (table representation, mgb_common.cuh); whichever the spec asks
+        // for is picked at the end.  Loads are issued four at a time (they are independent).
         const uint64_t* col0 = p.rows + nk + c;      // value c of row i at col0[i * W]
         const long long W = p.W;
         const int j0 = pass == 0 ? 0 : lane, jstep = pass == 0 ? 1 : 32;
-#pragma unroll 2
-        for (int j = j0; j < n; j += jstep) {
-          const uint64_t x = __ldg(col0 + (long long)r_loc[sorted[st + j]] * W);
+        double fs = 0.0, fq = 0.0;
+        unsigned long long is = 0, iq = 0, cn = 0, mn = ~0ULL, mx = 0ULL;
+        const bool f64 = dt == MGB_F64;
+        for (int j = j0; j < n; j += 4 * jstep) {
+          uint64_t x[4];
+          bool have[4];
 #pragma unroll
-          for (int q = 0; q < BK_MAXA; ++q) {
-            if (q < na_c) {
-              uint64_t t;
-              if (mgb_contrib(L.acc[a0 + q].op, dt, x, &t)) acc[q] = mgb_combine(L.acc[a0 + q].kind, acc[q], t);
+          for (int u = 0; u < 4; ++u) {
+            const int jj = j + u * jstep;
+            have[u] = jj < n;
+            x[u] = have[u] ? col0[(long long)r_loc[sorted[st + jj]] * W] : 0;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (!have[u]) continue;
+            if (f64) {
+              if (mgb_is_nan_bits(x[u])) continue;
+              const double v = __longlong_as_double((long long)x[u]);
+              fs += v;
+              fq += v * v;
+              const uint64_t e = mgb_enc_f64(x[u]);
+              mn = e < mn ? e : mn;
+              mx = e > mx ? e : mx;
+            } else {
+              is += x[u];
+              iq += x[u] * x[u];
+              const uint64_t e = mgb_enc_i64(x[u]);
+              mn = e < mn ? e : mn;
+              mx = e > mx ? e : mx;
             }
+            ++cn;
           }
         }
         if (pass == 1) {
 #pragma unroll
-          for (int q = 0; q < BK_MAXA; ++q) {
-            if (q < na_c) {
-              const int kind = L.acc[a0 + q].kind;
-#pragma unroll
-              for (int o = 16; o > 0; o >>= 1) acc[q] = mgb_combine(kind, acc[q], bk_shfl_down(acc[q], o));
-            }
+          for (int o = 16; o > 0; o >>= 1) {
+            fs += __shfl_down_sync(0xffffffffu, fs, o);
+            fq += __shfl_down_sync(0xffffffffu, fq, o);
+            is += __shfl_down_sync(0xffffffffu, is, o);
+            iq += __shfl_down_sync(0xffffffffu, iq, o);
+            cn += __shfl_down_sync(0xffffffffu, cn, o);
+            const unsigned long long a = __shfl_down_sync(0xffffffffu, mn, o);
+            const unsigned long long z = __shfl_down_sync(0xffffffffu, mx, o);
+            mn = a < mn ? a : mn;
+            mx = z > mx ? z : mx;
           }
           if (lane != 0) continue;
         }
 #pragma unroll
         for (int q = 0; q < BK_MAXA; ++q) {
           if (q < na_c) {
+            const int op = L.acc[a0 + q].op;
+            uint64_t v;
+            if (op == MGB_SUM)
+              v = f64 ? (uint64_t)__double_as_longlong(fs) : (uint64_t)is;
+            else if (op == MGB_SUMSQ)
+              v = f64 ? (uint64_t)__double_as_longlong(fq) : (uint64_t)iq;
+            else if (op == MGB_COUNT)
+              v = (uint64_t)cn;
+            else
+              v = op == MGB_MIN ? (uint64_t)mn : (uint64_t)mx;
             uint64_t* dst = p.scratch + (long long)(nk + L.acc_index[a0 + q]) * T + lo + g;
-            *dst = g >= ng_before ? acc[q] : mgb_combine(L.acc[a0 + q].kind, *dst, acc[q]);
+            *dst = g >= ng_before ? v : mgb_combine(L.acc[a0 + q].kind, *dst, v);
           }
         }
       }
@@ -335,6 +364,26 @@ __global__ void __launch_bounds__(BK_THREADS) k_bucket_agg(const BktParams p) {
     __syncthreads();
   }
   if (tid == 0) p.gcount[b] = n_unique;
+}
+
+// bucket histogram and (unordered) placement of the row ids: within a bucket the order of the rows does not
+// matter to the fold, so one pass with an atomic cursor per bucket replaces the stable radix passes
+__global__ void __launch_bounds__(256) k_bucket_hist(const int32_t* __restrict__ pid, long long T,
+                                                     unsigned long long* __restrict__ counts) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < T; i += (long long)gridDim.x * blockDim.x)
+    atomicAdd(&counts[pid[i]], 1ULL);
+}
+
+__global__ void __launch_bounds__(256) k_bucket_place(const int32_t* __restrict__ pid, long long T,
+                                                      unsigned long long* __restrict__ cursor,
+                                                      int32_t* __restrict__ perm) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < T; i += (long long)gridDim.x * blockDim.x)
+    perm[atomicAdd(&cursor[pid[i]], 1ULL)] = (int32_t)i;
+}
+
+__global__ void __launch_bounds__(256) k_copy_i64(const int64_t* __restrict__ a, int64_t* __restrict__ b, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    b[i] = a[i];
 }
 
 // longest bucket (skew check)
@@ -474,9 +523,24 @@ int mgb_bucket_aggregate(const Layout& L, const BktSource* srcs_host, int nsrc, 
     }
     MGB_CHECK_LAUNCH();
     bk_debug("k_bucket_pack", st);
-    // 2. row ids in bucket order
-    status = mgb_radix_sort_perm_pid_ex(pid, T, B, perm, out->off, false, st);
-    bk_debug("radix sort by bucket", st);
+    // 2. row ids in bucket order: histogram -> offsets -> placement through one atomic cursor per bucket
+    {
+      const long long blocks = (T + 255) / 256, capg = (long long)mgb_sm_count() * 16;
+      const unsigned g2 = (unsigned)(blocks > capg ? capg : blocks);
+      const unsigned gB = (unsigned)(((long long)B + 256) / 256 > capg ? capg : ((long long)B + 256) / 256);
+      MGB_CUDA(cudaMemsetAsync(out->off, 0, sizeof(int64_t) * ((size_t)B + 1), st));
+      k_bucket_hist<<<g2, 256, 0, st>>>(pid, T, (unsigned long long*)out->off);
+      MGB_CHECK_LAUNCH();
+      status = mgb_scan_exclusive_i64(out->off, (int64_t)B + 1, nullptr, st);
+      if (status == MGB_OK) {
+        // goff doubles as the cursor array until the aggregation kernel overwrites it with the group counts
+        k_copy_i64<<<gB, 256, 0, st>>>(out->off, out->goff, (long long)B + 1);
+        k_bucket_place<<<g2, 256, 0, st>>>(pid, T, (unsigned long long*)out->goff, perm);
+        MGB_CHECK_LAUNCH();
+        MGB_CUDA(cudaMemsetAsync(out->goff + B, 0, sizeof(int64_t), st));
+      }
+    }
+    bk_debug("row ids in bucket order", st);
     if (status == MGB_OK) {   // a hot key makes one bucket as long as its row count: leave that input to the table
       const int gb = (B + 255) / 256;
       k_bucket_max<<<gb > 1024 ? 1024 : gb, 256, 0, st>>>(out->off, B, d_err + 1);
