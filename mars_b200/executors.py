@@ -193,7 +193,7 @@ _map_plans: Dict[Any, _MapPlan] = {}
 
 _map_plans_fast: Dict[Any, Any] = {}
 _DEVICE_RESULTS = os.environ.get("MGB_DEVICE_RESULTS", "1") not in ("0", "")
-_DEVICE_RESULT_ROWS = int(os.environ.get("MGB_DEVICE_RESULT_ROWS", "65536"))   # smaller results go straight to pandas
+_DEVICE_RESULT_ROWS = int(os.environ.get("MGB_DEVICE_RESULT_ROWS", "2049"))   # smaller results go straight to pandas
 _PREAGG_GROUPS = 2048     # chunks with at most this many groups are worth the shared-memory pre-aggregation
 
 
@@ -642,7 +642,7 @@ def _multi_index(arrays, names):
     try:
         levels, codes = [], []
         for a in arrays:
-            lv, inv = np.unique(a, return_inverse=True)
+            inv, lv = pd.factorize(a, sort=True)     # hash-based: linear in the rows, sorts the distinct values only
             levels.append(pd.Index(lv))
             codes.append(inv)
         return pd.MultiIndex(levels=levels, codes=codes, names=names, verify_integrity=False)

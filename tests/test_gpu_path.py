@@ -170,7 +170,7 @@ def test_empty_reducers_and_tiny_input(md):
 
 @pytest.mark.parametrize("nkeys,sort", [(1, False), (2, False), (1, True)])
 def test_large_result_chunks_stay_on_the_device_until_fetch(md, nkeys, sort):
-    """result chunks of >= 65536 groups are DeviceResult objects (the reference's GPU mode returns cudf frames);
+    """result chunks of more than 2048 groups are DeviceResult objects (the reference's GPU mode returns cudf frames);
     fetch() reads all of them into one pinned block -- same frame as pandas"""
     from mars_b200.executors import DeviceResult
 
