@@ -26,12 +26,15 @@
 
 #include "mgb_layout.cuh"
 
+#ifndef BK_THREADS
 #define BK_THREADS 256
+#endif
 #define BK_TAB 1024           // key table slots per bucket (power of two)
 #define BK_MAXG 896           // groups per bucket before overflow is declared (load <= 7/8)
 #define BK_RT 1024            // rows per tile
 #define BK_TARGET 512         // average rows per bucket (upper bound)
 #define BK_BIG 32             // groups with >= BK_BIG rows in a tile are folded by a whole warp
+#define BK_EPT (BK_TAB / BK_THREADS)   // table entries per thread in the block scan
 #define BK_MAXA 8             // accumulators per value column handled in registers
 #define BK_SKEW_ROWS (64 * BK_TARGET)   // a longer bucket (one hot key) would serialise on one CTA: decline
 
@@ -235,18 +238,17 @@ __global__ void __launch_bounds__(BK_THREADS) k_bucket_agg(const BktParams p) {
       return;
     }
     const int ng = n_unique;
-    // 2. exclusive scan of cnt[0..ng) (4 entries per thread)
+    // 2. exclusive scan of cnt[0..ng) (BK_EPT consecutive entries per thread)
     {
-      const int base = tid * 4;
-      int v0 = base + 0 < ng ? cnt[base + 0] : 0;
-      int v1 = base + 1 < ng ? cnt[base + 1] : 0;
-      int v2 = base + 2 < ng ? cnt[base + 2] : 0;
-      int v3 = base + 3 < ng ? cnt[base + 3] : 0;
-      const int tot = v0 + v1 + v2 + v3;
-      if (v0 >= BK_BIG) big[atomicAdd(&n_big, 1)] = base + 0;
-      if (v1 >= BK_BIG) big[atomicAdd(&n_big, 1)] = base + 1;
-      if (v2 >= BK_BIG) big[atomicAdd(&n_big, 1)] = base + 2;
-      if (v3 >= BK_BIG) big[atomicAdd(&n_big, 1)] = base + 3;
+      const int base = tid * BK_EPT;
+      int v[BK_EPT];
+      int tot = 0;
+#pragma unroll
+      for (int q = 0; q < BK_EPT; ++q) {
+        v[q] = base + q < ng ? cnt[base + q] : 0;
+        if (v[q] >= BK_BIG) big[atomicAdd(&n_big, 1)] = base + q;
+        tot += v[q];
+      }
       int x = tot;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
@@ -255,13 +257,16 @@ __global__ void __launch_bounds__(BK_THREADS) k_bucket_agg(const BktParams p) {
       }
       if (lane == 31) warp_tot[warp] = x;
       __syncthreads();
-      int wp = 0;
-      for (int w = 0; w < warp; ++w) wp += warp_tot[w];
-      const int e = wp + x - tot;
-      if (base + 0 < ng) { cnt[base + 0] = e; cursor[base + 0] = e; }
-      if (base + 1 < ng) { cnt[base + 1] = e + v0; cursor[base + 1] = e + v0; }
-      if (base + 2 < ng) { cnt[base + 2] = e + v0 + v1; cursor[base + 2] = e + v0 + v1; }
-      if (base + 3 < ng) { cnt[base + 3] = e + v0 + v1 + v2; cursor[base + 3] = e + v0 + v1 + v2; }
+      int e = x - tot;
+      for (int w = 0; w < warp; ++w) e += warp_tot[w];
+#pragma unroll
+      for (int q = 0; q < BK_EPT; ++q) {
+        if (base + q < ng) {
+          cnt[base + q] = e;
+          cursor[base + q] = e;
+        }
+        e += v[q];
+      }
       if (tid == 0) cnt[ng] = m;
     }
     __syncthreads();
