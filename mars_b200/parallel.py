@@ -193,6 +193,15 @@ class Exchange:
         return out
 
     @staticmethod
+    def _unwrap(entry):
+        """shuffle block in ctx -> (payload, wrapped): the hash shuffle stores ``(mapper_index, payload)``
+        (groupby/core.py:389-435), the range shuffle of sort=True the bare tuple of frames (sort.py:113-135)"""
+        if (isinstance(entry, tuple) and len(entry) == 2 and not isinstance(entry[0], DeviceFrame)
+                and isinstance(entry[1], (tuple, DeviceFrame))):
+            return entry[1], True
+        return entry, False
+
+    @staticmethod
     def _payload_frames(payload) -> Tuple[List[DeviceFrame], bool]:
         if isinstance(payload, tuple):
             return [f for f in payload if isinstance(f, DeviceFrame)], True
@@ -238,11 +247,11 @@ class Exchange:
         def key_of(m, r):
             return (m.key, (r, m.index[1] if len(m.index) > 1 else 0))
 
-        counts, schema, as_tuple = {}, None, True
+        counts, schema, as_tuple, wrapped = {}, None, True, True
         for i in local:
             m = mappers[i]
             for r in range(R):
-                _, payload = ctx[key_of(m, r)]
+                payload, wrapped = self._unwrap(ctx[key_of(m, r)])
                 frames, as_tuple = self._payload_frames(payload)
                 counts[(i, r)] = len(frames[0])
                 if schema is None:
@@ -272,7 +281,7 @@ class Exchange:
                 m = mappers[i]
                 for r in reducers_of[p]:
                     key = key_of(m, r)
-                    frames, _ = self._payload_frames(ctx[key][1])
+                    frames, _ = self._payload_frames(self._unwrap(ctx[key])[0])
                     n = len(frames[0])
                     if n:
                         for c, t in enumerate(self._flatten(frames)):
@@ -294,13 +303,17 @@ class Exchange:
         if pull:
             torch.cuda.current_stream().synchronize()   # the arena is complete before its handle is published
         # ---- one metadata all-gather: block counts (+ the arena handle and slice offsets for pull transports)
-        metas = self._gather_meta(dict(counts=counts, schema=schema, as_tuple=as_tuple, handle=handle,
+        metas = self._gather_meta(dict(counts=counts, schema=schema, as_tuple=as_tuple, wrapped=wrapped, handle=handle,
                                        send_off=send_off if pull else None))
         all_counts = {}
         for m_ in metas:
             all_counts.update(m_["counts"])
             if schema is None and m_["schema"] is not None:
-                schema, as_tuple = m_["schema"], m_["as_tuple"]
+                schema, as_tuple, wrapped = m_["schema"], m_["as_tuple"], m_["wrapped"]
+
+        def entry(m, block):   # hash shuffle blocks carry the mapper index, range shuffle blocks do not
+            return (m.index, block) if wrapped else block
+
         if schema is None:
             if pull:
                 dist.barrier(group=self.meta_group)
@@ -331,7 +344,7 @@ class Exchange:
                     for i, m in enumerate(mappers):
                         if owner_of_mapper[i] == q:
                             for r in reducers_of[self.rank]:
-                                ctx[key_of(m, r)] = (m.index, self._rebuild(
+                                ctx[key_of(m, r)] = entry(m, self._rebuild(
                                     schema, [recvbuf[:0].view(dt) for dt in dtypes], 0, 0, as_tuple))
                 continue
             cols = [recvbuf[recv_off[q] + c * recv_rows[q]: recv_off[q] + (c + 1) * recv_rows[q]].view(dtypes[c])
@@ -342,7 +355,7 @@ class Exchange:
                     continue
                 for r in reducers_of[self.rank]:
                     n = all_counts[(i, r)]
-                    ctx[key_of(m, r)] = (m.index, self._rebuild(schema, cols, pos, pos + n, as_tuple))
+                    ctx[key_of(m, r)] = entry(m, self._rebuild(schema, cols, pos, pos + n, as_tuple))
                     pos += n
 
     # ------------------------------------------------------------------------------- point-to-point fetch
@@ -350,10 +363,18 @@ class Exchange:
         """Move ctx[key] (a tuple of partial frames) from rank src to rank dst (tree branch gather)."""
         box = [None]
         if self.rank == src:
-            frames, as_tuple = self._payload_frames(ctx[key])
-            box = [dict(schema=self._schema(frames), n=len(frames[0]), as_tuple=as_tuple)]
+            value = ctx[key]
+            frames, as_tuple = self._payload_frames(value)
+            if frames and all(isinstance(f, DeviceFrame) for f in frames):
+                box = [dict(schema=self._schema(frames), n=len(frames[0]), as_tuple=as_tuple)]
+            else:   # small host objects (PSRS samples / pivots: pandas index frames, numpy arrays)
+                box = [dict(obj=value)]
         dist.broadcast_object_list(box, src=src, group=self.meta_group)
         meta = box[0]
+        if "obj" in meta:
+            if self.rank == dst:
+                ctx[key] = meta["obj"]
+            return
         if self.rank not in (src, dst):
             return
         n = meta["n"]

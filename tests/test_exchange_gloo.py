@@ -72,6 +72,15 @@ def _worker(rank, world, port, case, q):
             exp = raw.groupby(["key", "k2"]).agg(["sum", "mean", "count", "min", "max", "var"])
             q.put((rank, got.sort_index().equals(exp) or _close(got.sort_index(), exp), ex.shuffle_rows_sent,
                    sorted(set(sess.executed_ops))))
+        elif case == "psrs":   # sort=True shuffle: samples -> pivots -> range shuffle across ranks
+            ex = parallel.Exchange(GlooTransport(rank, world), rank, world)
+            sess = md.new_session(exchange=ex, default=False)
+            r = md.DataFrame(raw, chunk_size=500).to_gpu().groupby(["key", "k2"], sort=True) \
+                .agg(["sum", "mean", "count", "min", "max"], method="shuffle")
+            r.execute(session=sess)
+            got = sess.fetch(r)
+            exp = raw.groupby(["key", "k2"]).agg(["sum", "mean", "count", "min", "max"])
+            q.put((rank, _close(got, exp), ex.shuffle_rows_sent, sorted(set(sess.executed_ops))))
         else:   # sharded tree: each rank owns half of the rows
             half = raw.iloc[rank * (n // 2):(rank + 1) * (n // 2)]
             sess = md.new_session(default=False)
@@ -114,6 +123,17 @@ def test_hash_shuffle_across_two_ranks():
         assert ok, f"rank {rank}: result differs from pandas"
         assert rows_sent > 0                      # blocks really crossed ranks
         assert "DataFrameGroupByOperand:map" in ops and "DataFrameGroupByOperand:reduce" in ops
+
+
+@pytest.mark.timeout(180)
+def test_psrs_sort_shuffle_across_two_ranks():
+    """groupby(sort=True) + shuffle over two ranks: the sample / pivot / range-split operands of
+    mars/dataframe/groupby/sort.py; the fetched frame is globally sorted (no sort_index before comparing)"""
+    out = _run("psrs", 29643)
+    for rank, ok, rows_sent, ops in out:
+        assert ok, f"rank {rank}: result differs from pandas"
+        assert rows_sent > 0
+    assert any("DataFrameGroupbySortShuffle:map" in ops for _, _, _, ops in out)
 
 
 @pytest.mark.timeout(180)

@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--keys", type=int, default=1_000_000)
     ap.add_argument("--chunks-per-gpu", type=int, default=4)
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--sort", action="store_true", help="groupby(sort=True): PSRS range shuffle instead of the hash shuffle")
     args = ap.parse_args()
     ex = parallel.init_exchange("gloo")          # gloo: host metadata; bytes move through libmarsgb + NCCL
     rank, world = ex.rank, ex.world
@@ -50,7 +51,7 @@ def main():
     times = []
     for it in range(4):
         sess = md.new_session(exchange=ex, default=False)
-        r = md.DataFrame.from_chunks(pieces).groupby("key", sort=False).agg(["sum", "count"], method="shuffle")
+        r = md.DataFrame.from_chunks(pieces).groupby("key", sort=args.sort).agg(["sum", "count"], method="shuffle")
         if it == 1:
             ex.transport._events.clear()
         torch.cuda.synchronize()
@@ -66,7 +67,7 @@ def main():
     got = sess.fetch(r) if args.check else None      # gathers every result chunk as pandas: small inputs only
     if args.check and rank == 0:
         exp = raw.groupby("key").agg(["sum", "count"])
-        g = got.sort_index()
+        g = got if args.sort else got.sort_index()      # sort=True: the fetched frame must already be ordered
         ok = bool(g.index.equals(exp.index) and np.array_equal(g[("v", "count")], exp[("v", "count")])
                   and np.allclose(g[("v", "sum")], exp[("v", "sum")], rtol=1e-9, atol=0))
     ms, nbytes = ex.transport.exchange_stats()          # runs 1..3 (run 0 = warm-up incl. NCCL connection setup)
@@ -76,7 +77,7 @@ def main():
     if rank == 0:
         worst_ms = max(float(s_[0]) for s_ in stats)
         per_gpu_bytes = max(float(s_[1]) for s_ in stats)
-        print(json.dumps({"n_gpus": world, "transport": type(ex.transport).__name__, "rows": args.rows, "groups": int(local_groups.item()), "chunks": n_chunks,
+        print(json.dumps({"n_gpus": world, "sort": bool(args.sort), "transport": type(ex.transport).__name__, "rows": args.rows, "groups": int(local_groups.item()), "chunks": n_chunks,
                           "parity_vs_pandas": ok, "seconds_per_run": times, "rows_per_s": args.rows / min(times[1:]),
                           "exchange": {"runs": 3, "device_ms_max_over_ranks": worst_ms,
                                        "bytes_sent_per_gpu": per_gpu_bytes,
