@@ -115,13 +115,40 @@ _dtypes_cache: dict = {}
 
 
 class ColumnSet:
-    """Equally long device columns that many row-range frames share (the output of one partition scatter), with
-    their base pointers read once."""
-    __slots__ = ("cols", "ptrs")
+    """Equally long device columns that many frames share -- the output of one partition scatter, or the
+    int64 / float64 block pair of one aggregation result -- with their base pointers known without creating a
+    tensor view per column.  ``cols`` (the views) are only built when a consumer asks for tensors."""
+    __slots__ = ("_cols", "ptrs", "_block", "dtypes", "device")
 
     def __init__(self, cols: Sequence[torch.Tensor]):
-        self.cols = list(cols)
-        self.ptrs = [t.data_ptr() for t in self.cols]
+        self._cols = list(cols)
+        self.ptrs = [t.data_ptr() for t in self._cols]
+        self._block = None
+        self.dtypes = [t.dtype for t in self._cols]
+        self.device = self._cols[0].device if self._cols else None
+
+    @classmethod
+    def from_block(cls, bi: torch.Tensor, bf: torch.Tensor, layout) -> "ColumnSet":
+        """columns of a result block pair (kernels._FastCall layout): keys first, then the accumulators in spec
+        order; pointers by arithmetic on the two base pointers"""
+        s = cls.__new__(cls)
+        s._cols = None
+        s._block = (bi, bf, layout)
+        pi, pf, stride = bi.data_ptr(), bf.data_ptr(), bi.shape[1] * 8
+        s.ptrs = [pi + j * stride for j in range(layout.nk)] + [
+            (pf + layout.float_row[a] * stride) if layout.is_float[a] else (pi + layout.int_row[a] * stride)
+            for a in range(layout.na)]
+        s.dtypes = layout.col_dtypes
+        s.device = bi.device
+        return s
+
+    @property
+    def cols(self):
+        if self._cols is None:
+            bi, bf, layout = self._block
+            k, a = layout.views(bi, bf)
+            self._cols = list(k) + list(a)
+        return self._cols
 
 
 class DeviceFrame:
@@ -155,7 +182,7 @@ class DeviceFrame:
     # ---- row range of shared columns (shuffle blocks) ---------------------------------------------------
     @classmethod
     def from_range(cls, index_names, columns, src: "ColumnSet", k0: int, k1: int, d0: int, d1: int, a: int,
-                   b: int) -> "DeviceFrame":
+                   b: int, pending: Optional[Pending] = None, slot=None) -> "DeviceFrame":
         """Rows [a, b) of ``src.cols[k0:k1]`` (group keys) and ``src.cols[d0:d1]`` (data): a shuffle block.  A
         mapper emits R x K of these per chunk; nothing is sliced until a consumer asks for tensors, and the
         aggregation kernels never do -- they take ``ptrs()``."""
@@ -165,10 +192,13 @@ class DeviceFrame:
         f.columns = columns
         f._data = None
         f._n = b - a
-        f._pending = None
-        f._slot = None
+        f._pending = pending
+        f._slot = slot
         f._home = None
         f._src = (src, k0, k1, d0, d1, a, b)
+        if pending is not None:      # rows [0, capacity) of a speculative result: the size is still on the device
+            pending.attach(f)
+            f._n = None
         return f
 
     def _mat(self):
@@ -177,6 +207,16 @@ class DeviceFrame:
         self._index = [t[a:b] for t in cols[k0:k1]]
         self._data = [t[a:b] for t in cols[d0:d1]]
         self._src = None
+
+    def ptrs_raw(self):
+        """like ``ptrs`` but without resolving a pending size (capacity-length columns; the consumer reads the
+        row count on the device)"""
+        if self._src is not None:
+            src, k0, k1, d0, d1, a, b = self._src
+            off, p = a * 8, src.ptrs
+            return [x + off for x in p[k0:k1]], [x + off for x in p[d0:d1]]
+        idx = self._index
+        return ([t.data_ptr() for t in idx] if idx else []), [t.data_ptr() for t in self._data]
 
     def ptrs(self):
         """(key column pointers, data column pointers) as integers"""
@@ -198,12 +238,18 @@ class DeviceFrame:
 
     def _finalize(self, n: int):
         """the speculative columns are valid: cut the capacity-length views down to n rows"""
+        if self._src is not None:
+            src, k0, k1, d0, d1, a, _ = self._src
+            self._src = (src, k0, k1, d0, d1, a, a + n)
+            self._n = n
+            return
         if self._index is not None:
             self._index = [t[:n] for t in self._index]
         self._data = [t[:n] for t in self._data]
         self._n = n
 
     def _repoint(self, keys, accs, n: int):
+        self._src = None
         a0, a1 = self._slot
         self._index = list(keys)
         self._data = list(accs[a0:a1])
@@ -245,7 +291,7 @@ class DeviceFrame:
 
     def col_dtype(self, i: int):
         if self._src is not None:
-            return self._src[0].cols[self._src[3] + i].dtype
+            return self._src[0].dtypes[self._src[3] + i]
         return self._data[i].dtype
 
     @data.setter
@@ -312,7 +358,7 @@ class DeviceFrame:
     @property
     def device(self):
         if self._src is not None:
-            return self._src[0].cols[0].device
+            return self._src[0].device
         if self._home is not None:
             return self._home
         ts = self._data or self._index or []

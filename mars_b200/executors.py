@@ -301,9 +301,13 @@ def _execute_agg_map(ctx, op):
                     k, a, _ = _kernels.groupby_aggregate(keys, all_vals(), accs, sort=False)
                     return k, a
 
-                pend = Pending(bi, fc.n_int, bi.shape[1], replay)
-                ck, ca = fc.views(bi, bf)
-                frames = [DeviceFrame(plan.by, ck, cols, ca[a0:a1], pending=pend, slot=(a0, a1))
+                pend = Pending(bi, fc.n_int, bi.shape[1], replay, fblock=bf, layout=fc)
+                # the K partial frames are row ranges [0, capacity) of the block pair: no tensor view is made
+                # unless a consumer asks for one (the merges of the tree take pointers)
+                src = ColumnSet.from_block(bi, bf, fc)
+                nk, cap = fc.nk, bi.shape[1]
+                frames = [DeviceFrame.from_range(plan.by, cols, src, 0, nk, nk + a0, nk + a1, 0, cap, pending=pend,
+                                                 slot=(a0, a1))
                           for cols, a0, a1 in plan.slots]
         elif hasattr(_kernels, "preagg_dense"):
             vals = all_vals()
@@ -384,22 +388,31 @@ def _merge_partials(slots: Sequence[Sequence[DeviceFrame]], steps: Sequence[_Ste
         if small and _ASYNC and hasattr(_kernels, "merge_small_async"):
             # sizes that are still on the device stay there: the merge reads them in the kernel
             pieces = []
+            dev = base[0].device
+            dts = [_kernels.F64 if slots[s][0].col_dtype(j) == torch.float64 else _kernels.I64
+                   for s in grp for j in range(len(slots[s][0].columns))]
+
+            def piece_of(i, n, cptr):
+                kp, ap = base[i].ptrs_raw()
+                for s_ in grp[1:]:
+                    ap = ap + slots[s_][i].ptrs_raw()[1]
+                return (kp, ap, n, cptr, dts, dev)
+
             for i in range(len(base)):
                 f0 = base[i]
-                cols = [t for s in grp for t in slots[s][i].raw_data]
                 if f0.is_pending:
-                    pieces.append((f0.raw_index, cols, None, f0._pending.count_ptr()))
+                    pieces.append(piece_of(i, None, f0._pending.count_ptr()))
                 elif len(f0) > 0:
-                    pieces.append((f0.raw_index, cols, len(f0), 0))
+                    pieces.append(piece_of(i, len(f0), 0))
             if not pieces:
-                pieces.append((base[0].raw_index, [t for s in grp for t in slots[s][0].raw_data], 0, 0))
+                pieces.append(piece_of(0, 0, 0))
             res = _kernels.merge_small_async(pieces, ops, sort=force_sort, checked=True)
             if res is not None:
                 bi, bf, fc = res
                 pend_out = Pending(bi, fc.n_int, bi.shape[1],
                                    lambda grp=grp, ops=ops: _merge_general(slots, grp, ops, force_sort),
                                    fblock=bf, layout=fc)
-                k, a = fc.views(bi, bf)
+                out_src = ColumnSet.from_block(bi, bf, fc)
         if pend_out is None:
             res = None
             live = [i for i in range(len(base)) if len(base[i]) > 0] or [0]
@@ -412,8 +425,10 @@ def _merge_partials(slots: Sequence[Sequence[DeviceFrame]], steps: Sequence[_Ste
         for i in grp:
             ncol = len(slots[i][0].columns)
             if pend_out is not None:
-                out[i] = DeviceFrame(base[0].index_names, k, slots[i][0].columns, a[pos:pos + ncol], pending=pend_out,
-                                     slot=(pos, pos + ncol))
+                nk_ = pend_out.layout.nk
+                out[i] = DeviceFrame.from_range(base[0].index_names, slots[i][0].columns, out_src, 0, nk_, nk_ + pos,
+                                                nk_ + pos + ncol, 0, pend_out.cap, pending=pend_out,
+                                                slot=(pos, pos + ncol))
             else:
                 out[i] = DeviceFrame(base[0].index_names, k, slots[i][0].columns, a[pos:pos + ncol], int(k[0].numel()))
             pos += ncol

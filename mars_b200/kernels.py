@@ -247,7 +247,7 @@ class _FastCall:
     """Pre-built ctypes argument arrays of one call shape: per call only raw pointers are filled in."""
 
     __slots__ = ("spec", "nk", "nv", "na", "kp", "vp", "okp", "oap", "is_float", "n_int", "n_float", "int_row",
-                 "float_row", "g")
+                 "float_row", "g", "col_dtypes", "acc_dts")
 
     def __init__(self, nk, dts, accs):
         self.spec = _lib.make_spec(nk, list(dts), list(accs))
@@ -270,6 +270,9 @@ class _FastCall:
                 ni += 1
         self.n_int, self.n_float = ni, nf
         self.g = C.c_int64()
+        # torch dtypes of the output columns (keys, then accumulators) and dtype codes of the accumulators
+        self.col_dtypes = [torch.int64] * nk + [torch.float64 if f else torch.int64 for f in self.is_float]
+        self.acc_dts = [F64 if f else I64 for f in self.is_float]
 
     def alloc(self, cap, device):
         """int64 block [n_keys + int accs + 1, cap] and float64 block [float accs, cap]; output pointers set.
@@ -458,14 +461,32 @@ def merge_small_async(pieces, acc_ops: Sequence[int], sort: bool = False, checke
     if known > SMALL_MAX_ROWS or live > SMALL_MAX_PIECES or na > _lib.MGB_MAX_ACCS or na > _lib.MGB_MAX_VALS:
         return None
     nk = len(pieces[0][0])
-    dts = [F64 if t.dtype == torch.float64 else I64 for t in pieces[0][1]]
+    by_ptr = len(pieces[0]) == 6        # (key pointers, accumulator pointers, n, count pointer, dtype codes, device)
+    if by_ptr:
+        dts = pieces[0][4]
+        out_device = pieces[0][5]
+    else:
+        dts = [F64 if t.dtype == torch.float64 else I64 for t in pieces[0][1]]
+        out_device = pieces[0][0][0].device
     fc = _fast(nk, dts, tuple((a, op) for a, op in enumerate(acc_ops)))
     kt = (_lib._pp * max(n_pieces, 1))()
     at = (_lib._pp * max(n_pieces, 1))()
     rows_arr = (C.c_int64 * max(n_pieces, 1))()
     rows_dev = (C.c_void_p * max(n_pieces, 1))()
     keep = []
-    for i, (pk, pa, n, cptr) in enumerate(pieces):
+    for i, piece in enumerate(pieces):
+        pk, pa, n, cptr = piece[0], piece[1], piece[2], piece[3]
+        if by_ptr:
+            if piece[4] != dts and list(piece[4]) != list(dts):
+                raise MarsGBError(1, "partial blocks differ in accumulator dtype")
+            karr = (C.c_void_p * nk)(*pk)
+            aarr = (C.c_void_p * max(na, 1))(*pa)
+            keep.append((karr, aarr))
+            kt[i] = C.cast(karr, _lib._pp)
+            at[i] = C.cast(aarr, _lib._pp)
+            rows_arr[i] = -1 if n is None else int(n)
+            rows_dev[i] = cptr if n is None else None
+            continue
         karr = (C.c_void_p * nk)()
         aarr = (C.c_void_p * max(na, 1))()
         for j, t in enumerate(pk):
@@ -483,7 +504,7 @@ def merge_small_async(pieces, acc_ops: Sequence[int], sort: bool = False, checke
         at[i] = C.cast(aarr, _lib._pp)
         rows_arr[i] = -1 if n is None else int(n)
         rows_dev[i] = cptr if n is None else None
-    bi, bf = fc.alloc(SMALL_MAX_ROWS, pieces[0][0][0].device)
+    bi, bf = fc.alloc(SMALL_MAX_ROWS, out_device)
     check(lib.mgb_merge_small_async(C.byref(fc.spec), n_pieces, rows_arr, rows_dev, kt, at, fc.okp, fc.oap,
                                     SMALL_MAX_ROWS, 1 if sort else 0, fc.count_ptr(bi), _stream()))
     _count(1)
