@@ -586,8 +586,14 @@ def _assemble_result(host: Dict[Any, Any], idx_arrays, meta) -> pd.DataFrame:
     if meta["as_index"] and len(set(labels)) == len(labels) and set(labels) == set(col_value):
         # declared column order == a permutation of what was computed: assemble in that order, one block per
         # column and no consolidation copy (copy=False) -- the frame wraps the arrays that came off the device
-        result = pd.DataFrame({i: host[l] for i, l in enumerate(col_value)}, index=index, copy=False)
-        result.columns = col_value
+        if len(index) < 4096 and hasattr(pd.DataFrame, "_from_arrays"):
+            # tiny results: the array-list constructor skips most of the per-column validation (it copies
+            # into consolidated blocks, which is free at this size)
+            result = pd.DataFrame._from_arrays([host[l] for l in col_value], columns=col_value, index=index,
+                                               verify_integrity=False)
+        else:
+            result = pd.DataFrame({i: host[l] for i, l in enumerate(col_value)}, index=index, copy=False)
+            result.columns = col_value
     if result is None:
         result = pd.DataFrame({i: host[l] for i, l in enumerate(labels)}, index=index)
         result.columns = pd.MultiIndex.from_tuples(labels) if meta["two_level"] else pd.Index(labels)
@@ -657,7 +663,10 @@ def _multi_index(arrays, names):
     try:
         levels, codes = [], []
         for a in arrays:
-            inv, lv = pd.factorize(a, sort=True)     # hash-based: linear in the rows, sorts the distinct values only
+            if len(a) < 4096:     # tiny results (the tree branch): the sort-based path has the smaller fixed cost
+                lv, inv = np.unique(a, return_inverse=True)
+            else:                 # hash-based: linear in the rows, sorts the distinct values only
+                inv, lv = pd.factorize(a, sort=True)
             levels.append(pd.Index(lv))
             codes.append(inv)
         return pd.MultiIndex(levels=levels, codes=codes, names=names, verify_integrity=False)
