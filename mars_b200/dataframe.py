@@ -392,6 +392,8 @@ class DataFrame:
         if columns is None:
             columns = pd.Index(list(first.columns))
             if ckey is not None:
+                if len(_columns_cache) > 256:
+                    _columns_cache.clear()
                 _columns_cache[ckey] = columns
         n = sum(len(c) for c in chunks)
         op = DataFrameDataSource(gpu=gpu)

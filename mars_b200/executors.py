@@ -257,6 +257,8 @@ def _map_plan_slow(op, frame: DeviceFrame) -> _MapPlan:
     plan.shape_key = (tuple(by), tuple(used), plan.accs)
     plan._by_dtypes = {}
     if sig is not None:
+        if len(_map_plans) > 1024:
+            _map_plans.clear()
         _map_plans[sig] = plan
     return plan
 
@@ -333,6 +335,8 @@ def _execute_agg_map(ctx, op):
             if stats and stats.get("rows_spilled", 0) * 2 > int(keys[0].numel()):
                 _distinct_shapes.add(plan.shape_key)
         n_out = int(out_keys[0].numel())
+        if n_out <= 32:
+            _dense_rejected.discard(plan.shape_key)      # the data changed: the one-launch path fits again
         frames = [DeviceFrame(plan.by, out_keys, cols, out_accs[a0:a1], n_out) for cols, a0, a1 in plan.slots]
     if rec is not None:   # method='auto' samples real sizes: resolves the count when the recorder is read
         _record_sizes(ctx, rec, frame.nbytes,
