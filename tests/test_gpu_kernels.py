@@ -436,6 +436,18 @@ def test_bucketed_aggregation_wide_min_max_var_shape(K):
     assert _bucketed(stats), stats
 
 
+def test_bucketed_aggregation_many_columns(K):
+    """24 value columns: the row-major staging tile of the pack kernel needs more than 48 KB of shared memory
+    (opt-in attribute), and the fold walks 24 (group, column) items per group"""
+    rng = np.random.default_rng(48)
+    n = 150_000
+    keys = [rng.integers(0, 60_000, n, dtype=np.int64)]
+    vals = [rng.normal(10, 3, n) if c % 3 else rng.integers(-50, 50, n, dtype=np.int64) for c in range(24)]
+    accs = [(c, "sum") for c in range(24)] + [(c, "max") for c in range(24)]
+    stats = check_agg(K, keys, vals, accs, batches=3, distinct=True)
+    assert _bucketed(stats), stats
+
+
 def test_bucketed_aggregation_skew_and_merge_ops(K):
     """one key holds 4 % of the rows (a bucket of many tiles, folded by warps, merged across tiles);
     reducer-side merge shape: int64 count partials summed, float64 min / max partials with NaN = no value"""
