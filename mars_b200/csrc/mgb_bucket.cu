@@ -176,7 +176,7 @@ __device__ __forceinline__ int bk_find_or_insert(uint64_t* tab_keys, int* tab_id
 }
 
 template <int NK>
-__global__ void __launch_bounds__(BK_THREADS) k_bucket_agg(const BktParams p) {
+__global__ void __launch_bounds__(BK_THREADS, 5) k_bucket_agg(const BktParams p) {
   __shared__ uint64_t tab_keys[NK * BK_TAB];
   __shared__ int tab_idx[BK_TAB];
   __shared__ int cnt[BK_TAB + 1];      // rows per group of the current tile -> exclusive starts
