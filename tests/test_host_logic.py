@@ -172,3 +172,75 @@ def test_errors_wrap_into_execution_error(md):
     r = md.DataFrame(raw, chunk_size=1).to_gpu().groupby("key").agg(["sum"], method="tree")
     with pytest.raises(ExecutionError):
         r.execute(session=md.new_session(default=False))
+
+
+# ------------------------------------------------------------------- frames that are not sliced until asked
+def test_row_range_frames_give_pointers_without_slicing():
+    """shuffle blocks / result partials are row ranges of shared columns (DeviceFrame.from_range): pointers by
+    arithmetic, tensors only on demand, and both views agree"""
+    from mars_b200.device import ColumnSet, DeviceFrame
+
+    cols = [torch.arange(100, dtype=torch.int64), torch.arange(100, dtype=torch.float64) * 2,
+            torch.arange(100, dtype=torch.float64) * 3]
+    src = ColumnSet(cols)
+    f = DeviceFrame.from_range(["k"], ["a", "b"], src, 0, 1, 1, 3, 10, 25)
+    g = DeviceFrame.from_range(["k"], ["a", "b"], src, 0, 1, 1, 3, 10, 25)
+    h = DeviceFrame.from_range(["k"], ["a", "b"], src, 0, 1, 1, 3, 25, 40)
+    assert len(f) == 15 and f.nbytes == 15 * 8 * 3 and f.col_dtype(0) == torch.float64
+    assert f.same_index(g) and not f.same_index(h)
+    kp, dp = f.ptrs()
+    assert f._src is not None                        # nothing was sliced so far
+    assert kp == [cols[0].data_ptr() + 80] and dp == [cols[1].data_ptr() + 80, cols[2].data_ptr() + 80]
+    assert f.index[0].tolist() == list(range(10, 25)) and f._src is None      # now it is
+    assert f.data[1].tolist() == [3.0 * i for i in range(10, 25)]
+    assert (kp, dp) == f.ptrs()                      # same pointers from the materialised tensors
+    assert f.same_index(g)                           # mixed: one side sliced, the other not
+
+
+def test_block_backed_column_set_matches_the_block_views():
+    """ColumnSet.from_block: column pointers of a result block pair by arithmetic == pointers of the views"""
+    from mars_b200 import kernels as K
+    from mars_b200.device import ColumnSet, DeviceFrame, Pending
+
+    accs = ((0, K.SUM), (1, K.SUM), (0, K.COUNT), (2, K.MAX), (2, K.COUNT))
+    fc = K._FastCall(2, [K.F64, K.F64, K.I64], accs)
+    bi, bf = fc.alloc(64, "cpu")
+    src = ColumnSet.from_block(bi, bf, fc)
+    keys, outs = fc.views(bi, bf)
+    assert src.ptrs == [t.data_ptr() for t in keys + outs]
+    assert src.dtypes == [t.dtype for t in keys + outs]
+    assert src._cols is None                         # no view was made for the pointers
+    # a pending partial frame over accumulators [1, 3): capacity rows until the count settles
+    bi[fc.n_int, 0] = 7
+    pend = Pending(bi, fc.n_int, 64, lambda: None, fblock=bf, layout=fc)
+    f = DeviceFrame.from_range(["x", "y"], ["p", "q"], src, 0, 2, 2 + 1, 2 + 3, 0, 64, pending=pend, slot=(1, 3))
+    assert f.is_pending and f.ptrs_raw()[1] == [outs[1].data_ptr(), outs[2].data_ptr()]
+    assert len(f) == 7 and not f.is_pending          # resolves: one 8-byte read
+    assert [t.numel() for t in f.data] == [7, 7] and f.data[0].data_ptr() == outs[1].data_ptr()
+
+
+def test_result_frame_assembly_small_and_large_paths_agree():
+    """tiny results take the cheap constructors, large ones the zero-copy ones: same frame either way"""
+    from mars_b200 import executors as E
+
+    rng = np.random.default_rng(3)
+    for n in (5, 5000):
+        k1, k2 = rng.integers(0, 50, n), rng.integers(0, 7, n)
+        cols = pd.MultiIndex.from_tuples([("v", "sum"), ("v", "count"), ("w", "mean")])
+        host = {("v", "count"): rng.integers(1, 9, n), ("w", "mean"): rng.random(n), ("v", "sum"): rng.random(n)}
+        meta = dict(names=["a", "b"], col_value=cols, two_level=True, as_index=True, dtypes=None)
+        got = E._assemble_result(dict(host), [k1, k2], meta)
+        exp = pd.DataFrame({c: host[c] for c in cols}, index=pd.MultiIndex.from_arrays([k1, k2], names=["a", "b"]))
+        pd.testing.assert_frame_equal(got, exp)
+        assert list(got.columns) == list(cols) and got.dtypes.tolist() == exp.dtypes.tolist()
+
+
+def test_session_pauses_and_restores_the_cyclic_gc(md):
+    import gc
+
+    raw = pd.DataFrame({"key": np.arange(40) % 5, "v": np.arange(40.0)})
+    r = md.DataFrame(raw, chunk_size=10).to_gpu().groupby("key").agg(["sum"], method="tree")
+    assert gc.isenabled()
+    got = r.execute(session=md.new_session(default=False))
+    assert gc.isenabled()
+    assert got is r
