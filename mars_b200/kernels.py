@@ -278,8 +278,12 @@ class _FastCall:
         """int64 block [n_keys + int accs + 1, cap] and float64 block [float accs, cap]; output pointers set.
         The last int64 row is scratch for the device-side group count of the asynchronous entry points."""
         cap = max(int(cap), 1)
-        bi = torch.empty((self.n_int + 1, cap), dtype=torch.int64, device=device)
-        bf = torch.empty((max(self.n_float, 1), cap), dtype=torch.float64, device=device)
+        # ONE allocation: the float64 block is a dtype view of the rows behind the int64 block, so a consumer
+        # can ship / read back the whole result (count row included) as a single tensor (``bi._base``)
+        ni = self.n_int + 1
+        blk = torch.empty((ni + max(self.n_float, 1), cap), dtype=torch.int64, device=device)
+        bi = blk[:ni]
+        bf = blk[ni:].view(torch.float64)
         pi, pf, stride = bi.data_ptr(), bf.data_ptr(), cap * 8
         for j in range(self.nk):
             self.okp[j] = pi + j * stride

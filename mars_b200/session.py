@@ -227,12 +227,21 @@ class Session:
             bi, bf, fc = pend.block, pend.fblock, pend.layout
         else:
             bi, bf, fc = self._pack_block(merged, steps, max_groups)
-        gi = torch.empty((world * bi.shape[0], bi.shape[1]), dtype=bi.dtype, device=bi.device)
-        gf = torch.empty((world * bf.shape[0], bf.shape[1]), dtype=bf.dtype, device=bf.device)
-        dist.all_gather_into_tensor(gi, bi, group=group)     # concatenation along dim 0
-        dist.all_gather_into_tensor(gf, bf, group=group)
-        gi = gi.view(world, bi.shape[0], bi.shape[1])
-        gf = gf.view(world, bf.shape[0], bf.shape[1])
+        root = bi._base
+        if root is not None and bf._base is root and root.shape[0] == bi.shape[0] + bf.shape[0]:
+            # both blocks are views of one allocation (kernels._FastCall.alloc): ONE all-gather
+            g = torch.empty((world * root.shape[0], root.shape[1]), dtype=root.dtype, device=root.device)
+            dist.all_gather_into_tensor(g, root, group=group)     # concatenation along dim 0
+            g = g.view(world, root.shape[0], root.shape[1])
+            gi = g[:, :bi.shape[0]]
+            gf = g[:, bi.shape[0]:].view(torch.float64)
+        else:
+            gi = torch.empty((world * bi.shape[0], bi.shape[1]), dtype=bi.dtype, device=bi.device)
+            gf = torch.empty((world * bf.shape[0], bf.shape[1]), dtype=bf.dtype, device=bf.device)
+            dist.all_gather_into_tensor(gi, bi, group=group)
+            dist.all_gather_into_tensor(gf, bf, group=group)
+            gi = gi.view(world, bi.shape[0], bi.shape[1])
+            gf = gf.view(world, bf.shape[0], bf.shape[1])
         if rank != 0:
             return None
 
@@ -242,7 +251,7 @@ class Session:
 
         pieces: List[List[DeviceFrame]] = [[] for _ in merged]
         for r in range(world):
-            pr = Pending(gi[r], fc.n_int, gi.shape[2], no_replay)
+            pr = Pending(gi[r], fc.n_int, gi.shape[2], no_replay)   # gi[r]: rows of rank r's block, contiguous
             k, a = fc.views(gi[r], gf[r])
             a0 = 0
             for i, f in enumerate(merged):
