@@ -12,14 +12,18 @@
 //                   (keys + values) into a ROW-MAJOR staging array through a shared-memory transpose.  The
 //                   gathers of the next kernel then fetch one row = one or two 64-byte DRAM bursts instead
 //                   of one burst per 8-byte column value (measured: 1118 -> ~190 B/row on 80-byte rows).
-//   radix passes    stable permutation of the row ids by bucket + bucket offsets   (mgb_partition.cu)
+//   k_bucket_hist / scan / k_bucket_place
+//                   row ids into bucket order through one atomic cursor per bucket (the order of the rows
+//                   inside a bucket does not matter to the fold, so no stable radix passes are needed)
 //   k_bucket_agg    one CTA per bucket: key table in shared memory (dense group ids), counting sort of the
 //                   bucket's rows by group id, then one thread (one warp for groups of >= 32 rows) per
-//                   (group, value column) folds that group's values in REGISTERS and stores every
-//                   accumulator once.  No atomics on values; buckets of any length are processed in tiles.
+//                   (group, value column) folds that group's values into five canonical REGISTER accumulators
+//                   (sum, sum of squares, count, encoded min / max) and stores every accumulator the spec
+//                   asks for once.  No atomics on values; buckets of any length are processed in tiles.
 //   scan + k_bucket_emit   compaction of the per-bucket results into the caller's columns
 //
-// A bucket that holds more groups than its table reports overflow; the caller then runs the hash-table path.
+// A bucket that holds more groups than its table reports overflow, a bucket far longer than the average (one
+// hot key) is declined before the aggregation kernel runs; the caller then takes the hash-table path.
 #include <stdlib.h>
 
 #include <vector>
