@@ -133,7 +133,7 @@ def check_agg(K, keys, vals, accs, batches=1, expect_path=None, distinct=False):
         if a.dtype.kind in "iu":
             np.testing.assert_array_equal(a[order], b)
         else:
-            np.testing.assert_allclose(a[order], b, rtol=1e-12, equal_nan=True)
+            np.testing.assert_allclose(a[order], b, rtol=1e-9, equal_nan=True)   # two runs: atomics / fold order differ
     return stats
 
 

@@ -194,6 +194,24 @@ def test_large_result_chunks_stay_on_the_device_until_fetch(md, nkeys, sort):
     assert_frames_match(one.to_pandas().sort_index(), exp.loc[one.to_pandas().sort_index().index], sort_index=False)
 
 
+@pytest.mark.parametrize("cfg,scale", [("cfg3", 0.02), ("cfg4", 0.04), ("cfg5", 0.02), ("cfg1-shuffle", 1.0)])
+def test_baseline_configs_through_the_operand_api(md, cfg, scale, capsys):
+    """BASELINE.json configs (scaled down) through tile -> executors -> fetch with device-generated inputs:
+    size-independent properties (sum of counts == rows, keys unique, groups == distinct keys, sum of sums ==
+    column total at 1e-9, min <= max and global extrema); the high-cardinality ones take the bucketed
+    aggregation on both sides of the shuffle.  tools/run_configs.py runs the same at full size."""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import run_configs
+
+    rec = run_configs.run(cfg, scale, 1)
+    capsys.readouterr()
+    assert rec["all_checks_pass"], rec["checks"]
+    assert "DataFrameGroupByOperand:map" in rec["plan"] and "DataFrameGroupByOperand:reduce" in rec["plan"]
+
+
 def test_unsupported_function_raises(md):
     raw, by = make_inputs(100, ("key", 5), 1, seed=3)
     with pytest.raises(NotImplementedError):

@@ -125,13 +125,15 @@ def run(cfg, scale, repeats):
                                         and float(out[(vcol, "max")].max()) == float(max(f.data[f.columns.index(vcol)].max() for f in frames)))
     if kw["sort"]:
         checks["sorted"] = bool(out.index.is_monotonic_increasing)
-    print(json.dumps({"config": cfg, "scale": scale, "rows": n, "chunks": len(frames), "groups": int(len(out)),
-                      "result_chunks": len(r.data.chunks), "plan": sorted(set(sess.executed_ops)),
-                      "seconds": times, "rows_per_s": n / min(times),
-                      "execute_seconds": exec_times, "execute_rows_per_s": n / min(exec_times), "checks": checks,
-                      "all_checks_pass": all(checks.values())}), flush=True)
+    rec = {"config": cfg, "scale": scale, "rows": n, "chunks": len(frames), "groups": int(len(out)),
+           "result_chunks": len(r.data.chunks), "plan": sorted(set(sess.executed_ops)),
+           "seconds": times, "rows_per_s": n / min(times),
+           "execute_seconds": exec_times, "execute_rows_per_s": n / min(exec_times), "checks": checks,
+           "all_checks_pass": all(checks.values())}
+    print(json.dumps(rec), flush=True)
     del frames, out
     torch.cuda.empty_cache()
+    return rec
 
 
 if __name__ == "__main__":
