@@ -1361,6 +1361,11 @@ extern "C" int mgb_agg_emit(mgb_agg* a, int64_t* const* out_key_cols, void* cons
   int64_t* tile_counts = nullptr;
   int status = MGB_OK;
   if (a->bucket_mode) {
+    if (!a->bkt.scratch) {   // the bucketed result is released by its first emit
+      if (tmp) cudaFreeAsync(tmp, st);
+      mgb_set_error("emit called twice on a bucketed aggregation result");
+      return MGB_ERR_STATE;
+    }
     status = mgb_bucket_emit(L, a->bkt, out.key, out.acc, st);
     mgb_bucket_free(&a->bkt, st);
   } else {
