@@ -47,21 +47,10 @@ BYTES_PER_ROW = 8 * len(COLUMNS)          # every input column read once (SURVEY
 L2_BYTES = 126 << 20
 
 
-def gen_chunk(global_chunk_index: int, rows: int) -> dict:
-    """Q1-shaped synthetic lineitem chunk, numpy default_rng(seed + chunk)."""
-    rng = np.random.default_rng(SEED + global_chunk_index)
-    grp = rng.choice(4, size=rows, p=[0.2466, 0.0006, 0.5063, 0.2465])      # AF, NF, NO, RF
-    returnflag = np.array([0, 1, 1, 2], dtype=np.int64)[grp]
-    linestatus = np.array([0, 0, 1, 0], dtype=np.int64)[grp]
-    quantity = rng.integers(1, 51, rows).astype(np.float64)
-    price = rng.uniform(900.0, 105000.0, rows)
-    discount = rng.integers(0, 11, rows) / 100.0
-    tax = rng.integers(0, 9, rows) / 100.0
-    disc_price = price * (1.0 - discount)
-    charge = disc_price * (1.0 + tax)
-    orderkey = rng.integers(1, 60_000_000, rows, dtype=np.int64)
-    return dict(returnflag=returnflag, linestatus=linestatus, quantity=quantity, extendedprice=price,
-                discount=discount, disc_price=disc_price, charge=charge, orderkey=orderkey)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import baseline_configs as bc  # noqa: E402
+
+gen_chunk = bc.CONFIGS["cfg2"].gen      # Q1-shaped synthetic lineitem chunk
 
 
 def chunk_sizes(total_rows: int, chunk_rows: int):
@@ -69,46 +58,110 @@ def chunk_sizes(total_rows: int, chunk_rows: int):
 
 
 # ----------------------------------------------------------------------------------------------------
-# CPU arm: oracle port of the reference's pandas path (bounded sample, all host cores)
+# CPU arm: the reference's OWN operands (unmodified mars-project/mars built into baseline/_ref by
+# oracle/build_ref.sh, driven by oracle/ref_runner.ReferenceTreeRun: its tiling, its compiled reduction steps,
+# its pandas-backed execute(ctx, op); stage=map operands fanned out over all host cores, concat / combine / agg
+# in the parent).  Falls back to the oracle PORT (same pandas arithmetic at the same call sites) only when
+# baseline/_ref is absent, and says which in cpu_baseline.kind.
 # ----------------------------------------------------------------------------------------------------
-_CPU_CHUNKS = None
+def reference_build_available() -> bool:
+    return os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "mars"))
 
 
-def _cpu_map(i):
+def _host_frame(rows: int, chunk_rows: int):
+    """the Q1-shaped frame of `rows` rows, chunk c generated with default_rng(SEED + c) -- the same bytes the
+    GPU arm sees -- written straight into full-length columns (no concat copy)"""
     import pandas as pd
+
+    cols = {name: None for name in COLUMNS}
+    start = 0
+    for c, n in enumerate(chunk_sizes(rows, chunk_rows)):
+        chunk = gen_chunk(c, n)
+        for name in COLUMNS:
+            if cols[name] is None:
+                cols[name] = np.empty(rows, dtype=chunk[name].dtype)
+            cols[name][start:start + n] = chunk[name]
+        start += n
+    return pd.DataFrame(cols, copy=False)
+
+
+_PORT_CHUNKS = None
+
+
+def _port_map(i):
     import mars_groupby_oracle as orc
 
-    return orc.agg_map(pd.DataFrame(_CPU_CHUNKS[i], copy=False), BY, Q1_FUNC)
+    return orc.agg_map(_PORT_CHUNKS[i], BY, Q1_FUNC)
 
 
-def cpu_path(n_chunks: int, rows: int, steps: int, warmup: int, cores: int):
-    """map stage fanned out over `cores` processes (one chunk per task, what Mars does with n_cpu bands),
-    concat / combine tree / agg in the parent.  Returns (rows/s, seconds per step list)."""
-    global _CPU_CHUNKS
-    import multiprocessing as mp
-    import pandas as pd
+class _PortTreeRun:
+    """same structure as ReferenceTreeRun on the oracle's restatement (used only without baseline/_ref)"""
+
+    def __init__(self, raw, chunk_rows, cores):
+        global _PORT_CHUNKS
+        import multiprocessing as mp
+
+        _PORT_CHUNKS = [raw.iloc[s:s + chunk_rows] for s in range(0, len(raw), chunk_rows)]
+        self.n = len(_PORT_CHUNKS)
+        self.pool = mp.get_context("fork").Pool(cores)
+
+    def step(self):
+        import mars_groupby_oracle as orc
+
+        level = self.pool.map(_port_map, range(self.n), chunksize=1)
+        while len(level) > 4:
+            level = [orc.agg_combine(orc.concat_partials(level[i:i + 4]), Q1_FUNC) if len(level[i:i + 4]) > 1
+                     else orc.agg_combine(level[i], Q1_FUNC) for i in range(0, len(level), 4)]
+        cat = level[0] if len(level) == 1 else orc.concat_partials(level)
+        return orc.agg_agg(cat, Q1_FUNC, sort=True)
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def cpu_path(rows: int, chunk_rows: int, steps: int, warmup: int, cores: int):
+    """-> (rows/s, seconds per timed step, kind, result frame of the last step)"""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import mars_groupby_oracle as orc
+    raw = _host_frame(rows, chunk_rows)
+    if reference_build_available():
+        import ref_runner
 
-    _CPU_CHUNKS = [gen_chunk(i, rows) for i in range(n_chunks)]
-    ctx = mp.get_context("fork")
-    times = []
-    with ctx.Pool(cores) as pool:
+        run, kind = ref_runner.ReferenceTreeRun(raw, BY, Q1_FUNC, chunk_rows, cores, method="tree", sort=True), "reference"
+    else:
+        run, kind = _PortTreeRun(raw, chunk_rows, cores), "port"
+    times, res = [], None
+    try:
         for it in range(warmup + steps):
             t0 = time.perf_counter()
-            level = pool.map(_cpu_map, range(n_chunks), chunksize=1)
-            while len(level) > 4:
-                level = [orc.agg_combine(orc.concat_partials(level[i:i + 4]), Q1_FUNC) if len(level[i:i + 4]) > 1
-                         else orc.agg_combine(level[i], Q1_FUNC) for i in range(0, len(level), 4)]
-            cat = level[0] if len(level) == 1 else orc.concat_partials(level)
-            res = orc.agg_agg(cat, Q1_FUNC, sort=True)
+            res = run.step()
             dt = time.perf_counter() - t0
             if it >= warmup:
                 times.append(dt)
-            assert len(res) >= 1
-    _CPU_CHUNKS = None
-    total_rows = n_chunks * rows
-    return total_rows * len(times) / sum(times), times
+    finally:
+        run.close()
+    assert res is not None and len(res) >= 1
+    return rows * len(times) / sum(times), times, kind, res
+
+
+def cpu_baseline_leg(args, n_chunks: int = 8, steps: int = 4, warmup: int = 1):
+    """the reference arm on a bounded sample (n_chunks full chunks), run as `bench.py --impl reference` in a
+    child process; returns the cpu_baseline object of the bench line"""
+    rows = min(args.rows, n_chunks * args.chunk_rows)
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", str(steps), "--warmup", str(warmup),
+           "--rows", str(rows), "--chunk-rows", str(args.chunk_rows)]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    t0 = time.perf_counter()
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
+        line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+        cb = line["cpu_baseline"]
+        cb["sample"] = (f"{rows} rows ({n_chunks} chunks) per step, {steps} steps after {warmup} warm-up: " + cb["sample"]
+                        + f"; {time.perf_counter() - t0:.1f} s in total incl. input generation")
+        return cb
+    except Exception as e:  # noqa: BLE001
+        return {"value": None, "unit": "rows/s", "cores": os.cpu_count(), "kind": "unavailable",
+                "sample": f"cpu baseline leg failed: {e!r}"}
 
 
 def run_reference_arm(args):
@@ -116,18 +169,23 @@ def run_reference_arm(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n_chunks = max(2, min(15, cores))
-    steps, warmup = args.steps, min(args.warmup, 1)
-    rps, times = cpu_path(n_chunks, args.chunk_rows, steps, warmup, cores)
-    sample = f"{n_chunks} chunks x {args.chunk_rows} rows of the Q1-shaped workload per step, map stage on {cores} processes"
+    steps, warmup = args.steps, args.warmup
+    rps, times, kind, res = cpu_path(args.rows, args.chunk_rows, steps, warmup, cores)
+    n_chunks = len(chunk_sizes(args.rows, args.chunk_rows))
+    what = ("unmodified reference operands (baseline/_ref, oracle/ref_runner.ReferenceTreeRun)" if kind == "reference"
+            else "oracle port of the reference operands (baseline/_ref absent)")
+    sample = (f"{args.rows} rows = {n_chunks} chunks of <= {args.chunk_rows} rows of the Q1-shaped workload per step "
+              f"(one GPU's share of the job), {what}, stage=map operands on {cores} processes")
+    cfg = workload_config(args, 1)
     line = {
         "impl": "reference", "metric": "groupby-agg rows/s", "value": rps, "unit": "rows/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * sum(times) / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, 1),
-        "cpu_baseline": {"value": rps, "unit": "rows/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": cfg,
+        "cpu_baseline": {"value": rps, "unit": "rows/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": rps, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "result_groups": int(len(res)),
     }
     print(json.dumps(line), flush=True)
 
@@ -227,16 +285,11 @@ def main_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
 
-    # CPU baseline first (rank 0, N=1 only): it forks worker processes, which must happen before CUDA starts
+    # CPU baseline first (rank 0, N=1 only), in a process of its own: it imports the reference behind its
+    # compatibility shim and forks worker processes -- neither belongs in the process that drives CUDA
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        n_chunks = max(2, min(8, cores))
-        rps, times = cpu_path(n_chunks, args.chunk_rows, 4, 1, cores)
-        cpu_baseline = {"value": rps, "unit": "rows/s", "cores": cores, "kind": "port",
-                        "sample": f"{n_chunks} chunks x {args.chunk_rows} rows per step, 4 steps after 1 warm-up, "
-                                  f"oracle port (pandas) of the reference operands, map stage on {cores} processes; "
-                                  f"{sum(times):.1f} s"}
+        cpu_baseline = cpu_baseline_leg(args)
 
     import pandas as pd
     import torch

@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE ONLY -- drives the *real* reference operands (build container only).
 
 ``run_reference(raw, by, func, ...)`` builds ``md.DataFrame(raw, chunk_size).groupby(...).agg(...)`` with
-the unmodified reference imported from ``$MARS_REF_DIR`` (default ``/tmp/mars_ref``, produced by
+the unmodified reference imported from ``$MARS_REF_DIR`` (default ``baseline/_ref``, produced by
 ``oracle/build_ref.sh``), tiles it with the reference's own ``ChunkGraphBuilder`` and executes every chunk
 operand through the reference's global ``execute(ctx, op)`` (mars/core/operand/core.py:475-512) with a
 ``dict`` context -- the same call the worker makes (mars/services/subtask/worker/processor.py:206-214).
@@ -12,7 +12,9 @@ from __future__ import annotations
 import os
 import sys
 
-REF_DIR = os.environ.get("MARS_REF_DIR", "/tmp/mars_ref")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# built by oracle/build_ref.sh; git-ignored, but it travels to the GPU box with the gpurun snapshot
+REF_DIR = os.environ.get("MARS_REF_DIR", os.path.join(_REPO, "baseline", "_ref"))
 
 
 def reference_available() -> bool:
@@ -112,3 +114,77 @@ if __name__ == "__main__":
         exp = raw.groupby("key", sort=True).agg(["sum", "mean", "count", "min", "max", "var"])
         pd.testing.assert_frame_equal(out["result"].sort_index(), exp, rtol=1e-9)
         print(method, sort, "OK", [(r["op"], r["stage"]) for r in out["records"]][:12])
+
+
+# ----------------------------------------------------------------------------------------------------
+# timed CPU arm (bench.py --impl reference / cpu_baseline): the reference's own operands on all host cores
+# ----------------------------------------------------------------------------------------------------
+_POOL_STATE = None     # (chunk graph order, map chunks) -- inherited by the forked workers
+
+
+def _pool_run_map(i):
+    """worker: the data-source + stage=map operands of map chunk i through the reference's execute(ctx, op)"""
+    from mars.core.mode import enter_mode
+    from mars.core.operand import execute
+
+    order, maps = _POOL_STATE
+    ctx = _Ctx()
+    m = maps[i]
+    with enter_mode(build=False, kernel=True):
+        for src in m.op.inputs:
+            ctx.set_current_chunk(src)
+            execute(ctx, src.op)
+        ctx.set_current_chunk(m)
+        execute(ctx, m.op)
+    return ctx[m.key]
+
+
+class ReferenceTreeRun:
+    """One tree-branch groupby-agg over row chunks with the UNMODIFIED reference: its tiling, its compiled
+    reduction steps, its pandas-backed ``execute(ctx, op)`` classmethods.  The stage=map operands (one per
+    row chunk, what dominates the cost) are fanned out over ``cores`` forked worker processes -- what Mars
+    does with ``n_cpu`` bands; concat / combine / agg operands run in the parent, like the last subtasks of
+    the reference's chunk graph.  ``step()`` runs the whole graph once and returns the result frame."""
+
+    def __init__(self, raw, by, func, chunk_size, cores, method="tree", sort=True):
+        global _POOL_STATE
+        import multiprocessing as mp
+
+        md = _import_reference()
+        from mars.core import TileableGraph, TileableGraphBuilder, ChunkGraphBuilder
+        from mars.core.operand import OperandStage
+
+        t = md.DataFrame(raw, chunk_size=chunk_size).groupby(by, sort=sort).agg(func, method=method)
+        tg = TileableGraph([t.data])
+        next(TileableGraphBuilder(tg).build())
+        cg = next(ChunkGraphBuilder(tg, fuse_enabled=False).build())
+        self.order = list(cg.topological_iter())
+        self.maps = [c for c in self.order
+                     if type(c.op).__name__ == "DataFrameGroupByAgg" and c.op.stage == OperandStage.map]
+        self.skip = {c.key for c in self.maps} | {s.key for m in self.maps for s in m.op.inputs}
+        self.result_chunks = sorted(cg.result_chunks, key=lambda c: c.index)
+        _POOL_STATE = (self.order, self.maps)
+        self.cores = cores
+        self.pool = mp.get_context("fork").Pool(cores)
+
+    def step(self):
+        from mars.core.mode import enter_mode
+        from mars.core.operand import execute
+        import pandas as pd
+
+        ctx = _Ctx()
+        partials = self.pool.map(_pool_run_map, range(len(self.maps)), chunksize=1)
+        for m, p in zip(self.maps, partials):
+            ctx[m.key] = p
+        with enter_mode(build=False, kernel=True):
+            for c in self.order:
+                if c.key in self.skip:
+                    continue
+                ctx.set_current_chunk(c)
+                execute(ctx, c.op)
+        outs = [ctx[c.key] for c in self.result_chunks]
+        return outs[0] if len(outs) == 1 else pd.concat(outs, axis=0)
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()

@@ -20,7 +20,9 @@ import torch
 import fake_kernels
 from conftest import assert_frames_match
 
-REF_DIR = os.environ.get("MARS_REF_DIR", "/tmp/mars_ref")
+import ref_runner as _rr
+
+REF_DIR = _rr.REF_DIR
 pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF_DIR, "mars")),
                                 reason="shimmed reference build not present (build container only)")
 
