@@ -43,6 +43,18 @@ _ASYNC = os.environ.get("MGB_EAGER", "0") in ("", "0")
 _LAZY_H2D = os.environ.get("MGB_EAGER_H2D", "0") in ("", "0")
 
 
+def _kernels_limits():
+    """(max keys, max value columns, max accumulators) of the C ABI (include/mgb.h)"""
+    from . import _lib
+
+    return _lib.MGB_MAX_KEYS, _lib.MGB_MAX_VALS, _lib.MGB_MAX_ACCS
+
+
+def _check_key_count(n: int):
+    if n > _kernels_limits()[0]:
+        raise NotImplementedError(f"{n} group keys: the GPU path handles up to {_kernels_limits()[0]} int64 keys")
+
+
 def _stage(op) -> Optional[str]:
     st = getattr(op, "stage", None)
     return None if st is None else getattr(st, "name", str(st))
@@ -56,6 +68,8 @@ def _as_device_frame(value, index_as_keys=False, lazy=False) -> DeviceFrame:
     if isinstance(value, DeviceFrame):
         return value
     if isinstance(value, pd.DataFrame):
+        if index_as_keys:
+            _check_key_count(value.index.nlevels)      # before any byte is copied: the caller falls back
         return DeviceFrame.from_pandas(value, device=_device(), index_as_keys=index_as_keys, lazy=lazy)
     raise NotImplementedError(f"cannot move {type(value).__name__} to the GPU groupby path")
 
@@ -228,6 +242,10 @@ def _map_plan_slow(op, frame: DeviceFrame) -> _MapPlan:
     if not isinstance(by, (list, tuple)) or not by or any(not isinstance(b, (str, int, tuple)) for b in by):
         raise NotImplementedError("groupby keys must be column labels on the GPU path")
     by = list(by)
+    if len(by) > _kernels_limits()[0]:
+        # library envelope (include/mgb.h: MGB_MAX_KEYS); raised BEFORE any data is touched so that the plugin
+        # hands the operand to the reference executor (plugin._with_reference_fallback)
+        raise NotImplementedError(f"{len(by)} group keys: the GPU path handles up to {_kernels_limits()[0]} int64 keys")
     value_cols = [c for c in frame.columns if c not in by and (selection is None or c in selection)]
     steps = _plan_steps(op, value_cols)
     used: List[Any] = []
@@ -247,6 +265,9 @@ def _map_plan_slow(op, frame: DeviceFrame) -> _MapPlan:
         slots.append((list(s.cols), len(accs), len(accs) + len(s.cols)))
         for c in s.cols:
             accs.append((used.index(c), code))
+    if len(used) > _kernels_limits()[1] or len(accs) > _kernels_limits()[2]:
+        raise NotImplementedError(f"{len(used)} value columns / {len(accs)} map-side accumulators exceed the library "
+                                  f"envelope ({_kernels_limits()[1]} / {_kernels_limits()[2]})")
     plan = _MapPlan()
     plan.by = by
     plan.key_pos = [frame.columns.index(b) for b in by]
@@ -912,6 +933,10 @@ def execute_concat(ctx, op):
     inputs = [ctx[c.key] for c in op.inputs]
     if not inputs or not isinstance(inputs[0], tuple):
         raise NotImplementedError("DataFrameConcat of plain frames stays on the reference executor")
+    if any(isinstance(f, (pd.DataFrame, pd.Series)) for v in inputs for f in v):
+        # partial tuples produced by the reference executor (a map stage outside the GPU envelope): its own
+        # concat keeps them on the host; a later combine / agg inside the envelope uploads them itself
+        raise NotImplementedError("partial tuples of pandas frames are concatenated by the reference executor")
     items = [[PiecewiseFrame(pieces) for pieces in _pieces_of(v)] for v in inputs]
     ctx[op.outputs[0].key] = _concat_partial_tuples(items)
 

@@ -29,6 +29,38 @@ import functools
 from . import executors
 
 
+def _to_host_value(v):
+    """device-resident value of the GPU executors -> what the reference executors expect (pandas)"""
+    from .device import DeviceFrame, PiecewiseFrame
+    from .executors import DeviceResult
+
+    if isinstance(v, (DeviceFrame, PiecewiseFrame, DeviceResult)):
+        return v.to_pandas()
+    if isinstance(v, tuple):
+        return tuple(_to_host_value(x) for x in v)
+    return v
+
+
+def _inputs_to_host(ctx, op):
+    """An operand that falls back to the reference executor may be fed by operands that ran on the GPU (e.g.
+    a stage=agg with a custom reduction after our concat): its inputs are converted in place first."""
+    keys = [inp.key for inp in (op.inputs or [])]
+    it = getattr(op, "iter_mapper_keys", None)
+    if it is not None and getattr(getattr(op, "stage", None), "name", None) == "reduce":
+        try:
+            keys += list(it())
+        except Exception:  # noqa: BLE001
+            pass
+    for k in keys:
+        try:
+            v = ctx[k]
+        except KeyError:
+            continue
+        h = _to_host_value(v)
+        if h is not v:
+            ctx[k] = h
+
+
 def _with_reference_fallback(cls, fn, gpu_only=True):
     reference_execute = cls.execute
 
@@ -39,7 +71,17 @@ def _with_reference_fallback(cls, fn, gpu_only=True):
         try:
             return fn(ctx, op)
         except NotImplementedError:
-            return reference_execute(ctx, op)
+            _inputs_to_host(ctx, op)
+            # the reference's GPU mode means cudf (`xdf = cudf if op.gpu else pd`, aggregation.py:1045); the
+            # inputs were just handed over as pandas, so the operand runs the reference's pandas path
+            gpu = getattr(op, "gpu", None)
+            try:
+                if gpu:
+                    op.gpu = False
+                return reference_execute(ctx, op)
+            finally:
+                if gpu:
+                    op.gpu = gpu
 
     return wrapped
 

@@ -50,7 +50,7 @@ class _Ctx(dict):
 
 
 def run_reference(raw, by, func, chunk_size, method="tree", sort=True, as_index=True,
-                  combine_size=None, selection=None):
+                  combine_size=None, selection=None, to_gpu=False):
     """Returns dict(result=pd.DataFrame, chunks=[...per-op records...])."""
     md = _import_reference()
     from mars.core import TileableGraph, TileableGraphBuilder, ChunkGraphBuilder
@@ -58,6 +58,8 @@ def run_reference(raw, by, func, chunk_size, method="tree", sort=True, as_index=
     from mars.core.operand import execute, OperandStage
 
     mdf = md.DataFrame(raw, chunk_size=chunk_size)
+    if to_gpu:      # GPU bands: op.gpu propagates to every downstream operand (core/operand/core.py:62-76)
+        mdf = mdf.to_gpu()
     g = mdf.groupby(by, sort=sort, as_index=as_index)
     if selection is not None:
         g = g[selection]
@@ -68,33 +70,38 @@ def run_reference(raw, by, func, chunk_size, method="tree", sort=True, as_index=
 
     tg = TileableGraph([t.data])
     next(TileableGraphBuilder(tg).build())
-    cg = next(ChunkGraphBuilder(tg, fuse_enabled=False).build())
     ctx = _Ctx()
     records = []
-    result_chunks = {c.key: c for c in cg.result_chunks}
+    result_chunks = {}
+    # the chunk-graph builder is a generator: iterative tiling (method='auto', to_gpu) yields the graph in stages,
+    # each stage is executed before the tiler continues (core/graph/builder/chunk.py:201-250)
     with enter_mode(build=False, kernel=True):
-        for c in cg.topological_iter():
-            ctx.set_current_chunk(c)
-            before = set(ctx.keys())
-            execute(ctx, c.op)
-            new_keys = [k for k in ctx.keys() if k not in before]
-            step_keys = None
-            if getattr(c.op, "agg_funcs", None) and getattr(c.op, "pre_funcs", None):
-                # slot order of the partial tuple is the (hash-seed dependent) order of op.agg_funcs: name
-                # every slot "<map func>_<identity|square>" so fixtures do not depend on it
-                ident = {p.output_key for p in c.op.pre_funcs if p.input_key == p.output_key}
-                step_keys = [f"{a.map_func_name}_{'identity' if a.input_key in ident else 'square'}"
-                             for a in c.op.agg_funcs]
-            records.append(
-                dict(
-                    step_keys=step_keys,
-                    op=type(c.op).__name__,
-                    stage=None if c.op.stage is None else OperandStage(c.op.stage).name,
-                    index=tuple(c.index) if c.index is not None else None,
-                    key=c.key,
-                    new_keys=new_keys,
+        for cg in ChunkGraphBuilder(tg, fuse_enabled=False).build():
+            result_chunks = {c.key: c for c in cg.result_chunks}
+            for c in cg.topological_iter():
+                if c.key in ctx:
+                    continue
+                ctx.set_current_chunk(c)
+                before = set(ctx.keys())
+                execute(ctx, c.op)
+                new_keys = [k for k in ctx.keys() if k not in before]
+                step_keys = None
+                if getattr(c.op, "agg_funcs", None) and getattr(c.op, "pre_funcs", None):
+                    # slot order of the partial tuple is the (hash-seed dependent) order of op.agg_funcs: name
+                    # every slot "<map func>_<identity|square>" so fixtures do not depend on it
+                    ident = {p.output_key for p in c.op.pre_funcs if p.input_key == p.output_key}
+                    step_keys = [f"{a.map_func_name}_{'identity' if a.input_key in ident else 'square'}"
+                                 for a in c.op.agg_funcs]
+                records.append(
+                    dict(
+                        step_keys=step_keys,
+                        op=type(c.op).__name__,
+                        stage=None if c.op.stage is None else OperandStage(c.op.stage).name,
+                        index=tuple(c.index) if c.index is not None else None,
+                        key=c.key,
+                        new_keys=new_keys,
+                    )
                 )
-            )
     outs = sorted(result_chunks.values(), key=lambda c: c.index)
     import pandas as pd
 

@@ -84,3 +84,45 @@ def test_unsupported_inputs_fall_back_to_the_reference_path(ref):
     out = ref.run_reference(raw, "key", ["sum", "count"], 50, method="tree", sort=True)
     exp = raw.groupby("key").agg(["sum", "count"])
     pd.testing.assert_frame_equal(out["result"], exp)
+
+
+def test_three_keys_fall_back_to_the_reference_path(ref):
+    """more group keys than the library holds (MGB_MAX_KEYS): NotImplementedError before any data is touched
+    -> the reference's own executor"""
+    rng = np.random.default_rng(3)
+    n = 600
+    raw = pd.DataFrame({"a": rng.integers(0, 3, n), "b": rng.integers(0, 3, n), "c": rng.integers(0, 2, n),
+                        "v": rng.random(n)})
+    fake_kernels.calls.clear()
+    out = ref.run_reference(raw, ["a", "b", "c"], ["sum", "count"], 150, method="tree", sort=True)
+    assert "groupby_aggregate" not in fake_kernels.calls and "preagg_dense_async" not in fake_kernels.calls
+    pd.testing.assert_frame_equal(out["result"], raw.groupby(["a", "b", "c"]).agg(["sum", "count"]))
+
+
+def test_more_than_64_accumulators_fall_back_to_the_reference_path(ref):
+    rng = np.random.default_rng(4)
+    n = 400
+    cols = {"key": rng.integers(0, 5, n)}
+    for i in range(23):                      # min / max / var = 5 atomic steps x 23 columns = 115 accumulators
+        cols[f"v{i}"] = rng.normal(10, 3, n)
+    raw = pd.DataFrame(cols)
+    fake_kernels.calls.clear()
+    out = ref.run_reference(raw, "key", ["min", "max", "var"], 100, method="tree", sort=True)
+    # the map stage (115 accumulators in one call) went to the reference executor: its outputs are pandas
+    # partial frames; the merges split the slots into groups of <= 64 accumulators and do run on our executors
+    maps = [r for r in out["records"] if r["op"] == "DataFrameGroupByAgg" and r["stage"] == "map"]
+    assert maps and all(isinstance(f, pd.DataFrame) for r in maps for f in out["ctx"][r["key"]])
+    pd.testing.assert_frame_equal(out["result"], raw.groupby("key").agg(["min", "max", "var"]), rtol=1e-9)
+
+
+def test_custom_reduction_nunique_falls_back_to_the_reference_path(ref):
+    """a12: custom reductions (only `nunique` uses the registry, groupby/custom_aggregation.py:20-86) are outside
+    the six functions: every stage of the operand goes to the reference executor"""
+    rng = np.random.default_rng(5)
+    n = 800
+    raw = pd.DataFrame({"key": rng.integers(0, 9, n), "v": rng.integers(0, 20, n)})
+    fake_kernels.calls.clear()
+    out = ref.run_reference(raw, "key", ["nunique"], 200, method="tree", sort=True)
+    assert "groupby_aggregate" not in fake_kernels.calls
+    exp = raw.groupby("key").agg(["nunique"])
+    pd.testing.assert_frame_equal(out["result"].sort_index(), exp, check_dtype=False)
