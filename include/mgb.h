@@ -165,6 +165,40 @@ int mgb_merge_small_async(const mgb_agg_spec* spec, int32_t n_pieces, const int6
                           void* const* out_acc_cols, int64_t out_capacity, int32_t sort_keys, int64_t* out_n_dev,
                           void* stream);
 
+/* Band-level batch (one launch for a whole subtask): the worker runs the chunk operands of a subtask back to
+ * back (mars/services/subtask/worker/processor.py:216-282); for the tree branch that is n stage=map operands
+ * followed by the concat / stage=combine tree (aggregation.py:715-780).  mgb_preagg_dense_batch_async streams
+ * ALL row batches of the band through one launch of the dense kernel (the chunks form one virtual sequence of
+ * row tiles; one cross-CTA merge at the end instead of one per chunk) and yields what the map operands plus
+ * the combine tree yield: one partial row per distinct key tuple of the band.  chunk_key_cols[i] /
+ * chunk_val_cols[i] are the column tables of chunk i (a count-only int64 column may be null, as above);
+ * at most mgb_dense_batch_max() chunks per call; out_n_dev as for mgb_preagg_dense_async.               */
+int mgb_dense_batch_max(int32_t* out_chunks);
+int mgb_preagg_dense_batch_async(const mgb_agg_spec* spec, int32_t n_chunks, const int64_t* chunk_rows,
+                                 const int64_t* const* const* chunk_key_cols,
+                                 const void* const* const* chunk_val_cols, int64_t* const* out_key_cols,
+                                 void* const* out_acc_cols, int64_t out_capacity, int64_t* out_n_dev, void* stream);
+
+/* stage=agg in ONE launch (aggregation.py:1166-1267): mgb_merge_small_async followed, inside the same kernel,
+ * by the post functions of the reference on the merged rows (reduction/mean.py:26-33, var.py:38-48, same
+ * operation order as mgb_post_mean / mgb_post_var).  Result column j = post[j] evaluated on the merged
+ * accumulators a0 (, a1, a2):  IDENTITY: a0;  MEAN: a0 = sum, a1 = count;  VAR: a0 = sum, a1 = sum of squares,
+ * a2 = count.  out_post_cols[j] are 8-byte columns of out_capacity rows (float64, or the accumulator's own
+ * dtype for IDENTITY); out_acc_cols is scratch for the merged accumulators.                             */
+typedef enum { MGB_POST_IDENTITY = 0, MGB_POST_MEAN = 1, MGB_POST_VAR = 2 } mgb_post_kind;
+typedef struct {
+  int32_t kind;        /* mgb_post_kind */
+  int32_t a0, a1, a2;  /* accumulator indices of the merge spec */
+  int32_t ddof;        /* VAR only */
+} mgb_post_step;
+#define MGB_MAX_POST 128
+int mgb_merge_small_post_async(const mgb_agg_spec* spec, int32_t n_pieces, const int64_t* piece_rows,
+                               const int64_t* const* piece_rows_dev, const int64_t* const* const* piece_key_cols,
+                               const void* const* const* piece_acc_cols, int64_t* const* out_key_cols,
+                               void* const* out_acc_cols, int64_t out_capacity, int32_t sort_keys,
+                               const mgb_post_step* post, int32_t n_post, void* const* out_post_cols,
+                               int64_t* out_n_dev, void* stream);
+
 /* Host-buffer convenience used by the end-to-end path: key/value columns live in (pinned) host memory,
  * are streamed to the device in row blocks overlapped with the kernels, and the result is written to
  * host arrays with capacity max_groups.  Returns the number of groups through out_n_groups

@@ -47,6 +47,13 @@ class AggSpec(C.Structure):
     ]
 
 
+class PostStep(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("a0", C.c_int32), ("a1", C.c_int32), ("a2", C.c_int32), ("ddof", C.c_int32)]
+
+
+POST_IDENTITY, POST_MEAN, POST_VAR = 0, 1, 2
+MGB_MAX_POST = 128
+
 _vp = C.c_void_p
 _pp = C.POINTER(C.c_void_p)
 _i64 = C.c_int64
@@ -75,6 +82,12 @@ SIGNATURES = {
     "mgb_preagg_dense_async": (C.c_int, [C.POINTER(AggSpec), _pp, _pp, _i64, _pp, _pp, _i64, _vp, _vp]),
     "mgb_merge_small_async": (C.c_int, [C.POINTER(AggSpec), _i32, C.POINTER(_i64), _pp, C.POINTER(_pp), C.POINTER(_pp),
                                         _pp, _pp, _i64, _i32, _vp, _vp]),
+    "mgb_dense_batch_max": (C.c_int, [C.POINTER(_i32)]),
+    "mgb_preagg_dense_batch_async": (C.c_int, [C.POINTER(AggSpec), _i32, C.POINTER(_i64), C.POINTER(_pp), C.POINTER(_pp),
+                                               _pp, _pp, _i64, _vp, _vp]),
+    "mgb_merge_small_post_async": (C.c_int, [C.POINTER(AggSpec), _i32, C.POINTER(_i64), _pp, C.POINTER(_pp),
+                                             C.POINTER(_pp), _pp, _pp, _i64, _i32, C.POINTER(PostStep), _i32, _pp,
+                                             _vp, _vp]),
     "mgb_groupby_agg_host": (
         C.c_int,
         [C.POINTER(AggSpec), _pp, _pp, _i64, _i64, _pp, _pp, _i64, _i32, C.POINTER(_i64), _vp],

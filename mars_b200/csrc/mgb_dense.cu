@@ -21,10 +21,10 @@
 
 #include "mgb_dense.cuh"
 
-int mgb_dense_launch_1_256(const DenseParams&, int, bool, int, size_t, cudaStream_t);
-int mgb_dense_launch_1_512(const DenseParams&, int, bool, int, size_t, cudaStream_t);
-int mgb_dense_launch_2_256(const DenseParams&, int, bool, int, size_t, cudaStream_t);
-int mgb_dense_launch_2_512(const DenseParams&, int, bool, int, size_t, cudaStream_t);
+int mgb_dense_launch_1_256(const DenseParams&, const DenseBatch&, int, bool, int, size_t, cudaStream_t);
+int mgb_dense_launch_1_512(const DenseParams&, const DenseBatch&, int, bool, int, size_t, cudaStream_t);
+int mgb_dense_launch_2_256(const DenseParams&, const DenseBatch&, int, bool, int, size_t, cudaStream_t);
+int mgb_dense_launch_2_512(const DenseParams&, const DenseBatch&, int, bool, int, size_t, cudaStream_t);
 
 // --------------------------------------------------------------------------------------------------
 // host side of the dense path
@@ -68,19 +68,26 @@ static int dense_set_count(int64_t* out_n_dev, int value, cudaStream_t st) {
   return MGB_OK;
 }
 
-extern "C" int mgb_preagg_dense_async(const mgb_agg_spec* spec, const int64_t* const* key_cols,
-                                      const void* const* val_cols, int64_t n_rows, int64_t* const* out_key_cols,
-                                      void* const* out_acc_cols, int64_t out_capacity, int64_t* out_n_dev,
-                                      void* stream) {
-  MGB_REQUIRE(spec && key_cols && val_cols && out_key_cols && out_acc_cols && out_n_dev, MGB_ERR_INVALID,
-              "null pointer");
+extern "C" int mgb_dense_batch_max(int32_t* out_chunks) {
+  MGB_REQUIRE(out_chunks, MGB_ERR_INVALID, "null pointer");
+  *out_chunks = DN_MAX_CHUNKS;
+  return MGB_OK;
+}
+
+extern "C" int mgb_preagg_dense_batch_async(const mgb_agg_spec* spec, int32_t n_chunks, const int64_t* chunk_rows,
+                                            const int64_t* const* const* chunk_key_cols,
+                                            const void* const* const* chunk_val_cols, int64_t* const* out_key_cols,
+                                            void* const* out_acc_cols, int64_t out_capacity, int64_t* out_n_dev,
+                                            void* stream) {
+  MGB_REQUIRE(spec && chunk_rows && chunk_key_cols && chunk_val_cols && out_key_cols && out_acc_cols && out_n_dev,
+              MGB_ERR_INVALID, "null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   const int nk = spec->n_keys, na = spec->n_accs;
   MGB_REQUIRE(nk >= 1 && nk <= MGB_MAX_KEYS, MGB_ERR_UNSUPPORTED, "n_keys=%d", nk);
   MGB_REQUIRE(na >= 1 && na <= MGB_MAX_ACCS && spec->n_vals >= 1 && spec->n_vals <= MGB_MAX_VALS,
               MGB_ERR_UNSUPPORTED, "spec outside the supported envelope");
-  MGB_REQUIRE(n_rows >= 0, MGB_ERR_INVALID, "negative n_rows");
-  if (n_rows == 0) return dense_set_count(out_n_dev, 0, st);
+  MGB_REQUIRE(n_chunks >= 0 && n_chunks <= DN_MAX_CHUNKS, MGB_ERR_UNSUPPORTED,
+              "%d chunks in one launch (mgb_dense_batch_max: %d)", n_chunks, DN_MAX_CHUNKS);
   DenseParams p;
   memset(&p, 0, sizeof(p));
   // columns that must be read: everything except int64 columns that are only counted
@@ -95,22 +102,43 @@ extern "C" int mgb_preagg_dense_async(const mgb_agg_spec* spec, const int64_t* c
     if (m == 0) continue;
     if (spec->val_dtype[c] == MGB_I64 && m == OPB(MGB_COUNT)) continue;
     if (ncol == 8) return dense_set_count(out_n_dev, -1, st);   // more than 8 live columns: not a dense shape
-    MGB_REQUIRE(val_cols[c], MGB_ERR_INVALID, "null value column %d", c);
     loaded_of[c] = ncol;
-    p.cols[ncol] = (const uint64_t*)val_cols[c];
     if (spec->val_dtype[c] == MGB_F64) p.f64_mask |= 1u << ncol;
     for (int o = MGB_SUM; o <= MGB_MAX; ++o)
       if (m & OPB(o)) p.op_mask[o] |= 1u << ncol;
     if (m & (OPB(MGB_SUMSQ) | OPB(MGB_MIN) | OPB(MGB_MAX))) allops = true;
     ++ncol;
   }
+  if (ncol == 0) return dense_set_count(out_n_dev, -1, st);   // only counts of int64 columns: general path
+  // the batch: non-empty chunks as one virtual sequence of 1024-row tiles
+  const long long tile_rows = 1024;
+  DenseBatch bt;
+  memset(&bt, 0, sizeof(bt));
+  long long tiles = 0, work_tiles = 0;
+  for (int i = 0; i < n_chunks; ++i) {
+    MGB_REQUIRE(chunk_rows[i] >= 0, MGB_ERR_INVALID, "negative row count of chunk %d", i);
+    if (chunk_rows[i] == 0) continue;
+    MGB_REQUIRE(chunk_key_cols[i] && chunk_val_cols[i], MGB_ERR_INVALID, "null column table of chunk %d", i);
+    const int q = bt.n_chunks++;
+    for (int j = 0; j < nk; ++j) {
+      MGB_REQUIRE(chunk_key_cols[i][j], MGB_ERR_INVALID, "null key column %d of chunk %d", j, i);
+      bt.ptr[q][j] = (const uint64_t*)chunk_key_cols[i][j];
+    }
+    for (int c = 0; c < spec->n_vals; ++c) {
+      if (loaded_of[c] < 0) continue;
+      MGB_REQUIRE(chunk_val_cols[i][c], MGB_ERR_INVALID, "null value column %d of chunk %d", c, i);
+      bt.ptr[q][MGB_MAX_KEYS + loaded_of[c]] = (const uint64_t*)chunk_val_cols[i][c];
+    }
+    bt.n[q] = chunk_rows[i];
+    tiles += chunk_rows[i] / tile_rows;
+    bt.tile_end[q] = tiles;
+    work_tiles += (chunk_rows[i] + tile_rows - 1) / tile_rows;
+  }
+  if (bt.n_chunks == 0) return dense_set_count(out_n_dev, 0, st);
   for (int j = 0; j < nk; ++j) {
-    MGB_REQUIRE(key_cols[j] && out_key_cols[j], MGB_ERR_INVALID, "null key column %d", j);
-    p.keys[j] = (const uint64_t*)key_cols[j];
+    MGB_REQUIRE(out_key_cols[j], MGB_ERR_INVALID, "null output key column %d", j);
     p.out.key[j] = (uint64_t*)out_key_cols[j];
   }
-  p.n = n_rows;
-  if (ncol == 0) return dense_set_count(out_n_dev, -1, st);   // only counts of int64 columns: general path
   // accumulator block of one (warp, group), 32-bit words: rows[32] | sum[ncol][64] | (sumsq|min|max)[ncol][64]
   // | nan[32] (lane-private 8-byte slots except the per-column NaN counters, which are touched rarely)
   const uint32_t all_cols = (1u << ncol) - 1u;
@@ -131,7 +159,9 @@ extern "C" int mgb_preagg_dense_async(const mgb_agg_spec* spec, const int64_t* c
   p.off_nan = off;
   p.stride_g = p.off_nan + 32;   // a multiple of 32 words: the bank of a lane-private slot depends on the lane only
   p.wpc = w;
-  const size_t fixed = (size_t)(MGB_MAX_KEYS * DN_TAB + MGB_MAX_KEYS * DN_MAX_GC) * 8 + DN_TAB * 4 + 128;
+  // key table + group keys + table ids + ints + the chunk table (tile ends, rows, column pointers)
+  const size_t fixed = (size_t)(MGB_MAX_KEYS * DN_TAB + MGB_MAX_KEYS * DN_MAX_GC) * 8 + DN_TAB * 4 + 128 +
+                       (size_t)DN_MAX_CHUNKS * (2 + DN_PTRS) * 8;
   // 16 warps per CTA when that still leaves 8 group slots (and registers for the double-buffered rows),
   // otherwise 8 warps with twice the rows per thread
   int threads = 512;
@@ -147,10 +177,8 @@ extern "C" int mgb_preagg_dense_async(const mgb_agg_spec* spec, const int64_t* c
   if (GC < 2) return dense_set_count(out_n_dev, -1, st);   // accumulators of one group do not fit: general path
   p.GC = GC;
   const int n_warps = threads / 32;
-  const long long tile_rows = 1024;
-  const long long ntiles = (n_rows + tile_rows - 1) / tile_rows;
   const int sms = mgb_sm_count();
-  const int grid = (int)(ntiles < sms ? ntiles : sms);
+  const int grid = (int)(work_tiles < sms ? work_tiles : sms);
   MGB_REQUIRE(out_capacity >= (int64_t)grid * GC, MGB_ERR_INVALID,
               "output capacity %lld < %d (mgb_dense_capacity)", (long long)out_capacity, grid * GC);
   p.stg_w = nk + 1 + p.wpc * ncol;
@@ -194,11 +222,11 @@ extern "C" int mgb_preagg_dense_async(const mgb_agg_spec* spec, const int64_t* c
     MgbProfScope prof(MGB_K_PREAGG_TINY, st);
     int status;
     if (nk == 1)
-      status = threads == 512 ? mgb_dense_launch_1_512(p, ncol, plain, grid, smem, st)
-                              : mgb_dense_launch_1_256(p, ncol, plain, grid, smem, st);
+      status = threads == 512 ? mgb_dense_launch_1_512(p, bt, ncol, plain, grid, smem, st)
+                              : mgb_dense_launch_1_256(p, bt, ncol, plain, grid, smem, st);
     else
-      status = threads == 512 ? mgb_dense_launch_2_512(p, ncol, plain, grid, smem, st)
-                              : mgb_dense_launch_2_256(p, ncol, plain, grid, smem, st);
+      status = threads == 512 ? mgb_dense_launch_2_512(p, bt, ncol, plain, grid, smem, st)
+                              : mgb_dense_launch_2_256(p, bt, ncol, plain, grid, smem, st);
     MGB_TRY(status);
   }
   if (dbg) {
@@ -222,6 +250,15 @@ extern "C" int mgb_preagg_dense_async(const mgb_agg_spec* spec, const int64_t* c
     cudaFree(dbg);
   }
   return MGB_OK;
+}
+
+extern "C" int mgb_preagg_dense_async(const mgb_agg_spec* spec, const int64_t* const* key_cols,
+                                      const void* const* val_cols, int64_t n_rows, int64_t* const* out_key_cols,
+                                      void* const* out_acc_cols, int64_t out_capacity, int64_t* out_n_dev,
+                                      void* stream) {
+  MGB_REQUIRE(key_cols && val_cols, MGB_ERR_INVALID, "null pointer");
+  return mgb_preagg_dense_batch_async(spec, 1, &n_rows, &key_cols, &val_cols, out_key_cols, out_acc_cols,
+                                      out_capacity, out_n_dev, stream);
 }
 
 extern "C" int mgb_preagg_dense(const mgb_agg_spec* spec, const int64_t* const* key_cols,
@@ -252,6 +289,13 @@ struct SmallPiece {
   int n;                    // host-known row count (used when n_dev == nullptr)
 };
 
+struct SmallPost {      // one result column of the stage=agg post functions (mgb_post_step, packed)
+  uint8_t kind;         // mgb_post_kind
+  uint8_t a0, a1, a2;   // merged accumulators it reads
+  int8_t ddof;
+  uint8_t pad[3];
+};
+
 struct SmallParams {
   int n_pieces;
   int out_cap;
@@ -260,7 +304,14 @@ struct SmallParams {
   OutCols out;                       // destination columns; op: MGB_SUM / MGB_MIN / MGB_MAX, dt: column dtype
   int sort;
   long long* out_n;                  // device: number of groups, -1: not a small input / an input had failed
+  int n_post;                        // > 0: evaluate the post functions on the merged rows (stage=agg in one launch)
+  SmallPost post[MGB_MAX_POST];
+  uint64_t* post_out[MGB_MAX_POST];
 };
+
+__device__ __forceinline__ double small_as_f64(uint64_t bits, int dt) {
+  return dt == MGB_F64 ? __longlong_as_double((long long)bits) : (double)(long long)bits;
+}
 
 template <int NK>
 __global__ void __launch_bounds__(SM_THREADS, 1) k_merge_small(const SmallParams p) {
@@ -408,6 +459,35 @@ __global__ void __launch_bounds__(SM_THREADS, 1) k_merge_small(const SmallParams
     for (int o = 1; o < 8; o <<= 1) v = dense_combine(kind, f, v, __shfl_xor_sync(0xffffffffu, v, o));
     if (on && sl == 0) p.out.acc[a][rank[u]] = v;
   }
+  if (p.n_post > 0) {
+    // a10: the generated post functions of the reference on the merged rows, in its operation order and
+    // without FMA contraction (mars/dataframe/reduction/mean.py:26-33, var.py:38-48)
+    __syncthreads();   // the merged accumulators (global, written by this CTA) are visible to all its threads
+    for (int i = threadIdx.x; i < nu * p.n_post; i += SM_THREADS) {
+      const int j = i / nu, r = i - j * nu;
+      const SmallPost ps = p.post[j];
+      uint64_t v = p.out.acc[ps.a0][r];
+      if (ps.kind == MGB_POST_MEAN) {
+        const double s_ = small_as_f64(v, p.out.dt[ps.a0]);
+        const double c_ = (double)(long long)p.out.acc[ps.a1][r];
+        v = (uint64_t)__double_as_longlong(__ddiv_rn(s_, c_));
+      } else if (ps.kind == MGB_POST_VAR) {
+        const double s_ = small_as_f64(v, p.out.dt[ps.a0]);
+        const double q_ = small_as_f64(p.out.acc[ps.a1][r], p.out.dt[ps.a1]);
+        const double c_ = (double)(long long)p.out.acc[ps.a2][r];
+        double res;
+        if (ps.ddof == 0) {
+          const double m2 = __ddiv_rn(q_, c_), m = __ddiv_rn(s_, c_);
+          res = __dsub_rn(m2, __dmul_rn(m, m));
+        } else {
+          const double t_ = __ddiv_rn(__dmul_rn(s_, s_), c_);
+          res = __ddiv_rn(__dsub_rn(q_, t_), __dsub_rn(c_, (double)ps.ddof));
+        }
+        v = (uint64_t)__double_as_longlong(res);
+      }
+      p.post_out[j][r] = v;
+    }
+  }
   if (threadIdx.x == 0) *p.out_n = nu;
 }
 
@@ -446,14 +526,16 @@ static int small_scratch(int dev, SmallScratch** out) {
   return MGB_OK;
 }
 
-extern "C" int mgb_merge_small_async(const mgb_agg_spec* spec, int32_t n_pieces, const int64_t* piece_rows,
-                                     const int64_t* const* piece_rows_dev,
-                                     const int64_t* const* const* piece_key_cols,
-                                     const void* const* const* piece_acc_cols, int64_t* const* out_key_cols,
-                                     void* const* out_acc_cols, int64_t out_capacity, int32_t sort_keys,
-                                     int64_t* out_n_dev, void* stream) {
+static int merge_small_impl(const mgb_agg_spec* spec, int32_t n_pieces, const int64_t* piece_rows,
+                            const int64_t* const* piece_rows_dev, const int64_t* const* const* piece_key_cols,
+                            const void* const* const* piece_acc_cols, int64_t* const* out_key_cols,
+                            void* const* out_acc_cols, int64_t out_capacity, int32_t sort_keys,
+                            const mgb_post_step* post, int32_t n_post, void* const* out_post_cols,
+                            int64_t* out_n_dev, void* stream) {
   MGB_REQUIRE(spec && piece_rows && piece_key_cols && piece_acc_cols && out_key_cols && out_acc_cols && out_n_dev,
               MGB_ERR_INVALID, "null pointer");
+  MGB_REQUIRE(n_post >= 0 && n_post <= MGB_MAX_POST && (n_post == 0 || (post && out_post_cols)), MGB_ERR_INVALID,
+              "bad post steps (%d, at most %d)", n_post, MGB_MAX_POST);
   cudaStream_t st = (cudaStream_t)stream;
   const int nk = spec->n_keys, na = spec->n_accs;
   MGB_REQUIRE(nk >= 1 && nk <= MGB_MAX_KEYS && na >= 1 && na <= MGB_MAX_ACCS, MGB_ERR_UNSUPPORTED,
@@ -528,6 +610,22 @@ extern "C" int mgb_merge_small_async(const mgb_agg_spec* spec, int32_t n_pieces,
   }
   p.sort = sort_keys ? 1 : 0;
   p.out_n = (long long*)out_n_dev;
+  p.n_post = n_post;
+  for (int j = 0; j < n_post; ++j) {
+    const mgb_post_step& q = post[j];
+    const int need = q.kind == MGB_POST_IDENTITY ? 1 : q.kind == MGB_POST_MEAN ? 2 : 3;
+    MGB_REQUIRE(q.kind >= MGB_POST_IDENTITY && q.kind <= MGB_POST_VAR && out_post_cols[j], MGB_ERR_INVALID,
+                "bad post step %d", j);
+    const int idx[3] = {q.a0, q.a1, q.a2};
+    for (int t = 0; t < need; ++t)
+      MGB_REQUIRE(idx[t] >= 0 && idx[t] < na, MGB_ERR_INVALID, "post step %d reads accumulator %d of %d", j, idx[t], na);
+    p.post[j].kind = (uint8_t)q.kind;
+    p.post[j].a0 = (uint8_t)q.a0;
+    p.post[j].a1 = (uint8_t)(need > 1 ? q.a1 : 0);
+    p.post[j].a2 = (uint8_t)(need > 2 ? q.a2 : 0);
+    p.post[j].ddof = (int8_t)q.ddof;
+    p.post_out[j] = (uint64_t*)out_post_cols[j];
+  }
   {
     MgbProfScope prof(MGB_K_MERGE, st);
     const size_t smem = small_smem_bytes();
@@ -540,6 +638,27 @@ extern "C" int mgb_merge_small_async(const mgb_agg_spec* spec, int32_t n_pieces,
   MGB_CUDA(cudaEventRecord(s.ev[slot], st));
   s.used[slot] = true;
   return MGB_OK;
+}
+
+extern "C" int mgb_merge_small_async(const mgb_agg_spec* spec, int32_t n_pieces, const int64_t* piece_rows,
+                                     const int64_t* const* piece_rows_dev,
+                                     const int64_t* const* const* piece_key_cols,
+                                     const void* const* const* piece_acc_cols, int64_t* const* out_key_cols,
+                                     void* const* out_acc_cols, int64_t out_capacity, int32_t sort_keys,
+                                     int64_t* out_n_dev, void* stream) {
+  return merge_small_impl(spec, n_pieces, piece_rows, piece_rows_dev, piece_key_cols, piece_acc_cols, out_key_cols,
+                          out_acc_cols, out_capacity, sort_keys, nullptr, 0, nullptr, out_n_dev, stream);
+}
+
+extern "C" int mgb_merge_small_post_async(const mgb_agg_spec* spec, int32_t n_pieces, const int64_t* piece_rows,
+                                          const int64_t* const* piece_rows_dev,
+                                          const int64_t* const* const* piece_key_cols,
+                                          const void* const* const* piece_acc_cols, int64_t* const* out_key_cols,
+                                          void* const* out_acc_cols, int64_t out_capacity, int32_t sort_keys,
+                                          const mgb_post_step* post, int32_t n_post, void* const* out_post_cols,
+                                          int64_t* out_n_dev, void* stream) {
+  return merge_small_impl(spec, n_pieces, piece_rows, piece_rows_dev, piece_key_cols, piece_acc_cols, out_key_cols,
+                          out_acc_cols, out_capacity, sort_keys, post, n_post, out_post_cols, out_n_dev, stream);
 }
 
 extern "C" int mgb_merge_small(const mgb_agg_spec* spec, int32_t n_pieces, const int64_t* piece_rows,

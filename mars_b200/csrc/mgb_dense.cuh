@@ -127,10 +127,21 @@ __device__ __forceinline__ bool key_less(const uint64_t* a, const uint64_t* b) {
 // --------------------------------------------------------------------------------------------------
 #define DN_TAB 64             // key-table slots per CTA (open addressing; entries never move)
 
+#define DN_MAX_CHUNKS 64      // row batches (chunks) one launch streams through
+#define DN_PTRS (MGB_MAX_KEYS + 8)
+
+// The row batches of one launch: a band's chunks are streamed as ONE virtual sequence of 1024-row tiles
+// (full tiles of chunk 0, then of chunk 1, ...); the < 1024-row remainders are handled afterwards, chunk c by
+// CTA c % grid.  Passed by value (kernel parameter space) and copied to shared memory by every CTA.
+struct DenseBatch {
+  int n_chunks;
+  int pad;
+  long long tile_end[DN_MAX_CHUNKS];              // full tiles of chunks 0..c (inclusive prefix sum)
+  long long n[DN_MAX_CHUNKS];                     // rows of chunk c
+  const uint64_t* ptr[DN_MAX_CHUNKS][DN_PTRS];    // key columns [0, NK), then the loaded value columns
+};
+
 struct DenseParams {
-  const uint64_t* keys[MGB_MAX_KEYS];
-  const uint64_t* cols[8];
-  long long n;
   int GC;                   // groups per CTA (accumulator capacity); group ids are dense, in insertion order
   int stride_g;             // 32-bit words per (warp, group) accumulator block
   int off_nan, off_sum, off_sumsq, off_min, off_max;   // word offsets of column 0's slot inside a block
@@ -258,7 +269,7 @@ __device__ __forceinline__ uint64_t dense_combine(int kind, bool f, uint64_t v, 
 // PLAIN: every loaded column is float64 and carries SUM, no SUMSQ / MIN / MAX (sum / mean / count shapes):
 // straight-line DADD updates.  Otherwise the generic body tests the per-column masks (warp-uniform branches).
 template <int NK, int NV, bool PLAIN, int THREADS>
-__global__ void __launch_bounds__(THREADS, 1) k_preagg_dense(const DenseParams p) {
+__global__ void __launch_bounds__(THREADS, 1) k_preagg_dense(const DenseParams p, const DenseBatch bt) {
   constexpr int DN_WARPS = THREADS / 32;
   constexpr int DN_R = 1024 / THREADS;   // rows per thread per tile: a tile is always 1024 rows
   constexpr int DN_THREADS = THREADS;
@@ -271,6 +282,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_preagg_dense(const DenseParams p
   uint64_t* gkeys = tkeys + MGB_MAX_KEYS * DN_TAB;
   int* tgid = (int*)(gkeys + MGB_MAX_KEYS * DN_MAX_GC);
   int* s_int = tgid + DN_TAB;
+  // chunk table (behind the ints; the last-CTA merge re-uses the memory before it, never this part... it does
+  // re-use everything, but only after the streaming loop is over)
+  long long* s_tile_end = (long long*)(s_int + 32);                 // [DN_MAX_CHUNKS]
+  long long* s_rows = s_tile_end + DN_MAX_CHUNKS;                   // [DN_MAX_CHUNKS]
+  const uint64_t** s_ptr = (const uint64_t**)(s_rows + DN_MAX_CHUNKS);   // [DN_MAX_CHUNKS][DN_PTRS]
   int* s_ng = s_int;
   int* s_lock = s_int + 1;
   int* s_fail = s_int + 2;
@@ -297,6 +313,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_preagg_dense(const DenseParams p
       }
   }
   for (int i = threadIdx.x; i < DN_TAB; i += DN_THREADS) tgid[i] = -1;
+  const int n_chunks = bt.n_chunks;
+  for (int i = threadIdx.x; i < n_chunks; i += DN_THREADS) {
+    s_tile_end[i] = bt.tile_end[i];
+    s_rows[i] = bt.n[i];
+  }
+  for (int i = threadIdx.x; i < n_chunks * DN_PTRS; i += DN_THREADS)
+    s_ptr[i] = bt.ptr[i / DN_PTRS][i % DN_PTRS];
   if (threadIdx.x == 0) {
     *s_ng = 0;
     *s_lock = 0;
@@ -387,21 +410,29 @@ __global__ void __launch_bounds__(THREADS, 1) k_preagg_dense(const DenseParams p
     }
   };
 
-  const long long n = p.n;
   constexpr long long TILE = (long long)DN_THREADS * DN_R;
-  const long long nfull = n / TILE;   // full tiles take the unpredicated, double-buffered loop
+  const long long nfull = s_tile_end[n_chunks - 1];   // full tiles of all chunks: the unpredicated, double-buffered loop
 
   uint64_t kb[2][DN_R][NK];
   uint64_t xb[2][DN_R][NV];
   const uint64_t* pk[NK];
   const uint64_t* pc[NV];
-#pragma unroll
-  for (int j = 0; j < NK; ++j) pk[j] = p.keys[j] + threadIdx.x;
-#pragma unroll
-  for (int c = 0; c < NV; ++c) pc[c] = p.cols[c] + threadIdx.x;
+  int cur = -1, cc = 0;          // chunk whose pointers are in pk / pc; chunk cursor (tiles are visited in order)
+  long long cbeg = 0;            // first tile of chunk cc
 
   auto load_tile = [&](int buf, long long t) {
-    const long long off = t * TILE;
+    while (t >= s_tile_end[cc]) {     // uniform across the CTA
+      cbeg = s_tile_end[cc];
+      ++cc;
+    }
+    if (cc != cur) {
+      cur = cc;
+#pragma unroll
+      for (int j = 0; j < NK; ++j) pk[j] = s_ptr[cc * DN_PTRS + j] + threadIdx.x;
+#pragma unroll
+      for (int c = 0; c < NV; ++c) pc[c] = s_ptr[cc * DN_PTRS + MGB_MAX_KEYS + c] + threadIdx.x;
+    }
+    const long long off = (t - cbeg) * TILE;
 #pragma unroll
     for (int j = 0; j < NK; ++j) {
       const uint64_t* b = pk[j] + off;
@@ -437,17 +468,20 @@ __global__ void __launch_bounds__(THREADS, 1) k_preagg_dense(const DenseParams p
     t = t2;
     if ((++iter & 7) == 0 && *(volatile int*)p.fail) failed = true;   // somebody else gave up: stop early
   }
-  // ragged tail (< TILE rows): one CTA, a warp-sized slice at a time; lanes past the end stay in the
-  // warp-collective lookup but neither look up nor accumulate
-  if (!failed && (int)(nfull % gridDim.x) == (int)blockIdx.x) {
-    for (long long i0 = nfull * TILE + warp * 32; i0 < n && !failed; i0 += DN_THREADS) {
+  // ragged remainders (< TILE rows per chunk): chunk c by CTA c % grid, a warp-sized slice at a time; lanes
+  // past the end stay in the warp-collective lookup but neither look up nor accumulate
+  for (int c = (int)blockIdx.x; c < n_chunks && !failed; c += (int)gridDim.x) {
+    const long long n = s_rows[c];
+    const long long done = (s_tile_end[c] - (c ? s_tile_end[c - 1] : 0)) * TILE;
+    const uint64_t* const* cp = s_ptr + c * DN_PTRS;
+    for (long long i0 = done + warp * 32; i0 < n && !failed; i0 += DN_THREADS) {
       const long long i = i0 + lane;
       const bool live = i < n;
       uint64_t k[NK], x[NV];
 #pragma unroll
-      for (int j = 0; j < NK; ++j) k[j] = live ? p.keys[j][i] : 0;
+      for (int j = 0; j < NK; ++j) k[j] = live ? cp[j][i] : 0;
 #pragma unroll
-      for (int c = 0; c < NV; ++c) x[c] = live ? p.cols[c][i] : 0;
+      for (int cl = 0; cl < NV; ++cl) x[cl] = live ? cp[MGB_MAX_KEYS + cl][i] : 0;
       process_row(k, x, live);
     }
   }
@@ -746,7 +780,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_preagg_dense(const DenseParams p
 
 // one translation unit per (NK, THREADS) pair instantiates the kernels (mgb_dense_inst.cu)
 template <int NK, int TH>
-int mgb_dense_launch(const DenseParams& p, int ncol, bool plain, int grid, size_t smem, cudaStream_t st) {
+int mgb_dense_launch(const DenseParams& p, const DenseBatch& bt, int ncol, bool plain, int grid, size_t smem,
+                     cudaStream_t st) {
   int dev = 0;
   cudaGetDevice(&dev);
 #define LAUNCH(NV, PL)                                                                                       \
@@ -757,7 +792,7 @@ int mgb_dense_launch(const DenseParams& p, int ncol, bool plain, int grid, size_
                                     227 * 1024));                                                           \
       attr_set[dev & 7] = true;                                                                             \
     }                                                                                                       \
-    k_preagg_dense<NK, NV, PL, TH><<<grid, TH, smem, st>>>(p);                                              \
+    k_preagg_dense<NK, NV, PL, TH><<<grid, TH, smem, st>>>(p, bt);                                             \
   } while (0)
 #define PICK_NV(PL)                     \
   do {                                  \

@@ -4,7 +4,7 @@
 
 #define CAT_(a, b, c, d) a##b##c##d
 #define CAT(a, b, c, d) CAT_(a, b, c, d)
-int CAT(mgb_dense_launch_, DN_NK, _, DN_TH)(const DenseParams& p, int ncol, bool plain, int grid, size_t smem,
-                                              cudaStream_t st) {
-  return mgb_dense_launch<DN_NK, DN_TH>(p, ncol, plain, grid, smem, st);
+int CAT(mgb_dense_launch_, DN_NK, _, DN_TH)(const DenseParams& p, const DenseBatch& bt, int ncol, bool plain, int grid,
+                                              size_t smem, cudaStream_t st) {
+  return mgb_dense_launch<DN_NK, DN_TH>(p, bt, ncol, plain, grid, smem, st);
 }

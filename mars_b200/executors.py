@@ -516,12 +516,116 @@ def _execute_agg_combine(ctx, op):
     ctx[op.outputs[0].key] = tuple(_merge_partials(slots, steps, sort=False))
 
 
+_post_plans: Dict[Any, Any] = {}
+
+
+def _post_plan(op, slots, steps, two_level):
+    """ctypes post steps of a stage=agg operand whose post functions are all identity / mean / var, or None.
+    Cached on the identity of ``op.post_funcs`` (compiled reductions are shared between the operands of one
+    computation) and the partial schema."""
+    first = [sl[0] for sl in slots]
+    key = (id(op.post_funcs), two_level, tuple(tuple(f.columns) for f in first))
+    hit = _post_plans.get(key)
+    if hit is not None and hit[0] is op.post_funcs:
+        return hit[1]
+    off, pos = [], 0
+    for f in first:
+        off.append(pos)
+        pos += len(f.columns)
+    by_key = {s.output_key: i for i, s in enumerate(steps)}
+    plan = None
+    post_steps, labels, is_float = [], [], []
+    ok = True
+    for p in op.post_funcs:
+        idx = [by_key[k] for k in p.input_keys]
+        cols = list(p.columns) if p.columns is not None else None
+        common = [c for c in first[idx[0]].columns if all(c in first[i].columns for i in idx[1:])
+                  and (cols is None or c in cols)]
+        cls = classify_post(p.func, len(idx))
+        if cls is None:
+            ok = False
+            break
+        kind, ddof = cls
+        for c in common:
+            acc = [off[i] + first[i].columns.index(c) for i in idx]
+            labels.append((c, p.func_name) if two_level else c)
+            if kind == "identity":
+                post_steps.append((_kernels.POST_IDENTITY, acc[0], 0, 0, 0))
+                is_float.append(first[idx[0]].col_dtype(first[idx[0]].columns.index(c)) == torch.float64)
+            elif kind == "mean":
+                post_steps.append((_kernels.POST_MEAN, acc[0], acc[1], 0, 0))
+                is_float.append(True)
+            else:   # inputs of the generated var: sum(x**2), sum(x), count
+                post_steps.append((_kernels.POST_VAR, acc[1], acc[0], acc[2], int(ddof)))
+                is_float.append(True)
+    if ok and post_steps and len(post_steps) <= _kernels.MAX_POST and len(set(labels)) == len(labels):
+        ops = [_OPCODE[steps[i].agg_func] for i, f in enumerate(first) for _ in f.columns]
+        dts = [_kernels.F64 if f.col_dtype(j) == torch.float64 else _kernels.I64
+               for f in first for j in range(len(f.columns))]
+        plan = (_kernels.PostPlan(post_steps, is_float), labels, ops, dts)
+    if len(_post_plans) > 256:
+        _post_plans.clear()
+    _post_plans[key] = (op.post_funcs, plan)
+    return plan
+
+
+def _agg_one_launch(ctx, op, out_chunk, slots, steps, sort, col_value) -> bool:
+    """stage=agg of a small input in ONE launch + ONE device->host copy: merge of the partial pieces, the post
+    functions and the key sort happen inside mgb_merge_small_post_async; the pieces' sizes may still be on the
+    device.  Returns False when the input is not small / a post function is not one of identity, mean, var /
+    the speculative chain failed -- the caller then takes the general route (which replays)."""
+    if not (_ASYNC and hasattr(_kernels, "merge_small_post_async")):
+        return False
+    first = slots[0]
+    n_pieces = len(first)
+    if any(len(sl) != n_pieces for sl in slots[1:]):
+        return False
+    for sl in slots[1:]:
+        for i in range(n_pieces):
+            if not first[i].same_index(sl[i]):
+                return False
+    if sum(len(sl[0].columns) for sl in slots) > 64:
+        return False
+    known = sum(len(f) for f in first if not f.is_pending)
+    n_live = sum(1 for f in first if f.is_pending or len(f) > 0)
+    if known > _kernels.SMALL_MAX_ROWS or n_live > _kernels.SMALL_MAX_PIECES or n_live == 0:
+        return False
+    plan = _post_plan(op, slots, steps, col_value.nlevels > 1)
+    if plan is None:
+        return False
+    post, labels, ops, dts = plan
+    dev = first[0].device
+    pieces = []
+    for i in range(n_pieces):
+        f0 = first[i]
+        pend = f0.is_pending
+        if not pend and len(f0) == 0:
+            continue
+        kp, ap = f0.ptrs_raw()
+        for sl in slots[1:]:
+            ap = ap + sl[i].ptrs_raw()[1]
+        pieces.append((kp, ap, None if pend else len(f0), f0._pending.count_ptr() if pend else 0, dts, dev))
+    res = _kernels.merge_small_post_async(pieces, ops, post, sort=sort)
+    if res is None:
+        return False
+    blk, nk, n_post = res
+    n, keys, cols = _kernels.result_block_to_host(blk, nk, n_post, post.is_float)
+    if n < 0:
+        return False          # a speculation failed up the chain: the general route resolves and replays
+    ctx[out_chunk.key] = _assemble_result(dict(zip(labels, cols)), keys,
+                                          _result_meta(op, out_chunk, first[0].index_names, col_value))
+    return True
+
+
 def _execute_agg_agg(ctx, op):
     """stage=agg: final merge, post functions, result frame (reference: _execute_agg, aggregation.py:1166-1267)"""
     out_chunk = op.outputs[0]
     slots = _pieces_of(ctx[op.inputs[0].key])
     steps = _plan_steps(op, None)
     sort = bool(op.groupby_params.get("sort", True))
+    if len(slots) == len(steps) and _agg_one_launch(ctx, op, out_chunk, slots, steps, sort,
+                                                    out_chunk.columns_value.to_pandas()):
+        return
     merged = _merge_partials(slots, steps, sort=sort)
     col_value = out_chunk.columns_value.to_pandas()
     two_level = col_value.nlevels > 1
@@ -704,6 +808,146 @@ def _to_host(columns):
     if fn is not None:
         return fn(columns)
     return [t.cpu().numpy() for t in columns]
+
+
+# ----------------------------------------------------------------------------------------------------
+# band-level fusion of the tree branch: n stage=map operands + concat / stage=combine tree -> one launch
+# ----------------------------------------------------------------------------------------------------
+class FusedTree:
+    """The part of a chunk graph below one stage=agg operand of the tree branch (aggregation.py:715-823):
+    ``leaves`` are the not yet executed stage=map chunks, ``interior`` the DataFrameConcat / stage=combine
+    chunks between them and the agg operand's input ``root``, ``opaque`` chunks that were executed earlier
+    (method='auto' samples the first combine_size map chunks) and feed the tree as ready partial tuples."""
+    __slots__ = ("agg", "root", "leaves", "interior", "opaque", "nodes")
+
+    def __init__(self, agg, root, leaves, interior, opaque, nodes):
+        self.agg, self.root, self.leaves, self.interior, self.opaque, self.nodes = agg, root, leaves, interior, opaque, nodes
+
+
+def find_fused_trees(order, keep) -> List[FusedTree]:
+    """``order``: the chunks about to run, topologically sorted; ``keep``: keys whose values must survive (result
+    chunks).  A subtree qualifies when every node has exactly one consumer and is a stage=map / stage=combine
+    DataFrameGroupByAgg or a DataFrameConcat -- i.e. when nothing but the stage=agg operand can observe the
+    intermediate partial tuples."""
+    if not (_ASYNC and hasattr(_kernels, "preagg_dense_batch_async")):
+        return []
+    pos = {c.key: i for i, c in enumerate(order)}
+    nsucc: Dict[Any, int] = {}
+    for c in order:
+        for inp in c.op.inputs:
+            nsucc[inp.key] = nsucc.get(inp.key, 0) + 1
+    out = []
+    for a in order:
+        op = a.op
+        if type(op).__name__ != "DataFrameGroupByAgg" or _stage(op) != "agg" or len(op.inputs) != 1:
+            continue
+        root = op.inputs[0]
+        if root.key not in pos:
+            continue
+        leaves, interior, opaque, ok = [], [], [], True
+        stack = [root]
+        while stack:
+            c = stack.pop()
+            if c.key not in pos:
+                opaque.append(c)
+                continue
+            name, st = type(c.op).__name__, _stage(c.op)
+            if nsucc.get(c.key, 0) != 1 or c.key in keep:
+                ok = False
+                break
+            if name == "DataFrameGroupByAgg" and st == "map":
+                if getattr(c.op, "size_recorder_name", None) is not None or len(c.op.inputs) != 1:
+                    ok = False
+                    break
+                leaves.append(c)
+            elif (name == "DataFrameGroupByAgg" and st == "combine") or name == "DataFrameConcat":
+                interior.append(c)
+                stack.extend(reversed(c.op.inputs))
+            else:
+                ok = False
+                break
+        if ok and len(leaves) >= 2:
+            nodes = sorted(leaves + interior, key=lambda c: pos[c.key])
+            out.append(FusedTree(a, root, sorted(leaves, key=lambda c: pos[c.key]), interior, opaque, nodes))
+    return out
+
+
+def execute_fused_tree(ctx, ft: FusedTree) -> bool:
+    """Runs the fused part of the graph: ONE launch of the band-level batch kernel over the input chunks of all
+    leaf map operands (per mgb_dense_batch_max() chunks) instead of n map launches and the merges of the
+    combine tree; ``ctx[ft.root.key]`` receives the partial tuple the stage=agg operand expects (a virtual
+    concat of the batch results and the opaque partial tuples).  Returns False -- nothing done -- when the
+    shape is not a low-cardinality one or the chunks differ in schema: the caller then runs the operands one
+    by one."""
+    fn = getattr(_kernels, "preagg_dense_batch_async", None)
+    if fn is None or not _ASYNC:
+        return False
+    frames = []
+    for leaf in ft.leaves:
+        v = ctx[leaf.op.inputs[0].key]
+        if not isinstance(v, DeviceFrame) or v.index is not None:
+            return False
+        frames.append(v)
+    op0 = ft.leaves[0].op
+    for leaf in ft.leaves[1:]:
+        if leaf.op.agg_funcs is not op0.agg_funcs and leaf.op.agg_funcs != op0.agg_funcs:
+            return False
+    try:
+        plan = _map_plan(op0, frames[0])
+    except NotImplementedError:
+        return False
+    if plan.shape_key in _dense_rejected:
+        return False
+    sig = plan.for_dtypes(frames[0])
+    keys_ok, count_only, dts = sig
+    if not keys_ok:
+        return False
+    cols0 = frames[0].columns
+    for f in frames[1:]:
+        if (f.columns is not cols0 and f.columns != cols0) or plan.for_dtypes(f) is not sig:
+            return False
+    chunks = []
+    for f in frames:
+        kp = [f.col(i).data_ptr() for i in plan.key_pos]
+        vp = [None if j in count_only else f.col(i).data_ptr() for j, i in enumerate(plan.val_pos)]
+        chunks.append((kp, vp, len(f)))
+    B = _kernels.dense_batch_max()
+    dev = frames[0].device
+    nk = len(plan.by)
+    per_slot: List[List[DeviceFrame]] = [[] for _ in plan.slots]
+    for g0 in range(0, len(chunks), B):
+        res = fn(chunks[g0:g0 + B], plan.accs, dts, nk, dev)
+        if res is None:
+            _dense_rejected.add(plan.shape_key)
+            if g0 == 0:
+                return False
+            raise MarsGBError(6, "dense batch shape rejected after the first batch was launched")
+        bi, bf, fc = res
+        group = frames[g0:g0 + B]
+
+        def replay(group=group, plan=plan):
+            """a CTA met more groups than it holds: the band's chunks go through the general aggregator"""
+            _dense_rejected.add(plan.shape_key)
+            agg = _kernels.Aggregator(len(plan.by), [_kernels.dtype_code(group[0].col(i)) for i in plan.val_pos],
+                                      list(plan.accs))
+            try:
+                for f in group:
+                    agg.update([f.col(i) for i in plan.key_pos], [f.col(i) for i in plan.val_pos])
+                return agg.result(sort=False, device=group[0].device)
+            finally:
+                agg.close()
+
+        pend = Pending(bi, fc.n_int, bi.shape[1], replay, fblock=bf, layout=fc)
+        src = ColumnSet.from_block(bi, bf, fc)
+        cap = bi.shape[1]
+        for s_, (cols, a0, a1) in enumerate(plan.slots):
+            per_slot[s_].append(DeviceFrame.from_range(plan.by, cols, src, 0, nk, nk + a0, nk + a1, 0, cap,
+                                                       pending=pend, slot=(a0, a1)))
+    for c in ft.opaque:
+        for s_, pcs in enumerate(_pieces_of(ctx[c.key])):
+            per_slot[s_].extend(pcs)
+    ctx[ft.root.key] = tuple(PiecewiseFrame(p) for p in per_slot)
+    return True
 
 
 def execute_groupby_agg(ctx, op):

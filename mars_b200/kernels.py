@@ -13,6 +13,7 @@ import torch
 
 from . import _lib
 from ._lib import F64, I64, SUM, SUMSQ, COUNT, MIN, MAX, MarsGBError, check  # noqa: F401
+from ._lib import POST_IDENTITY, POST_MEAN, POST_VAR, MGB_MAX_POST as MAX_POST  # noqa: F401
 
 # number of libmarsgb kernel launches issued through this module (bench.py reports it as gpu_launches)
 launch_counter = 0
@@ -447,6 +448,56 @@ def preagg_dense_async(keys: Sequence[torch.Tensor], vals: Sequence[Optional[tor
     return bi, bf, fc
 
 
+_batch_max = None
+
+
+def dense_batch_max() -> int:
+    global _batch_max
+    if _batch_max is None:
+        c = C.c_int32()
+        check(_lib.load().mgb_dense_batch_max(C.byref(c)))
+        _batch_max = c.value
+    return _batch_max
+
+
+def preagg_dense_batch_async(chunks, accs: Sequence[Tuple[int, int]], val_dtypes, n_keys: int, device):
+    """Band-level batch of the dense pre-aggregation (mgb_preagg_dense_batch_async): ONE launch streams all
+    row batches and yields the partial rows of the whole band -- what n stage=map operands plus the combine
+    tree yield.  ``chunks``: list of (key pointers, value pointers (None for a count-only int64 column), rows);
+    at most ``dense_batch_max()`` of them.  Returns (int block, float block, fast-call) like
+    ``preagg_dense_async``; None when the shape can never be dense."""
+    global _dense_cap
+    lib = _lib.load()
+    nv, n = len(val_dtypes), len(chunks)
+    if nv > _lib.MGB_MAX_VALS or len(accs) > _lib.MGB_MAX_ACCS:
+        return None
+    if n > dense_batch_max():
+        raise MarsGBError(1, f"{n} chunks in one batch (at most {dense_batch_max()})")
+    fc = _fast(n_keys, val_dtypes, accs)
+    if _dense_cap is None:
+        c = C.c_int64()
+        check(lib.mgb_dense_capacity(C.byref(c)))
+        _dense_cap = c.value
+    rows = (C.c_int64 * max(n, 1))()
+    kt = (_lib._pp * max(n, 1))()
+    vt = (_lib._pp * max(n, 1))()
+    keep = []
+    live = 0
+    for i, (kp, vp, m) in enumerate(chunks):
+        karr = (C.c_void_p * n_keys)(*kp)
+        varr = (C.c_void_p * max(nv, 1))(*vp)
+        keep.append((karr, varr))
+        kt[i] = C.cast(karr, _lib._pp)
+        vt[i] = C.cast(varr, _lib._pp)
+        rows[i] = int(m)
+        live += 1 if m else 0
+    bi, bf = fc.alloc(_dense_cap, device)
+    check(lib.mgb_preagg_dense_batch_async(C.byref(fc.spec), n, rows, kt, vt, fc.okp, fc.oap, _dense_cap,
+                                           fc.count_ptr(bi), _stream()))
+    _count(1 if live else 0)
+    return bi, bf, fc
+
+
 SMALL_MAX_ROWS = 2048
 SMALL_MAX_PIECES = 16
 
@@ -513,6 +564,105 @@ def merge_small_async(pieces, acc_ops: Sequence[int], sort: bool = False, checke
                                     SMALL_MAX_ROWS, 1 if sort else 0, fc.count_ptr(bi), _stream()))
     _count(1)
     return bi, bf, fc
+
+
+class PostPlan:
+    """ctypes side of the post steps of one stage=agg call shape (cached by the executors per operand shape)"""
+    __slots__ = ("steps", "n", "is_float")
+
+    def __init__(self, steps, is_float):
+        """steps: list of (kind, a0, a1, a2, ddof); is_float[j]: result column j is float64 (else int64)"""
+        self.n = len(steps)
+        if self.n > _lib.MGB_MAX_POST:
+            raise MarsGBError(3, f"{self.n} result columns (at most {_lib.MGB_MAX_POST} in one launch)")
+        self.steps = (_lib.PostStep * max(self.n, 1))()
+        for j, (kind, a0, a1, a2, ddof) in enumerate(steps):
+            st = self.steps[j]
+            st.kind, st.a0, st.a1, st.a2, st.ddof = kind, a0, a1, a2, ddof
+        self.is_float = list(is_float)
+
+
+def merge_small_post_async(pieces, acc_ops: Sequence[int], post: PostPlan, sort: bool = False):
+    """stage=agg in one launch (mgb_merge_small_post_async): merge of small partial blocks + the post functions.
+    ``pieces`` as for ``merge_small_async`` in pointer form: (key pointers, accumulator pointers, n or None,
+    count pointer, dtype codes, device).  Returns (result block, n_keys, n_post) -- an int64 tensor
+    [1 + n_keys + n_post (+ scratch), SMALL_MAX_ROWS]: row 0 holds the row count (or -1) in its first element,
+    rows 1..n_keys the group keys, then the result columns (float64 bit patterns where ``post.is_float``) --
+    or None when the host can already tell that the input is not small."""
+    lib = _lib.load()
+    n_pieces = len(pieces)
+    na = len(acc_ops)
+    known = sum(p[2] for p in pieces if p[2] is not None)
+    live = sum(1 for p in pieces if p[2] is None or p[2] > 0)
+    if known > SMALL_MAX_ROWS or live > SMALL_MAX_PIECES or na > _lib.MGB_MAX_ACCS or na > _lib.MGB_MAX_VALS:
+        return None
+    nk = len(pieces[0][0])
+    dts = pieces[0][4]
+    device = pieces[0][5]
+    fc = _fast(nk, dts, tuple((a, op) for a, op in enumerate(acc_ops)))
+    kt = (_lib._pp * max(n_pieces, 1))()
+    at = (_lib._pp * max(n_pieces, 1))()
+    rows_arr = (C.c_int64 * max(n_pieces, 1))()
+    rows_dev = (C.c_void_p * max(n_pieces, 1))()
+    keep = []
+    for i, piece in enumerate(pieces):
+        pk, pa, n, cptr = piece[0], piece[1], piece[2], piece[3]
+        if piece[4] != dts and list(piece[4]) != list(dts):
+            raise MarsGBError(1, "partial blocks differ in accumulator dtype")
+        karr = (C.c_void_p * nk)(*pk)
+        aarr = (C.c_void_p * max(na, 1))(*pa)
+        keep.append((karr, aarr))
+        kt[i] = C.cast(karr, _lib._pp)
+        at[i] = C.cast(aarr, _lib._pp)
+        rows_arr[i] = -1 if n is None else int(n)
+        rows_dev[i] = cptr if n is None else None
+    cap = SMALL_MAX_ROWS
+    n_res = 1 + nk + post.n
+    blk = torch.empty((n_res + na, cap), dtype=torch.int64, device=device)
+    base, stride = blk.data_ptr(), cap * 8
+    okp = (C.c_void_p * nk)(*[base + (1 + j) * stride for j in range(nk)])
+    opp = (C.c_void_p * max(post.n, 1))(*[base + (1 + nk + j) * stride for j in range(post.n)])
+    oap = (C.c_void_p * max(na, 1))(*[base + (n_res + a) * stride for a in range(na)])
+    check(lib.mgb_merge_small_post_async(C.byref(fc.spec), n_pieces, rows_arr, rows_dev, kt, at, okp, oap, cap,
+                                         1 if sort else 0, post.steps, post.n, opp, base, _stream()))
+    _count(1)
+    return blk, nk, post.n
+
+
+_pinned = {}
+
+
+def _pinned_block(nbytes: int) -> torch.Tensor:
+    """re-used pinned staging block of the current thread (results are copied out of it before it is re-used)"""
+    import threading
+
+    key = threading.get_ident()
+    buf = _pinned.get(key)
+    if buf is None or buf.numel() * 8 < nbytes:
+        words = max(1 << 15, 1 << (max(nbytes - 1, 1).bit_length() - 3 + 1))
+        buf = _pinned[key] = torch.empty(words, dtype=torch.int64, pin_memory=True)
+    return buf
+
+
+def result_block_to_host(blk: torch.Tensor, nk: int, n_post: int, is_float: Sequence[bool]):
+    """One device -> host copy of the result part of a ``merge_small_post_async`` block (count row, keys, result
+    columns) into a re-used pinned block, one synchronisation.  Returns (n, key arrays, column arrays) cut to
+    n rows -- n < 0: the speculative chain failed somewhere (arrays are None)."""
+    import numpy as np
+
+    cap = blk.shape[1]
+    rows = 1 + nk + n_post
+    host = _pinned_block(rows * cap * 8)[:rows * cap].view(rows, cap)
+    host.copy_(blk[:rows], non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    n = int(host[0, 0])
+    if n < 0:
+        return n, None, None
+    hn = host.numpy()
+    keys = [hn[1 + j, :n].copy() for j in range(nk)]
+    cols = [hn[1 + nk + j, :n].view(np.float64).copy() if is_float[j] else hn[1 + nk + j, :n].copy()
+            for j in range(n_post)]
+    return n, keys, cols
 
 
 def to_host_counted(columns: Sequence[torch.Tensor], count_block: torch.Tensor, count_row: int):

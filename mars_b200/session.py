@@ -15,6 +15,7 @@ reproduces the parts of that machinery the hot path depends on:
 from __future__ import annotations
 
 import collections
+import os
 from typing import Dict, List, Optional
 
 import pandas as pd
@@ -38,6 +39,9 @@ class Session:
         self.world = exchange.world if exchange is not None else 1
         self._results: Dict[str, object] = {}
         self.executed_ops: List[str] = []      # "<OperandClass>:<stage>" log, used by tests
+        # band-level fusion of the tree branch (MGB_FUSE=0: per-operand execution, what a real Mars worker does)
+        self.fuse = os.environ.get("MGB_FUSE", "1") not in ("0", "")
+        self.fused_trees = 0
 
     # ---------------------------------------------------------------------------------- placement
     def _owner(self, chunk: ChunkData, owners: Dict[str, int]) -> int:
@@ -57,7 +61,11 @@ class Session:
     # ---------------------------------------------------------------------------------- execution
     def _run_chunks_local(self, result_chunks: List[ChunkData], ctx: ProcessorContext, owners: Dict[str, int]):
         """single-process form of ``_run_chunks``: same order, same reference-counted release of inputs, none
-        of the placement / transfer bookkeeping"""
+        of the placement / transfer bookkeeping.  The chunk operands of a subtask run back to back on one band
+        (SubtaskProcessor._execute_graph, processor.py:216-282); where the graph holds the tree branch of a
+        groupby-agg (stage=map operands under a concat / combine tree that only a stage=agg operand observes)
+        the band-level batch executor runs that part as ONE launch (executors.execute_fused_tree) -- unless
+        ``self.fuse`` is off, which reproduces the per-operand execution of a real Mars worker."""
         order = [c for c in build_chunk_graph(result_chunks) if c.key not in owners]
         refs: Dict[str, int] = {}
         for c in order:
@@ -67,8 +75,23 @@ class Session:
         keep = {c.key for c in result_chunks}
         log = self.executed_ops
         execute = core.execute
-        for c in order:
-            owners[c.key] = 0
+        fused_at, skip = {}, set()
+        if self.fuse and len(order) > 3:
+            from . import executors
+
+            for ft in executors.find_fused_trees(order, keep):
+                fused_at[ft.root.key] = ft
+                skip.update(c.key for c in ft.nodes)
+
+        def release(op):
+            for inp in op.inputs:
+                k = inp.key
+                n = refs[k] - 1
+                refs[k] = n
+                if n == 0 and k not in keep:
+                    ctx.pop(k, None)
+
+        def run_one(c):
             op = c.op
             if not isinstance(op, DataFrameShuffleProxy):
                 ctx._current_chunk = c
@@ -81,15 +104,37 @@ class Session:
                 if name is None:
                     name = _op_names[tag] = f"{type(op).__name__}:{getattr(op.stage, 'name', None)}"
                 log.append(name)
-            for inp in op.inputs:
-                k = inp.key
-                n = refs[k] - 1
-                refs[k] = n
-                if n == 0 and k not in keep:
-                    ctx.pop(k, None)
+            release(op)
             if op.stage is core.OperandStage.reduce and isinstance(op, core.MapReduceOperand):
                 for key in op.iter_mapper_keys():    # mapper blocks of this reducer are consumed
                     ctx.pop(key, None)
+
+        for c in order:
+            owners[c.key] = 0
+            ft = fused_at.get(c.key) if fused_at else None
+            if ft is not None:
+                from . import executors
+
+                try:
+                    done = executors.execute_fused_tree(ctx, ft)
+                except Exception as e:
+                    raise core.ExecutionError(e) from e
+                if done:
+                    self.fused_trees += 1
+                    for node in ft.nodes:
+                        tag = (type(node.op), node.op.stage)
+                        name = _op_names.get(tag)
+                        if name is None:
+                            name = _op_names[tag] = f"{type(node.op).__name__}:{getattr(node.op.stage, 'name', None)}"
+                        log.append(name)
+                        release(node.op)
+                else:       # not a shape the batch kernel takes: the operands one by one, in graph order
+                    for node in ft.nodes:
+                        run_one(node)
+                continue
+            if c.key in skip:
+                continue
+            run_one(c)
 
     def _run_chunks(self, result_chunks: List[ChunkData], ctx: ProcessorContext, owners: Dict[str, int]):
         if self.world == 1:

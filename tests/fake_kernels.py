@@ -119,3 +119,168 @@ def argsort_keys(keys):
 def gather_rows(cols, perm):
     idx = perm.to(torch.int64)
     return [c[idx] for c in cols]
+
+
+# ----------------------------------------------------------------------------------------------------
+# doubles of the asynchronous / pointer-level entry points: the "device" is host memory, so a raw pointer is
+# read back as a numpy view.  Layouts (block pair, count row, result block) are the real ones of
+# mars_b200.kernels, which the executors rely on.
+# ----------------------------------------------------------------------------------------------------
+import ctypes as _C
+
+from mars_b200 import kernels as _K
+
+POST_IDENTITY, POST_MEAN, POST_VAR, MAX_POST = _K.POST_IDENTITY, _K.POST_MEAN, _K.POST_VAR, _K.MAX_POST
+PostPlan = _K.PostPlan
+SMALL_MAX_ROWS, SMALL_MAX_PIECES = _K.SMALL_MAX_ROWS, _K.SMALL_MAX_PIECES
+DENSE_GROUPS = 16          # a batch with more groups "is not dense" (device count -1), like a CTA overflowing
+_DENSE_CAP = 148 * 16
+
+
+def _view(ptr, n, is_float):
+    if n == 0:
+        return np.empty(0, dtype=np.float64 if is_float else np.int64)
+    buf = (_C.c_int64 * n).from_address(int(ptr))
+    a = np.frombuffer(buf, dtype=np.int64)
+    return a.view(np.float64) if is_float else a
+
+
+def dense_batch_max():
+    return 64
+
+
+def _agg_np(keys, vals, accs, is_float_val, sort=False):
+    """(key arrays, accumulator arrays) with pandas (first-appearance order unless sort)"""
+    names = [f"k{j}" for j in range(len(keys))]
+    df = pd.DataFrame({n: k for n, k in zip(names, keys)})
+    outs = []
+    for col, op in accs:
+        v = vals[col]
+        df["_v"] = v * v if op == SUMSQ else v
+        g = df.groupby(names, sort=sort)["_v"]
+        outs.append({SUM: g.sum, SUMSQ: g.sum, COUNT: g.count, MIN: g.min, MAX: g.max}[op]().to_numpy())
+    idx = df.groupby(names, sort=sort).size().index
+    return [idx.get_level_values(j).to_numpy() for j in range(len(keys))], outs
+
+
+def _fill_block(fc, bi, bf, keys, accs_out, n):
+    k_views, a_views = fc.views(bi, bf)
+    if n >= 0:
+        for dst, src in zip(k_views, keys):
+            dst[:n] = torch.from_numpy(np.ascontiguousarray(src))
+        for dst, src in zip(a_views, accs_out):
+            dst[:n] = torch.from_numpy(np.ascontiguousarray(src).astype(np.float64 if dst.dtype == torch.float64 else np.int64))
+    bi[fc.n_int, 0] = n
+
+
+def preagg_dense_batch_async(chunks, accs, val_dtypes, n_keys, device):
+    calls.append("preagg_dense_batch_async")
+    fc = _K._fast(n_keys, val_dtypes, accs)
+    bi, bf = fc.alloc(_DENSE_CAP, device)
+    used = {c for c, _ in accs}
+    keys = [np.concatenate([_view(kp[j], m, False) for kp, vp, m in chunks]) for j in range(n_keys)]
+    vals = []
+    for c, dt in enumerate(val_dtypes):
+        if c in used and all(vp[c] is not None for _, vp, _ in chunks):
+            vals.append(np.concatenate([_view(vp[c], m, dt == F64) for _, vp, m in chunks]))
+        else:   # count-only int64 column that was not uploaded: its values do not matter
+            vals.append(np.zeros(len(keys[0]), dtype=np.int64))
+    k, a = _agg_np(keys, vals, accs, None)
+    n = len(k[0]) if len(k[0]) <= DENSE_GROUPS else -1
+    _fill_block(fc, bi, bf, k, a, n)
+    return bi, bf, fc
+
+
+def preagg_dense_async(keys, vals, accs, checked=False, val_dtypes=None):
+    calls.append("preagg_dense_async")
+    dts = val_dtypes if val_dtypes is not None else [dtype_code(v) for v in vals]
+    chunk = ([k.data_ptr() for k in keys], [None if v is None else v.data_ptr() for v in vals], int(keys[0].numel()))
+    calls.pop()
+    out = preagg_dense_batch_async([chunk], accs, dts, len(keys), keys[0].device)
+    calls[-1] = "preagg_dense_async"
+    return out
+
+
+def _merge_np(pieces, acc_ops, sort):
+    """pieces in pointer form -> (n or -1, key arrays, merged accumulator arrays)"""
+    nk, dts = len(pieces[0][0]), pieces[0][4]
+    ks, vs = [[] for _ in range(nk)], [[] for _ in dts]
+    for kp, ap, n, cptr, _, _ in pieces:
+        if n is None:
+            n = int(_view(cptr, 1, False)[0])
+            if n < 0:
+                return -1, None, None
+        for j in range(nk):
+            ks[j].append(_view(kp[j], n, False).copy())
+        for a in range(len(dts)):
+            vs[a].append(_view(ap[a], n, dts[a] == F64).copy())
+    keys = [np.concatenate(k) for k in ks]
+    vals = [np.concatenate(v) for v in vs]
+    if len(keys[0]) > SMALL_MAX_ROWS:
+        return -1, None, None
+    k, a = _agg_np(keys, vals, [(i, op) for i, op in enumerate(acc_ops)], None, sort=sort)
+    return len(k[0]), k, a
+
+
+def merge_small_async(pieces, acc_ops, sort=False, checked=False):
+    calls.append("merge_small_async")
+    known = sum(p[2] for p in pieces if p[2] is not None)
+    live = sum(1 for p in pieces if p[2] is None or p[2] > 0)
+    if known > SMALL_MAX_ROWS or live > SMALL_MAX_PIECES or len(pieces[0]) != 6:
+        return None
+    nk, dts, dev = len(pieces[0][0]), pieces[0][4], pieces[0][5]
+    fc = _K._fast(nk, dts, tuple((a, op) for a, op in enumerate(acc_ops)))
+    bi, bf = fc.alloc(SMALL_MAX_ROWS, dev)
+    n, k, a = _merge_np(pieces, acc_ops, sort)
+    _fill_block(fc, bi, bf, k, a, n)
+    return bi, bf, fc
+
+
+def merge_small_post_async(pieces, acc_ops, post, sort=False):
+    calls.append("merge_small_post_async")
+    known = sum(p[2] for p in pieces if p[2] is not None)
+    live = sum(1 for p in pieces if p[2] is None or p[2] > 0)
+    if known > SMALL_MAX_ROWS or live > SMALL_MAX_PIECES:
+        return None
+    nk, dts, dev = len(pieces[0][0]), pieces[0][4], pieces[0][5]
+    blk = torch.zeros((1 + nk + post.n + len(acc_ops), SMALL_MAX_ROWS), dtype=torch.int64, device=dev)
+    n, k, a = _merge_np(pieces, acc_ops, sort)
+    blk[0, 0] = n
+    if n >= 0:
+        for j in range(nk):
+            blk[1 + j, :n] = torch.from_numpy(np.ascontiguousarray(k[j]))
+        for j in range(post.n):
+            st = post.steps[j]
+            f = lambda i: a[i].astype(np.float64)   # noqa: E731
+            with np.errstate(all="ignore"):
+                if st.kind == POST_IDENTITY:
+                    r = a[st.a0]
+                elif st.kind == POST_MEAN:
+                    r = f(st.a0) / f(st.a1)
+                else:
+                    r = orc.post_var(pd.Series(f(st.a1)), pd.Series(f(st.a0)), pd.Series(f(st.a2)), ddof=st.ddof).to_numpy()
+            r = np.ascontiguousarray(r)
+            blk[1 + nk + j, :n] = torch.from_numpy(r.view(np.int64) if r.dtype == np.float64 else r.astype(np.int64))
+    return blk, nk, post.n
+
+
+def result_block_to_host(blk, nk, n_post, is_float):
+    calls.append("result_block_to_host")
+    n = int(blk[0, 0])
+    if n < 0:
+        return n, None, None
+    hn = blk.numpy()
+    keys = [hn[1 + j, :n].copy() for j in range(nk)]
+    cols = [hn[1 + nk + j, :n].view(np.float64).copy() if is_float[j] else hn[1 + nk + j, :n].copy() for j in range(n_post)]
+    return n, keys, cols
+
+
+def to_host_counted(columns, count_block, count_row):
+    n = int(count_block[count_row, 0])
+    if n < 0:
+        return n, None
+    return n, [c[:n].numpy().copy() for c in columns]
+
+
+def to_host(columns):
+    return [c.numpy().copy() for c in columns]

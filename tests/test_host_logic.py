@@ -244,3 +244,80 @@ def test_session_pauses_and_restores_the_cyclic_gc(md):
     got = r.execute(session=md.new_session(default=False))
     assert gc.isenabled()
     assert got is r
+
+
+# ---------------------------------------------------------------- band-level fusion of the tree branch
+def _run_tree(md, raw, by, func, chunk, method="tree", fuse=True, sort=True):
+    sess = md.new_session(default=False)
+    sess.fuse = fuse
+    r = md.DataFrame(raw, chunk_size=chunk).to_gpu().groupby(by, sort=sort).agg(func, method=method)
+    r.execute(session=sess)
+    return r.fetch(session=sess), sess
+
+
+@pytest.mark.parametrize("func", [["sum", "mean", "count"], ["min", "max", "var"],
+                                  {"v0": ["sum", "mean"], "v1": ["count"]}])
+def test_fused_tree_is_one_batch_launch_and_one_agg_launch(md, func):
+    rng = np.random.default_rng(1)
+    n = 4000
+    raw = pd.DataFrame({"k1": rng.integers(0, 3, n), "k2": rng.integers(0, 2, n), "v0": rng.normal(10, 3, n),
+                        "v1": rng.integers(0, 9, n)})
+    from mars_b200 import executors
+
+    executors._dense_rejected.clear()
+    fake_kernels.calls.clear()
+    got, sess = _run_tree(md, raw, ["k1", "k2"], func, 400)
+    assert sess.fused_trees == 1
+    assert fake_kernels.calls.count("preagg_dense_batch_async") == 1          # 10 map operands + 3 combines: one launch
+    assert fake_kernels.calls.count("merge_small_post_async") == 1            # merge + post functions + sort: one launch
+    assert "preagg_dense_async" not in fake_kernels.calls and "post_mean" not in fake_kernels.calls
+    # the plan the reference's tiler produced is still what was (logically) executed
+    assert sess.executed_ops.count("DataFrameGroupByAgg:map") == 10
+    assert sess.executed_ops.count("DataFrameGroupByAgg:combine") == 3
+    exp = orc.run_groupby_agg(raw, ["k1", "k2"], func, 400, method="tree", sort=True)
+    assert_frames_match(got, exp, sort_index=False)
+    # per-operand execution (what a real Mars worker does) gives the same frame
+    got2, sess2 = _run_tree(md, raw, ["k1", "k2"], func, 400, fuse=False)
+    assert sess2.fused_trees == 0
+    assert_frames_match(got2, exp, sort_index=False)
+
+
+def test_fused_tree_under_method_auto_merges_the_sampled_partials(md):
+    """method='auto' runs the first combine_size map operands on their own (size sampling,
+    aggregation.py:887-925); the rest of the tree is fused and the sampled partial tuples join as ready pieces"""
+    rng = np.random.default_rng(2)
+    n = 6000
+    raw = pd.DataFrame({"akey": rng.integers(0, 5, n), "av0": rng.random(n), "av1": rng.random(n)})
+    fake_kernels.calls.clear()
+    got, sess = _run_tree(md, raw, "akey", ["sum", "mean", "count"], 500, method="auto")
+    assert sess.fused_trees == 1
+    assert fake_kernels.calls.count("preagg_dense_async") == 4 and fake_kernels.calls.count("preagg_dense_batch_async") == 1
+    exp = orc.run_groupby_agg(raw, "akey", ["sum", "mean", "count"], 500, method="tree", sort=True)
+    assert_frames_match(got, exp, sort_index=False)
+
+
+def test_fused_tree_replays_when_the_band_is_not_low_cardinality(md):
+    from mars_b200 import executors
+
+    rng = np.random.default_rng(3)
+    n = 3000
+    raw = pd.DataFrame({"fkey": rng.integers(0, 200, n), "fv": rng.random(n)})     # 200 groups > what a CTA holds
+    before = set(executors._dense_rejected)
+    fake_kernels.calls.clear()
+    got, sess = _run_tree(md, raw, "fkey", ["sum", "count", "max"], 300)
+    exp = orc.run_groupby_agg(raw, "fkey", ["sum", "count", "max"], 300, method="tree", sort=True)
+    assert_frames_match(got, exp, sort_index=False)
+    assert fake_kernels.calls.count("preagg_dense_batch_async") == 1 and "groupby_aggregate" in fake_kernels.calls
+    assert set(executors._dense_rejected) - before          # remembered: the next run goes per operand
+    fake_kernels.calls.clear()
+    got2, sess2 = _run_tree(md, raw, "fkey", ["sum", "count", "max"], 300)
+    assert sess2.fused_trees == 0 and "preagg_dense_batch_async" not in fake_kernels.calls
+    assert_frames_match(got2, exp, sort_index=False)
+
+
+def test_shuffle_branch_is_not_fused(md):
+    rng = np.random.default_rng(4)
+    raw = pd.DataFrame({"key": rng.integers(0, 5, 2000), "v": rng.random(2000)})
+    got, sess = _run_tree(md, raw, "key", ["sum"], 250, method="shuffle", sort=False)
+    assert sess.fused_trees == 0
+    assert_frames_match(got, raw.groupby("key").agg(["sum"]), sort_index=True)
