@@ -280,6 +280,16 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------------
+# bench sizes of the other BASELINE.json configs (sub-records of the N=1 line): exact chunk shape, fewer chunks
+CONFIG_BENCH = {
+    "cfg1": (10_000_000, 1_000_000),         # full size, default sort=True / method='auto' (tree)
+    "cfg1s": (10_000_000, 1_000_000),        # same data, sort=False + method='shuffle' (the named hash path, R = 10)
+    "cfg3": (8 * 15_625_000, 15_625_000),    # 1/8 of the rows, R = 8
+    "cfg4": (8 * 7_812_500, 7_812_500),
+    "cfg5": (8 * 15_625_000, 15_625_000),
+}
+
+
 def main_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -301,17 +311,20 @@ def main_ours(args):
 
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    exchange = None
+    comm = None
     if world > 1:
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+        from mars_b200.parallel import NcclTransport
+
+        comm = NcclTransport(rank, world)       # libmarsgb's own communicator (dlopen()ed NCCL)
     lib = _lib.load()
 
     sizes = chunk_sizes(args.rows, args.chunk_rows)
     n_chunks = len(sizes)
     rows_rank = sum(sizes)
 
-    # host chunks in pinned memory (one flat pinned tensor per chunk, columns are views) -> pandas frames
-    host_frames, dev_frames = [], []
+    # host chunks: pinned (one flat pinned tensor per chunk, columns are views) and pageable pandas frames
+    host_frames, host_pageable, dev_frames = [], [], []
     for c, rows in enumerate(sizes):
         cols = gen_chunk(rank * n_chunks + c, rows)
         flat = torch.empty((len(COLUMNS), rows), dtype=torch.int64).pin_memory()
@@ -321,10 +334,10 @@ def main_ours(args):
             view[:] = cols[name]
             data[name] = view
         host_frames.append(pd.DataFrame(data, copy=False))
+        host_pageable.append(pd.DataFrame(cols, copy=False))
         dev_frames.append(DeviceFrame([], None, COLUMNS, [
             flat[j].to(dev, non_blocking=True).view(torch.float64 if cols[n_].dtype == np.float64 else torch.int64)
             for j, n_ in enumerate(COLUMNS)], rows))
-        del cols
     torch.cuda.synchronize()
 
     def barrier():
@@ -333,29 +346,29 @@ def main_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step(resident: bool):
-        frames = dev_frames if resident else host_frames
+    def step(frames, fuse=True):
         mdf = md.DataFrame.from_chunks(frames)
-        if not resident:
+        if frames is not dev_frames:
             mdf = mdf.to_gpu()
         sess = md.new_session(default=False)
+        sess.fuse = fuse
         r = mdf.groupby(BY).agg(Q1_FUNC, method="auto")
         if world == 1:
             r.execute(session=sess)
             out = r.fetch(session=sess)
         else:
-            out = sess.execute_sharded_tree(r)
+            out = sess.execute_sharded_tree(r, comm=comm)
         return out
 
-    def timed(resident: bool, steps: int, warmup: int, sampler=None):
+    def timed(frames, steps, warmup, sampler=None, fuse=True):
         for _ in range(warmup):
-            step(resident)
+            step(frames, fuse)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record()
         for _ in range(steps):
-            out = step(resident)
+            out = step(frames, fuse)
             if sampler is not None:
                 sampler.poke()
         e1.record()
@@ -371,24 +384,30 @@ def main_ours(args):
             ms = float(t.item())
         return ms, out
 
-    # ---- e2e (host chunks) first, then the device-resident headline with clocks + per-kernel timing
+    # ---- e2e (host chunks: pinned, then pageable), then the device-resident headline with clocks + per-kernel timing
     from mars_b200 import device as _dev
 
     e2e_steps = max(1, min(args.steps, 3))
-    step(False)                                   # warm-up (allocator, plans)
+    step(host_frames)                                   # warm-up (allocator, plans)
     h2d0 = _dev.h2d_bytes
-    ms_e2e, out_e2e = timed(False, e2e_steps, 0)
+    ms_e2e, out_e2e = timed(host_frames, e2e_steps, 0)
     h2d_bytes = (_dev.h2d_bytes - h2d0) // e2e_steps   # bytes really copied per step (counted at the copy call)
+    ms_page = None
+    if world == 1:
+        step(host_pageable)
+        ms_page, _ = timed(host_pageable, 2, 0)
+        ms_page /= 2
+    del host_pageable
 
     sampler = ClockSampler(local)
     lib.mgb_prof_enable(1)
     for _ in range(args.warmup):
-        step(True)
+        step(dev_frames)
     barrier()
     lib.mgb_prof_reset()
     launches0 = kernels.launch_counter
     sampler.start()
-    ms, out = timed(True, args.steps, 0, sampler)
+    ms, out = timed(dev_frames, args.steps, 0, sampler)
     clocks = sampler.stop()
     launches = kernels.launch_counter - launches0
     import ctypes as C
@@ -401,12 +420,51 @@ def main_ours(args):
             prof[name] = {"ms_total": tot.value, "launches": cnt.value}
     lib.mgb_prof_enable(0)
 
+    # the same step without the band-level batch: every chunk operand on its own, what a real Mars worker does
+    po_steps = max(2, min(args.steps, 5))
+    ms_po, out_po = timed(dev_frames, po_steps, 2, fuse=False)
+
+    parity = None
+    if rank == 0 and world == 1 and cpu_baseline and cpu_baseline.get("kind") != "unavailable":
+        # the result of this run against the CPU arm's on the SAME chunks (the cpu leg's bounded sample)
+        try:
+            n_cpu = min(8, n_chunks)
+            sess = md.new_session(default=False)
+            r = md.DataFrame.from_chunks(dev_frames[:n_cpu]).groupby(BY).agg(Q1_FUNC, method="auto")
+            got = r.execute(session=sess).fetch(session=sess)
+            sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            import mars_groupby_oracle as orc
+
+            raw = pd.concat(host_frames[:n_cpu], axis=0, ignore_index=True)
+            exp = orc.run_groupby_agg(raw, BY, Q1_FUNC, args.chunk_rows, method="tree", sort=True)
+            ok = list(got.columns) == list(exp.columns) and got.index.equals(exp.index)
+            for c in exp.columns:
+                g, e = got[c].to_numpy(), exp[c].to_numpy()
+                ok = ok and (np.array_equal(g, e) if c[1] == "count" else np.allclose(g, e, rtol=1e-9, atol=0))
+            parity = {"ok": bool(ok), "mode": f"full frame vs the oracle on the first {n_cpu} chunks (counts bit-exact, float64 1e-9)"}
+        except Exception as e:  # noqa: BLE001
+            parity = {"ok": False, "mode": f"check failed to run: {e!r}"}
+
+    configs = None
+    if rank == 0 and world == 1 and not args.no_configs:
+        del host_frames, dev_frames
+        torch.cuda.empty_cache()
+        import config_runner
+
+        configs = {}
+        for name, (rows, chunk_rows) in CONFIG_BENCH.items():
+            try:
+                configs[name] = config_runner.run_record(name, rows, chunk_rows, repeats=2)
+            except Exception as e:  # noqa: BLE001
+                configs[name] = {"config": name, "error": repr(e)[:300]}
+
     if rank == 0:
-        # sanity: the two paths agree and the counts add up
-        assert out.shape == out_e2e.shape
+        # sanity: the paths agree and the counts add up
+        assert out.shape == out_e2e.shape == out_po.shape
         total_rows = rows_rank * world
         cnt_col = ("orderkey", "count")
         assert int(out[cnt_col].sum()) == total_rows, (int(out[cnt_col].sum()), total_rows)
+        assert int(out_po[cnt_col].sum()) == total_rows
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -417,11 +475,12 @@ def main_ours(args):
         per_launch_ms = dom["ms_total"] / dom["launches"]
         rows_per_launch = rows_rank * args.steps / dom["launches"]
         achieved = rows_per_launch * BYTES_PER_ROW / (per_launch_ms * 1e-3) / 1e9
-        traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu capture
+        traffic, traffic_per_row = None, None   # dram__bytes_read.sum + dram__bytes_write.sum per launch (committed ncu capture)
         tpath = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
         if os.path.exists(tpath):
             try:
-                traffic = json.load(open(tpath))["dram_bytes_per_row"] * rows_per_launch
+                traffic_per_row = json.load(open(tpath))["dram_bytes_per_row"]
+                traffic = traffic_per_row * rows_per_launch
             except Exception:  # noqa: BLE001
                 traffic = None
         value = total_rows * args.steps / (ms * 1e-3)
@@ -435,18 +494,32 @@ def main_ours(args):
                     "h2d_note": "columns are uploaded on first use: the int64 column that is only counted never crosses "
                                 "PCIe (chunk bytes in host memory: %d per step per GPU)" % (rows_rank * BYTES_PER_ROW),
                     "d2h_bytes_per_step": int(out.shape[0] * (out.shape[1] + len(BY)) * 8),
-                    "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps},
+                    "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps, "host_memory": "pinned",
+                    "pageable": None if ms_page is None else {"value": total_rows / (ms_page * 1e-3), "ms_per_step": ms_page,
+                                                               "note": "same step from pageable pandas chunks (what a Mars chunk store hands over)"}},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "k_preagg_dense" if "preagg_dense" in prof else "k_preagg_hash/k_preagg_smem",
                          "kernel_ms_per_launch": per_launch_ms, "bytes_per_launch": rows_per_launch * BYTES_PER_ROW,
+                         "launches": dom["launches"],
+                         "frac_on_traffic": None if not traffic_per_row else achieved * traffic_per_row / BYTES_PER_ROW / peak,
+                         "note": "achieved counts the 64 algorithmic B/row (SURVEY 8d); the kernel does not read the count-only "
+                                 "int64 column, frac_on_traffic counts the DRAM bytes it really moves (ncu capture)",
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
                          "step_hbm_frac": (rows_rank * BYTES_PER_ROW / (ms / args.steps * 1e-3) / 1e9) / peak},
             "kernel_time_ms": prof,
+            "per_operand": {"value": total_rows * po_steps / (ms_po * 1e-3), "unit": "rows/s", "ms_per_step": ms_po / po_steps,
+                            "steps": po_steps,
+                            "note": "same step with the band-level batch off (MGB_FUSE=0): every chunk operand executed on "
+                                    "its own through execute(ctx, op), as under a real Mars worker"},
+            "parity": parity,
             "clocks": clocks,
             "cpu_baseline": cpu_baseline,
+            "configs": configs,
         }
         print(json.dumps(line), flush=True)
+    if comm is not None:
+        comm.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -460,6 +533,7 @@ def main():
     ap.add_argument("--rows", type=int, default=ROWS_PER_GPU, help="rows per GPU (default: SF10 lineitem cardinality)")
     ap.add_argument("--chunk-rows", type=int, default=CHUNK_ROWS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the sub-records of the other BASELINE.json configs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -837,13 +837,15 @@ def find_fused_trees(order, keep) -> List[FusedTree]:
         for inp in c.op.inputs:
             nsucc[inp.key] = nsucc.get(inp.key, 0) + 1
     out = []
+    cands = []
     for a in order:
         op = a.op
-        if type(op).__name__ != "DataFrameGroupByAgg" or _stage(op) != "agg" or len(op.inputs) != 1:
-            continue
-        root = op.inputs[0]
-        if root.key not in pos:
-            continue
+        name, st = type(op).__name__, _stage(op)
+        if name == "DataFrameGroupByAgg" and st == "agg" and len(op.inputs) == 1 and op.inputs[0].key in pos:
+            cands.append((a, op.inputs[0]))
+        elif a.key in keep and ((name == "DataFrameGroupByAgg" and st == "combine") or name == "DataFrameConcat"):
+            cands.append((None, a))      # the tree's root itself is a result chunk (sharded tree: the feed of the agg)
+    for a, root in cands:
         leaves, interior, opaque, ok = [], [], [], True
         stack = [root]
         while stack:
@@ -852,7 +854,10 @@ def find_fused_trees(order, keep) -> List[FusedTree]:
                 opaque.append(c)
                 continue
             name, st = type(c.op).__name__, _stage(c.op)
-            if nsucc.get(c.key, 0) != 1 or c.key in keep:
+            if c is not root and (nsucc.get(c.key, 0) != 1 or c.key in keep):
+                ok = False
+                break
+            if c is root and a is not None and (nsucc.get(c.key, 0) != 1 or c.key in keep):
                 ok = False
                 break
             if name == "DataFrameGroupByAgg" and st == "map":

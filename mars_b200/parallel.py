@@ -97,6 +97,15 @@ class NcclTransport:
         self.bytes_sent += nbytes
         return recv_cols
 
+    def allgather_i64(self, send: torch.Tensor, recv: torch.Tensor):
+        """recv[r * n : (r + 1) * n] = rank r's ``send`` (8-byte elements; mgb_comm_allgather_i64, ncclAllGather)"""
+        if not (send.is_cuda and recv.is_cuda and send.is_contiguous() and recv.is_contiguous()):
+            raise MarsGBError(2, "NCCL all-gather needs contiguous CUDA tensors")
+        if send.element_size() != 8 or recv.numel() != send.numel() * self.world:
+            raise MarsGBError(1, "all-gather buffers do not match")
+        check(self._lib.mgb_comm_allgather_i64(self._comm, send.data_ptr(), recv.data_ptr(), send.numel(),
+                                               torch.cuda.current_stream().cuda_stream))
+
     def close(self):
         if self._comm:
             self._lib.mgb_comm_destroy(self._comm)

@@ -215,7 +215,7 @@ class Session:
         return df
 
     # ------------------------------------------------------------------------- sharded tree branch
-    def execute_sharded_tree(self, df: DataFrame, group=None, max_groups: int = 2368):
+    def execute_sharded_tree(self, df: DataFrame, group=None, max_groups: int = 2368, comm=None):
         """Weak-scaling execution of a low-cardinality (tree-branch) groupby-agg over row chunks that are
         sharded across ranks -- one process per GPU:
 
@@ -261,32 +261,40 @@ class Session:
         finally:
             self.rank, self.world = saved_rank, saved_world
         steps = _plan_steps(agg_chunk.op, None)
-        merged = _merge_partials(_pieces_of(ctx[feed.key]), steps, sort=False)
-        # Every rank ships its local result as the block pair of the speculative small-merge layout (int64
-        # block with the row count in its last row + float64 block, fixed capacity): two all-gathers of
-        # identical shape on every rank, no host synchronisation when the result is still speculative;
-        # rank 0's stage=agg merge reads every rank's row count on the device.
-        pend = merged[0]._pending
-        if (pend is not None and pend.value is None and pend.fblock is not None
-                and all(f._pending is pend for f in merged)):
+        slots = _pieces_of(ctx[feed.key])
+        # Every rank ships its local result as the block pair of a speculative result (int64 block with the row
+        # count in its last row + float64 block, fixed capacity): ONE all-gather of identical shape on every rank,
+        # no host synchronisation while the result is still speculative; rank 0's stage=agg merge reads every
+        # rank's row count on the device.  The fused local tree leaves exactly such a block (one piece per slot,
+        # one shared Pending): it is shipped as it is.  A rank whose partials do not fit the small-merge layout
+        # ships a poisoned count (-1) instead of raising before the collective -- all ranks always enter it.
+        pend = slots[0][0]._pending if len(slots[0]) == 1 else None
+        if not (pend is not None and pend.value is None and pend.fblock is not None
+                and all(len(sl) == 1 and sl[0]._pending is pend for sl in slots)):
+            merged = _merge_partials(slots, steps, sort=False)
+            pend = merged[0]._pending
+            if (pend is not None and pend.value is None and pend.fblock is not None
+                    and all(f._pending is pend for f in merged)):
+                pass
+            else:
+                pend = None
+        else:
+            merged = [sl[0] for sl in slots]
+        if pend is not None:
             bi, bf, fc = pend.block, pend.fblock, pend.layout
         else:
             bi, bf, fc = self._pack_block(merged, steps, max_groups)
         root = bi._base
-        if root is not None and bf._base is root and root.shape[0] == bi.shape[0] + bf.shape[0]:
-            # both blocks are views of one allocation (kernels._FastCall.alloc): ONE all-gather
-            g = torch.empty((world * root.shape[0], root.shape[1]), dtype=root.dtype, device=root.device)
-            dist.all_gather_into_tensor(g, root, group=group)     # concatenation along dim 0
-            g = g.view(world, root.shape[0], root.shape[1])
-            gi = g[:, :bi.shape[0]]
-            gf = g[:, bi.shape[0]:].view(torch.float64)
+        if root is None or bf._base is not root or root.shape[0] != bi.shape[0] + bf.shape[0]:
+            root = torch.cat([bi, bf.view(torch.int64)], dim=0)
+        g = torch.empty((world * root.shape[0], root.shape[1]), dtype=root.dtype, device=root.device)
+        if comm is not None:     # the library's own NCCL all-gather (mgb_comm_allgather_i64)
+            comm.allgather_i64(root, g)
         else:
-            gi = torch.empty((world * bi.shape[0], bi.shape[1]), dtype=bi.dtype, device=bi.device)
-            gf = torch.empty((world * bf.shape[0], bf.shape[1]), dtype=bf.dtype, device=bf.device)
-            dist.all_gather_into_tensor(gi, bi, group=group)
-            dist.all_gather_into_tensor(gf, bf, group=group)
-            gi = gi.view(world, bi.shape[0], bi.shape[1])
-            gf = gf.view(world, bf.shape[0], bf.shape[1])
+            dist.all_gather_into_tensor(g, root, group=group)     # concatenation along dim 0
+        g = g.view(world, root.shape[0], root.shape[1])
+        gi = g[:, :bi.shape[0]]
+        gf = g[:, bi.shape[0]:].view(torch.float64)
         if rank != 0:
             return None
 
@@ -303,8 +311,7 @@ class Session:
                 a1 = a0 + len(f.columns)
                 pieces[i].append(DeviceFrame(f.index_names, k, f.columns, a[a0:a1], pending=pr, slot=(a0, a1)))
                 a0 = a1
-        slots = [PiecewiseFrame(p) for p in pieces]
-        ctx[feed.key] = tuple(slots)
+        ctx[feed.key] = tuple(PiecewiseFrame(p) for p in pieces)
         ctx.set_current_chunk(agg_chunk)
         try:
             core.execute(ctx, agg_chunk.op)
@@ -322,16 +329,16 @@ class Session:
 
         n = len(merged[0])
         cap = K.SMALL_MAX_ROWS
-        if n > min(cap, max_groups):
-            raise NotImplementedError(f"{n} groups on one rank: use the shuffle branch")
+        poisoned = n > min(cap, max_groups)      # does not fit: ship count -1, never raise before the collective
         cols = [t for f in merged for t in f.data]
         ops = [_OPCODE[st.agg_func] for st, f in zip(steps, merged) for _ in f.columns]
         fc = K._fast(len(merged[0].index), [K.dtype_code(t) for t in cols], tuple(enumerate(ops)))
         bi, bf = fc.alloc(cap, merged[0].device)
         keys, accs = fc.views(bi, bf)
-        for dst, src in zip(keys + accs, list(merged[0].index) + cols):
-            dst[:n].copy_(src)
-        bi[fc.n_int, :1].fill_(n)
+        if not poisoned:
+            for dst, src in zip(keys + accs, list(merged[0].index) + cols):
+                dst[:n].copy_(src)
+        bi[fc.n_int, :1].fill_(-1 if poisoned else n)
         return bi, bf, fc
 
     def fetch(self, df: DataFrame) -> pd.DataFrame:

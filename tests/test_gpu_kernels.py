@@ -510,3 +510,123 @@ def test_range_partition_ids_match_oracle(K, n_keys):
         pcols = [np.array([t[j] for t in tuples], dtype=np.int64) for j in range(2)]
     got = K.range_partition_ids([dev(c) for c in cols], [dev(p) for p in pcols]).cpu().numpy()
     np.testing.assert_array_equal(got, orc.range_partition_ids(cols, pivots))
+
+
+# ------------------------------------------------------------------- band-level batch / one-launch agg stage
+def _batch(K, chunks_keys, chunks_vals, accs, skip_cols=()):
+    """mgb_preagg_dense_batch_async over host chunks -> (n, key arrays, accumulator arrays) read back"""
+    dk = [[dev(k) for k in ks] for ks in chunks_keys]
+    dv = [[None if c in skip_cols else dev(v) for c, v in enumerate(vs)] for vs in chunks_vals]
+    dts = [K.F64 if v.dtype == np.float64 else K.I64 for v in chunks_vals[0]]
+    chunks = [([k.data_ptr() for k in ks], [None if v is None else v.data_ptr() for v in vs], len(chunks_keys[i][0]))
+              for i, (ks, vs) in enumerate(zip(dk, dv))]
+    res = K.preagg_dense_batch_async(chunks, tuple(_codes(K, accs)), dts, len(chunks_keys[0]), torch.device("cuda", 0))
+    if res is None:
+        return None
+    bi, bf, fc = res
+    torch.cuda.synchronize()
+    n = int(bi[fc.n_int, 0])
+    if n < 0:
+        return n, None, None
+    k, a = fc.views(bi, bf, n)
+    return n, [t.cpu().numpy() for t in k], [t.cpu().numpy() for t in a]
+
+
+@pytest.mark.parametrize("n_keys", [1, 2])
+@pytest.mark.parametrize("sizes", [[5000, 0, 1024, 777, 300_000, 1, 2048], [4_194_304, 1_265_796], [10] * 64, [0, 0]])
+def test_dense_batch_streams_all_chunks_in_one_launch(K, n_keys, sizes):
+    """ragged chunk sizes (empty, shorter than a tile, exact multiples of the tile): one launch == pandas on the
+    concatenation; sum / mean / count shape with NaNs and a count-only int64 column that is never uploaded"""
+    rng = np.random.default_rng(len(sizes) + n_keys)
+    ck, cv = [], []
+    for n in sizes:
+        ck.append([rng.integers(0, 3, n, dtype=np.int64)] + ([rng.integers(-1, 1, n, dtype=np.int64)] if n_keys == 2 else []))
+        v = [rng.random(n), rng.normal(5, 2, n), rng.integers(1, 10 ** 6, n, dtype=np.int64)]
+        v[1][rng.random(n) < 0.1] = np.nan
+        cv.append(v)
+    accs = [(0, "sum"), (1, "sum"), (0, "count"), (1, "count"), (2, "count")]
+    before = K.launch_counter
+    got = _batch(K, ck, cv, accs, skip_cols=(2,))
+    assert K.launch_counter - before == (1 if sum(sizes) else 0)
+    n, gk, ga = got
+    keys = [np.concatenate([c[j] for c in ck]) for j in range(n_keys)]
+    vals = [np.concatenate([c[j] for c in cv]) for j in range(3)]
+    if sum(sizes) == 0:
+        assert n == 0
+        return
+    ek, ea = pandas_agg(keys, vals, accs)
+    assert n == len(ek[0])
+    order = np.lexsort(tuple(reversed(gk)))
+    for a, b in zip(gk, ek):
+        np.testing.assert_array_equal(a[order], b)
+    for (col, op), a, b in zip(accs, ga, ea):
+        if op == "count":
+            np.testing.assert_array_equal(a[order], b)
+        else:
+            np.testing.assert_allclose(a[order], b, rtol=1e-9, atol=0)
+
+
+def test_dense_batch_all_ops_and_overflow(K):
+    rng = np.random.default_rng(9)
+    sizes = [70_000, 999, 130_000]
+    ck = [[rng.integers(-2, 3, n, dtype=np.int64)] for n in sizes]
+    cv = [[rng.normal(10, 3, n), rng.integers(-1000, 1000, n, dtype=np.int64)] for n in sizes]
+    accs = [(c, o) for c in range(2) for o in ALL_OPS]
+    n, gk, ga = _batch(K, ck, cv, accs)
+    ek, ea = pandas_agg([np.concatenate([c[0] for c in ck])], [np.concatenate([c[j] for c in cv]) for j in range(2)], accs)
+    order = np.lexsort(tuple(reversed(gk)))
+    np.testing.assert_array_equal(gk[0][order], ek[0])
+    for (col, op), a, b in zip(accs, ga, ea):
+        if op in ("count", "min", "max") or b.dtype.kind in "iu":
+            np.testing.assert_array_equal(a[order], b.astype(a.dtype), err_msg=f"{op} of column {col}")
+        else:
+            np.testing.assert_allclose(a[order], b, rtol=1e-9, atol=0, err_msg=f"{op} of column {col}")
+    # a chunk in the middle of the band with too many groups poisons the whole launch (-1), nothing else
+    ck[1] = [rng.integers(0, 900, sizes[1], dtype=np.int64)]
+    n, _, _ = _batch(K, ck, cv, accs)
+    assert n == -1
+
+
+@pytest.mark.parametrize("sort", [False, True])
+def test_merge_small_post_is_the_whole_agg_stage(K, sort):
+    """merge of partial pieces (sizes on the device) + identity / mean / var post functions in one launch"""
+    rng = np.random.default_rng(17)
+    frames, pieces, keep = [], [], []
+    for n in [40, 0, 700, 3]:
+        k = rng.integers(-30, 30, n, dtype=np.int64)
+        s = rng.normal(50, 5, n)
+        q = s * s + rng.random(n)
+        c = rng.integers(1, 9, n, dtype=np.int64)
+        si = rng.integers(-50, 50, n, dtype=np.int64)
+        frames.append(pd.DataFrame(dict(k=k, s=s, q=q, c=c, si=si)))
+        cols = [dev(k), dev(s), dev(q), dev(c), dev(si)]
+        cnt = dev(np.array([n], dtype=np.int64))
+        keep.append((cols, cnt))
+        pieces.append(([cols[0].data_ptr()], [t.data_ptr() for t in cols[1:]], None, cnt.data_ptr(),
+                       [K.F64, K.F64, K.I64, K.I64], torch.device("cuda", 0)))
+    steps = [(K.POST_IDENTITY, 0, 0, 0, 0), (K.POST_MEAN, 0, 2, 0, 0), (K.POST_VAR, 0, 1, 2, 1), (K.POST_VAR, 0, 1, 2, 0),
+             (K.POST_IDENTITY, 2, 0, 0, 0), (K.POST_MEAN, 3, 2, 0, 0)]
+    post = K.PostPlan(steps, [True, True, True, True, False, True])
+    blk, nk, npost = K.merge_small_post_async(pieces, [K.SUM, K.SUM, K.SUM, K.SUM], post, sort=sort)
+    n, keys, cols = K.result_block_to_host(blk, nk, npost, post.is_float)
+    m = pd.concat(frames).groupby("k", sort=True).sum()
+    assert n == len(m)
+    order = np.argsort(keys[0], kind="stable")
+    if sort:
+        np.testing.assert_array_equal(order, np.arange(n))
+    np.testing.assert_array_equal(keys[0][order], m.index.to_numpy())
+    S, Q, Cn, SI = m["s"], m["q"], m["c"], m["si"]
+    np.testing.assert_allclose(cols[0][order], S.to_numpy(), rtol=1e-12)
+    np.testing.assert_allclose(cols[1][order], (S / Cn).to_numpy(), rtol=1e-12)
+    with np.errstate(all="ignore"):
+        np.testing.assert_allclose(cols[2][order], orc.post_var(Q, S, Cn, ddof=1).to_numpy(), rtol=1e-9, equal_nan=True)
+        np.testing.assert_allclose(cols[3][order], orc.post_var(Q, S, Cn, ddof=0).to_numpy(), rtol=1e-9, equal_nan=True)
+    np.testing.assert_array_equal(cols[4][order], Cn.to_numpy())
+    np.testing.assert_allclose(cols[5][order], (SI / Cn).to_numpy(), rtol=1e-15)
+    # a piece whose device count says "failed" (-1) poisons the result; too many rows are declined on the host
+    bad = dev(np.array([-1], dtype=np.int64))
+    pieces[0] = pieces[0][:3] + (bad.data_ptr(),) + pieces[0][4:]
+    blk, nk, npost = K.merge_small_post_async(pieces, [K.SUM] * 4, post, sort=sort)
+    assert K.result_block_to_host(blk, nk, npost, post.is_float)[0] == -1
+    big = (pieces[1][0], pieces[1][1], 5000, 0) + pieces[1][4:]
+    assert K.merge_small_post_async([big], [K.SUM] * 4, post) is None

@@ -194,22 +194,21 @@ def test_large_result_chunks_stay_on_the_device_until_fetch(md, nkeys, sort):
     assert_frames_match(one.to_pandas().sort_index(), exp.loc[one.to_pandas().sort_index().index], sort_index=False)
 
 
-@pytest.mark.parametrize("cfg,scale", [("cfg3", 0.02), ("cfg4", 0.04), ("cfg5", 0.02), ("cfg1-shuffle", 1.0)])
-def test_baseline_configs_through_the_operand_api(md, cfg, scale, capsys):
-    """BASELINE.json configs (scaled down) through tile -> executors -> fetch with device-generated inputs:
-    size-independent properties (sum of counts == rows, keys unique, groups == distinct keys, sum of sums ==
-    column total at 1e-9, min <= max and global extrema); the high-cardinality ones take the bucketed
-    aggregation on both sides of the shuffle.  tools/run_configs.py runs the same at full size."""
+@pytest.mark.parametrize("cfg,rows,chunk", [("cfg3", 4_000_000, 500_000), ("cfg5", 4_000_000, 500_000)])
+def test_config_runner_record(md, cfg, rows, chunk, capsys):
+    """the record bench.py attaches per BASELINE.json config: value, roofline fraction, oracle parity on sampled
+    groups + invariants (full-frame parity per config: tests/test_baseline_configs.py)"""
     import os
     import sys
 
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
-    import run_configs
+    import config_runner
 
-    rec = run_configs.run(cfg, scale, 1)
+    rec = config_runner.run_record(cfg, rows, chunk, repeats=1, n_sample=512)
     capsys.readouterr()
-    assert rec["all_checks_pass"], rec["checks"]
+    assert rec["parity"]["ok"], rec["parity"]
     assert "DataFrameGroupByOperand:map" in rec["plan"] and "DataFrameGroupByOperand:reduce" in rec["plan"]
+    assert 0 < rec["roofline"]["frac"] < 1 and rec["value"] > 0
 
 
 def test_unsupported_function_raises(md):
@@ -286,3 +285,36 @@ def test_pending_partials_feed_the_shuffle_branch(md):
     got, sess, r = run(md, raw, "pk", ["sum", "count"], 5_000, "shuffle", False)
     exp = raw.groupby("pk").agg(["sum", "count"])
     assert_frames_match(got, exp, sort_index=True)
+
+
+@pytest.mark.parametrize("method", ["tree", "auto"])
+@pytest.mark.parametrize("func", [["sum", "mean", "count"], ["min", "max", "var"],
+                                  {"v0": ["sum", "mean"], "v1": ["count"], "v2": ["var", "max"]}])
+def test_tree_branch_runs_as_one_batch_launch(md, method, func):
+    """band-level batch: the map operands + concat / combine tree of the tree branch are ONE launch of the dense
+    kernel over all chunks (ragged last chunk), the agg stage ONE launch; same frame as the oracle and as the
+    per-operand execution of a real Mars worker (fuse off)"""
+    from mars_b200 import executors, kernels
+
+    rng = np.random.default_rng(31)
+    n = 1_000_003
+    raw = pd.DataFrame({"fk1": rng.integers(0, 3, n), "fk2": rng.integers(0, 2, n), "v0": rng.normal(10, 3, n),
+                        "v1": rng.integers(0, 9, n), "v2": rng.random(n)})
+    executors._dense_rejected.clear()
+    mdf = md.DataFrame(raw, chunk_size=90_000).to_gpu()
+    exp = orc.run_groupby_agg(raw, ["fk1", "fk2"], func, 90_000, method="tree", sort=True)
+    results = {}
+    for fuse in (True, False):
+        sess = md.new_session(default=False)
+        sess.fuse = fuse
+        r = mdf.groupby(["fk1", "fk2"]).agg(func, method=method)
+        before = kernels.launch_counter
+        r.execute(session=sess)
+        got = r.fetch(session=sess)
+        results[fuse] = (got, kernels.launch_counter - before, sess)
+        assert_frames_match(got, exp, sort_index=False)
+    got, launches, sess = results[True]
+    assert sess.fused_trees == 1
+    assert launches == (2 if method == "tree" else 4 + 2), launches     # auto: 4 sampled map operands on their own
+    assert results[False][2].fused_trees == 0 and results[False][1] > launches
+    assert sess.executed_ops.count("DataFrameGroupByAgg:map") == 12
