@@ -299,11 +299,19 @@ class DataFrameGroupByAgg(Operand):
             for c in chunks:
                 c.op.size_recorder_name = recorder.name
             yield chunks
+            # sizes of still speculative results are first read as their capacity BOUNDS (known without asking
+            # the device): a plan that is a tree under the bounds is a tree under the exact sizes too.  Only when
+            # the bounds alone would choose the shuffle branch are the exact sizes read (one host wait) -- what
+            # the reference always does (aggregation.py:887-925).
             raw_sizes, agg_sizes = recorder.get()
+            out = cls._build_tree_and_shuffle_chunks(op, in_df, out_df, steps, chunks, agg_sizes)
+            if recorder.bounded and len(out.chunks) > 1:
+                raw_sizes, agg_sizes = recorder.get(exact=True)
+                out = cls._build_tree_and_shuffle_chunks(op, in_df, out_df, steps, chunks, agg_sizes)
             SizeRecorder.destroy(recorder.name)
             for c in chunks:
                 c.op.size_recorder_name = None
-            return cls._build_tree_and_shuffle_chunks(op, in_df, out_df, steps, chunks, agg_sizes)
+            return out
         if op.method == "shuffle":
             return cls._tile_with_shuffle(op, in_df, out_df, steps)
         if op.method == "tree":
@@ -317,16 +325,24 @@ class SizeRecorder:
 
     def __init__(self):
         self.name = new_key("sizerec")
-        self._raw, self._agg = [], []
+        self._raw, self._agg, self._bound = [], [], []
+        self.bounded = False
         SizeRecorder._registry[self.name] = self
 
-    def record(self, raw_size: int, agg_size: int):
+    def record(self, raw_size: int, agg_size, bound=None):
+        """agg_size: the exact size or a zero-argument callable giving it (may wait for the device); bound: an
+        upper bound known on the host (capacity of a speculative result), or None"""
         self._raw.append(raw_size)
         self._agg.append(agg_size)
+        self._bound.append(bound)
+        if bound is not None:
+            self.bounded = True
 
-    def get(self):
-        self._agg = [a() if callable(a) else a for a in self._agg]
-        return self._raw, self._agg
+    def get(self, exact: bool = False):
+        if exact or not self.bounded:
+            self._agg = [a() if callable(a) else a for a in self._agg]
+            return self._raw, self._agg
+        return self._raw, [b if b is not None else (a() if callable(a) else a) for a, b in zip(self._agg, self._bound)]
 
     @classmethod
     def lookup(cls, name):

@@ -25,6 +25,7 @@ import numpy as np
 import pandas as pd
 import torch
 
+from . import _lib as _lib_mod
 from . import kernels as K
 from ._lib import MarsGBError
 from .device import ColumnSet, DeviceFrame, Pending, PiecewiseFrame
@@ -45,9 +46,7 @@ _LAZY_H2D = os.environ.get("MGB_EAGER_H2D", "0") in ("", "0")
 
 def _kernels_limits():
     """(max keys, max value columns, max accumulators) of the C ABI (include/mgb.h)"""
-    from . import _lib
-
-    return _lib.MGB_MAX_KEYS, _lib.MGB_MAX_VALS, _lib.MGB_MAX_ACCS
+    return _lib_mod.MGB_MAX_KEYS, _lib_mod.MGB_MAX_VALS, _lib_mod.MGB_MAX_ACCS
 
 
 def _check_key_count(n: int):
@@ -359,22 +358,35 @@ def _execute_agg_map(ctx, op):
         if n_out <= 32:
             _dense_rejected.discard(plan.shape_key)      # the data changed: the one-launch path fits again
         frames = [DeviceFrame(plan.by, out_keys, cols, out_accs[a0:a1], n_out) for cols, a0, a1 in plan.slots]
-    if rec is not None:   # method='auto' samples real sizes: resolves the count when the recorder is read
+    if rec is not None:   # method='auto' samples sizes: exact ones resolve the count (a host wait), the capacity bound does not
+        pend0 = frames[0]._pending
+        bound = None
+        if pend0 is not None and pend0.value is None:
+            bound = sum(pend0.cap * 8 * (len(f.columns) + len(plan.by)) for f in frames)
         _record_sizes(ctx, rec, frame.nbytes,
-                      lambda: sum(len(f) * 8 * (len(f.columns) + len(plan.by)) for f in frames))
+                      lambda: sum(len(f) * 8 * (len(f.columns) + len(plan.by)) for f in frames), bound)
     ctx[op.outputs[0].key] = tuple(frames)
 
 
-def _record_sizes(ctx, name, raw_size, agg_size):
-    """agg_size may be a zero-argument callable: the mirror's recorder evaluates it when the tiler reads the
-    sizes (all sampled chunks are enqueued by then: one wait instead of one per chunk); a real Mars recorder
-    is a remote object and gets the number right away (aggregation.py:1120-1126)"""
+_size_recorder_cls = None
+
+
+def _record_sizes(ctx, name, raw_size, agg_size, bound=None):
+    """agg_size may be a zero-argument callable.  A real Mars recorder is a remote object and gets the exact
+    number right away (aggregation.py:1120-1126).  The mirror's recorder evaluates it when the tiler reads the
+    sizes; when ``bound`` is given -- the capacity of a still speculative result, known without asking the
+    device -- the tiler first decides on the bounds and reads the exact sizes (one host wait) only if the bounds
+    alone would send the plan to the shuffle branch (dataframe.DataFrameGroupByAgg.tile)."""
+    global _size_recorder_cls
     getter = getattr(ctx, "get_remote_object", None)
     if getter is not None:
         getter(name).record(raw_size, agg_size() if callable(agg_size) else agg_size)
         return
-    from .dataframe import SizeRecorder
-    SizeRecorder.lookup(name).record(raw_size, agg_size)
+    if _size_recorder_cls is None:
+        from .dataframe import SizeRecorder
+
+        _size_recorder_cls = SizeRecorder
+    _size_recorder_cls.lookup(name).record(raw_size, agg_size, bound)
 
 
 def _merge_partials(slots: Sequence[Sequence[DeviceFrame]], steps: Sequence[_Step], sort: bool) -> List[DeviceFrame]:
@@ -877,40 +889,56 @@ def find_fused_trees(order, keep) -> List[FusedTree]:
     return out
 
 
-def execute_fused_tree(ctx, ft: FusedTree) -> bool:
-    """Runs the fused part of the graph: ONE launch of the band-level batch kernel over the input chunks of all
-    leaf map operands (per mgb_dense_batch_max() chunks) instead of n map launches and the merges of the
-    combine tree; ``ctx[ft.root.key]`` receives the partial tuple the stage=agg operand expects (a virtual
-    concat of the batch results and the opaque partial tuples).  Returns False -- nothing done -- when the
-    shape is not a low-cardinality one or the chunks differ in schema: the caller then runs the operands one
-    by one."""
-    fn = getattr(_kernels, "preagg_dense_batch_async", None)
-    if fn is None or not _ASYNC:
-        return False
-    frames = []
-    for leaf in ft.leaves:
-        v = ctx[leaf.op.inputs[0].key]
-        if not isinstance(v, DeviceFrame) or v.index is not None:
-            return False
-        frames.append(v)
-    op0 = ft.leaves[0].op
-    for leaf in ft.leaves[1:]:
-        if leaf.op.agg_funcs is not op0.agg_funcs and leaf.op.agg_funcs != op0.agg_funcs:
-            return False
-    try:
-        plan = _map_plan(op0, frames[0])
-    except NotImplementedError:
-        return False
-    if plan.shape_key in _dense_rejected:
-        return False
-    sig = plan.for_dtypes(frames[0])
+class EagerBatch:
+    """A band-level batch that was launched BEFORE the chunk graph was tiled (session.Session._execute): the
+    map stage of every input chunk is needed under any plan, so its launch does not have to wait for the host
+    to tile and walk the graph -- the GPU streams the band while the host builds the plan.  ``pieces`` is the
+    partial tuple of the whole band (one piece per slot), ``covered`` maps the key of every input chunk that
+    went into the launch to its frame."""
+    __slots__ = ("plan", "op", "pieces", "covered", "used", "bound")
+
+    def __init__(self, plan, op, pieces, covered, bound):
+        self.plan, self.op, self.pieces, self.covered, self.bound = plan, op, pieces, covered, bound
+        self.used = False
+
+
+class EagerRef:
+    """What ``ctx`` holds for a stage=map chunk whose input is covered by an eager batch: the chunk's own
+    partial tuple does not exist (the band was aggregated as a whole).  A consumer that is not the fused tree
+    (e.g. the shuffle branch) gets the real per-chunk result through ``materialize``."""
+    __slots__ = ("eager", "op", "in_key")
+
+    def __init__(self, eager, op, in_key):
+        self.eager, self.op, self.in_key = eager, op, in_key
+
+    def materialize(self):
+        tmp = _MiniCtx({self.in_key: self.eager.covered[self.in_key]})
+        saved, self.op.size_recorder_name = getattr(self.op, "size_recorder_name", None), None
+        try:
+            _execute_agg_map(tmp, self.op)
+        finally:
+            self.op.size_recorder_name = saved
+        return tmp[self.op.outputs[0].key]
+
+
+def exact_partial_size(ctx, key, ref) -> int:
+    """exact size of a skipped map chunk's partial tuple (only asked for when the capacity bounds alone would
+    send the plan to the shuffle branch): the chunk is aggregated for real"""
+    v = ctx.get(key)
+    if isinstance(v, EagerRef):
+        v = ctx[key] = v.materialize()
+    return sum(len(f) * 8 * (len(f.columns) + len(f.index_names)) for f in v)
+
+
+class _MiniCtx(dict):
+    def get_current_chunk(self):
+        return None
+
+
+def _launch_band(plan, sig, frames):
+    """one batch launch per mgb_dense_batch_max() chunks -> per slot the list of pieces, or None"""
+    fn = _kernels.preagg_dense_batch_async
     keys_ok, count_only, dts = sig
-    if not keys_ok:
-        return False
-    cols0 = frames[0].columns
-    for f in frames[1:]:
-        if (f.columns is not cols0 and f.columns != cols0) or plan.for_dtypes(f) is not sig:
-            return False
     chunks = []
     for f in frames:
         kp = [f.col(i).data_ptr() for i in plan.key_pos]
@@ -925,7 +953,7 @@ def execute_fused_tree(ctx, ft: FusedTree) -> bool:
         if res is None:
             _dense_rejected.add(plan.shape_key)
             if g0 == 0:
-                return False
+                return None
             raise MarsGBError(6, "dense batch shape rejected after the first batch was launched")
         bi, bf, fc = res
         group = frames[g0:g0 + B]
@@ -948,8 +976,84 @@ def execute_fused_tree(ctx, ft: FusedTree) -> bool:
         for s_, (cols, a0, a1) in enumerate(plan.slots):
             per_slot[s_].append(DeviceFrame.from_range(plan.by, cols, src, 0, nk, nk + a0, nk + a1, 0, cap,
                                                        pending=pend, slot=(a0, a1)))
+    return per_slot
+
+
+def _band_frames_plan(op0, frames):
+    """(plan, dtype signature) when all frames of a band share one low-cardinality-capable schema, else None"""
+    for v in frames:
+        if not isinstance(v, DeviceFrame) or v.index is not None:
+            return None
+    try:
+        plan = _map_plan(op0, frames[0])
+    except NotImplementedError:
+        return None
+    if plan.shape_key in _dense_rejected:
+        return None
+    sig = plan.for_dtypes(frames[0])
+    if not sig[0]:
+        return None
+    cols0 = frames[0].columns
+    for f in frames[1:]:
+        if (f.columns is not cols0 and f.columns != cols0) or plan.for_dtypes(f) is not sig:
+            return None
+    return plan, sig
+
+
+def launch_eager_band(map_op, in_keys, frames) -> Optional[EagerBatch]:
+    """Launch the band-level batch over the input chunks of a groupby-agg before its graph exists.  ``map_op``
+    is a stage=map operand as the tiler will create it (same compiled functions)."""
+    if not (_ASYNC and hasattr(_kernels, "preagg_dense_batch_async")) or len(frames) < 2:
+        return None
+    ps = _band_frames_plan(map_op, frames)
+    if ps is None:
+        return None
+    plan, sig = ps
+    per_slot = _launch_band(plan, sig, frames)
+    if per_slot is None:
+        return None
+    cap = per_slot[0][0]._pending.cap
+    bound = sum(cap * 8 * (len(cols) + len(plan.by)) for cols, _, _ in plan.slots)
+    return EagerBatch(plan, map_op, per_slot, dict(zip(in_keys, frames)), bound)
+
+
+def execute_fused_tree(ctx, ft: FusedTree, eager: Optional[EagerBatch] = None) -> bool:
+    """Runs the fused part of the graph: ONE launch of the band-level batch kernel over the input chunks of all
+    leaf map operands (per mgb_dense_batch_max() chunks) instead of n map launches and the merges of the
+    combine tree; ``ctx[ft.root.key]`` receives the partial tuple the stage=agg operand expects (a virtual
+    concat of the batch results and the opaque partial tuples).  Returns False -- nothing done -- when the
+    shape is not a low-cardinality one or the chunks differ in schema: the caller then runs the operands one
+    by one."""
+    fn = getattr(_kernels, "preagg_dense_batch_async", None)
+    if fn is None or not _ASYNC:
+        return False
+    op0 = ft.leaves[0].op
+    for leaf in ft.leaves[1:]:
+        if leaf.op.agg_funcs is not op0.agg_funcs and leaf.op.agg_funcs != op0.agg_funcs:
+            return False
+    if eager is not None and not eager.used:
+        # the band was launched before tiling: the tree is served by that launch when its leaves plus the map
+        # chunks that were skipped earlier (EagerRef) are exactly the chunks the launch covered
+        refs = [ctx[c.key] for c in ft.opaque]
+        if all(isinstance(v, EagerRef) and v.eager is eager for v in refs):
+            keys = {leaf.op.inputs[0].key for leaf in ft.leaves} | {v.in_key for v in refs}
+            if keys == set(eager.covered) and len(keys) == len(ft.leaves) + len(refs):
+                eager.used = True
+                ctx[ft.root.key] = tuple(PiecewiseFrame(p) for p in eager.pieces)
+                return True
+    frames = [ctx[leaf.op.inputs[0].key] for leaf in ft.leaves]
+    ps = _band_frames_plan(op0, frames)
+    if ps is None:
+        return False
+    plan, sig = ps
+    per_slot = _launch_band(plan, sig, frames)
+    if per_slot is None:
+        return False
     for c in ft.opaque:
-        for s_, pcs in enumerate(_pieces_of(ctx[c.key])):
+        v = ctx[c.key]
+        if isinstance(v, EagerRef):
+            v = ctx[c.key] = v.materialize()
+        for s_, pcs in enumerate(_pieces_of(v)):
             per_slot[s_].extend(pcs)
     ctx[ft.root.key] = tuple(PiecewiseFrame(p) for p in per_slot)
     return True

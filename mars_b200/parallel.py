@@ -418,7 +418,9 @@ class Exchange:
         names = sorted({c.op.size_recorder_name for c in chunks if getattr(c.op, "size_recorder_name", None)})
         for name in names:
             rec = SizeRecorder.lookup(name)
-            rec.get()   # evaluates deferred sizes
+            rec.get(exact=True)   # evaluates deferred sizes (every rank needs real numbers to agree on the plan)
+            rec._bound = [None] * len(rec._agg)
+            rec.bounded = False
             metas = self._gather_meta((list(rec._raw), list(rec._agg)))
             rec._raw = [x for m in metas for x in m[0]]
             rec._agg = [x for m in metas for x in m[1]]

@@ -15,25 +15,27 @@ reproduces the parts of that machinery the hot path depends on:
 from __future__ import annotations
 
 import collections
+import gc
 import os
 from typing import Dict, List, Optional
 
 import pandas as pd
 
 from . import core
+from . import executors as _ex
 from .core import ChunkData, ProcessorContext, build_chunk_graph
-from .dataframe import DataFrame, DataFrameShuffleProxy
+from .dataframe import DataFrame, DataFrameGroupByAgg, DataFrameShuffleProxy
 
 
 _op_names: Dict[object, str] = {}
+_map_name = "DataFrameGroupByAgg:map"
+_gc_frozen = False
 
 
 class Session:
     def __init__(self, exchange=None):
         """exchange: a ``mars_b200.parallel.Exchange`` for multi-GPU runs (None: single GPU)."""
-        from .executors import register_gpu_executors
-
-        register_gpu_executors()
+        _ex.register_gpu_executors()
         self.exchange = exchange
         self.rank = exchange.rank if exchange is not None else 0
         self.world = exchange.world if exchange is not None else 1
@@ -42,6 +44,7 @@ class Session:
         # band-level fusion of the tree branch (MGB_FUSE=0: per-operand execution, what a real Mars worker does)
         self.fuse = os.environ.get("MGB_FUSE", "1") not in ("0", "")
         self.fused_trees = 0
+        self._eager = None                     # executors.EagerBatch of the graph that is being executed
 
     # ---------------------------------------------------------------------------------- placement
     def _owner(self, chunk: ChunkData, owners: Dict[str, int]) -> int:
@@ -76,10 +79,9 @@ class Session:
         log = self.executed_ops
         execute = core.execute
         fused_at, skip = {}, set()
+        eager = self._eager
         if self.fuse and len(order) > 3:
-            from . import executors
-
-            for ft in executors.find_fused_trees(order, keep):
+            for ft in _ex.find_fused_trees(order, keep):
                 fused_at[ft.root.key] = ft
                 skip.update(c.key for c in ft.nodes)
 
@@ -93,6 +95,25 @@ class Session:
 
         def run_one(c):
             op = c.op
+            if eager is not None:
+                if (type(op) is DataFrameGroupByAgg and op.stage is core.OperandStage.map and len(op.inputs) == 1
+                        and op.inputs[0].key in eager.covered and not eager.used):
+                    # the band was aggregated as a whole by the launch that preceded tiling: this chunk has no
+                    # partial tuple of its own; its sampled size is the capacity bound of the speculative result
+                    ctx[c.key] = _ex.EagerRef(eager, op, op.inputs[0].key)
+                    rec = getattr(op, "size_recorder_name", None)
+                    if rec is not None:
+                        ref = ctx[c.key]
+                        frame = eager.covered[op.inputs[0].key]
+                        _ex._record_sizes(ctx, rec, frame.nbytes,
+                                          lambda ref=ref, key=c.key: _ex.exact_partial_size(ctx, key, ref), eager.bound)
+                    log.append(_map_name)
+                    release(op)
+                    return
+                for inp in op.inputs:       # a consumer outside the fused tree needs the chunk's real partials
+                    v = ctx.get(inp.key)
+                    if isinstance(v, _ex.EagerRef):
+                        ctx[inp.key] = v.materialize()
             if not isinstance(op, DataFrameShuffleProxy):
                 ctx._current_chunk = c
                 try:
@@ -113,10 +134,8 @@ class Session:
             owners[c.key] = 0
             ft = fused_at.get(c.key) if fused_at else None
             if ft is not None:
-                from . import executors
-
                 try:
-                    done = executors.execute_fused_tree(ctx, ft)
+                    done = _ex.execute_fused_tree(ctx, ft, eager)
                 except Exception as e:
                     raise core.ExecutionError(e) from e
                 if done:
@@ -180,22 +199,60 @@ class Session:
     def execute(self, df: DataFrame, **kw):
         # The chunk graph of a large shuffle keeps ~1e5 small containers alive (frames, column lists, tensor
         # views); none of them forms a reference cycle (device.Pending holds weak references), but every few
-        # hundred allocations the cyclic collector walks all of them.  It is paused while the graph runs.
-        import gc
-
+        # hundred allocations the cyclic collector walks all of them.  It is paused while the graph runs; and the
+        # objects that exist when the first graph runs (the imported libraries) are moved to the permanent
+        # generation once, so that the collection which follows a run only looks at what the run left behind.
+        global _gc_frozen
+        if not _gc_frozen and os.environ.get("MGB_GC_FREEZE", "1") not in ("0", ""):
+            gc.collect()
+            gc.freeze()
+            _gc_frozen = True
         was_enabled = gc.isenabled()
         gc.disable()
         try:
             return self._execute(df, **kw)
         finally:
+            self._eager = None
             if was_enabled:
                 gc.enable()
+
+    def _launch_eager(self, t, ctx, owners):
+        """Before the graph of a groupby-agg over resident row chunks is tiled, enqueue the band-level batch over
+        all its input chunks: the map stage of every chunk is needed under any plan (tree or shuffle,
+        aggregation.py:473-523), so the GPU can stream the band while the host tiles and walks the graph.  The
+        tree branch is then served by this launch (executors.execute_fused_tree); any other consumer gets the
+        per-chunk partials on demand (executors.EagerRef)."""
+        op = t.op
+        if type(op) is not DataFrameGroupByAgg or op.method not in ("auto", "tree") or not op.inputs:
+            return None
+        src = op.inputs[0]
+        chunks = getattr(src, "chunks", None)
+        if not chunks or len(chunks) < 2 or len(chunks) > 4096:
+            return None
+        by = op.groupby_params.get("by")
+        if not isinstance(by, (list, tuple)):
+            return None
+        steps = type(op)._compile_funcs(op)
+        map_op = op.copy().reset_key()
+        map_op.groupby_params = dict(op.groupby_params, as_index=True)
+        map_op.stage = core.OperandStage.map
+        map_op.pre_funcs, map_op.agg_funcs = steps.pre_funcs, steps.agg_funcs
+        map_op.new_chunk([chunks[0]], index=(0, 0))
+        self._run_chunks_local(list(chunks), ctx, owners)       # data sources (and H2D operands) of the band
+        frames = [ctx[c.key] for c in chunks]
+        return _ex.launch_eager_band(map_op, [c.key for c in chunks], frames)
 
     def _execute(self, df: DataFrame, **kw):
         t = df.data
         ctx = ProcessorContext()
         owners: Dict[str, int] = {}
+        self._eager = None
         if t.chunks is None:
+            if self.fuse and self.world == 1:
+                try:
+                    self._eager = self._launch_eager(t, ctx, owners)
+                except NotImplementedError:
+                    self._eager = None
             gen = type(t.op).tile(t.op)
             try:
                 to_run = next(gen)
@@ -242,8 +299,14 @@ class Session:
         rank = dist.get_rank(group)
         saved_rank, saved_world = self.rank, self.world
         self.rank, self.world = 0, 1                      # the local graph runs entirely on this rank
+        self._eager = None
         try:
             if t.chunks is None:
+                if self.fuse:
+                    try:
+                        self._eager = self._launch_eager(t, ctx, owners)
+                    except NotImplementedError:
+                        self._eager = None
                 gen = type(t.op).tile(t.op)
                 try:
                     to_run = next(gen)
@@ -260,6 +323,7 @@ class Session:
             self._run_chunks([feed], ctx, owners)
         finally:
             self.rank, self.world = saved_rank, saved_world
+            self._eager = None
         steps = _plan_steps(agg_chunk.op, None)
         slots = _pieces_of(ctx[feed.key])
         # Every rank ships its local result as the block pair of a speculative result (int64 block with the row

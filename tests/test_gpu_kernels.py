@@ -599,7 +599,9 @@ def test_merge_small_post_is_the_whole_agg_stage(K, sort):
         c = rng.integers(1, 9, n, dtype=np.int64)
         si = rng.integers(-50, 50, n, dtype=np.int64)
         frames.append(pd.DataFrame(dict(k=k, s=s, q=q, c=c, si=si)))
-        cols = [dev(k), dev(s), dev(q), dev(c), dev(si)]
+        # capacity-length columns, like the blocks of the speculative chain: the row count lives on the device
+        pad = lambda a: dev(np.concatenate([a, np.zeros(8, dtype=a.dtype)]))   # noqa: E731
+        cols = [pad(k), pad(s), pad(q), pad(c), pad(si)]
         cnt = dev(np.array([n], dtype=np.int64))
         keep.append((cols, cnt))
         pieces.append(([cols[0].data_ptr()], [t.data_ptr() for t in cols[1:]], None, cnt.data_ptr(),

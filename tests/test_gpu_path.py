@@ -315,6 +315,6 @@ def test_tree_branch_runs_as_one_batch_launch(md, method, func):
         assert_frames_match(got, exp, sort_index=False)
     got, launches, sess = results[True]
     assert sess.fused_trees == 1
-    assert launches == (2 if method == "tree" else 4 + 2), launches     # auto: 4 sampled map operands on their own
+    assert launches == 2, launches     # one band-level batch (launched before tiling) + one agg-stage launch
     assert results[False][2].fused_trees == 0 and results[False][1] > launches
     assert sess.executed_ops.count("DataFrameGroupByAgg:map") == 12

@@ -291,9 +291,35 @@ def test_fused_tree_under_method_auto_merges_the_sampled_partials(md):
     fake_kernels.calls.clear()
     got, sess = _run_tree(md, raw, "akey", ["sum", "mean", "count"], 500, method="auto")
     assert sess.fused_trees == 1
-    assert fake_kernels.calls.count("preagg_dense_async") == 4 and fake_kernels.calls.count("preagg_dense_batch_async") == 1
+    # the band is launched once, BEFORE tiling (session._launch_eager): the sampled map operands are not run on
+    # their own, their sizes are recorded as the capacity bound of the speculative result (no host wait)
+    assert fake_kernels.calls.count("preagg_dense_batch_async") == 1 and "preagg_dense_async" not in fake_kernels.calls
+    assert sess.executed_ops.count("DataFrameGroupByAgg:map") == 12
     exp = orc.run_groupby_agg(raw, "akey", ["sum", "mean", "count"], 500, method="tree", sort=True)
     assert_frames_match(got, exp, sort_index=False)
+    # without the band-level batch: 4 sampled + 8 further map operands, each on its own
+    fake_kernels.calls.clear()
+    got2, sess2 = _run_tree(md, raw, "akey", ["sum", "mean", "count"], 500, method="auto", fuse=False)
+    assert fake_kernels.calls.count("preagg_dense_async") == 12 and "preagg_dense_batch_async" not in fake_kernels.calls
+    assert_frames_match(got2, exp, sort_index=False)
+
+
+def test_eager_band_gives_way_when_auto_chooses_the_shuffle_branch(md, monkeypatch):
+    """the band is launched before tiling; when the sampled sizes send method='auto' to the shuffle branch (here:
+    a tiny chunk_store_limit), the skipped map chunks are aggregated for real (EagerRef.materialize) and the
+    graph runs operand by operand"""
+    rng = np.random.default_rng(6)
+    n = 6000
+    raw = pd.DataFrame({"bkey": rng.integers(0, 5, n), "bv0": rng.random(n)})
+    monkeypatch.setattr(md.options, "chunk_store_limit", 64)
+    fake_kernels.calls.clear()
+    sess = md.new_session(default=False)
+    r = md.DataFrame(raw, chunk_size=500).to_gpu().groupby("bkey", sort=False).agg(["sum", "count"], method="auto")
+    r.execute(session=sess)
+    got = r.fetch(session=sess)
+    assert len(r.data.chunks) > 1 and "DataFrameGroupByOperand:map" in sess.executed_ops
+    assert sess.fused_trees == 0
+    assert_frames_match(got, raw.groupby("bkey").agg(["sum", "count"]), sort_index=True)
 
 
 def test_fused_tree_replays_when_the_band_is_not_low_cardinality(md):
