@@ -124,6 +124,12 @@ int mgb_agg_destroy(mgb_agg* agg);
  * produced the result, no table was built), [5]=kernels launched by this aggregator so far.               */
 int mgb_agg_stats(mgb_agg* agg, int64_t* stats6);
 
+/* Cardinality probe for the choice between the two map-side paths above: hashes a strided sample (at most
+ * 16384 rows) of the batch's key tuples into an on-chip bitmap and reports how many rows were sampled and how
+ * many distinct hashes they had.  One tiny launch + one 16-byte device->host read (synchronises the stream). */
+int mgb_estimate_distinct(const int64_t* const* key_cols, int32_t n_keys, int64_t n_rows, int64_t* out_sampled,
+                          int64_t* out_distinct, void* stream);
+
 
 /* Low-cardinality fast paths (one kernel launch + one 8-byte device->host read each).
  *
@@ -178,6 +184,19 @@ int mgb_preagg_dense_batch_async(const mgb_agg_spec* spec, int32_t n_chunks, con
                                  const int64_t* const* const* chunk_key_cols,
                                  const void* const* const* chunk_val_cols, int64_t* const* out_key_cols,
                                  void* const* out_acc_cols, int64_t out_capacity, int64_t* out_n_dev, void* stream);
+
+/* The same band-level batch for the MID-cardinality sum / mean / count shapes (BASELINE.json config 1: 1000
+ * keys): more distinct key tuples than the dense kernel keeps per CTA, few enough for one shared-memory table
+ * per CTA -- float64 columns with SUM and / or COUNT (int64 columns that are only counted are not read), at
+ * most mgb_mid_capacity() groups in the band, no NaN values.  Anything else reports -1 through out_n_dev
+ * (nothing useful written) and the caller takes mgb_agg_*.  Accumulator records are updated under a per-slot
+ * lock with plain shared-memory loads / stores: one atomic per row instead of one compare-and-swap loop per
+ * (row, column).  Output columns need capacity mgb_mid_capacity() rows; rows come in table order.           */
+int mgb_mid_capacity(int64_t* out_rows);
+int mgb_preagg_mid_batch_async(const mgb_agg_spec* spec, int32_t n_chunks, const int64_t* chunk_rows,
+                               const int64_t* const* const* chunk_key_cols,
+                               const void* const* const* chunk_val_cols, int64_t* const* out_key_cols,
+                               void* const* out_acc_cols, int64_t out_capacity, int64_t* out_n_dev, void* stream);
 
 /* stage=agg in ONE launch (aggregation.py:1166-1267): mgb_merge_small_async followed, inside the same kernel,
  * by the post functions of the reference on the merged rows (reduction/mean.py:26-33, var.py:38-48, same

@@ -75,6 +75,7 @@ SIGNATURES = {
     "mgb_agg_emit": (C.c_int, [_vp, _pp, _pp, _i32]),
     "mgb_agg_destroy": (C.c_int, [_vp]),
     "mgb_agg_stats": (C.c_int, [_vp, C.POINTER(_i64)]),
+    "mgb_estimate_distinct": (C.c_int, [_pp, _i32, _i64, C.POINTER(_i64), C.POINTER(_i64), _vp]),
     "mgb_dense_capacity": (C.c_int, [C.POINTER(_i64)]),
     "mgb_preagg_dense": (C.c_int, [C.POINTER(AggSpec), _pp, _pp, _i64, _pp, _pp, _i64, C.POINTER(_i64), _vp]),
     "mgb_merge_small": (C.c_int, [C.POINTER(AggSpec), _i32, C.POINTER(_i64), C.POINTER(_pp), C.POINTER(_pp), _pp, _pp,
@@ -85,6 +86,9 @@ SIGNATURES = {
     "mgb_dense_batch_max": (C.c_int, [C.POINTER(_i32)]),
     "mgb_preagg_dense_batch_async": (C.c_int, [C.POINTER(AggSpec), _i32, C.POINTER(_i64), C.POINTER(_pp), C.POINTER(_pp),
                                                _pp, _pp, _i64, _vp, _vp]),
+    "mgb_mid_capacity": (C.c_int, [C.POINTER(_i64)]),
+    "mgb_preagg_mid_batch_async": (C.c_int, [C.POINTER(AggSpec), _i32, C.POINTER(_i64), C.POINTER(_pp), C.POINTER(_pp),
+                                             _pp, _pp, _i64, _vp, _vp]),
     "mgb_merge_small_post_async": (C.c_int, [C.POINTER(AggSpec), _i32, C.POINTER(_i64), _pp, C.POINTER(_pp),
                                              C.POINTER(_pp), _pp, _pp, _i64, _i32, C.POINTER(PostStep), _i32, _pp,
                                              _vp, _vp]),

@@ -179,6 +179,13 @@ __device__ __forceinline__ int bk_find_or_insert(uint64_t* tab_keys, int* tab_id
   return g;
 }
 
+// s += v with the rounding error of the addition accumulated in c (Neumaier's variant of Kahan summation)
+__device__ __forceinline__ void bk_comp_add(double& s, double& c, const double v) {
+  const double t = s + v;
+  c += fabs(s) >= fabs(v) ? (s - t) + v : (v - t) + s;
+  s = t;
+}
+
 template <int NK>
 __global__ void __launch_bounds__(BK_THREADS, 5) k_bucket_agg(const BktParams p) {
   __shared__ uint64_t tab_keys[NK * BK_TAB];
@@ -303,7 +310,13 @@ __global__ void __launch_bounds__(BK_THREADS, 5) k_bucket_agg(const BktParams p)
         const uint64_t* col0 = p.rows + nk + c;      // value c of row i at col0[i * W]
         const long long W = p.W;
         const int j0 = pass == 0 ? 0 : lane, jstep = pass == 0 ? 1 : 32;
-        double fs = 0.0, fq = 0.0;
+        // float64 sums are COMPENSATED (Neumaier: running sum + running error term): pandas' group_sum is a
+        // Kahan sum (pandas/_libs/groupby.pyx), so the reference's partial sums are the correctly rounded true
+        // sums except on a set of measure ~1e-15; a plain DADD chain differs from that in the last bit for a few
+        // groups per million, which the sum-of-squares variance formula of the reference (var.py:38-48) turns
+        // into relative errors beyond 1e-9 when a group's variance is tiny.  Squares are rounded before they are
+        // added (no FMA), like `x ** 2` followed by the sum.
+        double fs = 0.0, fq = 0.0, fsc = 0.0, fqc = 0.0;
         unsigned long long is = 0, iq = 0, cn = 0, mn = ~0ULL, mx = 0ULL;
         const bool f64 = dt == MGB_F64;
         for (int j = j0; j < n; j += 4 * jstep) {
@@ -321,8 +334,8 @@ __global__ void __launch_bounds__(BK_THREADS, 5) k_bucket_agg(const BktParams p)
             if (f64) {
               if (mgb_is_nan_bits(x[u])) continue;
               const double v = __longlong_as_double((long long)x[u]);
-              fs += v;
-              fq += v * v;
+              bk_comp_add(fs, fsc, v);
+              bk_comp_add(fq, fqc, __dmul_rn(v, v));
               const uint64_t e = mgb_enc_f64(x[u]);
               mn = e < mn ? e : mn;
               mx = e > mx ? e : mx;
@@ -339,8 +352,12 @@ __global__ void __launch_bounds__(BK_THREADS, 5) k_bucket_agg(const BktParams p)
         if (pass == 1) {
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) {
-            fs += __shfl_down_sync(0xffffffffu, fs, o);
-            fq += __shfl_down_sync(0xffffffffu, fq, o);
+            const double os = __shfl_down_sync(0xffffffffu, fs, o), osc = __shfl_down_sync(0xffffffffu, fsc, o);
+            const double oq = __shfl_down_sync(0xffffffffu, fq, o), oqc = __shfl_down_sync(0xffffffffu, fqc, o);
+            bk_comp_add(fs, fsc, os);
+            fsc += osc;
+            bk_comp_add(fq, fqc, oq);
+            fqc += oqc;
             is += __shfl_down_sync(0xffffffffu, is, o);
             iq += __shfl_down_sync(0xffffffffu, iq, o);
             cn += __shfl_down_sync(0xffffffffu, cn, o);
@@ -351,6 +368,9 @@ __global__ void __launch_bounds__(BK_THREADS, 5) k_bucket_agg(const BktParams p)
           }
           if (lane != 0) continue;
         }
+        // fold the error terms in (a NaN error term -- inf - inf on the way -- is dropped, as pandas does)
+        if (fsc == fsc) fs += fsc;
+        if (fqc == fqc) fq += fqc;
 #pragma unroll
         for (int q = 0; q < BK_MAXA; ++q) {
           if (q < na_c) {

@@ -299,6 +299,78 @@ extern "C" int mgb_partition_ids(const int64_t* const* key_cols, int32_t n_keys,
 }
 
 // ----------------------------------------------------------------------------------------------------
+// a4: cardinality probe.  Which map-side path pays -- on-chip pre-aggregation (few groups per chunk) or the
+// bucketed aggregation (nearly distinct keys) -- depends on the data; the reference has no such choice (pandas
+// factorizes either way, aggregation.py:951-984).  A strided sample of the chunk's key tuples is hashed into a
+// shared-memory bitmap; the number of distinct hashes tells the two regimes apart for the cost of one tiny
+// launch and a 16-byte read.
+// ----------------------------------------------------------------------------------------------------
+#define EST_THREADS 1024
+#define EST_SAMPLE 16384
+#define EST_BITS (1 << 18)
+
+template <int NK>
+__global__ void __launch_bounds__(EST_THREADS) k_estimate_distinct(KeyCols kc, int64_t n, int64_t* out2) {
+  __shared__ uint32_t bm[EST_BITS / 32];
+  __shared__ int total;
+  for (int i = threadIdx.x; i < EST_BITS / 32; i += EST_THREADS) bm[i] = 0;
+  if (threadIdx.x == 0) total = 0;
+  __syncthreads();
+  const int64_t S = n < EST_SAMPLE ? n : EST_SAMPLE;
+  const int64_t stride = n / S;
+  int fresh = 0;
+  for (int64_t i = threadIdx.x; i < S; i += EST_THREADS) {
+    int64_t k[NK];
+#pragma unroll
+    for (int j = 0; j < NK; ++j) k[j] = kc.k[j][i * stride];
+    const uint64_t h = mgb_slot_hash(mgb_hash_tuple<NK>(k));
+    const uint32_t bit = (uint32_t)(h >> (64 - 18));
+    const uint32_t m = 1u << (bit & 31);
+    const uint32_t old = atomicOr(&bm[bit >> 5], m);
+    fresh += (old & m) ? 0 : 1;
+  }
+  for (int o = 16; o > 0; o >>= 1) fresh += __shfl_xor_sync(0xffffffffu, fresh, o);
+  if ((threadIdx.x & 31) == 0 && fresh) atomicAdd(&total, fresh);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    out2[0] = S;
+    out2[1] = total;
+  }
+}
+
+extern "C" int mgb_estimate_distinct(const int64_t* const* key_cols, int32_t n_keys, int64_t n_rows,
+                                     int64_t* out_sampled, int64_t* out_distinct, void* stream) {
+  MGB_REQUIRE(key_cols && out_sampled && out_distinct, MGB_ERR_INVALID, "null pointer");
+  MGB_REQUIRE(n_keys >= 1 && n_keys <= MGB_MAX_KEYS, MGB_ERR_UNSUPPORTED, "n_keys=%d outside [1,%d]", n_keys,
+              MGB_MAX_KEYS);
+  MGB_REQUIRE(n_rows >= 0, MGB_ERR_INVALID, "negative row count");
+  *out_sampled = 0;
+  *out_distinct = 0;
+  if (n_rows == 0) return MGB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  KeyCols kc;
+  for (int j = 0; j < MGB_MAX_KEYS; ++j) kc.k[j] = j < n_keys ? key_cols[j] : nullptr;
+  int64_t* d = nullptr;
+  MGB_CUDA(cudaMallocAsync((void**)&d, 16, st));
+  if (n_keys == 1)
+    k_estimate_distinct<1><<<1, EST_THREADS, 0, st>>>(kc, n_rows, d);
+  else
+    k_estimate_distinct<2><<<1, EST_THREADS, 0, st>>>(kc, n_rows, d);
+  cudaError_t e = cudaGetLastError();
+  int64_t h[2] = {0, 0};
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h, d, 16, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFreeAsync(d, st);
+  if (e != cudaSuccess) {
+    mgb_set_error("cardinality probe: %s", cudaGetErrorString(e));
+    return MGB_ERR_CUDA;
+  }
+  *out_sampled = h[0];
+  *out_distinct = h[1];
+  return MGB_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------
 // sort=True shuffle: range partition of partial rows by pivots (DataFrameGroupbySortShuffle._execute_map,
 // mars/dataframe/groupby/sort.py:113-135).  Partition i holds the key tuples in (pivot[i-1], pivot[i]], i.e.
 // partition id = number of pivots strictly smaller than the key tuple (pivots ascending, signed int64,

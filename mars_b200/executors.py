@@ -38,6 +38,8 @@ _DECOMP_EXT = dict(_DECOMP, std=_DECOMP["var"])
 # recording double; the product never rebinds it.
 _kernels = K
 _dense_rejected = set()
+_mid_rejected = set()      # shapes the mid-cardinality batch kernel declined (functions, groups, NaNs)
+_probed = set()            # shapes whose first chunk was probed for its cardinality
 _distinct_shapes = set()   # shapes whose chunks spilled most rows: skip the shared-memory pre-aggregation
 # MGB_EAGER=1 disables the speculative asynchronous chain (every operand then waits for its result size)
 _ASYNC = os.environ.get("MGB_EAGER", "0") in ("", "0")
@@ -208,6 +210,7 @@ _map_plans_fast: Dict[Any, Any] = {}
 _DEVICE_RESULTS = os.environ.get("MGB_DEVICE_RESULTS", "1") not in ("0", "")
 _DEVICE_RESULT_ROWS = int(os.environ.get("MGB_DEVICE_RESULT_ROWS", "2049"))   # smaller results go straight to pandas
 _PREAGG_GROUPS = 2048     # chunks with at most this many groups are worth the shared-memory pre-aggregation
+_PROBE_MIN_ROWS = 65536   # smaller chunks are not worth the cardinality probe
 
 
 def _map_plan(op, frame: DeviceFrame) -> _MapPlan:
@@ -295,7 +298,11 @@ def _execute_agg_map(ctx, op):
             if frame.col_dtype(i) != torch.int64:
                 raise NotImplementedError(f"group key {b!r} has dtype {frame.col_dtype(i)}: int64 keys only")
     keys = [frame.col(i) for i in plan.key_pos]
-    dense_ok = plan.shape_key not in _dense_rejected
+    if _ASYNC and hasattr(_kernels, "preagg_dense_batch_async"):
+        which = _band_kernel(plan, (keys_ok, count_only, dts), [frame])
+    else:
+        which = "dense" if plan.shape_key not in _dense_rejected else None
+    dense_ok = which == "dense"
     # the dense kernel does not read int64 columns that are only counted (count == rows of the group): those
     # stay where they are (possibly in host memory) unless the general path turns out to be needed
     skip = count_only if dense_ok and _ASYNC and hasattr(_kernels, "preagg_dense_async") else ()
@@ -340,12 +347,25 @@ def _execute_agg_map(ctx, op):
                 out_keys, out_accs = res
                 n_out = int(out_keys[0].numel())
                 frames = [DeviceFrame(plan.by, out_keys, cols, out_accs[a0:a1], n_out) for cols, a0, a1 in plan.slots]
+    if frames is None and which == "mid":
+        # mid-cardinality sum / mean / count shape: one asynchronous launch of the locked-record kernel
+        per_slot = _launch_band(plan, (keys_ok, count_only, dts), [frame])
+        if per_slot is not None:
+            frames = [p[0] for p in per_slot]
     if frames is None:
         vals = all_vals()
         # Shared-memory pre-aggregation pays while a CTA's table holds (nearly) all groups of the chunk; a
         # shape whose rows mostly spilled is remembered and its next chunks go straight to the bucketed
         # aggregation (distinct-keys hint), until a chunk comes back with few groups again.
-        if plan.shape_key in _distinct_shapes:
+        distinct = plan.shape_key in _distinct_shapes
+        if not distinct and hasattr(_kernels, "estimate_distinct") and len(frame) >= _PROBE_MIN_ROWS:
+            # first chunk of a shape: a strided sample of its keys tells nearly-distinct keys (bucketed aggregation
+            # right away) from the regimes where the on-chip pre-aggregation absorbs most rows
+            sampled, uniq = _kernels.estimate_distinct(keys)
+            if sampled and uniq * 4 >= sampled * 3:
+                _distinct_shapes.add(plan.shape_key)
+                distinct = True
+        if distinct:
             out_keys, out_accs, stats = _kernels.groupby_aggregate(keys, vals, list(plan.accs), sort=False,
                                                                    expect_distinct=True)
             if stats and (int(out_keys[0].numel()) <= _PREAGG_GROUPS or stats.get("bucket_fallback") == 2):
@@ -935,9 +955,46 @@ class _MiniCtx(dict):
         return None
 
 
+def _mid_eligible(plan, sig) -> bool:
+    """sum / mean / count shape: float64 value columns with SUM / COUNT only (int64 columns only counted)"""
+    _, count_only, dts = sig
+    for j, dt in enumerate(dts):
+        if dt != _kernels.F64 and j not in count_only:
+            return False
+    return all(op in (_kernels.SUM, _kernels.COUNT) for _, op in plan.accs)
+
+
+def _band_kernel(plan, sig, frames):
+    """Which band-level batch kernel takes this shape: 'dense' (a handful of groups), 'mid' (up to ~2000 groups,
+    sum / mean / count shapes) or None (general path).  The first chunk of an unknown shape is probed once
+    (a strided key sample, one small host wait); afterwards the choice follows what the kernels reported."""
+    key = plan.shape_key
+    has_mid = hasattr(_kernels, "preagg_mid_batch_async")
+    if key not in _probed and hasattr(_kernels, "estimate_distinct") and key not in _dense_rejected:
+        _probed.add(key)
+        if len(_probed) > 4096:
+            _probed.clear()
+        f0 = frames[0]
+        if len(f0) >= 4096:
+            sampled, uniq = _kernels.estimate_distinct([f0.col(i) for i in plan.key_pos])
+            if uniq > 12:
+                _dense_rejected.add(key)
+            if uniq > 1400:
+                _mid_rejected.add(key)
+    if key not in _dense_rejected:
+        return "dense"
+    if has_mid and key not in _mid_rejected and _mid_eligible(plan, sig):
+        return "mid"
+    return None
+
+
 def _launch_band(plan, sig, frames):
     """one batch launch per mgb_dense_batch_max() chunks -> per slot the list of pieces, or None"""
-    fn = _kernels.preagg_dense_batch_async
+    which = _band_kernel(plan, sig, frames)
+    if which is None:
+        return None
+    fn = _kernels.preagg_dense_batch_async if which == "dense" else _kernels.preagg_mid_batch_async
+    rejected = _dense_rejected if which == "dense" else _mid_rejected
     keys_ok, count_only, dts = sig
     chunks = []
     for f in frames:
@@ -951,16 +1008,17 @@ def _launch_band(plan, sig, frames):
     for g0 in range(0, len(chunks), B):
         res = fn(chunks[g0:g0 + B], plan.accs, dts, nk, dev)
         if res is None:
-            _dense_rejected.add(plan.shape_key)
+            rejected.add(plan.shape_key)
             if g0 == 0:
                 return None
-            raise MarsGBError(6, "dense batch shape rejected after the first batch was launched")
+            raise MarsGBError(6, "batch shape rejected after the first batch was launched")
         bi, bf, fc = res
         group = frames[g0:g0 + B]
 
-        def replay(group=group, plan=plan):
-            """a CTA met more groups than it holds: the band's chunks go through the general aggregator"""
-            _dense_rejected.add(plan.shape_key)
+        def replay(group=group, plan=plan, rejected=rejected):
+            """the kernel reported -1 (more groups than it holds, ...): the band's chunks go through the general
+            aggregator, and the shape is remembered"""
+            rejected.add(plan.shape_key)
             agg = _kernels.Aggregator(len(plan.by), [_kernels.dtype_code(group[0].col(i)) for i in plan.val_pos],
                                       list(plan.accs))
             try:
@@ -988,10 +1046,11 @@ def _band_frames_plan(op0, frames):
         plan = _map_plan(op0, frames[0])
     except NotImplementedError:
         return None
-    if plan.shape_key in _dense_rejected:
-        return None
     sig = plan.for_dtypes(frames[0])
     if not sig[0]:
+        return None
+    if plan.shape_key in _dense_rejected and (plan.shape_key in _mid_rejected or not _mid_eligible(plan, sig)
+                                              or not hasattr(_kernels, "preagg_mid_batch_async")):
         return None
     cols0 = frames[0].columns
     for f in frames[1:]:

@@ -216,6 +216,16 @@ def groupby_aggregate(keys, vals, accs, sort=False, expect_distinct=False):
         agg.close()
 
 
+def estimate_distinct(keys: Sequence[torch.Tensor]) -> Tuple[int, int]:
+    """(rows sampled, distinct key hashes among them) of a strided sample of the chunk (mgb_estimate_distinct)"""
+    lib = _lib.load()
+    keys = [_req(k, f"key {i}", (torch.int64,)) for i, k in enumerate(keys)]
+    a, b = C.c_int64(), C.c_int64()
+    check(lib.mgb_estimate_distinct(_ptrs(keys), len(keys), keys[0].numel(), C.byref(a), C.byref(b), _stream()))
+    _count(1 if keys[0].numel() else 0)
+    return a.value, b.value
+
+
 # ------------------------------------------------------------------------------ low-cardinality fast paths
 _spec_cache = {}
 _dense_cap = None
@@ -460,13 +470,7 @@ def dense_batch_max() -> int:
     return _batch_max
 
 
-def preagg_dense_batch_async(chunks, accs: Sequence[Tuple[int, int]], val_dtypes, n_keys: int, device):
-    """Band-level batch of the dense pre-aggregation (mgb_preagg_dense_batch_async): ONE launch streams all
-    row batches and yields the partial rows of the whole band -- what n stage=map operands plus the combine
-    tree yield.  ``chunks``: list of (key pointers, value pointers (None for a count-only int64 column), rows);
-    at most ``dense_batch_max()`` of them.  Returns (int block, float block, fast-call) like
-    ``preagg_dense_async``; None when the shape can never be dense."""
-    global _dense_cap
+def _preagg_batch(entry: str, cap: int, chunks, accs, val_dtypes, n_keys: int, device):
     lib = _lib.load()
     nv, n = len(val_dtypes), len(chunks)
     if nv > _lib.MGB_MAX_VALS or len(accs) > _lib.MGB_MAX_ACCS:
@@ -474,10 +478,6 @@ def preagg_dense_batch_async(chunks, accs: Sequence[Tuple[int, int]], val_dtypes
     if n > dense_batch_max():
         raise MarsGBError(1, f"{n} chunks in one batch (at most {dense_batch_max()})")
     fc = _fast(n_keys, val_dtypes, accs)
-    if _dense_cap is None:
-        c = C.c_int64()
-        check(lib.mgb_dense_capacity(C.byref(c)))
-        _dense_cap = c.value
     rows = (C.c_int64 * max(n, 1))()
     kt = (_lib._pp * max(n, 1))()
     vt = (_lib._pp * max(n, 1))()
@@ -491,11 +491,46 @@ def preagg_dense_batch_async(chunks, accs: Sequence[Tuple[int, int]], val_dtypes
         vt[i] = C.cast(varr, _lib._pp)
         rows[i] = int(m)
         live += 1 if m else 0
-    bi, bf = fc.alloc(_dense_cap, device)
-    check(lib.mgb_preagg_dense_batch_async(C.byref(fc.spec), n, rows, kt, vt, fc.okp, fc.oap, _dense_cap,
-                                           fc.count_ptr(bi), _stream()))
-    _count(1 if live else 0)
-    return bi, bf, fc
+    bi, bf = fc.alloc(cap, device)
+    check(getattr(lib, entry)(C.byref(fc.spec), n, rows, kt, vt, fc.okp, fc.oap, cap, fc.count_ptr(bi), _stream()))
+    return bi, bf, fc, live
+
+
+def preagg_dense_batch_async(chunks, accs: Sequence[Tuple[int, int]], val_dtypes, n_keys: int, device):
+    """Band-level batch of the dense pre-aggregation (mgb_preagg_dense_batch_async): ONE launch streams all
+    row batches and yields the partial rows of the whole band -- what n stage=map operands plus the combine
+    tree yield.  ``chunks``: list of (key pointers, value pointers (None for a count-only int64 column), rows);
+    at most ``dense_batch_max()`` of them.  Returns (int block, float block, fast-call) like
+    ``preagg_dense_async``; None when the shape can never be dense."""
+    global _dense_cap
+    if _dense_cap is None:
+        c = C.c_int64()
+        check(_lib.load().mgb_dense_capacity(C.byref(c)))
+        _dense_cap = c.value
+    res = _preagg_batch("mgb_preagg_dense_batch_async", _dense_cap, chunks, accs, val_dtypes, n_keys, device)
+    if res is None:
+        return None
+    _count(1 if res[3] else 0)
+    return res[:3]
+
+
+_mid_cap = None
+
+
+def preagg_mid_batch_async(chunks, accs: Sequence[Tuple[int, int]], val_dtypes, n_keys: int, device):
+    """The same for the mid-cardinality sum / mean / count shapes (mgb_preagg_mid_batch_async): up to
+    mgb_mid_capacity() groups in the band; the device count is -1 for anything the path does not take (other
+    functions, too many groups, NaN values)."""
+    global _mid_cap
+    if _mid_cap is None:
+        c = C.c_int64()
+        check(_lib.load().mgb_mid_capacity(C.byref(c)))
+        _mid_cap = c.value
+    res = _preagg_batch("mgb_preagg_mid_batch_async", _mid_cap, chunks, accs, val_dtypes, n_keys, device)
+    if res is None:
+        return None
+    _count(2 if res[3] else 0)
+    return res[:3]
 
 
 SMALL_MAX_ROWS = 2048

@@ -284,3 +284,39 @@ def to_host_counted(columns, count_block, count_row):
 
 def to_host(columns):
     return [c.numpy().copy() for c in columns]
+
+
+MID_GROUPS = 2048
+
+
+def preagg_mid_batch_async(chunks, accs, val_dtypes, n_keys, device):
+    """double of the mid-cardinality batch: sum / count over float64 columns, <= MID_GROUPS groups, no NaN"""
+    calls.append("preagg_mid_batch_async")
+    fc = _K._fast(n_keys, val_dtypes, accs)
+    bi, bf = fc.alloc(MID_GROUPS, device)
+    used = {c for c, _ in accs}
+    keys = [np.concatenate([_view(kp[j], m, False) for kp, vp, m in chunks]) for j in range(n_keys)]
+    vals, ok = [], all(op in (SUM, COUNT) for _, op in accs)
+    for c, dt in enumerate(val_dtypes):
+        if c in used and all(vp[c] is not None for _, vp, _ in chunks):
+            v = np.concatenate([_view(vp[c], m, dt == F64) for _, vp, m in chunks])
+            ok = ok and dt == F64 and not np.isnan(v).any()
+            vals.append(v)
+        else:
+            vals.append(np.zeros(len(keys[0]), dtype=np.int64))
+    k, a = _agg_np(keys, vals, accs, None)
+    n = len(k[0]) if ok and len(k[0]) <= MID_GROUPS else -1
+    _fill_block(fc, bi, bf, k, a, n)
+    return bi, bf, fc
+
+
+def estimate_distinct(keys):
+    calls.append("estimate_distinct")
+    n = int(keys[0].numel())
+    s = min(n, 16384)
+    if s == 0:
+        return 0, 0
+    stride = n // s
+    idx = np.arange(s) * stride
+    df = pd.DataFrame({j: _np(k)[idx] for j, k in enumerate(keys)})
+    return s, int(len(df.drop_duplicates()))

@@ -632,3 +632,83 @@ def test_merge_small_post_is_the_whole_agg_stage(K, sort):
     assert K.result_block_to_host(blk, nk, npost, post.is_float)[0] == -1
     big = (pieces[1][0], pieces[1][1], 5000, 0) + pieces[1][4:]
     assert K.merge_small_post_async([big], [K.SUM] * 4, post) is None
+
+
+# ------------------------------------------------------------------------------- mid-cardinality batch kernel
+def _mid(K, chunks_keys, chunks_vals, accs, skip_cols=()):
+    dk = [[dev(k) for k in ks] for ks in chunks_keys]
+    dv = [[None if c in skip_cols else dev(v) for c, v in enumerate(vs)] for vs in chunks_vals]
+    dts = [K.F64 if v.dtype == np.float64 else K.I64 for v in chunks_vals[0]]
+    chunks = [([k.data_ptr() for k in ks], [None if v is None else v.data_ptr() for v in vs], len(chunks_keys[i][0]))
+              for i, (ks, vs) in enumerate(zip(dk, dv))]
+    bi, bf, fc = K.preagg_mid_batch_async(chunks, tuple(_codes(K, accs)), dts, len(chunks_keys[0]), torch.device("cuda", 0))
+    torch.cuda.synchronize()
+    n = int(bi[fc.n_int, 0])
+    if n < 0:
+        return n, None, None
+    k, a = fc.views(bi, bf, n)
+    return n, [t.cpu().numpy() for t in k], [t.cpu().numpy() for t in a]
+
+
+@pytest.mark.parametrize("n_keys", [1, 2])
+@pytest.mark.parametrize("ncol,card,sizes", [(4, 1000, [1_000_000, 777, 0, 300_000]), (1, 1500, [50_000]),
+                                             (8, 40, [200_000, 1024]), (2, 2000, [3_000_000])])
+def test_mid_batch_matches_pandas(K, n_keys, ncol, card, sizes):
+    rng = np.random.default_rng(card + ncol + n_keys)
+    ck, cv = [], []
+    c1 = max(1, int(np.sqrt(card)))
+    for n in sizes:
+        if n_keys == 1:
+            ck.append([rng.integers(-card // 2, card - card // 2, n, dtype=np.int64)])
+        else:
+            ck.append([rng.integers(0, c1, n, dtype=np.int64), rng.integers(0, card // c1, n, dtype=np.int64)])
+        cv.append([rng.normal(5, 2, n) for _ in range(ncol)] + [rng.integers(0, 99, n, dtype=np.int64)])
+    accs = [(c, "sum") for c in range(ncol)] + [(0, "count"), (ncol, "count")]
+    before = K.launch_counter
+    n, gk, ga = _mid(K, ck, cv, accs, skip_cols=(ncol,))
+    assert K.launch_counter - before == 2           # the batch kernel + the compaction of its global table
+    keys = [np.concatenate([c[j] for c in ck]) for j in range(n_keys)]
+    vals = [np.concatenate([c[j] for c in cv]) for j in range(ncol + 1)]
+    ek, ea = pandas_agg(keys, vals, accs)
+    assert n == len(ek[0])
+    order = np.lexsort(tuple(reversed(gk)))
+    for a, b in zip(gk, ek):
+        np.testing.assert_array_equal(a[order], b)
+    for (col, op), a, b in zip(accs, ga, ea):
+        if op == "count":
+            np.testing.assert_array_equal(a[order], b)
+        else:
+            np.testing.assert_allclose(a[order], b, rtol=1e-9, atol=0)
+
+
+def test_mid_batch_declines_what_it_does_not_take(K):
+    rng = np.random.default_rng(5)
+    n = 200_000
+    k = [rng.integers(0, 500, n, dtype=np.int64)]
+    v = [rng.random(n)]
+    assert _mid(K, [k], [v], [(0, "sum"), (0, "count")])[0] == 500
+    assert _mid(K, [k], [v], [(0, "sum"), (0, "max")])[0] == -1                       # not a sum / count shape
+    assert _mid(K, [[rng.integers(0, 5000, n, dtype=np.int64)]], [v], [(0, "sum")])[0] == -1   # too many groups
+    vn = [v[0].copy()]
+    vn[0][12345] = np.nan
+    assert _mid(K, [k], [vn], [(0, "sum"), (0, "count")])[0] == -1                    # NaN: general path keeps the books
+    vi = [rng.integers(0, 9, n, dtype=np.int64)]
+    assert _mid(K, [k], [vi], [(0, "sum")])[0] == -1                                  # int64 sums: general path
+    # heavily skewed keys: every lane of a warp on the same slot
+    ks = [np.where(rng.random(n) < 0.9, 7, rng.integers(0, 300, n)).astype(np.int64)]
+    nn, gk, ga = _mid(K, [ks], [v], [(0, "sum"), (0, "count")])
+    ek, ea = pandas_agg(ks, v, [(0, "sum"), (0, "count")])
+    order = np.argsort(gk[0])
+    np.testing.assert_array_equal(gk[0][order], ek[0])
+    np.testing.assert_array_equal(ga[1][order], ea[1])
+    np.testing.assert_allclose(ga[0][order], ea[0], rtol=1e-9)
+
+
+def test_estimate_distinct_tells_the_regimes_apart(K):
+    rng = np.random.default_rng(2)
+    n = 1_000_000
+    for card, lo, hi in [(4, 4, 4), (1000, 900, 1000), (10 ** 8, 15_000, 16_384)]:
+        s, d = K.estimate_distinct([dev(rng.integers(0, card, n, dtype=np.int64))])
+        assert s == 16384 and lo <= d <= hi, (card, s, d)
+    s, d = K.estimate_distinct([dev(rng.integers(0, 30, 5000, dtype=np.int64)), dev(rng.integers(0, 30, 5000, dtype=np.int64))])
+    assert s == 5000 and 850 <= d <= 900

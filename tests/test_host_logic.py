@@ -347,3 +347,28 @@ def test_shuffle_branch_is_not_fused(md):
     got, sess = _run_tree(md, raw, "key", ["sum"], 250, method="shuffle", sort=False)
     assert sess.fused_trees == 0
     assert_frames_match(got, raw.groupby("key").agg(["sum"]), sort_index=True)
+
+
+def test_mid_cardinality_band_takes_the_mid_batch_kernel(md):
+    """sum / mean / count over a few hundred groups: too many for the dense kernel, one launch of the
+    mid-cardinality batch kernel once the shape is known (the first run learns it)"""
+    from mars_b200 import executors
+
+    rng = np.random.default_rng(8)
+    n = 6000
+    raw = pd.DataFrame({"mkey": rng.integers(0, 300, n), "mv0": rng.random(n), "mv1": rng.random(n)})
+    exp = orc.run_groupby_agg(raw, "mkey", ["sum", "mean", "count"], 500, method="tree", sort=True)
+    got, sess = _run_tree(md, raw, "mkey", ["sum", "mean", "count"], 500)          # dense is tried, fails, replays
+    assert_frames_match(got, exp, sort_index=False)
+    assert any(k[0] == ("mkey",) for k in executors._dense_rejected)
+    fake_kernels.calls.clear()
+    got, sess = _run_tree(md, raw, "mkey", ["sum", "mean", "count"], 500)
+    assert sess.fused_trees == 1
+    assert fake_kernels.calls.count("preagg_mid_batch_async") == 1 and "preagg_dense_batch_async" not in fake_kernels.calls
+    assert fake_kernels.calls.count("merge_small_post_async") == 1 and "groupby_aggregate" not in fake_kernels.calls
+    assert_frames_match(got, exp, sort_index=False)
+    # per operand: every map operand is one asynchronous mid launch
+    fake_kernels.calls.clear()
+    got, sess = _run_tree(md, raw, "mkey", ["sum", "mean", "count"], 500, fuse=False)
+    assert fake_kernels.calls.count("preagg_mid_batch_async") == 12 and "groupby_aggregate" not in fake_kernels.calls
+    assert_frames_match(got, exp, sort_index=False)
