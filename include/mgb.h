@@ -92,6 +92,15 @@ int mgb_partition_scatter(const int32_t* pid, int64_t n_rows, int32_t n_partitio
                           const void* const* in_cols, void* const* out_cols, int32_t n_cols,
                           int64_t* out_offsets, void* stream);
 
+/* a5 in one call, without exposing the partition ids and without any host synchronisation: partition id =
+ * pandas hash of the key tuple % n_partitions (as mgb_partition_ids), stable split of the rows of in_cols into
+ * per-reducer blocks of out_cols (as mgb_partition_scatter), out_offsets[n_partitions + 1] on the device.  For
+ * n_partitions <= 256 every row is scattered straight to its destination (one pass over the columns, scattered
+ * 8-byte writes combined in L2) instead of being gathered through a permutation (random 8-byte reads).      */
+int mgb_hash_partition(const int64_t* const* key_cols, int32_t n_keys, int64_t n_rows, int32_t n_partitions,
+                       const void* const* in_cols, void* const* out_cols, int32_t n_cols, int64_t* out_offsets,
+                       void* stream);
+
 /* ---- a4/a9/a10: hash aggregation -------------------------------------------------------------------
  * Replaces `df.groupby(keys).agg(...)` of DataFrameGroupByAgg._execute_map / _execute_combine /
  * _execute_agg (mars/dataframe/groupby/aggregation.py:1043-1267, pandas group_sum/min/max/count).

@@ -68,6 +68,7 @@ SIGNATURES = {
     "mgb_partition_ids": (C.c_int, [_pp, _i32, _i64, _i64, _vp, _vp]),
     "mgb_range_partition_ids": (C.c_int, [_pp, _i32, _i64, _pp, _i32, _vp, _vp]),
     "mgb_partition_scatter": (C.c_int, [_vp, _i64, _i32, _pp, _pp, _i32, _vp, _vp]),
+    "mgb_hash_partition": (C.c_int, [_pp, _i32, _i64, _i32, _pp, _pp, _i32, _vp, _vp]),
     "mgb_agg_create": (C.c_int, [C.POINTER(_vp), C.POINTER(AggSpec), _vp]),
     "mgb_agg_set_hint": (C.c_int, [_vp, _i32]),
     "mgb_agg_update": (C.c_int, [_vp, _pp, _pp, _i64]),

@@ -1157,11 +1157,14 @@ def _execute_shuffle_map(ctx, op):
     blocks: List[List[Optional[DeviceFrame]]] = [[None] * len(frames) for _ in range(R)]
     for g in groups:
         base = frames[g[0]]
-        pid = _kernels.partition_ids(base.index, R)
         cols = list(base.index)
         for i in g:
             cols.extend(frames[i].data)
-        outs, offsets = _kernels.partition_scatter(pid, R, cols)
+        if hasattr(_kernels, "hash_partition"):     # hash + split in one call, rows scattered to their blocks
+            outs, offsets = _kernels.hash_partition(base.index, R, cols)
+        else:
+            pid = _kernels.partition_ids(base.index, R)
+            outs, offsets = _kernels.partition_scatter(pid, R, cols)
         nk = len(base.index)
         # R x K blocks per chunk: row ranges of the scattered columns, sliced only if somebody asks for tensors
         src = ColumnSet(outs)

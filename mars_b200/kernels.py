@@ -117,6 +117,22 @@ def partition_scatter(pid: torch.Tensor, n_partitions: int, cols: Sequence[torch
     return outs, offsets.cpu().tolist()
 
 
+def hash_partition(keys: Sequence[torch.Tensor], n_partitions: int, cols: Sequence[torch.Tensor]):
+    """a5 in one call (mgb_hash_partition): reducer index = pandas hash of the key tuple % n_partitions, stable
+    split of ``cols`` into per-reducer blocks.  Returns (out_cols, offsets) with offsets a host list of
+    n_partitions + 1 ints -- the only host wait of the call."""
+    lib = _lib.load()
+    keys = [_req(k, f"key {i}", (torch.int64,)) for i, k in enumerate(keys)]
+    cols = [_req(c, f"column {i}") for i, c in enumerate(cols)]
+    n = keys[0].numel()
+    outs = [torch.empty_like(c) for c in cols]
+    offsets = torch.empty(n_partitions + 1, dtype=torch.int64, device=keys[0].device)
+    check(lib.mgb_hash_partition(_ptrs(keys), len(keys), n, int(n_partitions), _ptrs(cols), _ptrs(outs), len(cols),
+                                 offsets.data_ptr(), _stream()))
+    _count(7 if n else 1)
+    return outs, offsets.cpu().tolist()
+
+
 # ------------------------------------------------------------------------------------------ aggregation
 class Aggregator:
     """Streaming hash aggregation: update() any number of row batches, then result()."""

@@ -320,3 +320,12 @@ def estimate_distinct(keys):
     idx = np.arange(s) * stride
     df = pd.DataFrame({j: _np(k)[idx] for j, k in enumerate(keys)})
     return s, int(len(df.drop_duplicates()))
+
+
+def hash_partition(keys, n_partitions, cols):
+    calls.append("hash_partition")
+    pid = partition_ids(keys, n_partitions)
+    calls.pop()
+    out = partition_scatter(pid, n_partitions, cols)
+    calls.pop()
+    return out

@@ -712,3 +712,20 @@ def test_estimate_distinct_tells_the_regimes_apart(K):
         assert s == 16384 and lo <= d <= hi, (card, s, d)
     s, d = K.estimate_distinct([dev(rng.integers(0, 30, 5000, dtype=np.int64)), dev(rng.integers(0, 30, 5000, dtype=np.int64))])
     assert s == 5000 and 850 <= d <= 900
+
+
+@pytest.mark.parametrize("n_keys", [1, 2])
+@pytest.mark.parametrize("n,R", [(0, 4), (1, 1), (5000, 7), (300_000, 64), (1_000_003, 256), (200_000, 1000)])
+def test_hash_partition_equals_ids_plus_stable_split(K, n_keys, n, R):
+    """a5 in one call: same blocks, same order inside every block (ascending input positions f_i of the
+    reference, groupby/core.py:389-435) as mgb_partition_ids + mgb_partition_scatter, and as the oracle"""
+    rng = np.random.default_rng(n + R)
+    keys = [rng.integers(-10 ** 9, 10 ** 9, n, dtype=np.int64) for _ in range(n_keys)]
+    cols = keys + [rng.random(n), np.arange(n, dtype=np.int64)]
+    outs, offsets = K.hash_partition([dev(k) for k in keys], R, [dev(c) for c in cols])
+    pid = orc.partition_ids(keys, R)
+    order = np.argsort(pid, kind="stable")
+    exp_off = np.searchsorted(pid[order], np.arange(R + 1)).tolist()
+    assert offsets == exp_off
+    for got, src in zip(outs, cols):
+        np.testing.assert_array_equal(got.cpu().numpy(), src[order])
