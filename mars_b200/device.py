@@ -153,7 +153,7 @@ class ColumnSet:
 
 class DeviceFrame:
     __slots__ = ("index_names", "_index", "columns", "_data", "_n", "_pending", "_slot", "_home", "_src",
-                 "__weakref__")
+                 "_ptrs_cache", "__weakref__")
 
     def __init__(self, index_names: Sequence[Any], index: Optional[Sequence[torch.Tensor]],
                  columns: Sequence[Any], data: Sequence[torch.Tensor], n_rows: Optional[int] = None,
@@ -166,6 +166,7 @@ class DeviceFrame:
         self._slot = slot
         self._home = None            # device of lazily uploaded columns (set by from_pandas(lazy=True))
         self._src = None             # row range of scattered columns that has not been sliced yet (from_range)
+        self._ptrs_cache = None      # (column selection, pointers) of the last band-level batch over this chunk
         if pending is not None:
             pending.attach(self)
             self._n = None
@@ -195,6 +196,7 @@ class DeviceFrame:
         f._pending = pending
         f._slot = slot
         f._home = None
+        f._ptrs_cache = None
         f._src = (src, k0, k1, d0, d1, a, b)
         if pending is not None:      # rows [0, capacity) of a speculative result: the size is still on the device
             pending.attach(f)

@@ -556,7 +556,8 @@ def _post_plan(op, slots, steps, two_level):
     Cached on the identity of ``op.post_funcs`` (compiled reductions are shared between the operands of one
     computation) and the partial schema."""
     first = [sl[0] for sl in slots]
-    key = (id(op.post_funcs), two_level, tuple(tuple(f.columns) for f in first))
+    key = (id(op.post_funcs), two_level, tuple(tuple(f.columns) for f in first),
+           tuple(f.col_dtype(j) for f in first for j in range(len(f.columns))))
     hit = _post_plans.get(key)
     if hit is not None and hit[0] is op.post_funcs:
         return hit[1]
@@ -997,10 +998,18 @@ def _launch_band(plan, sig, frames):
     rejected = _dense_rejected if which == "dense" else _mid_rejected
     keys_ok, count_only, dts = sig
     chunks = []
+    ck = (tuple(plan.key_pos), tuple(plan.val_pos), count_only)
     for f in frames:
+        hit = f._ptrs_cache
+        if hit is not None and hit[0] == ck:      # the column pointers of a resident chunk do not change
+            chunks.append(hit[1])
+            continue
         kp = [f.col(i).data_ptr() for i in plan.key_pos]
         vp = [None if j in count_only else f.col(i).data_ptr() for j, i in enumerate(plan.val_pos)]
-        chunks.append((kp, vp, len(f)))
+        ent = [kp, vp, len(f)]          # (a list: the batch wrapper appends its ctypes arrays for the next call)
+        if f._pending is None and f._src is None:
+            f._ptrs_cache = (ck, ent)
+        chunks.append(ent)
     B = _kernels.dense_batch_max()
     dev = frames[0].device
     nk = len(plan.by)

@@ -499,9 +499,15 @@ def _preagg_batch(entry: str, cap: int, chunks, accs, val_dtypes, n_keys: int, d
     vt = (_lib._pp * max(n, 1))()
     keep = []
     live = 0
-    for i, (kp, vp, m) in enumerate(chunks):
-        karr = (C.c_void_p * n_keys)(*kp)
-        varr = (C.c_void_p * max(nv, 1))(*vp)
+    for i, ent in enumerate(chunks):
+        kp, vp, m = ent[0], ent[1], ent[2]
+        if len(ent) > 3:                   # ctypes arrays built by an earlier call over the same resident chunk
+            karr, varr = ent[3]
+        else:
+            karr = (C.c_void_p * n_keys)(*kp)
+            varr = (C.c_void_p * max(nv, 1))(*vp)
+            if isinstance(ent, list):
+                ent.append((karr, varr))
         keep.append((karr, varr))
         kt[i] = C.cast(karr, _lib._pp)
         vt[i] = C.cast(varr, _lib._pp)

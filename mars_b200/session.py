@@ -24,7 +24,7 @@ import pandas as pd
 from . import core
 from . import executors as _ex
 from .core import ChunkData, ProcessorContext, build_chunk_graph
-from .dataframe import DataFrame, DataFrameGroupByAgg, DataFrameShuffleProxy
+from .dataframe import DataFrame, DataFrameDataSource, DataFrameGroupByAgg, DataFrameShuffleProxy
 
 
 _op_names: Dict[object, str] = {}
@@ -238,7 +238,13 @@ class Session:
         map_op.stage = core.OperandStage.map
         map_op.pre_funcs, map_op.agg_funcs = steps.pre_funcs, steps.agg_funcs
         map_op.new_chunk([chunks[0]], index=(0, 0))
-        self._run_chunks_local(list(chunks), ctx, owners)       # data sources (and H2D operands) of the band
+        if all(type(c.op) is DataFrameDataSource for c in chunks):
+            for c in chunks:                      # resident chunks: the data-source operand only hands over its frame
+                ctx[c.key] = c.op.data
+                owners[c.key] = 0
+            self.executed_ops.extend(["DataFrameDataSource:None"] * len(chunks))
+        else:
+            self._run_chunks_local(list(chunks), ctx, owners)   # data sources and H2D operands of the band
         frames = [ctx[c.key] for c in chunks]
         return _ex.launch_eager_band(map_op, [c.key for c in chunks], frames)
 
@@ -419,8 +425,7 @@ class Session:
                 if obj is not None and not isinstance(obj, pd.DataFrame):
                     obj = obj.to_pandas()         # device-resident result chunk: read back on its owner
                 parts.append(self.exchange.fetch_result(obj, self._owners[c.key]))
-        from .executors import DeviceResult
-
+        DeviceResult = _ex.DeviceResult
         if parts and all(isinstance(p, DeviceResult) for p in parts):
             return DeviceResult.fetch_all(parts)      # one pinned block, no host-side concat
         parts = [p if isinstance(p, pd.DataFrame) else p.to_pandas() for p in parts]

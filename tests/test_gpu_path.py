@@ -303,6 +303,8 @@ def test_tree_branch_runs_as_one_batch_launch(md, method, func):
     executors._dense_rejected.clear()
     mdf = md.DataFrame(raw, chunk_size=90_000).to_gpu()
     exp = orc.run_groupby_agg(raw, ["fk1", "fk2"], func, 90_000, method="tree", sort=True)
+    warm = mdf.groupby(["fk1", "fk2"]).agg(func, method=method)      # first sight of the shape: cardinality probe
+    warm.execute(session=md.new_session(default=False))
     results = {}
     for fuse in (True, False):
         sess = md.new_session(default=False)

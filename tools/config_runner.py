@@ -95,7 +95,17 @@ def run_record(name: str, rows: int, chunk_rows: int = None, repeats: int = 2, p
     by = cfg.by if len(cfg.by) > 1 else cfg.by[0]
     times, fetch_times, out, sess = [], [], None, None
     launches = 0
-    for it in range(repeats + 1):
+    import ctypes as C
+
+    from mars_b200 import _lib
+
+    lib = _lib.load()
+    kernel_ms = None
+    for it in range(repeats + 2):
+        profiled = it == repeats + 1            # one extra, untimed run with per-kernel CUDA events
+        if profiled:
+            lib.mgb_prof_enable(1)
+            lib.mgb_prof_reset()
         sess = md.new_session(default=False)
         sess.fuse = fuse
         r = md.DataFrame.from_chunks(frames).groupby(by, sort=cfg.sort).agg(cfg.func, method=cfg.method)
@@ -111,7 +121,17 @@ def run_record(name: str, rows: int, chunk_rows: int = None, repeats: int = 2, p
         out = r.fetch(session=sess)
         torch.cuda.synchronize()
         t2 = time.perf_counter()
-        if it:
+        if profiled:
+            kernel_ms = {}
+            names = ["preagg_dense", "preagg_smem_or_mid", "merge", "update_global", "table_init", "emit", "hash",
+                     "partition", "sort", "post", "bucket"]
+            for kid, nm in enumerate(names):
+                tot, cnt = C.c_double(), C.c_int64()
+                lib.mgb_prof_read(kid, C.byref(tot), C.byref(cnt))
+                if cnt.value:
+                    kernel_ms[nm] = {"ms_total": tot.value, "launches": cnt.value}
+            lib.mgb_prof_enable(0)
+        elif it:
             times.append(max(t1 - t0, e0.elapsed_time(e1) * 1e-3))
             fetch_times.append(t2 - t1)
             launches = kernels.launch_counter - l0
@@ -123,7 +143,7 @@ def run_record(name: str, rows: int, chunk_rows: int = None, repeats: int = 2, p
            "by": cfg.by, "func": cfg.func, "sort": cfg.sort, "method": cfg.method,
            "plan": sorted(set(sess.executed_ops)), "fused_trees": sess.fused_trees,
            "value": rows / sec, "unit": "rows/s", "seconds": times, "fetch_seconds": fetch_times,
-           "gpu_launches": int(launches),
+           "gpu_launches": int(launches), "kernel_time_ms": kernel_ms,
            "roofline": {"bound": "hbm", "algorithmic_bytes": alg, "achieved": alg / sec / 1e9, "peak": peak,
                         "unit": "GB/s", "frac": alg / sec / 1e9 / peak},
            "input": f"host numpy default_rng({bc.SEED} + chunk), uploaded before the timed region; {gen_s:.1f} s to generate"}
