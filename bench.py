@@ -203,77 +203,84 @@ def workload_config(args, world):
 # clocks
 # ----------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """SM clock + throttle reasons sampled DURING the timed region (NVML in a background thread, 5 ms period;
-    falls back to one `nvidia-smi` query when NVML is unavailable)."""
+    """SM clock + throttle reasons DURING the measured window, sampled by a separate `nvidia-smi -lms` process (the
+    recipe of /opt/skills/guides/B200_PROFILING.md): started before the warm-up steps, killed after the timed
+    steps, so every sample is taken under the bench's own load.  An NVML thread inside this process was measured
+    to double the step time (its queries contend with the launches for the driver); one NVML sample is still
+    taken by the timed thread itself in the middle of the timed region (``poke``)."""
 
-    def __init__(self, device_index: int):
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int, period_ms: int = 100):
         self.idx = device_index
-        self.samples, self.max_mhz, self.reasons = [], None, set()
-        self._stop = threading.Event()
-        self._thread = None
+        self.period_ms = period_ms
+        self.proc, self.path = None, None
+        self.poked = []
         self._nvml = None
 
-    def _loop(self):
-        nv, h = self._nvml, self._handle
-        bits = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "sw_power_cap": 0x4}
-        while not self._stop.is_set():
-            try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
-                try:
-                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
-                except Exception:  # noqa: BLE001
-                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                for name, bit in bits.items():
-                    if r & bit:
-                        self.reasons.add(name)
-            except Exception:  # noqa: BLE001
-                break
-            self._stop.wait(0.005)
+    def _physical_index(self):
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if visible:
+            parts = visible.split(",")
+            if self.idx < len(parts) and parts[self.idx].strip().isdigit():
+                return int(parts[self.idx])
+        return self.idx
 
     def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(prefix="mgb_clocks_", suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-i", str(self._physical_index()),
+                 "-lms", str(self.period_ms), "-f", self.path], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        except Exception:  # noqa: BLE001
+            self.proc = None
         try:
             import pynvml as nv
 
             nv.nvmlInit()
-            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
-            phys = int(visible.split(",")[self.idx]) if visible and visible.split(",")[self.idx].isdigit() else self.idx
-            self._handle = nv.nvmlDeviceGetHandleByIndex(phys)
-            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(self._handle, nv.NVML_CLOCK_SM)
+            self._handle = nv.nvmlDeviceGetHandleByIndex(self._physical_index())
             self._nvml = nv
-            self._thread = threading.Thread(target=self._loop, daemon=True)
-            self._thread.start()
         except Exception:  # noqa: BLE001
             self._nvml = None
 
     def poke(self):
-        """one sample taken by the caller itself (between two steps of the timed region): the background
-        thread can be starved by the GIL while the main thread runs Python"""
+        """one sample taken by the timed thread itself, inside the timed region"""
         if self._nvml is not None:
             try:
-                self.samples.append(self._nvml.nvmlDeviceGetClockInfo(self._handle, self._nvml.NVML_CLOCK_SM))
+                self.poked.append(self._nvml.nvmlDeviceGetClockInfo(self._handle, self._nvml.NVML_CLOCK_SM))
             except Exception:  # noqa: BLE001
                 pass
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        if self._nvml is not None:
-            self._stop.set()
-            self._thread.join(timeout=2)
-            if self.samples:
-                out.update(sm_mhz=statistics.median(self.samples), sm_max_mhz=self.max_mhz, samples=len(self.samples),
-                           reasons=sorted(self.reasons), source="nvml: background thread (5 ms) + one sample after every step, inside the timed region")
-                return out
-        try:   # fallback: one nvidia-smi query right after the timed region
-            q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-                "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-            txt = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.idx)],
-                                 capture_output=True, text=True, timeout=10).stdout.strip().splitlines()[0]
-            f = [x.strip() for x in txt.split(",")]
-            out.update(sm_mhz=float(f[0]), sm_max_mhz=float(f[1]), samples=1, source="nvidia-smi after the timed region",
-                       reasons=[n for n, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
-                                                   "sw_power_cap"), f[2:6]) if v.lower().startswith("active")])
-        except Exception:  # noqa: BLE001
-            pass
+        samples, mx, reasons = [], None, set()
+        if self.proc is not None:
+            try:
+                time.sleep(self.period_ms / 1000.0)       # let the sampler write the sample that covers the last steps
+                self.proc.terminate()
+                self.proc.wait(timeout=5)
+            except Exception:  # noqa: BLE001
+                pass
+            try:
+                names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+                for line in open(self.path):
+                    f = [x.strip() for x in line.split(",")]
+                    if len(f) < 6 or not f[0].replace(".", "").isdigit():
+                        continue
+                    samples.append(float(f[0]))
+                    mx = float(f[1])
+                    reasons.update(n for n, v in zip(names, f[2:6]) if v.lower().startswith("active"))
+                os.unlink(self.path)
+            except Exception:  # noqa: BLE001
+                pass
+        allv = samples + [float(x) for x in self.poked]
+        if allv:
+            out.update(sm_mhz=statistics.median(allv), sm_max_mhz=mx, samples=len(allv), in_region_nvml_samples=len(self.poked),
+                       reasons=sorted(reasons),
+                       source=f"nvidia-smi -lms {self.period_ms} in a separate process over warm-up + timed steps (same load), "
+                              f"plus one NVML sample taken inside the timed region")
         return out
 
 
@@ -401,12 +408,12 @@ def main_ours(args):
 
     sampler = ClockSampler(local)
     lib.mgb_prof_enable(1)
+    sampler.start()
     for _ in range(args.warmup):
         step(dev_frames)
     barrier()
     lib.mgb_prof_reset()
     launches0 = kernels.launch_counter
-    sampler.start()
     ms, out = timed(dev_frames, args.steps, 0, sampler)
     clocks = sampler.stop()
     launches = kernels.launch_counter - launches0

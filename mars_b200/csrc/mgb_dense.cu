@@ -388,10 +388,53 @@ __global__ void __launch_bounds__(SM_THREADS, 1) k_merge_small(const SmallParams
   }
   __syncthreads();
   const int nu = *n_unique;
-  // output position of every unique key: rank by key tuple when sorting (keys are unique), else table order
+  // output position of every unique key: rank by key tuple when sorting (keys are unique), else table order.
+  // More than a handful of keys are ranked by a bitonic sort of their indices in shared memory (`sorted` is
+  // free until the counting sort below): O(n log^2 n) instead of the n^2 comparisons of the direct ranking.
+  const bool big_sort = p.sort && nu > 96;
+  if (big_sort) {
+    int n2 = 128;
+    while (n2 < nu) n2 <<= 1;
+    for (int i = threadIdx.x; i < n2; i += SM_THREADS) sorted[i] = i < nu ? i : -1;   // -1: +infinity padding
+    __syncthreads();
+    for (int k = 2; k <= n2; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = threadIdx.x; i < n2; i += SM_THREADS) {
+          const int ixj = i ^ j;
+          if (ixj > i) {
+            const int a = sorted[i], b = sorted[ixj];
+            bool b_less_a;   // is entry b strictly smaller than entry a ?
+            if (b < 0)
+              b_less_a = false;
+            else if (a < 0)
+              b_less_a = true;
+            else {
+              uint64_t ka[NK], kb2[NK];
+#pragma unroll
+              for (int q = 0; q < NK; ++q) {
+                ka[q] = ukeys[q * MAXR + a];
+                kb2[q] = ukeys[q * MAXR + b];
+              }
+              b_less_a = key_less<NK>(kb2, ka);
+            }
+            const bool up = (i & k) == 0;
+            if (b_less_a == up) {
+              sorted[i] = b;
+              sorted[ixj] = a;
+            }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    for (int i = threadIdx.x; i < nu; i += SM_THREADS) rank[sorted[i]] = i;
+    __syncthreads();
+  }
   for (int u = threadIdx.x; u < nu; u += SM_THREADS) {
     int pos = u;
-    if (p.sort) {
+    if (big_sort) {
+      pos = rank[u];
+    } else if (p.sort) {
       uint64_t k[NK];
 #pragma unroll
       for (int j = 0; j < NK; ++j) k[j] = ukeys[j * MAXR + u];
