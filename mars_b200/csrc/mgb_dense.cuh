@@ -331,7 +331,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_preagg_dense(const DenseParams p
   bool failed = false;
 
   // one row: group lookup, then lane-private accumulator updates
-  auto process_row = [&](const uint64_t* k, const uint64_t* x, const bool live) {
+  // group id of one row (all 32 lanes together); sets `failed` when the CTA would need more than GC groups
+  auto find_group = [&](const uint64_t* k, const bool live) -> int {
     const int s = (int)(dense_hash<NK>(k) >> 26);
     // first probe without branches (the common case); further probes only for the lanes that need them
     const int tg = ((const volatile int*)tgid)[s];
@@ -343,11 +344,56 @@ __global__ void __launch_bounds__(THREADS, 1) k_preagg_dense(const DenseParams p
         g = dense_probe<NK>(tkeys, tgid, (s + 1) & (DN_TAB - 1), k[0], NK == 2 ? k[1] : 0);
       if (__any_sync(0xffffffffu, live && g < 0)) {   // some lane met a key this CTA has not seen yet
         g = dense_slow_lookup<NK>(tkeys, tgid, gkeys, s_ng, s_lock, GC, k[0], NK == 2 ? k[1] : 0, live, g);
-        if (__any_sync(0xffffffffu, g == -2)) {   // more distinct keys than group slots: not a dense chunk
-          failed = true;
-          return;
-        }
+        if (__any_sync(0xffffffffu, g == -2)) failed = true;   // more distinct keys than group slots: not a dense chunk
       }
+    }
+    return g;
+  };
+
+  // PLAIN shapes, two rows of a lane at once: the accumulator read-modify-write chains of the two rows are
+  // independent unless both rows belong to the same group, so all loads are issued first, the adds of the second
+  // row take the first row's sums when the groups coincide (a select, no branch), and the stores follow in
+  // order -- half the shared-memory latency per row of the one-row-at-a-time update.  NaN values (rare) take the
+  // one-row path.  Same summation order per (lane, group) as before: (a + x0) + x1.
+  auto update_pair_plain = [&](const int g0, const uint64_t* x0, const int g1, const uint64_t* x1) -> bool {
+    bool anynan = false;
+#pragma unroll
+    for (int c = 0; c < NV; ++c) {
+      const double u = __longlong_as_double((long long)x0[c]), v = __longlong_as_double((long long)x1[c]);
+      anynan = anynan || (u != u) || (v != v);
+    }
+    if (anynan) return false;
+    uint32_t* b0 = wacc + g0 * p.stride_g;
+    uint32_t* b1 = wacc + g1 * p.stride_g;
+    const bool same = g0 == g1;
+    const uint32_t r0 = b0[lane], r1 = b1[lane];
+    double a0[NV], a1[NV];
+    double* d0 = (double*)b0 + lane;
+    double* d1 = (double*)b1 + lane;
+#pragma unroll
+    for (int c = 0; c < NV; ++c) {
+      a0[c] = d0[o_sum + c * 32];
+      a1[c] = d1[o_sum + c * 32];
+    }
+#pragma unroll
+    for (int c = 0; c < NV; ++c) {
+      a0[c] += __longlong_as_double((long long)x0[c]);
+      a1[c] = (same ? a0[c] : a1[c]) + __longlong_as_double((long long)x1[c]);
+    }
+    b0[lane] = r0 + 1;
+    b1[lane] = (same ? r0 + 1 : r1) + 1;
+#pragma unroll
+    for (int c = 0; c < NV; ++c) d0[o_sum + c * 32] = a0[c];
+#pragma unroll
+    for (int c = 0; c < NV; ++c) d1[o_sum + c * 32] = a1[c];
+    return true;
+  };
+
+  auto process_row = [&](const uint64_t* k, const uint64_t* x, const bool live, int g_known = -1) {
+    int g = g_known;
+    if (g_known < 0) {
+      g = find_group(k, live);
+      if (failed) return;
     }
     if (!live) return;
     uint32_t* blk = wacc + g * p.stride_g;   // block base; lane-private columns inside
@@ -447,6 +493,21 @@ __global__ void __launch_bounds__(THREADS, 1) k_preagg_dense(const DenseParams p
     }
   };
   auto process_tile = [&](int buf) {
+    if (PLAIN) {
+#pragma unroll
+      for (int r = 0; r < DN_R; r += 2) {
+        if (failed) return;
+        const int g0 = find_group(kb[buf][r], true);
+        if (failed) return;
+        const int g1 = find_group(kb[buf][r + 1], true);
+        if (failed) return;
+        if (!update_pair_plain(g0, xb[buf][r], g1, xb[buf][r + 1])) {
+          process_row(kb[buf][r], xb[buf][r], true, g0);
+          process_row(kb[buf][r + 1], xb[buf][r + 1], true, g1);
+        }
+      }
+      return;
+    }
 #pragma unroll
     for (int r = 0; r < DN_R; ++r) {
       if (failed) return;

@@ -5,10 +5,11 @@
 //
 // One launch streams ALL row batches of a band (same chunk table as the dense batch: the chunks form one virtual
 // sequence of 1024-row tiles, register double-buffered).  Per CTA (one per SM):
-//   * key table: open addressing over MID_TAB slots, slot state 0 empty / 1 being published / 2 ready; lookups
-//     and inserts are warp-converged retry loops (a lane never spins on a slot that another lane of its own warp
-//     is publishing);
-//   * accumulators: ONE record per slot -- [sum 0 .. sum NV-1 | rows (u32) | lock (u32)] -- updated under a
+//   * key table: open addressing over MID_TAB slots that map a key tuple to a dense group id (-1 empty, -2 being
+//     published); lookups and inserts are warp-converged retry loops (a lane never spins on a slot that another
+//     lane of its own warp is publishing).  The table is kept sparse (load <= 0.375) because a warp iterates as
+//     long as its unluckiest lane probes (ncu, first version at load 0.5: 6.5 rounds per row);
+//   * accumulators: ONE record per group -- [sum 0 .. sum NV-1 | rows (u32) | lock (u32)] -- updated under a
 //     per-slot try-lock with plain 128-bit shared-memory loads / DADDs / stores.  Shared memory has no native
 //     float64 add: `atomicAdd(double*)` is a compare-and-swap loop per column (what k_preagg_hash pays, 47 % of
 //     its stall samples); here a row costs one ATOMS.EXCH to take the lock however many columns it carries.
@@ -24,8 +25,8 @@
 
 #define MID_THREADS 512
 #define MID_R 2                    // rows per thread per tile: a tile is 1024 rows
-#define MID_TAB 2048               // slots of the per-CTA table
-#define MID_CTA_GROUPS 1536        // a CTA gives up beyond this many groups (load 0.75)
+#define MID_TAB 4096               // slots of the per-CTA key table (load <= 0.375: short probe sequences)
+#define MID_CTA_GROUPS 1536        // accumulator records per CTA == groups a CTA holds before it gives up
 #define MID_GTAB 4096              // slots of the global merge table
 #define MID_MAX_GROUPS 2048        // groups of a band this path reports (== capacity of the small merge)
 #define MID_EMIT_THREADS 1024
@@ -64,20 +65,20 @@ __device__ __forceinline__ uint32_t mid_hash(const uint64_t* k) {
 template <int NK, int NV>
 __global__ void __launch_bounds__(MID_THREADS, 1) k_preagg_mid(const MidParams p, const DenseBatch bt) {
   extern __shared__ __align__(16) uint64_t msm[];
-  // layout: rec[MID_TAB][rec_w] | tkeys[NK][MID_TAB] | tstate[MID_TAB] (u32) | ints | chunk table
+  // layout: rec[MID_CTA_GROUPS][rec_w] | tkeys[NK][MID_TAB] | tgid[MID_TAB] (int) | ints | chunk table
   const int RW = p.rec_w;
   uint64_t* rec = msm;
-  uint64_t* tkeys = rec + (size_t)MID_TAB * RW;
-  uint32_t* tstate = (uint32_t*)(tkeys + (size_t)NK * MID_TAB);
-  int* s_int = (int*)(tstate + MID_TAB);
+  uint64_t* tkeys = rec + (size_t)MID_CTA_GROUPS * RW;
+  int* tgid = (int*)(tkeys + (size_t)NK * MID_TAB);
+  int* s_int = tgid + MID_TAB;
   int* s_count = s_int;          // groups in this CTA's table
   int* s_fail = s_int + 1;
   long long* s_tile_end = (long long*)(s_int + 8);
   long long* s_rows = s_tile_end + DN_MAX_CHUNKS;
   const uint64_t** s_ptr = (const uint64_t**)(s_rows + DN_MAX_CHUNKS);
 
-  for (int i = threadIdx.x; i < MID_TAB * RW; i += MID_THREADS) rec[i] = 0;
-  for (int i = threadIdx.x; i < MID_TAB; i += MID_THREADS) tstate[i] = 0;
+  for (int i = threadIdx.x; i < MID_CTA_GROUPS * RW; i += MID_THREADS) rec[i] = 0;
+  for (int i = threadIdx.x; i < MID_TAB; i += MID_THREADS) tgid[i] = -1;
   const int n_chunks = bt.n_chunks;
   for (int i = threadIdx.x; i < n_chunks; i += MID_THREADS) {
     s_tile_end[i] = bt.tile_end[i];
@@ -103,32 +104,38 @@ __global__ void __launch_bounds__(MID_THREADS, 1) k_preagg_mid(const MidParams p
     int probes = 0;
     while (__any_sync(FULL, !done)) {
       if (!done) {
-        const uint32_t st = ((volatile uint32_t*)tstate)[s];
-        if (st == 2u) {
+        const int tg = ((volatile int*)tgid)[s];
+        if (tg >= 0) {
           bool eq = ((volatile uint64_t*)tkeys)[s] == k[0];
           if (NK == 2) eq = eq && ((volatile uint64_t*)tkeys)[MID_TAB + s] == k[1];
           if (eq) {
-            slot = (int)s;
+            slot = tg;
             done = true;
           } else {
             s = (s + 1) & (MID_TAB - 1);
             if (++probes > MID_TAB) done = true;      // cannot happen below the group limit
           }
-        } else if (st == 0u) {
+        } else if (tg == -1) {
           if (*(volatile int*)s_count >= MID_CTA_GROUPS) {
             done = true;                               // too many groups for this path
-          } else if (atomicCAS(&tstate[s], 0u, 1u) == 0u) {
-            ((volatile uint64_t*)tkeys)[s] = k[0];
-            if (NK == 2) ((volatile uint64_t*)tkeys)[MID_TAB + s] = k[1];
-            atomicAdd(s_count, 1);
-            __threadfence_block();
-            ((volatile uint32_t*)tstate)[s] = 2u;
-            slot = (int)s;
+          } else if (atomicCAS(&tgid[s], -1, -2) == -1) {
+            const int id = atomicAdd(s_count, 1);
+            if (id < MID_CTA_GROUPS) {
+              ((volatile uint64_t*)tkeys)[s] = k[0];
+              if (NK == 2) ((volatile uint64_t*)tkeys)[MID_TAB + s] = k[1];
+              __threadfence_block();
+              ((volatile int*)tgid)[s] = id;
+              slot = id;
+            } else {
+              ((volatile int*)tgid)[s] = -3;           // poisoned: nobody waits on it, the launch fails
+            }
             done = true;
           }
           // lost the claim: the winner may hold this very key -- look at the slot again next round
+        } else if (tg == -3) {
+          done = true;
         }
-        // st == 1: being published by another thread, look again next round
+        // tg == -2: being published by another thread, look again next round
       }
     }
     bool bad = live && slot < 0;
@@ -248,7 +255,8 @@ __global__ void __launch_bounds__(MID_THREADS, 1) k_preagg_mid(const MidParams p
   // ---- fold this CTA's groups into the global table (uniform trip count: the claim loop votes per warp)
   for (int i0 = 0; i0 < MID_TAB; i0 += MID_THREADS) {
     const int i = i0 + (int)threadIdx.x;
-    const bool live = tstate[i] == 2u;
+    const int my = tgid[i];
+    const bool live = my >= 0;
     uint64_t k[NK];
 #pragma unroll
     for (int j = 0; j < NK; ++j) k[j] = live ? tkeys[(size_t)j * MID_TAB + i] : 0;
@@ -287,7 +295,7 @@ __global__ void __launch_bounds__(MID_THREADS, 1) k_preagg_mid(const MidParams p
     if (live && gs < 0) {
       *p.flags = 1;
     } else if (live) {
-      const uint64_t* r = rec + (size_t)i * RW;
+      const uint64_t* r = rec + (size_t)my * RW;
       const unsigned long long rows = (unsigned long long)*(const uint32_t*)(r + NV);
       for (int a = 0; a < p.na; ++a) {
         uint64_t* dst = p.gacc + (size_t)a * MID_GTAB + gs;
@@ -447,7 +455,7 @@ extern "C" int mgb_preagg_mid_batch_async(const mgb_agg_spec* spec, int32_t n_ch
   MGB_CUDA(cudaMemsetAsync(p.flags, 0, 64, st));
   const int sms = mgb_sm_count();
   const int grid = (int)(work_tiles < sms ? work_tiles : sms);
-  const size_t smem = (size_t)MID_TAB * p.rec_w * 8 + (size_t)nk * MID_TAB * 8 + (size_t)MID_TAB * 4 + 32 +
+  const size_t smem = (size_t)MID_CTA_GROUPS * p.rec_w * 8 + (size_t)nk * MID_TAB * 8 + (size_t)MID_TAB * 4 + 32 +
                       (size_t)DN_MAX_CHUNKS * (2 + DN_PTRS) * 8 + 64;
   MGB_REQUIRE(smem <= 227 * 1024, MGB_ERR_OVERFLOW, "mid path shared-memory plan does not fit (%zu)", smem);
   {
