@@ -203,21 +203,22 @@ def workload_config(args, world):
 # clocks
 # ----------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """SM clock + throttle reasons DURING the measured window, sampled by a separate `nvidia-smi -lms` process (the
-    recipe of /opt/skills/guides/B200_PROFILING.md): started before the warm-up steps, killed after the timed
-    steps, so every sample is taken under the bench's own load.  An NVML thread inside this process was measured
-    to double the step time (its queries contend with the launches for the driver); one NVML sample is still
-    taken by the timed thread itself in the middle of the timed region (``poke``)."""
+    """SM clock + throttle reasons under the bench's load, sampled by a separate `nvidia-smi -lms` process (the recipe
+    of /opt/skills/guides/B200_PROFILING.md: start before, kill after).  In-process NVML queries were measured to
+    slow the step down by up to 2x (they contend with the kernel launches for the driver), so nothing inside this
+    process touches NVML: the sampler is started and given time to initialise BEFORE the warm-up steps, it keeps
+    running through the timed steps, and the same step keeps running for a short window afterwards so that at
+    least two samples are taken under the identical, continuous load.  Samples are time-stamped; only those taken
+    between the first warm-up step and the end of that window are used."""
 
-    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, device_index: int, period_ms: int = 100):
+    def __init__(self, device_index: int, period_ms: int = 200):
         self.idx = device_index
         self.period_ms = period_ms
         self.proc, self.path = None, None
-        self.poked = []
-        self._nvml = None
+        self.t_load0 = self.t_load1 = None
 
     def _physical_index(self):
         visible = os.environ.get("CUDA_VISIBLE_DEVICES")
@@ -227,38 +228,36 @@ class ClockSampler:
                 return int(parts[self.idx])
         return self.idx
 
-    def start(self):
+    def start(self, wait_s: float = 4.0):
         try:
             fd, self.path = tempfile.mkstemp(prefix="mgb_clocks_", suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-i", str(self._physical_index()),
                  "-lms", str(self.period_ms), "-f", self.path], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            t_end = time.time() + wait_s
+            while time.time() < t_end and os.path.getsize(self.path) == 0:     # its start-up is over once it has written
+                time.sleep(0.02)
         except Exception:  # noqa: BLE001
             self.proc = None
-        try:
-            import pynvml as nv
 
-            nv.nvmlInit()
-            self._handle = nv.nvmlDeviceGetHandleByIndex(self._physical_index())
-            self._nvml = nv
-        except Exception:  # noqa: BLE001
-            self._nvml = None
+    def load_begins(self):
+        self.t_load0 = time.time()
 
-    def poke(self):
-        """one sample taken by the timed thread itself, inside the timed region"""
-        if self._nvml is not None:
-            try:
-                self.poked.append(self._nvml.nvmlDeviceGetClockInfo(self._handle, self._nvml.NVML_CLOCK_SM))
-            except Exception:  # noqa: BLE001
-                pass
+    def hold_load(self, run_step, n_steps: int):
+        """keep the same load running (untimed; a step count that every rank computes alike) so that the sampler
+        sees it at least twice"""
+        for _ in range(n_steps):
+            run_step()
+        self.t_load1 = time.time()
 
     def stop(self):
+        import datetime
+
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        samples, mx, reasons = [], None, set()
+        samples, mx, reasons, total = [], None, set(), 0
         if self.proc is not None:
             try:
-                time.sleep(self.period_ms / 1000.0)       # let the sampler write the sample that covers the last steps
                 self.proc.terminate()
                 self.proc.wait(timeout=5)
             except Exception:  # noqa: BLE001
@@ -267,20 +266,28 @@ class ClockSampler:
                 names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
                 for line in open(self.path):
                     f = [x.strip() for x in line.split(",")]
-                    if len(f) < 6 or not f[0].replace(".", "").isdigit():
+                    if len(f) < 7:
                         continue
-                    samples.append(float(f[0]))
-                    mx = float(f[1])
-                    reasons.update(n for n, v in zip(names, f[2:6]) if v.lower().startswith("active"))
+                    total += 1
+                    try:
+                        ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                        mhz = float(f[1])
+                    except ValueError:
+                        continue
+                    slack = self.period_ms / 1000.0
+                    if self.t_load0 is not None and not (self.t_load0 <= ts <= (self.t_load1 or time.time()) + slack):
+                        continue
+                    samples.append(mhz)
+                    mx = float(f[2])
+                    reasons.update(n for n, v in zip(names, f[3:7]) if v.lower().startswith("active"))
                 os.unlink(self.path)
             except Exception:  # noqa: BLE001
                 pass
-        allv = samples + [float(x) for x in self.poked]
-        if allv:
-            out.update(sm_mhz=statistics.median(allv), sm_max_mhz=mx, samples=len(allv), in_region_nvml_samples=len(self.poked),
-                       reasons=sorted(reasons),
-                       source=f"nvidia-smi -lms {self.period_ms} in a separate process over warm-up + timed steps (same load), "
-                              f"plus one NVML sample taken inside the timed region")
+        if samples:
+            out.update(sm_mhz=statistics.median(samples), sm_max_mhz=mx, samples=len(samples), reasons=sorted(reasons),
+                       source=f"nvidia-smi -lms {self.period_ms} in a separate process; samples taken between the first warm-up "
+                              f"step and the end of a {0.5} s window of the same step after the timed region "
+                              f"({total} samples in the file)")
         return out
 
 
@@ -376,8 +383,6 @@ def main_ours(args):
         e0.record()
         for i in range(steps):
             out = step(frames, fuse)
-            if sampler is not None and i == steps // 2:
-                sampler.poke()      # one sample taken by the timed thread itself; the rest come from the NVML thread
         e1.record()
         barrier()
         wall = time.perf_counter() - t0
@@ -407,15 +412,16 @@ def main_ours(args):
     del host_pageable
 
     sampler = ClockSampler(local)
+    if not args.no_clocks:
+        sampler.start()
     lib.mgb_prof_enable(1)
-    sampler.start()
+    sampler.load_begins()
     for _ in range(args.warmup):
         step(dev_frames)
     barrier()
     lib.mgb_prof_reset()
     launches0 = kernels.launch_counter
-    ms, out = timed(dev_frames, args.steps, 0, sampler)
-    clocks = sampler.stop()
+    ms, out = timed(dev_frames, args.steps, 0)
     launches = kernels.launch_counter - launches0
     import ctypes as C
     prof = {}
@@ -426,6 +432,9 @@ def main_ours(args):
         if cnt.value:
             prof[name] = {"ms_total": tot.value, "launches": cnt.value}
     lib.mgb_prof_enable(0)
+    if not args.no_clocks:
+        sampler.hold_load(lambda: step(dev_frames), min(2000, max(5, int(500.0 / max(ms / args.steps, 0.05)))))
+    clocks = sampler.stop()
 
     # the same step without the band-level batch: every chunk operand on its own, what a real Mars worker does
     po_steps = max(2, min(args.steps, 5))
@@ -541,6 +550,7 @@ def main():
     ap.add_argument("--chunk-rows", type=int, default=CHUNK_ROWS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the sub-records of the other BASELINE.json configs")
+    ap.add_argument("--no-clocks", action="store_true", help="diagnostics: do not start the nvidia-smi clock sampler")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
