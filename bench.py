@@ -22,6 +22,7 @@ rank 0 with the NCCL exchange and the final agg stage runs there.  No other data
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import statistics
@@ -374,18 +375,28 @@ def main_ours(args):
             out = sess.execute_sharded_tree(r, comm=comm)
         return out
 
+    step_ms = {}
+
     def timed(frames, steps, warmup, sampler=None, fuse=True):
         for _ in range(warmup):
             step(frames, fuse)
+        # no collector pause inside the timed region: what the earlier phases of this process left behind (host
+        # frames, e2e runs) is collected now and parked; the session itself pauses the collector per graph
+        gc.collect()
+        gc.freeze()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record()
+        per_step = []
         for i in range(steps):
+            ts = time.perf_counter()
             out = step(frames, fuse)
+            per_step.append((time.perf_counter() - ts) * 1e3)
         e1.record()
         barrier()
         wall = time.perf_counter() - t0
+        step_ms[id(frames), fuse] = per_step
         ms = e0.elapsed_time(e1)
         # the result frame is fetched to the host inside every step, so device time ~ wall time; use the
         # larger of the two so that host-side work after the last kernel is not hidden
@@ -524,6 +535,9 @@ def main_ours(args):
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
                          "step_hbm_frac": (rows_rank * BYTES_PER_ROW / (ms / args.steps * 1e-3) / 1e9) / peak},
             "kernel_time_ms": prof,
+            "step_ms": {"min": min(step_ms[id(dev_frames), True]), "median": statistics.median(step_ms[id(dev_frames), True]),
+                        "max": max(step_ms[id(dev_frames), True]),
+                        "note": "host wall time of every timed step; value uses the whole region (device events / wall, max)"},
             "per_operand": {"value": total_rows * po_steps / (ms_po * 1e-3), "unit": "rows/s", "ms_per_step": ms_po / po_steps,
                             "steps": po_steps,
                             "note": "same step with the band-level batch off (MGB_FUSE=0): every chunk operand executed on "

@@ -76,6 +76,14 @@ int mgb_hash_keys(const int64_t* const* key_cols, int32_t n_keys, int64_t n_rows
 int mgb_partition_ids(const int64_t* const* key_cols, int32_t n_keys, int64_t n_rows, int64_t n_partitions,
                       int32_t* out_pid, void* stream);
 
+/* The same for shuffles keyed on COLUMNS of a frame -- `hash_dataframe_on(df, on=[...], size)` as used by the
+ * plain groupby (mars/dataframe/groupby/core.py:353-435, `on = by`), the merge shuffle
+ * (mars/dataframe/merge/merge.py:93-128) and drop_duplicates (mars/dataframe/base/drop_duplicates.py:150-168):
+ * pandas hashes the rows of `df[on]` with hash_pandas_object(index=False), which combines the per-column hashes
+ * also when there is ONE column (an Index of one level is hashed directly: mgb_partition_ids).              */
+int mgb_partition_ids_frame(const int64_t* const* key_cols, int32_t n_keys, int64_t n_rows, int64_t n_partitions,
+                            int32_t* out_pid, void* stream);
+
 /* sort=True shuffle (PSRS): range partition by pivots.  Replaces the label slices
  * `in_df.loc[pivots[i-1]:pivots[i]].drop(index=pivots[i-1])` of DataFrameGroupbySortShuffle._execute_map
  * (mars/dataframe/groupby/sort.py:113-135): out_pid = number of pivot tuples strictly smaller than the key

@@ -12,7 +12,7 @@ Layout (only what the path needs):
 """
 from .core import OperandStage, ExecutionError, execute  # noqa: F401
 from .dataframe import (DataFrame, DataFrameConcat, DataFrameGroupByAgg, DataFrameGroupByOperand,  # noqa: F401
-                        DataFrameGroupbyConcatPivot, DataFrameGroupbySortShuffle, DataFramePSRSGroupbySample,
+                        DataFrameGroupbyConcatPivot, DataFrameGroupbySortShuffle, DataFrameMergeAlign, DataFramePSRSGroupbySample,
                         DataFrameShuffleProxy, DataFrameToGPU, options)
 from .executors import register_gpu_executors  # noqa: F401
 from .session import Session, new_session, get_default_session  # noqa: F401

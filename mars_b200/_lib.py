@@ -66,6 +66,7 @@ SIGNATURES = {
     "mgb_device_info": (C.c_int, [C.POINTER(_i32), C.POINTER(_i32)]),
     "mgb_hash_keys": (C.c_int, [_pp, _i32, _i64, _vp, _vp]),
     "mgb_partition_ids": (C.c_int, [_pp, _i32, _i64, _i64, _vp, _vp]),
+    "mgb_partition_ids_frame": (C.c_int, [_pp, _i32, _i64, _i64, _vp, _vp]),
     "mgb_range_partition_ids": (C.c_int, [_pp, _i32, _i64, _pp, _i32, _vp, _vp]),
     "mgb_partition_scatter": (C.c_int, [_vp, _i64, _i32, _pp, _pp, _i32, _vp, _vp]),
     "mgb_hash_partition": (C.c_int, [_pp, _i32, _i64, _i32, _pp, _pp, _i32, _vp, _vp]),

@@ -94,6 +94,16 @@ __host__ __device__ __forceinline__ uint64_t mgb_hash_tuple(const int64_t* k) {
   return out;
 }
 
+// hash of a ROW of key columns with pandas' DataFrame semantics -- hash_pandas_object(df[on], index=False), what
+// hash_dataframe_on(df, on=[...]) uses for plain groupby / merge / drop_duplicates shuffles
+// (mars/dataframe/utils.py:88-100): the per-column hashes always go through combine_hash_arrays, also when there
+// is a single column (an Index, in contrast, is hashed directly: mgb_hash_tuple<1>).
+template <int NK>
+__host__ __device__ __forceinline__ uint64_t mgb_hash_frame_row(const int64_t* k) {
+  if (NK == 1) return (0x345678ULL ^ mgb_mix64((uint64_t)k[0])) * 1000003ULL + 97531ULL;
+  return mgb_hash_tuple<NK>(k);
+}
+
 // slot hash: decorrelated from `hash % R` (all keys of one reducer share hash % R).
 __host__ __device__ __forceinline__ uint64_t mgb_slot_hash(uint64_t h) { return h * 0x9e3779b97f4a7c15ULL; }
 

@@ -477,11 +477,15 @@ __global__ void __launch_bounds__(SM_THREADS, 1) k_merge_small(const SmallParams
     sorted[ucnt[u] + atomicAdd(&ufill[u], 1)] = it;
   }
   __syncthreads();
-  // 8 lanes per (output row, accumulator): contributions straight from L2, combined by shuffles
-  const int sl = lane & 7, pl = lane >> 3;
+  // L lanes per (output row, accumulator): contributions straight from L2, combined by shuffles.  L = 8 when the
+  // output rows have several contributions each (a tree merge of many pieces), L = 1 when there are about as many
+  // output rows as input rows (one band's partials with hundreds of groups: the loop is bound by the latency of
+  // its dependent loads, so every lane takes a pair of its own)
+  const int L = total >= 3 * nu ? 8 : 1;
+  const int sl = lane & (L - 1), pl = lane / L, ppw = 32 / L;
   constexpr int WARPS = SM_THREADS / 32;
-  for (int pair0 = 0; pair0 < nu * na; pair0 += WARPS * 4) {
-    const int pair = pair0 + warp * 4 + pl;
+  for (int pair0 = 0; pair0 < nu * na; pair0 += WARPS * ppw) {
+    const int pair = pair0 + warp * ppw + pl;
     const bool on = pair < nu * na;
     const int u = on ? pair / na : 0, a = on ? pair - u * na : 0;
     const int op = p.out.op[a];
@@ -493,13 +497,12 @@ __global__ void __launch_bounds__(SM_THREADS, 1) k_merge_small(const SmallParams
     if (kind == 4) v = f ? 0x7ff8000000000000ULL : 0x8000000000000000ULL;
     const int q1 = on ? ucnt[u + 1] : 0;
 #pragma unroll 4
-    for (int q = (on ? ucnt[u] : 0) + sl; q < q1; q += 8) {
+    for (int q = (on ? ucnt[u] : 0) + sl; q < q1; q += L) {
       const int it = sorted[q];
       const uint64_t* col = p.acc_ptrs[item_pc[it] * na + a];
       v = dense_combine(kind, f, v, ld_cg(col + item_r[it]));
     }
-#pragma unroll
-    for (int o = 1; o < 8; o <<= 1) v = dense_combine(kind, f, v, __shfl_xor_sync(0xffffffffu, v, o));
+    for (int o = 1; o < L; o <<= 1) v = dense_combine(kind, f, v, __shfl_xor_sync(0xffffffffu, v, o));
     if (on && sl == 0) p.out.acc[a][rank[u]] = v;
   }
   if (p.n_post > 0) {

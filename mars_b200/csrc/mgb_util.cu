@@ -238,7 +238,7 @@ struct KeyCols {
   const int64_t* k[MGB_MAX_KEYS];
 };
 
-template <int NK, bool WANT_PID>
+template <int NK, bool WANT_PID, bool FRAME = false>
 __global__ void __launch_bounds__(256) k_hash(KeyCols kc, int64_t n, uint64_t R, uint64_t* out_hash,
                                               int32_t* out_pid) {
   const bool pow2 = (R & (R - 1)) == 0;
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(256) k_hash(KeyCols kc, int64_t n, uint64_t R,
     int64_t k[NK];
 #pragma unroll
     for (int j = 0; j < NK; ++j) k[j] = (int64_t)mgb_ld_stream((const uint64_t*)kc.k[j] + i);
-    uint64_t h = mgb_hash_tuple<NK>(k);
+    uint64_t h = FRAME ? mgb_hash_frame_row<NK>(k) : mgb_hash_tuple<NK>(k);
     if (WANT_PID)
       out_pid[i] = (int32_t)(pow2 ? (h & (R - 1)) : (h % R));
     else
@@ -287,6 +287,29 @@ extern "C" int mgb_hash_keys(const int64_t* const* key_cols, int32_t n_keys, int
                              uint64_t* out_hash, void* stream) {
   MGB_REQUIRE(key_cols && (out_hash || n_rows == 0), MGB_ERR_INVALID, "null pointer");
   return launch_hash(key_cols, n_keys, n_rows, 1, out_hash, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int mgb_partition_ids_frame(const int64_t* const* key_cols, int32_t n_keys, int64_t n_rows,
+                                       int64_t n_partitions, int32_t* out_pid, void* stream) {
+  MGB_REQUIRE(key_cols && (out_pid || n_rows == 0), MGB_ERR_INVALID, "null pointer");
+  MGB_REQUIRE(n_partitions >= 1 && n_partitions <= 0x7fffffffLL, MGB_ERR_INVALID, "n_partitions=%lld out of range",
+              (long long)n_partitions);
+  MGB_REQUIRE(n_keys >= 1 && n_keys <= MGB_MAX_KEYS, MGB_ERR_UNSUPPORTED, "n_keys=%d outside [1,%d]", n_keys,
+              MGB_MAX_KEYS);
+  MGB_REQUIRE(n_rows >= 0, MGB_ERR_INVALID, "negative row count");
+  if (n_rows == 0) return MGB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  KeyCols kc;
+  for (int j = 0; j < MGB_MAX_KEYS; ++j) kc.k[j] = j < n_keys ? key_cols[j] : nullptr;
+  int64_t blocks = (n_rows + 255) / 256, cap = (int64_t)mgb_sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  MgbProfScope prof(MGB_K_HASH, st);
+  if (n_keys == 1)
+    k_hash<1, true, true><<<(unsigned)blocks, 256, 0, st>>>(kc, n_rows, (uint64_t)n_partitions, nullptr, out_pid);
+  else
+    k_hash<2, true, true><<<(unsigned)blocks, 256, 0, st>>>(kc, n_rows, (uint64_t)n_partitions, nullptr, out_pid);
+  MGB_CHECK_LAUNCH();
+  return MGB_OK;
 }
 
 extern "C" int mgb_partition_ids(const int64_t* const* key_cols, int32_t n_keys, int64_t n_rows,

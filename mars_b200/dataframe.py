@@ -96,6 +96,15 @@ class DataFrameGroupByOperand(MapReduceOperand):
                     group_keys=self.group_keys)
 
 
+class DataFrameMergeAlign(MapReduceOperand):
+    """hash shuffle of the two sides of a merge on their join columns (reference: merge/merge.py:60-147).
+
+    fields: shuffle_on, index_shuffle_size, mapper_id"""
+
+    def __init__(self, shuffle_on=None, index_shuffle_size=None, **kw):
+        super().__init__(shuffle_on=shuffle_on, index_shuffle_size=index_shuffle_size, **kw)
+
+
 class DataFrameGroupByAgg(Operand):
     """groupby aggregation operand with stages map / combine / agg (aggregation.py:164-1284)."""
 

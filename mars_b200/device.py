@@ -153,7 +153,7 @@ class ColumnSet:
 
 class DeviceFrame:
     __slots__ = ("index_names", "_index", "columns", "_data", "_n", "_pending", "_slot", "_home", "_src",
-                 "_ptrs_cache", "__weakref__")
+                 "_ptrs_cache", "range_start", "__weakref__")
 
     def __init__(self, index_names: Sequence[Any], index: Optional[Sequence[torch.Tensor]],
                  columns: Sequence[Any], data: Sequence[torch.Tensor], n_rows: Optional[int] = None,
@@ -167,6 +167,7 @@ class DeviceFrame:
         self._home = None            # device of lazily uploaded columns (set by from_pandas(lazy=True))
         self._src = None             # row range of scattered columns that has not been sliced yet (from_range)
         self._ptrs_cache = None      # (column selection, pointers) of the last band-level batch over this chunk
+        self.range_start = None      # raw chunk (index None): first label of its RangeIndex, when known
         if pending is not None:
             pending.attach(self)
             self._n = None
@@ -197,6 +198,7 @@ class DeviceFrame:
         f._slot = slot
         f._home = None
         f._ptrs_cache = None
+        f.range_start = None
         f._src = (src, k0, k1, d0, d1, a, b)
         if pending is not None:      # rows [0, capacity) of a speculative result: the size is still on the device
             pending.attach(f)
@@ -426,6 +428,8 @@ class DeviceFrame:
                     raise NotImplementedError(f"group key dtype {lv.dtype}: int64 keys only")
                 index.append(_to_device(lv, device))
         out = cls(names, index, cols, data, len(df))
+        if index is None and isinstance(df.index, pd.RangeIndex) and df.index.step == 1:
+            out.range_start = int(df.index.start)
         if lazy:
             out._home = torch.device(device) if not isinstance(device, torch.device) else device
         return out
@@ -435,6 +439,8 @@ class DeviceFrame:
         df = pd.DataFrame(data)
         df.columns = pd.Index(self.columns) if not (self.columns and isinstance(self.columns[0], tuple)) \
             else pd.MultiIndex.from_tuples(self.columns)
+        if self.index is None and self.range_start is not None:
+            df.index = pd.RangeIndex(self.range_start, self.range_start + len(df))
         if self.index is not None:
             arrays = [t.cpu().numpy() for t in self.index]
             if len(arrays) == 1:

@@ -1142,12 +1142,89 @@ def execute_groupby_agg(ctx, op):
 # ----------------------------------------------------------------------------------------------------
 # DataFrameGroupByOperand: hash shuffle
 # ----------------------------------------------------------------------------------------------------
+def hash_split_frame(frame: DeviceFrame, on: Sequence[Any], n_partitions: int) -> List[DeviceFrame]:
+    """`hash_dataframe_on(df, on=[...], size)` + `df.iloc[filter]` per reducer (mars/dataframe/utils.py:77-101)
+    for a device-resident frame: the rows are hashed on the `on` COLUMNS with pandas' DataFrame semantics
+    (mgb_partition_ids_frame) and split stably; every block keeps the original row labels as its index.  Shared
+    by the hash-partition consumers outside the agg path: plain groupby (groupby/core.py:353-435 with `by`),
+    the merge shuffle (merge/merge.py:93-128)."""
+    on = list(on)
+    _check_key_count(len(on))
+    for c in on:
+        if c not in frame.columns:
+            raise NotImplementedError(f"shuffle column {c!r} is not a data column of the chunk")
+    keys = [frame.column(c) for c in on]
+    for c, t in zip(on, keys):
+        if t.dtype != torch.int64:
+            raise NotImplementedError(f"shuffle column {c!r} has dtype {t.dtype}: int64 columns only")
+    n = len(frame)
+    if frame.index is None:
+        if frame.range_start is None:
+            raise NotImplementedError("the chunk's row labels are unknown")
+        index = [torch.arange(frame.range_start, frame.range_start + n, dtype=torch.int64, device=frame.device)]
+        names = [None]
+    else:
+        index, names = list(frame.index), list(frame.index_names)
+    cols = index + list(frame.data)
+    if n == 0:
+        outs, offsets = cols, [0] * (n_partitions + 1)
+    else:
+        pid = _kernels.partition_ids_frame(keys, n_partitions)
+        outs, offsets = _kernels.partition_scatter(pid, n_partitions, cols)
+    nk = len(index)
+    src = ColumnSet(outs)
+    return [DeviceFrame.from_range(names, frame.columns, src, 0, nk, nk, len(cols), offsets[r], offsets[r + 1])
+            for r in range(n_partitions)]
+
+
+def _execute_by_shuffle_map(ctx, op, by):
+    """plain groupby (apply / transform follow on the reference executors): shuffle of the raw chunk on its `by`
+    columns (reference: execute_map with on = by, groupby/core.py:353-435)"""
+    if callable(by) or any(not isinstance(b, (str, int, tuple)) for b in by):
+        raise NotImplementedError("`by` must be column labels on the GPU path")
+    chunk = op.outputs[0]
+    value = ctx[op.inputs[0].key]
+    if isinstance(value, tuple):
+        raise NotImplementedError("`by` shuffles of partial tuples are outside the GPU path")
+    frame = _as_device_frame(value)
+    if getattr(op, "level", None) is not None:
+        raise NotImplementedError("level= shuffles are outside the GPU path")
+    blocks = hash_split_frame(frame, by, int(op.shuffle_size))
+    mapper_index = ctx.get_current_chunk().index
+    for r, block in enumerate(blocks):
+        reducer_index = (r, chunk.index[1]) if getattr(op, "is_dataframe_obj", True) else (r,)
+        ctx[chunk.key, reducer_index] = (mapper_index, block)
+
+
+def execute_merge_align(ctx, op):
+    """DataFrameMergeAlign (mars/dataframe/merge/merge.py:93-147): map = hash split of a chunk on its
+    `shuffle_on` columns, one block per reducer incl. empty ones, payload (mapper_id, chunk index, block);
+    reduce = row concat of the blocks of one side, ordered by mapper row."""
+    st = _stage(op)
+    chunk = op.outputs[0]
+    if st == "map":
+        on = op.shuffle_on
+        if on is None:
+            raise NotImplementedError("merge shuffles on the index stay on the reference executor")
+        on = list(on) if isinstance(on, (list, tuple)) else [on]
+        frame = _as_device_frame(ctx[op.inputs[0].key])
+        blocks = hash_split_frame(frame, on, int(op.index_shuffle_size))
+        idx = ctx.get_current_chunk().index
+        for r, block in enumerate(blocks):
+            ctx[chunk.key, (r, chunk.index[1])] = (op.mapper_id, idx, block)
+        return
+    for i, out in enumerate(op.outputs):
+        got = {pidx: data for mapper_id, pidx, data in op.iter_mapper_data(ctx, skip_none=True) if mapper_id == i}
+        res = [got[k] for k in sorted(got) if got[k] is not None]
+        ctx[out.key] = _concat_frames([_as_device_frame(v, index_as_keys=True) for v in res])
+
+
 def _execute_shuffle_map(ctx, op):
     """stage=map: partition id = pandas hash of the group keys % shuffle_size; one block per reducer,
     empty ones included (reference: execute_map, groupby/core.py:353-435; contract shuffle.py:124-130)."""
     by = getattr(op, "by", None)
     if isinstance(by, (list, tuple)) or callable(by):
-        raise NotImplementedError("shuffling on `by` columns (plain groupby) is outside the agg path")
+        return _execute_by_shuffle_map(ctx, op, by)
     chunk = op.outputs[0]
     value = ctx[op.inputs[0].key]
     is_tuple = isinstance(value, tuple)
@@ -1393,3 +1470,4 @@ def register_gpu_executors():
     md.DataFramePSRSGroupbySample.register_executor(execute_psrs_sample)
     md.DataFrameGroupbyConcatPivot.register_executor(execute_concat_pivot)
     md.DataFrameGroupbySortShuffle.register_executor(execute_sort_shuffle)
+    md.DataFrameMergeAlign.register_executor(execute_merge_align)

@@ -87,6 +87,18 @@ def partition_ids(keys: Sequence[torch.Tensor], n_partitions: int) -> torch.Tens
     return out
 
 
+def partition_ids_frame(keys: Sequence[torch.Tensor], n_partitions: int) -> torch.Tensor:
+    """int32 reducer index of every ROW of the given key columns, pandas DataFrame hashing semantics
+    (`hash_dataframe_on(df, on=[...], size)`: mgb_partition_ids_frame)."""
+    lib = _lib.load()
+    keys = [_req(k, f"key {i}", (torch.int64,)) for i, k in enumerate(keys)]
+    n = keys[0].numel()
+    out = torch.empty(n, dtype=torch.int32, device=keys[0].device)
+    check(lib.mgb_partition_ids_frame(_ptrs(keys), len(keys), n, int(n_partitions), out.data_ptr(), _stream()))
+    _count(1 if n else 0)
+    return out
+
+
 def range_partition_ids(keys: Sequence[torch.Tensor], pivots: Sequence[torch.Tensor]) -> torch.Tensor:
     """int32 range partition of every key tuple: number of pivot tuples strictly smaller than it
     (mgb_range_partition_ids; PSRS shuffle of groupby(sort=True))."""

@@ -95,6 +95,7 @@ def register_on_mars(gpu_only: bool = True):
     from mars.dataframe.groupby.sort import (DataFrameGroupbyConcatPivot, DataFrameGroupbySortShuffle,
                                              DataFramePSRSGroupbySample)
     from mars.dataframe.merge.concat import DataFrameConcat
+    from mars.dataframe.merge.merge import DataFrameMergeAlign
 
     # result chunks go through Mars's storage service, which expects pandas (or cudf) frames: hand out pandas
     # until a GPU StorageBackend holds DeviceResult chunks
@@ -109,6 +110,7 @@ def register_on_mars(gpu_only: bool = True):
         (DataFrameConcat, executors.execute_concat),
         (DataFrameToGPU, executors.execute_to_gpu),
         (DataFrameToCPU, executors.execute_to_cpu),
+        (DataFrameMergeAlign, executors.execute_merge_align),
     ]
     for cls, fn in table:
         cls.register_executor(_with_reference_fallback(cls, fn, gpu_only=gpu_only))
@@ -124,8 +126,10 @@ def unregister_on_mars():
                                              DataFramePSRSGroupbySample)
     from mars.dataframe.merge.concat import DataFrameConcat
 
+    from mars.dataframe.merge.merge import DataFrameMergeAlign
+
     for cls in (DataFrameGroupByAgg, DataFrameGroupByOperand, DataFrameConcat, DataFrameToGPU, DataFrameToCPU,
-                DataFramePSRSGroupbySample, DataFrameGroupbyConcatPivot, DataFrameGroupbySortShuffle):
+                DataFramePSRSGroupbySample, DataFrameGroupbyConcatPivot, DataFrameGroupbySortShuffle, DataFrameMergeAlign):
         cls.unregister_executor()
 
 

@@ -80,6 +80,25 @@ def partition_ids(key_cols: Sequence[np.ndarray], n_partitions: int) -> np.ndarr
     return (hash_keys(key_cols) % np.uint64(n_partitions)).astype(np.int64)
 
 
+def hash_frame_rows(cols: Sequence[np.ndarray]) -> np.ndarray:
+    """uint64 hash of every ROW of `df[on]` -- pd.util.hash_pandas_object(df[on], index=False, categorize=False) as
+    called by hash_dataframe_on(df, on=[...]) (mars/dataframe/utils.py:88-99): the per-column hashes are always
+    combined (combine_hash_arrays), also for a single column."""
+    cols = [np.asarray(c, dtype=np.int64) for c in cols]
+    if len(cols) > 1:
+        return hash_keys(cols)
+    with np.errstate(over="ignore"):
+        return (np.uint64(0x345678) ^ mix64(cols[0])) * np.uint64(1000003) + np.uint64(97531)
+
+
+def hash_dataframe_on_columns(df: pd.DataFrame, on: Sequence[Any], size: int) -> List[np.ndarray]:
+    """hash_dataframe_on(df, on=[...], size) restated: ascending row positions per reducer"""
+    pid = (hash_frame_rows([df[c].to_numpy() for c in on]) % np.uint64(size)).astype(np.int64)
+    order = np.argsort(pid, kind="stable")
+    bounds = np.searchsorted(pid[order], np.arange(size + 1))
+    return [order[bounds[i]:bounds[i + 1]] for i in range(size)]
+
+
 def hash_dataframe_on_index(index: pd.Index, size: int) -> List[np.ndarray]:
     """hash_dataframe_on(df, on=None, size) restated: ascending row positions per reducer."""
     if isinstance(index, pd.MultiIndex):

@@ -329,3 +329,9 @@ def hash_partition(keys, n_partitions, cols):
     out = partition_scatter(pid, n_partitions, cols)
     calls.pop()
     return out
+
+
+def partition_ids_frame(keys, n_partitions):
+    calls.append("partition_ids_frame")
+    h = orc.hash_frame_rows([_np(k) for k in keys])
+    return torch.from_numpy((h % np.uint64(n_partitions)).astype(np.int32))
