@@ -97,9 +97,18 @@ def register_on_mars(gpu_only: bool = True):
     from mars.dataframe.merge.concat import DataFrameConcat
     from mars.dataframe.merge.merge import DataFrameMergeAlign
 
-    # result chunks go through Mars's storage service, which expects pandas (or cudf) frames: hand out pandas
-    # until a GPU StorageBackend holds DeviceResult chunks
-    executors._DEVICE_RESULTS = False
+    # the GPU-level chunk store + the serializer of the device types: partial tuples (DeviceFrame / PiecewiseFrame)
+    # cross subtask boundaries by handle and worker boundaries through the reference's own transfer code
+    from . import storage
+
+    storage.register_on_mars()
+    # FINAL result chunks are handed out as pandas by default: the client that calls fetch() has no GPU, and
+    # chunk metas are computed from the frame (subtask/utils.py:62-68).  MGB_MARS_DEVICE_RESULTS=1 keeps large
+    # result chunks in HBM as DeviceResult (frame-like; `.to_pandas()` reads it back), as the reference's GPU mode
+    # does with cudf frames (test_groupby_execution.py:788-793).
+    import os
+
+    executors._DEVICE_RESULTS = os.environ.get("MGB_MARS_DEVICE_RESULTS", "0") not in ("0", "")
 
     table = [
         (DataFramePSRSGroupbySample, executors.execute_psrs_sample),
