@@ -317,11 +317,17 @@ class DeviceChunkStore:
 # ----------------------------------------------------------------------------------------------------
 # the same store behind the reference's own interfaces
 # ----------------------------------------------------------------------------------------------------
+_mars_backend = None
+
+
 def register_on_mars():
     """Registers (i) ``MgbGpuStorage``, a ``mars.storage.base.StorageBackend`` at ``StorageLevel.GPU`` that holds
     the GPU executors' values by handle, under the backend name "mgb_gpu"; (ii) a ``Serializer`` for the device
     types, so that ``mars.serialization.serialize`` / ``AioSerializer`` -- what the reference's storage handler and
     transfer code call -- can move them between processes.  Returns the backend class."""
+    global _mars_backend
+    if _mars_backend is not None:       # idempotent: the serializer registry asserts one class per serializer id
+        return _mars_backend
     from mars.serialization.core import Serializer, buffered
     from mars.serialization import serialize as mars_serialize, deserialize as mars_deserialize
     from mars.storage.base import ObjectInfo as MarsObjectInfo, StorageBackend, StorageLevel, register_storage_backend
@@ -442,4 +448,5 @@ def register_on_mars():
             return await self._store.list()
 
     del mars_serialize, mars_deserialize
+    _mars_backend = MgbGpuStorage
     return MgbGpuStorage
