@@ -202,6 +202,42 @@ int mgb_preagg_dense_batch_async(const mgb_agg_spec* spec, int32_t n_chunks, con
                                  const void* const* const* chunk_val_cols, int64_t* const* out_key_cols,
                                  void* const* out_acc_cols, int64_t out_capacity, int64_t* out_n_dev, void* stream);
 
+/* Fused pre-path: TPC-H Q1 is filter + two derived columns + groupby
+ * (benchmarks/tpch/run_queries.py:110-163); run operator by operator that is three extra passes over lineitem
+ * (mask + compaction, `price * (1 - discount)`, `... * (1 + tax)`) before the map stage reads it again.  Here the
+ * band-level batch kernel loads prog->n_phys PHYSICAL columns per row (chunk_phys_cols[i][0 .. n_phys)), drops
+ * the rows that fail `physical column filter_col <op> constant` (op: 0 <=, 1 <, 2 >=, 3 >, 4 ==, 5 !=; filter_col
+ * -1: no filter) and aggregates LOGICAL columns: logical column c is physical column c (n_factors[c] == 0) or the
+ * left-to-right product of n_factors[c] <= 3 terms alpha + beta * physical column `col`, every operation rounded
+ * on its own like the reference's chain of pandas operators.  Column indices count the loaded columns of the
+ * spec (its float64 value columns in spec order; int64 columns that are only counted take no index).  Only the
+ * sum / mean / count shapes are fused (*out_n_dev = -1 otherwise: the caller materialises the columns).      */
+typedef struct {
+  int32_t col;
+  double alpha, beta;
+} mgb_affine_factor;
+typedef struct {
+  int32_t n_phys;
+  int32_t n_factors[8];
+  mgb_affine_factor factors[8][3];
+  int32_t filter_col, filter_op, filter_dtype;   /* filter_dtype: mgb_dtype of the filter column */
+  int64_t filter_i64;
+  double filter_f64;
+} mgb_row_program;
+int mgb_preagg_dense_batch_fused_async(const mgb_agg_spec* spec, const mgb_row_program* prog, int32_t n_chunks,
+                                       const int64_t* chunk_rows, const int64_t* const* const* chunk_key_cols,
+                                       const void* const* const* chunk_phys_cols, int64_t* const* out_key_cols,
+                                       void* const* out_acc_cols, int64_t out_capacity, int64_t* out_n_dev,
+                                       void* stream);
+
+/* Elementwise evaluation of one such derived column (the unfused form: materialises it), and the row filter as a
+ * stable compaction of n_cols 8-byte columns (*out_n_dev = rows kept; output columns need capacity n_rows).   */
+int mgb_eval_product(const void* const* phys_cols, const mgb_affine_factor* factors, int32_t n_factors, double* out,
+                     int64_t n_rows, void* stream);
+int mgb_filter_rows(const void* filter_col, int32_t filter_dtype, int32_t filter_op, int64_t filter_i64,
+                    double filter_f64, const void* const* in_cols, void* const* out_cols, int32_t n_cols,
+                    int64_t n_rows, int64_t* out_n_host, void* stream);
+
 /* The same band-level batch for the MID-cardinality sum / mean / count shapes (BASELINE.json config 1: 1000
  * keys): more distinct key tuples than the dense kernel keeps per CTA, few enough for one shared-memory table
  * per CTA -- float64 columns with SUM and / or COUNT (int64 columns that are only counted are not read), at

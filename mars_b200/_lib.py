@@ -47,6 +47,16 @@ class AggSpec(C.Structure):
     ]
 
 
+class AffineFactor(C.Structure):
+    _fields_ = [("col", C.c_int32), ("alpha", C.c_double), ("beta", C.c_double)]
+
+
+class RowProgram(C.Structure):
+    _fields_ = [("n_phys", C.c_int32), ("n_factors", C.c_int32 * 8), ("factors", (AffineFactor * 3) * 8),
+                ("filter_col", C.c_int32), ("filter_op", C.c_int32), ("filter_dtype", C.c_int32),
+                ("filter_i64", C.c_int64), ("filter_f64", C.c_double)]
+
+
 class PostStep(C.Structure):
     _fields_ = [("kind", C.c_int32), ("a0", C.c_int32), ("a1", C.c_int32), ("a2", C.c_int32), ("ddof", C.c_int32)]
 
@@ -88,6 +98,10 @@ SIGNATURES = {
     "mgb_dense_batch_max": (C.c_int, [C.POINTER(_i32)]),
     "mgb_preagg_dense_batch_async": (C.c_int, [C.POINTER(AggSpec), _i32, C.POINTER(_i64), C.POINTER(_pp), C.POINTER(_pp),
                                                _pp, _pp, _i64, _vp, _vp]),
+    "mgb_preagg_dense_batch_fused_async": (C.c_int, [C.POINTER(AggSpec), C.POINTER(RowProgram), _i32, C.POINTER(_i64),
+                                                     C.POINTER(_pp), C.POINTER(_pp), _pp, _pp, _i64, _vp, _vp]),
+    "mgb_eval_product": (C.c_int, [_pp, C.POINTER(AffineFactor), _i32, _vp, _i64, _vp]),
+    "mgb_filter_rows": (C.c_int, [_vp, _i32, _i32, _i64, C.c_double, _pp, _pp, _i32, _i64, C.POINTER(_i64), _vp]),
     "mgb_mid_capacity": (C.c_int, [C.POINTER(_i64)]),
     "mgb_preagg_mid_batch_async": (C.c_int, [C.POINTER(AggSpec), _i32, C.POINTER(_i64), C.POINTER(_pp), C.POINTER(_pp),
                                              _pp, _pp, _i64, _vp, _vp]),

@@ -74,11 +74,10 @@ extern "C" int mgb_dense_batch_max(int32_t* out_chunks) {
   return MGB_OK;
 }
 
-extern "C" int mgb_preagg_dense_batch_async(const mgb_agg_spec* spec, int32_t n_chunks, const int64_t* chunk_rows,
-                                            const int64_t* const* const* chunk_key_cols,
-                                            const void* const* const* chunk_val_cols, int64_t* const* out_key_cols,
-                                            void* const* out_acc_cols, int64_t out_capacity, int64_t* out_n_dev,
-                                            void* stream) {
+static int dense_batch_impl(const mgb_agg_spec* spec, const mgb_row_program* prog, int32_t n_chunks,
+                            const int64_t* chunk_rows, const int64_t* const* const* chunk_key_cols,
+                            const void* const* const* chunk_val_cols, int64_t* const* out_key_cols,
+                            void* const* out_acc_cols, int64_t out_capacity, int64_t* out_n_dev, void* stream) {
   MGB_REQUIRE(spec && chunk_rows && chunk_key_cols && chunk_val_cols && out_key_cols && out_acc_cols && out_n_dev,
               MGB_ERR_INVALID, "null pointer");
   cudaStream_t st = (cudaStream_t)stream;
@@ -110,6 +109,35 @@ extern "C" int mgb_preagg_dense_batch_async(const mgb_agg_spec* spec, int32_t n_
     ++ncol;
   }
   if (ncol == 0) return dense_set_count(out_n_dev, -1, st);   // only counts of int64 columns: general path
+  if (prog) {
+    // fused pre-path: sum / mean / count shapes over float64 logical columns; the program's column indices count
+    // the LOADED columns (the spec's value columns minus int64 columns that are only counted, in spec order)
+    const uint32_t all = (1u << ncol) - 1u;
+    if (allops || p.f64_mask != all || p.op_mask[MGB_SUM] != all) return dense_set_count(out_n_dev, -1, st);
+    MGB_REQUIRE(prog->n_phys >= 1 && prog->n_phys <= ncol, MGB_ERR_UNSUPPORTED,
+                "row program: %d physical columns for %d logical ones", prog->n_phys, ncol);
+    p.prog.n_phys = prog->n_phys;
+    p.prog.filter_col = prog->filter_col;
+    MGB_REQUIRE(prog->filter_col < prog->n_phys && prog->filter_op >= 0 && prog->filter_op <= 5, MGB_ERR_INVALID,
+                "bad row filter");
+    p.prog.filter_op = prog->filter_op;
+    p.prog.filter_f64 = prog->filter_dtype == MGB_F64;
+    p.prog.filter_i = prog->filter_i64;
+    p.prog.filter_d = prog->filter_f64;
+    for (int c = 0; c < ncol; ++c) {
+      const int nf = prog->n_factors[c];
+      MGB_REQUIRE(nf >= 0 && nf <= 3, MGB_ERR_INVALID, "logical column %d: %d factors", c, nf);
+      MGB_REQUIRE(nf > 0 || c < prog->n_phys, MGB_ERR_INVALID, "logical column %d has no physical column", c);
+      p.prog.nf[c] = (signed char)nf;
+      for (int f = 0; f < nf; ++f) {
+        MGB_REQUIRE(prog->factors[c][f].col >= 0 && prog->factors[c][f].col < prog->n_phys, MGB_ERR_INVALID,
+                    "logical column %d reads physical column %d of %d", c, prog->factors[c][f].col, prog->n_phys);
+        p.prog.fcol[c][f] = (signed char)prog->factors[c][f].col;
+        p.prog.falpha[c][f] = prog->factors[c][f].alpha;
+        p.prog.fbeta[c][f] = prog->factors[c][f].beta;
+      }
+    }
+  }
   // the batch: non-empty chunks as one virtual sequence of 1024-row tiles
   const long long tile_rows = 1024;
   DenseBatch bt;
@@ -124,10 +152,17 @@ extern "C" int mgb_preagg_dense_batch_async(const mgb_agg_spec* spec, int32_t n_
       MGB_REQUIRE(chunk_key_cols[i][j], MGB_ERR_INVALID, "null key column %d of chunk %d", j, i);
       bt.ptr[q][j] = (const uint64_t*)chunk_key_cols[i][j];
     }
-    for (int c = 0; c < spec->n_vals; ++c) {
-      if (loaded_of[c] < 0) continue;
-      MGB_REQUIRE(chunk_val_cols[i][c], MGB_ERR_INVALID, "null value column %d of chunk %d", c, i);
-      bt.ptr[q][MGB_MAX_KEYS + loaded_of[c]] = (const uint64_t*)chunk_val_cols[i][c];
+    if (prog) {      // physical columns of the row program, in program order
+      for (int j = 0; j < prog->n_phys; ++j) {
+        MGB_REQUIRE(chunk_val_cols[i][j], MGB_ERR_INVALID, "null physical column %d of chunk %d", j, i);
+        bt.ptr[q][MGB_MAX_KEYS + j] = (const uint64_t*)chunk_val_cols[i][j];
+      }
+    } else {
+      for (int c = 0; c < spec->n_vals; ++c) {
+        if (loaded_of[c] < 0) continue;
+        MGB_REQUIRE(chunk_val_cols[i][c], MGB_ERR_INVALID, "null value column %d of chunk %d", c, i);
+        bt.ptr[q][MGB_MAX_KEYS + loaded_of[c]] = (const uint64_t*)chunk_val_cols[i][c];
+      }
     }
     bt.n[q] = chunk_rows[i];
     tiles += chunk_rows[i] / tile_rows;
@@ -250,6 +285,26 @@ extern "C" int mgb_preagg_dense_batch_async(const mgb_agg_spec* spec, int32_t n_
     cudaFree(dbg);
   }
   return MGB_OK;
+}
+
+extern "C" int mgb_preagg_dense_batch_async(const mgb_agg_spec* spec, int32_t n_chunks, const int64_t* chunk_rows,
+                                            const int64_t* const* const* chunk_key_cols,
+                                            const void* const* const* chunk_val_cols, int64_t* const* out_key_cols,
+                                            void* const* out_acc_cols, int64_t out_capacity, int64_t* out_n_dev,
+                                            void* stream) {
+  return dense_batch_impl(spec, nullptr, n_chunks, chunk_rows, chunk_key_cols, chunk_val_cols, out_key_cols,
+                          out_acc_cols, out_capacity, out_n_dev, stream);
+}
+
+extern "C" int mgb_preagg_dense_batch_fused_async(const mgb_agg_spec* spec, const mgb_row_program* prog,
+                                                  int32_t n_chunks, const int64_t* chunk_rows,
+                                                  const int64_t* const* const* chunk_key_cols,
+                                                  const void* const* const* chunk_phys_cols,
+                                                  int64_t* const* out_key_cols, void* const* out_acc_cols,
+                                                  int64_t out_capacity, int64_t* out_n_dev, void* stream) {
+  MGB_REQUIRE(prog, MGB_ERR_INVALID, "null row program");
+  return dense_batch_impl(spec, prog, n_chunks, chunk_rows, chunk_key_cols, chunk_phys_cols, out_key_cols,
+                          out_acc_cols, out_capacity, out_n_dev, stream);
 }
 
 extern "C" int mgb_preagg_dense_async(const mgb_agg_spec* spec, const int64_t* const* key_cols,

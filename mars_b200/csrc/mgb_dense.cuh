@@ -141,7 +141,26 @@ struct DenseBatch {
   const uint64_t* ptr[DN_MAX_CHUNKS][DN_PTRS];    // key columns [0, NK), then the loaded value columns
 };
 
+// Row program of the fused pre-path (TPC-H Q1: filter + derived columns + groupby in one pass over lineitem,
+// benchmarks/tpch/run_queries.py:110-163): the kernel loads n_phys PHYSICAL columns per row, drops the rows a
+// comparison rejects, and computes the LOGICAL value columns it aggregates -- logical column c is physical column
+// c itself (nf[c] == 0) or a left-to-right product of up to three affine factors alpha + beta * physical column,
+// each operation rounded on its own (no FMA), which is what the reference's chain of pandas operators computes
+// (`price * (1 - discount) * (1 + tax)`).
+struct DenseProgram {
+  int n_phys;               // physical columns loaded per row (<= NV); 0: no program
+  int filter_col;           // physical column the row filter reads, -1: none
+  int filter_op;            // 0 <=, 1 <, 2 >=, 3 >, 4 ==, 5 !=
+  int filter_f64;           // compare as float64 (else int64)
+  long long filter_i;
+  double filter_d;
+  signed char nf[8];
+  signed char fcol[8][3];
+  double falpha[8][3], fbeta[8][3];
+};
+
 struct DenseParams {
+  DenseProgram prog;
   int GC;                   // groups per CTA (accumulator capacity); group ids are dense, in insertion order
   int stride_g;             // 32-bit words per (warp, group) accumulator block
   int off_nan, off_sum, off_sumsq, off_min, off_max;   // word offsets of column 0's slot inside a block
@@ -268,7 +287,8 @@ __device__ __forceinline__ uint64_t dense_combine(int kind, bool f, uint64_t v, 
 
 // PLAIN: every loaded column is float64 and carries SUM, no SUMSQ / MIN / MAX (sum / mean / count shapes):
 // straight-line DADD updates.  Otherwise the generic body tests the per-column masks (warp-uniform branches).
-template <int NK, int NV, bool PLAIN, int THREADS>
+// PROG (PLAIN shapes only): the row program of DenseProgram runs between the loads and the group update.
+template <int NK, int NV, bool PLAIN, int THREADS, bool PROG = false>
 __global__ void __launch_bounds__(THREADS, 1) k_preagg_dense(const DenseParams p, const DenseBatch bt) {
   constexpr int DN_WARPS = THREADS / 32;
   constexpr int DN_R = 1024 / THREADS;   // rows per thread per tile: a tile is always 1024 rows
@@ -331,6 +351,53 @@ __global__ void __launch_bounds__(THREADS, 1) k_preagg_dense(const DenseParams p
   bool failed = false;
 
   // one row: group lookup, then lane-private accumulator updates
+  // row program: physical values in x[] -> logical values in x[]; returns whether the row passes the filter.
+  // Operand selection is a chain of warp-uniform predicated moves (registers cannot be indexed dynamically).
+  auto apply_program = [&](uint64_t* x) -> bool {
+    double ph[NV];
+#pragma unroll
+    for (int c = 0; c < NV; ++c) ph[c] = __longlong_as_double((long long)x[c]);
+    bool keep = true;
+    if (p.prog.filter_col >= 0) {
+      uint64_t raw = 0;
+#pragma unroll
+      for (int c = 0; c < NV; ++c)
+        if (p.prog.filter_col == c) raw = x[c];
+      int cmp;   // -1, 0, 1 (NaN compares as "unordered": every comparison but != fails, like pandas)
+      bool unordered = false;
+      if (p.prog.filter_f64) {
+        const double v = __longlong_as_double((long long)raw);
+        unordered = v != v;
+        cmp = v < p.prog.filter_d ? -1 : (v > p.prog.filter_d ? 1 : 0);
+      } else {
+        const long long v = (long long)raw;
+        cmp = v < p.prog.filter_i ? -1 : (v > p.prog.filter_i ? 1 : 0);
+      }
+      const int op = p.prog.filter_op;
+      keep = op == 0 ? cmp <= 0 : op == 1 ? cmp < 0 : op == 2 ? cmp >= 0 : op == 3 ? cmp > 0 : op == 4 ? cmp == 0 : cmp != 0;
+      if (unordered) keep = op == 5;
+    }
+#pragma unroll
+    for (int c = 0; c < NV; ++c) {
+      const int nf = p.prog.nf[c];
+      if (nf == 0) continue;            // logical column c == physical column c
+      double v = 1.0;
+#pragma unroll
+      for (int f = 0; f < 3; ++f) {
+        if (f < nf) {
+          double o = 0.0;
+#pragma unroll
+          for (int j = 0; j < NV; ++j)
+            if (p.prog.fcol[c][f] == j) o = ph[j];
+          const double term = __dadd_rn(p.prog.falpha[c][f], __dmul_rn(p.prog.fbeta[c][f], o));
+          v = f == 0 ? term : __dmul_rn(v, term);
+        }
+      }
+      x[c] = (uint64_t)__double_as_longlong(v);
+    }
+    return keep;
+  };
+
   // group id of one row (all 32 lanes together); sets `failed` when the CTA would need more than GC groups
   auto find_group = [&](const uint64_t* k, const bool live) -> int {
     const int s = (int)(dense_hash<NK>(k) >> 26);
@@ -487,12 +554,26 @@ __global__ void __launch_bounds__(THREADS, 1) k_preagg_dense(const DenseParams p
     }
 #pragma unroll
     for (int c = 0; c < NV; ++c) {
+      if (PROG && c >= p.prog.n_phys) {
+#pragma unroll
+        for (int r = 0; r < DN_R; ++r) xb[buf][r][c] = 0;
+        continue;
+      }
       const uint64_t* b = pc[c] + off;
 #pragma unroll
       for (int r = 0; r < DN_R; ++r) xb[buf][r][c] = __ldcs((const unsigned long long*)b + r * DN_THREADS);
     }
   };
   auto process_tile = [&](int buf) {
+    if (PROG) {     // filter + derived columns first; rows the filter drops take no part in the update
+#pragma unroll
+      for (int r = 0; r < DN_R; ++r) {
+        if (failed) return;
+        const bool keep = apply_program(xb[buf][r]);
+        process_row(kb[buf][r], xb[buf][r], keep);
+      }
+      return;
+    }
     if (PLAIN) {
 #pragma unroll
       for (int r = 0; r < DN_R; r += 2) {
@@ -542,8 +623,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_preagg_dense(const DenseParams p
 #pragma unroll
       for (int j = 0; j < NK; ++j) k[j] = live ? cp[j][i] : 0;
 #pragma unroll
-      for (int cl = 0; cl < NV; ++cl) x[cl] = live ? cp[MGB_MAX_KEYS + cl][i] : 0;
-      process_row(k, x, live);
+      for (int cl = 0; cl < NV; ++cl) x[cl] = (live && !(PROG && cl >= p.prog.n_phys)) ? cp[MGB_MAX_KEYS + cl][i] : 0;
+      bool keep = live;
+      if (PROG) keep = apply_program(x) && live;
+      process_row(k, x, keep);
     }
   }
   if (failed) {
@@ -868,7 +951,29 @@ int mgb_dense_launch(const DenseParams& p, const DenseBatch& bt, int ncol, bool 
       default: LAUNCH(8, PL); break;    \
     }                                   \
   } while (0)
-  if (plain) PICK_NV(true); else PICK_NV(false);
+  if (p.prog.n_phys > 0) {
+#define LAUNCH_PROG(NV)                                                                                        \
+  do {                                                                                                        \
+    static bool attr_set[8] = {false};                                                                        \
+    if (!attr_set[dev & 7]) {                                                                                 \
+      MGB_CUDA(cudaFuncSetAttribute(k_preagg_dense<NK, NV, true, TH, true>,                                    \
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));                \
+      attr_set[dev & 7] = true;                                                                               \
+    }                                                                                                         \
+    k_preagg_dense<NK, NV, true, TH, true><<<grid, TH, smem, st>>>(p, bt);                                     \
+  } while (0)
+    switch (ncol) {
+      case 1: LAUNCH_PROG(1); break;
+      case 2: LAUNCH_PROG(2); break;
+      case 3: LAUNCH_PROG(3); break;
+      case 4: LAUNCH_PROG(4); break;
+      case 5: LAUNCH_PROG(5); break;
+      case 6: LAUNCH_PROG(6); break;
+      case 7: LAUNCH_PROG(7); break;
+      default: LAUNCH_PROG(8); break;
+    }
+#undef LAUNCH_PROG
+  } else if (plain) PICK_NV(true); else PICK_NV(false);
 #undef PICK_NV
 #undef LAUNCH
   MGB_CHECK_LAUNCH();

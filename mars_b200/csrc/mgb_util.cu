@@ -576,3 +576,99 @@ extern "C" int mgb_copy_rows(void* dst, int64_t dst_offset, const void* src, int
                            (cudaStream_t)stream));
   return MGB_OK;
 }
+
+
+// ----------------------------------------------------------------------------------------------------
+// f3, unfused forms: a derived column as an elementwise kernel, the row filter as a stable compaction.  The fused
+// form lives in the dense batch kernel (mgb_dense.cuh: DenseProgram); these serve the shapes it does not take.
+// ----------------------------------------------------------------------------------------------------
+struct ProductArgs {
+  const double* col[3];
+  double alpha[3], beta[3];
+  int nf;
+};
+
+__global__ void __launch_bounds__(256) k_eval_product(ProductArgs a, double* out, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double v = 1.0;
+#pragma unroll
+    for (int f = 0; f < 3; ++f) {
+      if (f < a.nf) {
+        const double term = __dadd_rn(a.alpha[f], __dmul_rn(a.beta[f], a.col[f][i]));
+        v = f == 0 ? term : __dmul_rn(v, term);
+      }
+    }
+    out[i] = v;
+  }
+}
+
+extern "C" int mgb_eval_product(const void* const* phys_cols, const mgb_affine_factor* factors, int32_t n_factors,
+                                double* out, int64_t n_rows, void* stream) {
+  MGB_REQUIRE(n_rows >= 0 && n_factors >= 1 && n_factors <= 3, MGB_ERR_INVALID, "bad argument");
+  if (n_rows == 0) return MGB_OK;
+  MGB_REQUIRE(phys_cols && factors && out, MGB_ERR_INVALID, "null pointer");
+  ProductArgs a;
+  memset(&a, 0, sizeof(a));
+  a.nf = n_factors;
+  for (int f = 0; f < n_factors; ++f) {
+    MGB_REQUIRE(factors[f].col >= 0 && phys_cols[factors[f].col], MGB_ERR_INVALID, "factor %d: bad column", f);
+    a.col[f] = (const double*)phys_cols[factors[f].col];
+    a.alpha[f] = factors[f].alpha;
+    a.beta[f] = factors[f].beta;
+  }
+  MgbProfScope prof(MGB_K_POST, (cudaStream_t)stream);
+  k_eval_product<<<grid_for(n_rows), 256, 0, (cudaStream_t)stream>>>(a, out, n_rows);
+  MGB_CHECK_LAUNCH();
+  return MGB_OK;
+}
+
+__global__ void __launch_bounds__(256) k_filter_pid(const uint64_t* col, int f64, int op, long long ci, double cd,
+                                                    int32_t* pid, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint64_t raw = mgb_ld_stream(col + i);
+    int cmp;
+    bool unordered = false;
+    if (f64) {
+      const double v = __longlong_as_double((long long)raw);
+      unordered = v != v;
+      cmp = v < cd ? -1 : (v > cd ? 1 : 0);
+    } else {
+      const long long v = (long long)raw;
+      cmp = v < ci ? -1 : (v > ci ? 1 : 0);
+    }
+    bool keep = op == 0 ? cmp <= 0 : op == 1 ? cmp < 0 : op == 2 ? cmp >= 0 : op == 3 ? cmp > 0 : op == 4 ? cmp == 0 : cmp != 0;
+    if (unordered) keep = op == 5;
+    pid[i] = keep ? 0 : 1;
+  }
+}
+
+extern "C" int mgb_filter_rows(const void* filter_col, int32_t filter_dtype, int32_t filter_op, int64_t filter_i64,
+                               double filter_f64, const void* const* in_cols, void* const* out_cols, int32_t n_cols,
+                               int64_t n_rows, int64_t* out_n_host, void* stream) {
+  MGB_REQUIRE(out_n_host && n_rows >= 0 && n_cols >= 0 && filter_op >= 0 && filter_op <= 5, MGB_ERR_INVALID,
+              "bad argument");
+  *out_n_host = 0;
+  if (n_rows == 0) return MGB_OK;
+  MGB_REQUIRE(filter_col && (n_cols == 0 || (in_cols && out_cols)), MGB_ERR_INVALID, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  int32_t* pid = nullptr;
+  int64_t* off = nullptr;
+  MGB_CUDA(cudaMallocAsync((void**)&pid, sizeof(int32_t) * n_rows, st));
+  MGB_CUDA(cudaMallocAsync((void**)&off, sizeof(int64_t) * 3, st));
+  k_filter_pid<<<grid_for(n_rows), 256, 0, st>>>((const uint64_t*)filter_col, filter_dtype == MGB_F64, filter_op,
+                                                  (long long)filter_i64, filter_f64, pid, n_rows);
+  int status = mgb_partition_scatter(pid, n_rows, 2, in_cols, out_cols, n_cols, off, stream);
+  int64_t h[3] = {0, 0, 0};
+  if (status == MGB_OK) {
+    cudaError_t e = cudaMemcpyAsync(h, off, sizeof(h), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+      mgb_set_error("row filter: %s", cudaGetErrorString(e));
+      status = MGB_ERR_CUDA;
+    }
+  }
+  cudaFreeAsync(pid, st);
+  cudaFreeAsync(off, st);
+  *out_n_host = h[1];
+  return status;
+}
