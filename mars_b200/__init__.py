@@ -11,7 +11,7 @@ Layout (only what the path needs):
   plugin.py              registration on the real `mars` package when it is importable
 """
 from .core import OperandStage, ExecutionError, execute  # noqa: F401
-from .dataframe import (DataFrame, DataFrameConcat, DataFrameGroupByAgg, DataFrameGroupByOperand,  # noqa: F401
+from .dataframe import (DataFrame, DataFrameConcat, DataFrameFilter, DataFrameSetitem, DataFrameGroupByAgg, DataFrameGroupByOperand,  # noqa: F401
                         DataFrameGroupbyConcatPivot, DataFrameGroupbySortShuffle, DataFrameMergeAlign, DataFramePSRSGroupbySample,
                         DataFrameShuffleProxy, DataFrameToGPU, options)
 from .executors import register_gpu_executors  # noqa: F401

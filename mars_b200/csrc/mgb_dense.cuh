@@ -566,12 +566,18 @@ __global__ void __launch_bounds__(THREADS, 1) k_preagg_dense(const DenseParams p
   };
   auto process_tile = [&](int buf) {
     if (PROG) {     // filter + derived columns first; rows the filter drops take no part in the update
+      auto rows = [&](uint64_t (&kk)[DN_R][NK], uint64_t (&xx)[DN_R][NV]) {
 #pragma unroll
-      for (int r = 0; r < DN_R; ++r) {
-        if (failed) return;
-        const bool keep = apply_program(xb[buf][r]);
-        process_row(kb[buf][r], xb[buf][r], keep);
-      }
+        for (int r = 0; r < DN_R; ++r) {
+          if (failed) return;
+          const bool keep = apply_program(xx[r]);
+          process_row(kk[r], xx[r], keep);
+        }
+      };
+      if (buf == 0)       // constant buffer index on either side: the tile buffers stay in registers
+        rows(kb[0], xb[0]);
+      else
+        rows(kb[1], xb[1]);
       return;
     }
     if (PLAIN) {

@@ -96,6 +96,88 @@ class DataFrameGroupByOperand(MapReduceOperand):
                     group_keys=self.group_keys)
 
 
+class DataFrameFilter(Operand):
+    """row selection by a comparison mask, `df[df[col] <op> value]` (reference: DataFrameIndex with a boolean
+    mask, mars/dataframe/indexing/getitem.py).  fields: mask_col, mask_op ("<=", "<", ">=", ">", "==", "!="),
+    mask_value"""
+
+    def __init__(self, mask_col=None, mask_op=None, mask_value=None, **kw):
+        super().__init__(mask_col=mask_col, mask_op=mask_op, mask_value=mask_value, **kw)
+
+
+class DataFrameSetitem(Operand):
+    """`df[target] = expression` where the expression is a product of affine factors of columns (reference:
+    DataFrameSetitem fed by arithmetic operands, mars/dataframe/indexing/setitem.py).  fields: target, factors
+    [(column, alpha, beta)]"""
+
+    def __init__(self, target=None, factors=None, **kw):
+        super().__init__(target=target, factors=factors, **kw)
+
+
+class ColumnExpr:
+    """Lazy column expression of the mirror API: a left-to-right product of affine factors alpha + beta * column --
+    enough for `price * (1 - discount) * (1 + tax)`; comparisons of a plain column with a scalar give a row mask."""
+
+    def __init__(self, df, factors):
+        self.df, self.factors = df, list(factors)
+
+    def _plain(self):
+        return len(self.factors) == 1 and self.factors[0][1] == 0.0 and self.factors[0][2] == 1.0
+
+    def _affine(self, mul, add):
+        if len(self.factors) != 1:
+            raise NotImplementedError("scalar arithmetic on a product is outside the mirror's expression form")
+        c, a, b = self.factors[0]
+        return ColumnExpr(self.df, [(c, a * mul + add, b * mul)])
+
+    def __mul__(self, other):
+        if isinstance(other, ColumnExpr):
+            if other.df is not self.df:
+                raise NotImplementedError("columns of two frames")
+            if len(self.factors) + len(other.factors) > 3:
+                raise NotImplementedError("more than three factors")
+            return ColumnExpr(self.df, self.factors + other.factors)
+        return self._affine(float(other), 0.0)
+
+    __rmul__ = __mul__
+
+    def __add__(self, other):
+        return self._affine(1.0, float(other))
+
+    __radd__ = __add__
+
+    def __sub__(self, other):
+        return self._affine(1.0, -float(other))
+
+    def __rsub__(self, other):
+        return self._affine(-1.0, float(other))
+
+    def __neg__(self):
+        return self._affine(-1.0, 0.0)
+
+    def _mask(self, op, value):
+        if not self._plain():
+            raise NotImplementedError("row masks compare a stored column with a scalar")
+        return RowMask(self.df, self.factors[0][0], op, value)
+
+    def __le__(self, v):
+        return self._mask("<=", v)
+
+    def __lt__(self, v):
+        return self._mask("<", v)
+
+    def __ge__(self, v):
+        return self._mask(">=", v)
+
+    def __gt__(self, v):
+        return self._mask(">", v)
+
+
+class RowMask:
+    def __init__(self, df, column, op, value):
+        self.df, self.column, self.op, self.value = df, column, op, value
+
+
 class DataFrameMergeAlign(MapReduceOperand):
     """hash shuffle of the two sides of a merge on their join columns (reference: merge/merge.py:60-147).
 
@@ -461,6 +543,52 @@ class DataFrame:
     @property
     def index_value(self):
         return self.data.index_value
+
+    # ---- column expressions, row masks, setitem (the operators TPC-H Q1 applies before its groupby) ----------
+    def __getitem__(self, item):
+        if isinstance(item, RowMask):
+            if item.df is not self:
+                raise NotImplementedError("mask of another frame")
+            return self._per_chunk(lambda gpu: DataFrameFilter(mask_col=item.column, mask_op=item.op,
+                                                               mask_value=item.value, gpu=gpu),
+                                   self.data.dtypes, rows_known=False)
+        if isinstance(item, (list, tuple)):
+            raise NotImplementedError("column projection is applied by the groupby selection in this mirror")
+        if item not in self.data.dtypes.index:
+            raise KeyError(item)
+        return ColumnExpr(self, [(item, 0.0, 1.0)])
+
+    def __getattr__(self, name):
+        data = self.__dict__.get("data")
+        if data is not None and name in data.dtypes.index:
+            return self[name]
+        raise AttributeError(name)
+
+    def __setitem__(self, name, value):
+        if not isinstance(value, ColumnExpr) or value.df is not self:
+            raise NotImplementedError("only expressions over this frame's own columns can be assigned")
+        for c, _, _ in value.factors:
+            if self.data.dtypes[c] != np.float64:
+                raise NotImplementedError(f"column {c!r}: float64 operands only")
+        dtypes = self.data.dtypes.copy()
+        dtypes[name] = np.dtype("float64")
+        new = self._per_chunk(lambda gpu: DataFrameSetitem(target=name, factors=list(value.factors), gpu=gpu), dtypes,
+                              rows_known=True)
+        self.data = new.data          # pandas semantics: the assignment changes this (lazy) frame
+
+    def _per_chunk(self, make_op, dtypes, rows_known):
+        src = self.data
+        gpu = bool(src.op.gpu)
+        columns = pd.Index(list(dtypes.index))
+        cv = IndexValue(columns)
+        nrows = src.shape[0] if rows_known else np.nan
+        t = make_op(gpu).new_tileable([src], shape=(nrows, len(columns)), dtypes=dtypes, index_value=src.index_value,
+                                      columns_value=cv)
+        t.chunks = [make_op(gpu).new_chunk([c], shape=(c.shape[0] if rows_known else np.nan, len(columns)), index=c.index,
+                                           dtypes=dtypes, index_value=c.index_value, columns_value=cv)
+                    for c in src.chunks]
+        t.nsplits = src.nsplits if rows_known else ((np.nan,) * len(src.chunks), (len(columns),))
+        return DataFrame(None, _tileable=t)
 
     def to_gpu(self) -> "DataFrame":
         src = self.data

@@ -39,6 +39,30 @@ class HostColumn:
         return 8
 
 
+class DerivedColumn:
+    """A column of a chunk that is DEFINED, not stored: the left-to-right product of up to three affine factors
+    ``alpha + beta * <data column>`` of the same frame (``price * (1 - discount) * (1 + tax)``).  The band-level
+    batch kernel evaluates it inside the pre-aggregation pass (kernels.make_row_program); any other consumer gets
+    it materialised by ``DeviceFrame.col`` (one elementwise kernel)."""
+    __slots__ = ("factors",)
+    dtype = torch.float64
+
+    def __init__(self, factors):
+        self.factors = [(c, float(a), float(b)) for c, a, b in factors]
+
+    def element_size(self):
+        return 8
+
+    def numel(self):
+        return 0        # not stored
+
+
+FILTER_OPS = {"<=": 0, "<": 1, ">=": 2, ">": 3, "==": 4, "!=": 5}
+
+# set by mars_b200.executors (the kernels module it dispatches to): materialisation of lazy parts
+_lazy_kernels = None
+
+
 def _to_device(arr: np.ndarray, device) -> torch.Tensor:
     """H2D copy of one 8-byte column (pandas hands out read-only views; torch wants writable memory)."""
     global h2d_bytes
@@ -153,7 +177,7 @@ class ColumnSet:
 
 class DeviceFrame:
     __slots__ = ("index_names", "_index", "columns", "_data", "_n", "_pending", "_slot", "_home", "_src",
-                 "_ptrs_cache", "range_start", "__weakref__")
+                 "_ptrs_cache", "range_start", "_filter", "__weakref__")
 
     def __init__(self, index_names: Sequence[Any], index: Optional[Sequence[torch.Tensor]],
                  columns: Sequence[Any], data: Sequence[torch.Tensor], n_rows: Optional[int] = None,
@@ -168,6 +192,7 @@ class DeviceFrame:
         self._src = None             # row range of scattered columns that has not been sliced yet (from_range)
         self._ptrs_cache = None      # (column selection, pointers) of the last band-level batch over this chunk
         self.range_start = None      # raw chunk (index None): first label of its RangeIndex, when known
+        self._filter = None          # pending row filter (column, op code, value): rows are dropped when first needed
         if pending is not None:
             pending.attach(self)
             self._n = None
@@ -199,6 +224,7 @@ class DeviceFrame:
         f._home = None
         f._ptrs_cache = None
         f.range_start = None
+        f._filter = None
         f._src = (src, k0, k1, d0, d1, a, b)
         if pending is not None:      # rows [0, capacity) of a speculative result: the size is still on the device
             pending.attach(f)
@@ -231,12 +257,104 @@ class DeviceFrame:
         idx = self.index
         return ([t.data_ptr() for t in idx] if idx else []), [t.data_ptr() for t in self.data]
 
+    # ---- lazy row filter / derived columns (fused pre-path) ---------------------------------------------
+    @property
+    def is_lazy(self) -> bool:
+        return self._filter is not None or (self._data is not None and any(type(t) is DerivedColumn for t in self._data))
+
+    @property
+    def physical_rows(self) -> int:
+        """rows stored (before a pending row filter is applied)"""
+        return self._n
+
+    def lazy_spec(self):
+        """hashable description of the pending filter and the derived columns (equal for the chunks of one frame)"""
+        der = tuple((self.columns[i], tuple(t.factors)) for i, t in enumerate(self._data) if type(t) is DerivedColumn)
+        return self._filter, der
+
+    def with_filter(self, column, op: str, value) -> "DeviceFrame":
+        """shallow copy whose rows are (lazily) restricted to ``column <op> value``"""
+        if self._filter is not None:
+            self._apply_lazy()
+        out = DeviceFrame(self.index_names, self._index, self.columns, list(self.raw_data), self._n)
+        out._home, out.range_start = self._home, self.range_start
+        out._filter = (column, FILTER_OPS[op], value)
+        return out
+
+    def with_column(self, name, factors) -> "DeviceFrame":
+        """shallow copy with column ``name`` set to the product of the given affine factors of data columns"""
+        cols, data = list(self.columns), list(self.raw_data)
+        for c, _, _ in factors:
+            j = cols.index(c)
+            if type(data[j]) is DerivedColumn:
+                raise NotImplementedError("derived columns of derived columns are materialised by the caller")
+            if data[j].dtype != torch.float64:
+                raise NotImplementedError(f"column {c!r} has dtype {data[j].dtype}: float64 operands only")
+        d = DerivedColumn(factors)
+        if name in cols:
+            data[cols.index(name)] = d
+        else:
+            cols.append(name)
+            data.append(d)
+        out = DeviceFrame(self.index_names, self._index, cols, data, self._n)
+        out._home, out.range_start, out._filter = self._home, self.range_start, self._filter
+        return out
+
+    def physical(self, name) -> torch.Tensor:
+        """a stored data column on the device, WITHOUT applying a pending row filter (fused pre-path only)"""
+        i = self.columns.index(name)
+        t = self._data[i]
+        if isinstance(t, HostColumn):
+            t = self._data[i] = _to_device(t.array, self._home)
+        if type(t) is DerivedColumn:
+            raise KeyError(name)
+        return t
+
+    def _materialise_derived(self, i):
+        t = self._data[i]
+        names = []
+        for c, _, _ in t.factors:
+            if c not in names:
+                names.append(c)
+        phys = [self.physical(c) for c in names]
+        self._data[i] = _lazy_kernels.eval_product(phys, [(names.index(c), a, b) for c, a, b in t.factors])
+        return self._data[i]
+
+    def _apply_lazy(self):
+        """materialise what is pending: derived columns by elementwise kernels, the row filter by a stable
+        compaction of every column (what the unfused operator chain of the reference does, pass by pass)"""
+        if self._data is None:
+            return
+        for i, t in enumerate(self._data):
+            if type(t) is DerivedColumn:
+                self._materialise_derived(i)
+        if self._filter is not None:
+            col, op, value = self._filter
+            self._filter = None
+            for i, t in enumerate(self._data):
+                if isinstance(t, HostColumn):
+                    self._data[i] = _to_device(t.array, self._home)
+            self._home = None
+            n = self._n
+            idx = list(self._index) if self._index is not None else (
+                [torch.arange(self.range_start, self.range_start + n, dtype=torch.int64, device=self._data[0].device)]
+                if self.range_start is not None else [])
+            cols = idx + list(self._data)
+            outs, kept = _lazy_kernels.filter_rows(self._data[self.columns.index(col)], op, value, cols)
+            if idx:
+                self._index, self.index_names = outs[:len(idx)], (self.index_names or [None] * len(idx))
+            self._data = outs[len(idx):]
+            self._n = kept
+            self._ptrs_cache = None
+
     # ---- deferred size -------------------------------------------------------------------------------
     @property
     def is_pending(self) -> bool:
         return self._pending is not None and self._pending.value is None
 
     def _resolve(self):
+        if self._filter is not None:
+            self._apply_lazy()
         if self._pending is not None and self._pending.value is None:
             self._pending.resolve()
 
@@ -280,15 +398,22 @@ class DeviceFrame:
                 if isinstance(t, HostColumn):
                     self._data[i] = _to_device(t.array, self._home)
             self._home = None
+        for i, t in enumerate(self._data):
+            if type(t) is DerivedColumn:
+                self._materialise_derived(i)
         return self._data
 
     def col(self, i: int) -> torch.Tensor:
         """data column i on the device (uploads it now if it is still in host memory)"""
         if self._src is not None:
             self._mat()
+        if self._filter is not None:
+            self._apply_lazy()
         t = self._data[i]
         if isinstance(t, HostColumn):
             t = self._data[i] = _to_device(t.array, self._home)
+        elif type(t) is DerivedColumn:
+            t = self._materialise_derived(i)
         elif self._pending is not None:
             return self.data[i]
         return t

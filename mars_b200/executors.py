@@ -28,7 +28,8 @@ import torch
 from . import _lib as _lib_mod
 from . import kernels as K
 from ._lib import MarsGBError
-from .device import ColumnSet, DeviceFrame, Pending, PiecewiseFrame
+from . import device as _device_mod
+from .device import ColumnSet, DerivedColumn, DeviceFrame, Pending, PiecewiseFrame
 from .reduction import _DECOMP
 
 _OPCODE = {"sum": K.SUM, "count": K.COUNT, "min": K.MIN, "max": K.MAX}
@@ -37,6 +38,7 @@ _DECOMP_EXT = dict(_DECOMP, std=_DECOMP["var"])
 # the kernels module is looked up through this indirection so that host-logic tests can substitute a
 # recording double; the product never rebinds it.
 _kernels = K
+_device_mod._lazy_kernels = K     # materialisation of lazy row filters / derived columns (device.DeviceFrame)
 _dense_rejected = set()
 _mid_rejected = set()      # shapes the mid-cardinality batch kernel declined (functions, groups, NaNs)
 _probed = set()            # shapes whose first chunk was probed for its cardinality
@@ -289,7 +291,7 @@ def _map_plan_slow(op, frame: DeviceFrame) -> _MapPlan:
 def _execute_agg_map(ctx, op):
     """stage=map: per-chunk group-by + K atomic reductions (reference: _execute_map, aggregation.py:1043-1128)"""
     frame = _as_device_frame(ctx[op.inputs[0].key])
-    if frame.index is not None:
+    if frame.raw_index is not None:
         raise NotImplementedError("map stage expects a raw chunk (RangeIndex)")
     plan = _map_plan(op, frame)
     keys_ok, count_only, dts = plan.for_dtypes(frame)
@@ -297,6 +299,20 @@ def _execute_agg_map(ctx, op):
         for b, i in zip(plan.by, plan.key_pos):
             if frame.col_dtype(i) != torch.int64:
                 raise NotImplementedError(f"group key {b!r} has dtype {frame.col_dtype(i)}: int64 keys only")
+    if frame.is_lazy and _ASYNC and hasattr(_kernels, "preagg_dense_batch_async"):
+        # pending row filter / derived columns: the batch kernels evaluate them inside the pre-aggregation pass
+        # when the shape allows (fused pre-path), else they are materialised on the way
+        per_slot = _launch_band(plan, (keys_ok, count_only, dts), [frame])
+        if per_slot is not None:
+            frames = [p[0] for p in per_slot]
+            rec = getattr(op, "size_recorder_name", None)
+            if rec is not None:
+                pend0 = frames[0]._pending
+                bound = sum(pend0.cap * 8 * (len(f.columns) + len(plan.by)) for f in frames)
+                _record_sizes(ctx, rec, frame.nbytes,
+                              lambda: sum(len(f) * 8 * (len(f.columns) + len(plan.by)) for f in frames), bound)
+            ctx[op.outputs[0].key] = tuple(frames)
+            return
     keys = [frame.col(i) for i in plan.key_pos]
     if _ASYNC and hasattr(_kernels, "preagg_dense_batch_async"):
         which = _band_kernel(plan, (keys_ok, count_only, dts), [frame])
@@ -976,8 +992,10 @@ def _band_kernel(plan, sig, frames):
         if len(_probed) > 4096:
             _probed.clear()
         f0 = frames[0]
-        if len(f0) >= 4096:
-            sampled, uniq = _kernels.estimate_distinct([f0.col(i) for i in plan.key_pos])
+        if f0.physical_rows is not None and f0.physical_rows >= 4096:
+            # (a pending row filter is not applied for the probe: the stored keys bound the cardinality)
+            keys0 = [f0.physical(b) for b in plan.by] if f0.is_lazy else [f0.col(i) for i in plan.key_pos]
+            sampled, uniq = _kernels.estimate_distinct(keys0)
             if uniq > 12:
                 _dense_rejected.add(key)
             if uniq > 1400:
@@ -989,6 +1007,106 @@ def _band_kernel(plan, sig, frames):
     return None
 
 
+def _row_program(plan, sig, frame):
+    """(program, physical column names) of the fused pre-path for one chunk schema, or None when the shape does not
+    fit: only float64 SUM / COUNT accumulators, the extra operands (columns that are read but not aggregated, the
+    filter column) must fit into the index slots of the derived columns."""
+    _, count_only, dts = sig
+    if not _mid_eligible(plan, sig) or not hasattr(_kernels, "preagg_dense_batch_fused_async"):
+        return None
+    logical = [plan.used[j] for j in range(len(plan.used)) if j not in count_only]     # loaded logical columns
+    if len(logical) > 8:
+        return None
+    filt, derived = frame.lazy_spec()
+    derived = dict(derived)
+    phys: List[Any] = [None if c in derived else c for c in logical]
+    free = [i for i, c in enumerate(phys) if c is None]
+
+    def slot_of(name):
+        if name in phys:
+            return phys.index(name)
+        if not free or name in derived or name not in frame.columns:
+            return None
+        i = free.pop(0)
+        phys[i] = name
+        return i
+
+    prog_logical = []
+    for c in logical:
+        if c not in derived:
+            prog_logical.append(None)
+            continue
+        facs = []
+        for name, alpha, beta in derived[c]:
+            i = slot_of(name)
+            if i is None:
+                return None
+            facs.append((i, alpha, beta))
+        prog_logical.append(facs)
+    row_filter = None
+    if filt is not None:
+        col, op, value = filt
+        i = slot_of(col)
+        if i is None:
+            return None
+        dt = frame.raw_data[frame.columns.index(col)].dtype
+        row_filter = (i, op, _kernels.F64 if dt == torch.float64 else _kernels.I64, value)
+    n_phys = max(i for i, c in enumerate(phys) if c is not None) + 1
+    for i in range(n_phys):
+        if phys[i] is None:
+            phys[i] = plan.by[0]          # an unused slot below n_phys: any valid column, its values are never read
+    # aggregated operands must be float64 (the kernel treats every loaded column as such)
+    for i, name in enumerate(phys[:n_phys]):
+        t = frame.raw_data[frame.columns.index(name)]
+        if row_filter is not None and i == row_filter[0]:
+            continue
+        if t.dtype != torch.float64 and name != plan.by[0]:
+            return None
+    return _kernels.make_row_program(n_phys, prog_logical, row_filter), phys[:n_phys]
+
+
+def _launch_band_fused(plan, sig, frames):
+    """band-level batch with the row program (filter + derived columns evaluated inside the pre-aggregation pass)"""
+    spec0 = frames[0].lazy_spec()
+    for f in frames[1:]:
+        if f.lazy_spec() != spec0:
+            return None
+    rp = _row_program(plan, sig, frames[0])
+    if rp is None:
+        return None
+    prog, phys = rp
+    keys_ok, count_only, dts = sig
+    B = _kernels.dense_batch_max()
+    dev = frames[0].device
+    nk = len(plan.by)
+    per_slot: List[List[DeviceFrame]] = [[] for _ in plan.slots]
+    for g0 in range(0, len(frames), B):
+        group = frames[g0:g0 + B]
+        chunks = [([f.physical(b).data_ptr() for b in plan.by], [f.physical(c).data_ptr() for c in phys],
+                   f.physical_rows) for f in group]
+        bi, bf, fc = _kernels.preagg_dense_batch_fused_async(chunks, plan.accs, dts, nk, dev, prog)
+
+        def replay(group=group, plan=plan):
+            """not a low-cardinality band after all: lazy parts are materialised, general aggregator"""
+            _dense_rejected.add(plan.shape_key)
+            agg = _kernels.Aggregator(len(plan.by), [_kernels.dtype_code(group[0].col(i)) for i in plan.val_pos],
+                                      list(plan.accs))
+            try:
+                for f in group:
+                    agg.update([f.col(i) for i in plan.key_pos], [f.col(i) for i in plan.val_pos])
+                return agg.result(sort=False, device=group[0].device)
+            finally:
+                agg.close()
+
+        pend = Pending(bi, fc.n_int, bi.shape[1], replay, fblock=bf, layout=fc)
+        src = ColumnSet.from_block(bi, bf, fc)
+        cap = bi.shape[1]
+        for s_, (cols, a0, a1) in enumerate(plan.slots):
+            per_slot[s_].append(DeviceFrame.from_range(plan.by, cols, src, 0, nk, nk + a0, nk + a1, 0, cap,
+                                                       pending=pend, slot=(a0, a1)))
+    return per_slot
+
+
 def _launch_band(plan, sig, frames):
     """one batch launch per mgb_dense_batch_max() chunks -> per slot the list of pieces, or None"""
     which = _band_kernel(plan, sig, frames)
@@ -997,6 +1115,11 @@ def _launch_band(plan, sig, frames):
     fn = _kernels.preagg_dense_batch_async if which == "dense" else _kernels.preagg_mid_batch_async
     rejected = _dense_rejected if which == "dense" else _mid_rejected
     keys_ok, count_only, dts = sig
+    if frames[0].is_lazy:
+        fused = _launch_band_fused(plan, sig, frames) if which == "dense" else None
+        if fused is not None:
+            return fused
+        # not a shape the fused pre-path takes: the lazy parts are materialised by the column accessors below
     chunks = []
     ck = (tuple(plan.key_pos), tuple(plan.val_pos), count_only)
     for f in frames:
@@ -1049,7 +1172,7 @@ def _launch_band(plan, sig, frames):
 def _band_frames_plan(op0, frames):
     """(plan, dtype signature) when all frames of a band share one low-cardinality-capable schema, else None"""
     for v in frames:
-        if not isinstance(v, DeviceFrame) or v.index is not None:
+        if not isinstance(v, DeviceFrame) or v.raw_index is not None:
             return None
     try:
         plan = _map_plan(op0, frames[0])
@@ -1442,6 +1565,23 @@ def execute_concat(ctx, op):
     ctx[op.outputs[0].key] = _concat_partial_tuples(items)
 
 
+def execute_filter(ctx, op):
+    """boolean-mask row selection `df[df[col] <op> value]` (reference: DataFrameIndex with a mask,
+    mars/dataframe/indexing/getitem.py).  Lazy: the rows are dropped by whoever reads the chunk -- inside the
+    pre-aggregation pass when the fused pre-path applies (TPC-H Q1), by a stable compaction otherwise."""
+    frame = _as_device_frame(ctx[op.inputs[0].key], lazy=_LAZY_H2D)
+    if op.mask_col not in frame.columns:
+        raise NotImplementedError(f"filter column {op.mask_col!r} is not a data column")
+    ctx[op.outputs[0].key] = frame.with_filter(op.mask_col, op.mask_op, op.mask_value)
+
+
+def execute_setitem(ctx, op):
+    """`df[name] = <product of affine factors of columns>` (reference: DataFrameSetitem + the arithmetic operands
+    that feed it, mars/dataframe/indexing/setitem.py, mars/dataframe/arithmetic).  Lazy, like the filter."""
+    frame = _as_device_frame(ctx[op.inputs[0].key], lazy=_LAZY_H2D)
+    ctx[op.outputs[0].key] = frame.with_column(op.target, op.factors)
+
+
 def execute_to_gpu(ctx, op):
     """DataFrameToGPU.execute (base/to_gpu.py:28-35).  The columns are uploaded when their first consumer asks
     for them, so a column no kernel reads (an int64 column that is only counted) never crosses PCIe."""
@@ -1471,3 +1611,5 @@ def register_gpu_executors():
     md.DataFrameGroupbyConcatPivot.register_executor(execute_concat_pivot)
     md.DataFrameGroupbySortShuffle.register_executor(execute_sort_shuffle)
     md.DataFrameMergeAlign.register_executor(execute_merge_align)
+    md.DataFrameFilter.register_executor(execute_filter)
+    md.DataFrameSetitem.register_executor(execute_setitem)

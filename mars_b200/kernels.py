@@ -548,6 +548,86 @@ def preagg_dense_batch_async(chunks, accs: Sequence[Tuple[int, int]], val_dtypes
     return res[:3]
 
 
+def make_row_program(n_phys: int, logical, row_filter=None):
+    """ctypes row program (include/mgb.h: mgb_row_program).  ``logical``: per loaded logical column either None (the
+    column is physical column of the same index) or a list of up to 3 factors (physical column, alpha, beta);
+    ``row_filter``: None or (physical column, op code 0..5, dtype code, value)."""
+    prog = _lib.RowProgram()
+    prog.n_phys = n_phys
+    for c, fac in enumerate(logical):
+        prog.n_factors[c] = 0 if fac is None else len(fac)
+        for f, (col, alpha, beta) in enumerate(fac or []):
+            prog.factors[c][f].col, prog.factors[c][f].alpha, prog.factors[c][f].beta = col, float(alpha), float(beta)
+    if row_filter is None:
+        prog.filter_col = -1
+    else:
+        col, op, dt, val = row_filter
+        prog.filter_col, prog.filter_op, prog.filter_dtype = col, op, dt
+        prog.filter_i64 = int(val) if dt == I64 else 0
+        prog.filter_f64 = float(val)
+    return prog
+
+
+def preagg_dense_batch_fused_async(chunks, accs, val_dtypes, n_keys: int, device, prog):
+    """Band-level batch with the fused pre-path (mgb_preagg_dense_batch_fused_async): ``chunks`` carry the
+    PHYSICAL value columns of the row program ``prog``; the spec (accs / val_dtypes) describes the logical ones."""
+    global _dense_cap
+    if _dense_cap is None:
+        c = C.c_int64()
+        check(_lib.load().mgb_dense_capacity(C.byref(c)))
+        _dense_cap = c.value
+    lib = _lib.load()
+    n = len(chunks)
+    if n > dense_batch_max():
+        raise MarsGBError(1, f"{n} chunks in one batch (at most {dense_batch_max()})")
+    fc = _fast(n_keys, val_dtypes, accs)
+    rows = (C.c_int64 * max(n, 1))()
+    kt = (_lib._pp * max(n, 1))()
+    vt = (_lib._pp * max(n, 1))()
+    keep = []
+    for i, (kp, vp, m) in enumerate(chunks):
+        karr = (C.c_void_p * n_keys)(*kp)
+        varr = (C.c_void_p * max(len(vp), 1))(*vp)
+        keep.append((karr, varr))
+        kt[i] = C.cast(karr, _lib._pp)
+        vt[i] = C.cast(varr, _lib._pp)
+        rows[i] = int(m)
+    bi, bf = fc.alloc(_dense_cap, device)
+    check(lib.mgb_preagg_dense_batch_fused_async(C.byref(fc.spec), C.byref(prog), n, rows, kt, vt, fc.okp, fc.oap,
+                                                 _dense_cap, fc.count_ptr(bi), _stream()))
+    _count(1 if any(m for _, _, m in chunks) else 0)
+    return bi, bf, fc
+
+
+def eval_product(phys: Sequence[torch.Tensor], factors) -> torch.Tensor:
+    """materialises one derived column: product of (alpha + beta * phys[col]) terms (mgb_eval_product)"""
+    lib = _lib.load()
+    phys = [_req(t, f"column {i}", (torch.float64,)) for i, t in enumerate(phys)]
+    n = phys[0].numel()
+    out = torch.empty(n, dtype=torch.float64, device=phys[0].device)
+    fa = (_lib.AffineFactor * max(len(factors), 1))()
+    for f, (col, alpha, beta) in enumerate(factors):
+        fa[f].col, fa[f].alpha, fa[f].beta = col, float(alpha), float(beta)
+    check(lib.mgb_eval_product(_ptrs(phys), fa, len(factors), out.data_ptr(), n, _stream()))
+    _count(1 if n else 0)
+    return out
+
+
+def filter_rows(filter_col: torch.Tensor, op: int, value, cols: Sequence[torch.Tensor]):
+    """stable compaction of ``cols`` to the rows where ``filter_col <op> value`` (mgb_filter_rows; one host wait)"""
+    lib = _lib.load()
+    fcol = _req(filter_col, "filter column")
+    cols = [_req(c, f"column {i}") for i, c in enumerate(cols)]
+    n = fcol.numel()
+    outs = [torch.empty_like(c) for c in cols]
+    k = C.c_int64()
+    dt = dtype_code(fcol)
+    check(lib.mgb_filter_rows(fcol.data_ptr(), dt, int(op), int(value) if dt == I64 else 0, float(value), _ptrs(cols),
+                              _ptrs(outs), len(cols), n, C.byref(k), _stream()))
+    _count(8 if n else 0)
+    return [o[:k.value] for o in outs], k.value
+
+
 _mid_cap = None
 
 

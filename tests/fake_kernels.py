@@ -335,3 +335,65 @@ def partition_ids_frame(keys, n_partitions):
     calls.append("partition_ids_frame")
     h = orc.hash_frame_rows([_np(k) for k in keys])
     return torch.from_numpy((h % np.uint64(n_partitions)).astype(np.int32))
+
+
+make_row_program = _K.make_row_program
+
+
+def _cmp(v, op, value):
+    with np.errstate(invalid="ignore"):
+        return [v <= value, v < value, v >= value, v > value, v == value, v != value][op]
+
+
+def preagg_dense_batch_fused_async(chunks, accs, val_dtypes, n_keys, device, prog):
+    """double of the fused pre-path: the row program is evaluated with numpy, then the dense double aggregates"""
+    calls.append("preagg_dense_batch_fused_async")
+    used = [c for c, dt in enumerate(val_dtypes) if any(col == c and op != COUNT for col, op in accs) or dt == F64]
+    new_chunks, keep_alive = [], []
+    for kp, vp, m in chunks:
+        phys = [_view(vp[j], m, True).copy() for j in range(prog.n_phys)]
+        keep = np.ones(m, dtype=bool)
+        if prog.filter_col >= 0:
+            raw = _view(vp[prog.filter_col], m, prog.filter_dtype == F64)
+            keep = _cmp(raw, prog.filter_op, prog.filter_f64 if prog.filter_dtype == F64 else prog.filter_i64)
+        logical = []
+        for c in range(len(used)):
+            nf = prog.n_factors[c]
+            if nf == 0:
+                logical.append(phys[c])
+                continue
+            v = None
+            for f in range(nf):
+                fac = prog.factors[c][f]
+                term = fac.alpha + fac.beta * phys[fac.col]
+                v = term if v is None else v * term
+            logical.append(v)
+        ks = [torch.from_numpy(_view(kp[j], m, False)[keep].copy()) for j in range(n_keys)]
+        vs, li = [], 0
+        for c, dt in enumerate(val_dtypes):
+            if c in used:
+                vs.append(torch.from_numpy(np.ascontiguousarray(logical[li][keep])))
+                li += 1
+            else:
+                vs.append(None)
+        keep_alive.append((ks, vs))
+        new_chunks.append(([k.data_ptr() for k in ks], [None if v is None else v.data_ptr() for v in vs], int(keep.sum())))
+    out = preagg_dense_batch_async(new_chunks, accs, val_dtypes, n_keys, device)
+    calls.pop()
+    return out
+
+
+def eval_product(phys, factors):
+    calls.append("eval_product")
+    v = None
+    for col, alpha, beta in factors:
+        term = alpha + beta * _np(phys[col])
+        v = term if v is None else v * term
+    return torch.from_numpy(np.ascontiguousarray(v))
+
+
+def filter_rows(filter_col, op, value, cols):
+    calls.append("filter_rows")
+    keep = _cmp(_np(filter_col), op, value)
+    idx = torch.from_numpy(np.nonzero(keep)[0])
+    return [c[idx] for c in cols], int(keep.sum())
