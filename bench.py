@@ -472,6 +472,7 @@ def main_ours(args):
         except Exception as e:  # noqa: BLE001
             parity = {"ok": False, "mode": f"check failed to run: {e!r}"}
 
+    dev_step_ms = step_ms[id(dev_frames), True]
     configs = None
     if rank == 0 and world == 1 and not args.no_configs:
         del host_frames, dev_frames
@@ -535,8 +536,7 @@ def main_ours(args):
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
                          "step_hbm_frac": (rows_rank * BYTES_PER_ROW / (ms / args.steps * 1e-3) / 1e9) / peak},
             "kernel_time_ms": prof,
-            "step_ms": {"min": min(step_ms[id(dev_frames), True]), "median": statistics.median(step_ms[id(dev_frames), True]),
-                        "max": max(step_ms[id(dev_frames), True]),
+            "step_ms": {"min": min(dev_step_ms), "median": statistics.median(dev_step_ms), "max": max(dev_step_ms),
                         "note": "host wall time of every timed step; value uses the whole region (device events / wall, max)"},
             "per_operand": {"value": total_rows * po_steps / (ms_po * 1e-3), "unit": "rows/s", "ms_per_step": ms_po / po_steps,
                             "steps": po_steps,
