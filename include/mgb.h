@@ -109,6 +109,30 @@ int mgb_hash_partition(const int64_t* const* key_cols, int32_t n_keys, int64_t n
                        const void* const* in_cols, void* const* out_cols, int32_t n_cols, int64_t* out_offsets,
                        void* stream);
 
+/* The partition kernel in its two passes (north_star: per-destination histogram -> prefix scan -> coalesced 128-bit
+ * vectorised scatter), for 1 <= n_partitions <= 256.  Same split as mgb_hash_partition; the passes are separate so
+ * that a caller can learn the block sizes first (out_offsets), decide where every block goes, and then let the
+ * scatter write each row ONCE straight to that place -- e.g. into the receive arena of the GPU that runs the reducer,
+ * mapped through CUDA IPC (mgb_ipc_arena_slot / mgb_ipc_open_slot): partition + pack + transfer of the shuffle in one
+ * kernel (replaces execute_map's block takes, groupby/core.py:389-435, AND the storage-service transfer of the
+ * blocks, mars/services/storage/transfer.py:63-206).
+ *   mode 0: partition id = pandas hash of the key tuple, Index semantics (mgb_partition_ids) % n_partitions
+ *   mode 1: DataFrame-row semantics (mgb_partition_ids_frame);  mode 2: ids given in `pid` (clamped to range)
+ *   mgb_split_tiles   number of row tiles T of a chunk; tile_hist is device scratch of n_partitions * T int64 that
+ *                     must stay untouched between the two passes
+ *   mgb_split_plan    pass 1: tile histograms, scanned; out_offsets[n_partitions + 1] on the device
+ *   mgb_split_scatter pass 2: column tiles staged in shared memory by TMA (cp.async.bulk + mbarrier), permuted into
+ *                     partition order on chip, written out in runs with 16-byte stores.  Destination of row j of
+ *                     partition p in column c: out_cols[c] + out_offsets[p] + j when dst_table is NULL, else
+ *                     (uint64_t*)dst_table[c * n_partitions + p] + j (device array of addresses; peer memory allowed;
+ *                     16-byte aligned addresses get 16-byte stores).  Stable.  No host synchronisation.            */
+int mgb_split_tiles(int64_t n_rows, int64_t* out_tiles);
+int mgb_split_plan(const int64_t* const* key_cols, int32_t n_keys, int32_t mode, const int32_t* pid, int64_t n_rows,
+                   int32_t n_partitions, int64_t* tile_hist, int64_t* out_offsets, void* stream);
+int mgb_split_scatter(const int64_t* const* key_cols, int32_t n_keys, int32_t mode, const int32_t* pid, int64_t n_rows,
+                      int32_t n_partitions, const int64_t* tile_hist, const void* const* in_cols, int32_t n_cols,
+                      void* const* out_cols, const uint64_t* dst_table, void* stream);
+
 /* ---- a4/a9/a10: hash aggregation -------------------------------------------------------------------
  * Replaces `df.groupby(keys).agg(...)` of DataFrameGroupByAgg._execute_map / _execute_combine /
  * _execute_agg (mars/dataframe/groupby/aggregation.py:1043-1267, pandas group_sum/min/max/count).
@@ -352,10 +376,15 @@ int mgb_prof_read(int32_t kernel_id, double* out_total_ms, int64_t* out_launches
 int mgb_ipc_arena(int64_t bytes, void** out_ptr, uint8_t out_handle[64]);
 int mgb_ipc_open(int32_t peer, const uint8_t handle[64], void** out_ptr);
 int mgb_ipc_pull(void* dst, const void* peer_src, int64_t bytes, void* stream);
-
-/* ---- microbenchmarks used by profiles/ (not part of the operand path) -------------------------------- */
-int mgb_bench_atomics(int32_t mode, int64_t n_rows, int32_t n_slots, int32_t iters, float* out_ms,
-                      void* stream);
+/* Numbered arenas (slot 0 is the arena of mgb_ipc_arena; slots 1..3 are receive arenas of the push shuffle, rotated so
+ * that the blocks of one shuffle stay valid while the next one is written).  mgb_ipc_arena_slot (re)allocates when
+ * `bytes` exceeds the slot's capacity: the caller must first make every peer drop its mapping of that slot
+ * (mgb_ipc_close_slot on the peers, then a barrier) -- an exported allocation is never freed while it is mapped.
+ * out_capacity / out_fresh (may be NULL): capacity in bytes, 1 when this call allocated.                          */
+int mgb_ipc_arena_slot(int32_t slot, int64_t bytes, void** out_ptr, uint8_t out_handle[64], int64_t* out_capacity,
+                       int32_t* out_fresh);
+int mgb_ipc_open_slot(int32_t peer, int32_t slot, const uint8_t handle[64], void** out_ptr);
+int mgb_ipc_close_slot(int32_t peer, int32_t slot);
 
 #ifdef __cplusplus
 }

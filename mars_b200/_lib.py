@@ -80,6 +80,9 @@ SIGNATURES = {
     "mgb_range_partition_ids": (C.c_int, [_pp, _i32, _i64, _pp, _i32, _vp, _vp]),
     "mgb_partition_scatter": (C.c_int, [_vp, _i64, _i32, _pp, _pp, _i32, _vp, _vp]),
     "mgb_hash_partition": (C.c_int, [_pp, _i32, _i64, _i32, _pp, _pp, _i32, _vp, _vp]),
+    "mgb_split_tiles": (C.c_int, [_i64, C.POINTER(_i64)]),
+    "mgb_split_plan": (C.c_int, [_pp, _i32, _i32, _vp, _i64, _i32, _vp, _vp, _vp]),
+    "mgb_split_scatter": (C.c_int, [_pp, _i32, _i32, _vp, _i64, _i32, _vp, _pp, _i32, _pp, _vp, _vp]),
     "mgb_agg_create": (C.c_int, [C.POINTER(_vp), C.POINTER(AggSpec), _vp]),
     "mgb_agg_set_hint": (C.c_int, [_vp, _i32]),
     "mgb_agg_update": (C.c_int, [_vp, _pp, _pp, _i64]),
@@ -127,10 +130,12 @@ SIGNATURES = {
     "mgb_ipc_arena": (C.c_int, [_i64, C.POINTER(_vp), _vp]),
     "mgb_ipc_open": (C.c_int, [_i32, _vp, C.POINTER(_vp)]),
     "mgb_ipc_pull": (C.c_int, [_vp, _vp, _i64, _vp]),
+    "mgb_ipc_arena_slot": (C.c_int, [_i32, _i64, C.POINTER(_vp), _vp, C.POINTER(_i64), C.POINTER(_i32)]),
+    "mgb_ipc_open_slot": (C.c_int, [_i32, _i32, _vp, C.POINTER(_vp)]),
+    "mgb_ipc_close_slot": (C.c_int, [_i32, _i32]),
     "mgb_prof_enable": (C.c_int, [_i32]),
     "mgb_prof_reset": (C.c_int, []),
     "mgb_prof_read": (C.c_int, [_i32, C.POINTER(C.c_double), C.POINTER(_i64)]),
-    "mgb_bench_atomics": (C.c_int, [_i32, _i64, _i32, _i32, C.POINTER(C.c_float), _vp]),
 }
 
 _lock = threading.Lock()

@@ -232,3 +232,8 @@ int mgb_radix_sort_perm_pid_ex(const int32_t* pid, int64_t n, int32_t n_partitio
                                int64_t* offsets_out, bool check_range, cudaStream_t st);
 int mgb_radix_sort_perm_keys(const int64_t* const* key_cols_host_array, int32_t n_keys, int64_t n,
                              int32_t* perm_out, cudaStream_t st);
+// histogram -> scan -> staged vectorised scatter into local columns (mgb_split.cu), n_partitions <= 256.
+// mode 0 / 1: pandas hash of the keys (Index / DataFrame-row semantics); 2: ids given in pid (out-of-range ids set *bad)
+int mgb_split_local(const int64_t* const* key_cols, int32_t n_keys, int32_t mode, const int32_t* pid, int64_t n_rows,
+                    int32_t n_partitions, const void* const* in_cols, void* const* out_cols, int32_t n_cols,
+                    int64_t* out_offsets, int32_t* bad, cudaStream_t st);

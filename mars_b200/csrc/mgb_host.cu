@@ -1,4 +1,4 @@
-// libmarsgb: host-buffer entry point (end-to-end path) and atomic-throughput microbenchmarks.
+// libmarsgb: host-buffer entry point (end-to-end path).
 #include <vector>
 
 #include "mgb_common.cuh"
@@ -116,95 +116,4 @@ extern "C" int mgb_groupby_agg_host(const mgb_agg_spec* spec, const int64_t* con
   for (auto e : events) cudaEventDestroy(e);
   if (copy) cudaStreamDestroy(copy);
   return status;
-}
-
-// ----------------------------------------------------------------------------------------------------
-// Microbenchmarks (profiles/): how fast can one B200 SM apply 8 accumulator updates per row?
-//   mode 0: shared-memory atomicAdd(double) (ATOMS.CAST.SPIN loop), random slot in [0, n_slots)
-//   mode 1: per-lane privatised LDS/DADD/STS (no atomics), n_slots <= 8
-//   mode 2: global RED.ADD.F64, random slot in [0, n_slots)
-//   mode 3: shared-memory atomicAdd(uint32) (native ATOMS.ADD), random slot
-//   mode 4: warp-aggregated (match_any leader) then shared atomicAdd(double)
-// Rows are synthesised in registers (slot = mix64(i) % n_slots) so only the update path is timed.
-// ----------------------------------------------------------------------------------------------------
-#define MB_ACCS 8
-
-__global__ void __launch_bounds__(512, 1) k_mb(int mode, long long n, int n_slots, double* gacc, double* sink) {
-  extern __shared__ __align__(16) uint64_t sm[];
-  double* sd = (double*)sm;
-  unsigned* su = (unsigned*)sm;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int words = mode == 1 ? (blockDim.x / 32) * n_slots * MB_ACCS * 32 : n_slots * MB_ACCS;
-  for (int i = threadIdx.x; i < words; i += blockDim.x) sd[i] = 0.0;
-  __syncthreads();
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int slot = (int)(mgb_mix64((uint64_t)i) % (uint64_t)n_slots);
-    const double v = 1.0 + (double)(i & 7);
-    if (mode == 0) {
-#pragma unroll
-      for (int a = 0; a < MB_ACCS; ++a) atomicAdd(&sd[a * n_slots + slot], v);
-    } else if (mode == 1) {
-      double* p = sd + ((size_t)(warp * n_slots + slot) * MB_ACCS) * 32 + lane;
-#pragma unroll
-      for (int a = 0; a < MB_ACCS; ++a) p[a * 32] += v;
-    } else if (mode == 2) {
-#pragma unroll
-      for (int a = 0; a < MB_ACCS; ++a) atomicAdd(&gacc[(size_t)slot * MB_ACCS + a], v);
-    } else if (mode == 3) {
-#pragma unroll
-      for (int a = 0; a < MB_ACCS; ++a) atomicAdd(&su[a * n_slots + slot], 1u);
-    } else {
-      const unsigned peers = __match_any_sync(__activemask(), slot);
-      const int leader = __ffs(peers) - 1;
-      double s = v;
-      // peers share the slot: sum their values with a butterfly over the whole warp restricted to peers
-      for (int o = 16; o > 0; o >>= 1) {
-        double y = __shfl_xor_sync(0xffffffffu, s, o);
-        int ys = __shfl_xor_sync(0xffffffffu, slot, o);
-        if (ys == slot) s += y;  // approximation of the peer reduction cost (exact when peers are contiguous)
-      }
-      if (lane == leader) {
-#pragma unroll
-        for (int a = 0; a < MB_ACCS; ++a) atomicAdd(&sd[a * n_slots + slot], s);
-      }
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x == 0 && sink) sink[blockIdx.x] = sd[0] + (double)su[1];
-}
-
-extern "C" int mgb_bench_atomics(int32_t mode, int64_t n_rows, int32_t n_slots, int32_t iters, float* out_ms,
-                                 void* stream) {
-  cudaStream_t st = (cudaStream_t)stream;
-  MGB_REQUIRE(mode >= 0 && mode <= 4 && n_rows > 0 && n_slots > 0 && iters > 0 && out_ms, MGB_ERR_INVALID,
-              "bad argument");
-  const int threads = 512;
-  size_t sm = mode == 1 ? (size_t)(threads / 32) * n_slots * MB_ACCS * 32 * 8 : (size_t)n_slots * MB_ACCS * 8;
-  if (mode == 2) sm = 64;
-  MGB_REQUIRE(sm <= 200 * 1024, MGB_ERR_INVALID, "n_slots too large for shared memory in mode %d", mode);
-  if (sm < 64) sm = 64;
-  MGB_CUDA(cudaFuncSetAttribute(k_mb, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  double *gacc = nullptr, *sink = nullptr;
-  MGB_CUDA(cudaMallocAsync((void**)&gacc, (size_t)n_slots * MB_ACCS * 8, st));
-  MGB_CUDA(cudaMemsetAsync(gacc, 0, (size_t)n_slots * MB_ACCS * 8, st));
-  const int grid = mgb_sm_count();
-  MGB_CUDA(cudaMallocAsync((void**)&sink, (size_t)grid * 8, st));
-  cudaEvent_t e0, e1;
-  MGB_CUDA(cudaEventCreate(&e0));
-  MGB_CUDA(cudaEventCreate(&e1));
-  k_mb<<<grid, threads, sm, st>>>(mode, n_rows, n_slots, gacc, sink);  // warm-up
-  MGB_CUDA(cudaEventRecord(e0, st));
-  for (int i = 0; i < iters; ++i) k_mb<<<grid, threads, sm, st>>>(mode, n_rows, n_slots, gacc, sink);
-  MGB_CUDA(cudaEventRecord(e1, st));
-  MGB_CUDA(cudaEventSynchronize(e1));
-  MGB_CHECK_LAUNCH();
-  float ms = 0;
-  MGB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-  *out_ms = ms / iters;
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
-  cudaFreeAsync(gacc, st);
-  cudaFreeAsync(sink, st);
-  return MGB_OK;
 }

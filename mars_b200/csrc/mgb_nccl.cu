@@ -189,17 +189,25 @@ struct IpcPeer {
   cudaIpcMemHandle_t handle;
   void* ptr = nullptr;
 };
-static IpcArena g_arena[8];
-static IpcPeer g_peers[8][64];   // [local device][peer rank]
+#define MGB_IPC_SLOTS 4
+static IpcArena g_arena[8][MGB_IPC_SLOTS];          // [local device][slot]
+static IpcPeer g_peers[8][64][MGB_IPC_SLOTS];       // [local device][peer rank][slot]
 
-extern "C" int mgb_ipc_arena(int64_t bytes, void** out_ptr, uint8_t out_handle[64]) {
-  MGB_REQUIRE(out_ptr && out_handle && bytes >= 0, MGB_ERR_INVALID, "bad argument");
+static int ipc_device(int* dev) {
+  MGB_CUDA(cudaGetDevice(dev));
+  MGB_REQUIRE(*dev >= 0 && *dev < 8, MGB_ERR_UNSUPPORTED, "device ordinal %d", *dev);
+  return MGB_OK;
+}
+
+extern "C" int mgb_ipc_arena_slot(int32_t slot, int64_t bytes, void** out_ptr, uint8_t out_handle[64],
+                                  int64_t* out_capacity, int32_t* out_fresh) {
+  MGB_REQUIRE(out_ptr && out_handle && bytes >= 0 && slot >= 0 && slot < MGB_IPC_SLOTS, MGB_ERR_INVALID, "bad argument");
   int dev = 0;
-  MGB_CUDA(cudaGetDevice(&dev));
-  MGB_REQUIRE(dev >= 0 && dev < 8, MGB_ERR_UNSUPPORTED, "device ordinal %d", dev);
-  IpcArena& a = g_arena[dev];
+  MGB_TRY(ipc_device(&dev));
+  IpcArena& a = g_arena[dev][slot];
+  if (out_fresh) *out_fresh = 0;
   if (a.bytes < (size_t)bytes || !a.base) {
-    // the caller guarantees (barrier after every exchange) that no peer is still reading the old arena
+    // the caller guarantees that no peer still maps the old allocation (close on the peers + barrier, see mgb.h)
     if (a.base) MGB_CUDA(cudaFree(a.base));
     size_t want = (size_t)bytes + ((size_t)bytes >> 2);
     if (want < (64u << 20)) want = 64u << 20;
@@ -208,19 +216,38 @@ extern "C" int mgb_ipc_arena(int64_t bytes, void** out_ptr, uint8_t out_handle[6
     MGB_CUDA(cudaMalloc(&a.base, want));
     a.bytes = want;
     MGB_CUDA(cudaIpcGetMemHandle(&a.handle, a.base));
+    if (out_fresh) *out_fresh = 1;
   }
   *out_ptr = a.base;
+  if (out_capacity) *out_capacity = (int64_t)a.bytes;
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
   memcpy(out_handle, &a.handle, 64);
   return MGB_OK;
 }
 
-extern "C" int mgb_ipc_open(int32_t peer, const uint8_t handle[64], void** out_ptr) {
-  MGB_REQUIRE(handle && out_ptr && peer >= 0 && peer < 64, MGB_ERR_INVALID, "bad argument");
+extern "C" int mgb_ipc_arena(int64_t bytes, void** out_ptr, uint8_t out_handle[64]) {
+  return mgb_ipc_arena_slot(0, bytes, out_ptr, out_handle, nullptr, nullptr);
+}
+
+extern "C" int mgb_ipc_close_slot(int32_t peer, int32_t slot) {
+  MGB_REQUIRE(peer >= 0 && peer < 64 && slot >= 0 && slot < MGB_IPC_SLOTS, MGB_ERR_INVALID, "bad argument");
   int dev = 0;
-  MGB_CUDA(cudaGetDevice(&dev));
-  MGB_REQUIRE(dev >= 0 && dev < 8, MGB_ERR_UNSUPPORTED, "device ordinal %d", dev);
-  IpcPeer& p = g_peers[dev][peer];
+  MGB_TRY(ipc_device(&dev));
+  IpcPeer& p = g_peers[dev][peer][slot];
+  if (p.open) {
+    MGB_CUDA(cudaIpcCloseMemHandle(p.ptr));
+    p.open = false;
+    p.ptr = nullptr;
+  }
+  return MGB_OK;
+}
+
+extern "C" int mgb_ipc_open_slot(int32_t peer, int32_t slot, const uint8_t handle[64], void** out_ptr) {
+  MGB_REQUIRE(handle && out_ptr && peer >= 0 && peer < 64 && slot >= 0 && slot < MGB_IPC_SLOTS, MGB_ERR_INVALID,
+              "bad argument");
+  int dev = 0;
+  MGB_TRY(ipc_device(&dev));
+  IpcPeer& p = g_peers[dev][peer][slot];
   if (p.open && memcmp(&p.handle, handle, 64) == 0) {
     *out_ptr = p.ptr;
     return MGB_OK;
@@ -234,6 +261,10 @@ extern "C" int mgb_ipc_open(int32_t peer, const uint8_t handle[64], void** out_p
   p.open = true;
   *out_ptr = p.ptr;
   return MGB_OK;
+}
+
+extern "C" int mgb_ipc_open(int32_t peer, const uint8_t handle[64], void** out_ptr) {
+  return mgb_ipc_open_slot(peer, 0, handle, out_ptr);
 }
 
 extern "C" int mgb_ipc_pull(void* dst, const void* peer_src, int64_t bytes, void* stream) {

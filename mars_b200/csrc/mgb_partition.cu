@@ -287,20 +287,6 @@ static int gather_impl(const void* const* in_cols, void* const* out_cols, int32_
   return MGB_OK;
 }
 
-// rows of many 8-byte columns to their destinations: out[c][dest[i]] = in[c][i] (reads coalesced)
-__global__ void __launch_bounds__(256) k_scatter_cols(GatherCols gc, const int32_t* __restrict__ dest, int64_t n) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t d = dest[i];
-    for (int c = 0; c < gc.n; ++c) gc.out[c][d] = mgb_ld_stream(gc.in[c] + i);
-  }
-}
-
-// partition starts out of the scanned [digit][tile] histogram of a single pass
-__global__ void k_offsets_from_hist(const int64_t* hist, int64_t ntiles, int32_t R, int64_t n, int64_t* offsets) {
-  for (int d = threadIdx.x; d <= R; d += blockDim.x) offsets[d] = d < R && d < 256 ? hist[(int64_t)d * ntiles] : n;
-}
-
 extern "C" int mgb_gather_rows(const void* const* in_cols, void* const* out_cols, int32_t n_cols,
                                const int32_t* perm, int64_t n_rows, void* stream) {
   MGB_REQUIRE(n_rows >= 0 && n_cols >= 0, MGB_ERR_INVALID, "negative size");
@@ -334,6 +320,27 @@ extern "C" int mgb_partition_scatter(const int32_t* pid, int64_t n_rows, int32_t
     MGB_CUDA(cudaMemsetAsync(out_offsets, 0, sizeof(int64_t) * ((size_t)n_partitions + 1), st));
     return MGB_OK;
   }
+  if (n_partitions <= 256) {
+    // histogram -> scan -> staged, vectorised scatter (mgb_split.cu); the range check of the caller's ids costs the
+    // one small synchronisation this entry has always had
+    int32_t* bad = nullptr;
+    MGB_CUDA(cudaMallocAsync((void**)&bad, sizeof(int32_t), st));
+    MGB_CUDA(cudaMemsetAsync(bad, 0, sizeof(int32_t), st));
+    int status = mgb_split_local(nullptr, 0, 2, pid, n_rows, n_partitions, in_cols, out_cols, n_cols, out_offsets, bad, st);
+    int32_t bad_h = 0;
+    if (status == MGB_OK) {
+      cudaError_t e = cudaMemcpyAsync(&bad_h, bad, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) {
+        mgb_set_error("partition range check: %s", cudaGetErrorString(e));
+        status = MGB_ERR_CUDA;
+      }
+    }
+    cudaFreeAsync(bad, st);
+    MGB_TRY(status);
+    MGB_REQUIRE(bad_h == 0, MGB_ERR_INVALID, "partition id outside [0, %d)", n_partitions);
+    return MGB_OK;
+  }
   MgbProfScope prof(MGB_K_PARTITION, st);
   int32_t* perm = nullptr;
   MGB_CUDA(cudaMallocAsync((void**)&perm, sizeof(int32_t) * n_rows, st));
@@ -345,9 +352,9 @@ extern "C" int mgb_partition_scatter(const int32_t* pid, int64_t n_rows, int32_t
 
 
 // a5 in one call: partition id = pandas hash of the key tuple % n_partitions (mgb_partition_ids), stable split
-// of the rows into per-reducer blocks (mgb_partition_scatter).  For n_partitions <= 256 the rows are scattered
-// to their destinations in one pass over the columns (k_radix_scatter<true> + k_scatter_cols) -- no permutation
-// array, no gather, no host synchronisation; more partitions take the general radix passes.
+// of the rows into per-reducer blocks.  n_partitions <= 256: histogram -> scan -> staged, 128-bit vectorised scatter
+// (mgb_split.cu: no partition-id array, no permutation, no gather, no host synchronisation); more partitions take
+// the general radix passes over a permutation.
 extern "C" int mgb_hash_partition(const int64_t* const* key_cols, int32_t n_keys, int64_t n_rows, int32_t n_partitions,
                                   const void* const* in_cols, void* const* out_cols, int32_t n_cols,
                                   int64_t* out_offsets, void* stream) {
@@ -362,11 +369,14 @@ extern "C" int mgb_hash_partition(const int64_t* const* key_cols, int32_t n_keys
     return MGB_OK;
   }
   MGB_REQUIRE(key_cols && (n_cols == 0 || (in_cols && out_cols)), MGB_ERR_INVALID, "null pointer");
+  if (n_partitions <= 256)
+    return mgb_split_local(key_cols, n_keys, 0, nullptr, n_rows, n_partitions, in_cols, out_cols, n_cols, out_offsets,
+                           nullptr, st);
+  // general path (ids come from the hash kernel: no range check, no synchronisation)
   int32_t* pid = nullptr;
   MGB_CUDA(cudaMallocAsync((void**)&pid, sizeof(int32_t) * n_rows, st));
   int status = mgb_partition_ids(key_cols, n_keys, n_rows, n_partitions, pid, stream);
-  if (status == MGB_OK && n_partitions > 256) {
-    // general path (ids come from the hash kernel above: no range check, no synchronisation)
+  if (status == MGB_OK) {
     MgbProfScope prof(MGB_K_PARTITION, st);
     int32_t* perm = nullptr;
     cudaError_t e = cudaMallocAsync((void**)&perm, sizeof(int32_t) * n_rows, st);
@@ -378,41 +388,6 @@ extern "C" int mgb_hash_partition(const int64_t* const* key_cols, int32_t n_keys
       if (status == MGB_OK && n_cols > 0) status = gather_impl(in_cols, out_cols, n_cols, perm, n_rows, st);
       cudaFreeAsync(perm, st);
     }
-  } else if (status == MGB_OK) {
-    MgbProfScope prof(MGB_K_PARTITION, st);
-    const int64_t ntiles = (n_rows + RP_TILE - 1) / RP_TILE;
-    int64_t* hist = nullptr;
-    int32_t* dest = nullptr;
-    cudaError_t e = cudaMallocAsync((void**)&hist, sizeof(int64_t) * 256 * ntiles, st);
-    if (e == cudaSuccess) e = cudaMallocAsync((void**)&dest, sizeof(int32_t) * n_rows, st);
-    if (e != cudaSuccess) {
-      mgb_set_error("cudaMallocAsync: %s", cudaGetErrorString(e));
-      status = MGB_ERR_CUDA;
-    } else {
-      DigitSrc s{pid, nullptr, nullptr, 0};
-      k_radix_hist<<<(unsigned)ntiles, RP_THREADS, 0, st>>>(s, n_rows, ntiles, hist);
-      status = mgb_scan_exclusive_i64(hist, 256 * ntiles, nullptr, st);
-      if (status == MGB_OK) {
-        k_offsets_from_hist<<<1, 288, 0, st>>>(hist, ntiles, n_partitions, n_rows, out_offsets);
-        k_radix_scatter<true><<<(unsigned)ntiles, RP_THREADS, 0, st>>>(s, n_rows, ntiles, hist, nullptr, dest);
-        for (int c0 = 0; c0 < n_cols; c0 += MGB_MAX_COLS) {
-          GatherCols gc;
-          gc.n = n_cols - c0 < MGB_MAX_COLS ? n_cols - c0 : MGB_MAX_COLS;
-          for (int c = 0; c < gc.n; ++c) {
-            gc.in[c] = (const uint64_t*)in_cols[c0 + c];
-            gc.out[c] = (uint64_t*)out_cols[c0 + c];
-          }
-          k_scatter_cols<<<grid_for(n_rows), 256, 0, st>>>(gc, dest, n_rows);
-        }
-        cudaError_t le = cudaGetLastError();
-        if (le != cudaSuccess) {
-          mgb_set_error("partition launch: %s", cudaGetErrorString(le));
-          status = MGB_ERR_CUDA;
-        }
-      }
-    }
-    if (hist) cudaFreeAsync(hist, st);
-    if (dest) cudaFreeAsync(dest, st);
   }
   cudaFreeAsync(pid, st);
   return status;

@@ -1,0 +1,435 @@
+// libmarsgb: the shuffle's partition kernel (a5 / a6) -- per-destination histogram, prefix scan, coalesced
+// 128-bit vectorised scatter, optionally straight into the receive arenas of peer GPUs.
+//
+// Replaces, for one mapper chunk, `hash_dataframe_on(df, on, size)` + the K `iloc[f_i]` takes of
+// DataFrameGroupByOperand.execute_map (mars/dataframe/groupby/core.py:389-435) -- and, when the destination
+// table points into IPC-mapped arenas of the reducers' GPUs, also the storage-service transfer of the blocks
+// (mars/services/storage/transfer.py:63-206): a row is read once from this GPU's HBM and written once into the
+// HBM of the GPU that reduces it.
+//
+//   pass 1  k_split_hist     tiles of 2048 rows: partition id of every row (pandas-exact hash % R, or a given id
+//                            array), per-tile histogram -> hist[R][ntiles]; exclusive scan -> every (partition,
+//                            tile) pair knows where its rows go; offsets[R + 1] = block boundaries
+//   pass 2  k_split_scatter  per tile: stable rank of every row inside its partition (warp match + per-warp
+//                            counters, no atomics), then column by column: the column tile is staged in shared
+//                            memory by the TMA unit (cp.async.bulk + mbarrier, double buffered: column c+1 is in
+//                            flight while column c is handled), permuted in shared memory into partition order,
+//                            and written out run by run -- consecutive lanes write consecutive addresses, two rows
+//                            per 16-byte store (runs are laid out in shared memory with the parity of their
+//                            destination so that aligned pairs in shared memory are aligned pairs in memory).
+//
+// Stable: inside a partition rows keep their input order (the ascending positions f_i of the reference).
+// No host synchronisation; 1 <= R <= 256 (more partitions: the radix passes of mgb_partition.cu).
+#include "mgb_common.cuh"
+
+#define SP_THREADS 256
+#define SP_WARPS 8
+#define SP_ROUNDS 8
+#define SP_TILE (SP_THREADS * SP_ROUNDS)
+#define SP_MAX_R 256
+#define SP_MAX_COLS 80
+#define SP_SLOTS (SP_TILE + SP_MAX_R + 2)
+#define SP_PAD 0xffffu
+
+struct SplitSrc {
+  const int64_t* k[MGB_MAX_KEYS];
+  const int32_t* pid;   // MODE 2: partition ids given by the caller
+  uint64_t R;
+};
+
+struct SplitCols {
+  const uint64_t* in[SP_MAX_COLS];
+  uint64_t* out[SP_MAX_COLS];   // local mode: out[c] + (absolute output row)
+  int n;
+};
+
+// MODE 0: hash of the key tuple with Index semantics (mgb_partition_ids); 1: DataFrame-row semantics
+// (mgb_partition_ids_frame); 2: ids given (range partition of the PSRS shuffle, mgb_range_partition_ids)
+template <int NK, int MODE>
+__device__ __forceinline__ uint32_t sp_pid(const SplitSrc& s, int64_t i, bool pow2, int32_t* bad) {
+  if (MODE == 2) {
+    uint32_t p = (uint32_t)s.pid[i];
+    if (p >= (uint32_t)s.R) {
+      *bad = 1;
+      p = (uint32_t)s.R - 1;
+    }
+    return p;
+  }
+  int64_t k[NK];
+#pragma unroll
+  for (int j = 0; j < NK; ++j) k[j] = (int64_t)mgb_ld_stream((const uint64_t*)s.k[j] + i);
+  const uint64_t h = MODE == 1 ? mgb_hash_frame_row<NK>(k) : mgb_hash_tuple<NK>(k);
+  return (uint32_t)(pow2 ? (h & (s.R - 1)) : (h % s.R));
+}
+
+template <int NK, int MODE>
+__global__ void __launch_bounds__(SP_THREADS) k_split_hist(SplitSrc s, int64_t n, int64_t ntiles, int R,
+                                                           int64_t* __restrict__ hist, int32_t* bad) {
+  __shared__ uint32_t wc[SP_WARPS][SP_MAX_R];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < SP_WARPS * SP_MAX_R; i += SP_THREADS) (&wc[0][0])[i] = 0;
+  __syncthreads();
+  const bool pow2 = (s.R & (s.R - 1)) == 0;
+  const int64_t tile = blockIdx.x;
+  const int64_t base = tile * SP_TILE + warp * (SP_TILE / SP_WARPS);
+  const unsigned lt = mgb_lanemask_lt();
+#pragma unroll
+  for (int r = 0; r < SP_ROUNDS; ++r) {
+    const int64_t i = base + r * 32 + lane;
+    const bool valid = i < n;
+    const uint32_t d = valid ? sp_pid<NK, MODE>(s, i, pow2, bad) : (uint32_t)(SP_MAX_R + lane);
+    const unsigned peers = __match_any_sync(0xffffffffu, d);
+    if (valid && (peers & lt) == 0) wc[warp][d] += (uint32_t)__popc(peers);
+    __syncwarp();
+  }
+  __syncthreads();
+  for (int p = threadIdx.x; p < R; p += SP_THREADS) {
+    uint32_t t = 0;
+#pragma unroll
+    for (int w = 0; w < SP_WARPS; ++w) t += wc[w][p];
+    hist[(int64_t)p * ntiles + tile] = t;
+  }
+}
+
+// block boundaries out of the scanned histogram
+__global__ void k_split_offsets(const int64_t* hist, int64_t ntiles, int R, int64_t n, int64_t* offsets) {
+  for (int p = threadIdx.x; p <= R; p += blockDim.x) offsets[p] = p < R ? hist[(int64_t)p * ntiles] : n;
+}
+
+// ---- TMA (bulk asynchronous copy) + mbarrier -------------------------------------------------------------------
+__device__ __forceinline__ uint32_t sp_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sp_mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sp_smem(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void sp_bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sp_smem(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   sp_smem(dst)),
+               "l"(src), "r"(bytes), "r"(sp_smem(bar))
+               : "memory");
+}
+__device__ __forceinline__ void sp_mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "SP_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra SP_DONE;\n"
+      "bra SP_WAIT;\n"
+      "SP_DONE:\n"
+      "}\n" ::"r"(sp_smem(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// destinations are global memory (this GPU's or an IPC-mapped peer's): typed stores, not generic ones
+__device__ __forceinline__ void sp_st128(uint64_t addr, const ulonglong2& v) {
+  asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(addr), "l"(v.x), "l"(v.y) : "memory");
+}
+__device__ __forceinline__ void sp_st64(uint64_t addr, uint64_t v) {
+  asm volatile("st.global.u64 [%0], %1;" ::"l"(addr), "l"(v) : "memory");
+}
+
+struct SplitSmem {
+  alignas(128) uint64_t a[2][SP_TILE];     // column tiles as they lie in memory (TMA destinations)
+  alignas(16) uint64_t b[SP_SLOTS + 2];    // the same rows in partition order, runs padded to destination parity
+  alignas(8) uint64_t colbase[SP_MAX_R];   // address of slot 0's row if slot 0 belonged to partition p (this column)
+  int64_t gof[SP_MAX_R];                   // first output row of this tile in partition p
+  uint64_t bar[2];
+  int32_t rsm[SP_MAX_R];                   // first slot of partition p's run
+  uint16_t wc[SP_WARPS][SP_MAX_R];         // rows of partition p in the warps before this one
+  alignas(4) uint16_t spart[SP_SLOTS + 2]; // partition of the row in slot s (SP_PAD: no row)
+  int32_t wsum[SP_WARPS];
+  int32_t nslots;
+};
+
+template <int NK, int MODE>
+__global__ void __launch_bounds__(SP_THREADS, 3) k_split_scatter(SplitSrc s, SplitCols cols, int64_t n, int64_t ntiles,
+                                                                 int R, const int64_t* __restrict__ hist,
+                                                                 const uint64_t* __restrict__ dst_tab) {
+  extern __shared__ __align__(128) unsigned char sp_raw[];
+  SplitSmem& sm = *reinterpret_cast<SplitSmem*>(sp_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t tile = blockIdx.x;
+  const int64_t tbase = tile * SP_TILE;
+  const int nt = (int)((n - tbase) < SP_TILE ? (n - tbase) : SP_TILE);   // rows of this tile
+  const uint32_t bulk_bytes = (uint32_t)(nt & ~1) * 8u;
+
+  if (tid == 0) {
+    sp_mbar_init(&sm.bar[0], 1);
+    sp_mbar_init(&sm.bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = tid; i < SP_WARPS * SP_MAX_R; i += SP_THREADS) (&sm.wc[0][0])[i] = 0;
+  for (int i = tid; i < SP_SLOTS + 2; i += SP_THREADS) sm.spart[i] = (uint16_t)SP_PAD;
+  __syncthreads();
+  // a column tile is fetched by the TMA unit when its address is 16-byte aligned (tile offsets are)
+  auto tma_ok = [&](int c) { return ((uintptr_t)cols.in[c] & 15) == 0 && bulk_bytes != 0; };
+  if (tid == 0 && cols.n > 0 && tma_ok(0)) sp_bulk_load(sm.a[0], cols.in[0] + tbase, bulk_bytes, &sm.bar[0]);
+
+  // ---- phase A: partition id and rank inside (warp, partition) of every row ------------------------------------
+  const bool pow2 = (s.R & (s.R - 1)) == 0;
+  const unsigned lt = mgb_lanemask_lt();
+  const int jbase = warp * (SP_TILE / SP_WARPS) + lane;
+  uint32_t dr[SP_ROUNDS];   // partition | rank << 16, later the slot of the row
+  int32_t dummy_bad;
+#pragma unroll
+  for (int r = 0; r < SP_ROUNDS; ++r) {
+    const int j = jbase + r * 32;
+    const bool valid = j < nt;
+    const uint32_t d = valid ? sp_pid<NK, MODE>(s, tbase + j, pow2, &dummy_bad) : (uint32_t)(SP_MAX_R + lane);
+    const unsigned peers = __match_any_sync(0xffffffffu, d);
+    uint32_t before = 0;
+    if (valid) before = sm.wc[warp][d];
+    __syncwarp();
+    if (valid && (peers & lt) == 0) sm.wc[warp][d] = (uint16_t)(before + __popc(peers));
+    __syncwarp();
+    dr[r] = d | ((before + __popc(peers & lt)) << 16);
+  }
+  __syncthreads();
+  // ---- phase B: runs.  Partition p gets count + 1 slots; its run starts on the slot whose parity equals the
+  // parity of its first destination row, so that (even, odd) slot pairs are 16-byte aligned destination pairs.
+  {
+    int cnt = 0;
+    int64_t g = 0;
+    if (tid < R) {
+#pragma unroll
+      for (int w = 0; w < SP_WARPS; ++w) {
+        const int t = sm.wc[w][tid];
+        sm.wc[w][tid] = (uint16_t)cnt;
+        cnt += t;
+      }
+      const int64_t abs0 = hist[(int64_t)tid * ntiles + tile];
+      g = dst_tab ? abs0 - hist[(int64_t)tid * ntiles] : abs0;
+    }
+    int v = tid < R ? cnt + 1 : 0;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) sm.wsum[warp] = inc;
+    __syncthreads();
+    int add = 0;
+#pragma unroll
+    for (int w = 0; w < SP_WARPS; ++w)
+      if (w < warp) add += sm.wsum[w];
+    const int excl = add + inc - v;
+    if (tid < R) {
+      const int rs = excl + (int)((excl ^ (int)g) & 1);
+      sm.rsm[tid] = rs;
+      sm.gof[tid] = g;
+    }
+    if (tid == SP_THREADS - 1) sm.nslots = (add + inc + 2) & ~1;
+  }
+  __syncthreads();
+  // ---- phase C: slot of every row -----------------------------------------------------------------------------
+#pragma unroll
+  for (int r = 0; r < SP_ROUNDS; ++r) {
+    const int j = jbase + r * 32;
+    if (j < nt) {
+      const uint32_t d = dr[r] & 0xffffu;
+      const uint32_t slot = (uint32_t)sm.rsm[d] + sm.wc[warp][d] + (dr[r] >> 16);
+      sm.spart[slot] = (uint16_t)d;
+      dr[r] = slot;
+    }
+  }
+  // ---- columns ---------------------------------------------------------------------------------------------------
+  uint32_t uses0 = 0, uses1 = 0;
+  for (int c = 0; c < cols.n; ++c) {
+    const int buf = c & 1;
+    if (tid < R) {
+      const uint64_t base = dst_tab ? dst_tab[(int64_t)c * R + tid] : (uint64_t)cols.out[c];
+      sm.colbase[tid] = base + 8ull * (uint64_t)(sm.gof[tid] - (int64_t)sm.rsm[tid]);
+    }
+    if (tid == 0 && c + 1 < cols.n && tma_ok(c + 1))
+      sp_bulk_load(sm.a[buf ^ 1], cols.in[c + 1] + tbase, bulk_bytes, &sm.bar[buf ^ 1]);
+    const uint64_t* src = cols.in[c] + tbase;
+    if (tma_ok(c)) {
+      const uint32_t use = buf ? uses1++ : uses0++;
+      sp_mbar_wait(&sm.bar[buf], use & 1);
+#pragma unroll
+      for (int r = 0; r < SP_ROUNDS; ++r) {
+        const int j = jbase + r * 32;
+        if (j < nt) sm.b[dr[r]] = (j == nt - 1 && (nt & 1)) ? mgb_ld_stream(src + j) : sm.a[buf][j];
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < SP_ROUNDS; ++r) {
+        const int j = jbase + r * 32;
+        if (j < nt) sm.b[dr[r]] = mgb_ld_stream(src + j);
+      }
+    }
+    __syncthreads();
+    const int npairs = sm.nslots >> 1;
+    for (int q = tid; q < npairs; q += SP_THREADS) {
+      const uint32_t pp = *reinterpret_cast<const uint32_t*>(&sm.spart[2 * q]);
+      const uint32_t p0 = pp & 0xffffu, p1 = pp >> 16;
+      if (pp == 0xffffffffu) continue;
+      const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(&sm.b[2 * q]);
+      const uint64_t a0 = p0 != SP_PAD ? sm.colbase[p0] + 16ull * (uint64_t)q : 0;
+      if (p0 == p1 && (a0 & 15) == 0) {
+        sp_st128(a0, v);
+      } else {
+        if (p0 != SP_PAD) sp_st64(a0, v.x);
+        if (p1 != SP_PAD) sp_st64(sm.colbase[p1] + 16ull * (uint64_t)q + 8, v.y);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------------------------------
+static int split_check(const int64_t* const* key_cols, int32_t n_keys, int32_t mode, const int32_t* pid, int64_t n_rows,
+                       int32_t R) {
+  MGB_REQUIRE(mode >= 0 && mode <= 2, MGB_ERR_INVALID, "mode=%d", mode);
+  MGB_REQUIRE(R >= 1 && R <= SP_MAX_R, MGB_ERR_UNSUPPORTED, "n_partitions=%d outside [1,%d]", R, SP_MAX_R);
+  MGB_REQUIRE(n_rows >= 0 && n_rows < 0x7fffffffLL, MGB_ERR_UNSUPPORTED, "n_rows=%lld", (long long)n_rows);
+  if (mode == 2) {
+    MGB_REQUIRE(pid || n_rows == 0, MGB_ERR_INVALID, "null partition ids");
+  } else {
+    MGB_REQUIRE(n_keys >= 1 && n_keys <= MGB_MAX_KEYS, MGB_ERR_UNSUPPORTED, "n_keys=%d outside [1,%d]", n_keys,
+                MGB_MAX_KEYS);
+    MGB_REQUIRE(key_cols || n_rows == 0, MGB_ERR_INVALID, "null key columns");
+  }
+  return MGB_OK;
+}
+
+static SplitSrc split_src(const int64_t* const* key_cols, int32_t n_keys, int32_t mode, const int32_t* pid, int32_t R) {
+  SplitSrc s;
+  for (int j = 0; j < MGB_MAX_KEYS; ++j) s.k[j] = (mode != 2 && j < n_keys) ? key_cols[j] : nullptr;
+  s.pid = pid;
+  s.R = (uint64_t)R;
+  return s;
+}
+
+#define SP_DISPATCH(KERNEL, ...)                                     \
+  do {                                                               \
+    if (mode == 2) {                                                 \
+      KERNEL<1, 2> __VA_ARGS__;                                      \
+    } else if (mode == 1) {                                          \
+      if (n_keys == 1) {                                             \
+        KERNEL<1, 1> __VA_ARGS__;                                    \
+      } else {                                                       \
+        KERNEL<2, 1> __VA_ARGS__;                                    \
+      }                                                              \
+    } else {                                                         \
+      if (n_keys == 1) {                                             \
+        KERNEL<1, 0> __VA_ARGS__;                                    \
+      } else {                                                       \
+        KERNEL<2, 0> __VA_ARGS__;                                    \
+      }                                                              \
+    }                                                                \
+  } while (0)
+
+extern "C" int mgb_split_tiles(int64_t n_rows, int64_t* out_tiles) {
+  MGB_REQUIRE(out_tiles && n_rows >= 0, MGB_ERR_INVALID, "bad argument");
+  *out_tiles = (n_rows + SP_TILE - 1) / SP_TILE;
+  return MGB_OK;
+}
+
+int mgb_split_plan_ex(const int64_t* const* key_cols, int32_t n_keys, int32_t mode, const int32_t* pid, int64_t n_rows,
+                      int32_t R, int64_t* tile_hist, int64_t* out_offsets, int32_t* bad, cudaStream_t st) {
+  MGB_TRY(split_check(key_cols, n_keys, mode, pid, n_rows, R));
+  MGB_REQUIRE(out_offsets, MGB_ERR_INVALID, "null out_offsets");
+  if (n_rows == 0) {
+    MGB_CUDA(cudaMemsetAsync(out_offsets, 0, sizeof(int64_t) * ((size_t)R + 1), st));
+    return MGB_OK;
+  }
+  MGB_REQUIRE(tile_hist, MGB_ERR_INVALID, "null tile histogram");
+  const int64_t ntiles = (n_rows + SP_TILE - 1) / SP_TILE;
+  SplitSrc s = split_src(key_cols, n_keys, mode, pid, R);
+  SP_DISPATCH(k_split_hist, <<<(unsigned)ntiles, SP_THREADS, 0, st>>>(s, n_rows, ntiles, R, tile_hist, bad));
+  MGB_CHECK_LAUNCH();
+  MGB_TRY(mgb_scan_exclusive_i64(tile_hist, (int64_t)R * ntiles, nullptr, st));
+  k_split_offsets<<<1, 288, 0, st>>>(tile_hist, ntiles, R, n_rows, out_offsets);
+  MGB_CHECK_LAUNCH();
+  return MGB_OK;
+}
+
+extern "C" int mgb_split_plan(const int64_t* const* key_cols, int32_t n_keys, int32_t mode, const int32_t* pid,
+                              int64_t n_rows, int32_t n_partitions, int64_t* tile_hist, int64_t* out_offsets,
+                              void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  MGB_REQUIRE(mode != 2, MGB_ERR_UNSUPPORTED, "given partition ids are range-checked by mgb_partition_scatter");
+  MgbProfScope prof(MGB_K_HASH, st);
+  return mgb_split_plan_ex(key_cols, n_keys, mode, pid, n_rows, n_partitions, tile_hist, out_offsets, nullptr, st);
+}
+
+int mgb_split_scatter_ex(const int64_t* const* key_cols, int32_t n_keys, int32_t mode, const int32_t* pid,
+                         int64_t n_rows, int32_t R, const int64_t* tile_hist, const void* const* in_cols, int32_t n_cols,
+                         void* const* out_cols, const uint64_t* dst_table, cudaStream_t st) {
+  MGB_TRY(split_check(key_cols, n_keys, mode, pid, n_rows, R));
+  MGB_REQUIRE(n_cols >= 0, MGB_ERR_INVALID, "negative column count");
+  if (n_rows == 0 || n_cols == 0) return MGB_OK;
+  MGB_REQUIRE(tile_hist && in_cols && (out_cols || dst_table), MGB_ERR_INVALID, "null pointer");
+  static bool attr_set[8] = {false};
+  int dev = 0;
+  MGB_CUDA(cudaGetDevice(&dev));
+  const size_t smem = sizeof(SplitSmem);
+  if (dev >= 0 && dev < 8 && !attr_set[dev]) {
+#define SP_ATTR(NK, MODE) \
+  MGB_CUDA(cudaFuncSetAttribute(k_split_scatter<NK, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))
+    SP_ATTR(1, 0);
+    SP_ATTR(2, 0);
+    SP_ATTR(1, 1);
+    SP_ATTR(2, 1);
+    SP_ATTR(1, 2);
+#undef SP_ATTR
+    attr_set[dev] = true;
+  }
+  const int64_t ntiles = (n_rows + SP_TILE - 1) / SP_TILE;
+  SplitSrc s = split_src(key_cols, n_keys, mode, pid, R);
+  for (int c0 = 0; c0 < n_cols; c0 += SP_MAX_COLS) {
+    SplitCols sc;
+    sc.n = n_cols - c0 < SP_MAX_COLS ? n_cols - c0 : SP_MAX_COLS;
+    for (int c = 0; c < sc.n; ++c) {
+      sc.in[c] = (const uint64_t*)in_cols[c0 + c];
+      sc.out[c] = out_cols ? (uint64_t*)out_cols[c0 + c] : nullptr;
+    }
+    const uint64_t* tab = dst_table ? dst_table + (size_t)c0 * R : nullptr;
+    SP_DISPATCH(k_split_scatter, <<<(unsigned)ntiles, SP_THREADS, smem, st>>>(s, sc, n_rows, ntiles, R, tile_hist, tab));
+    MGB_CHECK_LAUNCH();
+  }
+  return MGB_OK;
+}
+
+extern "C" int mgb_split_scatter(const int64_t* const* key_cols, int32_t n_keys, int32_t mode, const int32_t* pid,
+                                 int64_t n_rows, int32_t n_partitions, const int64_t* tile_hist,
+                                 const void* const* in_cols, int32_t n_cols, void* const* out_cols,
+                                 const uint64_t* dst_table, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  MgbProfScope prof(MGB_K_PARTITION, st);
+  return mgb_split_scatter_ex(key_cols, n_keys, mode, pid, n_rows, n_partitions, tile_hist, in_cols, n_cols, out_cols,
+                              dst_table, st);
+}
+
+// plan + scatter into local columns with a scratch histogram of its own (mgb_hash_partition / mgb_partition_scatter
+// for n_partitions <= 256).  bad (device int32, may be null): set when a given partition id is out of range.
+int mgb_split_local(const int64_t* const* key_cols, int32_t n_keys, int32_t mode, const int32_t* pid, int64_t n_rows,
+                    int32_t R, const void* const* in_cols, void* const* out_cols, int32_t n_cols, int64_t* out_offsets,
+                    int32_t* bad, cudaStream_t st) {
+  MGB_TRY(split_check(key_cols, n_keys, mode, pid, n_rows, R));
+  if (n_rows == 0) {
+    MGB_CUDA(cudaMemsetAsync(out_offsets, 0, sizeof(int64_t) * ((size_t)R + 1), st));
+    return MGB_OK;
+  }
+  const int64_t ntiles = (n_rows + SP_TILE - 1) / SP_TILE;
+  int64_t* hist = nullptr;
+  MGB_CUDA(cudaMallocAsync((void**)&hist, sizeof(int64_t) * (size_t)R * ntiles, st));
+  int status;
+  {
+    MgbProfScope prof(MGB_K_HASH, st);
+    status = mgb_split_plan_ex(key_cols, n_keys, mode, pid, n_rows, R, hist, out_offsets, bad, st);
+  }
+  if (status == MGB_OK) {
+    MgbProfScope prof(MGB_K_PARTITION, st);
+    status = mgb_split_scatter_ex(key_cols, n_keys, mode, pid, n_rows, R, hist, in_cols, n_cols, out_cols, nullptr, st);
+  }
+  cudaFreeAsync(hist, st);
+  return status;
+}

@@ -145,6 +145,43 @@ def hash_partition(keys: Sequence[torch.Tensor], n_partitions: int, cols: Sequen
     return outs, offsets.cpu().tolist()
 
 
+def split_plan(keys: Sequence[torch.Tensor], n_partitions: int, mode: int = 0):
+    """pass 1 of the partition kernel (mgb_split_plan): -> (tile_hist, offsets), both on the device; offsets holds
+    the n_partitions + 1 block boundaries.  No host wait."""
+    lib = _lib.load()
+    keys = [_req(k, f"key {i}", (torch.int64,)) for i, k in enumerate(keys)]
+    n = keys[0].numel()
+    tiles = C.c_int64()
+    check(lib.mgb_split_tiles(n, C.byref(tiles)))
+    dev = keys[0].device
+    hist = torch.empty(max(1, tiles.value * n_partitions), dtype=torch.int64, device=dev)
+    offsets = torch.empty(n_partitions + 1, dtype=torch.int64, device=dev)
+    check(lib.mgb_split_plan(_ptrs(keys), len(keys), int(mode), None, n, int(n_partitions), hist.data_ptr(),
+                             offsets.data_ptr(), _stream()))
+    _count(5 if n else 1)
+    return hist, offsets
+
+
+def split_scatter(keys: Sequence[torch.Tensor], n_partitions: int, hist: torch.Tensor, cols: Sequence[torch.Tensor],
+                  outs: Optional[Sequence[torch.Tensor]] = None, table: Optional[torch.Tensor] = None, mode: int = 0):
+    """pass 2 (mgb_split_scatter): every row of ``cols`` written once to its block -- into ``outs`` (block p of column
+    c at outs[c][offsets[p]:offsets[p + 1]]) or, with ``table`` (device int64 [n_cols * n_partitions] of addresses,
+    possibly in IPC-mapped peer memory), to (uint64*)table[c * n_partitions + p] + row-in-block."""
+    lib = _lib.load()
+    keys = [_req(k, f"key {i}", (torch.int64,)) for i, k in enumerate(keys)]
+    cols = [_req(c, f"column {i}") for i, c in enumerate(cols)]
+    n = keys[0].numel()
+    if table is not None:
+        if not table.is_cuda or table.dtype != torch.int64 or table.numel() != len(cols) * n_partitions:
+            raise MarsGBError(1, "destination table must be a CUDA int64 tensor of n_cols * n_partitions addresses")
+    elif outs is None or len(outs) != len(cols):
+        raise MarsGBError(1, "split_scatter needs output columns or a destination table")
+    check(lib.mgb_split_scatter(_ptrs(keys), len(keys), int(mode), None, n, int(n_partitions), hist.data_ptr(),
+                                _ptrs(cols), len(cols), _ptrs(outs) if table is None else None,
+                                table.data_ptr() if table is not None else None, _stream()))
+    _count(-(-len(cols) // 80) if n and cols else 0)
+
+
 # ------------------------------------------------------------------------------------------ aggregation
 class Aggregator:
     """Streaming hash aggregation: update() any number of row batches, then result()."""
@@ -974,10 +1011,3 @@ def gather_rows(cols: Sequence[torch.Tensor], perm: torch.Tensor) -> List[torch.
     check(lib.mgb_gather_rows(_ptrs(cols), _ptrs(outs), len(cols), perm.data_ptr(), n, _stream()))
     _count(1 if n and cols else 0)
     return outs
-
-
-def bench_atomics(mode: int, n_rows: int, n_slots: int, iters: int = 5) -> float:
-    lib = _lib.load()
-    ms = C.c_float()
-    check(lib.mgb_bench_atomics(mode, n_rows, n_slots, iters, C.byref(ms), _stream()))
-    return ms.value

@@ -729,3 +729,59 @@ def test_hash_partition_equals_ids_plus_stable_split(K, n_keys, n, R):
     assert offsets == exp_off
     for got, src in zip(outs, cols):
         np.testing.assert_array_equal(got.cpu().numpy(), src[order])
+
+
+@pytest.mark.parametrize("n_keys,mode", [(1, 0), (2, 0), (1, 1), (2, 1)])
+@pytest.mark.parametrize("n,R", [(1, 3), (2047, 5), (2049, 8), (123_457, 8), (500_001, 256), (40_000, 1)])
+def test_split_two_passes_with_destination_table(K, n_keys, mode, n, R):
+    """the partition kernel in its two passes (mgb_split_plan / mgb_split_scatter): block sizes first, then every row
+    written once to an address taken from a destination table -- here blocks laid out back to front with gaps, in
+    one buffer per column; column views at odd 8-byte offsets (no TMA, no 16-byte stores) give the same bytes"""
+    rng = np.random.default_rng(n * 7 + R + mode)
+    keys = [rng.integers(-10 ** 6, 10 ** 6, n, dtype=np.int64) for _ in range(n_keys)]
+    cols = keys + [rng.random(n), np.arange(n, dtype=np.int64), rng.normal(size=n)]
+    pid = ((orc.hash_frame_rows(keys) % np.uint64(R)).astype(np.int64) if mode == 1 else orc.partition_ids(keys, R))
+    order = np.argsort(pid, kind="stable")
+    counts = np.bincount(pid, minlength=R)
+    dk = [dev(k) for k in keys]
+    # odd element offset for every second column: source not 16-byte aligned
+    dcols = []
+    for i, c in enumerate(cols):
+        if i % 2:
+            buf = torch.empty(n + 1, dtype=torch.from_numpy(c).dtype, device="cuda")
+            buf[1:] = dev(c)
+            dcols.append(buf[1:])
+        else:
+            dcols.append(dev(c))
+    dcols[:n_keys] = dk
+    hist, offsets = K.split_plan(dk, R, mode)
+    off = offsets.cpu().numpy()
+    np.testing.assert_array_equal(off, np.concatenate([[0], np.cumsum(counts)]))
+    # local mode
+    outs = [torch.full_like(c, -1) for c in dcols]
+    K.split_scatter(dk, R, hist, dcols, outs=outs, mode=mode)
+    for got, src in zip(outs, cols):
+        np.testing.assert_array_equal(got.cpu().numpy(), src[order])
+    # table mode: block p of column c at element start[p] (+1 for odd columns: unaligned destinations) of arena c
+    gap = 3
+    start = np.zeros(R, dtype=np.int64)
+    pos = 0
+    for p in reversed(range(R)):
+        start[p] = pos
+        pos += (counts[p] + gap + 1) & ~1
+    arenas = [torch.full((pos + 2,), -7, dtype=torch.int64, device="cuda") for _ in cols]
+    table = np.zeros((len(cols), R), dtype=np.int64)
+    for c in range(len(cols)):
+        table[c] = arenas[c].data_ptr() + 8 * (start + (c % 2))
+    K.split_scatter(dk, R, hist, dcols, table=dev(table.reshape(-1)), mode=mode)
+    torch.cuda.synchronize()
+    for c, src in enumerate(cols):
+        a = arenas[c].cpu().numpy()
+        sorted_src = src[order]
+        touched = np.zeros(len(a), dtype=bool)
+        for p in range(R):
+            s0 = start[p] + (c % 2)
+            blk = a[s0:s0 + counts[p]]
+            np.testing.assert_array_equal(blk.view(src.dtype), sorted_src[off[p]:off[p + 1]])
+            touched[s0:s0 + counts[p]] = True
+        assert (a[~touched] == -7).all(), "a store outside the blocks"
