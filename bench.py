@@ -473,6 +473,25 @@ def main_ours(args):
             parity = {"ok": False, "mode": f"check failed to run: {e!r}"}
 
     dev_step_ms = step_ms[id(dev_frames), True]
+    # N > 1: the hash-shuffle branch across the ranks (cfg3-shaped, weak scaling: 125 M rows per GPU = the config's
+    # full size at 8 GPUs) -- whole-path rows/s, NVLink rate of the fused partition -> peer transfer, parity
+    shuffle = None
+    if world > 1 and not args.no_shuffle:
+        del host_frames
+        torch.cuda.empty_cache()
+        from mars_b200 import parallel
+        import shuffle_leg
+
+        try:
+            ex = parallel.init_exchange()
+            shuffle = shuffle_leg.run(ex, "cfg3", rows_per_gpu=args.shuffle_rows, chunk_rows=15_625_000,
+                                      steps=max(2, min(args.steps, 3)), warmup=2)
+            ex.transport.close()
+        except Exception as e:  # noqa: BLE001
+            import traceback
+
+            shuffle = {"error": repr(e)[:300], "trace": traceback.format_exc()[-600:]}
+        host_frames = []
     configs = None
     if rank == 0 and world == 1 and not args.no_configs:
         del host_frames, dev_frames
@@ -546,6 +565,7 @@ def main_ours(args):
             "clocks": clocks,
             "cpu_baseline": cpu_baseline,
             "configs": configs,
+            "shuffle": shuffle,
         }
         print(json.dumps(line), flush=True)
     if comm is not None:
@@ -564,6 +584,8 @@ def main():
     ap.add_argument("--chunk-rows", type=int, default=CHUNK_ROWS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the sub-records of the other BASELINE.json configs")
+    ap.add_argument("--no-shuffle", action="store_true", help="N > 1: skip the hash-shuffle leg")
+    ap.add_argument("--shuffle-rows", type=int, default=125_000_000, help="rows per GPU of the shuffle leg (cfg3-shaped)")
     ap.add_argument("--no-clocks", action="store_true", help="diagnostics: do not start the nvidia-smi clock sampler")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

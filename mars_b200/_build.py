@@ -19,7 +19,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC",
-]
+] + os.environ.get("MGB_NVCC_EXTRA", "").split()      # experiments only (e.g. -DBK_THREADS=128)
 
 
 def _nvcc() -> str:

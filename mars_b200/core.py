@@ -245,6 +245,9 @@ class ProcessorContext(dict):
     def __init__(self, *a, **kw):
         super().__init__(*a, **kw)
         self._current_chunk = None
+        # multi-GPU runs with a push transport: hash-shuffle mappers stop after pass 1 of the partition kernel and
+        # the exchange moves the rows (executors.DeferredSplit)
+        self.defer_split = False
 
     def set_current_chunk(self, chunk):
         self._current_chunk = chunk

@@ -5,22 +5,26 @@
 //
 // The hash-table path (mgb_agg.cu) pays one atomic per (row, accumulator) into a table sized by the row
 // count; at 40 accumulators per row (min/max/var over 8 columns) or ~1e7 distinct keys per chunk that is
-// latency- and init-bound.  Here the rows of ALL sources (update() batches, read in place) are split by the
-// top bits of the key hash into B buckets of <= 512 rows on average:
+// latency- and init-bound.  Here the ROWS of all sources (update() batches, read in place) are moved into bucket
+// order -- B buckets of <= 512 rows on average, bucket = top bits of the key hash -- by a multi-way split in one or
+// two levels of <= 256 ways each (mgb_split.cuh: tile histogram -> scan -> TMA-staged column tiles, permuted on chip,
+// written in runs with 16-byte stores; every level reads and writes each row once, sequentially on both sides):
 //
-//   k_bucket_pack   one sequential pass over the column-major batches: row -> bucket id, and the row itself
-//                   (keys + values) into a ROW-MAJOR staging array through a shared-memory transpose.  The
-//                   gathers of the next kernel then fetch one row = one or two 64-byte DRAM bursts instead
-//                   of one burst per 8-byte column value (measured: 1118 -> ~190 B/row on 80-byte rows).
-//   k_bucket_hist / scan / k_bucket_place
-//                   row ids into bucket order through one atomic cursor per bucket (the order of the rows
-//                   inside a bucket does not matter to the fold, so no stable radix passes are needed)
-//   k_bucket_agg    one CTA per bucket: key table in shared memory (dense group ids), counting sort of the
-//                   bucket's rows by group id, then one thread (one warp for groups of >= 32 rows) per
-//                   (group, value column) folds that group's values into five canonical REGISTER accumulators
-//                   (sum, sum of squares, count, encoded min / max) and stores every accumulator the spec
-//                   asks for once.  No atomics on values; buckets of any length are processed in tiles.
+//   k_bsplit_hist<1> / scan / k_bsplit_plan / k_bsplit_scatter<1>
+//                   level 1: rows of all sources by the top b1 hash bits into a column-major staging array in
+//                   which every partition starts on a tile boundary (so that a tile of level 2 lies in ONE partition)
+//   k_bsplit_hist<2> / scan / k_bsplit_scatter<2> / k_bsplit_off
+//                   level 2: every partition by the next b2 bits; output compact, in bucket order
+//   k_bucket_agg    one CTA per bucket, reading ITS rows as one contiguous range of every column: key table in
+//                   shared memory (dense group ids), counting sort of the bucket's rows by group id, then one
+//                   thread (one warp for groups of >= 32 rows) per (group, value column) folds that group's values
+//                   into five canonical REGISTER accumulators (sum, sum of squares, count, encoded min / max) and
+//                   stores every accumulator the spec asks for once.  No atomics on values.
 //   scan + k_bucket_emit   compaction of the per-bucket results into the caller's columns
+//
+// (Round 1 moved row IDS into bucket order and gathered the rows at random from a row-major copy: 99 B of DRAM
+// traffic per 16-byte row.)  The splits are stable, so the fold order -- and with it every float64 sum -- is the
+// same from run to run.
 //
 // A bucket that holds more groups than its table reports overflow, a bucket far longer than the average (one
 // hot key) is declined before the aggregation kernel runs; the caller then takes the hash-table path.
@@ -29,6 +33,7 @@
 #include <vector>
 
 #include "mgb_layout.cuh"
+#include "mgb_split.cuh"
 
 #ifndef BK_THREADS
 #define BK_THREADS 256
@@ -38,16 +43,13 @@
 #define BK_RT 1024            // rows per tile
 #define BK_TARGET 512         // average rows per bucket (upper bound)
 #define BK_BIG 32             // groups with >= BK_BIG rows in a tile are folded by a whole warp
-#define BK_EPT (BK_TAB / BK_THREADS)   // table entries per thread in the block scan
 #define BK_MAXA 8             // accumulators per value column handled in registers
 #define BK_SKEW_ROWS (64 * BK_TARGET)   // a longer bucket (one hot key) would serialise on one CTA: decline
 
 struct BktParams {
-  const uint64_t* __restrict__ rows;   // row-major staging: row i at rows + i * W, keys first, then the value columns
-  int W;
+  const uint64_t* __restrict__ rows;   // column-major staging in bucket order: column c (keys first) at rows + c * T
   long long T;
   int logB;
-  const int32_t* perm;
   const int64_t* off;
   uint64_t* scratch;
   int64_t* gcount;
@@ -67,61 +69,175 @@ __device__ __forceinline__ int bk_locate(const long long* __restrict__ begin, in
   return lo;
 }
 
-#define BKP_ROWS 256   // rows per tile of the pack kernel (== its block size)
-
-struct BktPackParams {
-  const BktSource* srcs;      // device array
-  const long long* begin;     // device [nsrc + 1]
-  BktSource src0;             // copy of source 0 (single-source fast path)
-  int nsrc, nk, nv;
-  long long T;
-  int logB;
-  int32_t* pid;
-  uint64_t* rows;
+// ---- multi-way split of the rows into bucket order ---------------------------------------------------------------
+struct BsSources {
+  const BktSource* srcs;        // device array
+  const long long* row_begin;   // device [nsrc + 1]: first global row of every source
+  const long long* tile_begin;  // device [nsrc + 1]: first tile of every source (sources are tiled one by one)
+  BktSource src0;               // copy of source 0 (single-source fast path)
+  long long rows0;
+  int nsrc;
 };
 
-// Tile of 256 rows: every thread reads its row column by column (coalesced across the warp), the tile is
-// transposed through shared memory (row stride padded to an odd number of words: no bank conflicts) and
-// written out as 256 * W contiguous words.
-template <int NK>
-__global__ void __launch_bounds__(BKP_ROWS) k_bucket_pack(const BktPackParams p) {
-  extern __shared__ uint64_t tile[];
-  const int W = p.nk + p.nv, Wp = W | 1;
-  const long long ntiles = (p.T + BKP_ROWS - 1) / BKP_ROWS;
-  for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
-    const long long i = t * BKP_ROWS + threadIdx.x;
-    if (i < p.T) {
-      const BktSource* src = &p.src0;
-      long long loc = i;
-      if (p.nsrc > 1) {
-        const int s = bk_locate(p.begin, p.nsrc, i);
-        src = &p.srcs[s];
-        loc = i - __ldg(&p.begin[s]);
-      }
-      uint64_t* row = tile + threadIdx.x * Wp;
-      int64_t k[NK];
+struct BsLevel2 {
+  const uint64_t* stage;        // level-1 output: column c at stage + c * stride, partitions padded to tiles
+  long long stride;
+  const long long* po;          // [P1 + 1] first (padded) row of every partition
+  const long long* cnt;         // [P1] rows of every partition
+  const int32_t* tile_part;     // [NT] partition of every tile, -1 beyond the last one
+};
+
+// where a tile's rows lie: column c starts at col(c); `rows` of them are valid
+template <int LEVEL>
+struct BsTileSrc {
+  const BktSource* src;      // LEVEL 1: the update() batch the tile belongs to
+  const uint64_t* base;      // LEVEL 2: level-1 staging, column c at base + c * stride
+  long long stride, r0;
+  int nk, rows;
+  __device__ __forceinline__ const uint64_t* col(int c) const {
+    if (LEVEL == 1) return (c < nk ? src->keys[c] : src->vals[c - nk]) + r0;
+    return base + (long long)c * stride + r0;
+  }
+};
+
+template <int LEVEL>
+__device__ __forceinline__ BsTileSrc<LEVEL> bs_tile(const BsSources& S, const BsLevel2& L2, long long tile, int nk) {
+  BsTileSrc<LEVEL> t;
+  t.nk = nk;
+  t.src = &S.src0;
+  t.base = L2.stage;
+  t.stride = L2.stride;
+  long long left;
+  if (LEVEL == 1) {
+    long long lt = tile, rows = S.rows0;
+    if (S.nsrc > 1) {
+      const int s_ = bk_locate(S.tile_begin, S.nsrc, tile);
+      t.src = &S.srcs[s_];
+      lt = tile - __ldg(&S.tile_begin[s_]);
+      rows = __ldg(&S.row_begin[s_ + 1]) - __ldg(&S.row_begin[s_]);
+    }
+    t.r0 = lt * SP_TILE;
+    left = rows - t.r0;
+  } else {
+    const int p = L2.tile_part[tile];
+    t.r0 = tile * SP_TILE;
+    left = p < 0 ? 0 : L2.po[p] + L2.cnt[p] - t.r0;
+  }
+  t.rows = (int)(left < 0 ? 0 : (left < SP_TILE ? left : SP_TILE));
+  return t;
+}
+
+template <int NK, int LEVEL>
+__device__ __forceinline__ uint32_t bs_digit(const BsTileSrc<LEVEL>& t, int j, int shift, uint32_t mask) {
+  int64_t k[NK];
 #pragma unroll
-      for (int j = 0; j < NK; ++j) {
-        const uint64_t v = mgb_ld_stream(src->keys[j] + loc);
-        k[j] = (int64_t)v;
-        row[j] = v;
-      }
-      const uint64_t sh = mgb_slot_hash(mgb_hash_tuple<NK>(k));
-      p.pid[i] = p.logB ? (int32_t)(sh >> (64 - p.logB)) : 0;
-#pragma unroll 4
-      for (int c = 0; c < p.nv; ++c) row[NK + c] = mgb_ld_stream(src->vals[c] + loc);
-    }
-    __syncthreads();
-    const long long base = t * BKP_ROWS;
-    const int nrow = (int)((p.T - base) < BKP_ROWS ? (p.T - base) : BKP_ROWS);
-    const int nword = nrow * W;
-    const uint32_t inv = 0xffffffffu / (uint32_t)W + 1u;
-    uint64_t* out = p.rows + base * W;
-    for (int idx = threadIdx.x; idx < nword; idx += BKP_ROWS) {
-      const int r = W == 1 ? idx : (int)__umulhi((uint32_t)idx, inv);
-      out[idx] = tile[r * Wp + (idx - r * W)];
-    }
-    __syncthreads();
+  for (int q = 0; q < NK; ++q) k[q] = (int64_t)mgb_ld_stream(t.col(q) + j);
+  return (uint32_t)(mgb_slot_hash(mgb_hash_tuple<NK>(k)) >> shift) & mask;
+}
+
+template <int NK, int LEVEL>
+__global__ void __launch_bounds__(SP_THREADS) k_bsplit_hist(const BsSources S, const BsLevel2 L2, long long NT, int shift,
+                                                            int R, int64_t* __restrict__ hist) {
+  __shared__ uint32_t cnt[SP_MAX_R];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x < SP_MAX_R) cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const long long tile = blockIdx.x;
+  const BsTileSrc<LEVEL> ts = bs_tile<LEVEL>(S, L2, tile, NK);
+  const int nt = ts.rows;
+  const uint32_t mask = (uint32_t)R - 1u;
+  uint32_t dg[SP_ROUNDS];
+#pragma unroll
+  for (int r = 0; r < SP_ROUNDS; ++r) {   // all key loads of the thread in flight together
+    const int j = warp * (SP_TILE / SP_WARPS) + r * 32 + lane;
+    dg[r] = j < nt ? bs_digit<NK, LEVEL>(ts, j, shift, mask) : 0xffffffffu;
+  }
+#pragma unroll
+  for (int r = 0; r < SP_ROUNDS; ++r)
+    if (dg[r] != 0xffffffffu) atomicAdd(&cnt[dg[r]], 1u);
+  __syncthreads();
+  for (int p = threadIdx.x; p < R; p += SP_THREADS) hist[(long long)p * NT + tile] = cnt[p];
+}
+
+// after the scan of the level-1 histogram: rows per partition, partitions padded to whole tiles, tile -> partition
+__global__ void __launch_bounds__(256) k_bsplit_plan(const int64_t* __restrict__ hist, long long NT, int P1, long long T,
+                                                     long long* __restrict__ po, long long* __restrict__ cnt,
+                                                     int32_t* __restrict__ tile_part, long long NT2) {
+  __shared__ long long tiles[257];
+  const int p = threadIdx.x;
+  long long c = 0, nt = 0;
+  if (p < P1) {
+    c = (p + 1 < P1 ? hist[(long long)(p + 1) * NT] : T) - hist[(long long)p * NT];
+    nt = (c + SP_TILE - 1) / SP_TILE;
+    cnt[p] = c;
+  }
+  tiles[p + 1] = nt;
+  if (p == 0) tiles[0] = 0;
+  __syncthreads();
+  if (p == 0)
+    for (int q = 1; q <= 256; ++q) tiles[q] += tiles[q - 1];
+  __syncthreads();
+  if (p < P1) {
+    po[p] = tiles[p] * SP_TILE;
+    for (long long t = tiles[p]; t < tiles[p + 1] && t < NT2; ++t) tile_part[t] = p;
+  }
+  if (p == 0) po[P1] = tiles[P1] * SP_TILE;
+  const long long last = tiles[256];
+  for (long long t = last + p; t < NT2; t += 256) tile_part[t] = -1;
+}
+
+template <int NK, int LEVEL>
+struct BucketTile {
+  BsTileSrc<LEVEL> ts;
+  const int64_t* __restrict__ hist;
+  const long long* __restrict__ po;   // level 1 with a second level to follow: padded partition starts; else nullptr
+  uint64_t* out;
+  long long out_stride, NT, tile;
+  int shift;
+  uint32_t mask;
+  __device__ __forceinline__ uint32_t digit(int j) const { return bs_digit<NK, LEVEL>(ts, j, shift, mask); }
+  __device__ __forceinline__ int64_t dest_row(int d) const {
+    const int64_t abs0 = hist[(long long)d * NT + tile];
+    return po ? po[d] + (abs0 - hist[(long long)d * NT]) : abs0;
+  }
+  __device__ __forceinline__ const uint64_t* src(int c) const { return ts.col(c); }
+  __device__ __forceinline__ uint64_t dst(int c, int) const { return (uint64_t)(out + (long long)c * out_stride); }
+};
+
+template <int NK, int LEVEL>
+__global__ void __launch_bounds__(SP_THREADS, 3) k_bsplit_scatter(const BsSources S, const BsLevel2 L2, long long NT,
+                                                                  int shift, int R, int ncols,
+                                                                  const int64_t* __restrict__ hist,
+                                                                  const long long* __restrict__ po, uint64_t* out,
+                                                                  long long out_stride) {
+  extern __shared__ __align__(128) unsigned char sp_raw[];
+  SplitSmem& sm = *reinterpret_cast<SplitSmem*>(sp_raw);
+  BucketTile<NK, LEVEL> f;
+  f.ts = bs_tile<LEVEL>(S, L2, blockIdx.x, NK);
+  f.hist = hist;
+  f.po = po;
+  f.out = out;
+  f.out_stride = out_stride;
+  f.NT = NT;
+  f.tile = blockIdx.x;
+  f.shift = shift;
+  f.mask = (uint32_t)R - 1u;
+  if (f.ts.rows == 0) return;
+  sp_tile_split<false>(sm, f.ts.rows, R, ncols, f);
+}
+
+// bucket boundaries.  One level: bucket b = digit b, off[b] = hist[b][0].  Two levels: the rows leave level 2 ordered
+// by (digit 2, partition, tile), so bucket (d2, p) is contiguous: off[d2 * P1 + p] = hist2[d2][first tile of p].
+__global__ void __launch_bounds__(256) k_bsplit_off(const int64_t* __restrict__ hist, long long NT, int P1, int B,
+                                                    const long long* __restrict__ po, long long T,
+                                                    int64_t* __restrict__ off) {
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b <= B; b += gridDim.x * blockDim.x) {
+    if (b == B)
+      off[b] = T;
+    else if (!po)
+      off[b] = hist[(long long)b * NT];
+    else
+      off[b] = hist[(long long)(b / P1) * NT + po[b % P1] / SP_TILE];
   }
 }
 
@@ -186,16 +302,17 @@ __device__ __forceinline__ void bk_comp_add(double& s, double& c, const double v
   s = t;
 }
 
-template <int NK>
-__global__ void __launch_bounds__(BK_THREADS, 5) k_bucket_agg(const BktParams p) {
+// NEED: which canonical accumulators some column of the spec asks for (1 = sum of squares, 2 = min / max); the
+// others are not computed
+template <int NK, int NEED, int TH>
+__global__ void __launch_bounds__(TH, 1280 / TH) k_bucket_agg(const BktParams p) {
   __shared__ uint64_t tab_keys[NK * BK_TAB];
   __shared__ int tab_idx[BK_TAB];
   __shared__ int cnt[BK_TAB + 1];      // rows per group of the current tile -> exclusive starts
   __shared__ int cursor[BK_TAB];
-  __shared__ uint32_t r_loc[BK_RT];
   __shared__ uint16_t r_gid[BK_RT];
   __shared__ uint16_t sorted[BK_RT];
-  __shared__ int warp_tot[BK_THREADS / 32];
+  __shared__ int warp_tot[TH / 32];
   __shared__ int big[BK_RT / BK_BIG];   // groups with >= BK_BIG rows in the current tile
   __shared__ int n_unique, failed, n_big;
 
@@ -209,7 +326,7 @@ __global__ void __launch_bounds__(BK_THREADS, 5) k_bucket_agg(const BktParams p)
   const long long T = p.T;
   const Layout& L = p.L;
   const int nk = L.nk, nv = L.nv;
-  for (int i = tid; i < BK_TAB; i += BK_THREADS) tab_idx[i] = -1;
+  for (int i = tid; i < BK_TAB; i += TH) tab_idx[i] = -1;
   if (tid == 0) {
     n_unique = 0;
     failed = 0;
@@ -219,17 +336,16 @@ __global__ void __launch_bounds__(BK_THREADS, 5) k_bucket_agg(const BktParams p)
   for (long long tlo = lo; tlo < hi; tlo += BK_RT) {
     const int m = (int)((hi - tlo) < BK_RT ? (hi - tlo) : BK_RT);
     const int ng_before = n_unique;
-    for (int i = tid; i <= BK_TAB; i += BK_THREADS) cnt[i] = 0;
+    for (int i = tid; i <= BK_TAB; i += TH) cnt[i] = 0;
     if (tid == 0) n_big = 0;
     __syncthreads();
     // 1. rows of the tile: key gather, group id, histogram by group
-    for (int r0 = 0; r0 < m; r0 += BK_THREADS) {   // uniform trip count: the table insert votes per warp
+    for (int r0 = 0; r0 < m; r0 += TH) {   // uniform trip count: the table insert votes per warp
       const int r = r0 + tid;
       const bool valid = r < m;
-      const long long i = valid ? (long long)p.perm[tlo + r] : 0;
       uint64_t k[NK];
 #pragma unroll
-      for (int j = 0; j < NK; ++j) k[j] = valid ? __ldg(p.rows + i * p.W + j) : 0;
+      for (int j = 0; j < NK; ++j) k[j] = valid ? mgb_ld_stream(p.rows + (long long)j * T + tlo + r) : 0;
       const uint64_t sh = mgb_slot_hash(mgb_hash_tuple<NK>((const int64_t*)k));
       const uint32_t slot = (uint32_t)(sh >> (54 - p.logB)) & (BK_TAB - 1);
       const int g = bk_find_or_insert<NK>(tab_keys, tab_idx, &n_unique, valid, k, slot, p.scratch, T, lo);
@@ -238,7 +354,6 @@ __global__ void __launch_bounds__(BK_THREADS, 5) k_bucket_agg(const BktParams p)
           failed = 1;
         } else {
           r_gid[r] = (uint16_t)g;
-          r_loc[r] = (uint32_t)i;
           atomicAdd(&cnt[g], 1);
         }
       }
@@ -249,13 +364,13 @@ __global__ void __launch_bounds__(BK_THREADS, 5) k_bucket_agg(const BktParams p)
       return;
     }
     const int ng = n_unique;
-    // 2. exclusive scan of cnt[0..ng) (BK_EPT consecutive entries per thread)
+    // 2. exclusive scan of cnt[0..ng) ((BK_TAB / TH) consecutive entries per thread)
     {
-      const int base = tid * BK_EPT;
-      int v[BK_EPT];
+      const int base = tid * (BK_TAB / TH);
+      int v[(BK_TAB / TH)];
       int tot = 0;
 #pragma unroll
-      for (int q = 0; q < BK_EPT; ++q) {
+      for (int q = 0; q < (BK_TAB / TH); ++q) {
         v[q] = base + q < ng ? cnt[base + q] : 0;
         if (v[q] >= BK_BIG) big[atomicAdd(&n_big, 1)] = base + q;
         tot += v[q];
@@ -271,7 +386,7 @@ __global__ void __launch_bounds__(BK_THREADS, 5) k_bucket_agg(const BktParams p)
       int e = x - tot;
       for (int w = 0; w < warp; ++w) e += warp_tot[w];
 #pragma unroll
-      for (int q = 0; q < BK_EPT; ++q) {
+      for (int q = 0; q < (BK_TAB / TH); ++q) {
         if (base + q < ng) {
           cnt[base + q] = e;
           cursor[base + q] = e;
@@ -282,7 +397,7 @@ __global__ void __launch_bounds__(BK_THREADS, 5) k_bucket_agg(const BktParams p)
     }
     __syncthreads();
     // 3. counting sort of the tile's rows by group
-    for (int r = tid; r < m; r += BK_THREADS) sorted[atomicAdd(&cursor[r_gid[r]], 1)] = (uint16_t)r;
+    for (int r = tid; r < m; r += TH) sorted[atomicAdd(&cursor[r_gid[r]], 1)] = (uint16_t)r;
     __syncthreads();
     // 4. fold: one (group, value column) per thread / per warp
     // pass 0: one thread per (group, column) with < BK_BIG rows; pass 1: one warp per (big group, column)
@@ -294,7 +409,7 @@ __global__ void __launch_bounds__(BK_THREADS, 5) k_bucket_agg(const BktParams p)
       const int per = pass == 0 ? ng : nb;
       const uint32_t inv = pass == 0 ? inv_ng : 0xffffffffu / (uint32_t)nb + 1u;
       const int first = pass == 0 ? tid : warp;
-      const int step = pass == 0 ? BK_THREADS : BK_THREADS / 32;
+      const int step = pass == 0 ? TH : TH / 32;
       for (int idx = first; idx < n_items; idx += step) {
         const int c = per == 1 ? idx : (int)__umulhi((uint32_t)idx, inv);
         const int gi = idx - c * per;
@@ -307,8 +422,7 @@ __global__ void __launch_bounds__(BK_THREADS, 5) k_bucket_agg(const BktParams p)
         // the five canonical accumulators of the column, in registers: sum, sum of squares, count, and the
         // sortable encodings of min / max (table representation, mgb_common.cuh); whichever the spec asks
         // for is picked at the end.  Loads are issued four at a time (they are independent).
-        const uint64_t* col0 = p.rows + nk + c;      // value c of row i at col0[i * W]
-        const long long W = p.W;
+        const uint64_t* col0 = p.rows + (long long)(nk + c) * T + tlo;      // value c of row r of the tile at col0[r]
         const int j0 = pass == 0 ? 0 : lane, jstep = pass == 0 ? 1 : 32;
         // float64 sums are COMPENSATED (Neumaier: running sum + running error term): pandas' group_sum is a
         // Kahan sum (pandas/_libs/groupby.pyx), so the reference's partial sums are the correctly rounded true
@@ -326,7 +440,7 @@ __global__ void __launch_bounds__(BK_THREADS, 5) k_bucket_agg(const BktParams p)
           for (int u = 0; u < 4; ++u) {
             const int jj = j + u * jstep;
             have[u] = jj < n;
-            x[u] = have[u] ? col0[(long long)r_loc[sorted[st + jj]] * W] : 0;
+            x[u] = have[u] ? __ldg(col0 + sorted[st + jj]) : 0;
           }
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
@@ -335,16 +449,20 @@ __global__ void __launch_bounds__(BK_THREADS, 5) k_bucket_agg(const BktParams p)
               if (mgb_is_nan_bits(x[u])) continue;
               const double v = __longlong_as_double((long long)x[u]);
               bk_comp_add(fs, fsc, v);
-              bk_comp_add(fq, fqc, __dmul_rn(v, v));
-              const uint64_t e = mgb_enc_f64(x[u]);
-              mn = e < mn ? e : mn;
-              mx = e > mx ? e : mx;
+              if (NEED & 1) bk_comp_add(fq, fqc, __dmul_rn(v, v));
+              if (NEED & 2) {
+                const uint64_t e = mgb_enc_f64(x[u]);
+                mn = e < mn ? e : mn;
+                mx = e > mx ? e : mx;
+              }
             } else {
               is += x[u];
-              iq += x[u] * x[u];
-              const uint64_t e = mgb_enc_i64(x[u]);
-              mn = e < mn ? e : mn;
-              mx = e > mx ? e : mx;
+              if (NEED & 1) iq += x[u] * x[u];
+              if (NEED & 2) {
+                const uint64_t e = mgb_enc_i64(x[u]);
+                mn = e < mn ? e : mn;
+                mx = e > mx ? e : mx;
+              }
             }
             ++cn;
           }
@@ -353,18 +471,23 @@ __global__ void __launch_bounds__(BK_THREADS, 5) k_bucket_agg(const BktParams p)
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) {
             const double os = __shfl_down_sync(0xffffffffu, fs, o), osc = __shfl_down_sync(0xffffffffu, fsc, o);
-            const double oq = __shfl_down_sync(0xffffffffu, fq, o), oqc = __shfl_down_sync(0xffffffffu, fqc, o);
+            const double oq = (NEED & 1) ? __shfl_down_sync(0xffffffffu, fq, o) : 0.0;
+            const double oqc = (NEED & 1) ? __shfl_down_sync(0xffffffffu, fqc, o) : 0.0;
             bk_comp_add(fs, fsc, os);
             fsc += osc;
-            bk_comp_add(fq, fqc, oq);
-            fqc += oqc;
             is += __shfl_down_sync(0xffffffffu, is, o);
-            iq += __shfl_down_sync(0xffffffffu, iq, o);
             cn += __shfl_down_sync(0xffffffffu, cn, o);
-            const unsigned long long a = __shfl_down_sync(0xffffffffu, mn, o);
-            const unsigned long long z = __shfl_down_sync(0xffffffffu, mx, o);
-            mn = a < mn ? a : mn;
-            mx = z > mx ? z : mx;
+            if (NEED & 1) {
+              bk_comp_add(fq, fqc, oq);
+              fqc += oqc;
+              iq += __shfl_down_sync(0xffffffffu, iq, o);
+            }
+            if (NEED & 2) {
+              const unsigned long long a = __shfl_down_sync(0xffffffffu, mn, o);
+              const unsigned long long z = __shfl_down_sync(0xffffffffu, mx, o);
+              mn = a < mn ? a : mn;
+              mx = z > mx ? z : mx;
+            }
           }
           if (lane != 0) continue;
         }
@@ -393,26 +516,6 @@ __global__ void __launch_bounds__(BK_THREADS, 5) k_bucket_agg(const BktParams p)
     __syncthreads();
   }
   if (tid == 0) p.gcount[b] = n_unique;
-}
-
-// bucket histogram and (unordered) placement of the row ids: within a bucket the order of the rows does not
-// matter to the fold, so one pass with an atomic cursor per bucket replaces the stable radix passes
-__global__ void __launch_bounds__(256) k_bucket_hist(const int32_t* __restrict__ pid, long long T,
-                                                     unsigned long long* __restrict__ counts) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < T; i += (long long)gridDim.x * blockDim.x)
-    atomicAdd(&counts[pid[i]], 1ULL);
-}
-
-__global__ void __launch_bounds__(256) k_bucket_place(const int32_t* __restrict__ pid, long long T,
-                                                      unsigned long long* __restrict__ cursor,
-                                                      int32_t* __restrict__ perm) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < T; i += (long long)gridDim.x * blockDim.x)
-    perm[atomicAdd(&cursor[pid[i]], 1ULL)] = (int32_t)i;
-}
-
-__global__ void __launch_bounds__(256) k_copy_i64(const int64_t* __restrict__ a, int64_t* __restrict__ b, long long n) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    b[i] = a[i];
 }
 
 // longest bucket (skew check)
@@ -481,6 +584,37 @@ static void bk_debug(const char* what, cudaStream_t st) {
   fflush(stderr);
 }
 
+template <int NK>
+static int bs_launch_level(int level, const BsSources& S, const BsLevel2& L2, long long NT, int shift, int R, int ncols,
+                           int64_t* hist, const long long* po, uint64_t* out, long long out_stride, cudaStream_t st) {
+  static bool attr_set[8] = {false};
+  int dev = 0;
+  MGB_CUDA(cudaGetDevice(&dev));
+  const size_t smem = sizeof(SplitSmem);
+  if (dev >= 0 && dev < 8 && !attr_set[dev]) {
+    MGB_CUDA(cudaFuncSetAttribute(k_bsplit_scatter<NK, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MGB_CUDA(cudaFuncSetAttribute(k_bsplit_scatter<NK, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set[dev] = true;
+  }
+  if (level == 1)
+    k_bsplit_scatter<NK, 1><<<(unsigned)NT, SP_THREADS, smem, st>>>(S, L2, NT, shift, R, ncols, hist, po, out, out_stride);
+  else
+    k_bsplit_scatter<NK, 2><<<(unsigned)NT, SP_THREADS, smem, st>>>(S, L2, NT, shift, R, ncols, hist, po, out, out_stride);
+  MGB_CHECK_LAUNCH();
+  return MGB_OK;
+}
+
+template <int NK>
+static int bs_launch_hist(int level, const BsSources& S, const BsLevel2& L2, long long NT, int shift, int R, int64_t* hist,
+                          cudaStream_t st) {
+  if (level == 1)
+    k_bsplit_hist<NK, 1><<<(unsigned)NT, SP_THREADS, 0, st>>>(S, L2, NT, shift, R, hist);
+  else
+    k_bsplit_hist<NK, 2><<<(unsigned)NT, SP_THREADS, 0, st>>>(S, L2, NT, shift, R, hist);
+  MGB_CHECK_LAUNCH();
+  return MGB_OK;
+}
+
 int mgb_bucket_aggregate(const Layout& L, const BktSource* srcs_host, int nsrc, long long T, cudaStream_t st,
                          BktResult* out, int* overflow) {
   *overflow = 0;
@@ -489,87 +623,118 @@ int mgb_bucket_aggregate(const Layout& L, const BktSource* srcs_host, int nsrc, 
               "bucketed aggregation: %d sources, %lld rows", nsrc, T);
   int logB = 0;
   while (logB < 22 && (T >> logB) > BK_TARGET) ++logB;
+  if (logB > 16) {   // more than two levels of 256 ways: left to the table path
+    *overflow = 3;
+    return MGB_OK;
+  }
   const int B = 1 << logB;
+  const int b1 = logB <= 8 ? logB : (logB + 1) / 2, b2 = logB - b1;
+  const int P1 = 1 << b1, R2 = 1 << b2;
   const int ncol = L.nk + L.na, W = L.nk + L.nv;
-  char* small = nullptr;     // srcs | begin | err, longest bucket
+  // sources are tiled one by one
+  std::vector<long long> row_begin((size_t)nsrc + 1), tile_begin((size_t)nsrc + 1);
+  tile_begin[0] = 0;
+  for (int s = 0; s < nsrc; ++s) {
+    row_begin[s] = srcs_host[s].begin;
+    const long long rows = (s + 1 < nsrc ? srcs_host[s + 1].begin : T) - srcs_host[s].begin;
+    tile_begin[s + 1] = tile_begin[s] + (rows + SP_TILE - 1) / SP_TILE;
+  }
+  row_begin[nsrc] = T;
+  const long long NT1 = tile_begin[nsrc] > 0 ? tile_begin[nsrc] : 1;
+  const long long NT2 = b2 ? (T + SP_TILE - 1) / SP_TILE + P1 + 1 : 0;   // padded tiles of level 2 (upper bound)
+  const long long SA = NT2 * SP_TILE;                                     // rows per column of the padded staging
   const size_t src_bytes = sizeof(BktSource) * (size_t)nsrc;
-  const size_t begin_bytes = sizeof(long long) * ((size_t)nsrc + 1);
-  const size_t src_pad = (src_bytes + 255) & ~(size_t)255, begin_pad = (begin_bytes + 255) & ~(size_t)255;
-  int32_t *pid = nullptr, *perm = nullptr;
-  uint64_t* rows = nullptr;
-  MGB_CUDA(cudaMallocAsync((void**)&small, src_pad + begin_pad + 256, st));
-  MGB_CUDA(cudaMallocAsync((void**)&pid, sizeof(int32_t) * (size_t)T, st));
-  MGB_CUDA(cudaMallocAsync((void**)&perm, sizeof(int32_t) * (size_t)T, st));
-  MGB_CUDA(cudaMallocAsync((void**)&rows, sizeof(uint64_t) * (size_t)W * (size_t)T, st));
+  const size_t tab_bytes = sizeof(long long) * ((size_t)nsrc + 1);
+  const size_t src_pad = (src_bytes + 255) & ~(size_t)255, tab_pad = (tab_bytes + 255) & ~(size_t)255;
+  const size_t plan_bytes = (sizeof(long long) * (2 * (size_t)P1 + 2) + sizeof(int32_t) * (size_t)(NT2 + 1) + 255) & ~(size_t)255;
+  char* small = nullptr;     // srcs | row_begin | tile_begin | err, longest bucket | po | cnt | tile_part
+  uint64_t *stageA = nullptr, *stageB = nullptr;
+  int64_t *hist1 = nullptr, *hist2 = nullptr;
+  MGB_CUDA(cudaMallocAsync((void**)&small, src_pad + 2 * tab_pad + 256 + plan_bytes, st));
+  MGB_CUDA(cudaMallocAsync((void**)&stageB, sizeof(uint64_t) * (size_t)W * (size_t)T, st));
+  MGB_CUDA(cudaMallocAsync((void**)&hist1, sizeof(int64_t) * (size_t)P1 * (size_t)NT1, st));
+  if (b2) {
+    MGB_CUDA(cudaMallocAsync((void**)&stageA, sizeof(uint64_t) * (size_t)W * (size_t)SA, st));
+    MGB_CUDA(cudaMallocAsync((void**)&hist2, sizeof(int64_t) * (size_t)R2 * (size_t)NT2, st));
+  }
   MGB_CUDA(cudaMallocAsync((void**)&out->off, sizeof(int64_t) * ((size_t)B + 1), st));
   MGB_CUDA(cudaMallocAsync((void**)&out->goff, sizeof(int64_t) * ((size_t)B + 1), st));
   MGB_CUDA(cudaMallocAsync((void**)&out->scratch, sizeof(uint64_t) * (size_t)ncol * (size_t)T, st));
   out->T = T;
   out->B = B;
   BktSource* d_srcs = (BktSource*)small;
-  long long* d_begin = (long long*)(small + src_pad);
-  int* d_err = (int*)(small + src_pad + begin_pad);
-  {
-    std::vector<long long> begin((size_t)nsrc + 1);
-    for (int s = 0; s < nsrc; ++s) begin[s] = srcs_host[s].begin;
-    begin[nsrc] = T;
-    // pageable sources: the runtime stages these small copies before cudaMemcpyAsync returns
-    MGB_CUDA(cudaMemcpyAsync(d_srcs, srcs_host, src_bytes, cudaMemcpyHostToDevice, st));
-    MGB_CUDA(cudaMemcpyAsync(d_begin, begin.data(), begin_bytes, cudaMemcpyHostToDevice, st));
-  }
+  long long* d_row_begin = (long long*)(small + src_pad);
+  long long* d_tile_begin = (long long*)(small + src_pad + tab_pad);
+  int* d_err = (int*)(small + src_pad + 2 * tab_pad);
+  long long* d_po = (long long*)(small + src_pad + 2 * tab_pad + 256);
+  long long* d_cnt = d_po + P1 + 1;
+  int32_t* d_tile_part = (int32_t*)(d_cnt + P1 + 1);
+  // pageable sources: the runtime stages these small copies before cudaMemcpyAsync returns
+  MGB_CUDA(cudaMemcpyAsync(d_srcs, srcs_host, src_bytes, cudaMemcpyHostToDevice, st));
+  MGB_CUDA(cudaMemcpyAsync(d_row_begin, row_begin.data(), tab_bytes, cudaMemcpyHostToDevice, st));
+  MGB_CUDA(cudaMemcpyAsync(d_tile_begin, tile_begin.data(), tab_bytes, cudaMemcpyHostToDevice, st));
   MGB_CUDA(cudaMemsetAsync(d_err, 0, 256, st));
   MGB_CUDA(cudaMemsetAsync(out->goff + B, 0, sizeof(int64_t), st));
   auto release = [&]() {
-    cudaFreeAsync(pid, st);
-    cudaFreeAsync(perm, st);
-    cudaFreeAsync(rows, st);
+    if (stageA) cudaFreeAsync(stageA, st);
+    cudaFreeAsync(stageB, st);
+    cudaFreeAsync(hist1, st);
+    if (hist2) cudaFreeAsync(hist2, st);
     cudaFreeAsync(small, st);
   };
   int status = MGB_OK;
   {
     MgbProfScope prof(MGB_K_BUCKET, st);
-    // 1. bucket ids + row-major copy of the rows
-    BktPackParams pp;
-    pp.srcs = d_srcs;
-    pp.begin = d_begin;
-    pp.src0 = srcs_host[0];
-    pp.nsrc = nsrc;
-    pp.nk = L.nk;
-    pp.nv = L.nv;
-    pp.T = T;
-    pp.logB = logB;
-    pp.pid = pid;
-    pp.rows = rows;
-    const size_t sm = (size_t)BKP_ROWS * (size_t)(W | 1) * 8;
-    const long long ntiles = (T + BKP_ROWS - 1) / BKP_ROWS, capb = (long long)mgb_sm_count() * 16;
-    const unsigned grid = (unsigned)(ntiles > capb ? capb : ntiles);
-    if (L.nk == 1) {
-      if (sm > 48 * 1024) MGB_CUDA(cudaFuncSetAttribute(k_bucket_pack<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-      k_bucket_pack<1><<<grid, BKP_ROWS, sm, st>>>(pp);
-    } else {
-      if (sm > 48 * 1024) MGB_CUDA(cudaFuncSetAttribute(k_bucket_pack<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-      k_bucket_pack<2><<<grid, BKP_ROWS, sm, st>>>(pp);
-    }
-    MGB_CHECK_LAUNCH();
-    bk_debug("k_bucket_pack", st);
-    // 2. row ids in bucket order: histogram -> offsets -> placement through one atomic cursor per bucket
-    {
-      const long long blocks = (T + 255) / 256, capg = (long long)mgb_sm_count() * 16;
-      const unsigned g2 = (unsigned)(blocks > capg ? capg : blocks);
-      const unsigned gB = (unsigned)(((long long)B + 256) / 256 > capg ? capg : ((long long)B + 256) / 256);
-      MGB_CUDA(cudaMemsetAsync(out->off, 0, sizeof(int64_t) * ((size_t)B + 1), st));
-      k_bucket_hist<<<g2, 256, 0, st>>>(pid, T, (unsigned long long*)out->off);
-      MGB_CHECK_LAUNCH();
-      status = mgb_scan_exclusive_i64(out->off, (int64_t)B + 1, nullptr, st);
-      if (status == MGB_OK) {
-        // goff doubles as the cursor array until the aggregation kernel overwrites it with the group counts
-        k_copy_i64<<<gB, 256, 0, st>>>(out->off, out->goff, (long long)B + 1);
-        k_bucket_place<<<g2, 256, 0, st>>>(pid, T, (unsigned long long*)out->goff, perm);
-        MGB_CHECK_LAUNCH();
-        MGB_CUDA(cudaMemsetAsync(out->goff + B, 0, sizeof(int64_t), st));
+    BsSources S;
+    S.srcs = d_srcs;
+    S.row_begin = d_row_begin;
+    S.tile_begin = d_tile_begin;
+    S.src0 = srcs_host[0];
+    S.rows0 = row_begin[1] - row_begin[0];
+    S.nsrc = nsrc;
+    BsLevel2 L2;
+    memset(&L2, 0, sizeof(L2));
+    const bool one = L.nk == 1;
+    // level 1: by the top b1 bits.  One level: compact into stageB; two levels: into stageA, partitions padded to tiles
+    const int shift1 = b1 ? 64 - b1 : 63;   // b1 == 0: one bucket (mask 0 makes the digit 0)
+    status = one ? bs_launch_hist<1>(1, S, L2, NT1, shift1, P1, hist1, st) : bs_launch_hist<2>(1, S, L2, NT1, shift1, P1, hist1, st);
+    if (status == MGB_OK) status = mgb_scan_exclusive_i64(hist1, (int64_t)P1 * NT1, nullptr, st);
+    if (status == MGB_OK && b2) {
+      k_bsplit_plan<<<1, 256, 0, st>>>(hist1, NT1, P1, T, d_po, d_cnt, d_tile_part, NT2);
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) {
+        mgb_set_error("bucket split plan launch: %s", cudaGetErrorString(e));
+        status = MGB_ERR_CUDA;
       }
     }
-    bk_debug("row ids in bucket order", st);
+    if (status == MGB_OK)
+      status = one ? bs_launch_level<1>(1, S, L2, NT1, shift1, P1, W, hist1, b2 ? d_po : nullptr, b2 ? stageA : stageB, b2 ? SA : T, st)
+                   : bs_launch_level<2>(1, S, L2, NT1, shift1, P1, W, hist1, b2 ? d_po : nullptr, b2 ? stageA : stageB, b2 ? SA : T, st);
+    bk_debug("bucket split level 1", st);
+    if (status == MGB_OK && b2) {   // level 2: every partition by the next b2 bits, compact, bucket order (digit 2, partition)
+      L2.stage = stageA;
+      L2.stride = SA;
+      L2.po = d_po;
+      L2.cnt = d_cnt;
+      L2.tile_part = d_tile_part;
+      const int shift2 = 64 - logB;
+      status = one ? bs_launch_hist<1>(2, S, L2, NT2, shift2, R2, hist2, st) : bs_launch_hist<2>(2, S, L2, NT2, shift2, R2, hist2, st);
+      if (status == MGB_OK) status = mgb_scan_exclusive_i64(hist2, (int64_t)R2 * NT2, nullptr, st);
+      if (status == MGB_OK)
+        status = one ? bs_launch_level<1>(2, S, L2, NT2, shift2, R2, W, hist2, nullptr, stageB, T, st)
+                     : bs_launch_level<2>(2, S, L2, NT2, shift2, R2, W, hist2, nullptr, stageB, T, st);
+      bk_debug("bucket split level 2", st);
+    }
+    if (status == MGB_OK) {
+      const int gb = (B + 256) / 256;
+      k_bsplit_off<<<gb > 1024 ? 1024 : gb, 256, 0, st>>>(b2 ? hist2 : hist1, b2 ? NT2 : NT1, P1, B, b2 ? d_po : nullptr, T,
+                                                          out->off);
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) {
+        mgb_set_error("bucket offsets launch: %s", cudaGetErrorString(e));
+        status = MGB_ERR_CUDA;
+      }
+    }
     if (status == MGB_OK) {   // a hot key makes one bucket as long as its row count: leave that input to the table
       const int gb = (B + 255) / 256;
       k_bucket_max<<<gb > 1024 ? 1024 : gb, 256, 0, st>>>(out->off, B, d_err + 1);
@@ -586,23 +751,40 @@ int mgb_bucket_aggregate(const Layout& L, const BktSource* srcs_host, int nsrc, 
         return MGB_OK;
       }
     }
-    // 3. one CTA per bucket
+    // one CTA per bucket
     if (status == MGB_OK) {
       BktParams p;
-      p.rows = rows;
-      p.W = W;
+      p.rows = stageB;
       p.T = T;
       p.logB = logB;
-      p.perm = perm;
       p.off = out->off;
       p.scratch = out->scratch;
       p.gcount = out->goff;
       p.err = d_err;
       p.L = L;
-      if (L.nk == 1)
-        k_bucket_agg<1><<<(unsigned)B, BK_THREADS, 0, st>>>(p);
-      else
-        k_bucket_agg<2><<<(unsigned)B, BK_THREADS, 0, st>>>(p);
+      int need = 0;
+      for (int a = 0; a < L.na; ++a) need |= L.spec_op[a] == MGB_SUMSQ ? 1 : ((L.spec_op[a] == MGB_MIN || L.spec_op[a] == MGB_MAX) ? 2 : 0);
+      // narrow rows (few value columns): 128-thread CTAs, twice as many resident -- the phases of a bucket are
+      // separated by CTA barriers; wide rows keep 256 threads for the (group, column) fold
+#define BK_LAUNCH(NK_, NEED_)                                       \
+  if (L.nv <= 3)                                                    \
+    k_bucket_agg<NK_, NEED_, 128><<<(unsigned)B, 128, 0, st>>>(p);  \
+  else                                                              \
+    k_bucket_agg<NK_, NEED_, 256><<<(unsigned)B, 256, 0, st>>>(p)
+#define BK_PICK(NK_)                 \
+  switch (need) {                    \
+    case 0: BK_LAUNCH(NK_, 0); break;  \
+    case 1: BK_LAUNCH(NK_, 1); break;  \
+    case 2: BK_LAUNCH(NK_, 2); break;  \
+    default: BK_LAUNCH(NK_, 3); break; \
+  }
+      if (L.nk == 1) {
+        BK_PICK(1)
+      } else {
+        BK_PICK(2)
+      }
+#undef BK_PICK
+#undef BK_LAUNCH
       cudaError_t e = cudaGetLastError();
       if (e != cudaSuccess) {
         mgb_set_error("bucket aggregation launch: %s", cudaGetErrorString(e));

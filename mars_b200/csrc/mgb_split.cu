@@ -20,16 +20,7 @@
 //
 // Stable: inside a partition rows keep their input order (the ascending positions f_i of the reference).
 // No host synchronisation; 1 <= R <= 256 (more partitions: the radix passes of mgb_partition.cu).
-#include "mgb_common.cuh"
-
-#define SP_THREADS 256
-#define SP_WARPS 8
-#define SP_ROUNDS 8
-#define SP_TILE (SP_THREADS * SP_ROUNDS)
-#define SP_MAX_R 256
-#define SP_MAX_COLS 80
-#define SP_SLOTS (SP_TILE + SP_MAX_R + 2)
-#define SP_PAD 0xffffu
+#include "mgb_split.cuh"
 
 struct SplitSrc {
   const int64_t* k[MGB_MAX_KEYS];
@@ -73,13 +64,17 @@ __global__ void __launch_bounds__(SP_THREADS) k_split_hist(SplitSrc s, int64_t n
   const int64_t tile = blockIdx.x;
   const int64_t base = tile * SP_TILE + warp * (SP_TILE / SP_WARPS);
   const unsigned lt = mgb_lanemask_lt();
+  uint32_t dg[SP_ROUNDS];
+#pragma unroll
+  for (int r = 0; r < SP_ROUNDS; ++r) {   // all key loads of the thread in flight together
+    const int64_t i = base + r * 32 + lane;
+    dg[r] = i < n ? sp_pid<NK, MODE>(s, i, pow2, bad) : (uint32_t)(SP_MAX_R + lane);
+  }
 #pragma unroll
   for (int r = 0; r < SP_ROUNDS; ++r) {
-    const int64_t i = base + r * 32 + lane;
-    const bool valid = i < n;
-    const uint32_t d = valid ? sp_pid<NK, MODE>(s, i, pow2, bad) : (uint32_t)(SP_MAX_R + lane);
-    const unsigned peers = __match_any_sync(0xffffffffu, d);
-    if (valid && (peers & lt) == 0) wc[warp][d] += (uint32_t)__popc(peers);
+    const bool valid = base + r * 32 + lane < n;
+    const unsigned peers = __match_any_sync(0xffffffffu, dg[r]);
+    if (valid && (peers & lt) == 0) wc[warp][dg[r]] += (uint32_t)__popc(peers);
     __syncwarp();
   }
   __syncthreads();
@@ -96,189 +91,39 @@ __global__ void k_split_offsets(const int64_t* hist, int64_t ntiles, int R, int6
   for (int p = threadIdx.x; p <= R; p += blockDim.x) offsets[p] = p < R ? hist[(int64_t)p * ntiles] : n;
 }
 
-// ---- TMA (bulk asynchronous copy) + mbarrier -------------------------------------------------------------------
-__device__ __forceinline__ uint32_t sp_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void sp_mbar_init(uint64_t* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sp_smem(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void sp_bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sp_smem(bar)), "r"(bytes) : "memory");
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   sp_smem(dst)),
-               "l"(src), "r"(bytes), "r"(sp_smem(bar))
-               : "memory");
-}
-__device__ __forceinline__ void sp_mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "SP_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra SP_DONE;\n"
-      "bra SP_WAIT;\n"
-      "SP_DONE:\n"
-      "}\n" ::"r"(sp_smem(bar)),
-      "r"(parity)
-      : "memory");
-}
-
-// destinations are global memory (this GPU's or an IPC-mapped peer's): typed stores, not generic ones
-__device__ __forceinline__ void sp_st128(uint64_t addr, const ulonglong2& v) {
-  asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(addr), "l"(v.x), "l"(v.y) : "memory");
-}
-__device__ __forceinline__ void sp_st64(uint64_t addr, uint64_t v) {
-  asm volatile("st.global.u64 [%0], %1;" ::"l"(addr), "l"(v) : "memory");
-}
-
-struct SplitSmem {
-  alignas(128) uint64_t a[2][SP_TILE];     // column tiles as they lie in memory (TMA destinations)
-  alignas(16) uint64_t b[SP_SLOTS + 2];    // the same rows in partition order, runs padded to destination parity
-  alignas(8) uint64_t colbase[SP_MAX_R];   // address of slot 0's row if slot 0 belonged to partition p (this column)
-  int64_t gof[SP_MAX_R];                   // first output row of this tile in partition p
-  uint64_t bar[2];
-  int32_t rsm[SP_MAX_R];                   // first slot of partition p's run
-  uint16_t wc[SP_WARPS][SP_MAX_R];         // rows of partition p in the warps before this one
-  alignas(4) uint16_t spart[SP_SLOTS + 2]; // partition of the row in slot s (SP_PAD: no row)
-  int32_t wsum[SP_WARPS];
-  int32_t nslots;
+template <int NK, int MODE>
+struct ShuffleTile {
+  const SplitSrc& s;
+  const SplitCols& cols;
+  const int64_t* __restrict__ hist;
+  const uint64_t* __restrict__ dst_tab;
+  int64_t ntiles, tile, tbase;
+  int R;
+  bool pow2;
+  __device__ __forceinline__ uint32_t digit(int j) const {
+    int32_t unused;
+    return sp_pid<NK, MODE>(s, tbase + j, pow2, &unused);
+  }
+  __device__ __forceinline__ int64_t dest_row(int d) const {
+    const int64_t abs0 = hist[(int64_t)d * ntiles + tile];
+    return dst_tab ? abs0 - hist[(int64_t)d * ntiles] : abs0;
+  }
+  __device__ __forceinline__ const uint64_t* src(int c) const { return cols.in[c] + tbase; }
+  __device__ __forceinline__ uint64_t dst(int c, int d) const {
+    return dst_tab ? dst_tab[(int64_t)c * R + d] : (uint64_t)cols.out[c];
+  }
 };
 
 template <int NK, int MODE>
-__global__ void __launch_bounds__(SP_THREADS, 3) k_split_scatter(SplitSrc s, SplitCols cols, int64_t n, int64_t ntiles,
-                                                                 int R, const int64_t* __restrict__ hist,
+__global__ void __launch_bounds__(SP_THREADS, 3) k_split_scatter(const SplitSrc s, const SplitCols cols, int64_t n,
+                                                                 int64_t ntiles, int R, const int64_t* __restrict__ hist,
                                                                  const uint64_t* __restrict__ dst_tab) {
   extern __shared__ __align__(128) unsigned char sp_raw[];
   SplitSmem& sm = *reinterpret_cast<SplitSmem*>(sp_raw);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t tile = blockIdx.x;
-  const int64_t tbase = tile * SP_TILE;
-  const int nt = (int)((n - tbase) < SP_TILE ? (n - tbase) : SP_TILE);   // rows of this tile
-  const uint32_t bulk_bytes = (uint32_t)(nt & ~1) * 8u;
-
-  if (tid == 0) {
-    sp_mbar_init(&sm.bar[0], 1);
-    sp_mbar_init(&sm.bar[1], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  for (int i = tid; i < SP_WARPS * SP_MAX_R; i += SP_THREADS) (&sm.wc[0][0])[i] = 0;
-  for (int i = tid; i < SP_SLOTS + 2; i += SP_THREADS) sm.spart[i] = (uint16_t)SP_PAD;
-  __syncthreads();
-  // a column tile is fetched by the TMA unit when its address is 16-byte aligned (tile offsets are)
-  auto tma_ok = [&](int c) { return ((uintptr_t)cols.in[c] & 15) == 0 && bulk_bytes != 0; };
-  if (tid == 0 && cols.n > 0 && tma_ok(0)) sp_bulk_load(sm.a[0], cols.in[0] + tbase, bulk_bytes, &sm.bar[0]);
-
-  // ---- phase A: partition id and rank inside (warp, partition) of every row ------------------------------------
-  const bool pow2 = (s.R & (s.R - 1)) == 0;
-  const unsigned lt = mgb_lanemask_lt();
-  const int jbase = warp * (SP_TILE / SP_WARPS) + lane;
-  uint32_t dr[SP_ROUNDS];   // partition | rank << 16, later the slot of the row
-  int32_t dummy_bad;
-#pragma unroll
-  for (int r = 0; r < SP_ROUNDS; ++r) {
-    const int j = jbase + r * 32;
-    const bool valid = j < nt;
-    const uint32_t d = valid ? sp_pid<NK, MODE>(s, tbase + j, pow2, &dummy_bad) : (uint32_t)(SP_MAX_R + lane);
-    const unsigned peers = __match_any_sync(0xffffffffu, d);
-    uint32_t before = 0;
-    if (valid) before = sm.wc[warp][d];
-    __syncwarp();
-    if (valid && (peers & lt) == 0) sm.wc[warp][d] = (uint16_t)(before + __popc(peers));
-    __syncwarp();
-    dr[r] = d | ((before + __popc(peers & lt)) << 16);
-  }
-  __syncthreads();
-  // ---- phase B: runs.  Partition p gets count + 1 slots; its run starts on the slot whose parity equals the
-  // parity of its first destination row, so that (even, odd) slot pairs are 16-byte aligned destination pairs.
-  {
-    int cnt = 0;
-    int64_t g = 0;
-    if (tid < R) {
-#pragma unroll
-      for (int w = 0; w < SP_WARPS; ++w) {
-        const int t = sm.wc[w][tid];
-        sm.wc[w][tid] = (uint16_t)cnt;
-        cnt += t;
-      }
-      const int64_t abs0 = hist[(int64_t)tid * ntiles + tile];
-      g = dst_tab ? abs0 - hist[(int64_t)tid * ntiles] : abs0;
-    }
-    int v = tid < R ? cnt + 1 : 0;
-    int inc = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += t;
-    }
-    if (lane == 31) sm.wsum[warp] = inc;
-    __syncthreads();
-    int add = 0;
-#pragma unroll
-    for (int w = 0; w < SP_WARPS; ++w)
-      if (w < warp) add += sm.wsum[w];
-    const int excl = add + inc - v;
-    if (tid < R) {
-      const int rs = excl + (int)((excl ^ (int)g) & 1);
-      sm.rsm[tid] = rs;
-      sm.gof[tid] = g;
-    }
-    if (tid == SP_THREADS - 1) sm.nslots = (add + inc + 2) & ~1;
-  }
-  __syncthreads();
-  // ---- phase C: slot of every row -----------------------------------------------------------------------------
-#pragma unroll
-  for (int r = 0; r < SP_ROUNDS; ++r) {
-    const int j = jbase + r * 32;
-    if (j < nt) {
-      const uint32_t d = dr[r] & 0xffffu;
-      const uint32_t slot = (uint32_t)sm.rsm[d] + sm.wc[warp][d] + (dr[r] >> 16);
-      sm.spart[slot] = (uint16_t)d;
-      dr[r] = slot;
-    }
-  }
-  // ---- columns ---------------------------------------------------------------------------------------------------
-  uint32_t uses0 = 0, uses1 = 0;
-  for (int c = 0; c < cols.n; ++c) {
-    const int buf = c & 1;
-    if (tid < R) {
-      const uint64_t base = dst_tab ? dst_tab[(int64_t)c * R + tid] : (uint64_t)cols.out[c];
-      sm.colbase[tid] = base + 8ull * (uint64_t)(sm.gof[tid] - (int64_t)sm.rsm[tid]);
-    }
-    if (tid == 0 && c + 1 < cols.n && tma_ok(c + 1))
-      sp_bulk_load(sm.a[buf ^ 1], cols.in[c + 1] + tbase, bulk_bytes, &sm.bar[buf ^ 1]);
-    const uint64_t* src = cols.in[c] + tbase;
-    if (tma_ok(c)) {
-      const uint32_t use = buf ? uses1++ : uses0++;
-      sp_mbar_wait(&sm.bar[buf], use & 1);
-#pragma unroll
-      for (int r = 0; r < SP_ROUNDS; ++r) {
-        const int j = jbase + r * 32;
-        if (j < nt) sm.b[dr[r]] = (j == nt - 1 && (nt & 1)) ? mgb_ld_stream(src + j) : sm.a[buf][j];
-      }
-    } else {
-#pragma unroll
-      for (int r = 0; r < SP_ROUNDS; ++r) {
-        const int j = jbase + r * 32;
-        if (j < nt) sm.b[dr[r]] = mgb_ld_stream(src + j);
-      }
-    }
-    __syncthreads();
-    const int npairs = sm.nslots >> 1;
-    for (int q = tid; q < npairs; q += SP_THREADS) {
-      const uint32_t pp = *reinterpret_cast<const uint32_t*>(&sm.spart[2 * q]);
-      const uint32_t p0 = pp & 0xffffu, p1 = pp >> 16;
-      if (pp == 0xffffffffu) continue;
-      const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(&sm.b[2 * q]);
-      const uint64_t a0 = p0 != SP_PAD ? sm.colbase[p0] + 16ull * (uint64_t)q : 0;
-      if (p0 == p1 && (a0 & 15) == 0) {
-        sp_st128(a0, v);
-      } else {
-        if (p0 != SP_PAD) sp_st64(a0, v.x);
-        if (p1 != SP_PAD) sp_st64(sm.colbase[p1] + 16ull * (uint64_t)q + 8, v.y);
-      }
-    }
-    __syncthreads();
-  }
+  const int64_t tile = blockIdx.x, tbase = tile * SP_TILE;
+  const int nt = (int)((n - tbase) < SP_TILE ? (n - tbase) : SP_TILE);
+  ShuffleTile<NK, MODE> f{s, cols, hist, dst_tab, ntiles, tile, tbase, R, (s.R & (s.R - 1)) == 0};
+  sp_tile_split<true>(sm, nt, R, cols.n, f);
 }
 
 // ----------------------------------------------------------------------------------------------------

@@ -1342,6 +1342,44 @@ def execute_merge_align(ctx, op):
         ctx[out.key] = _concat_frames([_as_device_frame(v, index_as_keys=True) for v in res])
 
 
+class DeferredSplit:
+    """One mapper chunk of a hash shuffle after pass 1 of the partition kernel (mgb_split_plan): the block sizes
+    are on the device, the rows have not moved.  The multi-GPU exchange (parallel.Exchange, push transport)
+    decides from the sizes of ALL mappers where every block goes and lets pass 2 write each row once, straight
+    into the receive arena of the GPU that runs its reducer; ``emit`` is the single-process form (blocks of local
+    columns under the reference's ctx keys, groupby/core.py:429-435)."""
+
+    def __init__(self, chunk, op, mapper_index, keys, cols, R, hist, offsets, spans, nk, is_tuple):
+        self.chunk, self.op, self.mapper_index = chunk, op, mapper_index
+        self.keys, self.cols, self.R, self.hist, self.offsets = keys, cols, R, hist, offsets
+        self.spans, self.nk, self.is_tuple = spans, nk, is_tuple      # spans: (slot, index_names, columns, c0, c1)
+        self.n_slots = len(spans)
+
+    def key_of(self, r):
+        chunk, op = self.chunk, self.op
+        return (chunk.key, (r, chunk.index[1]) if getattr(op, "is_dataframe_obj", True) else (r,))
+
+    def schema(self):
+        return dict(index_names=self.spans[0][1], nk=self.nk,
+                    slots=[(columns, [str(self.cols[c].dtype) for c in range(c0, c1)]) for _, _, columns, c0, c1 in self.spans])
+
+    def entry(self, frames):
+        if self.is_tuple:
+            return (self.mapper_index, tuple(frames) + (False,))
+        return (self.mapper_index, frames[0])
+
+    def emit(self, ctx):
+        """pass 2 into local columns"""
+        outs = [torch.empty_like(c) for c in self.cols]
+        _kernels.split_scatter(self.keys, self.R, self.hist, self.cols, outs=outs)
+        offsets = self.offsets.cpu().tolist()
+        src = ColumnSet(outs)
+        for r in range(self.R):
+            a, b = offsets[r], offsets[r + 1]
+            ctx[self.key_of(r)] = self.entry([DeviceFrame.from_range(names, columns, src, 0, self.nk, d0, d1, a, b)
+                                              for _, names, columns, d0, d1 in self.spans])
+
+
 def _execute_shuffle_map(ctx, op):
     """stage=map: partition id = pandas hash of the group keys % shuffle_size; one block per reducer,
     empty ones included (reference: execute_map, groupby/core.py:353-435; contract shuffle.py:124-130)."""
@@ -1363,6 +1401,20 @@ def _execute_shuffle_map(ctx, op):
                 break
         else:
             groups.append([i])
+    if (getattr(ctx, "defer_split", False) and len(groups) == 1 and R <= 256 and hasattr(_kernels, "split_plan")
+            and len(frames[0].index) >= 1):
+        # multi-GPU run with a push transport: sizes now, rows when the exchange knows where they go
+        base = frames[0]
+        cols = list(base.index)
+        spans, pos = [], len(cols)
+        for i, f in enumerate(frames):
+            cols.extend(f.data)
+            spans.append((i, f.index_names, f.columns, pos, pos + len(f.columns)))
+            pos += len(f.columns)
+        hist, offsets = _kernels.split_plan(base.index, R)
+        ctx[chunk.key, "deferred"] = DeferredSplit(chunk, op, mapper_index, list(base.index), cols, R, hist, offsets,
+                                                   spans, len(base.index), is_tuple)
+        return
     blocks: List[List[Optional[DeviceFrame]]] = [[None] * len(frames) for _ in range(R)]
     for g in groups:
         base = frames[g[0]]

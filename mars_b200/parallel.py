@@ -130,14 +130,52 @@ class IpcPullTransport:
     exchange_stats = NcclTransport.exchange_stats
 
     def reserve(self, n_elements: int):
-        """-> (device address of the send arena, IPC handle bytes)"""
+        """-> (device address of the send arena, IPC handle bytes).  Not collective: only valid while the arena does
+        not have to grow (first call / capacity probe); shuffles use ``reserve_collective``."""
         ptr = C.c_void_p()
         handle = (C.c_uint8 * 64)()
         check(self._lib.mgb_ipc_arena(int(n_elements) * 8, C.byref(ptr), handle))
         return int(ptr.value or 0), bytes(handle)
 
+    def reserve_collective(self, n_elements: int):
+        """Collective: every rank's send arena (slot 0) holds at least its ``n_elements``.  An exported allocation is
+        never freed while a peer maps it: ranks whose arena must grow are announced first, every peer closes its
+        mapping, and only after a barrier the arena is reallocated and its new handle published.  Returns this rank's
+        arena address; ``self.peer_base[q]`` is rank q's arena as mapped here."""
+        if not hasattr(self, "peer_base"):
+            self.peer_base = [0] * self.world
+            self._cap0 = [0] * self.world
+        need = int(n_elements) * 8
+        needs = [None] * self.world
+        dist.all_gather_object(needs, need, group=self.meta_group)
+        growing = [q for q in range(self.world) if needs[q] > self._cap0[q] or not self.peer_base[q]]
+        if growing:
+            for q in growing:
+                if q != self.rank:
+                    check(self._lib.mgb_ipc_close_slot(q, 0))
+            torch.cuda.synchronize()
+            dist.barrier(group=self.meta_group)
+            info = None
+            if self.rank in growing:
+                ptr, cap = C.c_void_p(), C.c_int64()
+                handle = (C.c_uint8 * 64)()
+                check(self._lib.mgb_ipc_arena_slot(0, need, C.byref(ptr), handle, C.byref(cap), None))
+                info = (bytes(handle), int(cap.value), int(ptr.value or 0))
+            infos = [None] * self.world
+            dist.all_gather_object(infos, info, group=self.meta_group)
+            for q in growing:
+                handle, cap, ptr = infos[q]
+                self._cap0[q] = cap
+                if q == self.rank:
+                    self.peer_base[q] = ptr
+                else:
+                    mapped = C.c_void_p()
+                    check(self._lib.mgb_ipc_open_slot(q, 0, (C.c_uint8 * 64).from_buffer_copy(handle), C.byref(mapped)))
+                    self.peer_base[q] = int(mapped.value or 0)
+        return self.peer_base[self.rank]
+
     def pull(self, recvbuf: torch.Tensor, recv_off, peers):
-        """peers[q] = (handle bytes, element offset of my slice in q's arena) or None"""
+        """peers[q] = element offset of my slice in q's arena, or None"""
         stream = torch.cuda.current_stream().cuda_stream
         nbytes = 0
         if self.timed:
@@ -147,15 +185,11 @@ class IpcPullTransport:
             e0.record()
         for step in range(1, self.world):
             q = (self.rank + step) % self.world     # staggered: at every step each arena serves one puller
-            info = peers[q]
+            off = peers[q]
             n = recv_off[q + 1] - recv_off[q]
-            if info is None or n == 0:
+            if off is None or n == 0:
                 continue
-            handle, off = info
-            src = C.c_void_p()
-            hb = (C.c_uint8 * 64).from_buffer_copy(handle)
-            check(self._lib.mgb_ipc_open(q, hb, C.byref(src)))
-            check(self._lib.mgb_ipc_pull(recvbuf.data_ptr() + recv_off[q] * 8, (src.value or 0) + off * 8, n * 8, stream))
+            check(self._lib.mgb_ipc_pull(recvbuf.data_ptr() + recv_off[q] * 8, self.peer_base[q] + off * 8, n * 8, stream))
             nbytes += n * 8
         if self.timed:
             e1.record()
@@ -167,6 +201,130 @@ class IpcPullTransport:
 
     def close(self):
         pass
+
+
+class _ArenaOwner:
+    """exposes a library-owned receive arena to torch (``torch.as_tensor`` keeps this object alive for as long as
+    any view of the arena lives: its death is the signal that the slot may be written again)"""
+
+    def __init__(self, ptr: int, n_elements: int):
+        self.__cuda_array_interface__ = {"shape": (int(n_elements),), "typestr": "<i8", "data": (int(ptr), False),
+                                         "version": 2}
+
+
+class PushTransport(IpcPullTransport):
+    """Fused partition -> peer transfer on one NVSwitch box.  Every rank owns receive arenas that all peers map
+    through CUDA IPC; after ONE fixed-size device-side exchange of the block sizes (ncclAllGather through
+    libmarsgb, mgb_comm_allgather_i64) every mapper's partition kernel (mgb_split_scatter) stores its rows
+    straight into the arenas of the ranks that reduce them -- SM stores over NVLink, no pack pass, no copy
+    engine, no pickled metadata; a stream-ordered all-gather of one word is the fence after which every rank's
+    blocks are complete.  Shuffles that cannot be deferred (the PSRS range shuffle) use the inherited pull path."""
+
+    push = True
+    SLOTS = (1, 2, 3)
+
+    def __init__(self, rank: int, world: int, meta_group=None):
+        super().__init__(rank, world, meta_group)
+        self.nccl = NcclTransport(rank, world, meta_group)
+        self.caps = {s_: [0] * world for s_ in self.SLOTS}     # every rank's capacity (bytes), known to all ranks
+        self.bases = {s_: [0] * world for s_ in self.SLOTS}    # arenas as mapped into this process
+        self._lease = {s_: None for s_ in self.SLOTS}
+        self._fence = None
+        self.push_events = []                                  # (e0, e1, bytes stored into peer arenas)
+
+    # -- collective helpers -----------------------------------------------------------------------------
+    def device(self):
+        return torch.device("cuda", torch.cuda.current_device())
+
+    def allgather_host(self, vec: torch.Tensor):
+        """vec: device int64 [n] -> numpy int64 [world, n] on the host (the one host wait of a push shuffle)"""
+        from . import kernels
+
+        out = torch.empty(self.world * vec.numel(), dtype=torch.int64, device=vec.device)
+        self.nccl.allgather_i64(vec, out)
+        return kernels.to_host([out])[0].reshape(self.world, vec.numel())
+
+    def free_slot(self) -> int:
+        for s_ in self.SLOTS:
+            ref = self._lease[s_]
+            if ref is None or ref() is None:
+                return s_
+        return -1
+
+    def ensure(self, slots: Sequence[int], need_bytes: Sequence[int]):
+        """collective and deterministic: rank q's arena ``slots[q]`` holds at least need_bytes[q].  A growing arena
+        is first unmapped by every peer (the exported allocation is never freed while mapped), then reallocated and
+        its handle published."""
+        growing = [q for q in range(self.world) if need_bytes[q] > self.caps[slots[q]][q] or not self.bases[slots[q]][q]]
+        if not growing:
+            return
+        for q in growing:
+            if q != self.rank:
+                check(self._lib.mgb_ipc_close_slot(q, slots[q]))
+        torch.cuda.synchronize()
+        dist.barrier(group=self.meta_group)
+        info = None
+        if self.rank in growing:
+            ptr, cap = C.c_void_p(), C.c_int64()
+            handle = (C.c_uint8 * 64)()
+            check(self._lib.mgb_ipc_arena_slot(slots[self.rank], int(need_bytes[self.rank]), C.byref(ptr), handle,
+                                               C.byref(cap), None))
+            info = (bytes(handle), int(cap.value), int(ptr.value or 0))
+        infos = [None] * self.world
+        dist.all_gather_object(infos, info, group=self.meta_group)
+        for q in growing:
+            handle, cap, ptr = infos[q]
+            self.caps[slots[q]][q] = cap
+            if q == self.rank:
+                self.bases[slots[q]][q] = ptr
+            else:
+                mapped = C.c_void_p()
+                check(self._lib.mgb_ipc_open_slot(q, slots[q], (C.c_uint8 * 64).from_buffer_copy(handle), C.byref(mapped)))
+                self.bases[slots[q]][q] = int(mapped.value or 0)
+
+    def local_view(self, slot: int, n_elements: int) -> torch.Tensor:
+        import weakref
+
+        owner = _ArenaOwner(self.bases[slot][self.rank], max(int(n_elements), 1))
+        self._lease[slot] = weakref.ref(owner)
+        return torch.as_tensor(owner, device=self.device())
+
+    def upload(self, array) -> torch.Tensor:
+        return torch.from_numpy(array).to(self.device(), non_blocking=True)
+
+    def fence(self):
+        """stream-ordered: when it completes on a rank, the partition kernels of ALL ranks have finished"""
+        if self._fence is None:
+            self._fence = (torch.zeros(1, dtype=torch.int64, device=self.device()),
+                           torch.zeros(self.world, dtype=torch.int64, device=self.device()))
+        self.nccl.allgather_i64(*self._fence)
+
+    def timed_begin(self):
+        if not self.timed:
+            return None
+        torch.cuda.synchronize()
+        dist.barrier(group=self.meta_group)
+        e0 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        return e0
+
+    def timed_end(self, e0, nbytes):
+        if e0 is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            self.push_events.append((e0, e1, nbytes))
+        self.bytes_sent += nbytes
+
+    def push_stats(self):
+        ms, nbytes = 0.0, 0
+        for e0, e1, b in self.push_events:
+            e1.synchronize()
+            ms += e0.elapsed_time(e1)
+            nbytes += b
+        return ms, nbytes
+
+    def close(self):
+        self.nccl.close()
 
 
 def _concat(pieces: List[torch.Tensor], like: torch.Tensor) -> torch.Tensor:
@@ -252,6 +410,13 @@ class Exchange:
         R = int(mappers[0].op.shuffle_size)
         P = self.world
         local = [i for i, m in enumerate(mappers) if owners[m.key] == self.rank]
+        if getattr(ctx, "defer_split", False) and getattr(self.transport, "push", False):
+            if self._shuffle_push(ctx, mappers, R, local, owners):
+                return
+        for i in local:      # mappers that stopped after pass 1: blocks of local columns for the packed exchange
+            d = ctx.pop((mappers[i].key, "deferred"), None)
+            if d is not None:
+                d.emit(ctx)
 
         def key_of(m, r):
             return (m.key, (r, m.index[1] if len(m.index) > 1 else 0))
@@ -275,9 +440,8 @@ class Exchange:
         send_off = [0]
         for p in range(P):
             send_off.append(send_off[-1] + ncols_local * send_rows[p])
-        handle = None
         if pull:
-            send_ptr, handle = self.transport.reserve(max(send_off[-1], 1))
+            send_ptr = self.transport.reserve_collective(max(send_off[-1], 1))
             sendbuf = None
         else:
             sendbuf = torch.empty(max(send_off[-1], 1), dtype=torch.int64, device=dev)
@@ -312,7 +476,7 @@ class Exchange:
         if pull:
             torch.cuda.current_stream().synchronize()   # the arena is complete before its handle is published
         # ---- one metadata all-gather: block counts (+ the arena handle and slice offsets for pull transports)
-        metas = self._gather_meta(dict(counts=counts, schema=schema, as_tuple=as_tuple, wrapped=wrapped, handle=handle,
+        metas = self._gather_meta(dict(counts=counts, schema=schema, as_tuple=as_tuple, wrapped=wrapped,
                                        send_off=send_off if pull else None))
         all_counts = {}
         for m_ in metas:
@@ -337,8 +501,8 @@ class Exchange:
             recv_off.append(recv_off[-1] + ncols * recv_rows[q])
         if pull:
             recvbuf = torch.empty(max(recv_off[-1], 1), dtype=torch.int64, device=dev)
-            peers = [None if q == self.rank or metas[q]["handle"] is None else
-                     (metas[q]["handle"], metas[q]["send_off"][self.rank]) for q in range(P)]
+            peers = [None if q == self.rank or metas[q]["send_off"] is None else metas[q]["send_off"][self.rank]
+                     for q in range(P)]
             self.transport.pull(recvbuf, recv_off, peers)
         else:
             recvbuf = self.transport.alltoallv([sendbuf], send_off, recv_off)[0]
@@ -366,6 +530,113 @@ class Exchange:
                     n = all_counts[(i, r)]
                     ctx[key_of(m, r)] = entry(m, self._rebuild(schema, cols, pos, pos + n, as_tuple))
                     pos += n
+
+    # ------------------------------------------------------------------------------------ push shuffle
+    def _shuffle_push(self, ctx, mappers, R: int, local: List[int], owners: Dict[str, int]) -> bool:
+        """Hash shuffle with the fused partition -> peer transfer (PushTransport).  Collective; returns False --
+        on every rank alike -- when some rank could not defer a mapper or has no free receive arena; the caller
+        then runs the packed exchange.
+
+        Layout of rank p's arena: for every source rank q, for every column c, the blocks (mapper of q ascending,
+        reducer of p ascending) back to back, each padded to an even number of rows so that every block starts on a
+        16-byte boundary (16-byte stores in the partition kernel); the reducers' blocks are views into it."""
+        import numpy as np
+
+        t = self.transport
+        P = self.world
+        per_rank = [[i for i, m in enumerate(mappers) if owners[m.key] == q] for q in range(P)]
+        M = max(1, max(len(x) for x in per_rank))
+        splits = [ctx.get((mappers[i].key, "deferred")) for i in local]
+        ok = all(d is not None and d.R == R for d in splits)
+        slot = t.free_slot() if ok else -1
+        ncols = len(splits[0].cols) if (ok and splits) else 0
+        head = np.zeros(4 + M * (R + 1), dtype=np.int64)
+        head[:3] = (1 if (ok and slot > 0) else 0, slot, ncols)
+        vec = t.upload(head)
+        if ok:
+            for j, d in enumerate(splits):
+                vec[4 + j * (R + 1): 4 + (j + 1) * (R + 1)].copy_(d.offsets)
+        allv = t.allgather_host(vec)                                   # [P, 4 + M (R + 1)]: the one host wait
+        if not all(int(allv[q, 0]) == 1 for q in range(P)):
+            return False
+        slots = [int(allv[q, 1]) for q in range(P)]
+        ncols = max(int(allv[q, 2]) for q in range(P))
+        if ncols == 0:
+            for i in local:
+                ctx.pop((mappers[i].key, "deferred"), None)
+            return True
+        offs = allv[:, 4:].reshape(P, M, R + 1)
+        cnt = offs[:, :, 1:] - offs[:, :, :-1]                          # [source rank, its j-th mapper, reducer]
+        for q in range(P):
+            cnt[q, len(per_rank[q]):, :] = 0
+        pad = (cnt + 1) & ~1
+        red_lo = [min((r for r in range(R) if reducer_rank(r, R, P) == p), default=0) for p in range(P)]
+        red_hi = [max((r + 1 for r in range(R) if reducer_rank(r, R, P) == p), default=0) for p in range(P)]
+        seg_rows = np.zeros((P, P), dtype=np.int64)                     # [receiver p, source q]: padded rows per column
+        within = [None] * P                                             # [p][q, j, r - lo]: row of the block in its segment
+        for p in range(P):
+            sub = pad[:, :, red_lo[p]:red_hi[p]]
+            flat = sub.reshape(P, -1)
+            csum = np.cumsum(flat, axis=1)
+            within[p] = (csum - flat).reshape(sub.shape)
+            seg_rows[p] = flat.sum(axis=1)
+        seg_base = np.zeros((P, P), dtype=np.int64)                     # first element of segment (p, q) in p's arena
+        seg_base[:, 1:] = np.cumsum(ncols * seg_rows, axis=1)[:, :-1]
+        need = [int(8 * ncols * seg_rows[p].sum()) for p in range(P)]
+        t.ensure(slots, need)
+        # ---- destination tables of the local mappers: [mapper, column, reducer] -> address
+        q = self.rank
+        sent = 0
+        if local:
+            tab = np.zeros((len(local), ncols, R), dtype=np.int64)
+            cix = np.arange(ncols, dtype=np.int64)[:, None]
+            for p in range(P):
+                lo, hi = red_lo[p], red_hi[p]
+                if hi <= lo:
+                    continue
+                base = t.bases[slots[p]][p]
+                for j in range(len(local)):
+                    tab[j, :, lo:hi] = base + 8 * (seg_base[p, q] + cix * seg_rows[p, q] + within[p][q, j][None, :])
+                if p != q:
+                    sent += int(cnt[q, :len(local), lo:hi].sum())
+            dtab = t.upload(tab.reshape(len(local), -1))
+            e0 = t.timed_begin()
+            from . import executors      # the kernels module the executors are bound to
+
+            for j, d in enumerate(splits):
+                executors._kernels.split_scatter(d.keys, R, d.hist, d.cols, table=dtab[j])
+            t.timed_end(e0, sent * ncols * 8)
+        else:
+            t.timed_end(t.timed_begin(), 0)
+        t.fence()
+        self.shuffle_rows_sent += sent
+        # ---- the blocks of this rank's reducers: views into its arena
+        schema = splits[0].schema() if splits else None
+        if any(not x for x in per_rank):
+            metas = self._gather_meta(schema)
+            schema = next(m_ for m_ in metas if m_ is not None)
+        dtypes = [torch.int64] * schema["nk"]
+        for _, dts in schema["slots"]:
+            dtypes += [getattr(torch, d_.replace("torch.", "")) for d_ in dts]
+        arena = t.local_view(slots[q], need[q] // 8)
+        p = self.rank
+        lo, hi = red_lo[p], red_hi[p]
+        template = splits[0] if splits else None
+        for src in range(P):
+            rows = int(seg_rows[p, src])
+            cols = [arena[seg_base[p, src] + c * rows: seg_base[p, src] + (c + 1) * rows].view(dtypes[c])
+                    for c in range(ncols)]
+            for j, i in enumerate(per_rank[src]):
+                m = mappers[i]
+                for r in range(lo, hi):
+                    a = int(within[p][src, j, r - lo])
+                    v = self._rebuild(schema, cols, a, a + int(cnt[src, j, r]), True)
+                    is_tuple = template.is_tuple if template is not None else True
+                    block = v if is_tuple else v[0]
+                    ctx[(m.key, (r, m.index[1] if len(m.index) > 1 else 0))] = (m.index, block)
+        for i in local:
+            ctx.pop((mappers[i].key, "deferred"), None)
+        return True
 
     # ------------------------------------------------------------------------------- point-to-point fetch
     def transfer(self, ctx, key, src: int, dst: int):
@@ -436,15 +707,19 @@ def init_exchange(backend: Optional[str] = None) -> Exchange:
         torch.cuda.set_device(local % torch.cuda.device_count())
     if not dist.is_initialized():
         dist.init_process_group(backend=backend or "gloo", rank=rank, world_size=world)
-    meta_group = None  # default group is gloo: host metadata only; bytes move through libmarsgb
+    # host metadata travels over gloo (the default group, or a gloo side group when the caller initialised NCCL);
+    # bytes move through libmarsgb
+    meta_group = None
+    if world > 1 and dist.get_backend() != "gloo":
+        meta_group = dist.new_group(backend="gloo")
     # transport: MGB_EXCHANGE = nccl | ipc | auto (default).  auto = the peer-to-peer pull transport when every
     # rank can map every peer's arena (one box, all GPUs visible, P2P capable), else grouped ncclSend/ncclRecv
-    kind = os.environ.get("MGB_EXCHANGE", "auto")
+    kind = os.environ.get("MGB_EXCHANGE", "auto")     # push (default where possible) | ipc (pull only) | nccl
     transport = None
-    if kind in ("ipc", "auto") and world > 1 and torch.cuda.is_available():
+    if kind in ("push", "ipc", "auto") and world > 1 and torch.cuda.is_available():
         ok = False
         try:
-            t = IpcPullTransport(rank, world, meta_group)
+            t = (IpcPullTransport if kind == "ipc" else PushTransport)(rank, world, meta_group)
             _, handle = t.reserve(1)
             handles = [None] * world
             dist.all_gather_object(handles, handle, group=meta_group)
@@ -455,7 +730,7 @@ def init_exchange(backend: Optional[str] = None) -> Exchange:
                     check(lib.mgb_ipc_open(q, (C.c_uint8 * 64).from_buffer_copy(h), C.byref(src)))
             ok = True
         except Exception:  # noqa: BLE001
-            if kind == "ipc":
+            if kind in ("ipc", "push"):
                 raise
         flags = [None] * world
         dist.all_gather_object(flags, ok, group=meta_group)

@@ -251,6 +251,7 @@ class Session:
     def _execute(self, df: DataFrame, **kw):
         t = df.data
         ctx = ProcessorContext()
+        ctx.defer_split = self.world > 1 and bool(getattr(getattr(self.exchange, "transport", None), "push", False))
         owners: Dict[str, int] = {}
         self._eager = None
         if t.chunks is None:

@@ -397,3 +397,34 @@ def filter_rows(filter_col, op, value, cols):
     keep = _cmp(_np(filter_col), op, value)
     idx = torch.from_numpy(np.nonzero(keep)[0])
     return [c[idx] for c in cols], int(keep.sum())
+
+
+# ---- two-pass partition kernel (mgb_split_plan / mgb_split_scatter).  Destination tables hold whatever "addresses"
+# the transport double hands out; ``poke(address, values)`` (set by that double) stores 8-byte values there.
+poke = None
+
+
+def split_plan(keys, n_partitions, mode=0):
+    calls.append("split_plan")
+    pid = (orc.hash_frame_rows([_np(k) for k in keys]) % np.uint64(n_partitions)).astype(np.int64) if mode == 1 \
+        else orc.partition_ids([_np(k) for k in keys], n_partitions)
+    counts = np.bincount(pid, minlength=n_partitions)
+    offsets = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    return torch.from_numpy(pid), torch.from_numpy(offsets)
+
+
+def split_scatter(keys, n_partitions, hist, cols, outs=None, table=None, mode=0):
+    calls.append("split_scatter")
+    pid = _np(hist)
+    order = np.argsort(pid, kind="stable")
+    bounds = np.searchsorted(pid[order], np.arange(n_partitions + 1))
+    for c, col in enumerate(cols):
+        src = _np(col)[order]
+        if table is None:
+            outs[c].copy_(torch.from_numpy(src))
+            continue
+        tab = _np(table).reshape(len(cols), n_partitions)
+        for p_ in range(n_partitions):
+            blk = src[bounds[p_]:bounds[p_ + 1]]
+            if len(blk):
+                poke(int(tab[c, p_]), blk.view(np.int64))

@@ -45,6 +45,83 @@ class GlooTransport:
         return out
 
 
+class FakePushTransport(GlooTransport):
+    """stand-in for parallel.PushTransport: receive arenas are files mapped by both processes, an "address" is
+    (owner rank + 1) << 48 | slot << 44 | byte offset, the count exchange is a gloo all_gather, the fence a barrier.
+    Everything above the C ABI of the push shuffle -- layout of the arenas, destination tables, slot rotation,
+    views handed to the reducers, fallback to the packed exchange -- runs unchanged."""
+
+    push = True
+    SLOTS = (1, 2, 3)
+
+    def __init__(self, rank, world, tag, deny_slot=False):
+        super().__init__(rank, world)
+        self.tag, self.deny_slot = tag, deny_slot
+        self.maps = {}                       # (owner, slot) -> np.memmap
+        self.caps = {s_: [0] * world for s_ in self.SLOTS}
+        self.bases = {s_: [((q + 1) << 48) | (s_ << 44) for q in range(world)] for s_ in self.SLOTS}
+        self.next = 0
+        self.pushes = 0
+        self.bytes_sent = 0
+        import fake_kernels
+
+        fake_kernels.poke = self.poke
+
+    def _path(self, owner, slot):
+        return f"/tmp/mgb_fake_arena_{self.tag}_{owner}_{slot}"
+
+    def poke(self, address, values):
+        owner, slot, off = (address >> 48) - 1, (address >> 44) & 15, address & ((1 << 44) - 1)
+        assert off % 8 == 0
+        m = self.maps[owner, slot]
+        m[off // 8: off // 8 + len(values)] = values
+
+    def allgather_host(self, vec):
+        out = [torch.empty_like(vec) for _ in range(self.world)]
+        dist.all_gather(out, vec)
+        return torch.stack(out).numpy()
+
+    def free_slot(self):
+        if self.deny_slot and self.rank == 1:
+            return -1
+        self.next = self.next % len(self.SLOTS) + 1
+        return self.next
+
+    def ensure(self, slots, need_bytes):
+        growing = [q for q in range(self.world) if need_bytes[q] > self.caps[slots[q]][q]]
+        if not growing:
+            return
+        for q in growing:
+            self.maps.pop((q, slots[q]), None)
+        dist.barrier()
+        if self.rank in growing:
+            n = max(need_bytes[self.rank] // 8, 1) * 2
+            np.memmap(self._path(self.rank, slots[self.rank]), dtype=np.int64, mode="w+", shape=(n,)).flush()
+        dist.barrier()
+        for q in growing:
+            m = np.memmap(self._path(q, slots[q]), dtype=np.int64, mode="r+")
+            self.maps[q, slots[q]] = m
+            self.caps[slots[q]][q] = m.nbytes
+
+    def local_view(self, slot, n_elements):
+        return torch.from_numpy(self.maps[self.rank, slot])[:max(n_elements, 1)]
+
+    def upload(self, array):
+        return torch.from_numpy(array)
+
+    def fence(self):
+        for m in self.maps.values():
+            m.flush()
+        dist.barrier()
+
+    def timed_begin(self):
+        return None
+
+    def timed_end(self, e0, nbytes):
+        self.pushes += 1
+        self.bytes_sent += nbytes
+
+
 def _worker(rank, world, port, case, q):
     for p in (ROOT, os.path.join(ROOT, "oracle"), HERE):
         if p not in sys.path:
@@ -72,6 +149,24 @@ def _worker(rank, world, port, case, q):
             exp = raw.groupby(["key", "k2"]).agg(["sum", "mean", "count", "min", "max", "var"])
             q.put((rank, got.sort_index().equals(exp) or _close(got.sort_index(), exp), ex.shuffle_rows_sent,
                    sorted(set(sess.executed_ops))))
+        elif case in ("push", "push_denied"):
+            # fused partition -> peer transfer: mappers stop after pass 1, the exchange lays out the arenas and
+            # lets pass 2 write into them; three shuffles in a row rotate the arena slots.  "push_denied": one rank
+            # has no free arena -> every rank takes the packed exchange for that shuffle
+            tr = FakePushTransport(rank, world, port, deny_slot=(case == "push_denied"))
+            ex = parallel.Exchange(tr, rank, world)
+            funcs = ["sum", "mean", "count", "min", "max", "var"]
+            exp = raw.groupby(["key", "k2"]).agg(funcs)
+            ok = True
+            for rep in range(3):
+                sess = md.new_session(exchange=ex, default=False)
+                r = md.DataFrame(raw, chunk_size=500 if rep < 2 else 1300).to_gpu().groupby(["key", "k2"], sort=False) \
+                    .agg(funcs, method="shuffle")
+                r.execute(session=sess)
+                got = sess.fetch(r)
+                ok = ok and _close(got.sort_index(), exp)
+            q.put((rank, ok, ex.shuffle_rows_sent, sorted(set(sess.executed_ops)), tr.pushes,
+                   fake_kernels.calls.count("split_scatter")))
         elif case == "psrs":   # sort=True shuffle: samples -> pivots -> range shuffle across ranks
             ex = parallel.Exchange(GlooTransport(rank, world), rank, world)
             sess = md.new_session(exchange=ex, default=False)
@@ -123,6 +218,24 @@ def test_hash_shuffle_across_two_ranks():
         assert ok, f"rank {rank}: result differs from pandas"
         assert rows_sent > 0                      # blocks really crossed ranks
         assert "DataFrameGroupByOperand:map" in ops and "DataFrameGroupByOperand:reduce" in ops
+
+
+@pytest.mark.timeout(180)
+def test_push_shuffle_across_two_ranks():
+    """deferred split + destination tables + arena views (parallel.Exchange._shuffle_push) against pandas"""
+    out = _run("push", 29644)
+    for rank, ok, rows_sent, ops, pushes, scatters in out:
+        assert ok, f"rank {rank}: result differs from pandas"
+        assert rows_sent > 0 and pushes == 3 and scatters > 0
+        assert "DataFrameGroupByOperand:map" in ops and "DataFrameGroupByOperand:reduce" in ops
+
+
+@pytest.mark.timeout(180)
+def test_push_shuffle_falls_back_on_every_rank_when_one_has_no_arena():
+    out = _run("push_denied", 29645)
+    for rank, ok, rows_sent, ops, pushes, scatters in out:
+        assert ok, f"rank {rank}: result differs from pandas"
+        assert rows_sent > 0 and pushes == 0
 
 
 @pytest.mark.timeout(180)

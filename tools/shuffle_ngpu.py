@@ -31,8 +31,21 @@ def main():
     ap.add_argument("--chunks-per-gpu", type=int, default=4)
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--sort", action="store_true", help="groupby(sort=True): PSRS range shuffle instead of the hash shuffle")
+    ap.add_argument("--config", default=None, help="run tools/shuffle_leg.py on this BASELINE config (cfg3 / cfg4 / cfg5) "
+                                                   "with --rows rows per GPU instead of the uniform-key frame")
+    ap.add_argument("--chunk-rows", type=int, default=15_625_000)
     args = ap.parse_args()
     ex = parallel.init_exchange("gloo")          # gloo: host metadata; bytes move through libmarsgb + NCCL
+    if args.config:
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+        import shuffle_leg
+
+        rec = shuffle_leg.run(ex, args.config, rows_per_gpu=args.rows, chunk_rows=args.chunk_rows)
+        if ex.rank == 0:
+            print(json.dumps(rec), flush=True)
+        ex.transport.close()
+        dist.destroy_process_group()
+        return
     rank, world = ex.rank, ex.world
     ex.transport.timed = True
     rng = np.random.default_rng(11)
