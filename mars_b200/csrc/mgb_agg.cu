@@ -724,12 +724,12 @@ __global__ void __launch_bounds__(GLOBAL_THREADS) k_merge_staged(const MergePara
       const AccDesc d = p.L.acc[j];
       const int a = p.L.acc_index[j];
       const uint64_t v = p.stg.base[(long long)(p.L.nk + a) * p.stg.cap + i];
-      // merge step of a decoded partial: SUM/SUMSQ/COUNT add, MIN/MAX re-encode (NaN == "no value")
+      // merge step of a staged row of THIS aggregator (phase 1 -> phase 2): SUM/SUMSQ/COUNT add -- a NaN sum
+      // (inf - inf) stays NaN, as in pandas' group_sum over the chunk; MIN/MAX re-encode (NaN == "no value")
       uint64_t contrib;
       bool ok = true;
       if (d.kind == 0) {
         contrib = v;
-        ok = !mgb_is_nan_bits(v);
       } else if (d.kind == 1) {
         contrib = v;
         ok = v != 0;

@@ -555,7 +555,11 @@ __global__ void __launch_bounds__(SM_THREADS, 1) k_merge_small(const SmallParams
     for (int q = (on ? ucnt[u] : 0) + sl; q < q1; q += L) {
       const int it = sorted[q];
       const uint64_t* col = p.acc_ptrs[item_pc[it] * na + a];
-      v = dense_combine(kind, f, v, ld_cg(col + item_r[it]));
+      uint64_t y = ld_cg(col + item_r[it]);
+      // a NaN partial SUM (inf - inf inside one chunk) is skipped, as the reference's combine / agg stages do: they
+      // re-aggregate the partial frames with pandas' skipna sum (aggregation.py:1130-1164, 1023-1032)
+      if (f && kind == 1 && mgb_is_nan_bits(y)) y = 0;
+      v = dense_combine(kind, f, v, y);
     }
     for (int o = 1; o < L; o <<= 1) v = dense_combine(kind, f, v, __shfl_xor_sync(0xffffffffu, v, o));
     if (on && sl == 0) p.out.acc[a][rank[u]] = v;

@@ -53,37 +53,27 @@ __device__ __forceinline__ uint32_t sp_pid(const SplitSrc& s, int64_t i, bool po
   return (uint32_t)(pow2 ? (h & (s.R - 1)) : (h % s.R));
 }
 
+// counting needs no order: one shared-memory atomic per row (the stable ranks are pass 2's business)
 template <int NK, int MODE>
 __global__ void __launch_bounds__(SP_THREADS) k_split_hist(SplitSrc s, int64_t n, int64_t ntiles, int R,
                                                            int64_t* __restrict__ hist, int32_t* bad) {
-  __shared__ uint32_t wc[SP_WARPS][SP_MAX_R];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < SP_WARPS * SP_MAX_R; i += SP_THREADS) (&wc[0][0])[i] = 0;
+  __shared__ uint32_t cnt[SP_MAX_R];
+  if (threadIdx.x < SP_MAX_R) cnt[threadIdx.x] = 0;
   __syncthreads();
   const bool pow2 = (s.R & (s.R - 1)) == 0;
   const int64_t tile = blockIdx.x;
-  const int64_t base = tile * SP_TILE + warp * (SP_TILE / SP_WARPS);
-  const unsigned lt = mgb_lanemask_lt();
+  const int64_t base = tile * SP_TILE + threadIdx.x;
   uint32_t dg[SP_ROUNDS];
 #pragma unroll
   for (int r = 0; r < SP_ROUNDS; ++r) {   // all key loads of the thread in flight together
-    const int64_t i = base + r * 32 + lane;
-    dg[r] = i < n ? sp_pid<NK, MODE>(s, i, pow2, bad) : (uint32_t)(SP_MAX_R + lane);
+    const int64_t i = base + r * SP_THREADS;
+    dg[r] = i < n ? sp_pid<NK, MODE>(s, i, pow2, bad) : 0xffffffffu;
   }
 #pragma unroll
-  for (int r = 0; r < SP_ROUNDS; ++r) {
-    const bool valid = base + r * 32 + lane < n;
-    const unsigned peers = __match_any_sync(0xffffffffu, dg[r]);
-    if (valid && (peers & lt) == 0) wc[warp][dg[r]] += (uint32_t)__popc(peers);
-    __syncwarp();
-  }
+  for (int r = 0; r < SP_ROUNDS; ++r)
+    if (dg[r] != 0xffffffffu) atomicAdd(&cnt[dg[r]], 1u);
   __syncthreads();
-  for (int p = threadIdx.x; p < R; p += SP_THREADS) {
-    uint32_t t = 0;
-#pragma unroll
-    for (int w = 0; w < SP_WARPS; ++w) t += wc[w][p];
-    hist[(int64_t)p * ntiles + tile] = t;
-  }
+  for (int p = threadIdx.x; p < R; p += SP_THREADS) hist[(int64_t)p * ntiles + tile] = cnt[p];
 }
 
 // block boundaries out of the scanned histogram

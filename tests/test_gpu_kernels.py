@@ -785,3 +785,51 @@ def test_split_two_passes_with_destination_table(K, n_keys, mode, n, R):
             np.testing.assert_array_equal(blk.view(src.dtype), sorted_src[off[p]:off[p + 1]])
             touched[s0:s0 + counts[p]] = True
         assert (a[~touched] == -7).all(), "a store outside the blocks"
+
+
+@pytest.mark.parametrize("n,card,block", [(200_000, 300, 0), (1_000_003, 50_000, 65_536), (0, 1, 0)])
+def test_host_buffer_entry_matches_pandas(K, n, card, block):
+    """mgb_groupby_agg_host: the whole path from HOST columns (blocked H2D overlapped with the kernels, result into
+    host arrays) -- what a binding without device arrays calls; every op, both dtypes, sorted keys"""
+    import ctypes as C
+
+    from mars_b200 import _lib
+
+    lib = _lib.load()
+    rng = np.random.default_rng(n + card)
+    k = rng.integers(-card, card, n, dtype=np.int64)
+    v = rng.normal(5, 2, n)
+    if n:
+        v[rng.integers(0, n, max(n // 50, 1))] = np.nan
+    w = rng.integers(-100, 100, n, dtype=np.int64)
+    accs = [(0, K.SUM), (0, K.COUNT), (0, K.MIN), (0, K.MAX), (0, K.SUMSQ), (1, K.SUM), (1, K.MIN), (1, K.MAX), (1, K.COUNT)]
+    spec = _lib.make_spec(1, [_lib.F64, _lib.I64], accs)
+    cap = max(2 * card + 8, 8)
+    out_k = np.zeros(cap, dtype=np.int64)
+    out_a = [np.zeros(cap, dtype=np.float64 if (c == 0 and op != K.COUNT) else np.int64) for c, op in accs]
+    keys_p = _lib.ptr_array([k.ctypes.data])
+    vals_p = _lib.ptr_array([v.ctypes.data, w.ctypes.data])
+    ok_p = _lib.ptr_array([out_k.ctypes.data])
+    oa_p = _lib.ptr_array([a.ctypes.data for a in out_a])
+    G = C.c_int64()
+    _lib.check(lib.mgb_groupby_agg_host(C.byref(spec), keys_p, vals_p, n, block, ok_p, oa_p, cap, 1, C.byref(G),
+                                         torch.cuda.current_stream().cuda_stream))
+    df = pd.DataFrame({"k": k, "v": v, "w": w})
+    g = df.groupby("k", sort=True)
+    assert G.value == g.ngroups
+    m = G.value
+    if m == 0:
+        return
+    np.testing.assert_array_equal(out_k[:m], np.array(sorted(g.groups.keys()), dtype=np.int64))
+    exp = g.agg(v_sum=("v", "sum"), v_count=("v", "count"), v_min=("v", "min"), v_max=("v", "max"),
+                w_sum=("w", "sum"), w_min=("w", "min"), w_max=("w", "max"), w_count=("w", "count"))
+    sq = (df["v"] ** 2).groupby(df["k"], sort=True).sum()
+    np.testing.assert_allclose(out_a[0][:m], exp["v_sum"].to_numpy(), rtol=1e-9, atol=0)
+    np.testing.assert_array_equal(out_a[1][:m], exp["v_count"].to_numpy())
+    np.testing.assert_array_equal(out_a[2][:m], exp["v_min"].to_numpy())
+    np.testing.assert_array_equal(out_a[3][:m], exp["v_max"].to_numpy())
+    np.testing.assert_allclose(out_a[4][:m], sq.to_numpy(), rtol=1e-9, atol=0)
+    np.testing.assert_array_equal(out_a[5][:m], exp["w_sum"].to_numpy())
+    np.testing.assert_array_equal(out_a[6][:m], exp["w_min"].to_numpy())
+    np.testing.assert_array_equal(out_a[7][:m], exp["w_max"].to_numpy())
+    np.testing.assert_array_equal(out_a[8][:m], exp["w_count"].to_numpy())

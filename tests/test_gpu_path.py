@@ -320,3 +320,27 @@ def test_tree_branch_runs_as_one_batch_launch(md, method, func):
     assert launches == 2, launches     # one band-level batch (launched before tiling) + one agg-stage launch
     assert results[False][2].fused_trees == 0 and results[False][1] > launches
     assert sess.executed_ops.count("DataFrameGroupByAgg:map") == 12
+
+
+def test_infinite_values_and_nan_partials_follow_the_reference(cuda_device):
+    """+inf and -inf in one group of one chunk make that chunk's partial sum NaN; the reference's combine / agg
+    stages re-aggregate the partials with pandas' skipna sum, i.e. they DROP it (aggregation.py:1130-1164).  The
+    per-operand path must give the oracle's (= the reference's) answer, not the all-rows-at-once one."""
+    import mars_b200 as md
+
+    rng = np.random.default_rng(3)
+    n = 40_000
+    raw = pd.DataFrame({"k": rng.integers(0, 5, n), "v": rng.normal(size=n), "w": rng.random(n)})
+    raw.loc[10, ["k", "v"]] = [2, np.inf]
+    raw.loc[11, ["k", "v"]] = [2, -np.inf]          # both in chunk 0
+    raw.loc[30_000, ["k", "w"]] = [3, np.inf]       # a lone +inf: the sum of group 3 is +inf everywhere
+    raw["k"] = raw["k"].astype(np.int64)
+    funcs = ["sum", "mean", "count", "min", "max"]
+    exp = orc.run_groupby_agg(raw, ["k"], funcs, 10_000, method="tree", sort=True)
+    sess = md.new_session(default=False)
+    sess.fuse = False                               # every chunk operand on its own, like a Mars worker
+    got = md.DataFrame(raw, chunk_size=10_000).to_gpu().groupby("k").agg(funcs, method="tree").execute(session=sess) \
+        .fetch(session=sess)
+    assert_frames_match(got, exp, sort_index=False)
+    assert np.isposinf(got.loc[3, ("w", "sum")]) and np.isfinite(got.loc[2, ("v", "sum")])
+    assert got.loc[2, ("v", "min")] == -np.inf and got.loc[2, ("v", "max")] == np.inf
