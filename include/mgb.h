@@ -304,6 +304,14 @@ int mgb_groupby_agg_host(const mgb_agg_spec* spec, const int64_t* const* key_col
                          int64_t* const* out_key_cols_host, void* const* out_acc_cols_host,
                          int64_t max_groups, int32_t sort_keys, int64_t* out_n_groups, void* stream);
 
+/* ---- a4 for chunks whose group keys are (nearly) all distinct: a row is its own partial ------------------------
+ * The map stage of the reference groups every chunk (aggregation.py:1043-1128); when a chunk has about as many
+ * groups as rows that fold reduces nothing, and the combine / agg stages re-group the partial rows anyway
+ * (aggregation.py:1130-1267).  The partial of such a chunk is then the chunk itself: SUM / MIN / MAX partials are
+ * the value column (aliased, no copy), and this entry writes the two that are not: op = MGB_COUNT -> int64
+ * "value is not NaN" (1 for an int64 column), op = MGB_SUMSQ -> value * value rounded (no FMA), dtype of the column. */
+int mgb_row_partial(const void* val, int32_t val_dtype, int32_t op, void* out, int64_t n, void* stream);
+
 /* ---- a10: post functions -----------------------------------------------------------------------------
  * The generated post_funcs of the reference, evaluated in float64 in the reference's operation order
  * (mars/dataframe/reduction/mean.py:26-33, var.py:38-48):

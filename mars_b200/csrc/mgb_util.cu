@@ -489,6 +489,48 @@ static unsigned grid_for(int64_t n) {
   return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
+// a4 without a fold: the per-row partial of one accumulator for chunks whose keys are (nearly) all distinct.  A row IS
+// its group's partial there: SUM / MIN / MAX are the value itself (the caller aliases the column), COUNT is
+// "value is not NaN" and SUMSQ the rounded square -- written here, two rows per 16-byte access.
+__global__ void __launch_bounds__(256) k_row_partial(const uint64_t* __restrict__ v, int dt, int op,
+                                                     uint64_t* __restrict__ out, int64_t n) {
+  const int64_t pairs = n >> 1;
+  auto one = [&](uint64_t x) -> uint64_t {
+    if (op == MGB_COUNT) return (dt == MGB_F64 && mgb_is_nan_bits(x)) ? 0ULL : 1ULL;
+    if (dt == MGB_F64) {
+      const double d = __longlong_as_double((long long)x);
+      return (uint64_t)__double_as_longlong(__dmul_rn(d, d));
+    }
+    return x * x;
+  };
+  const bool vec = (((uintptr_t)v | (uintptr_t)out) & 15) == 0;
+  if (vec) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < pairs; i += (int64_t)gridDim.x * blockDim.x) {
+      const ulonglong2 x = __ldg(reinterpret_cast<const ulonglong2*>(v) + i);
+      ulonglong2 y;
+      y.x = one(x.x);
+      y.y = one(x.y);
+      reinterpret_cast<ulonglong2*>(out)[i] = y;
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) out[n - 1] = one(v[n - 1]);
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+      out[i] = one(mgb_ld_stream(v + i));
+  }
+}
+
+extern "C" int mgb_row_partial(const void* val, int32_t val_dtype, int32_t op, void* out, int64_t n, void* stream) {
+  MGB_REQUIRE(n >= 0, MGB_ERR_INVALID, "negative n");
+  MGB_REQUIRE(op == MGB_COUNT || op == MGB_SUMSQ, MGB_ERR_INVALID, "op %d needs no per-row partial", op);
+  if (n == 0) return MGB_OK;
+  MGB_REQUIRE(val && out, MGB_ERR_INVALID, "null pointer");
+  MgbProfScope prof(MGB_K_POST, (cudaStream_t)stream);
+  k_row_partial<<<grid_for((n + 1) / 2), 256, 0, (cudaStream_t)stream>>>((const uint64_t*)val, val_dtype, op,
+                                                                        (uint64_t*)out, n);
+  MGB_CHECK_LAUNCH();
+  return MGB_OK;
+}
+
 extern "C" int mgb_post_mean(const void* sum, int32_t sum_dtype, const int64_t* count, double* out,
                              int64_t n, void* stream) {
   MGB_REQUIRE(n >= 0, MGB_ERR_INVALID, "negative n");

@@ -213,6 +213,11 @@ _DEVICE_RESULTS = os.environ.get("MGB_DEVICE_RESULTS", "1") not in ("0", "")
 _DEVICE_RESULT_ROWS = int(os.environ.get("MGB_DEVICE_RESULT_ROWS", "2049"))   # smaller results go straight to pandas
 _PREAGG_GROUPS = 2048     # chunks with at most this many groups are worth the shared-memory pre-aggregation
 _PROBE_MIN_ROWS = 65536   # smaller chunks are not worth the cardinality probe
+# map stage of chunks whose sampled keys are >= 90 % distinct hands the rows on as their own partials (MGB_MAP_PASSTHROUGH=0:
+# always group the chunk, like the reference's map stage)
+_PASSTHROUGH = os.environ.get("MGB_MAP_PASSTHROUGH", "1") not in ("0", "")
+passthrough_chunks = 0    # map operands that took that path (tests, bench records)
+_group_ratio: Dict[Any, float] = {}   # shape -> groups / rows of the last chunk of that shape that was really grouped
 
 
 def _map_plan(op, frame: DeviceFrame) -> _MapPlan:
@@ -381,7 +386,21 @@ def _execute_agg_map(ctx, op):
             if sampled and uniq * 4 >= sampled * 3:
                 _distinct_shapes.add(plan.shape_key)
                 distinct = True
-        if distinct:
+        passthrough = False
+        if (distinct and _PASSTHROUGH and hasattr(_kernels, "row_partials") and hasattr(_kernels, "estimate_distinct")
+                and len(frame) >= _PROBE_MIN_ROWS and _group_ratio.get(plan.shape_key, 0.0) >= 0.9):
+            # the last chunk of this shape that WAS grouped came back with about as many groups as rows: grouping
+            # reduces nothing, and the combine / agg stages re-group the partial rows anyway
+            # (aggregation.py:1130-1267) -- the rows ARE the partials.  (A sample cannot tell this regime from many
+            # groups of a few rows each: 16 K sampled keys of a million groups are all distinct, too; the sample is
+            # only the cheap check that this chunk still looks like the one that was measured.)
+            sampled, uniq = _kernels.estimate_distinct(keys)
+            passthrough = bool(sampled) and uniq * 10 >= sampled * 9
+        if passthrough:
+            global passthrough_chunks
+            passthrough_chunks += 1
+            out_keys, out_accs, stats = list(keys), _kernels.row_partials(vals, list(plan.accs)), None
+        elif distinct:
             out_keys, out_accs, stats = _kernels.groupby_aggregate(keys, vals, list(plan.accs), sort=False,
                                                                    expect_distinct=True)
             if stats and (int(out_keys[0].numel()) <= _PREAGG_GROUPS or stats.get("bucket_fallback") == 2):
@@ -391,6 +410,8 @@ def _execute_agg_map(ctx, op):
             if stats and stats.get("rows_spilled", 0) * 2 > int(keys[0].numel()):
                 _distinct_shapes.add(plan.shape_key)
         n_out = int(out_keys[0].numel())
+        if not passthrough and len(frame):
+            _group_ratio[plan.shape_key] = n_out / len(frame)
         if n_out <= 32:
             _dense_rejected.discard(plan.shape_key)      # the data changed: the one-launch path fits again
         frames = [DeviceFrame(plan.by, out_keys, cols, out_accs[a0:a1], n_out) for cols, a0, a1 in plan.slots]

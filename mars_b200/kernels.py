@@ -938,6 +938,23 @@ def to_host_concat(parts: Sequence[Sequence[torch.Tensor]]):
 
 
 # ------------------------------------------------------------------------------------------------- post
+def row_partials(vals: Sequence[torch.Tensor], accs: Sequence[Tuple[int, int]]) -> List[torch.Tensor]:
+    """per-row partials of a chunk whose keys are (nearly) all distinct (mgb_row_partial): SUM / MIN / MAX alias the
+    value column, COUNT and SUMSQ are written (one elementwise launch each)."""
+    lib = _lib.load()
+    out = []
+    for col, op in accs:
+        v = _req(vals[col], f"value column {col}")
+        if op in (SUM, MIN, MAX):
+            out.append(v)
+            continue
+        o = torch.empty(v.numel(), dtype=torch.int64 if op == COUNT else v.dtype, device=v.device)
+        check(lib.mgb_row_partial(v.data_ptr(), dtype_code(v), int(op), o.data_ptr(), v.numel(), _stream()))
+        _count(1 if v.numel() else 0)
+        out.append(o)
+    return out
+
+
 def post_mean(s: torch.Tensor, c: torch.Tensor) -> torch.Tensor:
     lib = _lib.load()
     s, c = _req(s, "sum"), _req(c, "count", (torch.int64,))

@@ -344,3 +344,47 @@ def test_infinite_values_and_nan_partials_follow_the_reference(cuda_device):
     assert_frames_match(got, exp, sort_index=False)
     assert np.isposinf(got.loc[3, ("w", "sum")]) and np.isfinite(got.loc[2, ("v", "sum")])
     assert got.loc[2, ("v", "min")] == -np.inf and got.loc[2, ("v", "max")] == np.inf
+
+
+@pytest.mark.parametrize("n", [131_072, 1_048_577, 5_000_003])
+def test_pageable_columns_are_uploaded_through_the_pinned_staging_ring(cuda_device, n):
+    """uploads from pageable host memory (pandas blocks of a Mars chunk): same bytes on the device as the plain copy,
+    for float64 and int64, sizes that are not a multiple of the slab, several columns back to back (slab reuse)"""
+    import torch
+
+    from mars_b200 import device as D
+
+    rng = np.random.default_rng(n)
+    cols = [rng.random(n), rng.integers(-2 ** 62, 2 ** 62, n, dtype=np.int64), rng.normal(size=n)]
+    before = D.h2d_bytes
+    ts = [D._to_device(c, cuda_device) for c in cols]
+    torch.cuda.synchronize()
+    assert D.h2d_bytes - before == 3 * 8 * n
+    for t, c in zip(ts, cols):
+        assert t.dtype == (torch.float64 if c.dtype == np.float64 else torch.int64)
+        np.testing.assert_array_equal(t.cpu().numpy(), c)
+
+
+@pytest.mark.parametrize("method,sort", [("shuffle", False), ("tree", True), ("shuffle", True)])
+def test_nearly_distinct_chunks_hand_their_rows_on_as_partials(md, method, sort):
+    """chunks whose keys are ~all distinct: after the first chunk has shown it, the map stage does not group the
+    following chunks (the rows are their own partials, COUNT / SUMSQ written per row) -- the final frame is the
+    oracle's, NaN values, an all-NaN group and duplicate keys inside a chunk included"""
+    from mars_b200 import executors as E
+
+    rng = np.random.default_rng(17)
+    n, chunk = 600_000, 100_000
+    raw = pd.DataFrame({"key": rng.integers(0, 40_000_000, n), "v": rng.normal(3, 2, n), "w": rng.integers(-50, 50, n)})
+    raw.loc[rng.integers(0, n, 5000), "v"] = np.nan
+    raw.loc[[5, 250_007, 599_999], "key"] = 123_456_789          # one key in three chunks ...
+    raw.loc[[250_008, 250_009], "key"] = 123_456_789             # ... three times in one of them
+    raw.loc[[7, 100_007], ["key", "v"]] = [[-5, np.nan], [-5, np.nan]]   # a group without any value
+    raw["key"] = raw["key"].astype(np.int64)
+    funcs = ["sum", "mean", "count", "min", "max", "var"]
+    before = E.passthrough_chunks
+    sess = md.new_session(default=False)
+    got = md.DataFrame(raw, chunk_size=chunk).to_gpu().groupby("key", sort=sort).agg(funcs, method=method) \
+        .execute(session=sess).fetch(session=sess)
+    assert E.passthrough_chunks - before >= 4, "the chunks after the first were expected to skip the fold"
+    exp = orc.run_groupby_agg(raw, ["key"], funcs, chunk, method=method, sort=sort)
+    assert_frames_match(got, exp, sort_index=not sort)
