@@ -857,7 +857,31 @@ class DeviceResult:
         return f"DeviceResult(rows={len(self)}, columns={len(self.labels)})"
 
 
+_small_index_cache: Dict[Any, Any] = {}
+
+
 def _multi_index(arrays, names):
+    # tiny results (the tree branch: a handful of groups): the same key tuples come back step after step; a
+    # MultiIndex is immutable, so one that was built for exactly these keys and names is handed out again
+    n = len(arrays[0])
+    ck = None
+    if n <= 64:
+        try:
+            ck = (tuple(names), tuple(a.tobytes() for a in arrays))
+            hit = _small_index_cache.get(ck)
+            if hit is not None:
+                return hit
+        except TypeError:
+            ck = None
+    mi = _multi_index_build(arrays, names)
+    if ck is not None:
+        if len(_small_index_cache) > 256:
+            _small_index_cache.clear()
+        _small_index_cache[ck] = mi
+    return mi
+
+
+def _multi_index_build(arrays, names):
     """pd.MultiIndex.from_arrays without its per-level Categorical round trip (the keys are int64 arrays)"""
     try:
         levels, codes = [], []

@@ -7,6 +7,7 @@ the CPU: a non-CUDA tensor raises ``MarsGBError`` (no fallback path exists).
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -894,6 +895,18 @@ def to_host_counted(columns: Sequence[torch.Tensor], count_block: torch.Tensor, 
     return n, out
 
 
+# Result frames wrap the arrays that came off the device without a copy, so they keep the PINNED block alive for as long
+# as the user holds the frame.  That is the point for the usual (small to medium) result; a block above this many bytes
+# is copied into pageable memory instead, so that a multi-GB result does not page-lock that much host RAM indefinitely.
+PINNED_RESULT_MAX = int(os.environ.get("MGB_PINNED_RESULT_MAX", str(1 << 30)))
+
+
+def _unpin_large(arrays, host_block: torch.Tensor):
+    if host_block.numel() * host_block.element_size() <= PINNED_RESULT_MAX:
+        return arrays
+    return [a.copy() for a in arrays]
+
+
 def to_host(columns: Sequence[torch.Tensor]):
     """Device -> host read of several equally long 8-byte columns with one synchronisation: asynchronous
     copies into one pinned block, then a single stream sync.  Returns numpy arrays (copies)."""
@@ -909,7 +922,8 @@ def to_host(columns: Sequence[torch.Tensor]):
     torch.cuda.current_stream().synchronize()
     # the arrays are views of the pinned block (which they keep alive): no second pass over the result
     hn = host.numpy()
-    return [hn[j, :n].view(np.float64) if c.dtype == torch.float64 else hn[j, :n] for j, c in enumerate(columns)]
+    return _unpin_large([hn[j, :n].view(np.float64) if c.dtype == torch.float64 else hn[j, :n] for j, c in enumerate(columns)],
+                        host)
 
 
 def to_host_concat(parts: Sequence[Sequence[torch.Tensor]]):
@@ -933,8 +947,8 @@ def to_host_concat(parts: Sequence[Sequence[torch.Tensor]]):
         off += n
     torch.cuda.current_stream().synchronize()
     hn = host.numpy()
-    return [hn[j, :total].view(np.float64) if c.dtype == torch.float64 else hn[j, :total]
-            for j, c in enumerate(parts[0])]
+    out = [hn[j, :total].view(np.float64) if c.dtype == torch.float64 else hn[j, :total] for j, c in enumerate(parts[0])]
+    return _unpin_large(out, host)
 
 
 # ------------------------------------------------------------------------------------------------- post
