@@ -546,7 +546,9 @@ def main_ours(args):
                                                                "note": "same step from pageable pandas chunks (what a Mars chunk store hands over)"}},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "k_preagg_dense" if "preagg_dense" in prof else "k_preagg_hash/k_preagg_smem",
+                         "traffic": traffic,
+                         "kernel": ("k_preagg_tiny (<= 4 groups per CTA in registers, TMA-staged tiles) + the immediate exit of "
+                                    "k_preagg_dense enqueued behind it" if "preagg_dense" in prof else "k_preagg_hash/k_preagg_smem"),
                          "kernel_ms_per_launch": per_launch_ms, "bytes_per_launch": rows_per_launch * BYTES_PER_ROW,
                          "launches": dom["launches"],
                          "frac_on_traffic": None if not traffic_per_row else achieved * traffic_per_row / BYTES_PER_ROW / peak,

@@ -221,6 +221,9 @@ int mgb_merge_small_async(const mgb_agg_spec* spec, int32_t n_pieces, const int6
  * chunk_val_cols[i] are the column tables of chunk i (a count-only int64 column may be null, as above);
  * at most mgb_dense_batch_max() chunks per call; out_n_dev as for mgb_preagg_dense_async.               */
 int mgb_dense_batch_max(int32_t* out_chunks);
+/* kernels the last mgb_preagg_dense* call of this thread enqueued (0: nothing to do / not a dense shape; 2: the
+ * register-accumulator kernel for <= 4 groups per CTA went first, the dense kernel behind it) -- for launch accounting */
+int mgb_dense_last_launches(int32_t* out_launches);
 int mgb_preagg_dense_batch_async(const mgb_agg_spec* spec, int32_t n_chunks, const int64_t* chunk_rows,
                                  const int64_t* const* const* chunk_key_cols,
                                  const void* const* const* chunk_val_cols, int64_t* const* out_key_cols,

@@ -99,6 +99,7 @@ SIGNATURES = {
     "mgb_merge_small_async": (C.c_int, [C.POINTER(AggSpec), _i32, C.POINTER(_i64), _pp, C.POINTER(_pp), C.POINTER(_pp),
                                         _pp, _pp, _i64, _i32, _vp, _vp]),
     "mgb_dense_batch_max": (C.c_int, [C.POINTER(_i32)]),
+    "mgb_dense_last_launches": (C.c_int, [C.POINTER(_i32)]),
     "mgb_preagg_dense_batch_async": (C.c_int, [C.POINTER(AggSpec), _i32, C.POINTER(_i64), C.POINTER(_pp), C.POINTER(_pp),
                                                _pp, _pp, _i64, _vp, _vp]),
     "mgb_preagg_dense_batch_fused_async": (C.c_int, [C.POINTER(AggSpec), C.POINTER(RowProgram), _i32, C.POINTER(_i64),

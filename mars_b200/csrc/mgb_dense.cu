@@ -25,6 +25,10 @@ int mgb_dense_launch_1_256(const DenseParams&, const DenseBatch&, int, bool, int
 int mgb_dense_launch_1_512(const DenseParams&, const DenseBatch&, int, bool, int, size_t, cudaStream_t);
 int mgb_dense_launch_2_256(const DenseParams&, const DenseBatch&, int, bool, int, size_t, cudaStream_t);
 int mgb_dense_launch_2_512(const DenseParams&, const DenseBatch&, int, bool, int, size_t, cudaStream_t);
+// mgb_tiny.cu: <= 4 groups per CTA, accumulators in registers, TMA-staged tiles
+bool mgb_tiny_eligible(const DenseBatch& bt, int nk, int ncol);
+int mgb_tiny_launch(const DenseParams& dp, const DenseBatch& bt, int nk, int ncol, int grid, int* ticket_fail2, int* sticky,
+                    cudaStream_t st);
 
 // --------------------------------------------------------------------------------------------------
 // host side of the dense path
@@ -37,6 +41,13 @@ struct DenseScratch {   // per (device, stream) scratch, grown on demand, reused
   long long* out_n_host = nullptr;   // pinned
 };
 static thread_local DenseScratch g_ds[8];
+static thread_local int g_last_launches = 0;   // kernels enqueued by the last dense / batch call of this thread
+
+extern "C" int mgb_dense_last_launches(int32_t* out_launches) {
+  MGB_REQUIRE(out_launches, MGB_ERR_INVALID, "null pointer");
+  *out_launches = g_last_launches;
+  return MGB_OK;
+}
 
 static int dense_scratch(int dev, size_t stg_words, int grid, DenseScratch** out) {
   MGB_REQUIRE(dev >= 0 && dev < 8, MGB_ERR_UNSUPPORTED, "device ordinal %d", dev);
@@ -47,7 +58,8 @@ static int dense_scratch(int dev, size_t stg_words, int grid, DenseScratch** out
     s.stg_words = stg_words;
   }
   if (!s.ints) {
-    MGB_CUDA(cudaMalloc((void**)&s.ints, sizeof(int) * (1024 + 8)));
+    MGB_CUDA(cudaMalloc((void**)&s.ints, sizeof(int) * (1024 + 128)));   // ... | tiny: ticket, fail | per-spec sticky flags
+    MGB_CUDA(cudaMemset(s.ints, 0, sizeof(int) * (1024 + 128)));
     MGB_CUDA(cudaMalloc((void**)&s.out_n, sizeof(long long) * 2));
     MGB_CUDA(cudaMallocHost((void**)&s.out_n_host, sizeof(long long) * 2));
   }
@@ -78,6 +90,7 @@ static int dense_batch_impl(const mgb_agg_spec* spec, const mgb_row_program* pro
                             const int64_t* chunk_rows, const int64_t* const* const* chunk_key_cols,
                             const void* const* const* chunk_val_cols, int64_t* const* out_key_cols,
                             void* const* out_acc_cols, int64_t out_capacity, int64_t* out_n_dev, void* stream) {
+  g_last_launches = 0;
   MGB_REQUIRE(spec && chunk_rows && chunk_key_cols && chunk_val_cols && out_key_cols && out_acc_cols && out_n_dev,
               MGB_ERR_INVALID, "null pointer");
   cudaStream_t st = (cudaStream_t)stream;
@@ -253,9 +266,22 @@ static int dense_batch_impl(const mgb_agg_spec* spec, const mgb_row_program* pro
     MGB_CUDA(cudaMemset(dbg, 0, sizeof(long long) * (4 * grid + 8)));
     p.dbg = dbg;
   }
+  g_last_launches = 1;
   {
     MgbProfScope prof(MGB_K_PREAGG_TINY, st);
     int status;
+    // sum / mean / count shapes: first the kernel that keeps <= 4 groups per CTA in registers and stages its tiles by
+    // TMA (mgb_tiny.cu); the dense kernel is enqueued right behind it and exits at once unless that one gave up
+    static const char* env_tiny = getenv("MGB_TINY");
+    if (plain && !prog && GC >= 4 && (!env_tiny || atoi(env_tiny) != 0) && mgb_tiny_eligible(bt, nk, ncol)) {
+      uint32_t h = (uint32_t)(nk * 131 + ncol * 31 + na);
+      for (int a = 0; a < na; ++a) h = h * 16777619u ^ (uint32_t)(spec->acc_col[a] * 8 + spec->acc_op[a]);
+      int* tf = s->ints + 1026;
+      MGB_CUDA(cudaMemsetAsync(tf, 0, 2 * sizeof(int), st));
+      MGB_TRY(mgb_tiny_launch(p, bt, nk, ncol, grid, tf, s->ints + 1032 + (int)(h % 64u), st));
+      p.run_if = tf + 1;
+      g_last_launches = 2;
+    }
     if (nk == 1)
       status = threads == 512 ? mgb_dense_launch_1_512(p, bt, ncol, plain, grid, smem, st)
                               : mgb_dense_launch_1_256(p, bt, ncol, plain, grid, smem, st);

@@ -180,6 +180,8 @@ struct DenseParams {
   uint8_t out_col[MGB_MAX_ACCS];   // loaded column of spec accumulator a, 0xFF: "rows of the group"
   uint8_t out_src[MGB_MAX_ACCS];   // mgb_op the staged value comes from
   long long* out_n;                // device: number of groups, -1 on failure
+  const int* run_if;               // optional: the kernel exits at once unless *run_if != 0 (set by k_preagg_tiny when it
+                                   // gave up on the band, mgb_tiny.cu)
   long long* dbg;                  // optional [grid][4] phase timestamps (ns), profiling experiments only
 };
 
@@ -295,6 +297,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_preagg_dense(const DenseParams p
   constexpr int DN_THREADS = THREADS;
   constexpr bool ALLOPS = !PLAIN;
   extern __shared__ __align__(16) uint32_t dsm[];
+  if (p.run_if && *(volatile const int*)p.run_if == 0) return;   // the register-accumulator kernel took the band
   // layout: acc[warp][GC][stride_g] | tkeys[NK][TAB] (u64) | gkeys[NK][MAX_GC] (u64) | tgid[TAB] | ints
   const int GC = p.GC;
   uint32_t* acc = dsm;

@@ -582,7 +582,10 @@ def preagg_dense_batch_async(chunks, accs: Sequence[Tuple[int, int]], val_dtypes
     res = _preagg_batch("mgb_preagg_dense_batch_async", _dense_cap, chunks, accs, val_dtypes, n_keys, device)
     if res is None:
         return None
-    _count(1 if res[3] else 0)
+    if res[3]:
+        n = C.c_int32()
+        check(_lib.load().mgb_dense_last_launches(C.byref(n)))
+        _count(n.value)     # 2 when the register-accumulator kernel (mgb_tiny.cu) went first, the dense one behind it
     return res[:3]
 
 

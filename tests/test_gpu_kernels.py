@@ -547,7 +547,7 @@ def test_dense_batch_streams_all_chunks_in_one_launch(K, n_keys, sizes):
     accs = [(0, "sum"), (1, "sum"), (0, "count"), (1, "count"), (2, "count")]
     before = K.launch_counter
     got = _batch(K, ck, cv, accs, skip_cols=(2,))
-    assert K.launch_counter - before == (1 if sum(sizes) else 0)
+    assert K.launch_counter - before == (2 if sum(sizes) else 0)   # register-accumulator kernel + the dense one behind it
     n, gk, ga = got
     keys = [np.concatenate([c[j] for c in ck]) for j in range(n_keys)]
     vals = [np.concatenate([c[j] for c in cv]) for j in range(3)]
@@ -833,3 +833,43 @@ def test_host_buffer_entry_matches_pandas(K, n, card, block):
     np.testing.assert_array_equal(out_a[6][:m], exp["w_min"].to_numpy())
     np.testing.assert_array_equal(out_a[7][:m], exp["w_max"].to_numpy())
     np.testing.assert_array_equal(out_a[8][:m], exp["w_count"].to_numpy())
+
+
+@pytest.mark.parametrize("n_keys,ncol", [(1, 1), (2, 5), (1, 6), (2, 3)])
+@pytest.mark.parametrize("layout", ["mixed4", "sorted12", "sorted40", "five"])
+def test_register_accumulator_kernel_and_its_hand_over(K, n_keys, ncol, layout):
+    """sum / count shapes go first to the kernel that keeps <= 4 groups per CTA in registers (TMA-staged tiles,
+    mgb_tiny.cu); whatever it cannot take -- a fifth key tuple in one CTA, more than 16 tuples in total -- is done by
+    the dense kernel enqueued behind it, in the same call.  mixed4: 4 tuples everywhere; sorted12 / sorted40: every CTA
+    sees few tuples but the band has 12 / 40; five: a fifth tuple appears in the last rows of the last chunk"""
+    rng = np.random.default_rng(n_keys * 10 + ncol)
+    sizes = [300_000, 1, 70_001, 1024, 2048 + 17]
+    total = sum(sizes)
+    if layout == "mixed4":
+        key = rng.integers(0, 4, total, dtype=np.int64)
+    elif layout == "five":
+        key = rng.integers(0, 4, total, dtype=np.int64)
+        key[-3:] = 9
+    else:
+        groups = 12 if layout == "sorted12" else 40
+        key = np.sort(rng.integers(0, groups, total, dtype=np.int64)) * 1_000_003 - 7
+    keys_all = [key] + ([(key % 2) * (2 ** 40)] if n_keys == 2 else [])
+    vals_all = [rng.normal(100, 30, total) for _ in range(ncol)] + [rng.integers(1, 99, total, dtype=np.int64)]
+    vals_all[0][rng.random(total) < 0.05] = np.nan
+    ck, cv, pos = [], [], 0
+    for n in sizes:
+        ck.append([k[pos:pos + n] for k in keys_all])
+        cv.append([v[pos:pos + n] for v in vals_all])
+        pos += n
+    accs = [(c, "sum") for c in range(ncol)] + [(0, "count")] + ([(ncol - 1, "count")] if ncol > 1 else []) + [(ncol, "count")]
+    n, gk, ga = _batch(K, ck, cv, accs, skip_cols=(ncol,))
+    ek, ea = pandas_agg(keys_all, vals_all, accs)
+    assert n == len(ek[0])
+    order = np.lexsort(tuple(reversed(gk)))
+    for a, b in zip(gk, ek):
+        np.testing.assert_array_equal(a[order], b)
+    for (col, op), a, b in zip(accs, ga, ea):
+        if op == "count":
+            np.testing.assert_array_equal(a[order], b)
+        else:
+            np.testing.assert_allclose(a[order], b, rtol=1e-9, atol=0)

@@ -317,7 +317,9 @@ def test_tree_branch_runs_as_one_batch_launch(md, method, func):
         assert_frames_match(got, exp, sort_index=False)
     got, launches, sess = results[True]
     assert sess.fused_trees == 1
-    assert launches == 2, launches     # one band-level batch (launched before tiling) + one agg-stage launch
+    # one band-level batch (launched before tiling; a sum / mean / count shape sends the register-accumulator kernel
+    # first and the dense kernel behind it) + one agg-stage launch
+    assert launches in (2, 3), launches
     assert results[False][2].fused_trees == 0 and results[False][1] > launches
     assert sess.executed_ops.count("DataFrameGroupByAgg:map") == 12
 

@@ -101,8 +101,9 @@ def run_record(name: str, rows: int, chunk_rows: int = None, repeats: int = 2, p
 
     lib = _lib.load()
     kernel_ms = None
-    for it in range(repeats + 2):
-        profiled = it == repeats + 1            # one extra, untimed run with per-kernel CUDA events
+    warm = 2        # untimed: the first run learns the shape (cardinality probe, first-chunk paths), the second grows the pools
+    for it in range(repeats + warm + 1):
+        profiled = it == repeats + warm         # one extra, untimed run with per-kernel CUDA events
         if profiled:
             lib.mgb_prof_enable(1)
             lib.mgb_prof_reset()
@@ -131,7 +132,7 @@ def run_record(name: str, rows: int, chunk_rows: int = None, repeats: int = 2, p
                 if cnt.value:
                     kernel_ms[nm] = {"ms_total": tot.value, "launches": cnt.value}
             lib.mgb_prof_enable(0)
-        elif it:
+        elif it >= warm:
             times.append(max(t1 - t0, e0.elapsed_time(e1) * 1e-3))
             fetch_times.append(t2 - t1)
             launches = kernels.launch_counter - l0
