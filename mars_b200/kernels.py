@@ -536,6 +536,9 @@ def dense_batch_max() -> int:
     return _batch_max
 
 
+_band_tables: dict = {}
+
+
 def _preagg_batch(entry: str, cap: int, chunks, accs, val_dtypes, n_keys: int, device):
     lib = _lib.load()
     nv, n = len(val_dtypes), len(chunks)
@@ -544,25 +547,36 @@ def _preagg_batch(entry: str, cap: int, chunks, accs, val_dtypes, n_keys: int, d
     if n > dense_batch_max():
         raise MarsGBError(1, f"{n} chunks in one batch (at most {dense_batch_max()})")
     fc = _fast(n_keys, val_dtypes, accs)
-    rows = (C.c_int64 * max(n, 1))()
-    kt = (_lib._pp * max(n, 1))()
-    vt = (_lib._pp * max(n, 1))()
-    keep = []
-    live = 0
-    for i, ent in enumerate(chunks):
-        kp, vp, m = ent[0], ent[1], ent[2]
-        if len(ent) > 3:                   # ctypes arrays built by an earlier call over the same resident chunk
-            karr, varr = ent[3]
-        else:
-            karr = (C.c_void_p * n_keys)(*kp)
-            varr = (C.c_void_p * max(nv, 1))(*vp)
-            if isinstance(ent, list):
-                ent.append((karr, varr))
-        keep.append((karr, varr))
-        kt[i] = C.cast(karr, _lib._pp)
-        vt[i] = C.cast(varr, _lib._pp)
-        rows[i] = int(m)
-        live += 1 if m else 0
+    # the chunk table of a band of RESIDENT chunks (cached entries, see executors._launch_band) is the same object list
+    # call after call: its ctypes form is kept (bounded), keyed on the identity of the entries it was built from
+    tkey = tuple(map(id, chunks)) if all(isinstance(e, list) and len(e) > 3 for e in chunks) else None
+    hit = _band_tables.get(tkey) if tkey is not None else None
+    if hit is not None and hit[0] == n_keys and hit[1] == nv:
+        _, _, rows, kt, vt, keep, live, _ = hit
+    else:
+        rows = (C.c_int64 * max(n, 1))()
+        kt = (_lib._pp * max(n, 1))()
+        vt = (_lib._pp * max(n, 1))()
+        keep = []
+        live = 0
+        for i, ent in enumerate(chunks):
+            kp, vp, m = ent[0], ent[1], ent[2]
+            if len(ent) > 3:                   # ctypes arrays built by an earlier call over the same resident chunk
+                karr, varr = ent[3]
+            else:
+                karr = (C.c_void_p * n_keys)(*kp)
+                varr = (C.c_void_p * max(nv, 1))(*vp)
+                if isinstance(ent, list):
+                    ent.append((karr, varr))
+            keep.append((karr, varr))
+            kt[i] = C.cast(karr, _lib._pp)
+            vt[i] = C.cast(varr, _lib._pp)
+            rows[i] = int(m)
+            live += 1 if m else 0
+        if tkey is not None:
+            if len(_band_tables) >= 16:
+                _band_tables.clear()
+            _band_tables[tkey] = (n_keys, nv, rows, kt, vt, keep, live, list(chunks))   # the entries stay alive: ids stay valid
     bi, bf = fc.alloc(cap, device)
     check(getattr(lib, entry)(C.byref(fc.spec), n, rows, kt, vt, fc.okp, fc.oap, cap, fc.count_ptr(bi), _stream()))
     return bi, bf, fc, live

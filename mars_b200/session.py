@@ -207,6 +207,14 @@ class Session:
             gc.collect()
             gc.freeze()
             _gc_frozen = True
+            # A graph leaves a few thousand short-lived, acyclic objects behind; with the default young-generation
+            # threshold (700 allocations) a collection runs right after every execute().  MGB_GC_THRESHOLD (default
+            # 50000, 0 = leave the interpreter's setting) raises it once.
+            thr = int(os.environ.get("MGB_GC_THRESHOLD", "50000"))
+            if thr > 0:
+                cur = gc.get_threshold()
+                if cur[0] and cur[0] < thr:
+                    gc.set_threshold(thr, cur[1], cur[2])
         was_enabled = gc.isenabled()
         gc.disable()
         try:
