@@ -171,6 +171,29 @@ def run(ex, cfg_name: str = "cfg3", rows_per_gpu: int = 125_000_000, chunk_rows:
                         "the receive arena of the GPU that reduces it (ranks lined up first); bytes = rows stored into "
                         "PEER arenas x row bytes; max over ranks" if getattr(t, "push_events", None) else
                         "CUDA events around the transport call (ranks lined up first); max over ranks")}
+    # one more step with per-kernel CUDA events (rank 0's kernels; untimed)
+    kernel_ms = None
+    try:
+        import ctypes as C
+
+        from mars_b200 import _lib
+
+        lib = _lib.load()
+        lib.mgb_prof_enable(1)
+        lib.mgb_prof_reset()
+        sess, r = step()
+        barrier()
+        del sess, r
+        kernel_ms = {}
+        for kid, nm in enumerate(["preagg_dense", "preagg_smem_or_mid", "merge", "update_global", "table_init", "emit", "hash",
+                                  "partition", "sort", "post_or_row_partial", "bucket"]):
+            tot, cnt = C.c_double(), C.c_int64()
+            lib.mgb_prof_read(kid, C.byref(tot), C.byref(cnt))
+            if cnt.value:
+                kernel_ms[nm] = {"ms_total": round(tot.value, 3), "launches": cnt.value}
+        lib.mgb_prof_enable(0)
+    except Exception as e:  # noqa: BLE001
+        kernel_ms = {"error": repr(e)[:200]}
     del frames
     torch.cuda.empty_cache()
     if rank != 0:
@@ -180,7 +203,7 @@ def run(ex, cfg_name: str = "cfg3", rows_per_gpu: int = 125_000_000, chunk_rows:
             "chunk_rows": chunk_rows, "chunks_per_gpu": chunks_per_gpu, "groups": int(groups),
             "value": total_rows / sec, "unit": "rows/s", "ms_per_step": sec * 1e3, "steps": steps, "warmup": warmup,
             "seconds": times, "sum_of_counts_eq_rows": bool(int(cnt_total) == total_rows),
-            "link": link, "parity": parity, "ops": ops,
+            "link": link, "parity": parity, "ops": ops, "kernel_time_ms_rank0": kernel_ms,
             "input": f"host numpy default_rng({bc.SEED} + chunk), uploaded before the timed region ({gen_s:.1f} s)",
             "what": "map (pre-aggregation per chunk) -> partition kernel writing into peer arenas -> reduce -> agg; result "
                     "chunks stay in HBM on the rank of their reducer"}
