@@ -706,8 +706,6 @@ class DataFrameGroupBy:
             method = "auto"
         if method not in ("shuffle", "tree", "auto"):
             raise ValueError(f"Method {method} is not available, please specify 'tree' or 'shuffle")
-        if not self.as_index:
-            raise NotImplementedError("as_index=False is applied on the host by the caller in this build")
         gpu = bool(self.df.op.gpu)
         op = DataFrameGroupByAgg(raw_func=func, raw_func_kw=kw, method=method,
                                  raw_groupby_params=self.groupby_params, groupby_params=self.groupby_params,

@@ -181,9 +181,7 @@ def test_large_result_chunks_stay_on_the_device_until_fetch(md, nkeys, sort):
     by = ["k1", "k2"][:nkeys] if nkeys > 1 else "k1"
     if nkeys == 1:
         raw = raw.drop(columns="k2")
-    # (no var: with 2-3 rows per group the reference's sum-of-squares formula cancels, its result then depends
-    # on the summation order beyond 1e-9 -- var parity is pinned on well-conditioned groups elsewhere)
-    func = ["sum", "mean", "count", "min", "max"]
+    func = ["sum", "mean", "count", "min", "max", "var"]
     got, sess, r = run(md, raw, by, func, 300_000, "shuffle", sort)
     kinds = {type(sess._results[c.key]) for c in r.data.chunks}
     assert kinds == {DeviceResult}, kinds
@@ -390,3 +388,21 @@ def test_nearly_distinct_chunks_hand_their_rows_on_as_partials(md, method, sort)
     assert E.passthrough_chunks - before >= 4, "the chunks after the first were expected to skip the fold"
     exp = orc.run_groupby_agg(raw, ["key"], funcs, chunk, method=method, sort=sort)
     assert_frames_match(got, exp, sort_index=not sort)
+
+
+@pytest.mark.parametrize("method,n_groups", [("tree", 40), ("shuffle", 40), ("shuffle", 30_000)])
+def test_as_index_false(md, method, n_groups):
+    """groupby(..., as_index=False): the keys come back as columns (aggregation.py:1259-1263), for small results
+    and for result chunks that stay on the device"""
+    rng = np.random.default_rng(5)
+    n = 200_000
+    raw = pd.DataFrame({"k": rng.integers(0, n_groups, n), "k2": rng.integers(0, 3, n), "v": rng.normal(1, 2, n),
+                        "w": rng.integers(0, 9, n)})
+    func = {"v": ["sum", "max"], "w": ["count", "mean"]}
+    sess = md.new_session(default=False)
+    got = md.DataFrame(raw, chunk_size=50_000).to_gpu().groupby(["k", "k2"], as_index=False).agg(func, method=method) \
+        .execute(session=sess).fetch(session=sess)
+    exp = raw.groupby(["k", "k2"], as_index=False).agg(func)
+    got = got.sort_values([("k", ""), ("k2", "")]).reset_index(drop=True)
+    assert list(got.columns) == list(exp.columns)
+    pd.testing.assert_frame_equal(got, exp.reset_index(drop=True), rtol=1e-9, atol=0, check_exact=False)

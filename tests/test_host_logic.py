@@ -372,3 +372,21 @@ def test_mid_cardinality_band_takes_the_mid_batch_kernel(md):
     got, sess = _run_tree(md, raw, "mkey", ["sum", "mean", "count"], 500, fuse=False)
     assert fake_kernels.calls.count("preagg_mid_batch_async") == 12 and "groupby_aggregate" not in fake_kernels.calls
     assert_frames_match(got, exp, sort_index=False)
+
+
+@pytest.mark.parametrize("method", ["tree", "shuffle"])
+@pytest.mark.parametrize("by", [["akey"], ["akey", "ak2"]])
+def test_as_index_false_returns_the_keys_as_columns(md, method, by):
+    """groupby(..., as_index=False).agg(...): same frame as pandas -- the keys are columns, a default RangeIndex
+    (reference: reset_index at the end of _execute_agg, aggregation.py:1259-1263)"""
+    rng = np.random.default_rng(12)
+    raw = pd.DataFrame({"akey": rng.integers(0, 50, 5000), "ak2": rng.integers(0, 3, 5000), "av": rng.random(5000),
+                        "aw": rng.integers(0, 9, 5000)})
+    func = {"av": ["sum", "max"], "aw": ["count"]}
+    sess = md.new_session(default=False)
+    got = md.DataFrame(raw, chunk_size=1200).to_gpu().groupby(by, as_index=False).agg(func, method=method) \
+        .execute(session=sess).fetch(session=sess)
+    exp = raw.groupby(by, as_index=False).agg(func)
+    got = got.sort_values([(b, "") for b in by]).reset_index(drop=True)
+    assert list(got.columns) == list(exp.columns)
+    pd.testing.assert_frame_equal(got, exp.reset_index(drop=True), rtol=1e-9, atol=0, check_exact=False)
