@@ -181,7 +181,10 @@ def test_large_result_chunks_stay_on_the_device_until_fetch(md, nkeys, sort):
     by = ["k1", "k2"][:nkeys] if nkeys > 1 else "k1"
     if nkeys == 1:
         raw = raw.drop(columns="k2")
-    func = ["sum", "mean", "count", "min", "max", "var"]
+    # (no var here: the expectation below is pandas' one-shot variance, and with 2-3 rows per group the reference's
+    # sum-of-squares formula (var.py:38-48) cancels differently -- var is compared with the ORACLE, which uses that
+    # formula, in the config-shaped tests and test_nearly_distinct_chunks_hand_their_rows_on_as_partials)
+    func = ["sum", "mean", "count", "min", "max"]
     got, sess, r = run(md, raw, by, func, 300_000, "shuffle", sort)
     kinds = {type(sess._results[c.key]) for c in r.data.chunks}
     assert kinds == {DeviceResult}, kinds
