@@ -220,6 +220,7 @@ __global__ void __launch_bounds__(HASH_THREADS, 1) k_preagg_hash(const HashParam
   constexpr long long TILE = (long long)HASH_THREADS * HASH_R;
   const long long nfull = n / TILE;
 
+  int hot_slot = -1;   // warp-uniform: the slot several lanes of this warp shared in an earlier row
   auto process_row = [&](const uint64_t* k, const uint64_t* x, long long row, bool live) {
     int slot = -1;
     if (live) {
@@ -261,11 +262,48 @@ __global__ void __launch_bounds__(HASH_THREADS, 1) k_preagg_hash(const HashParam
           }
         }
       }
-      if (slot >= 0) {
-        atomicAdd(&srows[slot], 1u);
+    }
+    // Warp pre-combine of a hot slot.  Shared-memory float64 adds are compare-and-swap loops; when several lanes of a
+    // warp hit the same slot (skewed keys: Zipf's first key is 18 % of BASELINE config 5) they serialise on it.  The
+    // rows of the slot most lanes share are therefore summed inside the warp -- __reduce_add_sync for the row count,
+    // shuffles for the float64 columns -- and cost ONE atomic per accumulator.  The candidate is the slot that was
+    // hot in the previous row of this warp, else the slot of the first lane that has one (re-elected until a hot one
+    // sticks); uniform keys pay three votes per row for it.
+    bool combined = false;
+    {
+      const unsigned have = __ballot_sync(0xffffffffu, slot >= 0);
+      if (have) {
+        int cand = hot_slot;
+        unsigned same = __ballot_sync(0xffffffffu, slot >= 0 && slot == cand);
+        if (__popc(same) < 3) {
+          cand = __shfl_sync(0xffffffffu, slot, __ffs(have) - 1);
+          same = __ballot_sync(0xffffffffu, slot >= 0 && slot == cand);
+        }
+        if (__popc(same) >= 3) {
+          hot_slot = cand;
+          const bool mem = (same >> lane) & 1u;
+          unsigned cnt = 0;
+          if (mem) cnt = __reduce_add_sync(same, 1u);
+          double v[NV];
 #pragma unroll
-        for (int c = 0; c < NV; ++c) atomicAdd(&ssum[(size_t)c * cap + slot], __longlong_as_double((long long)x[c]));
+          for (int c = 0; c < NV; ++c) {
+            v[c] = mem ? __longlong_as_double((long long)x[c]) : 0.0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v[c] += __shfl_xor_sync(0xffffffffu, v[c], o);
+          }
+          if (lane == __ffs(same) - 1) {
+            atomicAdd(&srows[cand], cnt);
+#pragma unroll
+            for (int c = 0; c < NV; ++c) atomicAdd(&ssum[(size_t)c * cap + cand], v[c]);
+          }
+          combined = mem;
+        }
       }
+    }
+    if (slot >= 0 && !combined) {
+      atomicAdd(&srows[slot], 1u);
+#pragma unroll
+      for (int c = 0; c < NV; ++c) atomicAdd(&ssum[(size_t)c * cap + slot], __longlong_as_double((long long)x[c]));
     }
     const bool miss = live && slot < 0;
     const unsigned mm = __ballot_sync(0xffffffffu, miss);
