@@ -9,6 +9,7 @@ the processor frees ctx entries (processor.py:276-282).
 """
 from __future__ import annotations
 
+import os
 import weakref
 from typing import Any, List, Optional, Sequence
 
@@ -70,9 +71,9 @@ class _StagingRing:
     engine moves the slabs already filled -- the H2D of one piece overlaps the host copy of the next ones, and the
     call returns as soon as the last piece is enqueued."""
 
-    SLAB_BYTES = 8 << 20
-    SLABS = 8
-    THREADS = 4
+    SLAB_BYTES = int(os.environ.get("MGB_STAGE_SLAB_MB", "8")) << 20
+    SLABS = int(os.environ.get("MGB_STAGE_SLABS", "8"))
+    THREADS = int(os.environ.get("MGB_STAGE_THREADS", "4"))
 
     def __init__(self):
         self.slabs = None
