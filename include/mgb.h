@@ -118,6 +118,9 @@ int mgb_hash_partition(const int64_t* const* key_cols, int32_t n_keys, int64_t n
  * blocks, mars/services/storage/transfer.py:63-206).
  *   mode 0: partition id = pandas hash of the key tuple, Index semantics (mgb_partition_ids) % n_partitions
  *   mode 1: DataFrame-row semantics (mgb_partition_ids_frame);  mode 2: ids given in `pid` (clamped to range)
+ *   mode | MGB_SPLIT_LONG_RUNS (all three calls alike): the destinations are peer GPUs -- 8192-row tiles (one CTA of
+ *                     1024 threads per SM) instead of 2048-row tiles, i.e. four times longer store runs, which is
+ *                     what NVLink wants (64 partitions: 453 -> 547 GB/s per GPU); also taken for >= 128 partitions
  *   mgb_split_tiles   number of row tiles T of a chunk; tile_hist is device scratch of n_partitions * T int64 that
  *                     must stay untouched between the two passes
  *   mgb_split_plan    pass 1: tile histograms, scanned; out_offsets[n_partitions + 1] on the device
@@ -126,7 +129,8 @@ int mgb_hash_partition(const int64_t* const* key_cols, int32_t n_keys, int64_t n
  *                     partition p in column c: out_cols[c] + out_offsets[p] + j when dst_table is NULL, else
  *                     (uint64_t*)dst_table[c * n_partitions + p] + j (device array of addresses; peer memory allowed;
  *                     16-byte aligned addresses get 16-byte stores).  Stable.  No host synchronisation.            */
-int mgb_split_tiles(int64_t n_rows, int64_t* out_tiles);
+#define MGB_SPLIT_LONG_RUNS 4
+int mgb_split_tiles(int64_t n_rows, int32_t n_partitions, int32_t mode, int64_t* out_tiles);
 int mgb_split_plan(const int64_t* const* key_cols, int32_t n_keys, int32_t mode, const int32_t* pid, int64_t n_rows,
                    int32_t n_partitions, int64_t* tile_hist, int64_t* out_offsets, void* stream);
 int mgb_split_scatter(const int64_t* const* key_cols, int32_t n_keys, int32_t mode, const int32_t* pid, int64_t n_rows,

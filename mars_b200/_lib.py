@@ -80,7 +80,7 @@ SIGNATURES = {
     "mgb_range_partition_ids": (C.c_int, [_pp, _i32, _i64, _pp, _i32, _vp, _vp]),
     "mgb_partition_scatter": (C.c_int, [_vp, _i64, _i32, _pp, _pp, _i32, _vp, _vp]),
     "mgb_hash_partition": (C.c_int, [_pp, _i32, _i64, _i32, _pp, _pp, _i32, _vp, _vp]),
-    "mgb_split_tiles": (C.c_int, [_i64, C.POINTER(_i64)]),
+    "mgb_split_tiles": (C.c_int, [_i64, _i32, _i32, C.POINTER(_i64)]),
     "mgb_split_plan": (C.c_int, [_pp, _i32, _i32, _vp, _i64, _i32, _vp, _vp, _vp]),
     "mgb_split_scatter": (C.c_int, [_pp, _i32, _i32, _vp, _i64, _i32, _vp, _pp, _i32, _pp, _vp, _vp]),
     "mgb_agg_create": (C.c_int, [C.POINTER(_vp), C.POINTER(AggSpec), _vp]),

@@ -20,6 +20,8 @@
 //
 // Stable: inside a partition rows keep their input order (the ascending positions f_i of the reference).
 // No host synchronisation; 1 <= R <= 256 (more partitions: the radix passes of mgb_partition.cu).
+#include <stdlib.h>
+
 #include "mgb_split.cuh"
 
 struct SplitSrc {
@@ -54,26 +56,26 @@ __device__ __forceinline__ uint32_t sp_pid(const SplitSrc& s, int64_t i, bool po
 }
 
 // counting needs no order: one shared-memory atomic per row (the stable ranks are pass 2's business)
-template <int NK, int MODE>
-__global__ void __launch_bounds__(SP_THREADS) k_split_hist(SplitSrc s, int64_t n, int64_t ntiles, int R,
-                                                           int64_t* __restrict__ hist, int32_t* bad) {
+template <int NK, int MODE, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_split_hist(SplitSrc s, int64_t n, int64_t ntiles, int R,
+                                                        int64_t* __restrict__ hist, int32_t* bad) {
   __shared__ uint32_t cnt[SP_MAX_R];
   if (threadIdx.x < SP_MAX_R) cnt[threadIdx.x] = 0;
   __syncthreads();
   const bool pow2 = (s.R & (s.R - 1)) == 0;
   const int64_t tile = blockIdx.x;
-  const int64_t base = tile * SP_TILE + threadIdx.x;
+  const int64_t base = tile * (THREADS * SP_ROUNDS) + threadIdx.x;
   uint32_t dg[SP_ROUNDS];
 #pragma unroll
   for (int r = 0; r < SP_ROUNDS; ++r) {   // all key loads of the thread in flight together
-    const int64_t i = base + r * SP_THREADS;
+    const int64_t i = base + r * THREADS;
     dg[r] = i < n ? sp_pid<NK, MODE>(s, i, pow2, bad) : 0xffffffffu;
   }
 #pragma unroll
   for (int r = 0; r < SP_ROUNDS; ++r)
     if (dg[r] != 0xffffffffu) atomicAdd(&cnt[dg[r]], 1u);
   __syncthreads();
-  for (int p = threadIdx.x; p < R; p += SP_THREADS) hist[(int64_t)p * ntiles + tile] = cnt[p];
+  for (int p = threadIdx.x; p < R; p += THREADS) hist[(int64_t)p * ntiles + tile] = cnt[p];
 }
 
 // block boundaries out of the scanned histogram
@@ -104,16 +106,37 @@ struct ShuffleTile {
   }
 };
 
-template <int NK, int MODE>
-__global__ void __launch_bounds__(SP_THREADS, 3) k_split_scatter(const SplitSrc s, const SplitCols cols, int64_t n,
-                                                                 int64_t ntiles, int R, const int64_t* __restrict__ hist,
-                                                                 const uint64_t* __restrict__ dst_tab) {
+// THREADS = 256, NBUF = 2: 2048-row tiles, three CTAs per SM (the default).  THREADS = 1024, NBUF = 1: 8192-row tiles, one
+// CTA per SM -- the runs a tile leaves are four times longer, which is what stores that cross NVLink want at many
+// partitions (tools/push_microbench.py: 256-byte runs 455 GB/s, 2 KB runs 614 GB/s per GPU)
+template <int NK, int MODE, int THREADS, int NBUF>
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 3 : 1)
+    k_split_scatter(const SplitSrc s, const SplitCols cols, int64_t n, int64_t ntiles, int R,
+                    const int64_t* __restrict__ hist, const uint64_t* __restrict__ dst_tab) {
   extern __shared__ __align__(128) unsigned char sp_raw[];
-  SplitSmem& sm = *reinterpret_cast<SplitSmem*>(sp_raw);
-  const int64_t tile = blockIdx.x, tbase = tile * SP_TILE;
-  const int nt = (int)((n - tbase) < SP_TILE ? (n - tbase) : SP_TILE);
+  SplitSmemT<THREADS, NBUF>& sm = *reinterpret_cast<SplitSmemT<THREADS, NBUF>*>(sp_raw);
+  constexpr int TILE = THREADS * SP_ROUNDS;
+  const int64_t tile = blockIdx.x, tbase = tile * TILE;
+  const int nt = (int)((n - tbase) < TILE ? (n - tbase) : TILE);
   ShuffleTile<NK, MODE> f{s, cols, hist, dst_tab, ntiles, tile, tbase, R, (s.R & (s.R - 1)) == 0};
-  sp_tile_split<true>(sm, nt, R, cols.n, f);
+  sp_tile_split_t<true, THREADS, NBUF>(sm, nt, R, cols.n, f);
+}
+
+// tile geometry of a split: big tiles when the rows go to many partitions (both passes must agree, so the rule
+// depends on nothing but the partition count and the chunk's length)
+#define SP_BIG_THREADS 1024
+// long_runs (mode bit 2, MGB_SPLIT_LONG_RUNS): the caller's destinations are peer GPUs.  Measured at N = 4
+// (tools/push_microbench.py, per GPU out): R = 8: 614 -> 628 GB/s, R = 64: 453 -> 547, R = 256: 238 -> 427.  Local
+// destinations: R = 64 is 6 % slower with big tiles (one CTA per SM), R = 256 9 % faster.
+static bool split_big(int64_t n_rows, int32_t R, bool long_runs) {
+  static const char* env = getenv("MGB_SPLIT_BIG");   // experiments: 0 = never, 1 = always
+  if (env && *env == '0') return false;
+  if (env && *env == '1') return true;
+  if (n_rows < (1 << 18)) return false;                // short chunks: keep the grid wide
+  return long_runs || R >= 128;
+}
+static int64_t split_tile_rows(int64_t n_rows, int32_t R, bool long_runs) {
+  return (int64_t)(split_big(n_rows, R, long_runs) ? SP_BIG_THREADS : SP_THREADS) * SP_ROUNDS;
 }
 
 // ----------------------------------------------------------------------------------------------------
@@ -142,33 +165,38 @@ static SplitSrc split_src(const int64_t* const* key_cols, int32_t n_keys, int32_
   return s;
 }
 
-#define SP_DISPATCH(KERNEL, ...)                                     \
+#define SP_DISPATCH(KERNEL, GEO, ...)                                \
   do {                                                               \
     if (mode == 2) {                                                 \
-      KERNEL<1, 2> __VA_ARGS__;                                      \
+      KERNEL<1, 2, GEO> __VA_ARGS__;                                 \
     } else if (mode == 1) {                                          \
       if (n_keys == 1) {                                             \
-        KERNEL<1, 1> __VA_ARGS__;                                    \
+        KERNEL<1, 1, GEO> __VA_ARGS__;                               \
       } else {                                                       \
-        KERNEL<2, 1> __VA_ARGS__;                                    \
+        KERNEL<2, 1, GEO> __VA_ARGS__;                               \
       }                                                              \
     } else {                                                         \
       if (n_keys == 1) {                                             \
-        KERNEL<1, 0> __VA_ARGS__;                                    \
+        KERNEL<1, 0, GEO> __VA_ARGS__;                               \
       } else {                                                       \
-        KERNEL<2, 0> __VA_ARGS__;                                    \
+        KERNEL<2, 0, GEO> __VA_ARGS__;                               \
       }                                                              \
     }                                                                \
   } while (0)
+#define SP_GEO_SMALL SP_THREADS, 2
+#define SP_GEO_BIG SP_BIG_THREADS, 1
 
-extern "C" int mgb_split_tiles(int64_t n_rows, int64_t* out_tiles) {
-  MGB_REQUIRE(out_tiles && n_rows >= 0, MGB_ERR_INVALID, "bad argument");
-  *out_tiles = (n_rows + SP_TILE - 1) / SP_TILE;
+extern "C" int mgb_split_tiles(int64_t n_rows, int32_t n_partitions, int32_t mode, int64_t* out_tiles) {
+  MGB_REQUIRE(out_tiles && n_rows >= 0 && n_partitions >= 1, MGB_ERR_INVALID, "bad argument");
+  const int64_t t = split_tile_rows(n_rows, n_partitions, (mode & MGB_SPLIT_LONG_RUNS) != 0);
+  *out_tiles = (n_rows + t - 1) / t;
   return MGB_OK;
 }
 
 int mgb_split_plan_ex(const int64_t* const* key_cols, int32_t n_keys, int32_t mode, const int32_t* pid, int64_t n_rows,
                       int32_t R, int64_t* tile_hist, int64_t* out_offsets, int32_t* bad, cudaStream_t st) {
+  const bool long_runs = (mode & MGB_SPLIT_LONG_RUNS) != 0;
+  mode &= 3;
   MGB_TRY(split_check(key_cols, n_keys, mode, pid, n_rows, R));
   MGB_REQUIRE(out_offsets, MGB_ERR_INVALID, "null out_offsets");
   if (n_rows == 0) {
@@ -176,9 +204,13 @@ int mgb_split_plan_ex(const int64_t* const* key_cols, int32_t n_keys, int32_t mo
     return MGB_OK;
   }
   MGB_REQUIRE(tile_hist, MGB_ERR_INVALID, "null tile histogram");
-  const int64_t ntiles = (n_rows + SP_TILE - 1) / SP_TILE;
+  const int64_t trows = split_tile_rows(n_rows, R, long_runs);
+  const int64_t ntiles = (n_rows + trows - 1) / trows;
   SplitSrc s = split_src(key_cols, n_keys, mode, pid, R);
-  SP_DISPATCH(k_split_hist, <<<(unsigned)ntiles, SP_THREADS, 0, st>>>(s, n_rows, ntiles, R, tile_hist, bad));
+  if (split_big(n_rows, R, long_runs))
+    SP_DISPATCH(k_split_hist, SP_BIG_THREADS, <<<(unsigned)ntiles, SP_BIG_THREADS, 0, st>>>(s, n_rows, ntiles, R, tile_hist, bad));
+  else
+    SP_DISPATCH(k_split_hist, SP_THREADS, <<<(unsigned)ntiles, SP_THREADS, 0, st>>>(s, n_rows, ntiles, R, tile_hist, bad));
   MGB_CHECK_LAUNCH();
   MGB_TRY(mgb_scan_exclusive_i64(tile_hist, (int64_t)R * ntiles, nullptr, st));
   k_split_offsets<<<1, 288, 0, st>>>(tile_hist, ntiles, R, n_rows, out_offsets);
@@ -190,7 +222,7 @@ extern "C" int mgb_split_plan(const int64_t* const* key_cols, int32_t n_keys, in
                               int64_t n_rows, int32_t n_partitions, int64_t* tile_hist, int64_t* out_offsets,
                               void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  MGB_REQUIRE(mode != 2, MGB_ERR_UNSUPPORTED, "given partition ids are range-checked by mgb_partition_scatter");
+  MGB_REQUIRE((mode & 3) != 2, MGB_ERR_UNSUPPORTED, "given partition ids are range-checked by mgb_partition_scatter");
   MgbProfScope prof(MGB_K_HASH, st);
   return mgb_split_plan_ex(key_cols, n_keys, mode, pid, n_rows, n_partitions, tile_hist, out_offsets, nullptr, st);
 }
@@ -198,6 +230,8 @@ extern "C" int mgb_split_plan(const int64_t* const* key_cols, int32_t n_keys, in
 int mgb_split_scatter_ex(const int64_t* const* key_cols, int32_t n_keys, int32_t mode, const int32_t* pid,
                          int64_t n_rows, int32_t R, const int64_t* tile_hist, const void* const* in_cols, int32_t n_cols,
                          void* const* out_cols, const uint64_t* dst_table, cudaStream_t st) {
+  const bool long_runs = (mode & MGB_SPLIT_LONG_RUNS) != 0;
+  mode &= 3;
   MGB_TRY(split_check(key_cols, n_keys, mode, pid, n_rows, R));
   MGB_REQUIRE(n_cols >= 0, MGB_ERR_INVALID, "negative column count");
   if (n_rows == 0 || n_cols == 0) return MGB_OK;
@@ -205,10 +239,13 @@ int mgb_split_scatter_ex(const int64_t* const* key_cols, int32_t n_keys, int32_t
   static bool attr_set[8] = {false};
   int dev = 0;
   MGB_CUDA(cudaGetDevice(&dev));
-  const size_t smem = sizeof(SplitSmem);
+  const size_t smem_small = sizeof(SplitSmemT<SP_THREADS, 2>), smem_big = sizeof(SplitSmemT<SP_BIG_THREADS, 1>);
   if (dev >= 0 && dev < 8 && !attr_set[dev]) {
-#define SP_ATTR(NK, MODE) \
-  MGB_CUDA(cudaFuncSetAttribute(k_split_scatter<NK, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))
+#define SP_ATTR(NK, MODE)                                                                                            \
+  MGB_CUDA(cudaFuncSetAttribute(k_split_scatter<NK, MODE, SP_GEO_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                (int)smem_small));                                                                   \
+  MGB_CUDA(cudaFuncSetAttribute(k_split_scatter<NK, MODE, SP_GEO_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                (int)smem_big))
     SP_ATTR(1, 0);
     SP_ATTR(2, 0);
     SP_ATTR(1, 1);
@@ -217,7 +254,9 @@ int mgb_split_scatter_ex(const int64_t* const* key_cols, int32_t n_keys, int32_t
 #undef SP_ATTR
     attr_set[dev] = true;
   }
-  const int64_t ntiles = (n_rows + SP_TILE - 1) / SP_TILE;
+  const bool big = split_big(n_rows, R, long_runs);
+  const int64_t trows = split_tile_rows(n_rows, R, long_runs);
+  const int64_t ntiles = (n_rows + trows - 1) / trows;
   SplitSrc s = split_src(key_cols, n_keys, mode, pid, R);
   for (int c0 = 0; c0 < n_cols; c0 += SP_MAX_COLS) {
     SplitCols sc;
@@ -227,7 +266,10 @@ int mgb_split_scatter_ex(const int64_t* const* key_cols, int32_t n_keys, int32_t
       sc.out[c] = out_cols ? (uint64_t*)out_cols[c0 + c] : nullptr;
     }
     const uint64_t* tab = dst_table ? dst_table + (size_t)c0 * R : nullptr;
-    SP_DISPATCH(k_split_scatter, <<<(unsigned)ntiles, SP_THREADS, smem, st>>>(s, sc, n_rows, ntiles, R, tile_hist, tab));
+    if (big)
+      SP_DISPATCH(k_split_scatter, SP_GEO_BIG, <<<(unsigned)ntiles, SP_BIG_THREADS, smem_big, st>>>(s, sc, n_rows, ntiles, R, tile_hist, tab));
+    else
+      SP_DISPATCH(k_split_scatter, SP_GEO_SMALL, <<<(unsigned)ntiles, SP_THREADS, smem_small, st>>>(s, sc, n_rows, ntiles, R, tile_hist, tab));
     MGB_CHECK_LAUNCH();
   }
   return MGB_OK;
@@ -248,12 +290,13 @@ extern "C" int mgb_split_scatter(const int64_t* const* key_cols, int32_t n_keys,
 int mgb_split_local(const int64_t* const* key_cols, int32_t n_keys, int32_t mode, const int32_t* pid, int64_t n_rows,
                     int32_t R, const void* const* in_cols, void* const* out_cols, int32_t n_cols, int64_t* out_offsets,
                     int32_t* bad, cudaStream_t st) {
-  MGB_TRY(split_check(key_cols, n_keys, mode, pid, n_rows, R));
+  MGB_TRY(split_check(key_cols, n_keys, mode & 3, pid, n_rows, R));
   if (n_rows == 0) {
     MGB_CUDA(cudaMemsetAsync(out_offsets, 0, sizeof(int64_t) * ((size_t)R + 1), st));
     return MGB_OK;
   }
-  const int64_t ntiles = (n_rows + SP_TILE - 1) / SP_TILE;
+  const int64_t trows = split_tile_rows(n_rows, R, (mode & MGB_SPLIT_LONG_RUNS) != 0);
+  const int64_t ntiles = (n_rows + trows - 1) / trows;
   int64_t* hist = nullptr;
   MGB_CUDA(cudaMallocAsync((void**)&hist, sizeof(int64_t) * (size_t)R * ntiles, st));
   int status;

@@ -58,19 +58,27 @@ __device__ __forceinline__ void sp_st64(uint64_t addr, uint64_t v) {
   asm volatile("st.global.u64 [%0], %1;" ::"l"(addr), "l"(v) : "memory");
 }
 
-struct SplitSmem {
-  alignas(128) uint64_t a[2][SP_TILE];     // column tiles as they lie in memory (TMA destinations)
-  alignas(16) uint64_t b[SP_SLOTS + 2];    // the same rows in partition order, runs padded to destination parity
+// THREADS threads split a tile of 8 * THREADS rows; NBUF = 2: the next column's tile is in flight while this one is
+// handled (256 threads, 2048 rows, 3 CTAs per SM); NBUF = 1: one staging tile, refilled while the previous column is
+// written out (1024 threads, 8192 rows, 1 CTA per SM: four times longer runs for stores that cross NVLink)
+template <int THREADS, int NBUF>
+struct SplitSmemT {
+  static constexpr int TILE = THREADS * SP_ROUNDS;
+  static constexpr int WARPS = THREADS / 32;
+  static constexpr int SLOTS = TILE + SP_MAX_R + 2;
+  alignas(128) uint64_t a[NBUF][TILE];     // column tiles as they lie in memory (TMA destinations)
+  alignas(16) uint64_t b[SLOTS + 2];       // the same rows in partition order, runs padded to destination parity
   alignas(8) uint64_t colbase[SP_MAX_R];   // address of slot 0's row if slot 0 belonged to partition p (this column)
   int64_t gof[SP_MAX_R];                   // first output row of this tile in partition p
   uint64_t bar[2];
   int32_t rsm[SP_MAX_R];                   // first slot of partition p's run
-  uint16_t wc[SP_WARPS][SP_MAX_R];         // rows of partition p in the warps before this one
-  alignas(4) uint16_t spart[SP_SLOTS + 2]; // partition of the row in slot s (SP_PAD: no row)
+  uint16_t wc[WARPS][SP_MAX_R];            // rows of partition p in the warps before this one
+  alignas(4) uint16_t spart[SLOTS + 2];    // partition of the row in slot s (SP_PAD: no row)
   int32_t cnt32[SP_MAX_R];                 // unordered ranking: rows of digit d seen so far
-  int32_t wsum[SP_WARPS];
+  int32_t wsum[WARPS];
   int32_t nslots;
 };
+using SplitSmem = SplitSmemT<SP_THREADS, 2>;
 
 // F supplies the tile:
 //   uint32_t        digit(int j)        digit of row j (j < nt)
@@ -81,8 +89,10 @@ struct SplitSmem {
 // blocks promise).  Otherwise the rank of a row is the return value of one shared-memory atomic -- MATCH.ANY costs a
 // round per DISTINCT digit in the warp, which at 128-256 ways is most of a tile's time -- and only the order of the
 // rows inside a run is unspecified (the bucket split: the fold of a bucket does not depend on it).
-template <bool STABLE, class F>
-__device__ __forceinline__ void sp_tile_split(SplitSmem& sm, const int nt, const int R, const int ncols, F& f) {
+template <bool STABLE, int THREADS, int NBUF, class F>
+__device__ __forceinline__ void sp_tile_split_t(SplitSmemT<THREADS, NBUF>& sm, const int nt, const int R, const int ncols,
+                                                F& f) {
+  constexpr int WARPS = THREADS / 32, TILE = THREADS * SP_ROUNDS, SLOTS = TILE + SP_MAX_R + 2;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t bulk_bytes = (uint32_t)(nt & ~1) * 8u;
   if (tid == 0) {
@@ -90,8 +100,8 @@ __device__ __forceinline__ void sp_tile_split(SplitSmem& sm, const int nt, const
     sp_mbar_init(&sm.bar[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = tid; i < SP_WARPS * SP_MAX_R; i += SP_THREADS) (&sm.wc[0][0])[i] = 0;
-  for (int i = tid; i < SP_SLOTS + 2; i += SP_THREADS) sm.spart[i] = (uint16_t)SP_PAD;
+  for (int i = tid; i < WARPS * SP_MAX_R; i += THREADS) (&sm.wc[0][0])[i] = 0;
+  for (int i = tid; i < SLOTS + 2; i += THREADS) sm.spart[i] = (uint16_t)SP_PAD;
   if (tid < SP_MAX_R) sm.cnt32[tid] = 0;
   __syncthreads();
   // a column tile is fetched by the TMA unit when its address is 16-byte aligned
@@ -101,7 +111,7 @@ __device__ __forceinline__ void sp_tile_split(SplitSmem& sm, const int nt, const
   const int64_t g_first = tid < R ? f.dest_row(tid) : 0;   // issued now: its latency overlaps the key loads of phase A
   // ---- A ---------------------------------------------------------------------------------------------------------
   const unsigned lt = mgb_lanemask_lt();
-  const int jbase = warp * (SP_TILE / SP_WARPS) + lane;
+  const int jbase = warp * (TILE / WARPS) + lane;
   uint32_t dr[SP_ROUNDS];   // digit | rank << 16, later the slot of the row
 #pragma unroll
   for (int r = 0; r < SP_ROUNDS; ++r) {   // all key loads of the thread in flight together
@@ -134,7 +144,7 @@ __device__ __forceinline__ void sp_tile_split(SplitSmem& sm, const int nt, const
     if (tid < R) {
       if (STABLE) {
 #pragma unroll
-        for (int w = 0; w < SP_WARPS; ++w) {
+        for (int w = 0; w < WARPS; ++w) {
           const int t = sm.wc[w][tid];
           sm.wc[w][tid] = (uint16_t)cnt;
           cnt += t;
@@ -155,7 +165,7 @@ __device__ __forceinline__ void sp_tile_split(SplitSmem& sm, const int nt, const
     __syncthreads();
     int add = 0;
 #pragma unroll
-    for (int w = 0; w < SP_WARPS; ++w)
+    for (int w = 0; w < WARPS; ++w)
       if (w < warp) add += sm.wsum[w];
     const int excl = add + inc - v;
     if (tid < R) {
@@ -163,7 +173,7 @@ __device__ __forceinline__ void sp_tile_split(SplitSmem& sm, const int nt, const
       sm.rsm[tid] = rs;
       sm.gof[tid] = g;
     }
-    if (tid == SP_THREADS - 1) sm.nslots = (add + inc + 2) & ~1;
+    if (tid == THREADS - 1) sm.nslots = (add + inc + 2) & ~1;
   }
   __syncthreads();
   // ---- C ---------------------------------------------------------------------------------------------------------
@@ -180,9 +190,10 @@ __device__ __forceinline__ void sp_tile_split(SplitSmem& sm, const int nt, const
   // ---- columns ---------------------------------------------------------------------------------------------------
   uint32_t uses0 = 0, uses1 = 0;
   for (int c = 0; c < ncols; ++c) {
-    const int buf = c & 1;
+    const int buf = NBUF == 2 ? (c & 1) : 0;
     if (tid < R) sm.colbase[tid] = f.dst(c, tid) + 8ull * (uint64_t)(sm.gof[tid] - (int64_t)sm.rsm[tid]);
-    if (tid == 0 && c + 1 < ncols && tma_ok(c + 1)) sp_bulk_load(sm.a[buf ^ 1], f.src(c + 1), bulk_bytes, &sm.bar[buf ^ 1]);
+    if (NBUF == 2 && tid == 0 && c + 1 < ncols && tma_ok(c + 1))
+      sp_bulk_load(sm.a[buf ^ (NBUF - 1)], f.src(c + 1), bulk_bytes, &sm.bar[buf ^ (NBUF - 1)]);
     const uint64_t* src = f.src(c);
     if (tma_ok(c)) {
       const uint32_t use = buf ? uses1++ : uses0++;
@@ -200,8 +211,10 @@ __device__ __forceinline__ void sp_tile_split(SplitSmem& sm, const int nt, const
       }
     }
     __syncthreads();
+    // one staging tile: it is free now -- the next column's tile arrives while this one is written out
+    if (NBUF == 1 && tid == 0 && c + 1 < ncols && tma_ok(c + 1)) sp_bulk_load(sm.a[0], f.src(c + 1), bulk_bytes, &sm.bar[0]);
     const int npairs = sm.nslots >> 1;
-    for (int q = tid; q < npairs; q += SP_THREADS) {
+    for (int q = tid; q < npairs; q += THREADS) {
       const uint32_t pp = *reinterpret_cast<const uint32_t*>(&sm.spart[2 * q]);
       const uint32_t p0 = pp & 0xffffu, p1 = pp >> 16;
       if (pp == 0xffffffffu) continue;
@@ -216,4 +229,10 @@ __device__ __forceinline__ void sp_tile_split(SplitSmem& sm, const int nt, const
     }
     __syncthreads();
   }
+}
+
+// the default geometry: 256 threads, 2048-row tiles, double-buffered staging
+template <bool STABLE, class F>
+__device__ __forceinline__ void sp_tile_split(SplitSmem& sm, const int nt, const int R, const int ncols, F& f) {
+  sp_tile_split_t<STABLE, SP_THREADS, 2>(sm, nt, R, ncols, f);
 }

@@ -1394,6 +1394,8 @@ class DeferredSplit:
     into the receive arena of the GPU that runs its reducer; ``emit`` is the single-process form (blocks of local
     columns under the reference's ctx keys, groupby/core.py:429-435)."""
 
+    MODE = 4      # kernels.SPLIT_LONG_RUNS: Index-hash semantics, 8192-row tiles
+
     def __init__(self, chunk, op, mapper_index, keys, cols, R, hist, offsets, spans, nk, is_tuple):
         self.chunk, self.op, self.mapper_index = chunk, op, mapper_index
         self.keys, self.cols, self.R, self.hist, self.offsets = keys, cols, R, hist, offsets
@@ -1416,7 +1418,7 @@ class DeferredSplit:
     def emit(self, ctx):
         """pass 2 into local columns"""
         outs = [torch.empty_like(c) for c in self.cols]
-        _kernels.split_scatter(self.keys, self.R, self.hist, self.cols, outs=outs)
+        _kernels.split_scatter(self.keys, self.R, self.hist, self.cols, outs=outs, mode=self.MODE)
         offsets = self.offsets.cpu().tolist()
         src = ColumnSet(outs)
         for r in range(self.R):
@@ -1456,7 +1458,8 @@ def _execute_shuffle_map(ctx, op):
             cols.extend(f.data)
             spans.append((i, f.index_names, f.columns, pos, pos + len(f.columns)))
             pos += len(f.columns)
-        hist, offsets = _kernels.split_plan(base.index, R)
+        # planned for stores that cross NVLink (long runs); emit() / the exchange scatter with the same mode
+        hist, offsets = _kernels.split_plan(base.index, R, DeferredSplit.MODE)
         ctx[chunk.key, "deferred"] = DeferredSplit(chunk, op, mapper_index, list(base.index), cols, R, hist, offsets,
                                                    spans, len(base.index), is_tuple)
         return

@@ -146,14 +146,18 @@ def hash_partition(keys: Sequence[torch.Tensor], n_partitions: int, cols: Sequen
     return outs, offsets.cpu().tolist()
 
 
+SPLIT_LONG_RUNS = 4     # mode bit: the rows will be stored into peer GPUs (8192-row tiles: longer runs over NVLink)
+
+
 def split_plan(keys: Sequence[torch.Tensor], n_partitions: int, mode: int = 0):
     """pass 1 of the partition kernel (mgb_split_plan): -> (tile_hist, offsets), both on the device; offsets holds
-    the n_partitions + 1 block boundaries.  No host wait."""
+    the n_partitions + 1 block boundaries.  No host wait.  ``mode``: 0 Index hash, 1 DataFrame-row hash, optionally
+    | SPLIT_LONG_RUNS -- the same mode must be given to split_scatter."""
     lib = _lib.load()
     keys = [_req(k, f"key {i}", (torch.int64,)) for i, k in enumerate(keys)]
     n = keys[0].numel()
     tiles = C.c_int64()
-    check(lib.mgb_split_tiles(n, C.byref(tiles)))
+    check(lib.mgb_split_tiles(n, int(n_partitions), int(mode), C.byref(tiles)))
     dev = keys[0].device
     hist = torch.empty(max(1, tiles.value * n_partitions), dtype=torch.int64, device=dev)
     offsets = torch.empty(n_partitions + 1, dtype=torch.int64, device=dev)

@@ -604,7 +604,7 @@ class Exchange:
             from . import executors      # the kernels module the executors are bound to
 
             for j, d in enumerate(splits):
-                executors._kernels.split_scatter(d.keys, R, d.hist, d.cols, table=dtab[j])
+                executors._kernels.split_scatter(d.keys, R, d.hist, d.cols, table=dtab[j], mode=d.MODE)
             t.timed_end(e0, sent * ncols * 8)
         else:
             t.timed_end(t.timed_begin(), 0)

@@ -406,7 +406,7 @@ poke = None
 
 def split_plan(keys, n_partitions, mode=0):
     calls.append("split_plan")
-    pid = (orc.hash_frame_rows([_np(k) for k in keys]) % np.uint64(n_partitions)).astype(np.int64) if mode == 1 \
+    pid = (orc.hash_frame_rows([_np(k) for k in keys]) % np.uint64(n_partitions)).astype(np.int64) if (mode & 3) == 1 \
         else orc.partition_ids([_np(k) for k in keys], n_partitions)
     counts = np.bincount(pid, minlength=n_partitions)
     offsets = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)

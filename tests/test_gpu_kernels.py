@@ -873,3 +873,21 @@ def test_register_accumulator_kernel_and_its_hand_over(K, n_keys, ncol, layout):
             np.testing.assert_array_equal(a[order], b)
         else:
             np.testing.assert_allclose(a[order], b, rtol=1e-9, atol=0)
+
+
+@pytest.mark.parametrize("n,R,nk", [(300_001, 8, 1), (1_000_003, 64, 2), (262_144, 3, 1), (100_000, 64, 1)])
+def test_split_with_long_runs_gives_the_same_blocks(K, n, R, nk):
+    """mode | SPLIT_LONG_RUNS (8192-row tiles, what the push shuffle asks for): same blocks, same order inside every
+    block as the default geometry; chunks below 2^18 rows keep the small tiles"""
+    rng = np.random.default_rng(n + R)
+    keys = [rng.integers(-10 ** 9, 10 ** 9, n, dtype=np.int64) for _ in range(nk)]
+    cols = keys + [rng.random(n), np.arange(n, dtype=np.int64)]
+    dk, dc = [dev(k) for k in keys], [dev(c) for c in cols]
+    pid = orc.partition_ids(keys, R)
+    order = np.argsort(pid, kind="stable")
+    hist, offsets = K.split_plan(dk, R, K.SPLIT_LONG_RUNS)
+    np.testing.assert_array_equal(offsets.cpu().numpy(), np.searchsorted(pid[order], np.arange(R + 1)))
+    outs = [torch.full_like(c, -1) for c in dc]
+    K.split_scatter(dk, R, hist, dc, outs=outs, mode=K.SPLIT_LONG_RUNS)
+    for got, src in zip(outs, cols):
+        np.testing.assert_array_equal(got.cpu().numpy(), src[order])

@@ -14,6 +14,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from mars_b200 import kernels as K, parallel  # noqa: E402
 
 rows = int(os.environ.get("ROWS", 15_625_000))
+LONG = K.SPLIT_LONG_RUNS if os.environ.get("LONG_RUNS", "1") != "0" else 0    # LONG_RUNS=0: 2048-row tiles
 ex = parallel.init_exchange("gloo")
 t = ex.transport
 rank, world = ex.rank, ex.world
@@ -25,7 +26,7 @@ for ncols, R, mode in ((3, 8, "ring"), (3, 64, "ring"), (3, 8, "all"), (3, 64, "
                        (3, 64, "local")):
     keys = [torch.randint(0, 1 << 40, (rows,), dtype=torch.int64, device=dev, generator=g)]
     cols = keys + [torch.rand(rows, dtype=torch.float64, device=dev, generator=g) for _ in range(ncols - 1)]
-    hist, offsets = K.split_plan(keys, R)
+    hist, offsets = K.split_plan(keys, R, LONG)
     off = offsets.cpu().numpy()
     cnt = off[1:] - off[:-1]
     pad = (cnt + 1) & ~1
@@ -49,7 +50,7 @@ for ncols, R, mode in ((3, 8, "ring"), (3, 64, "ring"), (3, 8, "all"), (3, 64, "
     remote = int(cnt[dest != rank].sum()) * ncols * 8
 
     def run():
-        K.split_scatter(keys, R, hist, cols, table=dtab)
+        K.split_scatter(keys, R, hist, cols, table=dtab, mode=LONG)
 
     for _ in range(3):
         run()
