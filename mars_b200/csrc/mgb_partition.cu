@@ -54,11 +54,8 @@ __global__ void k_radix_trivial(const int64_t* hist, int64_t ntiles, int64_t n, 
   if (threadIdx.x == 0) *flag = any ? 0 : 1;
 }
 
-// DEST = false: perm_out[output row] = input row (a permutation to gather by); DEST = true (single pass, no
-// indirection): perm_out[input row] = output row -- the destination every row is SCATTERED to.  Scattered
-// 8-byte writes of neighbouring output rows are combined in L2 (the runs of a partition advance tile by tile),
-// random 8-byte reads are not: each fetches a whole 32-byte sector from DRAM.
-template <bool DEST>
+// perm_out[output row] = input row: a permutation to gather by (more than 256 partitions, key argsort; the splits
+// of <= 256 ways move the rows themselves, mgb_split.cu)
 __global__ void __launch_bounds__(RP_THREADS) k_radix_scatter(DigitSrc s, int64_t n, int64_t ntiles,
                                                               const int64_t* hist, const int32_t* trivial,
                                                               int32_t* perm_out) {
@@ -105,10 +102,7 @@ __global__ void __launch_bounds__(RP_THREADS) k_radix_scatter(DigitSrc s, int64_
     }
     __syncthreads();
     if (valid) {
-      if (DEST)
-        perm_out[elem] = (int32_t)(wpos[warp][d] + lr);
-      else
-        perm_out[wpos[warp][d] + lr] = elem;
+      perm_out[wpos[warp][d] + lr] = elem;
     }
     // wc is re-zeroed at the top of the next round, after which a barrier follows: wpos reads above are
     // separated from the next round's wpos writes by that barrier and the one after the match.
@@ -126,7 +120,7 @@ static int radix_pass(const DigitSrc& s, int64_t n, int32_t* perm_out, int64_t* 
     k_radix_trivial<<<1, 256, 0, st>>>(hist, ntiles, n, trivial_flag);
     MGB_CHECK_LAUNCH();
   }
-  k_radix_scatter<false><<<(unsigned)ntiles, RP_THREADS, 0, st>>>(s, n, ntiles, hist, trivial_flag, perm_out);
+  k_radix_scatter<<<(unsigned)ntiles, RP_THREADS, 0, st>>>(s, n, ntiles, hist, trivial_flag, perm_out);
   MGB_CHECK_LAUNCH();
   return MGB_OK;
 }

@@ -1337,8 +1337,15 @@ def hash_split_frame(frame: DeviceFrame, on: Sequence[Any], n_partitions: int) -
     if n == 0:
         outs, offsets = cols, [0] * (n_partitions + 1)
     else:
-        pid = _kernels.partition_ids_frame(keys, n_partitions)
-        outs, offsets = _kernels.partition_scatter(pid, n_partitions, cols)
+        if n_partitions <= 256 and hasattr(_kernels, "split_plan"):
+            # the partition kernel with DataFrame-row hash semantics: no id array, no range-check synchronisation
+            hist, off_dev = _kernels.split_plan(keys, n_partitions, 1)
+            outs = [torch.empty_like(c) for c in cols]
+            _kernels.split_scatter(keys, n_partitions, hist, cols, outs=outs, mode=1)
+            offsets = off_dev.cpu().tolist()
+        else:
+            pid = _kernels.partition_ids_frame(keys, n_partitions)
+            outs, offsets = _kernels.partition_scatter(pid, n_partitions, cols)
     nk = len(index)
     src = ColumnSet(outs)
     return [DeviceFrame.from_range(names, frame.columns, src, 0, nk, nk, len(cols), offsets[r], offsets[r + 1])
