@@ -323,6 +323,13 @@ __global__ void __launch_bounds__(TH, 1280 / TH) k_bucket_agg(const BktParams p)
     if (tid == 0) p.gcount[b] = 0;
     return;
   }
+  if (hi - lo > BK_SKEW_ROWS) {   // one hot key: this bucket would serialise on one CTA -- the whole input is declined
+    if (tid == 0) {
+      p.gcount[b] = 0;
+      atomicMax(p.err, 2);
+    }
+    return;
+  }
   const long long T = p.T;
   const Layout& L = p.L;
   const int nk = L.nk, nv = L.nv;
@@ -360,7 +367,7 @@ __global__ void __launch_bounds__(TH, 1280 / TH) k_bucket_agg(const BktParams p)
     }
     __syncthreads();
     if (failed) {
-      if (tid == 0) atomicExch(p.err, 1);
+      if (tid == 0) atomicMax(p.err, 1);
       return;
     }
     const int ng = n_unique;
@@ -516,17 +523,6 @@ __global__ void __launch_bounds__(TH, 1280 / TH) k_bucket_agg(const BktParams p)
     __syncthreads();
   }
   if (tid == 0) p.gcount[b] = n_unique;
-}
-
-// longest bucket (skew check)
-__global__ void __launch_bounds__(256) k_bucket_max(const int64_t* __restrict__ off, int B, int* __restrict__ out) {
-  int m = 0;
-  for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (long long)gridDim.x * blockDim.x) {
-    const long long n = off[b + 1] - off[b];
-    m = max(m, (int)(n > 0x7fffffffLL ? 0x7fffffffLL : n));
-  }
-  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
 }
 
 struct BktEmitCols {
@@ -735,22 +731,8 @@ int mgb_bucket_aggregate(const Layout& L, const BktSource* srcs_host, int nsrc, 
         status = MGB_ERR_CUDA;
       }
     }
-    if (status == MGB_OK) {   // a hot key makes one bucket as long as its row count: leave that input to the table
-      const int gb = (B + 255) / 256;
-      k_bucket_max<<<gb > 1024 ? 1024 : gb, 256, 0, st>>>(out->off, B, d_err + 1);
-      int longest = 0;
-      cudaError_t e = cudaMemcpyAsync(&longest, d_err + 1, sizeof(int), cudaMemcpyDeviceToHost, st);
-      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-      if (e != cudaSuccess) {
-        mgb_set_error("bucket aggregation: %s", cudaGetErrorString(e));
-        status = MGB_ERR_CUDA;
-      } else if (longest > BK_SKEW_ROWS) {
-        release();
-        mgb_bucket_free(out, st);
-        *overflow = 2;
-        return MGB_OK;
-      }
-    }
+    // (a hot key makes one bucket as long as its row count: the CTA that meets such a bucket raises err = 2 and the
+    // input is left to the table -- checked with the group count below, no extra host synchronisation)
     // one CTA per bucket
     if (status == MGB_OK) {
       BktParams p;
@@ -809,7 +791,7 @@ int mgb_bucket_aggregate(const Layout& L, const BktSource* srcs_host, int nsrc, 
   release();
   if (status != MGB_OK || err_h) {
     mgb_bucket_free(out, st);
-    *overflow = err_h ? 1 : 0;
+    *overflow = err_h;      // 1 = a bucket held more groups than its table, 2 = a bucket far longer than the average
     return status;
   }
   out->G = (long long)G;

@@ -217,6 +217,7 @@ _PROBE_MIN_ROWS = 65536   # smaller chunks are not worth the cardinality probe
 # always group the chunk, like the reference's map stage)
 _PASSTHROUGH = os.environ.get("MGB_MAP_PASSTHROUGH", "1") not in ("0", "")
 passthrough_chunks = 0    # map operands that took that path (tests, bench records)
+_pt_streak: Dict[Any, int] = {}       # shape -> consecutive chunks that took the pass-through
 _group_ratio: Dict[Any, float] = {}   # shape -> groups / rows of the last chunk of that shape that was really grouped
 
 
@@ -394,8 +395,14 @@ def _execute_agg_map(ctx, op):
             # (aggregation.py:1130-1267) -- the rows ARE the partials.  (A sample cannot tell this regime from many
             # groups of a few rows each: 16 K sampled keys of a million groups are all distinct, too; the sample is
             # only the cheap check that this chunk still looks like the one that was measured.)
-            sampled, uniq = _kernels.estimate_distinct(keys)
-            passthrough = bool(sampled) and uniq * 10 >= sampled * 9
+            # ... sampled for the first chunks of a run and then every 8th one (a sample is a host wait)
+            streak = _pt_streak.get(plan.shape_key, 0)
+            if streak >= 2 and streak % 8:
+                passthrough = True
+            else:
+                sampled, uniq = _kernels.estimate_distinct(keys)
+                passthrough = bool(sampled) and uniq * 10 >= sampled * 9
+            _pt_streak[plan.shape_key] = streak + 1 if passthrough else 0
         if passthrough:
             global passthrough_chunks
             passthrough_chunks += 1
