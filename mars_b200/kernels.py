@@ -142,7 +142,7 @@ def hash_partition(keys: Sequence[torch.Tensor], n_partitions: int, cols: Sequen
     offsets = torch.empty(n_partitions + 1, dtype=torch.int64, device=keys[0].device)
     check(lib.mgb_hash_partition(_ptrs(keys), len(keys), n, int(n_partitions), _ptrs(cols), _ptrs(outs), len(cols),
                                  offsets.data_ptr(), _stream()))
-    _count(7 if n else 1)
+    _count(6 if n else 1)     # histogram, scan (3), offsets, scatter
     return outs, offsets.cpu().tolist()
 
 
