@@ -476,21 +476,35 @@ def main_ours(args):
     # N > 1: the hash-shuffle branch across the ranks (cfg3-shaped, weak scaling: 125 M rows per GPU = the config's
     # full size at 8 GPUs) -- whole-path rows/s, NVLink rate of the fused partition -> peer transfer, parity
     shuffle = None
+    shuffle_configs = {}
     if world > 1 and not args.no_shuffle:
         del host_frames
         torch.cuda.empty_cache()
         from mars_b200 import parallel
         import shuffle_leg
 
+        ex = None
         try:
             ex = parallel.init_exchange()
             shuffle = shuffle_leg.run(ex, "cfg3", rows_per_gpu=args.shuffle_rows, chunk_rows=15_625_000,
                                       steps=max(2, min(args.steps, 3)), warmup=2)
-            ex.transport.close()
         except Exception as e:  # noqa: BLE001
             import traceback
 
             shuffle = {"error": repr(e)[:300], "trace": traceback.format_exc()[-600:]}
+        # the other two shuffle-bound BASELINE configs at their per-GPU share of the full size (weak scaling: 8 GPUs
+        # hold the whole config): cfg4 62.5 M rows per GPU, cfg5 125 M rows per GPU
+        if ex is not None and not (shuffle or {}).get("error") and not args.no_shuffle_configs:
+            for name, rows_gpu, chunk in (("cfg4", 62_500_000, 7_812_500), ("cfg5", 125_000_000, 15_625_000)):
+                try:
+                    rec = shuffle_leg.run(ex, name, rows_per_gpu=min(rows_gpu, args.shuffle_rows), chunk_rows=chunk, steps=2,
+                                          warmup=2)
+                except Exception as e:  # noqa: BLE001
+                    rec = {"error": repr(e)[:300]}
+                if rank == 0:
+                    shuffle_configs[name] = rec
+        if ex is not None:
+            ex.transport.close()
         host_frames = []
     configs = None
     if rank == 0 and world == 1 and not args.no_configs:
@@ -568,6 +582,7 @@ def main_ours(args):
             "cpu_baseline": cpu_baseline,
             "configs": configs,
             "shuffle": shuffle,
+            "shuffle_configs": shuffle_configs or None,
         }
         print(json.dumps(line), flush=True)
     if comm is not None:
@@ -587,6 +602,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the sub-records of the other BASELINE.json configs")
     ap.add_argument("--no-shuffle", action="store_true", help="N > 1: skip the hash-shuffle leg")
+    ap.add_argument("--no-shuffle-configs", action="store_true", help="N > 1: only the cfg3 shuffle leg, not cfg4 / cfg5")
     ap.add_argument("--shuffle-rows", type=int, default=125_000_000, help="rows per GPU of the shuffle leg (cfg3-shaped)")
     ap.add_argument("--no-clocks", action="store_true", help="diagnostics: do not start the nvidia-smi clock sampler")
     args = ap.parse_args()

@@ -18,3 +18,6 @@ for k, v in (d.get("configs") or {}).items():
 if d.get("shuffle"):
     s = d["shuffle"]
     print("shuffle", {k: s.get(k) for k in ("value", "ms_per_step", "rows", "groups", "sum_of_counts_eq_rows", "error")}, s.get("link"), s.get("parity"))
+for k, v in (d.get("shuffle_configs") or {}).items():
+    print("shuffle", k, {a: v.get(a) for a in ("value", "ms_per_step", "rows", "groups", "sum_of_counts_eq_rows", "error")},
+          (v.get("link") or {}).get("GBps_per_gpu_per_direction"), (v.get("parity") or {}).get("ok"), v.get("kernel_time_ms_rank0"))

@@ -25,7 +25,7 @@ import baseline_configs as bc  # noqa: E402
 NVLINK_NOMINAL_GBPS = 900.0      # per GPU per direction (NVLink 5)
 
 
-def _frames(cfg, rank, world, chunks_per_gpu, chunk_rows, dev):
+def _frames(cfg, rank, world, chunks_per_gpu, chunk_rows, dev, keep_host=True):
     import torch
 
     from mars_b200.device import DeviceFrame
@@ -36,7 +36,8 @@ def _frames(cfg, rank, world, chunks_per_gpu, chunk_rows, dev):
     for c in range(chunks_per_gpu * world):
         if c % world == rank:
             data = cfg.gen(c, chunk_rows)
-            host[c] = data
+            if keep_host:
+                host[c] = data
             ts = [torch.from_numpy(data[k]).to(dev) for k in cols]
             frames.append(DeviceFrame([], None, cols, ts, chunk_rows))
         else:       # same schema, never executed on this rank
@@ -115,7 +116,7 @@ def run(ex, cfg_name: str = "cfg3", rows_per_gpu: int = 125_000_000, chunk_rows:
     chunks_per_gpu = max(1, rows_per_gpu // chunk_rows)
     rows_rank = chunks_per_gpu * chunk_rows
     t0 = time.perf_counter()
-    frames, _ = _frames(cfg, rank, world, chunks_per_gpu, chunk_rows, dev)
+    frames, _ = _frames(cfg, rank, world, chunks_per_gpu, chunk_rows, dev, keep_host=False)
     gen_s = time.perf_counter() - t0
     total_rows = rows_rank * world
 
@@ -137,15 +138,21 @@ def run(ex, cfg_name: str = "cfg3", rows_per_gpu: int = 125_000_000, chunk_rows:
             times.append(allmax(time.perf_counter() - t0))
     groups = allsum(sum(len(v) for v in sess._results.values()))
     # invariant at full size: the counts of all groups add up to the number of rows
-    cnt_total = 0
+    # (configs without a count column -- cfg4: min / max / var -- have no such invariant: None)
+    cnt_total, has_count = 0, False
     for v in sess._results.values():
         labels = getattr(v, "labels", None)      # executors.DeviceResult: result chunk resident in HBM
         if labels is not None:
-            col = next(c for lab, c in zip(labels, v.columns) if isinstance(lab, tuple) and lab[-1] == "count")
-            cnt_total += int(col.sum().item())
+            col = next((c for lab, c in zip(labels, v.columns) if isinstance(lab, tuple) and lab[-1] == "count"), None)
+            if col is not None:
+                has_count = True
+                cnt_total += int(col.sum().item())
         else:                                    # small result chunk handed back as pandas
-            lab = next(lab for lab in v.columns if isinstance(lab, tuple) and lab[-1] == "count")
-            cnt_total += int(v[lab].sum())
+            lab = next((lab for lab in v.columns if isinstance(lab, tuple) and lab[-1] == "count"), None)
+            if lab is not None:
+                has_count = True
+                cnt_total += int(v[lab].sum())
+    has_count = allsum(1 if has_count else 0) > 0
     cnt_total = allsum(cnt_total)
     ops = sorted(set(sess.executed_ops))
     del sess, r
@@ -202,7 +209,7 @@ def run(ex, cfg_name: str = "cfg3", rows_per_gpu: int = 125_000_000, chunk_rows:
     return {"config": cfg_name, "transport": type(t).__name__, "n_gpus": world, "rows": total_rows, "rows_per_gpu": rows_rank,
             "chunk_rows": chunk_rows, "chunks_per_gpu": chunks_per_gpu, "groups": int(groups),
             "value": total_rows / sec, "unit": "rows/s", "ms_per_step": sec * 1e3, "steps": steps, "warmup": warmup,
-            "seconds": times, "sum_of_counts_eq_rows": bool(int(cnt_total) == total_rows),
+            "seconds": times, "sum_of_counts_eq_rows": bool(int(cnt_total) == total_rows) if has_count else None,
             "link": link, "parity": parity, "ops": ops, "kernel_time_ms_rank0": kernel_ms,
             "input": f"host numpy default_rng({bc.SEED} + chunk), uploaded before the timed region ({gen_s:.1f} s)",
             "what": "map (pre-aggregation per chunk) -> partition kernel writing into peer arenas -> reduce -> agg; result "
