@@ -23,11 +23,12 @@
 //   scan + k_bucket_emit   compaction of the per-bucket results into the caller's columns
 //
 // (Round 1 moved row IDS into bucket order and gathered the rows at random from a row-major copy: 99 B of DRAM
-// traffic per 16-byte row.)  The splits are stable, so the fold order -- and with it every float64 sum -- is the
-// same from run to run.
+// traffic per 16-byte row.)  Inside a bucket the rows arrive in no particular order (the split ranks them with one
+// shared-memory atomic per row): the fold does not depend on it beyond the rounding of the compensated float64 sums.
 //
-// A bucket that holds more groups than its table reports overflow, a bucket far longer than the average (one
-// hot key) is declined before the aggregation kernel runs; the caller then takes the hash-table path.
+// A bucket that holds more groups than its table, or one far longer than the average (one hot key: it would
+// serialise on one CTA), makes the fold kernel raise its error word; the host reads it together with the group count
+// and the caller takes the hash-table path.
 #include <stdlib.h>
 
 #include <vector>
@@ -643,7 +644,7 @@ int mgb_bucket_aggregate(const Layout& L, const BktSource* srcs_host, int nsrc, 
   const size_t tab_bytes = sizeof(long long) * ((size_t)nsrc + 1);
   const size_t src_pad = (src_bytes + 255) & ~(size_t)255, tab_pad = (tab_bytes + 255) & ~(size_t)255;
   const size_t plan_bytes = (sizeof(long long) * (2 * (size_t)P1 + 2) + sizeof(int32_t) * (size_t)(NT2 + 1) + 255) & ~(size_t)255;
-  char* small = nullptr;     // srcs | row_begin | tile_begin | err, longest bucket | po | cnt | tile_part
+  char* small = nullptr;     // srcs | row_begin | tile_begin | err | po | cnt | tile_part
   uint64_t *stageA = nullptr, *stageB = nullptr;
   int64_t *hist1 = nullptr, *hist2 = nullptr;
   MGB_CUDA(cudaMallocAsync((void**)&small, src_pad + 2 * tab_pad + 256 + plan_bytes, st));
