@@ -158,14 +158,17 @@ def _worker(rank, world, port, case, q):
             funcs = ["sum", "mean", "count", "min", "max", "var"]
             exp = raw.groupby(["key", "k2"]).agg(funcs)
             ok = True
-            for rep in range(3):
+            seen_ops = set()
+            for rep in range(4):
                 sess = md.new_session(exchange=ex, default=False)
-                r = md.DataFrame(raw, chunk_size=500 if rep < 2 else 1300).to_gpu().groupby(["key", "k2"], sort=False) \
+                # rep 3: ONE chunk -- rank 1 owns neither a mapper nor a reducer and learns the schema from rank 0
+                r = md.DataFrame(raw, chunk_size=(500, 500, 1300, 5000)[rep]).to_gpu().groupby(["key", "k2"], sort=False) \
                     .agg(funcs, method="shuffle")
                 r.execute(session=sess)
                 got = sess.fetch(r)
                 ok = ok and _close(got.sort_index(), exp)
-            q.put((rank, ok, ex.shuffle_rows_sent, sorted(set(sess.executed_ops)), tr.pushes,
+                seen_ops.update(sess.executed_ops)
+            q.put((rank, ok, ex.shuffle_rows_sent, sorted(seen_ops), tr.pushes,
                    fake_kernels.calls.count("split_scatter")))
         elif case == "psrs":   # sort=True shuffle: samples -> pivots -> range shuffle across ranks
             ex = parallel.Exchange(GlooTransport(rank, world), rank, world)
@@ -226,7 +229,7 @@ def test_push_shuffle_across_two_ranks():
     out = _run("push", 29644)
     for rank, ok, rows_sent, ops, pushes, scatters in out:
         assert ok, f"rank {rank}: result differs from pandas"
-        assert rows_sent > 0 and pushes == 3 and scatters > 0
+        assert rows_sent > 0 and pushes == 4 and scatters > 0
         assert "DataFrameGroupByOperand:map" in ops and "DataFrameGroupByOperand:reduce" in ops
 
 
