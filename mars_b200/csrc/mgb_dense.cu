@@ -26,7 +26,7 @@ int mgb_dense_launch_1_512(const DenseParams&, const DenseBatch&, int, bool, int
 int mgb_dense_launch_2_256(const DenseParams&, const DenseBatch&, int, bool, int, size_t, cudaStream_t);
 int mgb_dense_launch_2_512(const DenseParams&, const DenseBatch&, int, bool, int, size_t, cudaStream_t);
 // mgb_tiny.cu: <= 4 groups per CTA, accumulators in registers, TMA-staged tiles
-bool mgb_tiny_eligible(const DenseBatch& bt, int nk, int ncol);
+bool mgb_tiny_eligible(const DenseBatch& bt, int nk, int ncol, int n_load);
 int mgb_tiny_launch(const DenseParams& dp, const DenseBatch& bt, int nk, int ncol, int grid, int* ticket_fail2, int* sticky,
                     cudaStream_t st);
 
@@ -273,8 +273,9 @@ static int dense_batch_impl(const mgb_agg_spec* spec, const mgb_row_program* pro
     // sum / mean / count shapes: first the kernel that keeps <= 4 groups per CTA in registers and stages its tiles by
     // TMA (mgb_tiny.cu); the dense kernel is enqueued right behind it and exits at once unless that one gave up
     static const char* env_tiny = getenv("MGB_TINY");
-    if (plain && !prog && GC >= 4 && (!env_tiny || atoi(env_tiny) != 0) && mgb_tiny_eligible(bt, nk, ncol)) {
-      uint32_t h = (uint32_t)(nk * 131 + ncol * 31 + na);
+    if (plain && GC >= 4 && (!env_tiny || atoi(env_tiny) != 0) &&
+        mgb_tiny_eligible(bt, nk, ncol, prog ? prog->n_phys : ncol)) {
+      uint32_t h = (uint32_t)(nk * 131 + ncol * 31 + na + (prog ? 7919 : 0));
       for (int a = 0; a < na; ++a) h = h * 16777619u ^ (uint32_t)(spec->acc_col[a] * 8 + spec->acc_op[a]);
       int* tf = s->ints + 1026;
       MGB_CUDA(cudaMemsetAsync(tf, 0, 2 * sizeof(int), st));

@@ -32,6 +32,7 @@
 #define TN_MAX_TOTAL 16
 
 struct TinyParams {
+  DenseProgram prog;        // PROG instantiations: row filter + derived columns (TPC-H Q1 pre-path), as in k_preagg_dense
   uint64_t* stg;            // [grid][TN_G][NK + 1 + 2 NV]: keys | rows | sums | NaN counts
   int* cta_ng;              // [grid]
   unsigned int* ticket;
@@ -63,7 +64,10 @@ __device__ __forceinline__ void tn_locate(const DenseBatch& bt, long long v, int
   row0 = (v - (q ? bt.tile_end[q - 1] : 0)) * TN_TILE;
 }
 
-template <int NK, int NV>
+// PROG: the tile holds the n_phys PHYSICAL columns of the row program; the NV logical columns a row contributes are
+// computed from them in registers (products of affine factors, each operation rounded on its own like the chain of
+// pandas operators it replaces), rows the filter rejects take no part in anything
+template <int NK, int NV, bool PROG>
 __global__ void __launch_bounds__(TN_THREADS, 1) k_preagg_tiny(const TinyParams p, const DenseBatch bt) {
   extern __shared__ __align__(128) unsigned char tn_raw[];
   TinySmem<NK, NV>& sm = *reinterpret_cast<TinySmem<NK, NV>*>(tn_raw);
@@ -90,6 +94,7 @@ __global__ void __launch_bounds__(TN_THREADS, 1) k_preagg_tiny(const TinyParams 
   if (tid < TN_G * NV) (&sm.nan[0][0])[tid] = 0;
   __syncthreads();
   const long long total_tiles = bt.tile_end[bt.n_chunks - 1];
+  const int n_load = PROG ? p.prog.n_phys : NV;      // value columns a tile carries
 
   double sum[TN_G][NV];
   uint32_t rows[TN_G];
@@ -155,6 +160,51 @@ __global__ void __launch_bounds__(TN_THREADS, 1) k_preagg_tiny(const TinyParams 
       }
     }
   };
+  // row program: physical values in x[] -> logical values in x[]; returns whether the row passes the filter
+  auto apply_program = [&](uint64_t* x) -> bool {
+    double ph[NV];
+#pragma unroll
+    for (int c = 0; c < NV; ++c) ph[c] = __longlong_as_double((long long)x[c]);
+    bool keep = true;
+    if (p.prog.filter_col >= 0) {
+      uint64_t raw = 0;
+#pragma unroll
+      for (int c = 0; c < NV; ++c)
+        if (p.prog.filter_col == c) raw = x[c];
+      int cmp;   // NaN compares as "unordered": every comparison but != fails, like pandas
+      bool unordered = false;
+      if (p.prog.filter_f64) {
+        const double v = __longlong_as_double((long long)raw);
+        unordered = v != v;
+        cmp = v < p.prog.filter_d ? -1 : (v > p.prog.filter_d ? 1 : 0);
+      } else {
+        const long long v = (long long)raw;
+        cmp = v < p.prog.filter_i ? -1 : (v > p.prog.filter_i ? 1 : 0);
+      }
+      const int op = p.prog.filter_op;
+      keep = op == 0 ? cmp <= 0 : op == 1 ? cmp < 0 : op == 2 ? cmp >= 0 : op == 3 ? cmp > 0 : op == 4 ? cmp == 0 : cmp != 0;
+      if (unordered) keep = op == 5;
+    }
+#pragma unroll
+    for (int c = 0; c < NV; ++c) {
+      const int nf = p.prog.nf[c];
+      if (nf == 0) continue;            // logical column c == physical column c
+      double v = 1.0;
+#pragma unroll
+      for (int f = 0; f < 3; ++f) {
+        if (f < nf) {
+          double o = 0.0;
+#pragma unroll
+          for (int j = 0; j < NV; ++j)
+            if (p.prog.fcol[c][f] == j) o = ph[j];
+          const double term = __dadd_rn(p.prog.falpha[c][f], __dmul_rn(p.prog.fbeta[c][f], o));
+          v = f == 0 ? term : __dmul_rn(v, term);
+        }
+      }
+      x[c] = (uint64_t)__double_as_longlong(v);
+    }
+    return keep;
+  };
   // warp-collective: lanes with live && gid < 0 hold key tuples the CTA does not know yet
   auto slow = [&](bool live, int gid, const uint64_t* k) {
     unsigned need = __ballot_sync(0xffffffffu, live && gid < 0);
@@ -208,10 +258,11 @@ __global__ void __launch_bounds__(TN_THREADS, 1) k_preagg_tiny(const TinyParams 
       tn_locate(bt, v, pq, row0);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sp_smem(&sm.full[s])),
-                   "r"((uint32_t)((NK + NV) * TN_TILE * 8))
+                   "r"((uint32_t)((NK + n_load) * TN_TILE * 8))
                    : "memory");
 #pragma unroll
       for (int c = 0; c < NK + NV; ++c) {
+        if (c >= NK + n_load) break;
         const uint64_t* src = bt.ptr[pq][c < NK ? c : MGB_MAX_KEYS + (c - NK)] + row0;
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                          sp_smem(&sm.tile[s][c][0])),
@@ -244,7 +295,8 @@ __global__ void __launch_bounds__(TN_THREADS, 1) k_preagg_tiny(const TinyParams 
         if (NK == 1) k[0][1] = k[1][1] = 0;
 #pragma unroll
         for (int c = 0; c < NV; ++c) {
-          const ulonglong2 t2 = reinterpret_cast<const ulonglong2*>(&sm.tile[s][NK + c][0])[tid];
+          ulonglong2 t2 = make_ulonglong2(0, 0);
+          if (c < n_load) t2 = reinterpret_cast<const ulonglong2*>(&sm.tile[s][NK + c][0])[tid];
           x[0][c] = t2.x;
           x[1][c] = t2.y;
         }
@@ -253,9 +305,10 @@ __global__ void __launch_bounds__(TN_THREADS, 1) k_preagg_tiny(const TinyParams 
       if (lane == 0) tn_mbar_arrive(&sm.empty[s]);   // the tile is in registers: the stage may be refilled
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
-        gid[r] = take_row(k[r]);
-        if (__any_sync(0xffffffffu, gid[r] < 0)) gid[r] = slow(true, gid[r], k[r]);
-        update(gid[r], x[r]);
+        const bool live = PROG ? apply_program(x[r]) : true;
+        gid[r] = live ? take_row(k[r]) : -4;
+        if (__any_sync(0xffffffffu, live && gid[r] < 0)) gid[r] = slow(live, gid[r], k[r]);
+        if (live) update(gid[r], x[r]);
       }
     }
     // remainders of the chunks (< 1024 rows each): chunk q by CTA q % grid, plain loads
@@ -263,7 +316,7 @@ __global__ void __launch_bounds__(TN_THREADS, 1) k_preagg_tiny(const TinyParams 
       const long long n = bt.n[q], r0 = (n / TN_TILE) * TN_TILE;
       for (long long j0 = r0; j0 < n; j0 += TN_CONSUMERS) {   // uniform trip count per warp: slow() is collective
         const long long j = j0 + tid;
-        const bool live = j < n;
+        bool live = j < n;
         uint64_t k[2] = {0, 0}, x[NV];
 #pragma unroll
         for (int c = 0; c < NV; ++c) x[c] = 0;
@@ -271,7 +324,9 @@ __global__ void __launch_bounds__(TN_THREADS, 1) k_preagg_tiny(const TinyParams 
 #pragma unroll
           for (int qq = 0; qq < NK; ++qq) k[qq] = mgb_ld_stream(bt.ptr[q][qq] + j);
 #pragma unroll
-          for (int c = 0; c < NV; ++c) x[c] = mgb_ld_stream(bt.ptr[q][MGB_MAX_KEYS + c] + j);
+          for (int c = 0; c < NV; ++c)
+            if (c < n_load) x[c] = mgb_ld_stream(bt.ptr[q][MGB_MAX_KEYS + c] + j);
+          if (PROG) live = apply_program(x);
         }
         refresh();
         int gid = live ? take_row(k) : -4;
@@ -410,28 +465,29 @@ __global__ void __launch_bounds__(TN_THREADS, 1) k_preagg_tiny(const TinyParams 
   if (tid == 0) *p.out_n = G;
 }
 
-template <int NK, int NV>
+template <int NK, int NV, bool PROG>
 static int tiny_launch(const TinyParams& p, const DenseBatch& bt, int grid, cudaStream_t st) {
   static bool attr_set[8] = {false};
   int dev = 0;
   MGB_CUDA(cudaGetDevice(&dev));
   const size_t smem = sizeof(TinySmem<NK, NV>);
   if (!attr_set[dev & 7]) {
-    MGB_CUDA(cudaFuncSetAttribute(k_preagg_tiny<NK, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MGB_CUDA(cudaFuncSetAttribute(k_preagg_tiny<NK, NV, PROG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set[dev & 7] = true;
   }
-  k_preagg_tiny<NK, NV><<<grid, TN_THREADS, smem, st>>>(p, bt);
+  k_preagg_tiny<NK, NV, PROG><<<grid, TN_THREADS, smem, st>>>(p, bt);
   MGB_CHECK_LAUNCH();
   return MGB_OK;
 }
 
-// eligible: sum / count shapes over <= 6 float64 columns, every column 16-byte aligned (bulk copies)
-bool mgb_tiny_eligible(const DenseBatch& bt, int nk, int ncol) {
-  if (ncol < 1 || ncol > 6) return false;
+// eligible: sum / count shapes over <= 6 float64 (logical) columns, every loaded column 16-byte aligned (bulk copies);
+// n_load: the columns a tile carries (== ncol, or the physical columns of a row program)
+bool mgb_tiny_eligible(const DenseBatch& bt, int nk, int ncol, int n_load) {
+  if (ncol < 1 || ncol > 6 || n_load < 1 || n_load > ncol) return false;
   for (int q = 0; q < bt.n_chunks; ++q) {
     for (int j = 0; j < nk; ++j)
       if ((uintptr_t)bt.ptr[q][j] & 15) return false;
-    for (int c = 0; c < ncol; ++c)
+    for (int c = 0; c < n_load; ++c)
       if ((uintptr_t)bt.ptr[q][MGB_MAX_KEYS + c] & 15) return false;
   }
   return true;
@@ -450,18 +506,25 @@ int mgb_tiny_launch(const DenseParams& dp, const DenseBatch& bt, int nk, int nco
   memcpy(p.out_col, dp.out_col, sizeof(p.out_col));
   memcpy(p.out_src, dp.out_src, sizeof(p.out_src));
   p.out_n = dp.out_n;
-#define TN_PICK(NK_)                                          \
-  switch (ncol) {                                             \
-    case 1: return tiny_launch<NK_, 1>(p, bt, grid, st);      \
-    case 2: return tiny_launch<NK_, 2>(p, bt, grid, st);      \
-    case 3: return tiny_launch<NK_, 3>(p, bt, grid, st);      \
-    case 4: return tiny_launch<NK_, 4>(p, bt, grid, st);      \
-    case 5: return tiny_launch<NK_, 5>(p, bt, grid, st);      \
-    default: return tiny_launch<NK_, 6>(p, bt, grid, st);     \
+  p.prog = dp.prog;
+#define TN_PICK(NK_, PROG_)                                          \
+  switch (ncol) {                                                    \
+    case 1: return tiny_launch<NK_, 1, PROG_>(p, bt, grid, st);      \
+    case 2: return tiny_launch<NK_, 2, PROG_>(p, bt, grid, st);      \
+    case 3: return tiny_launch<NK_, 3, PROG_>(p, bt, grid, st);      \
+    case 4: return tiny_launch<NK_, 4, PROG_>(p, bt, grid, st);      \
+    case 5: return tiny_launch<NK_, 5, PROG_>(p, bt, grid, st);      \
+    default: return tiny_launch<NK_, 6, PROG_>(p, bt, grid, st);     \
+  }
+  if (dp.prog.n_phys > 0) {
+    if (nk == 1) {
+      TN_PICK(1, true)
+    }
+    TN_PICK(2, true)
   }
   if (nk == 1) {
-    TN_PICK(1)
+    TN_PICK(1, false)
   }
-  TN_PICK(2)
+  TN_PICK(2, false)
 #undef TN_PICK
 }

@@ -654,7 +654,10 @@ def preagg_dense_batch_fused_async(chunks, accs, val_dtypes, n_keys: int, device
     bi, bf = fc.alloc(_dense_cap, device)
     check(lib.mgb_preagg_dense_batch_fused_async(C.byref(fc.spec), C.byref(prog), n, rows, kt, vt, fc.okp, fc.oap,
                                                  _dense_cap, fc.count_ptr(bi), _stream()))
-    _count(1 if any(m for _, _, m in chunks) else 0)
+    if any(m for _, _, m in chunks):
+        nl = C.c_int32()
+        check(lib.mgb_dense_last_launches(C.byref(nl)))
+        _count(nl.value)
     return bi, bf, fc
 
 
