@@ -428,3 +428,20 @@ def split_scatter(keys, n_partitions, hist, cols, outs=None, table=None, mode=0)
             blk = src[bounds[p_]:bounds[p_ + 1]]
             if len(blk):
                 poke(int(tab[c, p_]), blk.view(np.int64))
+
+
+def row_partials(vals, accs):
+    """per-row partials of a chunk with ~distinct keys (mgb_row_partial): SUM / MIN / MAX alias the column"""
+    calls.append("row_partials")
+    out = []
+    for col, op in accs:
+        v = vals[col]
+        if op in (_K.SUM, _K.MIN, _K.MAX):
+            out.append(v)
+        elif op == _K.COUNT:
+            a = _np(v)
+            out.append(torch.from_numpy((~np.isnan(a)).astype(np.int64) if a.dtype == np.float64 else np.ones(len(a), dtype=np.int64)))
+        else:
+            a = _np(v)
+            out.append(torch.from_numpy(a * a))
+    return out

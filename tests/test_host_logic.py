@@ -390,3 +390,33 @@ def test_as_index_false_returns_the_keys_as_columns(md, method, by):
     got = got.sort_values([(b, "") for b in by]).reset_index(drop=True)
     assert list(got.columns) == list(exp.columns)
     pd.testing.assert_frame_equal(got, exp.reset_index(drop=True), rtol=1e-9, atol=0, check_exact=False)
+
+
+@pytest.mark.parametrize("method,sort", [("shuffle", False), ("tree", True)])
+def test_nearly_distinct_chunks_skip_the_map_side_fold(md, method, sort):
+    """a chunk that was grouped and came back with ~as many groups as rows makes the following chunks of that shape
+    hand their rows on as partials (row_partials) -- until a chunk's sample stops looking distinct (the first chunks of
+    a run are all sampled, later ones every 8th); the final frame is
+    the oracle's either way (NaN values and duplicate keys inside a chunk included)"""
+    from mars_b200 import executors
+
+    rng = np.random.default_rng(23)
+    n, chunk = 350_000, 70_000
+    raw = pd.DataFrame({"dkey": rng.integers(0, 40_000_000, n), "dv": rng.normal(3, 2, n)})
+    raw.loc[rng.integers(0, n, 2000), "dv"] = np.nan
+    raw.loc[[5, 70_007, 70_008, 279_999, 349_999], "dkey"] = 77
+    raw.loc[140_000:209_999, "dkey"] = rng.integers(0, 50, 70_000)    # chunk 2 is NOT distinct
+    raw["dkey"] = raw["dkey"].astype(np.int64)
+    funcs = ["sum", "mean", "count", "min", "max", "var"]
+    fake_kernels.calls.clear()
+    for learned in (executors._pt_streak, executors._group_ratio, executors._distinct_shapes):
+        learned.clear()                       # what earlier chunks of this shape taught the map stage (per process)
+    before = executors.passthrough_chunks
+    sess = md.new_session(default=False)
+    got = md.DataFrame(raw, chunk_size=chunk).to_gpu().groupby("dkey", sort=sort).agg(funcs, method=method) \
+        .execute(session=sess).fetch(session=sess)
+    exp = orc.run_groupby_agg(raw, ["dkey"], funcs, chunk, method=method, sort=sort)
+    assert_frames_match(got, exp, sort_index=not sort)
+    # chunk 0 is measured, 1 passes through, 2 fails its sample and is grouped, 3 is grouped (and measured) again, 4 passes
+    assert executors.passthrough_chunks - before == 2
+    assert fake_kernels.calls.count("row_partials") == 2
