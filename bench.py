@@ -416,10 +416,36 @@ def main_ours(args):
     ms_e2e, out_e2e = timed(host_frames, e2e_steps, 0)
     h2d_bytes = (_dev.h2d_bytes - h2d0) // e2e_steps   # bytes really copied per step (counted at the copy call)
     ms_page = None
+    e2e_variants = {}
     if world == 1:
         step(host_pageable)
         ms_page, _ = timed(host_pageable, 2, 0)
         ms_page /= 2
+        # the same pinned step with less of the narrow transfer encoding (device._to_device)
+        saved = _dev.NARROW, _dev.NARROW_FLOATS, _dev.NARROW_DEFER
+        for name, flags, note in (
+                ("all_deferred", (True, True, True), "int64 columns and integer-valued float64 columns cross PCIe narrow; "
+                 "the host pass runs in the background of the band's other uploads"),
+                ("all_sync", (True, True, False), "MGB_NARROW_DEFER=0: the host pass of a column completes before the next "
+                 "column is requested"),
+                ("ints_deferred", (True, False, True), "MGB_NARROW_FLOATS=0: only int64 columns cross PCIe narrow"),
+                ("ints_sync", (True, False, False), "MGB_NARROW_FLOATS=0 MGB_NARROW_DEFER=0"),
+                ("full_width", (False, False, False), "MGB_NARROW=0: every uploaded column crosses PCIe at 8 bytes per element")):
+            if flags == saved:
+                continue
+            _dev.NARROW, _dev.NARROW_FLOATS, _dev.NARROW_DEFER = flags
+            _dev._no_narrow.clear()
+            _dev._narrow_hint.clear()
+            try:
+                step(host_frames)
+                h2d0 = _dev.h2d_bytes
+                ms_v, _ = timed(host_frames, e2e_steps, 0)
+                e2e_variants[name] = {"value": rows_rank * e2e_steps / (ms_v * 1e-3), "ms_per_step": ms_v / e2e_steps,
+                                      "h2d_bytes_per_step": int((_dev.h2d_bytes - h2d0) // e2e_steps), "note": note}
+            finally:
+                _dev.NARROW, _dev.NARROW_FLOATS, _dev.NARROW_DEFER = saved
+                _dev._no_narrow.clear()
+                _dev._narrow_hint.clear()
     del host_pageable
 
     sampler = ClockSampler(local)
@@ -553,7 +579,16 @@ def main_ours(args):
             "config": workload_config(args, world),
             "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": int(h2d_bytes) * world,
                     "h2d_note": "columns are uploaded on first use: the int64 column that is only counted never crosses "
-                                "PCIe (chunk bytes in host memory: %d per step per GPU)" % (rows_rank * BYTES_PER_ROW),
+                                "PCIe (chunk bytes in host memory: %d per step per GPU)" % (rows_rank * BYTES_PER_ROW)
+                                + ("; int64 columns%s whose values fit 1 / 2 / 4 bytes (here: the two key columns%s) are "
+                                   "narrowed on the host inside the timed region (checked on every value: lossless or not "
+                                   "done), cross PCIe narrow and are restored to 8-byte columns in HBM"
+                                   % ((" and float64 columns holding integers", " and quantity") if _dev.NARROW_FLOATS
+                                      else ("", "")) if _dev.NARROW else ""),
+                    "transfer_encoding": {"narrow_ints": bool(_dev.NARROW), "narrow_integer_valued_floats":
+                                          bool(_dev.NARROW and _dev.NARROW_FLOATS),
+                                          "deferred": bool(_dev.NARROW and _dev.NARROW_DEFER),
+                                          "variants": e2e_variants or None},
                     "d2h_bytes_per_step": int(out.shape[0] * (out.shape[1] + len(BY)) * 8),
                     "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps, "host_memory": "pinned",
                     "pageable": None if ms_page is None else {"value": total_rows / (ms_page * 1e-3), "ms_per_step": ms_page,

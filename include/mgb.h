@@ -338,6 +338,23 @@ int mgb_copy_rows(void* dst, int64_t dst_offset, const void* src, int64_t n_rows
 int mgb_copy_segments(const void* const* src, void* const* dst, const int64_t* n_rows, int32_t n_segments,
                       void* stream);
 
+/* ---- the step before the path: DataFrameToGPU (mars/dataframe/base/to_gpu.py:28-35) of int64 columns ----------
+ * The reference hands the whole pandas chunk to cudf.DataFrame.from_pandas, 8 bytes per int64 element over PCIe.
+ * Here an int64 column whose values fit a narrower integer crosses the link narrow and is restored in HBM:
+ *   mgb_host_narrow_i64  HOST code: dst[i] = (intW_t)src[i] for width W = 1 / 2 / 4 bytes; *fits = 1 when every value
+ *                        survived the round trip (the encoding is lossless), 0 as soon as one does not (dst is then
+ *                        garbage and the caller uploads the 8-byte column).  No device work, no stream: callers run
+ *                        it from several threads on sub-ranges of a column, writing into pinned staging memory.
+ *   mgb_widen_i64        device: dst[i] = (int64_t)src[i] (sign-extending), src / dst device pointers aligned to
+ *                        16 bytes.  Every kernel of the path keeps reading 8-byte columns.                          */
+int mgb_host_narrow_i64(const int64_t* src, int64_t n, int32_t width, void* dst, int32_t* fits);
+int mgb_widen_i64(const void* src, int32_t width, int64_t n, int64_t* dst, void* stream);
+/* The same for float64 columns that hold integers (quantities, counts kept as floats): dst[i] = (intW_t)src[i], *fits = 1
+ * when every value is in range and converts back to the same BITS (fractions, -0.0, NaN and +-inf refuse);
+ * mgb_widen_f64: dst[i] = (double)src[i].                                                                          */
+int mgb_host_narrow_f64(const double* src, int64_t n, int32_t width, void* dst, int32_t* fits);
+int mgb_widen_f64(const void* src, int32_t width, int64_t n, double* dst, void* stream);
+
 /* ---- sort=True support: argsort of int64 key tuples (lexicographic, stable) and row gather ---------- */
 int mgb_argsort_keys(const int64_t* const* key_cols, int32_t n_keys, int64_t n_rows, int32_t* out_perm,
                      void* stream);

@@ -10,11 +10,11 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmarsgb.so")
-SOURCES = ["mgb_util.cu", "mgb_partition.cu", "mgb_split.cu", "mgb_agg.cu", "mgb_bucket.cu", "mgb_dense.cu", "mgb_mid.cu", "mgb_tiny.cu", "mgb_nccl.cu",
+SOURCES = ["mgb_util.cu", "mgb_partition.cu", "mgb_split.cu", "mgb_agg.cu", "mgb_bucket.cu", "mgb_dense.cu", "mgb_mid.cu", "mgb_tiny.cu", "mgb_nccl.cu", "mgb_pack.cu",
            "mgb_host.cu"]
 # (source, object suffix, extra defines): the dense kernels are instantiated in four units to compile in parallel
 VARIANTS = [("mgb_dense_inst.cu", f"_{nk}_{th}", [f"-DDN_NK={nk}", f"-DDN_TH={th}"]) for nk in (1, 2) for th in (256, 512)]
-HEADERS = ["mgb_common.cuh", "mgb_dense.cuh", "mgb_layout.cuh"]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith(".cuh"))
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

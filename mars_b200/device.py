@@ -9,6 +9,7 @@ the processor frees ctx entries (processor.py:276-282).
 """
 from __future__ import annotations
 
+import contextlib
 import os
 import weakref
 from typing import Any, List, Optional, Sequence
@@ -74,6 +75,9 @@ class _StagingRing:
     SLAB_BYTES = int(os.environ.get("MGB_STAGE_SLAB_MB", "8")) << 20
     SLABS = int(os.environ.get("MGB_STAGE_SLABS", "8"))
     THREADS = int(os.environ.get("MGB_STAGE_THREADS", "4"))
+    # host threads of the narrowing pass: the ranks of a node share its cores
+    NARROW_THREADS = int(os.environ.get("MGB_NARROW_THREADS", "0")) or max(
+        2, min(8, (os.cpu_count() or 8) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
 
     def __init__(self):
         self.slabs = None
@@ -88,6 +92,7 @@ class _StagingRing:
         self.views = [t.numpy() for t in self.slabs]
         self.events = [None] * self.SLABS
         self.pool = ThreadPoolExecutor(self.THREADS, thread_name_prefix="mgb-stage")
+        self.npool = ThreadPoolExecutor(self.NARROW_THREADS, thread_name_prefix="mgb-narrow")
 
     def upload(self, arr: np.ndarray, device) -> torch.Tensor:
         if self.slabs is None:
@@ -122,26 +127,251 @@ class _StagingRing:
         drain(0)
         return out
 
+    # ---- int64 columns whose values fit 1 / 2 / 4 bytes cross PCIe narrow (mgb_host_narrow_i64 / mgb_widen_i64)
+    def upload_narrow(self, arr: np.ndarray, device, width: int) -> Optional[torch.Tensor]:
+        """Worker threads rewrite slab-sized pieces of the int64 (or integer-valued float64) column as ``width``-byte
+        integers straight into the pinned slabs (every value checked: lossless or refused), the copy engine moves the
+        narrow bytes, one kernel restores the 8-byte column in HBM.  Works from pinned and pageable sources alike (the
+        host pass reads the source once and writes 1/8 .. 1/2 of it).  None when a value does not fit: nothing useful
+        was enqueued, the caller uploads the 8-byte column."""
+        import ctypes as C
+
+        from . import _lib
+
+        if self.slabs is None:
+            self._init()
+        lib = _lib.load()
+        n = int(arr.shape[0])
+        narrow = torch.empty(n * width, dtype=torch.uint8, device=device)
+        per = (self.SLAB_BYTES // width) & ~15                  # elements per slab
+        T = max(1, min(self.NARROW_THREADS, arr.nbytes >> 21))     # >= 2 MB of source per thread
+        src0 = arr.ctypes.data
+
+        is_float = arr.dtype == np.float64
+        host_narrow = lib.mgb_host_narrow_f64 if is_float else lib.mgb_host_narrow_i64
+
+        def job(a, b, dst):
+            fits = C.c_int32(0)
+            _lib.check(host_narrow(src0 + a * 8, b - a, width, dst, C.byref(fits)))
+            return fits.value
+
+        for a in range(0, n, per):
+            b = min(a + per, n)
+            si = self.next
+            self.next = (self.next + 1) % self.SLABS
+            ev = self.events[si]
+            if ev is not None:
+                ev.synchronize()                                # its previous H2D has read the slab
+            base = self.slabs[si].data_ptr()
+            cuts = [a + (b - a) * t // T for t in range(T + 1)]
+            futs = [self.npool.submit(job, cuts[t], cuts[t + 1], base + (cuts[t] - a) * width)
+                    for t in range(1, T) if cuts[t + 1] > cuts[t]]
+            ok = job(cuts[0], cuts[1], base)                    # the calling thread takes the first part
+            if not all([f.result() for f in futs]) or not ok:
+                return None
+            narrow[a * width:b * width].copy_(self.slabs[si].view(torch.uint8)[:(b - a) * width], non_blocking=True)
+            ev = ev or torch.cuda.Event()
+            ev.record()
+            self.events[si] = ev
+        out = torch.empty(n, dtype=torch.float64 if is_float else torch.int64, device=device)
+        widen = lib.mgb_widen_f64 if is_float else lib.mgb_widen_i64
+        _lib.check(widen(narrow.data_ptr(), width, n, out.data_ptr(), torch.cuda.current_stream(device).cuda_stream))
+        return out
+
+
+    def submit_narrow(self, arr: np.ndarray, device, width: int, label) -> Optional[torch.Tensor]:
+        """Deferred form of ``upload_narrow`` (inside ``deferred_uploads()``): ONE worker narrows the whole column
+        into a pinned buffer of its own while the caller goes on enqueueing the copies of the other columns; the
+        returned device column is filled when the block ends (``_flush_deferred``: narrow H2D + widen, or the 8-byte
+        copy if a value did not fit).  None when the pinned pool is exhausted (the caller narrows synchronously)."""
+        import ctypes as C
+
+        from . import _lib
+
+        if self.slabs is None:
+            self._init()
+        n = int(arr.shape[0])
+        buf = _pinned.acquire(n * width)
+        if buf is None:
+            return None
+        lib = _lib.load()
+        is_float = arr.dtype == np.float64
+        host_narrow = lib.mgb_host_narrow_f64 if is_float else lib.mgb_host_narrow_i64
+        src, dst = arr.ctypes.data, buf.data_ptr()
+
+        def job():
+            fits = C.c_int32(0)
+            _lib.check(host_narrow(src, n, width, dst, C.byref(fits)))
+            return fits.value
+
+        out = torch.empty(n, dtype=torch.float64 if is_float else torch.int64, device=device)
+        _deferred.append((self.npool.submit(job), buf, out, arr, width, label, device))
+        return out
+
+
+class _PinnedPool:
+    """Pinned buffers of the deferred narrowing pass, by power-of-two size class; a buffer returns with the event
+    behind its last H2D and is handed out again only after that event."""
+    CAP = int(os.environ.get("MGB_NARROW_PINNED_MB", "1024")) << 20
+
+    def __init__(self):
+        self.free = {}
+        self.total = 0
+
+    def acquire(self, nbytes: int) -> Optional[torch.Tensor]:
+        cls = max(1 << 20, 1 << (max(nbytes, 1) - 1).bit_length())
+        lst = self.free.get(cls)
+        if lst:
+            t, ev = lst.pop(0)
+            if ev is not None:
+                ev.synchronize()
+            return t
+        if self.total + cls > self.CAP:
+            return None
+        self.total += cls
+        return torch.empty(cls, dtype=torch.uint8).pin_memory()
+
+    def release(self, t: torch.Tensor, ev) -> None:
+        self.free.setdefault(int(t.numel()), []).append((t, ev))
+
+
+_pinned = _PinnedPool()
+_deferred = None              # pending (future, pinned buffer, device column, ...) inside deferred_uploads()
+
+
+@contextlib.contextmanager
+def deferred_uploads():
+    """Uploads requested inside the block may complete when it ends: columns that cross PCIe narrow are narrowed by
+    worker threads in the background while the caller enqueues the copies of the other columns.  ONLY for blocks that
+    collect columns (pointers) and launch nothing that reads them -- the consumer is enqueued after the block."""
+    global _deferred
+    if _deferred is not None or not (NARROW and NARROW_DEFER):      # nested: the outer block flushes
+        yield
+        return
+    _deferred = []
+    try:
+        yield
+    finally:
+        pend, _deferred = _deferred, None
+        _flush_deferred(pend)
+
+
+def _flush_deferred(pend) -> None:
+    global h2d_bytes, narrowed_columns, deferred_columns
+    from . import _lib
+
+    if not pend:
+        return
+    lib = _lib.load()
+    used, err = [], None
+    for fut, buf, out, arr, width, label, device in pend:
+        used.append(buf)
+        try:
+            fits = fut.result()
+        except Exception as e:  # noqa: BLE001  (every future is waited for: the workers read ``arr`` and write ``buf``)
+            err = err or e
+            continue
+        n = int(out.numel())
+        if fits:
+            narrow = torch.empty(n * width, dtype=torch.uint8, device=device)
+            narrow.copy_(buf[:n * width], non_blocking=True)
+            widen = lib.mgb_widen_f64 if out.dtype == torch.float64 else lib.mgb_widen_i64
+            _lib.check(widen(narrow.data_ptr(), width, n, out.data_ptr(), torch.cuda.current_stream(device).cuda_stream))
+            h2d_bytes += n * width
+            narrowed_columns += 1
+            deferred_columns += 1
+            if label is not None:
+                _narrow_hint[label] = width
+        else:
+            out.copy_(_host_tensor(arr), non_blocking=True)
+            h2d_bytes += n * 8
+            _narrow_failed(label, width)
+    ev = torch.cuda.Event()
+    ev.record()
+    for buf in used:
+        _pinned.release(buf, ev)
+    if err is not None:
+        raise err
+
 
 _staging = _StagingRing()
 STAGE_MIN_BYTES = 1 << 20     # smaller pageable columns go through the driver's own staging
+NARROW = os.environ.get("MGB_NARROW", "1") != "0"
+NARROW_MIN_BYTES = 4 << 20    # below this the host pass and its thread hand-off cost more than the PCIe bytes saved
+NARROW_FLOATS = os.environ.get("MGB_NARROW_FLOATS", "1") != "0"   # float64 columns that hold small integers, too
+NARROW_DEFER = os.environ.get("MGB_NARROW_DEFER", "1") != "0"     # band launches narrow in the background (deferred_uploads)
+_no_narrow: set = set()       # column labels whose values did not fit the width their sample suggested
+_narrow_hint: dict = {}       # column label -> width its last chunk crossed with (saves the sample of the next chunk)
+narrowed_columns = 0          # columns that crossed PCIe narrow (tests, bench records)
+deferred_columns = 0          # ... of which the host pass ran in the background of a band's other uploads
 
 
-def _to_device(arr: np.ndarray, device) -> torch.Tensor:
-    """H2D copy of one 8-byte column (pandas hands out read-only views; torch wants writable memory).  Pinned
-    memory is copied asynchronously as it is; pageable memory goes through the pinned staging ring."""
-    global h2d_bytes
-    h2d_bytes += arr.size * arr.itemsize
-    arr = np.ascontiguousarray(arr)
+def _narrow_width(arr: np.ndarray) -> int:
+    """bytes per element a strided sample of the int64 (or integer-valued float64) column needs (8: leave it alone);
+    the full column is checked by the narrowing pass itself"""
+    n = arr.shape[0]
+    s = np.concatenate([arr[:256], arr[::max(1, n // 256)]])       # a few cache lines: the column is cold
+    if arr.dtype == np.float64:
+        with np.errstate(invalid="ignore"):
+            if not bool(np.all(s == np.rint(s))) or not bool(np.all(np.abs(s) <= 2.0 ** 31)):   # fractions, NaN, inf
+                return 8
+    lo, hi = int(s.min()), int(s.max())
+    for width, bound in ((1, 1 << 7), (2, 1 << 15), (4, 1 << 31)):
+        if -bound <= lo and hi < bound:
+            return width
+    return 8
+
+
+def _narrow_failed(label, width) -> None:
+    """a value did not fit: with a width remembered from an earlier chunk the next chunk samples again, with a freshly
+    sampled width the label is not tried any more"""
+    if label is None:
+        return
+    if _narrow_hint.pop(label, None) != width:
+        _no_narrow.add(label)
+
+
+def _host_tensor(arr: np.ndarray) -> torch.Tensor:
     if not arr.flags.writeable:
-        # pandas hands out read-only views of the column; the copy below only reads, so re-flag the view
-        # instead of copying the chunk on the host
+        # pandas hands out read-only views of the column; the copy only reads, so re-flag the view instead of
+        # copying the chunk on the host
         try:
             arr = arr.view()
             arr.flags.writeable = True
         except ValueError:
             arr = arr.copy()
-    t = torch.from_numpy(arr)
+    return torch.from_numpy(arr)
+
+
+def _to_device(arr: np.ndarray, device, label=None) -> torch.Tensor:
+    """H2D copy of one 8-byte column (pandas hands out read-only views; torch wants writable memory).  Pinned
+    memory is copied asynchronously as it is; pageable memory goes through the pinned staging ring; int64 columns
+    (and float64 columns holding integers) whose values fit a narrower integer cross the link narrow and are restored
+    in HBM.  A label whose column did not pass is not tried again (most float columns: the sample already says no)."""
+    global h2d_bytes, narrowed_columns
+    arr = np.ascontiguousarray(arr)
+    on_gpu = getattr(device, "type", "cuda") == "cuda" and torch.cuda.is_available()
+    if (NARROW and on_gpu and (arr.dtype == np.int64 or (NARROW_FLOATS and arr.dtype == np.float64)) and arr.ndim == 1
+            and arr.nbytes >= NARROW_MIN_BYTES and label not in _no_narrow):
+        width = _narrow_hint.get(label) or _narrow_width(arr)
+        if width < 8:
+            if _deferred is not None:
+                out = _staging.submit_narrow(arr, device, width, label)
+                if out is not None:
+                    return out                        # accounted for when the block ends
+            out = _staging.upload_narrow(arr, device, width)
+            if out is not None:
+                h2d_bytes += arr.size * width
+                narrowed_columns += 1
+                if label is not None:
+                    _narrow_hint[label] = width
+                return out
+            _narrow_failed(label, width)
+        elif label is not None:
+            _no_narrow.add(label)
+    h2d_bytes += arr.size * arr.itemsize
+    t = _host_tensor(arr)
+    arr = t.numpy()
     if (arr.nbytes >= STAGE_MIN_BYTES and arr.dtype.itemsize == 8 and arr.ndim == 1 and getattr(device, "type", "cuda") == "cuda"
             and torch.cuda.is_available() and not t.is_pinned()):
         return _staging.upload(arr, device)
@@ -374,7 +604,7 @@ class DeviceFrame:
         i = self.columns.index(name)
         t = self._data[i]
         if isinstance(t, HostColumn):
-            t = self._data[i] = _to_device(t.array, self._home)
+            t = self._data[i] = _to_device(t.array, self._home, self.columns[i])
         if type(t) is DerivedColumn:
             raise KeyError(name)
         return t
@@ -402,7 +632,7 @@ class DeviceFrame:
             self._filter = None
             for i, t in enumerate(self._data):
                 if isinstance(t, HostColumn):
-                    self._data[i] = _to_device(t.array, self._home)
+                    self._data[i] = _to_device(t.array, self._home, self.columns[i])
             self._home = None
             n = self._n
             idx = list(self._index) if self._index is not None else (
@@ -465,7 +695,7 @@ class DeviceFrame:
         if self._home is not None:
             for i, t in enumerate(self._data):
                 if isinstance(t, HostColumn):
-                    self._data[i] = _to_device(t.array, self._home)
+                    self._data[i] = _to_device(t.array, self._home, self.columns[i])
             self._home = None
         for i, t in enumerate(self._data):
             if type(t) is DerivedColumn:
@@ -480,7 +710,7 @@ class DeviceFrame:
             self._apply_lazy()
         t = self._data[i]
         if isinstance(t, HostColumn):
-            t = self._data[i] = _to_device(t.array, self._home)
+            t = self._data[i] = _to_device(t.array, self._home, self.columns[i])
         elif type(t) is DerivedColumn:
             t = self._materialise_derived(i)
         elif self._pending is not None:
@@ -606,7 +836,7 @@ class DeviceFrame:
             else:
                 raise NotImplementedError(f"column {name!r} has dtype {arr.dtype}: the GPU groupby path handles "
                                           f"float64 and int64 columns")
-            data.append(HostColumn(arr) if lazy else _to_device(arr, device))
+            data.append(HostColumn(arr) if lazy else _to_device(arr, device, name))
             cols.append(name)
         index = None
         names: List[Any] = []

@@ -18,6 +18,7 @@ All arithmetic happens in libmarsgb.so (mars_b200.kernels); there is no CPU fall
 """
 from __future__ import annotations
 
+import contextlib
 import os
 from typing import Any, Dict, List, Optional, Sequence, Tuple
 
@@ -1134,8 +1135,9 @@ def _launch_band_fused(plan, sig, frames):
     per_slot: List[List[DeviceFrame]] = [[] for _ in plan.slots]
     for g0 in range(0, len(frames), B):
         group = frames[g0:g0 + B]
-        chunks = [([f.physical(b).data_ptr() for b in plan.by], [f.physical(c).data_ptr() for c in phys],
-                   f.physical_rows) for f in group]
+        with _device_mod.deferred_uploads():      # host columns: nothing reads them before the launch below
+            chunks = [([f.physical(b).data_ptr() for b in plan.by], [f.physical(c).data_ptr() for c in phys],
+                       f.physical_rows) for f in group]
         bi, bf, fc = _kernels.preagg_dense_batch_fused_async(chunks, plan.accs, dts, nk, dev, prog)
 
         def replay(group=group, plan=plan):
@@ -1174,17 +1176,22 @@ def _launch_band(plan, sig, frames):
         # not a shape the fused pre-path takes: the lazy parts are materialised by the column accessors below
     chunks = []
     ck = (tuple(plan.key_pos), tuple(plan.val_pos), count_only)
-    for f in frames:
-        hit = f._ptrs_cache
-        if hit is not None and hit[0] == ck:      # the column pointers of a resident chunk do not change
-            chunks.append(hit[1])
-            continue
-        kp = [f.col(i).data_ptr() for i in plan.key_pos]
-        vp = [None if j in count_only else f.col(i).data_ptr() for j, i in enumerate(plan.val_pos)]
-        ent = [kp, vp, len(f)]          # (a list: the batch wrapper appends its ctypes arrays for the next call)
-        if f._pending is None and f._src is None:
-            f._ptrs_cache = (ck, ent)
-        chunks.append(ent)
+    # chunks still in host memory: their uploads may complete when the loop ends (nothing reads the columns before the
+    # launch below) -- unless a column accessor has lazy parts to materialise, which launches kernels on them
+    defer = (any(f._home is not None for f in frames)
+             and not any(f.is_lazy or f._pending is not None for f in frames))
+    with _device_mod.deferred_uploads() if defer else contextlib.nullcontext():
+        for f in frames:
+            hit = f._ptrs_cache
+            if hit is not None and hit[0] == ck:      # the column pointers of a resident chunk do not change
+                chunks.append(hit[1])
+                continue
+            kp = [f.col(i).data_ptr() for i in plan.key_pos]
+            vp = [None if j in count_only else f.col(i).data_ptr() for j, i in enumerate(plan.val_pos)]
+            ent = [kp, vp, len(f)]          # (a list: the batch wrapper appends its ctypes arrays for the next call)
+            if f._pending is None and f._src is None:
+                f._ptrs_cache = (ck, ent)
+            chunks.append(ent)
     B = _kernels.dense_batch_max()
     dev = frames[0].device
     nk = len(plan.by)
