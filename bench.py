@@ -412,9 +412,10 @@ def main_ours(args):
 
     e2e_steps = max(1, min(args.steps, 3))
     step(host_frames)                                   # warm-up (allocator, plans)
-    h2d0 = _dev.h2d_bytes
+    h2d0, nar0, skip0 = _dev.h2d_bytes, _dev.narrowed_columns, _dev.skipped_columns
     ms_e2e, out_e2e = timed(host_frames, e2e_steps, 0)
     h2d_bytes = (_dev.h2d_bytes - h2d0) // e2e_steps   # bytes really copied per step (counted at the copy call)
+    e2e_narrowed = (_dev.narrowed_columns - nar0) / e2e_steps, (_dev.skipped_columns - skip0) / e2e_steps
     ms_page = None
     e2e_variants = {}
     if world == 1:
@@ -422,28 +423,33 @@ def main_ours(args):
         ms_page, _ = timed(host_pageable, 2, 0)
         ms_page /= 2
         # the same pinned step with less of the narrow transfer encoding (device._to_device)
-        saved = _dev.NARROW, _dev.NARROW_FLOATS, _dev.NARROW_DEFER
+        saved = _dev.NARROW, _dev.NARROW_FLOATS, _dev.NARROW_DEFER, _dev.NARROW_OPPORTUNISTIC
         for name, flags, note in (
-                ("all_deferred", (True, True, True), "int64 columns and integer-valued float64 columns cross PCIe narrow; "
-                 "the host pass runs in the background of the band's other uploads"),
-                ("all_sync", (True, True, False), "MGB_NARROW_DEFER=0: the host pass of a column completes before the next "
-                 "column is requested"),
-                ("ints_deferred", (True, False, True), "MGB_NARROW_FLOATS=0: only int64 columns cross PCIe narrow"),
-                ("ints_sync", (True, False, False), "MGB_NARROW_FLOATS=0 MGB_NARROW_DEFER=0"),
-                ("full_width", (False, False, False), "MGB_NARROW=0: every uploaded column crosses PCIe at 8 bytes per element")):
+                ("all_deferred", (True, True, True, True), "int64 columns and integer-valued float64 columns cross PCIe narrow; "
+                 "the host pass runs in the background of the band's other uploads; a pass that has not started when the "
+                 "copy engine runs dry is skipped (that column crosses at 8 bytes)"),
+                ("all_deferred_wait", (True, True, True, False), "MGB_NARROW_OPPORTUNISTIC=0: every host pass is waited for"),
+                ("all_sync", (True, True, False, False), "MGB_NARROW_DEFER=0: the host pass of a column completes before the "
+                 "next column is requested"),
+                ("ints_deferred", (True, False, True, True), "MGB_NARROW_FLOATS=0: only int64 columns cross PCIe narrow"),
+                ("ints_sync", (True, False, False, False), "MGB_NARROW_FLOATS=0 MGB_NARROW_DEFER=0"),
+                ("full_width", (False, False, False, False), "MGB_NARROW=0: every uploaded column crosses PCIe at 8 bytes per "
+                 "element")):
             if flags == saved:
                 continue
-            _dev.NARROW, _dev.NARROW_FLOATS, _dev.NARROW_DEFER = flags
+            _dev.NARROW, _dev.NARROW_FLOATS, _dev.NARROW_DEFER, _dev.NARROW_OPPORTUNISTIC = flags
             _dev._no_narrow.clear()
             _dev._narrow_hint.clear()
             try:
                 step(host_frames)
-                h2d0 = _dev.h2d_bytes
+                h2d0, nar0, skip0 = _dev.h2d_bytes, _dev.narrowed_columns, _dev.skipped_columns
                 ms_v, _ = timed(host_frames, e2e_steps, 0)
                 e2e_variants[name] = {"value": rows_rank * e2e_steps / (ms_v * 1e-3), "ms_per_step": ms_v / e2e_steps,
-                                      "h2d_bytes_per_step": int((_dev.h2d_bytes - h2d0) // e2e_steps), "note": note}
+                                      "h2d_bytes_per_step": int((_dev.h2d_bytes - h2d0) // e2e_steps),
+                                      "narrowed_columns_per_step": (_dev.narrowed_columns - nar0) / e2e_steps,
+                                      "skipped_columns_per_step": (_dev.skipped_columns - skip0) / e2e_steps, "note": note}
             finally:
-                _dev.NARROW, _dev.NARROW_FLOATS, _dev.NARROW_DEFER = saved
+                _dev.NARROW, _dev.NARROW_FLOATS, _dev.NARROW_DEFER, _dev.NARROW_OPPORTUNISTIC = saved
                 _dev._no_narrow.clear()
                 _dev._narrow_hint.clear()
     del host_pageable
@@ -588,6 +594,8 @@ def main_ours(args):
                     "transfer_encoding": {"narrow_ints": bool(_dev.NARROW), "narrow_integer_valued_floats":
                                           bool(_dev.NARROW and _dev.NARROW_FLOATS),
                                           "deferred": bool(_dev.NARROW and _dev.NARROW_DEFER),
+                                          "narrowed_columns_per_step": e2e_narrowed[0],
+                                          "skipped_columns_per_step": e2e_narrowed[1],
                                           "variants": e2e_variants or None},
                     "d2h_bytes_per_step": int(out.shape[0] * (out.shape[1] + len(BY)) * 8),
                     "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps, "host_memory": "pinned",

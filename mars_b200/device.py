@@ -94,12 +94,13 @@ class _StagingRing:
         self.pool = ThreadPoolExecutor(self.THREADS, thread_name_prefix="mgb-stage")
         self.npool = ThreadPoolExecutor(self.NARROW_THREADS, thread_name_prefix="mgb-narrow")
 
-    def upload(self, arr: np.ndarray, device) -> torch.Tensor:
+    def upload(self, arr: np.ndarray, device, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         if self.slabs is None:
             self._init()
         n = arr.shape[0]
         src = arr.view(np.int64)
-        out = torch.empty(n, dtype=torch.float64 if arr.dtype == np.float64 else torch.int64, device=device)
+        if out is None:
+            out = torch.empty(n, dtype=torch.float64 if arr.dtype == np.float64 else torch.int64, device=device)
         out_i = out.view(torch.int64)
         per = self.SLAB_BYTES // 8
         pending = []          # (future, slab index, start, end) in submission order
@@ -256,8 +257,24 @@ def deferred_uploads():
         _flush_deferred(pend)
 
 
+def _upload_into(out: torch.Tensor, arr: np.ndarray, device) -> None:
+    """the 8-byte column into an existing device column (pinned: one asynchronous copy; pageable: the slab ring)"""
+    t = _host_tensor(arr)
+    if arr.nbytes >= STAGE_MIN_BYTES and not t.is_pinned():
+        _staging.upload(t.numpy(), device, out=out)
+    else:
+        out.copy_(t, non_blocking=True)
+
+
 def _flush_deferred(pend) -> None:
-    global h2d_bytes, narrowed_columns, deferred_columns
+    """End of a deferred block: per column, in submission order, the narrow copy + widen kernel -- or the 8-byte copy
+    when a value did not fit.  The copy engine must not wait for the host: when the stream has run dry and a column's
+    pass has not even started (``NARROW_OPPORTUNISTIC``), the job is cancelled and the column crosses at full width,
+    so the share of narrow columns follows what the host cores and its memory can keep up with (8 ranks of a node
+    share them)."""
+    global h2d_bytes, narrowed_columns, deferred_columns, skipped_columns
+    import concurrent.futures as cf
+
     from . import _lib
 
     if not pend:
@@ -266,13 +283,24 @@ def _flush_deferred(pend) -> None:
     used, err = [], None
     for fut, buf, out, arr, width, label, device in pend:
         used.append(buf)
+        n = int(out.numel())
+        fits = None
         try:
-            fits = fut.result()
+            while True:
+                try:
+                    fits = fut.result(timeout=None if not NARROW_OPPORTUNISTIC else 2e-4)
+                    break
+                except cf.TimeoutError:
+                    if torch.cuda.current_stream(device).query() and fut.cancel():
+                        break
         except Exception as e:  # noqa: BLE001  (every future is waited for: the workers read ``arr`` and write ``buf``)
             err = err or e
             continue
-        n = int(out.numel())
-        if fits:
+        if fits is None:                      # cancelled before it started
+            _upload_into(out, arr, device)
+            h2d_bytes += n * 8
+            skipped_columns += 1
+        elif fits:
             narrow = torch.empty(n * width, dtype=torch.uint8, device=device)
             narrow.copy_(buf[:n * width], non_blocking=True)
             widen = lib.mgb_widen_f64 if out.dtype == torch.float64 else lib.mgb_widen_i64
@@ -283,7 +311,7 @@ def _flush_deferred(pend) -> None:
             if label is not None:
                 _narrow_hint[label] = width
         else:
-            out.copy_(_host_tensor(arr), non_blocking=True)
+            _upload_into(out, arr, device)
             h2d_bytes += n * 8
             _narrow_failed(label, width)
     ev = torch.cuda.Event()
@@ -300,10 +328,12 @@ NARROW = os.environ.get("MGB_NARROW", "1") != "0"
 NARROW_MIN_BYTES = 4 << 20    # below this the host pass and its thread hand-off cost more than the PCIe bytes saved
 NARROW_FLOATS = os.environ.get("MGB_NARROW_FLOATS", "1") != "0"   # float64 columns that hold small integers, too
 NARROW_DEFER = os.environ.get("MGB_NARROW_DEFER", "1") != "0"     # band launches narrow in the background (deferred_uploads)
+NARROW_OPPORTUNISTIC = os.environ.get("MGB_NARROW_OPPORTUNISTIC", "1") != "0"   # never let the copy engine wait for a host pass
 _no_narrow: set = set()       # column labels whose values did not fit the width their sample suggested
 _narrow_hint: dict = {}       # column label -> width its last chunk crossed with (saves the sample of the next chunk)
 narrowed_columns = 0          # columns that crossed PCIe narrow (tests, bench records)
 deferred_columns = 0          # ... of which the host pass ran in the background of a band's other uploads
+skipped_columns = 0           # columns sent at full width because their host pass had not started when PCIe ran dry
 
 
 def _narrow_width(arr: np.ndarray) -> int:

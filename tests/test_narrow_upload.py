@@ -104,6 +104,7 @@ class _HostStandIn:
     def __init__(self, lib):
         self._lib = lib
         self.widened = 0
+        self.stream_idle = False
 
     def __getattr__(self, name):
         return getattr(self._lib, name)
@@ -136,6 +137,9 @@ def host_device(monkeypatch, lib):
 
     class Stream:
         cuda_stream = 0
+
+        def query(self):
+            return stand_in.stream_idle
 
     stand_in = _HostStandIn(lib)
     monkeypatch.setattr(_lib, "_lib", stand_in)
@@ -205,6 +209,39 @@ def test_deferred_block_hints_and_refusals(host_device):
     assert "small" not in device._narrow_hint and "small" not in device._no_narrow
     np.testing.assert_array_equal(device._to_device(wide, "cpu", "small").numpy(), wide)
     assert "small" in device._no_narrow                                  # a freshly sampled width that fails: not again
+
+
+def test_copy_engine_never_waits_for_a_host_pass_that_has_not_started(host_device, monkeypatch):
+    import threading
+    from concurrent.futures import ThreadPoolExecutor
+    from mars_b200 import device
+
+    n = 200_000
+    rng = np.random.default_rng(4)
+    cols = [rng.integers(0, 100, n) for _ in range(3)]
+    device._staging._init()
+    pool = ThreadPoolExecutor(1)
+    monkeypatch.setattr(device._staging, "npool", pool)
+    gate = threading.Event()
+    pool.submit(gate.wait)                                 # the only worker is busy: the passes below cannot start
+    before, skipped = device.narrowed_columns, device.skipped_columns
+    host_device.stream_idle = True                         # ... and the stream has nothing left to do
+    try:
+        with device.deferred_uploads():
+            outs = [device._to_device(a, "cpu", "busy") for a in cols]
+    finally:
+        gate.set()
+    for o, a in zip(outs, cols):
+        np.testing.assert_array_equal(o.numpy(), a)
+    assert device.skipped_columns - skipped == 3 and device.narrowed_columns == before
+    assert "busy" not in device._no_narrow and "busy" not in device._narrow_hint      # not a refusal
+    host_device.stream_idle = False                        # copies in flight: the passes are waited for
+    with device.deferred_uploads():
+        outs = [device._to_device(a, "cpu", "busy") for a in cols]
+    for o, a in zip(outs, cols):
+        np.testing.assert_array_equal(o.numpy(), a)
+    assert device.narrowed_columns - before == 3 and device.skipped_columns - skipped == 3
+    pool.shutdown()
 
 
 @pytest.mark.gpu
@@ -280,7 +317,7 @@ def test_host_chunks_with_narrow_keys_match_the_oracle(cuda_device, monkeypatch,
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("defer", [True, False])
+@pytest.mark.parametrize("defer", [True, False, "opportunistic"])
 def test_band_launch_narrows_in_the_background(cuda_device, monkeypatch, defer):
     """low-cardinality band: the batch launch collects the columns of all host chunks first, so the narrowing of the
     key columns runs in worker threads while the other columns are enqueued (device.deferred_uploads); a column with a
@@ -290,7 +327,8 @@ def test_band_launch_narrows_in_the_background(cuda_device, monkeypatch, defer):
     from mars_b200 import device
 
     monkeypatch.setattr(device, "NARROW_MIN_BYTES", 1 << 20)
-    monkeypatch.setattr(device, "NARROW_DEFER", defer)
+    monkeypatch.setattr(device, "NARROW_DEFER", bool(defer))
+    monkeypatch.setattr(device, "NARROW_OPPORTUNISTIC", defer == "opportunistic")
     for learned in (device._no_narrow, device._narrow_hint):
         learned.clear()
     rng = np.random.default_rng(11)
@@ -301,7 +339,7 @@ def test_band_launch_narrows_in_the_background(cuda_device, monkeypatch, defer):
     raw.loc[2 * chunk + 1000, "bunits"] = np.nan           # chunk 2: not sampled, found by the pass over the column
     raw.loc[chunk:, "bgrow"] += 1000                       # chunk 0 fits one byte, the later ones need two
     funcs = {"bqty": ["sum", "mean"], "bprice": ["sum", "mean"], "bunits": ["sum", "count"], "bgrow": ["sum", "count"]}
-    before, dbefore = device.narrowed_columns, device.deferred_columns
+    before, dbefore, sbefore = device.narrowed_columns, device.deferred_columns, device.skipped_columns
     sess = md.new_session(default=False)
     got = md.DataFrame(raw, chunk_size=chunk).to_gpu().groupby(["bflag", "bstat"]).agg(funcs, method="tree") \
         .execute(session=sess).fetch(session=sess)
@@ -309,6 +347,10 @@ def test_band_launch_narrows_in_the_background(cuda_device, monkeypatch, defer):
     assert_frames_match(got, exp, sort_index=False)
     # bflag, bstat, bqty: 4 chunks each; bunits: chunks 0, 1, 3 (chunk 2 is refused by the pass, the label stays);
     # bgrow: every chunk is sampled when the block collects them all, else chunk 1 is refused with chunk 0's width
-    assert device.narrowed_columns - before == 12 + 3 + (4 if defer else 3)
+    if defer == "opportunistic":      # small chunks: the copies finish early, passes that have not started are skipped
+        # 20 columns are candidates; the one with the NaN is refused if its pass ran, skipped if it did not
+        assert device.narrowed_columns - before + device.skipped_columns - sbefore in (19, 20)
+        return
+    assert device.narrowed_columns - before == 12 + 3 + (4 if defer else 3) and device.skipped_columns == sbefore
     assert (device.deferred_columns - dbefore > 0) == defer
     assert "bprice" in device._no_narrow and device._narrow_hint.get("bgrow") == 2
