@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import contextlib
 import os
+import threading
 import weakref
 from typing import Any, List, Optional, Sequence
 
@@ -206,7 +207,7 @@ class _StagingRing:
             return fits.value
 
         out = torch.empty(n, dtype=torch.float64 if is_float else torch.int64, device=device)
-        _deferred.append((self.npool.submit(job), buf, out, arr, width, label, device))
+        _tls.pending.append((self.npool.submit(job), buf, out, arr, width, label, device))
         return out
 
 
@@ -218,26 +219,32 @@ class _PinnedPool:
     def __init__(self):
         self.free = {}
         self.total = 0
+        self.lock = threading.Lock()
 
     def acquire(self, nbytes: int) -> Optional[torch.Tensor]:
         cls = max(1 << 20, 1 << (max(nbytes, 1) - 1).bit_length())
-        lst = self.free.get(cls)
-        if lst:
-            t, ev = lst.pop(0)
-            if ev is not None:
-                ev.synchronize()
-            return t
-        if self.total + cls > self.CAP:
-            return None
-        self.total += cls
-        return torch.empty(cls, dtype=torch.uint8).pin_memory()
+        with self.lock:
+            lst = self.free.get(cls)
+            hit = lst.pop(0) if lst else None
+            if hit is None:
+                if self.total + cls > self.CAP:
+                    return None
+                self.total += cls
+        if hit is None:
+            return torch.empty(cls, dtype=torch.uint8).pin_memory()
+        t, ev = hit
+        if ev is not None:
+            ev.synchronize()
+        return t
 
     def release(self, t: torch.Tensor, ev) -> None:
-        self.free.setdefault(int(t.numel()), []).append((t, ev))
+        with self.lock:
+            self.free.setdefault(int(t.numel()), []).append((t, ev))
 
 
 _pinned = _PinnedPool()
-_deferred = None              # pending (future, pinned buffer, device column, ...) inside deferred_uploads()
+_tls = threading.local()      # .pending: (future, pinned buffer, device column, ...) of the deferred_uploads() block this
+                              # thread is in -- another thread's uploads must not land in it (its consumer would not wait)
 
 
 @contextlib.contextmanager
@@ -245,15 +252,14 @@ def deferred_uploads():
     """Uploads requested inside the block may complete when it ends: columns that cross PCIe narrow are narrowed by
     worker threads in the background while the caller enqueues the copies of the other columns.  ONLY for blocks that
     collect columns (pointers) and launch nothing that reads them -- the consumer is enqueued after the block."""
-    global _deferred
-    if _deferred is not None or not (NARROW and NARROW_DEFER):      # nested: the outer block flushes
+    if getattr(_tls, "pending", None) is not None or not (NARROW and NARROW_DEFER):      # nested: the outer block flushes
         yield
         return
-    _deferred = []
+    _tls.pending = []
     try:
         yield
     finally:
-        pend, _deferred = _deferred, None
+        pend, _tls.pending = _tls.pending, None
         _flush_deferred(pend)
 
 
@@ -385,7 +391,7 @@ def _to_device(arr: np.ndarray, device, label=None) -> torch.Tensor:
             and arr.nbytes >= NARROW_MIN_BYTES and label not in _no_narrow):
         width = _narrow_hint.get(label) or _narrow_width(arr)
         if width < 8:
-            if _deferred is not None:
+            if getattr(_tls, "pending", None) is not None:
                 out = _staging.submit_narrow(arr, device, width, label)
                 if out is not None:
                     return out                        # accounted for when the block ends

@@ -211,6 +211,26 @@ def test_deferred_block_hints_and_refusals(host_device):
     assert "small" in device._no_narrow                                  # a freshly sampled width that fails: not again
 
 
+def test_deferred_block_belongs_to_its_thread(host_device):
+    import threading
+    from mars_b200 import device
+
+    n = 200_000
+    a = np.random.default_rng(8).integers(0, 100, n)
+    got = {}
+    before = device.narrowed_columns
+    with device.deferred_uploads():
+        mine = device._to_device(a, "cpu", "mine")
+        t = threading.Thread(target=lambda: got.setdefault("out", device._to_device(a, "cpu", "theirs")))
+        t.start()
+        t.join()
+        # the other thread's column is complete when its call returns (its consumer does not know about this block)
+        np.testing.assert_array_equal(got["out"].numpy(), a)
+        assert device.narrowed_columns == before + 1
+    np.testing.assert_array_equal(mine.numpy(), a)
+    assert device.narrowed_columns == before + 2
+
+
 def test_copy_engine_never_waits_for_a_host_pass_that_has_not_started(host_device, monkeypatch):
     import threading
     from concurrent.futures import ThreadPoolExecutor
