@@ -66,6 +66,13 @@ FILTER_OPS = {"<=": 0, "<": 1, ">=": 2, ">": 3, "==": 4, "!=": 5}
 _lazy_kernels = None
 
 
+def _usable_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))         # what nproc reports (the container's share), not the machine's cores
+    except (AttributeError, OSError):
+        return os.cpu_count() or 8
+
+
 class _StagingRing:
     """Pinned staging for uploads from PAGEABLE host memory (what a Mars chunk store hands over: pandas blocks).
     cudaMemcpy from pageable memory is staged by the driver on one thread (~10 GB/s measured); here worker threads copy
@@ -78,7 +85,7 @@ class _StagingRing:
     THREADS = int(os.environ.get("MGB_STAGE_THREADS", "4"))
     # host threads of the narrowing pass: the ranks of a node share its cores
     NARROW_THREADS = int(os.environ.get("MGB_NARROW_THREADS", "0")) or max(
-        2, min(8, (os.cpu_count() or 8) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
+        2, min(8, _usable_cores() // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))))
 
     def __init__(self):
         self.slabs = None
