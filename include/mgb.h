@@ -353,6 +353,9 @@ int mgb_widen_i64(const void* src, int32_t width, int64_t n, int64_t* dst, void*
  * when every value is in range and converts back to the same BITS (fractions, -0.0, NaN and +-inf refuse);
  * mgb_widen_f64: dst[i] = (double)src[i].                                                                          */
 int mgb_host_narrow_f64(const double* src, int64_t n, int32_t width, void* dst, int32_t* fits);
+/* Which bodies the two host passes run: returns 2 (AVX2, picked at run time when the CPU has it) or 1 (SSE2 / scalar);
+ * force_baseline != 0 pins the fallback bodies (tests compare the two), 0 restores the choice.                       */
+int mgb_host_narrow_isa(int32_t force_baseline);
 int mgb_widen_f64(const void* src, int32_t width, int64_t n, double* dst, void* stream);
 
 /* ---- sort=True support: argsort of int64 key tuples (lexicographic, stable) and row gather ---------- */

@@ -10,7 +10,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmarsgb.so")
-SOURCES = ["mgb_util.cu", "mgb_partition.cu", "mgb_split.cu", "mgb_agg.cu", "mgb_bucket.cu", "mgb_dense.cu", "mgb_mid.cu", "mgb_tiny.cu", "mgb_nccl.cu", "mgb_pack.cu",
+SOURCES = ["mgb_util.cu", "mgb_partition.cu", "mgb_split.cu", "mgb_agg.cu", "mgb_bucket.cu", "mgb_dense.cu", "mgb_mid.cu", "mgb_tiny.cu", "mgb_nccl.cu", "mgb_pack.cu", "mgb_hostpack.cpp",
            "mgb_host.cu"]
 # (source, object suffix, extra defines): the dense kernels are instantiated in four units to compile in parallel
 VARIANTS = [("mgb_dense_inst.cu", f"_{nk}_{th}", [f"-DDN_NK={nk}", f"-DDN_TH={th}"]) for nk in (1, 2) for th in (256, 512)]
@@ -47,7 +47,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(job):
         src, suffix, defines = job
-        obj = os.path.join(objdir, src.replace(".cu", suffix + ".o"))
+        obj = os.path.join(objdir, os.path.splitext(src)[0] + suffix + ".o")
         cmd = [nvcc, *NVCC_FLAGS, *defines, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             print(" ".join(cmd), file=sys.stderr)

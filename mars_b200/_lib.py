@@ -121,6 +121,7 @@ SIGNATURES = {
     "mgb_widen_i64": (C.c_int, [_vp, _i32, _i64, _vp, _vp]),
     "mgb_host_narrow_f64": (C.c_int, [_vp, _i64, _i32, _vp, C.POINTER(_i32)]),
     "mgb_widen_f64": (C.c_int, [_vp, _i32, _i64, _vp, _vp]),
+    "mgb_host_narrow_isa": (C.c_int, [_i32]),
     "mgb_post_mean": (C.c_int, [_vp, _i32, _vp, _vp, _i64, _vp]),
     "mgb_post_var": (C.c_int, [_vp, _vp, _i32, _vp, _i32, _vp, _i64, _vp]),
     "mgb_copy_rows": (C.c_int, [_vp, _i64, _vp, _i64, _vp]),

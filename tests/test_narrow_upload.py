@@ -28,27 +28,37 @@ def _narrow(lib, src, width):
     return fits.value, dst
 
 
+@pytest.fixture(params=["avx2-if-present", "baseline"])
+def isa(request, lib):
+    """both bodies of the host pass: the ones picked at run time, and the SSE2 / scalar fallback"""
+    got = lib.mgb_host_narrow_isa(1 if request.param == "baseline" else 0)
+    assert got == 1 if request.param == "baseline" else got in (1, 2)
+    yield got
+    lib.mgb_host_narrow_isa(0)
+
+
 @pytest.mark.parametrize("width", [1, 2, 4])
-def test_host_narrowing_is_lossless_or_refused(lib, width):
+def test_host_narrowing_is_lossless_or_refused(lib, isa, width):
     # host code of the library: no device is touched
     info = np.iinfo(WIDTHS[width])
     rng = np.random.default_rng(width)
-    for n in (0, 1, 7, 4095, 4096, 4097, 100_003):
+    for n in (0, 1, 7, 15, 16, 17, 33, 4095, 4096, 4097, 100_003):
         src = rng.integers(info.min, info.max + 1, n, dtype=np.int64)
         if n > 2:
             src[0], src[-1] = info.min, info.max
         fits, dst = _narrow(lib, src, width)
         assert fits == 1
         np.testing.assert_array_equal(dst.astype(np.int64), src)
-    for bad in (info.max + 1, info.min - 1, np.iinfo(np.int64).max, np.iinfo(np.int64).min, 1 << 32, -(1 << 32) + 5):
-        for pos in (0, 4095, 4096, 99_999):
+    for bad in (info.max + 1, info.min - 1, np.iinfo(np.int64).max, np.iinfo(np.int64).min, 1 << 32, -(1 << 32) + 5,
+                (1 << 32) + 3, (1 << 40) | 7, -(1 << 63) + 1):
+        for pos in (0, 3, 4095, 4096, 4100, 99_990, 99_999):
             src = rng.integers(0, 3, 100_000, dtype=np.int64)
             src[pos] = bad
             assert _narrow(lib, src, width)[0] == 0, (bad, pos)
 
 
 @pytest.mark.parametrize("width", [1, 2, 4])
-def test_host_narrowing_of_integer_valued_floats(lib, width):
+def test_host_narrowing_of_integer_valued_floats(lib, isa, width):
     info = np.iinfo(WIDTHS[width])
     rng = np.random.default_rng(10 + width)
 
@@ -58,7 +68,7 @@ def test_host_narrowing_of_integer_valued_floats(lib, width):
         assert lib.mgb_host_narrow_f64(src.ctypes.data, len(src), width, dst.ctypes.data, C.byref(fits)) == 0
         return fits.value, dst
 
-    for n in (0, 1, 4097, 100_003):
+    for n in (0, 1, 7, 8, 15, 16, 17, 33, 4097, 100_003):
         src = rng.integers(info.min, info.max + 1, n).astype(np.float64)
         if n > 2:
             src[0], src[-1] = info.min, info.max
@@ -67,7 +77,7 @@ def test_host_narrowing_of_integer_valued_floats(lib, width):
         back = dst.astype(np.float64)
         np.testing.assert_array_equal(back.view(np.int64), src.view(np.int64))      # the same bits
     for bad in (0.5, -0.0, np.nan, np.inf, -np.inf, float(info.max) + 1, float(info.min) - 1, 1e300, 5e-324, 3.0000000000000004):
-        for pos in (0, 4096, 9_999):
+        for pos in (0, 5, 4096, 4111, 9_990, 9_999):
             src = rng.integers(0, 50, 10_000).astype(np.float64)
             src[pos] = bad
             assert narrow(src)[0] == 0, (bad, pos)
